@@ -1,0 +1,175 @@
+/*
+ * nazb.h — C ABI of libnazb.so: B200-native draw-batched normalizing-flow evaluation.
+ *
+ * This is the drop-in boundary for ONE path of AnaryaRay1/naz: `log_prob` / `sample` of its discrete
+ * flows (masked-affine-autoregressive "maf", neural-spline-autoregressive "nsa") evaluated for S weight
+ * draws x N points.  The reference has no FFI of its own (it is 100 % Python) — the
+ * interface it exposes for this path is a set of Python methods.  Each entry point below names the
+ * reference code it replaces (paths relative to the reference tree):
+ *
+ *   nazb_create / nazb_destroy   NormalizingFlow.__init__ + flow_makers        src/naz/flows/flow.py:21-42
+ *                                masked_affine_autoregressive                  src/naz/flows/transforms.py:133-160
+ *                                neural_spline_autoregressive                  src/naz/flows/transforms.py:165-198
+ *   nazb_pack                    set_params (per-draw in-place weight swap)    src/naz/trainers/train_flows.py:47-71
+ *                                torch_to_jax (weights/masks/perm export)      src/naz/flows/bflow_jax_maf.py:26-46
+ *                                masked_linear's `W * mask` (re-done per call) src/naz/flows/bflow_jax_maf.py:74-77
+ *                                dropout conditioners (per-draw keep masks)    src/naz/flows/transforms.py:29-65
+ *   nazb_inverse                 NormalizingFlow.log_prob                      src/naz/flows/flow.py:45-79
+ *                                make_normalizing_flow(...)["lp"]              src/naz/flows/bflow_jax_maf.py:210-212
+ *                                inverse_fn (D-pass autoregressive inverse)    src/naz/flows/bflow_jax_maf.py:181-194
+ *                                the per-draw lp loops                         examples/papers/2506.05657/compute_bic_simpler.py:116-120
+ *   nazb_forward                 NormalizingFlow.sample                        src/naz/flows/flow.py:94-129
+ *                                make_normalizing_flow(...)["sampler"]         src/naz/flows/bflow_jax_maf.py:214-223
+ *                                predict (loop over posterior draws)           src/naz/trainers/train_flows.py:384-422
+ *                                MCDPNormalizingFlow.sample_uncertain          src/naz/flows/mcdpflow.py:39-56
+ *   nazb_lse_reduce/_finish      mean_s exp(lp_s) posterior predictive         examples/papers/2506.05657/plot.py:272-275
+ *   nazb_importance              Importance(...).run + posterior.ESS()         src/naz/trainers/train_flows.py:358-380
+ *                                compute_bic (max_s sum_n lp)                  src/naz/flows/bflow_jax_maf.py:474-475
+ *
+ * Conventions
+ *   - Every data pointer is a DEVICE pointer owned by the caller (e.g. torch.Tensor.data_ptr()),
+ *     contiguous row-major fp32 unless stated.  Pointer *tables* (W, b, mask) and `perm`, `hid_deg`
+ *     are HOST arrays.  The library owns only the handle (packed weights + workspace).
+ *   - All work is enqueued on `stream` (a cudaStream_t passed as void*); no hidden synchronisation
+ *     except inside nazb_create / nazb_destroy.
+ *   - Return value: 0 on success, negative nazb_status otherwise; nazb_strerror() explains; the last
+ *     CUDA error string is kept per handle (nazb_last_cuda_error).
+ *   - Base noise is always an INPUT (RNG stays with the caller; parity needs identical noise).
+ *   - One handle per device; a handle is not thread-safe, distinct handles are.
+ *   - There is no CPU fallback anywhere in this library.
+ */
+#ifndef NAZB_H_
+#define NAZB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NAZB_MAX_HIDDEN_LAYERS 8
+#define NAZB_MAX_DIM 32
+
+typedef enum {
+  NAZB_OK = 0,
+  NAZB_ERR_BAD_ARG = -1,       /* null pointer / non-positive size / inconsistent shapes            */
+  NAZB_ERR_UNSUPPORTED = -2,   /* configuration outside what any engine supports                      */
+  NAZB_ERR_CUDA = -3,          /* a CUDA runtime call failed; see nazb_last_cuda_error()              */
+  NAZB_ERR_NOT_PACKED = -4,    /* nazb_forward / nazb_inverse before nazb_pack                        */
+  NAZB_ERR_NO_DEVICE = -5      /* no CUDA device / wrong architecture (needs sm_100)                  */
+} nazb_status;
+
+typedef enum {
+  NAZB_KIND_AFFINE = 0,        /* pyro AffineAutoregressive: y = mu + x*exp(clip(s)), M = 2           */
+  NAZB_KIND_RQS = 1,           /* SplineAutoregressive order="quadratic" (naz default), M = 3K-1      */
+  NAZB_KIND_RLS = 2            /* SplineAutoregressive order="linear", M = 4K-1                       */
+} nazb_kind;
+
+typedef enum {
+  NAZB_ENGINE_AUTO = 0,        /* tcgen05 when the shape fits its envelope, else SIMT                 */
+  NAZB_ENGINE_SIMT = 1,        /* fp32 CUDA-core kernels, any shape                                   */
+  NAZB_ENGINE_TCGEN05 = 2      /* fp16 hi/lo-split tensor-core kernels (error if shape unsupported)   */
+} nazb_engine;
+
+typedef enum {
+  NAZB_INV_INCREMENTAL = 0,    /* one block-triangular pass per flow layer (needs hid_deg)            */
+  NAZB_INV_JACOBI = 1          /* the reference's D full conditioner passes per flow layer            */
+} nazb_inverse_mode;
+
+typedef struct nazb_handle nazb_handle;
+
+/* Static description of the flow; mirrors the positional arguments of naz's factories
+ * (theta_dim, condition_dim, hidden_dim, num_layers[, count_bins]) — transforms.py:133,165. */
+typedef struct nazb_desc {
+  int32_t kind;                               /* nazb_kind                                            */
+  int32_t D;                                  /* theta_dim, 1..NAZB_MAX_DIM                           */
+  int32_t C;                                  /* condition_dim, 0 = unconditional                     */
+  int32_t L;                                  /* num_layers (flow layers)                             */
+  int32_t n_hidden;                           /* len(hidden_dims), 1..NAZB_MAX_HIDDEN_LAYERS          */
+  int32_t hidden[NAZB_MAX_HIDDEN_LAYERS];     /* hidden_dims                                          */
+  int32_t count_bins;                         /* K (splines), ignored for affine                      */
+  float bound;                                /* spline box half-width B (pyro default 3.0)           */
+  float clip_lo, clip_hi;                     /* affine log-scale clamp (pyro default -5, 3)          */
+  int32_t S;                                  /* number of weight draws this handle holds (S_local)   */
+  int32_t engine;                             /* nazb_engine                                          */
+  int32_t inverse_mode;                       /* nazb_inverse_mode                                    */
+  int32_t device;                             /* CUDA device ordinal                                  */
+} nazb_desc;
+
+int nazb_create(nazb_handle** out, const nazb_desc* desc);
+void nazb_destroy(nazb_handle* h);
+
+/* Which engine the handle resolved to (nazb_engine), or a negative status. */
+int nazb_engine_in_use(const nazb_handle* h);
+
+/* Fold masks (and optional per-draw dropout keep-masks) into the packed, engine-specific weight
+ * image for all S draws.  n_lin = n_hidden + 1 linears per flow layer, tables indexed [l*n_lin + j].
+ *   W[i]         device, [S][out][in] with draw stride w_draw_stride[i] floats (0 = one shared set)
+ *   b[i]         device, [S][out]     with draw stride b_draw_stride[i] floats (0 = shared)
+ *   mask[i]      device, [out][in] fp32 0/1 (arn.masks as exported by torch_to_jax)
+ *   perm         host int64 [L][D] (arn.permutation)
+ *   hid_deg      host int32 [n_hidden][max(hidden)] MADE degrees of the hidden units (non-decreasing
+ *                per layer); required for NAZB_INV_INCREMENTAL, may be NULL for NAZB_INV_JACOBI
+ *   keep         device [S][L][n_hidden][max(hidden)] 0/1 or NULL; unit j of hidden layer k of flow
+ *                layer l in draw s is multiplied by keep/(1-p_drop) (transforms.py:38-43), folded into
+ *                the NEXT linear's packed columns
+ */
+int nazb_pack(nazb_handle* h, const float* const* W, const float* const* b,
+              const int64_t* w_draw_stride, const int64_t* b_draw_stride,
+              const float* const* mask, const int64_t* perm, const int32_t* hid_deg,
+              const float* keep, float p_drop, void* stream);
+
+/* Reference `log_prob` direction (autoregressive inverse) for draws [s_begin, s_begin + s_count).
+ *   x        [N][D] points (shared by all draws)
+ *   ctx      [ctx_rows][C]; ctx_rows == N (per point) or 1 (broadcast); NULL iff C == 0
+ *   lo, hi   [D] bounding box (flow.py:70-73) or both NULL
+ *   z        out [s_count][N][D] base-space points, or NULL
+ *   lp       out [s_count][N] log p(x_n | theta_s), or NULL
+ *   log_w    [s_count] per-draw log-weights added before the cross-draw logsumexp, or NULL (= 0)
+ *   lse_max, lse_sum   out [n_groups][N] running (max, sum exp) partials over the draws of each
+ *                      group (draw s belongs to group s % n_groups), or both NULL
+ *   sum_n    out [s_count] double, sum over points of lp (must be zeroed by the caller), or NULL
+ */
+int nazb_inverse(nazb_handle* h, int32_t s_begin, int32_t s_count,
+                 const float* x, const float* ctx, int32_t ctx_rows, int32_t N,
+                 const float* lo, const float* hi,
+                 float* z, float* lp, const float* log_w,
+                 float* lse_max, float* lse_sum, int32_t n_groups,
+                 double* sum_n, void* stream);
+
+/* Reference `sample` direction (one conditioner pass per flow layer).
+ *   z        base noise, [s_count][N][D] (z_shared == 0) or [N][D] shared by all draws (z_shared != 0)
+ *   x        out [s_count][N][D] samples (inverse bounding applied when lo/hi given)
+ *   logdet   out [s_count][N] sum of forward log|det J| over flow layers, or NULL
+ */
+int nazb_forward(nazb_handle* h, int32_t s_begin, int32_t s_count,
+                 const float* z, int32_t z_shared, const float* ctx, int32_t ctx_rows, int32_t N,
+                 const float* lo, const float* hi,
+                 float* x, float* logdet, void* stream);
+
+/* Stand-alone cross-draw reduction over a materialised lp[S][N] (kernel group 4):
+ * partial (max, sum exp) per point over this rank's draws.  HBM-bound: 4*S*N bytes read. */
+int nazb_lse_reduce(const float* lp, int32_t S, int32_t N, const float* log_w,
+                    float* lse_max, float* lse_sum, void* stream);
+
+/* Combine G partials (from draw groups and/or ranks): out[n] = log sum_g sum_g[n] exp(max_g[n]) + log_norm. */
+int nazb_lse_finish(const float* lse_max, const float* lse_sum, int32_t G, int32_t N,
+                    float log_norm, float* out, void* stream);
+
+/* Importance weights: log_w[s] = log_prior[s] + sum_n[s] - log_q[s]; log_evidence = lse(log_w) - log S;
+ * ess = exp(2 lse(log_w) - lse(2 log_w)); max_sum = max_s sum_n[s] (BIC).  log_prior / log_q may be NULL.
+ * out3 is a device double[3] = {log_evidence, ess, max_sum}; log_w_out device double[S] or NULL. */
+int nazb_importance(const double* sum_n, const float* log_prior, const float* log_q, int32_t S,
+                    double* log_w_out, double* out3, void* stream);
+
+const char* nazb_strerror(int status);
+const char* nazb_last_cuda_error(const nazb_handle* h);
+
+/* Introspection used by bench.py / tests: bytes of packed weights held, kernels launched so far. */
+int64_t nazb_packed_bytes(const nazb_handle* h);
+int64_t nazb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NAZB_H_ */

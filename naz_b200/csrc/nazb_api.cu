@@ -1,0 +1,250 @@
+// C-ABI glue of libnazb.so (see include/nazb.h for the contract and the reference mapping).
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include "nazb_internal.h"
+
+static std::atomic<long long> g_launches{0};
+void nazb_count_launch(int n) { g_launches += n; }
+extern "C" int64_t nazb_launch_count(void) { return g_launches.load(); }
+
+#define CK(h, call)                                    \
+  do {                                                 \
+    cudaError_t e_ = (call);                           \
+    if (e_ != cudaSuccess) {                           \
+      if (h) (h)->cuda_err = cudaGetErrorString(e_);   \
+      return NAZB_ERR_CUDA;                            \
+    }                                                  \
+  } while (0)
+
+extern "C" const char* nazb_strerror(int status) {
+  switch (status) {
+    case NAZB_OK: return "ok";
+    case NAZB_ERR_BAD_ARG: return "bad argument (null pointer, non-positive size or inconsistent shape)";
+    case NAZB_ERR_UNSUPPORTED: return "configuration not supported by the selected engine";
+    case NAZB_ERR_CUDA: return "CUDA runtime error (see nazb_last_cuda_error)";
+    case NAZB_ERR_NOT_PACKED: return "nazb_pack has not been called on this handle";
+    case NAZB_ERR_NO_DEVICE: return "no usable CUDA device (libnazb needs an sm_100 GPU)";
+    default: return "unknown nazb status";
+  }
+}
+
+extern "C" const char* nazb_last_cuda_error(const nazb_handle* h) { return h ? h->cuda_err.c_str() : ""; }
+
+static int round4(int v) { return (v + 3) & ~3; }
+
+static int build_geom(const nazb_desc& d, FlowGeom& g) {
+  memset(&g, 0, sizeof(g));
+  if (d.kind < NAZB_KIND_AFFINE || d.kind > NAZB_KIND_RLS) return NAZB_ERR_BAD_ARG;
+  if (d.D < 1 || d.D > NAZB_MAX_DIM || d.C < 0 || d.L < 1 || d.n_hidden < 1 || d.n_hidden > NAZB_MAX_HIDDEN_LAYERS ||
+      d.S < 1)
+    return NAZB_ERR_BAD_ARG;
+  g.kind = d.kind; g.D = d.D; g.C = d.C; g.L = d.L; g.n_hidden = d.n_hidden;
+  g.K = d.count_bins;
+  if (d.kind == NAZB_KIND_AFFINE) g.M = 2;
+  else {
+    if (d.count_bins < 2 || d.count_bins > 64 || !(d.bound > 0.f)) return NAZB_ERR_BAD_ARG;
+    g.M = (d.kind == NAZB_KIND_RQS) ? 3 * d.count_bins - 1 : 4 * d.count_bins - 1;
+  }
+  g.bound = d.bound; g.clip_lo = d.clip_lo; g.clip_hi = d.clip_hi;
+  g.kin = d.C + d.D;
+  g.md = g.M * d.D;
+  g.hmax = 0;
+  for (int j = 0; j < d.n_hidden; ++j) {
+    if (d.hidden[j] < d.D) return NAZB_ERR_BAD_ARG;   // pyro raises for hidden < input_dim
+    g.hidden[j] = d.hidden[j];
+    g.hmax = g.hmax > round4(d.hidden[j]) ? g.hmax : round4(d.hidden[j]);
+  }
+  long long off = 0;
+  const int n_lin = d.n_hidden + 1;
+  for (int j = 0; j < n_lin; ++j) {
+    g.kdim[j] = (j == 0) ? g.kin : d.hidden[j - 1];
+    g.ndim[j] = (j == n_lin - 1) ? g.md : d.hidden[j];
+    g.ldw[j] = round4(g.ndim[j]);
+    g.off_w[j] = off;
+    off += (long long)g.kdim[j] * g.ldw[j];
+    g.off_b[j] = off;
+    off += g.ldw[j];
+  }
+  g.layer_stride = off;            // multiple of 4 floats by construction
+  g.draw_stride = off * d.L;
+  g.inv_mode = d.inverse_mode;
+  return NAZB_OK;
+}
+
+extern "C" int nazb_create(nazb_handle** out, const nazb_desc* desc) {
+  if (!out || !desc) return NAZB_ERR_BAD_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return NAZB_ERR_NO_DEVICE;
+  if (desc->device < 0 || desc->device >= ndev) return NAZB_ERR_BAD_ARG;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, desc->device) != cudaSuccess) return NAZB_ERR_NO_DEVICE;
+  if (prop.major != 10) return NAZB_ERR_NO_DEVICE;   // sm_100a cubins only; no fallback
+  nazb_handle* h = new (std::nothrow) nazb_handle();
+  if (!h) return NAZB_ERR_BAD_ARG;
+  h->desc = *desc;
+  h->device = desc->device;
+  h->sm_count = prop.multiProcessorCount;
+  int rc = build_geom(*desc, h->geom);
+  if (rc != NAZB_OK) { delete h; return rc; }
+  if (desc->inverse_mode != NAZB_INV_INCREMENTAL && desc->inverse_mode != NAZB_INV_JACOBI) { delete h; return NAZB_ERR_BAD_ARG; }
+  // engine resolution
+  std::string why;
+  bool tc_ok = nazb_tc_supported(h->geom, &why);
+  if (desc->engine == NAZB_ENGINE_TCGEN05 && !tc_ok) { delete h; return NAZB_ERR_UNSUPPORTED; }
+  if (desc->engine == NAZB_ENGINE_AUTO) h->engine = tc_ok ? NAZB_ENGINE_TCGEN05 : NAZB_ENGINE_SIMT;
+  else if (desc->engine == NAZB_ENGINE_SIMT || desc->engine == NAZB_ENGINE_TCGEN05) h->engine = desc->engine;
+  else { delete h; return NAZB_ERR_BAD_ARG; }
+  if (const char* env = getenv("NAZB_FORCE_ENGINE")) {
+    if (!strcmp(env, "simt")) h->engine = NAZB_ENGINE_SIMT;
+    if (!strcmp(env, "tcgen05") && tc_ok) h->engine = NAZB_ENGINE_TCGEN05;
+  }
+  if (h->engine == NAZB_ENGINE_SIMT && nazb_simt_pick_P(h->geom) == 0) { delete h; return NAZB_ERR_UNSUPPORTED; }
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e == cudaSuccess) e = cudaMalloc(&h->perm_dev, sizeof(int) * 2 * (size_t)desc->L * desc->D);
+  if (e == cudaSuccess && h->engine == NAZB_ENGINE_SIMT)
+    e = cudaMalloc(&h->packed, sizeof(float) * (size_t)desc->S * h->geom.draw_stride);
+  if (e == cudaSuccess && h->engine == NAZB_ENGINE_TCGEN05) e = nazb_tc_create(h);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "nazb_create: %s\n", cudaGetErrorString(e));
+    nazb_destroy(h);
+    return NAZB_ERR_CUDA;
+  }
+  *out = h;
+  return NAZB_OK;
+}
+
+extern "C" void nazb_destroy(nazb_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->tc) nazb_tc_destroy(h);
+  if (h->packed) cudaFree(h->packed);
+  if (h->perm_dev) cudaFree(h->perm_dev);
+  delete h;
+}
+
+extern "C" int nazb_engine_in_use(const nazb_handle* h) { return h ? h->engine : NAZB_ERR_BAD_ARG; }
+
+extern "C" int64_t nazb_packed_bytes(const nazb_handle* h) {
+  if (!h) return 0;
+  if (h->engine == NAZB_ENGINE_TCGEN05) return nazb_tc_packed_bytes(h);
+  return (int64_t)h->desc.S * h->geom.draw_stride * (int64_t)sizeof(float);
+}
+
+extern "C" int nazb_pack(nazb_handle* h, const float* const* W, const float* const* b, const int64_t* wst,
+                         const int64_t* bst, const float* const* mask, const int64_t* perm, const int32_t* hid_deg,
+                         const float* keep, float p_drop, void* stream) {
+  if (!h || !W || !b || !wst || !bst || !mask || !perm) return NAZB_ERR_BAD_ARG;
+  if (keep && !(p_drop >= 0.f && p_drop < 1.f)) return NAZB_ERR_BAD_ARG;
+  FlowGeom& g = h->geom;
+  const int n_lin = g.n_hidden + 1;
+  for (int i = 0; i < g.L * n_lin; ++i)
+    if (!W[i] || !b[i] || !mask[i]) return NAZB_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(h, cudaSetDevice(h->device));
+  // perm + rank tables
+  std::vector<int> pr(2 * (size_t)g.L * g.D);
+  for (int l = 0; l < g.L; ++l) {
+    std::vector<char> seen(g.D, 0);
+    for (int r = 0; r < g.D; ++r) {
+      long long d = perm[(size_t)l * g.D + r];
+      if (d < 0 || d >= g.D || seen[d]) return NAZB_ERR_BAD_ARG;
+      seen[d] = 1;
+      pr[(size_t)l * g.D + r] = (int)d;
+      pr[(size_t)g.L * g.D + (size_t)l * g.D + d] = r;
+    }
+  }
+  // the tables are tiny; a synchronous copy keeps the host vector's lifetime trivial
+  CK(h, cudaMemcpy(h->perm_dev, pr.data(), pr.size() * sizeof(int), cudaMemcpyHostToDevice));
+  // inverse schedule from the MADE degrees
+  if (g.inv_mode == NAZB_INV_INCREMENTAL) {
+    if (!hid_deg) return NAZB_ERR_BAD_ARG;
+    int hk = 0;
+    for (int j = 0; j < g.n_hidden; ++j) hk = hk > g.hidden[j] ? hk : g.hidden[j];
+    for (int j = 0; j < g.n_hidden; ++j) {
+      const int32_t* dg = hid_deg + (size_t)j * hk;
+      for (int u = 0; u < g.hidden[j]; ++u) {
+        if (dg[u] < 0 || dg[u] >= g.D) return NAZB_ERR_BAD_ARG;
+        if (u > 0 && dg[u] < dg[u - 1]) return NAZB_ERR_UNSUPPORTED;   // needs degree-sorted units
+      }
+      for (int r = 0; r <= g.D; ++r) {
+        int cnt = 0;
+        while (cnt < g.hidden[j] && dg[cnt] < r) ++cnt;
+        g.blk[j][r] = (short)cnt;
+      }
+    }
+  }
+  cudaError_t e;
+  if (h->engine == NAZB_ENGINE_TCGEN05) e = nazb_tc_pack(h, W, b, wst, bst, mask, keep, p_drop, st);
+  else e = nazb_pack_simt(h, W, b, wst, bst, mask, keep, p_drop, st);
+  CK(h, e);
+  h->is_packed = true;
+  return NAZB_OK;
+}
+
+static int check_io(const nazb_handle* h, int s_begin, int s_count, const void* x, const float* ctx, int ctx_rows,
+                    int N, const float* lo, const float* hi) {
+  if (!h || !x) return NAZB_ERR_BAD_ARG;
+  if (!h->is_packed) return NAZB_ERR_NOT_PACKED;
+  if (N <= 0 || s_count <= 0 || s_begin < 0 || s_begin + s_count > h->desc.S) return NAZB_ERR_BAD_ARG;
+  if ((h->geom.C > 0) != (ctx != nullptr)) return NAZB_ERR_BAD_ARG;   // flow.py:75 asserts condition is given
+  if (ctx && ctx_rows != 1 && ctx_rows != N) return NAZB_ERR_BAD_ARG;
+  if ((lo == nullptr) != (hi == nullptr)) return NAZB_ERR_BAD_ARG;
+  return NAZB_OK;
+}
+
+static int pick_groups(const nazb_handle* h, int N, int s_count, int requested) {
+  if (requested > 0) return requested < s_count ? requested : s_count;
+  // enough CTAs for >= 4 waves if the draw axis allows it
+  int P = 64;
+  long long tiles = (N + P - 1) / P;
+  long long want = 4LL * h->sm_count * 2;
+  long long gq = (want + tiles - 1) / tiles;
+  if (gq < 1) gq = 1;
+  if (gq > s_count) gq = s_count;
+  if (gq > 65535) gq = 65535;
+  return (int)gq;
+}
+
+extern "C" int nazb_inverse(nazb_handle* h, int32_t s_begin, int32_t s_count, const float* x, const float* ctx,
+                            int32_t ctx_rows, int32_t N, const float* lo, const float* hi, float* z, float* lp,
+                            const float* log_w, float* lse_max, float* lse_sum, int32_t n_groups, double* sum_n,
+                            void* stream) {
+  int rc = check_io(h, s_begin, s_count, x, ctx, ctx_rows, N, lo, hi);
+  if (rc != NAZB_OK) return rc;
+  if ((lse_max == nullptr) != (lse_sum == nullptr)) return NAZB_ERR_BAD_ARG;
+  if (lse_max && (n_groups < 1 || n_groups > s_count || n_groups > 65535)) return NAZB_ERR_BAD_ARG;
+  if (!z && !lp && !lse_max && !sum_n) return NAZB_ERR_BAD_ARG;
+  CK(h, cudaSetDevice(h->device));
+  IoArgs io{};
+  io.x = x; io.x_draw_stride = 0; io.ctx = ctx; io.ctx_rows = ctx_rows; io.N = N;
+  io.s_begin = s_begin; io.s_count = s_count; io.lo = lo; io.hi = hi;
+  io.out_x = z; io.out_l = lp; io.log_w = log_w; io.lse_max = lse_max; io.lse_sum = lse_sum; io.sum_n = sum_n;
+  io.dir = 0;
+  int G = pick_groups(h, N, s_count, lse_max ? n_groups : 0);
+  cudaError_t e = (h->engine == NAZB_ENGINE_TCGEN05) ? nazb_tc_launch(h, io, G, (cudaStream_t)stream)
+                                                      : nazb_simt_launch(h, io, G, (cudaStream_t)stream);
+  CK(h, e);
+  return NAZB_OK;
+}
+
+extern "C" int nazb_forward(nazb_handle* h, int32_t s_begin, int32_t s_count, const float* z, int32_t z_shared,
+                            const float* ctx, int32_t ctx_rows, int32_t N, const float* lo, const float* hi, float* x,
+                            float* logdet, void* stream) {
+  int rc = check_io(h, s_begin, s_count, z, ctx, ctx_rows, N, lo, hi);
+  if (rc != NAZB_OK) return rc;
+  if (!x) return NAZB_ERR_BAD_ARG;
+  CK(h, cudaSetDevice(h->device));
+  IoArgs io{};
+  io.x = z; io.x_draw_stride = z_shared ? 0 : (long long)N * h->geom.D; io.ctx = ctx; io.ctx_rows = ctx_rows; io.N = N;
+  io.s_begin = s_begin; io.s_count = s_count; io.lo = lo; io.hi = hi;
+  io.out_x = x; io.out_l = logdet; io.dir = 1;
+  int G = pick_groups(h, N, s_count, 0);
+  cudaError_t e = (h->engine == NAZB_ENGINE_TCGEN05) ? nazb_tc_launch(h, io, G, (cudaStream_t)stream)
+                                                      : nazb_simt_launch(h, io, G, (cudaStream_t)stream);
+  CK(h, e);
+  return NAZB_OK;
+}

@@ -1,0 +1,85 @@
+// Internal structures shared by the kernels and the C-ABI glue of libnazb.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/nazb.h"
+
+#define NAZB_MAX_LIN (NAZB_MAX_HIDDEN_LAYERS + 1)
+
+// Geometry + schedule of one flow; passed BY VALUE to kernels (fits the 4 KB parameter space).
+struct FlowGeom {
+  int kind, D, C, L, n_hidden, M, K;
+  float bound, clip_lo, clip_hi;
+  int kin;                      // C + D
+  int hidden[NAZB_MAX_HIDDEN_LAYERS];
+  int hmax;                     // max hidden width rounded up to 4
+  int md;                       // M * D (output width)
+  // SIMT packed layout: per draw, per flow layer, linear j is Wt[kdim[j]][ldw[j]] (k-major rows,
+  // mask folded, output columns rank-major: col = rank(d)*M + m) followed by bias[ldw[j]].
+  int kdim[NAZB_MAX_LIN];
+  int ndim[NAZB_MAX_LIN];
+  int ldw[NAZB_MAX_LIN];
+  long long off_w[NAZB_MAX_LIN], off_b[NAZB_MAX_LIN];
+  long long layer_stride, draw_stride;   // floats
+  // Inverse schedule. Stage r (0..D-1) finalises the dimension of rank r.
+  //   incremental: hidden layer j computes units [blk[j][r], blk[j][r+1]) from the first
+  //                blk[j-1][r+1] units of the previous layer; output columns [r*M, (r+1)*M).
+  //   jacobi:      every stage recomputes everything (the reference's D full passes).
+  int inv_mode;
+  short blk[NAZB_MAX_HIDDEN_LAYERS][NAZB_MAX_DIM + 1];
+};
+
+struct IoArgs {
+  const float* x;          // inverse: points [N][D]; forward: base noise [S][N][D] or [N][D]
+  long long x_draw_stride; // floats between draws of x (0 = shared)
+  const float* ctx;        // [ctx_rows][C] or null
+  int ctx_rows;
+  int N;
+  int s_begin, s_count;
+  const float* lo;         // [D] or null
+  const float* hi;
+  float* out_x;            // [s_count][N][D] or null
+  float* out_l;            // inverse: lp [s_count][N]; forward: logdet [s_count][N]; or null
+  const float* log_w;      // [s_count] or null
+  float* lse_max;          // [G][N] or null
+  float* lse_sum;
+  double* sum_n;           // [s_count] or null
+  int dir;                 // 0 = inverse (log_prob direction), 1 = forward (sample direction)
+};
+
+struct nazb_handle {
+  nazb_desc desc;
+  FlowGeom geom;
+  int engine;               // resolved engine
+  int device;
+  int sm_count;
+  float* packed = nullptr;  // SIMT image
+  int* perm_dev = nullptr;  // [L][D] int32
+  bool is_packed = false;
+  std::string cuda_err;
+  // tcgen05 engine state (opaque here; defined in flow_tc.cu)
+  void* tc = nullptr;
+};
+
+// ---- launchers implemented in the .cu files ----
+cudaError_t nazb_simt_launch(const nazb_handle* h, const IoArgs& io, int n_groups, cudaStream_t st);
+size_t nazb_simt_smem_bytes(const FlowGeom& g, int P);
+int nazb_simt_pick_P(const FlowGeom& g);
+
+cudaError_t nazb_pack_simt(nazb_handle* h, const float* const* W, const float* const* b,
+                           const int64_t* wst, const int64_t* bst, const float* const* mask,
+                           const float* keep, float p_drop, cudaStream_t st);
+
+// tcgen05 engine
+bool nazb_tc_supported(const FlowGeom& g, std::string* why);
+cudaError_t nazb_tc_create(nazb_handle* h);
+void nazb_tc_destroy(nazb_handle* h);
+cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* const* b,
+                         const int64_t* wst, const int64_t* bst, const float* const* mask,
+                         const float* keep, float p_drop, cudaStream_t st);
+cudaError_t nazb_tc_launch(const nazb_handle* h, const IoArgs& io, int n_groups, cudaStream_t st);
+int64_t nazb_tc_packed_bytes(const nazb_handle* h);
+
+void nazb_count_launch(int n = 1);

@@ -1,0 +1,142 @@
+// Elementwise transform math shared by the SIMT and tcgen05 engines.
+// Arithmetic follows pyro's `_monotonic_rational_spline` / AffineAutoregressive as restated in
+// oracle/flow_oracle.py; operation order mirrors the oracle so the
+// fp32 results track the reference's own fp32 path.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace nazb {
+
+#define NAZB_LOG_2PI 1.8378770664093453f
+
+__device__ __forceinline__ float softplus_f(float a) {
+  // torch.nn.functional.softplus (beta = 1, threshold = 20)
+  return a > 20.f ? a : log1pf(expf(a));
+}
+__device__ __forceinline__ float sigmoid_f(float a) { return 1.f / (1.f + expf(-a)); }
+
+// Monotone rational spline on [-B, B] for ONE (point, dim).
+//   raw(m): conditioner output slot m for this dim; slots [0,K) widths, [K,2K) heights,
+//           [2K,3K-1) derivatives, [3K-1,4K-1) lambdas (linear order only).
+//   setw(m, v): scratch write-back (the same storage as raw) used to keep exp() values.
+// Returns the transformed value and the FORWARD log|dy/dx| at the solution (for the inverse this is
+// what pyro caches: ConditionedSpline._inverse stores the negated inverse log-det).
+template <bool LINEAR, class Raw, class SetW>
+__device__ __forceinline__ void rational_spline(float in, int K, float B, bool inverse, Raw raw, SetW setw,
+                                                float& out, float& ld_fwd) {
+  const float min_w = 1e-3f, min_h = 1e-3f, min_d = 1e-3f, min_lam = 0.025f, eps = 1e-6f;
+  if (!(in >= -B && in <= B)) {   // identity outside the box (NaN also lands here, like the oracle's where())
+    out = in;
+    ld_fwd = 0.f;
+    return;
+  }
+  // softmax of widths and heights: exp(v - max) kept in scratch, normalised on the fly
+  float mw = -INFINITY, mh = -INFINITY;
+  for (int j = 0; j < K; ++j) {
+    mw = fmaxf(mw, raw(j));
+    mh = fmaxf(mh, raw(K + j));
+  }
+  float sw = 0.f, sh = 0.f;
+  for (int j = 0; j < K; ++j) {
+    float ew = expf(raw(j) - mw), eh = expf(raw(K + j) - mh);
+    setw(j, ew);
+    setw(K + j, eh);
+    sw += ew;
+    sh += eh;
+  }
+  const float scale_w = 1.f - min_w * K, scale_h = 1.f - min_h * K;
+  // walk the knots: cumsum -> [-B,B] -> forced end points; select the bin on the fly
+  float cw = 0.f, ch = 0.f;                 // running cumsum of (min + scale * softmax)
+  float kx0 = -B, ky0 = -B;                 // left knot of the current bin
+  float sel_w = 0.f, sel_h = 0.f, sel_x = -B, sel_y = -B;
+  int sel = 0;
+  for (int j = 0; j < K; ++j) {
+    float wj = min_w + scale_w * (raw(j) / sw);
+    float hj = min_h + scale_h * (raw(K + j) / sh);
+    cw += wj;
+    ch += hj;
+    float kx1 = (j == K - 1) ? B : (2.f * B) * cw + (-B);
+    float ky1 = (j == K - 1) ? B : (2.f * B) * ch + (-B);
+    float ks = inverse ? ky0 : kx0;
+    if (j == 0 || in >= ks + eps) {
+      sel = j;
+      sel_w = kx1 - kx0;
+      sel_h = ky1 - ky0;
+      sel_x = kx0;
+      sel_y = ky0;
+    }
+    kx0 = kx1;
+    ky0 = ky1;
+  }
+  const float d_edge = 1.f - min_d;
+  float d0 = (sel == 0) ? d_edge : min_d + softplus_f(raw(2 * K + sel - 1));
+  float d1 = (sel == K - 1) ? d_edge : min_d + softplus_f(raw(2 * K + sel));
+  float delta = sel_h / sel_w;
+  if (!LINEAR) {
+    if (inverse) {
+      float dy = in - sel_y;
+      float t2 = d0 + d1 - 2.f * delta;
+      float a = dy * t2 + sel_h * (delta - d0);
+      float b = sel_h * d0 - dy * t2;
+      float c = -delta * dy;
+      float disc = b * b - 4.f * a * c;
+      float root = (2.f * c) / (-b - sqrtf(disc));
+      out = root * sel_w + sel_x;
+      float tomt = root * (1.f - root);
+      float den = delta + t2 * tomt;
+      float omr = 1.f - root;
+      float dnum = delta * delta * (d1 * root * root + 2.f * delta * tomt + d0 * omr * omr);
+      ld_fwd = logf(dnum) - 2.f * logf(den);
+    } else {
+      float theta = (in - sel_x) / sel_w;
+      float tomt = theta * (1.f - theta);
+      float t2 = d0 + d1 - 2.f * delta;
+      float num = sel_h * (delta * theta * theta + d0 * tomt);
+      float den = delta + t2 * tomt;
+      out = sel_y + num / den;
+      float omt = 1.f - theta;
+      float dnum = delta * delta * (d1 * theta * theta + 2.f * delta * tomt + d0 * omt * omt);
+      ld_fwd = logf(dnum) - 2.f * logf(den);
+    }
+  } else {
+    float lam = (1.f - 2.f * min_lam) * sigmoid_f(raw(3 * K - 1 + sel)) + min_lam;
+    float wa = 1.f;
+    float wb = sqrtf(d0 / d1) * wa;
+    float wc = (lam * wa * d0 + (1.f - lam) * wb * d1) / delta;
+    float ya = sel_y, yb = sel_h + sel_y;
+    float yc = ((1.f - lam) * wa * ya + lam * wb * yb) / ((1.f - lam) * wa + lam * wb);
+    if (inverse) {
+      bool le = in <= yc;
+      float numerator = le ? (lam * wa * (ya - in)) : ((wc - lam * wb) * in + lam * wb * yb - wc * yc);
+      float denominator = le ? ((wc - wa) * in + wa * ya - wc * yc) : ((wc - wb) * in + wb * yb - wc * yc);
+      float theta = numerator / denominator;
+      out = theta * sel_w + sel_x;
+      float dnum = (le ? wa * wc * lam * (yc - ya) : wb * wc * (1.f - lam) * (yb - yc)) * sel_w;
+      // inverse log-det; the forward one is its negation
+      ld_fwd = -(logf(dnum) - 2.f * logf(fabsf(denominator)));
+    } else {
+      float theta = (in - sel_x) / sel_w;
+      bool le = theta <= lam;
+      float numerator = le ? (wa * ya * (lam - theta) + wc * yc * theta)
+                           : (wc * yc * (1.f - theta) + wb * yb * (theta - lam));
+      float denominator = le ? (wa * (lam - theta) + wc * theta) : (wc * (1.f - theta) + wb * (theta - lam));
+      out = numerator / denominator;
+      float dnum = (le ? wa * wc * lam * (yc - ya) : wb * wc * (1.f - lam) * (yb - yc)) / sel_w;
+      ld_fwd = logf(dnum) - 2.f * logf(fabsf(denominator));
+    }
+  }
+}
+
+// Logit bounding transform of one coordinate (transforms.py:20-23): returns y, adds to log_jac.
+__device__ __forceinline__ float bound_fwd(float x, float lo, float hi, float& log_jac) {
+  float u = (x - lo) / (hi - lo);
+  float lu = logf(u), l1u = log1pf(-u);
+  log_jac -= (lu + l1u) + logf(hi - lo);
+  return lu - l1u;
+}
+__device__ __forceinline__ float bound_inv(float y, float lo, float hi) {
+  return sigmoid_f(y) * (hi - lo) + lo;
+}
+
+}  // namespace nazb

@@ -1,0 +1,47 @@
+"""Shared builders for the parity tests (oracle = checker; naz_b200 = the thing checked)."""
+import numpy as np
+import torch
+
+from oracle import flow_oracle as fo
+
+
+def make_case(kind, D, C, hidden, L, S, seed, count_bins=8, order="quadratic", scale=0.25, dropout_p=None):
+    """Synthetic weights per SURVEY §8(d): one MLE-like weight set, S perturbed draws
+    theta_s = theta_0 (1 + scale u_s) (bflow_jax_maf.py:239-240), random permutation per layer."""
+    rng = np.random.default_rng(seed)
+    perms = np.stack([rng.permutation(D) for _ in range(L)])
+    spec = fo.FlowSpec(kind, D, C, list(hidden), L, perms, count_bins=count_bins, order=order)
+    p0 = fo.init_weights(spec, rng, np.float32)
+    keep = None
+    if dropout_p:
+        draws = [[(W[None].repeat(S, 0), b[None].repeat(S, 0)) for (W, b) in layer] for layer in p0]
+        keep = (rng.uniform(size=(S, L, len(hidden), max(hidden))) > dropout_p).astype(np.float32)
+    else:
+        draws = fo.perturb_draws(p0, S, scale, rng, np.float32)
+    return spec, draws, keep, rng
+
+
+def engine_for(spec, draws, keep=None, p_drop=0.0, engine="auto", inverse_mode="incremental", device="cuda:0"):
+    from naz_b200 import FlowEngine, FlowShape
+    kind = spec.kind if spec.order == "quadratic" or spec.kind == "maf" else "nsa_linear"
+    shape = FlowShape(kind, spec.D, spec.C, list(spec.hidden), spec.L, spec.count_bins, spec.bound, spec.clip)
+    S = draws[0][0][0].shape[0]
+    eng = FlowEngine(shape, S, device=device, engine=engine, inverse_mode=inverse_mode)
+    masks = spec.masks()
+    tdraws = [[(torch.from_numpy(W), torch.from_numpy(b)) for (W, b) in layer] for layer in draws]
+    tmasks = [[torch.from_numpy(m) for m in ml] for ml in masks]
+    eng.pack(tdraws, tmasks, torch.from_numpy(spec.perms), None if keep is None else torch.from_numpy(keep), p_drop)
+    return eng
+
+
+def to64(draws):
+    return [[(W.astype(np.float64), b.astype(np.float64)) for (W, b) in layer] for layer in draws]
+
+
+def tol_report(got, ref64, rtol=1e-4, atol=1e-5):
+    """Fraction of entries outside |got-ref| <= atol + rtol |ref|, and the worst error / tolerance."""
+    got = np.asarray(got, np.float64)
+    err = np.abs(got - ref64)
+    tol = atol + rtol * np.abs(ref64)
+    bad = ~(err <= tol)
+    return float(bad.mean()), float(np.nanmax(err / tol)) if err.size else 0.0
