@@ -102,6 +102,11 @@ void nazb_destroy(nazb_handle* h);
 /* Which engine the handle resolved to (nazb_engine), or a negative status. */
 int nazb_engine_in_use(const nazb_handle* h);
 
+/* Engine serving one direction after nazb_pack: dir 0 = nazb_inverse, 1 = nazb_forward.  A direction whose
+ * tensor-core program does not fit TMEM is served by the SIMT engine when the handle was created with
+ * NAZB_ENGINE_AUTO (nazb_pack fails with NAZB_ERR_UNSUPPORTED when NAZB_ENGINE_TCGEN05 was forced). */
+int nazb_engine_for_direction(const nazb_handle* h, int dir);
+
 /* Fold masks (and optional per-draw dropout keep-masks) into the packed, engine-specific weight
  * image for all S draws.  n_lin = n_hidden + 1 linears per flow layer, tables indexed [l*n_lin + j].
  *   W[i]         device, [S][out][in] with draw stride w_draw_stride[i] floats (0 = one shared set)

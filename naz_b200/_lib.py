@@ -18,7 +18,7 @@ ENGINE_NAMES = {ENGINE_AUTO: "auto", ENGINE_SIMT: "simt", ENGINE_TCGEN05: "tcgen
 
 # every symbol include/nazb.h declares (tests check that the .so exports all of them)
 SYMBOLS = [
-    "nazb_create", "nazb_destroy", "nazb_engine_in_use", "nazb_pack", "nazb_inverse", "nazb_forward",
+    "nazb_create", "nazb_destroy", "nazb_engine_in_use", "nazb_engine_for_direction", "nazb_pack", "nazb_inverse", "nazb_forward",
     "nazb_lse_reduce", "nazb_lse_finish", "nazb_importance", "nazb_strerror", "nazb_last_cuda_error",
     "nazb_packed_bytes", "nazb_launch_count",
 ]
@@ -69,6 +69,8 @@ def lib() -> C.CDLL:
     L.nazb_destroy.restype = None
     L.nazb_engine_in_use.argtypes = [vp]
     L.nazb_engine_in_use.restype = C.c_int
+    L.nazb_engine_for_direction.argtypes = [vp, C.c_int]
+    L.nazb_engine_for_direction.restype = C.c_int
     L.nazb_pack.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), C.POINTER(vp),
                             C.POINTER(i64), C.POINTER(i32), vp, f32, vp]
     L.nazb_pack.restype = C.c_int

@@ -128,10 +128,21 @@ extern "C" void nazb_destroy(nazb_handle* h) {
 
 extern "C" int nazb_engine_in_use(const nazb_handle* h) { return h ? h->engine : NAZB_ERR_BAD_ARG; }
 
+bool nazb_tc_direction_ok(const nazb_handle* h, int dir);
+
+// Engine that serves one direction (0 = inverse / log_prob, 1 = forward / sample) after nazb_pack.
+extern "C" int nazb_engine_for_direction(const nazb_handle* h, int dir) {
+  if (!h || dir < 0 || dir > 1) return NAZB_ERR_BAD_ARG;
+  if (h->engine == NAZB_ENGINE_TCGEN05 && nazb_tc_direction_ok(h, dir)) return NAZB_ENGINE_TCGEN05;
+  return NAZB_ENGINE_SIMT;
+}
+
 extern "C" int64_t nazb_packed_bytes(const nazb_handle* h) {
   if (!h) return 0;
-  if (h->engine == NAZB_ENGINE_TCGEN05) return nazb_tc_packed_bytes(h);
-  return (int64_t)h->desc.S * h->geom.draw_stride * (int64_t)sizeof(float);
+  int64_t n = 0;
+  if (h->engine == NAZB_ENGINE_TCGEN05) n += nazb_tc_packed_bytes(h);
+  if (h->packed) n += (int64_t)h->desc.S * h->geom.draw_stride * (int64_t)sizeof(float);
+  return n;
 }
 
 extern "C" int nazb_pack(nazb_handle* h, const float* const* W, const float* const* b, const int64_t* wst,
@@ -177,10 +188,21 @@ extern "C" int nazb_pack(nazb_handle* h, const float* const* W, const float* con
       }
     }
   }
-  cudaError_t e;
-  if (h->engine == NAZB_ENGINE_TCGEN05) e = nazb_tc_pack(h, W, b, wst, bst, mask, keep, p_drop, st);
-  else e = nazb_pack_simt(h, W, b, wst, bst, mask, keep, p_drop, st);
-  CK(h, e);
+  cudaError_t e = cudaSuccess;
+  bool need_simt = (h->engine == NAZB_ENGINE_SIMT);
+  if (h->engine == NAZB_ENGINE_TCGEN05) {
+    e = nazb_tc_pack(h, W, b, wst, bst, mask, keep, p_drop, st);
+    CK(h, e);
+    // a direction the tensor-core programs cannot hold (TMEM budget) is served by the SIMT engine
+    need_simt = !nazb_tc_direction_ok(h, 0) || !nazb_tc_direction_ok(h, 1);
+    if (need_simt && h->desc.engine == NAZB_ENGINE_TCGEN05) return NAZB_ERR_UNSUPPORTED;
+    if (need_simt && nazb_simt_pick_P(h->geom) == 0) return NAZB_ERR_UNSUPPORTED;
+  }
+  if (need_simt) {
+    if (!h->packed) CK(h, cudaMalloc(&h->packed, sizeof(float) * (size_t)h->desc.S * h->geom.draw_stride));
+    e = nazb_pack_simt(h, W, b, wst, bst, mask, keep, p_drop, st);
+    CK(h, e);
+  }
   h->is_packed = true;
   return NAZB_OK;
 }
@@ -225,8 +247,9 @@ extern "C" int nazb_inverse(nazb_handle* h, int32_t s_begin, int32_t s_count, co
   io.out_x = z; io.out_l = lp; io.log_w = log_w; io.lse_max = lse_max; io.lse_sum = lse_sum; io.sum_n = sum_n;
   io.dir = 0;
   int G = pick_groups(h, N, s_count, lse_max ? n_groups : 0);
-  cudaError_t e = (h->engine == NAZB_ENGINE_TCGEN05) ? nazb_tc_launch(h, io, G, (cudaStream_t)stream)
-                                                      : nazb_simt_launch(h, io, G, (cudaStream_t)stream);
+  cudaError_t e = (nazb_engine_for_direction(h, 0) == NAZB_ENGINE_TCGEN05)
+                      ? nazb_tc_launch(h, io, G, (cudaStream_t)stream)
+                      : nazb_simt_launch(h, io, G, (cudaStream_t)stream);
   CK(h, e);
   return NAZB_OK;
 }
@@ -243,8 +266,9 @@ extern "C" int nazb_forward(nazb_handle* h, int32_t s_begin, int32_t s_count, co
   io.s_begin = s_begin; io.s_count = s_count; io.lo = lo; io.hi = hi;
   io.out_x = x; io.out_l = logdet; io.dir = 1;
   int G = pick_groups(h, N, s_count, 0);
-  cudaError_t e = (h->engine == NAZB_ENGINE_TCGEN05) ? nazb_tc_launch(h, io, G, (cudaStream_t)stream)
-                                                      : nazb_simt_launch(h, io, G, (cudaStream_t)stream);
+  cudaError_t e = (nazb_engine_for_direction(h, 1) == NAZB_ENGINE_TCGEN05)
+                      ? nazb_tc_launch(h, io, G, (cudaStream_t)stream)
+                      : nazb_simt_launch(h, io, G, (cudaStream_t)stream);
   CK(h, e);
   return NAZB_OK;
 }

@@ -126,6 +126,10 @@ class FlowEngine:
     def engine_name(self) -> str:
         return _lib.ENGINE_NAMES[self._lib.nazb_engine_in_use(self._h)]
 
+    def engine_for(self, direction: str) -> str:
+        """Engine serving `direction` ("inverse" = log_prob, "forward" = sample) after pack()."""
+        return _lib.ENGINE_NAMES[self._lib.nazb_engine_for_direction(self._h, 0 if direction == "inverse" else 1)]
+
     @property
     def packed_bytes(self) -> int:
         return int(self._lib.nazb_packed_bytes(self._h))
