@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the draw-batched flow-evaluation path (BASELINE.json).
+
+Workload (config.workload = "cfg3"): Bayesian-flow posterior-predictive log_prob — conditional
+quadratic-spline autoregressive flow, D=4 | C=2, hidden [150,150,150], 16 flow layers, K=8 bins,
+S = 1000 weight draws x N = 1,000,000 points, output log (1/S) sum_s p(x_n | theta_s)  [N]
+(SURVEY.md §8(d) row 3).  One "step" = one pass of that whole job.  Draws are sharded across ranks
+(strong scaling: the job is fixed, each of G ranks owns S/G draws) with ONE all-gather of the per-rank
+(max, sum-exp) partials per step.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (libnazb CUDA path)
+  python bench.py --impl reference --steps K --warmup W    # reference CPU path (oracle port) on host cores
+
+Prints ONE JSON line (rank 0).  `value` = whole-job log-prob evals/s with inputs resident in HBM;
+`e2e` = the same through the public API with pinned-host inputs (H2D + D2H inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (kind, D, C, hidden, L, K, S, N)
+    "cfg3": ("nsa", 4, 2, [150, 150, 150], 16, 8, 1000, 1_000_000),
+    "cfg4": ("maf", 2, 2, [150, 150, 150], 16, 8, 256, 1_000_000),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
+    ap.add_argument("--draws", type=int, default=None, help="override S (dev only; the judged run uses the default)")
+    ap.add_argument("--points", type=int, default=None, help="override N (dev only)")
+    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    return ap.parse_args()
+
+
+def flops_per_eval(D, C, hidden, L, M):
+    dims = [D + C] + list(hidden) + [M * D]
+    return 2 * L * sum(dims[i] * dims[i + 1] for i in range(len(dims) - 1))
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------
+# reference CPU path (oracle port): torch fp32 on all host cores, the reference's own structure
+# --------------------------------------------------------------------------------------
+def cpu_reference_rate(cfg, seconds: float, threads=None):
+    """Times oracle/pyro_style.py (the reference's torch path restated; pyro is not installable here) on a
+    bounded sample of the workload.  Returns (evals_per_s, cores, sample_description)."""
+    import numpy as np
+    import torch
+    from oracle import flow_oracle as fo
+    from oracle import pyro_style as ps
+    kind, D, C, hidden, L, K, S, N = cfg
+    cores = threads or os.cpu_count()
+    torch.set_num_threads(cores)
+    rng = np.random.default_rng(2)
+    perms = np.stack([rng.permutation(D) for _ in range(L)])
+    spec = fo.FlowSpec(kind, D, C, hidden, L, perms, count_bins=K)
+    p0 = fo.init_weights(spec, rng, np.float32)
+    flow = ps.PyroStyleFlow(kind, None, D, C, hidden, L, K, "quadratic", perms)
+    n_draws = 2
+    draws = fo.perturb_draws(p0, n_draws, 0.25, rng, np.float32)
+    tdraws = [[(torch.from_numpy(W), torch.from_numpy(b)) for (W, b) in layer] for layer in draws]
+    ctx = torch.from_numpy(rng.uniform(size=(C,)).astype(np.float32)) if C else None
+
+    def run(npts):
+        x = torch.from_numpy((rng.normal(size=(npts, D)) * 1.5).astype(np.float32))
+        t0 = time.perf_counter()
+        ps.log_prob_draws_reference_loop(flow, tdraws, x, ctx)
+        return time.perf_counter() - t0
+
+    run(512)                                   # warm-up
+    probe_n = 4096
+    t = run(probe_n)
+    rate = n_draws * probe_n / t
+    npts = int(max(probe_n, min(400_000, rate * seconds / n_draws)))
+    t = run(npts)
+    return n_draws * npts / t, cores, f"{n_draws} draws x {npts} points of the {L}-layer {kind} D={D}|C={C} flow, fp32 torch CPU, {t:.1f} s"
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cfg = CONFIGS[args.config]
+    kind, D, C, hidden, L, K, S, N = cfg
+    vals = []
+    for i in range(args.warmup + args.steps):
+        rate, cores, sample = cpu_reference_rate(cfg, max(2.0, args.cpu_seconds / 2))
+        if i >= args.warmup:
+            vals.append(rate)
+    v = sum(vals) / len(vals)
+    out = {
+        "impl": "reference", "metric": "log-prob evals/s (weight-draws x points)", "value": v, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.config, "flow": kind, "D": D, "C": C, "hidden": hidden, "layers": L, "draws": S,
+                   "points": N, "note": "reference CPU path = oracle/pyro_style.py (pyro-ppl is not installable here), bounded sample per step"},
+        "cpu_baseline": {"value": v, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+    return 0
+
+
+# --------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------
+def main_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from naz_b200 import FlowEngine, FlowShape, _lib
+    from naz_b200.flows.flow import NormalizingFlow
+    from naz_b200.parallel import all_gather_lse, shard_range
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    kind, D, C, hidden, L, K, S, N = CONFIGS[args.config]
+    S = args.draws or S
+    N = args.points or N
+    s_begin, s_end = shard_range(S, rank, world)
+    S_loc = s_end - s_begin
+
+    # ---- synthetic model: the public flow object (random-init weights of the named architecture) ----
+    torch.manual_seed(2)
+    if kind == "nsa":
+        flow = NormalizingFlow("nsa", None, D, C, hidden, L, K, engine=args.engine).to(dev)
+    else:
+        flow = NormalizingFlow("maf", None, D, C, hidden, L, engine=args.engine).to(dev)
+    M = flow.shape.M
+    # posterior draws theta_s = theta_0 (1 + 0.25 u_s), u ~ U(-1,1) (bflow_jax_maf.py:239-240), generated on device per rank
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    draws = []
+    for arn in flow.nets:
+        lay = []
+        for lin in arn.layers:
+            W, b = lin.weight.detach(), lin.bias.detach()
+            uW = torch.rand((S_loc,) + tuple(W.shape), device=dev, generator=gen) * 2 - 1
+            ub = torch.rand((S_loc,) + tuple(b.shape), device=dev, generator=gen) * 2 - 1
+            lay.append((W.unsqueeze(0) * (1 + 0.25 * uW), b.unsqueeze(0) * (1 + 0.25 * ub)))
+        draws.append(lay)
+    t0 = time.perf_counter()
+    eng = flow.make_engine(draws, device=dev)
+    torch.cuda.synchronize()
+    pack_s = time.perf_counter() - t0
+    del draws
+    torch.cuda.empty_cache()
+
+    # ---- synthetic points (same on every rank), pinned host copies for the e2e leg ----
+    g2 = torch.Generator().manual_seed(7)
+    x_host = (torch.randn((N, D), generator=g2) * 1.5).pin_memory()
+    c_host = torch.rand((C,), generator=g2).pin_memory() if C else None
+    x_dev = x_host.to(dev)
+    c_dev = c_host.to(dev) if C else None
+    out_host = torch.empty((N,), dtype=torch.float32).pin_memory()
+
+    kernel_ms = []
+
+    def step_device():
+        """One pass of the job with inputs resident in HBM."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = eng.inverse(x_dev, c_dev, None, want_lp=False, want_lse=True, n_groups=1)
+        e1.record()
+        kernel_ms.append((e0, e1))
+        return all_gather_lse(out["lse_max"], out["lse_sum"], S)
+
+    def step_e2e():
+        """The public API call: pinned-host points in, posterior-predictive log-density out on the host."""
+        xd = x_host.to(dev, non_blocking=True)
+        cd = c_host.to(dev, non_blocking=True) if C else None
+        out = eng.inverse(xd, cd, None, want_lp=False, want_lse=True, n_groups=1)
+        res = all_gather_lse(out["lse_max"], out["lse_sum"], S)
+        out_host.copy_(res, non_blocking=True)
+        return res
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    kernel_ms.clear()
+    clocks = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    launches0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        res = step_device()
+    ev1.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    clk = clocks.stop() if rank == 0 else None
+    total_ms = ev0.elapsed_time(ev1)
+    k_ms = sum(a.elapsed_time(b) for a, b in kernel_ms) / max(1, len(kernel_ms))
+
+    # e2e leg: one warm-up, then the same number of steps
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    tms = torch.tensor([total_ms, e2e_s * 1e3, k_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, k_ms = [float(v) for v in tms.tolist()]
+    finite = bool(torch.isfinite(res).all().item())
+
+    if rank == 0:
+        evals = float(S) * float(N)
+        ms_per_step = total_ms / args.steps
+        value = evals / (ms_per_step * 1e-3)
+        e2e_value = evals / (e2e_ms * 1e-3 / args.steps)
+        peaks, peak_kind = load_peaks()
+        f1 = flops_per_eval(D, C, hidden, L, M)
+        # dominant kernel: flow_tc_kernel / flow_simt_kernel, one launch per step per rank
+        ach_tf = f1 * float(S_loc) * float(N) / (k_ms * 1e-3) / 1e12
+        peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            try:
+                with open(tp) as f:
+                    traffic = json.load(f).get(args.config)
+            except Exception:
+                traffic = None
+        out = {
+            "metric": "log-prob evals/s (weight-draws x points)", "value": value, "unit": "evals/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (fp16 hi/lo-split tcgen05 MMAs, fp32 TMEM accumulate)"
+            if eng.engine_for("inverse") == "tcgen05" else "f32",
+            "data": "synthetic",
+            "config": {"workload": args.config, "flow": kind, "D": D, "C": C, "hidden": hidden, "layers": L, "count_bins": K,
+                       "draws": S, "points": N, "draws_per_gpu": S_loc, "output": "logsumexp_s(lp) - log S  [N]",
+                       "parallelism": f"draw-sharded x{world}, one all-gather of (max,sumexp) partials",
+                       "engine": eng.engine_for("inverse"), "l2": "inputs larger than L2: %.1f GB of packed weights streamed per step" % (eng.packed_bytes / 1e9),
+                       "pack_seconds_excluded": pack_s, "result_finite": finite},
+            "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
+                         "traffic": traffic, "peak_source": f"{peak_kind} bf16 dense, sustained",
+                         "note": "achieved = algorithmic F1 (%d flop/eval, masks as dense zeros, never the D-pass count) x evals per launch / CUDA-event kernel time; the kernel issues 3 fp16 MMAs per algorithmic product" % f1},
+            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(x_host.numel() * 4 + (C * 4 if C else 0)),
+                    "d2h_bytes_per_step": int(N * 4)},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            rate, cores, sample = cpu_reference_rate(CONFIGS[args.config], args.cpu_seconds)
+            out["cpu_baseline"] = {"value": rate, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse()
+    sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))

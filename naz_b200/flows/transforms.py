@@ -1,0 +1,99 @@
+"""Factories mirroring src/naz/flows/transforms.py: same names, arguments and return triple
+``(flow, transforms, nets)``; the transforms are weight containers whose arithmetic runs in libnazb."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .made import AutoRegressiveNN, ConditionalAutoRegressiveNN
+
+
+def bounding_transform(x, low, high):
+    """transforms.py:20-23 — provided for API compatibility; inside log_prob it is fused into the kernel."""
+    y = (x - low.expand(x.shape)) / ((high - low).expand(x.shape))
+    log_jac = -torch.sum(torch.log(y) + torch.log1p(-y), axis=-1) - torch.sum(torch.log(high - low))
+    return torch.logit(y), log_jac
+
+
+def inverse_bounding_transform(y, low, high):
+    """transforms.py:25-27."""
+    x = torch.sigmoid(y)
+    return x * ((high - low).expand(y.shape)) + low.expand(y.shape)
+
+
+class _ARTransform(nn.Module):
+    """One flow layer: holds the conditioner as ``.nn`` (pyro's ConditionalAffineAutoregressive /
+    ConditionalSplineAutoregressive keep it under that name; bflow_jax_maf.py:34 reads ``flow_layer.nn``)."""
+    kind = "maf"
+
+    def __init__(self, arn, **meta):
+        super().__init__()
+        self.nn = arn
+        self.arn = arn
+        self.meta = meta
+
+
+class AffineAutoregressive(_ARTransform):
+    kind = "maf"
+    log_scale_min_clip, log_scale_max_clip = -5.0, 3.0
+
+
+class SplineAutoregressive(_ARTransform):
+    kind = "nsa"
+
+
+class ComposeTransformModule(nn.ModuleList):
+    """`flow` in the returned triple; `.parts` as torch's ComposeTransform exposes (mcdpflow.py:15)."""
+
+    @property
+    def parts(self):
+        return list(self)
+
+
+def _hidden_list(hidden_dim):
+    return list(hidden_dim) if isinstance(hidden_dim, (list, tuple)) else [hidden_dim]
+
+
+def _check_opts(use_batchnorm, random_perm):
+    if use_batchnorm or random_perm:
+        raise NotImplementedError("Permute / BatchNorm layers are off in every naz example and not built (DESIGN.md scope)")
+
+
+def masked_affine_autoregressive(theta_dim, condition_dim, hidden_dim, num_layers, activation=None, use_batchnorm=False,
+                                 random_mask=True, random_perm=False, dropout_p=None):
+    """transforms.py:133-160."""
+    _check_opts(use_batchnorm, random_perm)
+    transforms, nets = [], []
+    for _ in range(num_layers):
+        perm = None if random_mask else torch.arange(theta_dim)
+        arn = ConditionalAutoRegressiveNN(theta_dim, condition_dim, _hidden_list(hidden_dim), nonlinearity=activation,
+                                          permutation=perm, dropout_p=dropout_p)
+        nets.append(arn)
+        transforms.append(AffineAutoregressive(arn))
+    return ComposeTransformModule(transforms), transforms, nets
+
+
+def neural_spline_autoregressive(theta_dim, condition_dim, hidden_dim, num_layers, count_bins, order="quadratic",
+                                 activation=None, use_batchnorm=False, random_mask=True, random_perm=False,
+                                 dropout_p=None):
+    """transforms.py:165-198."""
+    _check_opts(use_batchnorm, random_perm)
+    if order == "linear":
+        paramdim = [count_bins, count_bins, count_bins - 1, count_bins]
+    elif order == "quadratic":
+        paramdim = [count_bins, count_bins, count_bins - 1]
+    else:
+        raise ValueError(order)
+    transforms, nets = [], []
+    for _ in range(num_layers):
+        perm = None if random_mask else torch.arange(theta_dim)
+        arn = ConditionalAutoRegressiveNN(theta_dim, condition_dim, _hidden_list(hidden_dim), param_dims=paramdim,
+                                          nonlinearity=activation, permutation=perm, dropout_p=dropout_p)
+        nets.append(arn)
+        transforms.append(SplineAutoregressive(arn, count_bins=count_bins, order=order, bound=3.0))
+    return ComposeTransformModule(transforms), transforms, nets
+
+
+def neural_spline_coupling(*args, **kwargs):
+    """transforms.py:201-236 cannot be constructed upstream (undefined names); out of scope."""
+    raise NotImplementedError("'nsc' is unconstructible in the reference (transforms.py:201-236) and is out of scope")

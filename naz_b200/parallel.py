@@ -1,0 +1,64 @@
+"""Sharding by weight draw across the GPUs of one box: rank g owns a contiguous slice
+of the draws and its packed weights only; points are replicated.  Exactly one collective per call:
+an all-gather of the per-rank (max, sum-exp) partials for the per-point posterior predictive, or of the
+per-draw sums for importance weights.  Raw [S,N] / [S,N,D] outputs stay sharded."""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(S: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced: the first S % world ranks get one extra draw."""
+    base, rem = divmod(S, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def combine_lse_partials(pmax: torch.Tensor, psum: torch.Tensor, log_norm: float) -> torch.Tensor:
+    """[G,N] partial (max, sum exp) -> log sum.  Pure-torch combine used on CPU (gloo tests); on CUDA the
+    product path calls libnazb's nazb_lse_finish (engine.lse_finish)."""
+    m = pmax.max(dim=0).values
+    safe = torch.where(torch.isfinite(m), m, torch.zeros_like(m))
+    s = (psum * torch.exp(pmax - safe)).sum(dim=0)
+    return safe + torch.log(s) + log_norm
+
+
+def all_gather_lse(pmax: torch.Tensor, psum: torch.Tensor, S_total: int, log_w_given: bool = False,
+                   group=None) -> torch.Tensor:
+    """Each rank passes its local [N] (or [g,N]) partials; returns the global posterior predictive [N]."""
+    if pmax.dim() == 1:
+        pmax, psum = pmax.unsqueeze(0), psum.unsqueeze(0)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    local = torch.stack([pmax, psum])                      # [2, g, N]
+    if world > 1:
+        buf = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(buf, local, group=group)
+        allp = torch.cat(buf, dim=1)                       # [2, world*g, N]
+    else:
+        allp = local
+    log_norm = 0.0 if log_w_given else -math.log(S_total)
+    if allp.is_cuda:
+        from .engine import lse_finish
+        return lse_finish(allp[0].contiguous(), allp[1].contiguous(), log_norm)
+    return combine_lse_partials(allp[0], allp[1], log_norm)
+
+
+def all_gather_draw_sums(sum_local: torch.Tensor, S_total: int, group=None) -> torch.Tensor:
+    """Per-draw sums from every rank, in global draw order (shard_range order). Handles ragged shards."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return sum_local
+    cap = -(-S_total // world)
+    pad = torch.zeros(cap, dtype=sum_local.dtype, device=sum_local.device)
+    pad[: sum_local.numel()] = sum_local
+    buf = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(buf, pad, group=group)
+    parts = []
+    for r in range(world):
+        b, e = shard_range(S_total, r, world)
+        parts.append(buf[r][: e - b])
+    return torch.cat(parts)

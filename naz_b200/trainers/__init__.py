@@ -1,0 +1,1 @@
+from .train_flows import get_params, predict, set_params, importance_weights  # noqa: F401

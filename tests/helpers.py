@@ -45,3 +45,17 @@ def tol_report(got, ref64, rtol=1e-4, atol=1e-5):
     tol = atol + rtol * np.abs(ref64)
     bad = ~(err <= tol)
     return float(bad.mean()), float(np.nanmax(err / tol)) if err.size else 0.0
+
+
+def load_golden(name):
+    """-> (spec, draws [L][n_lin](W[S,..], b[S,..]) fp32, arrays dict)"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"), allow_pickle=False)
+    kind, D, C, L, K = str(g["kind"]), int(g["D"]), int(g["C"]), int(g["L"]), int(g["K"])
+    hidden = [int(h) for h in g["hidden"]]
+    spec = fo.FlowSpec(kind, D, C, hidden, L, g["perms"], count_bins=K, order=str(g["order"]))
+    draws = [[(g[f"W_{l}_{j}"], g[f"b_{l}_{j}"]) for j in range(len(hidden) + 1)] for l in range(L)]
+    return spec, draws, g
+
+
+GOLDEN = ["maf_uncond_2d", "maf_cond_3d", "nsa_cond_4d", "nsa_uncond_2d_k5", "nsa_linear_3d"]

