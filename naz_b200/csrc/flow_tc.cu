@@ -31,7 +31,9 @@
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;   // 4 per TMEM lane quadrant; the column range of a step is split 4 ways
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kParts = kEpiWarps / 4;
 constexpr int kThreads = (kEpiWarps + 2) * 32;
 constexpr int kSlotBytes = 32768;
 constexpr int kTmemCols = 512;
@@ -78,8 +80,11 @@ struct TcState {
   size_t draw_bytes[2] = {0, 0};
 };
 
+constexpr int kMaxSteps = 80;
+
 struct KParams {
-  const Step* steps;
+  long long* dbg;          // optional per-step clock stamps of CTA 0 (dev tool), layout [step][8]
+  Step steps[kMaxSteps];   // the program, read through the constant bank (uniform loads)
   int nsteps;
   const uint8_t* wimg;
   unsigned long long draw_bytes, layer_bytes;
@@ -189,7 +194,7 @@ bool build_forward(const FlowGeom& g, TcPlan& P) {
            mk_epi(EPI_XFWD, T_OUT, 0, 0, r0, r1 - r0));
   }
   P.layer_bytes[1] = b.w_off;
-  return true;
+  return (int)P.steps[1].size() <= kMaxSteps;
 }
 
 bool build_inverse(const FlowGeom& g, TcPlan& P) {
@@ -253,7 +258,7 @@ bool build_inverse(const FlowGeom& g, TcPlan& P) {
     }
   }
   P.layer_bytes[0] = b.w_off;
-  return true;
+  return (int)P.steps[0].size() <= kMaxSteps;
 }
 
 bool plan_smem(const FlowGeom& g, TcPlan& P) {
@@ -264,8 +269,8 @@ bool plan_smem(const FlowGeom& g, TcPlan& P) {
   P.off_y = off;       off += (uint32_t)g.D * kTileM * 4;
   P.off_xo = off;      off += (uint32_t)g.D * kTileM * 4;
   P.off_ctx = off;     off += (uint32_t)std::max(1, g.C) * kTileM * 4;
-  P.off_misc = off;    off += 4 * kTileM * 4;                                  // ljac, ld partials
-  P.off_scratch = off; off += (g.kind == NAZB_KIND_AFFINE) ? 0 : 2u * 32 * kTileM * 4;
+  P.off_misc = off;    off += (1 + kParts) * kTileM * 4;                       // ljac, ld partials
+  P.off_scratch = off; off += (g.kind == NAZB_KIND_AFFINE || (g.kind == NAZB_KIND_RQS && g.K == 8)) ? 0 : (uint32_t)kParts * 32 * kTileM * 4;
   off = (off + 127) & ~127u;
   P.off_ring = off;
   const uint32_t cap = 227 * 1024;
@@ -348,7 +353,11 @@ __global__ void tc_pack_kernel(Image im, int S, int L, int n_lin, int D, int M, 
 // ------------------------------------------------------------------------------------------------
 // Main kernel
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+__device__ __forceinline__ long long clk() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)); return t; }
+#define DBG(slot)                                                                       \
+  if (p.dbg && blockIdx.x == 0 && dbg_i < 256) p.dbg[dbg_i * 8 + (slot)] = clk();
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory"); }
 
 // 8 consecutive accumulator columns -> tanh -> fp16 hi / lo chunks
 __device__ __forceinline__ void tanh_chunk(const uint32_t* r, uint4& hi4, uint4& lo4) {
@@ -377,7 +386,8 @@ __device__ __forceinline__ void store_split(__half* hi_base, __half* lo_base, in
   lo_base[o] = l;
 }
 
-__global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(KParams p, IoArgs io, int n_groups) {
+__global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ IoArgs io,
+                                                               int n_groups) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem);          // [nslots]
   uint64_t* bar_empty = bar_full + 8;                               // [nslots]
@@ -393,11 +403,14 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(KParams p, IoArgs 
   float* xorig = reinterpret_cast<float*>(smem + p.off_xo);         // [D][128] tile input (after bounding)
   float* ctxs = reinterpret_cast<float*>(smem + p.off_ctx);         // [C][128]
   float* ljac = reinterpret_cast<float*>(smem + p.off_misc);        // [128]
-  float* ldpart = ljac + kTileM;                                    // [2][128]
-  float* scratch = reinterpret_cast<float*>(smem + p.off_scratch);  // [2][32][128]
+  float* ldpart = ljac + kTileM;                                    // [kParts][128]
+  float* scratch = reinterpret_cast<float*>(smem + p.off_scratch);  // [kParts][32][128]
   uint8_t* ring = smem + p.off_ring;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // broadcast so the compiler can prove the role index warp-uniform (role branches stay convergent and
+  // warp-uniform values are eligible for uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int D = p.D, C = p.C, M = p.M;
   const bool inverse = io.dir == 0;
 
@@ -446,52 +459,80 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(KParams p, IoArgs 
     }
   } else if (warp == kEpiWarps + 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      uint32_t cnt = 0, par_a = 0;
-      const uint32_t in_hi_a = tcx::smem_u32(in_hi), in_lo_a = tcx::smem_u32(in_lo);
-      const uint32_t h_hi_a = tcx::smem_u32(h_hi), h_lo_a = tcx::smem_u32(h_lo);
-      const uint32_t ring_a = tcx::smem_u32(ring);
-      const uint32_t lbo_a = kTileM * 16;
-      for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int grp = (int)(item / n_tiles);
-        for (int si = grp; si < io.s_count; si += n_groups) {
-          bool need_a = true;   // draw start: wait for the epilogue warps to stage `in`
-          for (int li = 0; li < p.L; ++li) {
-            for (int st = 0; st < p.nsteps; ++st) {
-              const Step s = p.steps[st];
-              if (need_a) {
-                tcx::mbar_wait(bar_a, par_a);
-                par_a ^= 1;
-                need_a = false;
+    // The whole warp runs this loop convergently on warp-uniform values (program in constant space), so the
+    // descriptors live in uniform registers; only the tcgen05 instructions are predicated on the elected lane.
+    const uint32_t elected = tcx::elect_one();
+    uint32_t slot = 0, use = 0, par_a = 0;
+    int dbg_i = 0;
+    const uint32_t in_hi_a = tcx::smem_u32(in_hi), in_lo_a = tcx::smem_u32(in_lo);
+    const uint32_t h_hi_a = tcx::smem_u32(h_hi), h_lo_a = tcx::smem_u32(h_lo);
+    const uint32_t ring_a = tcx::smem_u32(ring);
+    constexpr uint32_t lbo_a = kTileM * 16;
+    constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);            // SBO = 128 B, descriptor version 1
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int grp = (int)(item / n_tiles);
+      for (int si = grp; si < io.s_count; si += n_groups) {
+        bool need_a = true;   // draw start: wait for the epilogue warps to stage `in`
+        for (int li = 0; li < p.L; ++li) {
+          for (int st = 0; st < p.nsteps; ++st) {
+            // hoist every field of the step out of constant space BEFORE the waits (the asm "memory" clobbers
+            // would otherwise force indexed constant re-loads between MMAs)
+            const uint32_t s_wbytes = p.steps[st].w_bytes, s_n = p.steps[st].n, s_dcol = p.steps[st].d_col;
+            const uint32_t s_chunk0 = p.steps[st].a_chunk0, s_abuf = p.steps[st].a_buf, s_nsplit = p.steps[st].nsplit;
+            const int ksteps = p.steps[st].ksteps;
+            const uint32_t s_acc = p.steps[st].accumulate, s_epi = p.steps[st].epi;
+            const uint32_t idesc = tcx::make_idesc_f16(s_n);
+            const uint32_t lbo_b = s_n * 16;
+            const uint32_t a_off = s_chunk0 * lbo_a;
+            const uint32_t a_hi = (s_abuf == A_IN ? in_hi_a : h_hi_a) + a_off;
+            const uint32_t a_lo = (s_abuf == A_IN ? in_lo_a : h_lo_a) + a_off;
+            const uint32_t b_hi = ring_a + slot * kSlotBytes, b_lo = b_hi + (s_wbytes >> 1);
+            // low descriptor words: (addr >> 4) | (LBO >> 4) << 16; one k-step advances the address by 2 LBO
+            const uint32_t da_hi0 = (a_hi >> 4) | ((lbo_a >> 4) << 16), da_lo0 = (a_lo >> 4) | ((lbo_a >> 4) << 16);
+            const uint32_t db_hi0 = (b_hi >> 4) | ((lbo_b >> 4) << 16), db_lo0 = (b_lo >> 4) | ((lbo_b >> 4) << 16);
+            const uint32_t da_step = (2 * lbo_a) >> 4, db_step = (2 * lbo_b) >> 4;
+            const uint32_t d_addr = tmem + s_dcol;
+            constexpr uint64_t dhi = (uint64_t)desc_hi << 32;
+            if (elected) { DBG(0) }
+            if (need_a) {
+              tcx::mbar_wait(bar_a, par_a);
+              par_a ^= 1;
+              need_a = false;
+            }
+            if (s_wbytes) {
+              tcx::mbar_wait(bar_full + slot, use & 1);
+              tcx::tc_fence_after();
+              if (elected) { DBG(2) }
+              uint32_t da = da_hi0, db = db_hi0;
+#pragma unroll 4
+              for (int k = 0; k < ksteps; ++k) {            // a_hi * w_hi
+                tcx::mma_f16_ss_elect(d_addr, dhi | da, dhi | db, idesc, (k == 0) ? s_acc : 1u, elected);
+                da += da_step; db += db_step;
               }
-              if (s.w_bytes) {
-                const uint32_t slot = cnt % p.nslots, use = cnt / p.nslots;
-                tcx::mbar_wait(bar_full + slot, use & 1);
-                tcx::tc_fence_after();
-                const uint32_t idesc = tcx::make_idesc_f16(s.n);
-                const uint32_t b_hi = ring_a + slot * kSlotBytes, b_lo = b_hi + (s.w_bytes >> 1);
-                const uint32_t lbo_b = (uint32_t)s.n * 16;
-                const uint32_t a_hi = (s.a_buf == A_IN ? in_hi_a : h_hi_a) + (uint32_t)s.a_chunk0 * lbo_a;
-                const uint32_t a_lo = (s.a_buf == A_IN ? in_lo_a : h_lo_a) + (uint32_t)s.a_chunk0 * lbo_a;
-                uint32_t acc = s.accumulate;
-                for (int sp = 0; sp < s.nsplit; ++sp) {
-                  const uint32_t ab = (sp == 2) ? a_lo : a_hi;
-                  const uint32_t bb = (sp == 1) ? b_lo : b_hi;
-                  for (int k = 0; k < s.ksteps; ++k) {
-                    uint64_t da = tcx::make_smem_desc(ab + k * 2 * lbo_a, lbo_a, 128);
-                    uint64_t db = tcx::make_smem_desc(bb + k * 2 * lbo_b, lbo_b, 128);
-                    tcx::mma_f16_ss(tmem + s.d_col, da, db, idesc, acc);
-                    acc = 1;
-                  }
+              if (elected) { DBG(1) }
+              da = da_hi0; db = db_lo0;
+#pragma unroll 4
+              for (int k = 0; k < ksteps; ++k) {            // a_hi * w_lo
+                tcx::mma_f16_ss_elect(d_addr, dhi | da, dhi | db, idesc, 1u, elected);
+                da += da_step; db += db_step;
+              }
+              if (s_nsplit == 3) {
+                da = da_lo0; db = db_hi0;
+#pragma unroll 4
+                for (int k = 0; k < ksteps; ++k) {          // a_lo * w_hi
+                  tcx::mma_f16_ss_elect(d_addr, dhi | da, dhi | db, idesc, 1u, elected);
+                  da += da_step; db += db_step;
                 }
-                tcx::mma_commit(bar_empty + slot);   // weights slot is free once these MMAs retire
-                ++cnt;
               }
-              if (s.epi != EPI_NONE) {
-                tcx::mma_commit(bar_acc);
-                // the next step reads what this epilogue writes, except after the last step of a draw
-                need_a = !(li == p.L - 1 && st == p.nsteps - 1);
-              }
+              tcx::mma_commit_elect(bar_empty + slot, elected);   // weights slot is free once these MMAs retire
+              if (++slot == (uint32_t)p.nslots) { slot = 0; ++use; }
+            }
+            if (elected) { DBG(3) }
+            ++dbg_i;
+            if (s_epi != EPI_NONE) {
+              tcx::mma_commit_elect(bar_acc, elected);
+              // the next step reads what this epilogue writes, except after the last step of a draw
+              need_a = !(li == p.L - 1 && st == p.nsteps - 1);
             }
           }
         }
@@ -499,11 +540,14 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(KParams p, IoArgs 
     }
   } else {
     // ===================== epilogue warps =====================
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3, half = warp >> 2;   // `half` = column part 0..kParts-1
     const int row = q * 32 + lane;
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
     uint32_t par_acc = 0;
+    int dbg_i = 0;
+    const bool dbg_me = (tid == 0);
     const bool spline = p.kind != NAZB_KIND_AFFINE;
+    const bool fast_rqs = (p.kind == NAZB_KIND_RQS && p.K == 8);
     float* scr = scratch + (size_t)half * 32 * kTileM + row;   // [m * 128]
     auto raw = [&](int m) { return scr[m * kTileM]; };
     auto setw = [&](int m, float v) { scr[m * kTileM] = v; };
@@ -515,14 +559,14 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(KParams p, IoArgs 
       float run_m = -INFINITY, run_s = 0.f;
       // ---- tile load (shared across this item's draws) ----
       epi_bar_sync();   // previous item's readers are done with xorig / ctxs
-      for (int i = tid; i < kTileM * C; i += 256) {
+      for (int i = tid; i < kTileM * C; i += kEpiThreads) {
         int pt = i / C, c = i % C;
         float v = 0.f;
         if (pt < npts) v = io.ctx[((io.ctx_rows == 1) ? 0 : (size_t)(n0 + pt)) * C + c];
         ctxs[c * kTileM + pt] = v;
       }
       if (inverse || io.x_draw_stride == 0) {
-        for (int i = tid; i < kTileM * D; i += 256) {
+        for (int i = tid; i < kTileM * D; i += kEpiThreads) {
           int pt = i / D, d = i % D;
           xorig[d * kTileM + pt] = (pt < npts) ? io.x[(size_t)(n0 + pt) * D + d] : 0.f;
         }
@@ -540,13 +584,13 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(KParams p, IoArgs 
         if (!inverse && io.x_draw_stride != 0) {
           epi_bar_sync();
           const float* zs = io.x + (size_t)si * io.x_draw_stride;
-          for (int i = tid; i < kTileM * D; i += 256) {
+          for (int i = tid; i < kTileM * D; i += kEpiThreads) {
             int pt = i / D, d = i % D;
             xorig[d * kTileM + pt] = (pt < npts) ? zs[(size_t)(n0 + pt) * D + d] : 0.f;
           }
           epi_bar_sync();
         }
-        for (uint32_t i = tid; i < ((uint32_t)p.hp_max * kTileM * 4) / 16; i += 256)
+        for (uint32_t i = tid; i < ((uint32_t)p.hp_max * kTileM * 4) / 16; i += kEpiThreads)
           reinterpret_cast<uint4*>(smem + p.off_h)[i] = make_uint4(0, 0, 0, 0);
         float ld_acc = 0.f;
         if (half == 0) {
@@ -570,31 +614,40 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(KParams p, IoArgs 
           const int l = inverse ? (p.L - 1 - li) : li;
           const int* perm = p.perm + l * D;
           for (int st = 0; st < p.nsteps; ++st) {
-            const Step s = p.steps[st];
-            if (s.epi == EPI_NONE) continue;
+            // copy the step's epilogue fields out of constant space before parking on the barrier
+            struct { uint32_t epi, e_col, e_ncols, e_dst_chunk, stage, nranks; } s;
+            s.epi = p.steps[st].epi; s.e_col = p.steps[st].e_col; s.e_ncols = p.steps[st].e_ncols;
+            s.e_dst_chunk = p.steps[st].e_dst_chunk; s.stage = p.steps[st].stage; s.nranks = p.steps[st].nranks;
+            if (s.epi == EPI_NONE) { ++dbg_i; continue; }
             tcx::mbar_wait(bar_acc, par_acc);
             par_acc ^= 1;
             tcx::tc_fence_after();
+            if (dbg_me) { DBG(5) }
             if (s.epi == EPI_TANH) {
               const int nchunks = s.e_ncols >> 3;
-              const int per = (nchunks + 1) >> 1;
-              const int cb = half * per, ce = min(nchunks, cb + per);
-              for (int c = cb; c < ce; c += 2) {
-                uint32_t r[16];
-                const bool two = (c + 1 < ce);
-                if (two) tcx::tmem_ld16(lane_base + s.e_col + c * 8, r);
-                else tcx::tmem_ld8(lane_base + s.e_col + c * 8, r);
+              const int per = (nchunks + kParts - 1) / kParts;
+              const int cb = min(nchunks, half * per), ce = min(nchunks, cb + per);
+              // up to 4 chunks (32 columns) per batch: all TMEM loads in flight before the single wait
+              for (int c = cb; c < ce; c += 4) {
+                uint32_t r[32];
+                const int nb = min(4, ce - c);
+                const uint32_t ta = lane_base + s.e_col + c * 8;
+                if (nb == 4) tcx::tmem_ld32(ta, r);
+                else if (nb == 3) { tcx::tmem_ld16(ta, r); tcx::tmem_ld8(ta + 16, r + 16); }
+                else if (nb == 2) tcx::tmem_ld16(ta, r);
+                else tcx::tmem_ld8(ta, r);
                 tcx::tmem_ld_wait();
-                uint4 hi4, lo4;
-                tanh_chunk(r, hi4, lo4);
+                if (dbg_me) { DBG(4) }
                 size_t o = ((size_t)(s.e_dst_chunk + c) * kTileM + row) * 8;
-                *reinterpret_cast<uint4*>(h_hi + o) = hi4;
-                *reinterpret_cast<uint4*>(h_lo + o) = lo4;
-                if (two) {
-                  tanh_chunk(r + 8, hi4, lo4);
-                  o += (size_t)kTileM * 8;
-                  *reinterpret_cast<uint4*>(h_hi + o) = hi4;
-                  *reinterpret_cast<uint4*>(h_lo + o) = lo4;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  if (u < nb) {
+                    uint4 hi4, lo4;
+                    tanh_chunk(r + 8 * u, hi4, lo4);
+                    *reinterpret_cast<uint4*>(h_hi + o) = hi4;
+                    *reinterpret_cast<uint4*>(h_lo + o) = lo4;
+                    o += (size_t)kTileM * 8;
+                  }
                 }
               }
             } else if (s.epi == EPI_XINV) {
@@ -610,6 +663,15 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(KParams p, IoArgs 
                   float sc = fminf(fmaxf(__uint_as_float(rr[1]), p.clip_lo), p.clip_hi);
                   xv = (yv - mu) * expf(-sc);
                   ld = sc;
+                } else if (fast_rqs) {
+                  uint32_t rr[24];
+                  tcx::tmem_ld16(lane_base + s.e_col, rr);
+                  tcx::tmem_ld8(lane_base + s.e_col + 16, rr + 16);
+                  tcx::tmem_ld_wait();
+                  float rf[24];
+#pragma unroll
+                  for (int e = 0; e < 24; ++e) rf[e] = __uint_as_float(rr[e]);
+                  nazb::rqs_fast<8>(yv, p.bound, true, rf, xv, ld);
                 } else {
                   for (int m0 = 0; m0 < p.Mp; m0 += 16) {
                     uint32_t rr[16];
@@ -635,7 +697,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(KParams p, IoArgs 
                 }
               }
             } else {   // EPI_XFWD: transform the dims of ranks [stage, stage + nranks)
-              for (int i = half; i < s.nranks; i += 2) {
+              for (int i = half; i < (int)s.nranks; i += kParts) {
                 const int rr_ = s.stage + i, d = perm[rr_];
                 const float xv = xcur[d * kTileM + row];
                 float yv, ld;
@@ -647,6 +709,17 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(KParams p, IoArgs 
                   float sc = fminf(fmaxf(__uint_as_float(rr[1]), p.clip_lo), p.clip_hi);
                   yv = mu + xv * expf(sc);
                   ld = sc;
+                } else if (fast_rqs) {
+                  uint32_t rr[24];
+                  const uint32_t ta = lane_base + s.e_col + i * 23;
+                  tcx::tmem_ld8(ta, rr);
+                  tcx::tmem_ld8(ta + 8, rr + 8);
+                  tcx::tmem_ld8(ta + 16, rr + 16);
+                  tcx::tmem_ld_wait();
+                  float rf[24];
+#pragma unroll
+                  for (int e = 0; e < 24; ++e) rf[e] = __uint_as_float(rr[e]);
+                  nazb::rqs_fast<8>(xv, p.bound, false, rf, yv, ld);
                 } else {
                   for (int m0 = 0; m0 < M; m0 += 8) {
                     uint32_t rr[8];
@@ -665,12 +738,15 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(KParams p, IoArgs 
               }
             }
             const bool last_of_draw = (li == p.L - 1 && st == p.nsteps - 1);
+            if (dbg_me) { DBG(6) }
             if (!last_of_draw) {
               tcx::tc_fence_before();
               tcx::fence_async_smem();
               __syncwarp();
               if (lane == 0) tcx::mbar_arrive(bar_a);
             }
+            if (dbg_me) { DBG(7) }
+            ++dbg_i;
           }
         }
 
@@ -702,7 +778,11 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(KParams p, IoArgs 
           ldpart[half * kTileM + row] = ld_acc;
           epi_bar_sync();
           if (half == 0 && row < npts) {
-            if (io.out_l) io.out_l[(size_t)si * io.N + n0 + row] = ldpart[row] + ldpart[kTileM + row];
+            if (io.out_l) {
+              float a = 0.f;
+              for (int pp = 0; pp < kParts; ++pp) a += ldpart[pp * kTileM + row];
+              io.out_l[(size_t)si * io.N + n0 + row] = a;
+            }
             float* dst = io.out_x + ((size_t)si * io.N + n0 + row) * D;
             for (int d = 0; d < D; ++d) {
               float v = xcur[d * kTileM + row];
@@ -723,11 +803,16 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(KParams p, IoArgs 
   if (warp == kEpiWarps + 1) tcx::tmem_dealloc(tmem, kTmemCols);
 }
 
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
 // Host glue
 // ------------------------------------------------------------------------------------------------
+static long long* g_tc_dbg = nullptr;
+// dev tool (not part of include/nazb.h): device buffer [256][8] receiving CTA 0's per-step clock stamps
+extern "C" void nazb_debug_set_clock_buffer(long long* dev_buf) { g_tc_dbg = dev_buf; }
+extern "C" int nazb_debug_program(const nazb_handle* h, int dir, int* out, int cap);
 bool nazb_tc_supported(const FlowGeom& g, std::string* why) {
   TcPlan P;
   if (!base_dims(g, P)) { if (why) *why = "hidden width > 256, D + C + 1 > 48 or M > 32"; return false; }
@@ -831,8 +916,9 @@ cudaError_t nazb_tc_launch(const nazb_handle* h, const IoArgs& io, int n_groups,
   const int d = io.dir;
   if (!P.ok[d]) return cudaErrorNotSupported;
   KParams kp{};
-  kp.steps = t->steps_dev[d];
+  kp.dbg = g_tc_dbg;
   kp.nsteps = (int)P.steps[d].size();
+  for (int i = 0; i < kp.nsteps; ++i) kp.steps[i] = P.steps[d][i];
   kp.wimg = t->wimg[d];
   kp.draw_bytes = t->draw_bytes[d];
   kp.layer_bytes = P.layer_bytes[d];
@@ -850,4 +936,18 @@ cudaError_t nazb_tc_launch(const nazb_handle* h, const IoArgs& io, int n_groups,
   flow_tc_kernel<<<grid, kThreads, P.smem_bytes, st>>>(kp, io, n_groups);
   nazb_count_launch();
   return cudaGetLastError();
+}
+
+// dev tool: dump the step program (n, ksteps, nsplit, epi, e_ncols, w_bytes) of one direction
+extern "C" int nazb_debug_program(const nazb_handle* h, int dir, int* out, int cap) {
+  const TcState* t = static_cast<const TcState*>(h->tc);
+  if (!t || !t->plan.ok[dir]) return 0;
+  int n = 0;
+  for (const Step& s : t->plan.steps[dir]) {
+    if ((n + 1) * 8 > cap) break;
+    int* o = out + n * 8;
+    o[0] = s.n; o[1] = s.ksteps; o[2] = s.nsplit; o[3] = s.epi; o[4] = s.e_ncols; o[5] = (int)s.w_bytes; o[6] = s.d_col; o[7] = s.a_buf;
+    ++n;
+  }
+  return n;
 }

@@ -128,6 +128,74 @@ __device__ __forceinline__ void rational_spline(float in, int K, float B, bool i
   }
 }
 
+// Register-resident rational-QUADRATIC spline for a compile-time bin count K, built on the MUFU approximations
+// (ex2 / lg2 / rcp / sqrt .approx, each ~1-2 ulp) with every division turned into a reciprocal multiply.
+// `r` holds the raw conditioner outputs of this (point, dim): w[0..K), h[K..2K), d[2K..3K-1).  Same
+// operation order as rational_spline<false> above; used by the tcgen05 engine's transform epilogues.
+template <int K>
+__device__ __forceinline__ void rqs_fast(float in, float B, bool inverse, const float* r, float& out, float& ld_fwd) {
+  const float min_w = 1e-3f, min_h = 1e-3f, min_d = 1e-3f, eps = 1e-6f;
+  const float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+  auto ex2 = [](float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; };
+  auto lg2 = [](float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; };
+  auto rcp = [](float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; };
+  auto sqr = [](float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; };
+  if (!(in >= -B && in <= B)) { out = in; ld_fwd = 0.f; return; }
+  float mw = r[0], mh = r[K];
+#pragma unroll
+  for (int j = 1; j < K; ++j) { mw = fmaxf(mw, r[j]); mh = fmaxf(mh, r[K + j]); }
+  float ew[K], eh[K], sw = 0.f, sh = 0.f;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    ew[j] = ex2((r[j] - mw) * LOG2E);
+    eh[j] = ex2((r[K + j] - mh) * LOG2E);
+    sw += ew[j];
+    sh += eh[j];
+  }
+  const float iw = (1.f - min_w * K) * rcp(sw), ih = (1.f - min_h * K) * rcp(sh);
+  float cw = 0.f, ch = 0.f, kx0 = -B, ky0 = -B;
+  float sel_w = 0.f, sel_h = 0.f, sel_x = -B, sel_y = -B, dl_raw = 0.f, dr_raw = 0.f;
+  bool first = true, lastb = false;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    cw += fmaf(ew[j], iw, min_w);
+    ch += fmaf(eh[j], ih, min_h);
+    float kx1 = (j == K - 1) ? B : fmaf(2.f * B, cw, -B);
+    float ky1 = (j == K - 1) ? B : fmaf(2.f * B, ch, -B);
+    float ks = inverse ? ky0 : kx0;
+    if (j == 0 || in >= ks + eps) {
+      sel_w = kx1 - kx0; sel_h = ky1 - ky0; sel_x = kx0; sel_y = ky0;
+      first = (j == 0); lastb = (j == K - 1);
+      dl_raw = (j == 0) ? 0.f : r[2 * K + j - 1];
+      dr_raw = (j == K - 1) ? 0.f : r[2 * K + j];
+    }
+    kx0 = kx1; ky0 = ky1;
+  }
+  auto softplus = [&](float a) { return a > 20.f ? a : lg2(1.f + ex2(a * LOG2E)) * LN2; };
+  const float d_edge = 1.f - min_d;
+  const float d0 = first ? d_edge : min_d + softplus(dl_raw);
+  const float d1 = lastb ? d_edge : min_d + softplus(dr_raw);
+  const float delta = sel_h * rcp(sel_w);
+  const float t2 = d0 + d1 - 2.f * delta;
+  float th;
+  if (inverse) {
+    float dy = in - sel_y;
+    float a = fmaf(dy, t2, sel_h * (delta - d0));
+    float b = fmaf(-dy, t2, sel_h * d0);
+    float c = -delta * dy;
+    float disc = fmaf(b, b, -4.f * a * c);
+    th = (2.f * c) * rcp(-b - sqr(fmaxf(disc, 0.f)));
+    out = fmaf(th, sel_w, sel_x);
+  } else {
+    th = (in - sel_x) * rcp(sel_w);
+  }
+  const float tomt = th * (1.f - th), omt = 1.f - th;
+  const float den = fmaf(t2, tomt, delta);
+  if (!inverse) out = fmaf(sel_h * fmaf(delta, th * th, d0 * tomt), rcp(den), sel_y);
+  const float dnum = delta * delta * fmaf(d1, th * th, fmaf(2.f * delta, tomt, d0 * omt * omt));
+  ld_fwd = (lg2(dnum) - 2.f * lg2(den)) * LN2;
+}
+
 // Logit bounding transform of one coordinate (transforms.py:20-23): returns y, adds to log_jac.
 __device__ __forceinline__ float bound_fwd(float x, float lo, float hi, float& log_jac) {
   float u = (x - lo) / (hi - lo);
