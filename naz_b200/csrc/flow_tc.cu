@@ -22,6 +22,7 @@
 // (see oracle/flow_oracle.py).
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cuda_fp16.h>
 #include "nazb_internal.h"
@@ -38,7 +39,7 @@ constexpr int kThreads = (kEpiWarps + 2) * 32;
 constexpr int kSlotBytes = 32768;
 constexpr int kTmemCols = 512;
 
-enum : uint8_t { EPI_NONE = 0, EPI_TANH = 1, EPI_XINV = 2, EPI_XFWD = 3 };
+enum : uint8_t { EPI_NONE = 0, EPI_TANH = 1, EPI_XINV = 2, EPI_XFWD = 3, EPI_FIRST = 4 };
 enum : uint8_t { A_IN = 0, A_H = 1 };
 
 struct Step {
@@ -49,8 +50,10 @@ struct Step {
   uint16_t n;          // N extent (multiple of 16)
   uint16_t d_col;      // TMEM column of D
   uint8_t a_buf, nsplit, accumulate, epi;
-  uint8_t stage, nranks, pad0, pad1;
-  uint16_t e_col, e_ncols, e_dst_chunk, pad2;
+  uint8_t stage, nranks, flags, pad1;   // flags bit 0: the accumulator holds nothing yet (bias-only output)
+  uint16_t e_col, e_ncols, e_dst_chunk;
+  uint16_t e_aux;   // v2 inverse: TANH / XINV -> float offset of the bias of column e_col inside the layer
+                    // constants; FIRST -> first hidden unit of the block
 };
 
 struct Image {          // how the pack kernel fills one step's weight image
@@ -70,6 +73,12 @@ struct TcPlan {
   int kin_pad = 0, hp_max = 0, mp = 0, nslots = 0;
   size_t smem_bytes = 0;
   uint32_t off_in, off_h, off_x, off_y, off_xo, off_ctx, off_misc, off_scratch, off_ring;
+  // v2 inverse: per-(draw, layer) fp32 constants [W0 (Hp0 x kinp) | b_0 .. b_{nh-1} | b_out (D x Mp, rank-major)]
+  int kinp = 0, lc_floats = 0, lc_b[NAZB_MAX_HIDDEN_LAYERS] = {0}, lc_bout = 0;
+  // v2 inverse kernel shared-memory plan
+  uint32_t i_xin = 0, i_lc = 0, i_h = 0, i_y = 0, i_xo = 0, i_misc = 0, i_scratch = 0, i_ring = 0;
+  int i_nslots = 0;
+  size_t i_smem_bytes = 0;
 };
 
 struct TcState {
@@ -78,6 +87,7 @@ struct TcState {
   Step* steps_dev[2] = {nullptr, nullptr};
   const float** tab_dev = nullptr;   // [3][L * n_lin] W / b / mask pointer tables
   size_t draw_bytes[2] = {0, 0};
+  float* lc_dev = nullptr;           // [S][L][lc_floats]
 };
 
 constexpr int kMaxSteps = 80;
@@ -92,6 +102,21 @@ struct KParams {
   int D, C, L, M, Mp, K, kind, kin, kin_pad, hp_max, nslots;
   float bound, clip_lo, clip_hi;
   uint32_t off_in, off_h, off_x, off_y, off_xo, off_ctx, off_misc, off_scratch, off_ring;
+};
+
+struct KParamsInv {
+  long long* dbg;
+  Step steps[kMaxSteps];
+  int nsteps;
+  const uint8_t* wimg;
+  unsigned long long draw_bytes, layer_bytes;
+  const float* lc;                 // [S][L][lc_floats]
+  int lc_floats, lc_b0;
+  int phase_delay;
+  const int* perm;
+  int D, C, L, M, Mp, K, kind, kin, kinp, hp_max, nslots;
+  float bound, clip_lo, clip_hi;
+  uint32_t off_xin, off_lc, off_h, off_y, off_xo, off_misc, off_scratch, off_ring;
 };
 
 inline int ceil_to(int v, int m) { return (v + m - 1) / m * m; }
@@ -120,7 +145,7 @@ struct Builder {
       s.nsplit = (uint8_t)nsplit;
       s.accumulate = (uint8_t)((k_off > 0) ? 1 : accumulate);
       if (last) {
-        s.epi = epi.epi; s.stage = epi.stage; s.nranks = epi.nranks;
+        s.epi = epi.epi; s.stage = epi.stage; s.nranks = epi.nranks; s.flags = epi.flags; s.e_aux = epi.e_aux;
         s.e_col = epi.e_col; s.e_ncols = epi.e_ncols; s.e_dst_chunk = epi.e_dst_chunk;
       }
       Image sub = im;
@@ -135,7 +160,7 @@ struct Builder {
   void epi_only(Step epi) {
     Step s{};
     s.w_bytes = 0;
-    s.epi = epi.epi; s.stage = epi.stage; s.nranks = epi.nranks;
+    s.epi = epi.epi; s.stage = epi.stage; s.nranks = epi.nranks; s.flags = epi.flags; s.e_aux = epi.e_aux;
     s.e_col = epi.e_col; s.e_ncols = epi.e_ncols; s.e_dst_chunk = epi.e_dst_chunk;
     steps.push_back(s);
   }
@@ -197,64 +222,73 @@ bool build_forward(const FlowGeom& g, TcPlan& P) {
   return (int)P.steps[1].size() <= kMaxSteps;
 }
 
+// Inverse program, v2.  Per flow layer, stage r = 0..D-1 (finalises the dimension of rank r):
+//   FIRST(r)   fp32 CUDA-core first layer for the hidden units of degree r (K = C + D is tiny), tanh, -> A operand
+//   PUSH j->j+1 for j = 0..nh-2: pre_{j+1}[cols >= block r] += h_j[block r] . W^T  (tcgen05), epilogue tanh(block r of j+1)
+//   PUSH nh-1 -> out: out[ranks >= r] += h_last[block r] . Wout^T, epilogue = inverse transform of rank r
+// Biases are added in the epilogues from the layer-constants block, so accumulators need no init pass: the first
+// push into each accumulator (stage 0, or stage 1 for unconditional flows) covers its full width with accumulate = 0.
 bool build_inverse(const FlowGeom& g, TcPlan& P) {
   if (g.inv_mode != NAZB_INV_INCREMENTAL) return false;
   const int nh = g.n_hidden, D = g.D, Mp = P.mp;
-  if (D * Mp > 256) return false;
+  if (D * Mp > 256 || g.kin > 16) return false;
   auto hp = [&](int j) { return ceil_to(g.hidden[j], 16); };
-  // TMEM plan: persistent pre-activation accumulators of hidden layers 1.., the output accumulators,
-  // and a transient block accumulator for the pulled first layer.
   int col = 0;
   int T_PRE[NAZB_MAX_HIDDEN_LAYERS] = {0};
   for (int j = 1; j < nh; ++j) { T_PRE[j] = col; col += hp(j); }
   const int T_OUT = col; col += D * Mp;
-  const int T_TMP = col;
-  int tmp_w = 0;
+  if (col > kTmemCols) return false;
+  // layer constants
+  P.kinp = ceil_to(g.kin, 4);
+  int off = hp(0) * P.kinp;
+  for (int j = 0; j < nh; ++j) { P.lc_b[j] = off; off += hp(j); }
+  P.lc_bout = off; off += D * Mp;
+  P.lc_floats = ceil_to(off, 4);
   for (int r = 0; r < D; ++r) {
-    int b0 = g.blk[0][r], b1 = g.blk[0][r + 1];
-    bool empty0 = (b1 == b0);
+    bool empty0 = (g.blk[0][r + 1] == g.blk[0][r]);
     for (int j = 1; j < nh; ++j)
       if ((g.blk[j][r + 1] == g.blk[j][r]) != empty0) return false;   // blocks must be (non)empty together
-    if (!empty0) tmp_w = std::max(tmp_w, ceil_to(ceil_to(b1, 8) - (b0 & ~7), 16));
   }
-  if (T_TMP + tmp_w > kTmemCols) return false;
   Builder b{P.steps[0], P.images[0]};
-  const int kin = g.kin, kp = P.kin_pad;
-  for (int j = 1; j < nh; ++j)
-    b.gemm(A_IN, 0, kp, hp(j), T_PRE[j], 2, 0, mk_img(j, hp(j), kp, 0, 0, 0, 0, 0, 0, 0, kin, 1), mk_epi(EPI_NONE, 0));
-  b.gemm(A_IN, 0, kp, D * Mp, T_OUT, 2, 0, mk_img(nh, D * Mp, kp, 1, 0, 0, D, 0, 0, 0, kin, 1), mk_epi(EPI_NONE, 0));
+  bool first_push[NAZB_MAX_LIN];
+  for (int j = 0; j <= nh; ++j) first_push[j] = true;
   for (int r = 0; r < D; ++r) {
     int b0 = g.blk[0][r], b1 = g.blk[0][r + 1];
     if (b1 == b0) {
-      b.epi_only(mk_epi(EPI_XINV, T_OUT + r * Mp, 0, 0, r));
+      Step e = mk_epi(EPI_XINV, T_OUT + r * Mp, 0, 0, r);
+      e.flags = 1; e.e_aux = (uint16_t)(P.lc_bout + r * Mp);
+      b.epi_only(e);
       continue;
     }
-    int ec0 = b0 & ~7, ec1 = ceil_to(b1, 8);
-    int n1 = ceil_to(ec1 - ec0, 16);
-    if (ec0 + n1 > 65535) return false;
-    b.gemm(A_IN, 0, kp, n1, T_TMP, 3, 0, mk_img(0, n1, kp, 0, ec0, 0, 0, 0, 0, kin, kin, 0),
-           mk_epi(EPI_TANH, T_TMP, ec1 - ec0, 0));
-    for (int j = 0; j + 1 < nh; ++j) {
-      int sb0 = g.blk[j][r], sb1 = g.blk[j][r + 1];
-      int sc0 = sb0 & ~7, sc1 = ceil_to(sb1, 8);
-      int kr = ceil_to(sc1 - sc0, 16);
-      int tn0 = g.blk[j + 1][r] & ~15;
-      int n = hp(j + 1) - tn0;
-      int tb0 = g.blk[j + 1][r], tb1 = g.blk[j + 1][r + 1];
-      int tc0 = tb0 & ~7, tc1 = ceil_to(tb1, 8);
-      if (kr > P.hp_max) return false;
-      b.gemm(A_H, 0, kr, n, T_PRE[j + 1] + tn0, 3, 1, mk_img(j + 1, n, kr, 0, tn0, 0, 0, sc0, sb0, sb1, -1, 0),
-             mk_epi(EPI_TANH, T_PRE[j + 1] + tc0, tc1 - tc0, 0));
-    }
     {
-      int j = nh - 1;
+      int ec0 = b0 & ~7, ec1 = ceil_to(b1, 8);
+      Step e = mk_epi(EPI_FIRST, 0, ec1 - ec0, 0, r);
+      e.e_aux = (uint16_t)ec0;
+      b.epi_only(e);
+    }
+    for (int j = 0; j < nh; ++j) {
       int sb0 = g.blk[j][r], sb1 = g.blk[j][r + 1];
       int sc0 = sb0 & ~7, sc1 = ceil_to(sb1, 8);
       int kr = ceil_to(sc1 - sc0, 16);
       if (kr > P.hp_max) return false;
-      int n = (D - r) * Mp;
-      b.gemm(A_H, 0, kr, n, T_OUT + r * Mp, 3, 1, mk_img(nh, n, kr, 1, 0, r, D, sc0, sb0, sb1, -1, 0),
-             mk_epi(EPI_XINV, T_OUT + r * Mp, 0, 0, r));
+      if (j + 1 < nh) {
+        int tn0 = g.blk[j + 1][r] & ~15;
+        int n = hp(j + 1) - tn0;
+        int tb0 = g.blk[j + 1][r], tb1 = g.blk[j + 1][r + 1];
+        int tc0 = tb0 & ~7, tc1 = ceil_to(tb1, 8);
+        if (first_push[j + 1] && tn0 != 0) return false;
+        Step e = mk_epi(EPI_TANH, T_PRE[j + 1] + tc0, tc1 - tc0, 0);
+        e.e_aux = (uint16_t)(P.lc_b[j + 1] + tc0);
+        b.gemm(A_H, 0, kr, n, T_PRE[j + 1] + tn0, 3, first_push[j + 1] ? 0 : 1,
+               mk_img(j + 1, n, kr, 0, tn0, 0, 0, sc0, sb0, sb1, -1, 0), e);
+        first_push[j + 1] = false;
+      } else {
+        int n = (D - r) * Mp;
+        Step e = mk_epi(EPI_XINV, T_OUT + r * Mp, 0, 0, r);
+        e.e_aux = (uint16_t)(P.lc_bout + r * Mp);
+        b.gemm(A_H, 0, kr, n, T_OUT + r * Mp, 3, first_push[nh] ? 0 : 1, mk_img(nh, n, kr, 1, 0, r, D, sc0, sb0, sb1, -1, 0), e);
+        first_push[nh] = false;
+      }
     }
   }
   P.layer_bytes[0] = b.w_off;
@@ -277,6 +311,25 @@ bool plan_smem(const FlowGeom& g, TcPlan& P) {
   if (off + 2 * kSlotBytes > cap) return false;
   P.nslots = std::min(6u, (cap - off) / kSlotBytes);
   P.smem_bytes = off + (size_t)P.nslots * kSlotBytes;
+  return true;
+}
+
+bool plan_smem_inv(const FlowGeom& g, TcPlan& P) {
+  uint32_t off = 1024;
+  P.i_xin = off;     off += (uint32_t)ceil_to(g.kin, 4) * kTileM * 4;      // [kin][128] fp32: ctx rows then x rows
+  P.i_lc = off;      off += 2u * (uint32_t)P.lc_floats * 4;
+  off = (off + 127) & ~127u;
+  P.i_h = off;       off += (uint32_t)P.hp_max * kTileM * 2 * 2;
+  P.i_y = off;       off += (uint32_t)g.D * kTileM * 4;
+  P.i_xo = off;      off += (uint32_t)g.D * kTileM * 4;
+  P.i_misc = off;    off += kTileM * 4;
+  P.i_scratch = off; off += (g.kind == NAZB_KIND_AFFINE || (g.kind == NAZB_KIND_RQS && g.K == 8)) ? 0 : 32u * kTileM * 4;
+  off = (off + 127) & ~127u;
+  P.i_ring = off;
+  const uint32_t cap = 227 * 1024;
+  if (off + 2 * kSlotBytes > cap) return false;
+  P.i_nslots = std::min(6u, (cap - off) / kSlotBytes);
+  P.i_smem_bytes = off + (size_t)P.i_nslots * kSlotBytes;
   return true;
 }
 
@@ -804,6 +857,461 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const __grid_const
 }
 
 
+
+// ------------------------------------------------------------------------------------------------
+// Layer-constants pack kernel (v2 inverse): fp32 [W0 masked (Hp0 x kinp) | hidden biases | output bias rank-major]
+// ------------------------------------------------------------------------------------------------
+struct LcGeom { int lc_b[NAZB_MAX_HIDDEN_LAYERS]; int hdim[NAZB_MAX_HIDDEN_LAYERS]; };
+__global__ void tc_pack_lc_kernel(int S, int L, int n_lin, int D, int M, int Mp, int kin, int kinp, int hp0, int h0,
+                                  int lc_floats, LcGeom lg, int lc_bout,
+                                  const float* const* __restrict__ Wtab, const float* const* __restrict__ btab,
+                                  const float* const* __restrict__ mtab, const long long* __restrict__ wst,
+                                  const long long* __restrict__ bst, const int* __restrict__ perm, float* __restrict__ dst) {
+  const long long total = (long long)S * L * lc_floats;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int f = (int)(idx % lc_floats);
+    int l = (int)((idx / lc_floats) % L);
+    int s = (int)(idx / ((long long)lc_floats * L));
+    float v = 0.f;
+    if (f < hp0 * kinp) {
+      int n = f / kinp, k = f % kinp;
+      if (n < h0 && k < kin) {
+        int ti = l * n_lin;
+        v = Wtab[ti][(size_t)s * wst[ti] + (size_t)n * kin + k] * mtab[ti][(size_t)n * kin + k];
+      }
+    } else if (f < lc_bout) {
+      int j = 0;
+      while (j + 1 < n_lin - 1 && f >= lg.lc_b[j + 1]) ++j;
+      int n = f - lg.lc_b[j];
+      if (n < lg.hdim[j]) { int ti = l * n_lin + j; v = btab[ti][(size_t)s * bst[ti] + n]; }
+    } else if (f < lc_bout + D * Mp) {
+      int n = f - lc_bout, rank = n / Mp, m = n % Mp;
+      if (m < M) { int ti = l * n_lin + (n_lin - 1); v = btab[ti][(size_t)s * bst[ti] + m * D + perm[l * D + rank]]; }
+    }
+    dst[idx] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// v2 inverse kernel: two self-issuing 64-row chains (8 warps each) + 1 TMA producer warp.
+//
+// An M = 64 tcgen05.mma writes its rows to lanes 0-15 of each 32-lane TMEM quadrant, and a lane offset of
+// 16 in the D address selects lanes 16-31 (probed: tools/tc_probe_m64.cu).  The 128-point tile is therefore
+// run as TWO independent 64-row sub-tiles ("chains") that share every TMEM column, the weight ring and the
+// layer constants, but have their own A-operand buffers, barriers and dependency chain: while one chain
+// sits in its MMA / barrier latency the other one owns the MUFU and issue slots.
+// ------------------------------------------------------------------------------------------------
+constexpr int kChains = 2;
+constexpr int kChainWarps = kEpiWarps / kChains;      // 8
+constexpr int kChainThreads = kChainWarps * 32;       // 256
+constexpr int kChainRows = kTileM / kChains;          // 64
+constexpr int kInvThreads = kEpiThreads + 32;
+__device__ __forceinline__ void chain_sync(int c) { asm volatile("bar.sync %0, %1;\n" ::"r"(1 + c), "n"(kChainThreads) : "memory"); }
+
+#define DBGI(slot)                                                                       \
+  if (p.dbg && blockIdx.x == 0 && dbg_i < 128) p.dbg[dbg_i * 16 + (slot)] = clk();
+
+// per chunks of 8 columns: PER loads per thread, the two half-warps PER chunks apart
+template <int PER>
+__device__ __forceinline__ void ld_chunks(uint32_t taddr, uint32_t* r) {
+#pragma unroll
+  for (int j = 0; j < PER; ++j) tcx::tmem_ld16x2_8<PER * 8>(taddr + j * 8, r + 8 * j);
+}
+
+// First conditioner layer on CUDA cores for one work item = (pair of rows, chunk of 8 units).
+template <int KINP>
+__device__ __forceinline__ void first_layer_item(const float* __restrict__ lc, int lc_b0, const float* __restrict__ xin,
+                                                 int kin, int n0, int trow, uint32_t* ra, uint32_t* rb) {
+  float xa[KINP], xb[KINP];
+#pragma unroll
+  for (int k = 0; k < KINP; ++k) {
+    float2 v = (k < kin) ? *reinterpret_cast<const float2*>(xin + k * kTileM + trow) : make_float2(0.f, 0.f);
+    xa[k] = v.x; xb[k] = v.y;
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int n = n0 + e;
+    const float4* wr = reinterpret_cast<const float4*>(lc + (size_t)n * KINP);
+    float a0 = lc[lc_b0 + n], a1 = a0;
+#pragma unroll
+    for (int k4 = 0; k4 < KINP / 4; ++k4) {
+      float4 w = wr[k4];
+      a0 = fmaf(w.x, xa[k4 * 4 + 0], a0); a1 = fmaf(w.x, xb[k4 * 4 + 0], a1);
+      a0 = fmaf(w.y, xa[k4 * 4 + 1], a0); a1 = fmaf(w.y, xb[k4 * 4 + 1], a1);
+      a0 = fmaf(w.z, xa[k4 * 4 + 2], a0); a1 = fmaf(w.z, xb[k4 * 4 + 2], a1);
+      a0 = fmaf(w.w, xa[k4 * 4 + 3], a0); a1 = fmaf(w.w, xb[k4 * 4 + 3], a1);
+    }
+    ra[e] = __float_as_uint(a0); rb[e] = __float_as_uint(a1);
+  }
+}
+
+__global__ void __launch_bounds__(kInvThreads, 1) flow_tc_inv_kernel(const __grid_constant__ KParamsInv p,
+                                                                      const __grid_constant__ IoArgs io, int n_groups) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem);          // [nslots]
+  uint64_t* bar_empty = bar_full + 8;                               // [nslots], count = kChains
+  uint64_t* bar_acc = bar_empty + 8;                                // [kChains] MMA -> epilogue
+  uint64_t* lc_full = bar_acc + kChains;                            // [2]
+  uint64_t* lc_empty = lc_full + 2;                                 // [2], count = kChains
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lc_empty + 2);
+  float* xin = reinterpret_cast<float*>(smem + p.off_xin);          // [kin][128]: ctx rows, then x rows
+  float* lcs = reinterpret_cast<float*>(smem + p.off_lc);           // [2][lc_floats]
+  float* ycur = reinterpret_cast<float*>(smem + p.off_y);           // [D][128]
+  float* xorig = reinterpret_cast<float*>(smem + p.off_xo);         // [D][128]
+  float* ljac = reinterpret_cast<float*>(smem + p.off_misc);        // [128]
+  float* scratch = reinterpret_cast<float*>(smem + p.off_scratch);  // [32][128] (generic spline only)
+  uint8_t* ring = smem + p.off_ring;
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int D = p.D, C = p.C, M = p.M;
+
+  if (tid == 0) {
+    for (int i = 0; i < p.nslots; ++i) { tcx::mbar_init(bar_full + i, 1); tcx::mbar_init(bar_empty + i, kChains); }
+    for (int i = 0; i < kChains; ++i) tcx::mbar_init(bar_acc + i, 1);
+    for (int i = 0; i < 2; ++i) { tcx::mbar_init(lc_full + i, 1); tcx::mbar_init(lc_empty + i, kChains); }
+    tcx::mbar_fence_init();
+  }
+  if (warp == 0) tcx::tmem_alloc(tmem_slot, kTmemCols);
+  for (uint32_t i = tid; i < ((uint32_t)p.hp_max * kTileM * 4) / 16; i += kInvThreads)
+    reinterpret_cast<uint4*>(smem + p.off_h)[i] = make_uint4(0, 0, 0, 0);
+  tcx::fence_async_smem();
+  tcx::tc_fence_before();
+  __syncthreads();
+  tcx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const int n_tiles = (io.N + kTileM - 1) / kTileM;
+  const long long n_items = (long long)n_tiles * n_groups;
+
+  if (warp == kEpiWarps) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t cnt = 0, lcnt = 0;
+      for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int grp = (int)(item / n_tiles);
+        for (int si = grp; si < io.s_count; si += n_groups) {
+          const uint8_t* wdraw = p.wimg + (size_t)(io.s_begin + si) * p.draw_bytes;
+          const float* lcdraw = p.lc + (size_t)(io.s_begin + si) * p.L * p.lc_floats;
+          for (int li = 0; li < p.L; ++li) {
+            const int l = p.L - 1 - li;
+            {
+              const uint32_t b = lcnt & 1, use = lcnt >> 1;
+              tcx::mbar_wait(lc_empty + b, (use & 1) ^ 1);
+              tcx::mbar_expect_tx(lc_full + b, (uint32_t)p.lc_floats * 4);
+              tcx::bulk_g2s(lcs + (size_t)b * p.lc_floats, lcdraw + (size_t)l * p.lc_floats, (uint32_t)p.lc_floats * 4, lc_full + b);
+              ++lcnt;
+            }
+            const uint8_t* wl = wdraw + (size_t)l * p.layer_bytes;
+            for (int st = 0; st < p.nsteps; ++st) {
+              const uint32_t wb = p.steps[st].w_bytes;
+              if (wb == 0) continue;
+              const uint32_t slot = cnt % p.nslots, use = cnt / p.nslots;
+              tcx::mbar_wait(bar_empty + slot, (use & 1) ^ 1);
+              tcx::mbar_expect_tx(bar_full + slot, wb);
+              tcx::bulk_g2s(ring + (size_t)slot * kSlotBytes, wl + p.steps[st].w_off, wb, bar_full + slot);
+              ++cnt;
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== chain warps: MMA issue (first warp of the chain) + epilogues (all) =====================
+    const int ch = warp / kChainWarps, wq = warp % kChainWarps;
+    const int q = wq & 3, part = wq >> 2;          // TMEM quadrant, column part (2 parts x 2 half-warps = 4 column groups)
+    const int hw = lane >> 4, lr = lane & 15;
+    const int grp4 = part * 2 + hw;                // column group 0..3
+    const int crow = q * 16 + lr;                  // row inside the chain's 64-row sub-tile
+    const int trow = ch * kChainRows + crow;       // row inside the 128-point tile
+    const int ctid = tid - ch * kChainThreads;     // thread index inside the chain
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32 + ch * 16) << 16);
+    const uint32_t elected = tcx::elect_one();
+    const bool spline = p.kind != NAZB_KIND_AFFINE;
+    const bool fast_rqs = (p.kind == NAZB_KIND_RQS && p.K == 8);
+    const bool row_owner = (grp4 == 0);
+    float* scr = scratch + trow;
+    auto raw = [&](int m) { return scr[m * kTileM]; };
+    auto setw = [&](int m, float v) { scr[m * kTileM] = v; };
+    // this chain's A operand: [hi | lo][K-chunk][64 rows][8 halves]
+    __half* h_hi = reinterpret_cast<__half*>(smem + p.off_h) + (size_t)ch * 2 * p.hp_max * kChainRows;
+    __half* h_lo = h_hi + (size_t)p.hp_max * kChainRows;
+    const uint32_t h_hi_a = tcx::smem_u32(h_hi), h_lo_a = tcx::smem_u32(h_lo), ring_a = tcx::smem_u32(ring);
+    constexpr uint32_t lbo_a = kChainRows * 16;
+    constexpr uint64_t dhi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;   // SBO = 128 B, descriptor version 1
+    uint64_t* my_acc = bar_acc + ch;
+    uint32_t slot = 0, use = 0, par_acc = 0, lcnt = 0;
+    int dbg_i = 0;
+    const bool dbg_me = (tid == 0);
+
+    // start the second chain half a step late so the two chains' MUFU bursts and MMA / barrier latencies interleave
+    if (ch == 1) { const long long t0 = clk(); while (clk() - t0 < p.phase_delay) { } }
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int tile = (int)(item % n_tiles), grp = (int)(item / n_tiles);
+      const int n0 = tile * kTileM;
+      const int npts = min(kTileM, io.N - n0);
+      float run_m = -INFINITY, run_s = 0.f;
+      // ---- tile load: this chain's 64 rows ----
+      chain_sync(ch);
+      for (int i = ctid; i < kChainRows * C; i += kChainThreads) {
+        int pt = ch * kChainRows + i / C, c = i % C;
+        float v = 0.f;
+        if (pt < npts) v = io.ctx[((io.ctx_rows == 1) ? 0 : (size_t)(n0 + pt)) * C + c];
+        xin[c * kTileM + pt] = v;
+      }
+      for (int i = ctid; i < kChainRows * D; i += kChainThreads) {
+        int pt = ch * kChainRows + i / D, d = i % D;
+        xorig[d * kTileM + pt] = (pt < npts) ? io.x[(size_t)(n0 + pt) * D + d] : 0.f;
+      }
+      chain_sync(ch);
+      if (row_owner) {
+        float lj = 0.f;
+        if (io.lo != nullptr && trow < npts)
+          for (int d = 0; d < D; ++d) xorig[d * kTileM + trow] = nazb::bound_fwd(xorig[d * kTileM + trow], io.lo[d], io.hi[d], lj);
+        ljac[trow] = lj;
+      }
+
+      for (int si = grp; si < io.s_count; si += n_groups) {
+        // ---- draw start ----
+        for (uint32_t i = ctid; i < ((uint32_t)p.hp_max * kChainRows * 4) / 16; i += kChainThreads)
+          reinterpret_cast<uint4*>(h_hi)[i] = make_uint4(0, 0, 0, 0);
+        float ld_acc = 0.f;
+        if (row_owner)
+          for (int d = 0; d < D; ++d) {
+            ycur[d * kTileM + trow] = xorig[d * kTileM + trow];
+            xin[(C + d) * kTileM + trow] = 0.f;
+          }
+        tcx::fence_async_smem();
+        chain_sync(ch);
+
+        for (int li = 0; li < p.L; ++li) {
+          const int l = p.L - 1 - li;
+          const int* perm = p.perm + l * D;
+          const float* lc = lcs + (size_t)(lcnt & 1) * p.lc_floats;
+          tcx::mbar_wait(lc_full + (lcnt & 1), (lcnt >> 1) & 1);
+          for (int st = 0; st < p.nsteps; ++st) {
+            struct { uint32_t epi, e_col, e_ncols, e_aux, stage, flags; } s;
+            s.epi = p.steps[st].epi; s.e_col = p.steps[st].e_col; s.e_ncols = p.steps[st].e_ncols;
+            s.e_aux = p.steps[st].e_aux; s.stage = p.steps[st].stage; s.flags = p.steps[st].flags;
+            const uint32_t s_wbytes = p.steps[st].w_bytes;
+            if (s_wbytes) {
+              if (wq == 0) {
+                // ---- MMA issue (chain leader warp, convergent; tcgen05 instructions predicated on the elected lane) ----
+                const uint32_t s_n = p.steps[st].n, s_dcol = p.steps[st].d_col;
+                const int ksteps = p.steps[st].ksteps;
+                const uint32_t s_acc = p.steps[st].accumulate;
+                const uint32_t idesc = tcx::make_idesc_f16_m64(s_n);
+                const uint32_t lbo_b = s_n * 16;
+                const uint32_t b_hi = ring_a + slot * kSlotBytes, b_lo = b_hi + (s_wbytes >> 1);
+                const uint32_t a_off = (uint32_t)p.steps[st].a_chunk0 * lbo_a;
+                const uint32_t da_hi0 = ((h_hi_a + a_off) >> 4) | ((lbo_a >> 4) << 16);
+                const uint32_t da_lo0 = ((h_lo_a + a_off) >> 4) | ((lbo_a >> 4) << 16);
+                const uint32_t db_hi0 = (b_hi >> 4) | ((lbo_b >> 4) << 16), db_lo0 = (b_lo >> 4) | ((lbo_b >> 4) << 16);
+                const uint32_t da_step = (2 * lbo_a) >> 4, db_step = (2 * lbo_b) >> 4;
+                const uint32_t d_addr = tmem + ((uint32_t)(ch * 16) << 16) + s_dcol;
+                if (dbg_me) { DBGI(0) }
+                tcx::mbar_wait(bar_full + slot, use & 1);
+                tcx::tc_fence_after();
+                if (dbg_me) { DBGI(1) }
+                uint32_t da = da_hi0, db = db_hi0;
+#pragma unroll 4
+                for (int k = 0; k < ksteps; ++k) {            // a_hi * w_hi
+                  tcx::mma_f16_ss_elect(d_addr, dhi | da, dhi | db, idesc, (k == 0) ? s_acc : 1u, elected);
+                  da += da_step; db += db_step;
+                }
+                da = da_hi0; db = db_lo0;
+#pragma unroll 4
+                for (int k = 0; k < ksteps; ++k) {            // a_hi * w_lo
+                  tcx::mma_f16_ss_elect(d_addr, dhi | da, dhi | db, idesc, 1u, elected);
+                  da += da_step; db += db_step;
+                }
+                da = da_lo0; db = db_hi0;
+#pragma unroll 4
+                for (int k = 0; k < ksteps; ++k) {            // a_lo * w_hi
+                  tcx::mma_f16_ss_elect(d_addr, dhi | da, dhi | db, idesc, 1u, elected);
+                  da += da_step; db += db_step;
+                }
+                tcx::mma_commit_elect(bar_empty + slot, elected);
+                if (s.epi != EPI_NONE) tcx::mma_commit_elect(my_acc, elected);
+                if (dbg_me) { DBGI(2) }
+              }
+              if (++slot == (uint32_t)p.nslots) { slot = 0; ++use; }
+              if (s.epi == EPI_NONE) { ++dbg_i; continue; }   // K-split sub-step: the next sub-step's MMAs queue right behind
+              tcx::mbar_wait(my_acc, par_acc);
+              par_acc ^= 1;
+              tcx::tc_fence_after();
+            }
+            if (dbg_me) { DBGI(3) }
+            if (s.epi == EPI_TANH) {
+              const int nchunks = s.e_ncols >> 3;
+              const int per = (nchunks + 3) >> 2;            // chunks per column group
+              uint32_t r[40];
+              const uint32_t ta = lane_base + s.e_col + (uint32_t)(part * 2 * per) * 8;
+              switch (per) {
+                case 1: ld_chunks<1>(ta, r); break;
+                case 2: ld_chunks<2>(ta, r); break;
+                case 3: ld_chunks<3>(ta, r); break;
+                case 4: ld_chunks<4>(ta, r); break;
+                default: ld_chunks<5>(ta, r); break;
+              }
+              const int c0 = grp4 * per;
+              tcx::tmem_ld_wait();
+              if (dbg_me) { DBGI(4) }
+#pragma unroll
+              for (int u = 0; u < 5; ++u) {
+                const int c = c0 + u;
+                if (u < per && c < nchunks) {
+                  const float4* bv = reinterpret_cast<const float4*>(lc + s.e_aux + c * 8);
+                  float4 b0 = bv[0], b1 = bv[1];
+                  uint32_t* ru = r + 8 * u;
+                  ru[0] = __float_as_uint(__uint_as_float(ru[0]) + b0.x); ru[1] = __float_as_uint(__uint_as_float(ru[1]) + b0.y);
+                  ru[2] = __float_as_uint(__uint_as_float(ru[2]) + b0.z); ru[3] = __float_as_uint(__uint_as_float(ru[3]) + b0.w);
+                  ru[4] = __float_as_uint(__uint_as_float(ru[4]) + b1.x); ru[5] = __float_as_uint(__uint_as_float(ru[5]) + b1.y);
+                  ru[6] = __float_as_uint(__uint_as_float(ru[6]) + b1.z); ru[7] = __float_as_uint(__uint_as_float(ru[7]) + b1.w);
+                  uint4 hi4, lo4;
+                  if (dbg_me && u == 0) { DBGI(8) }
+                  tanh_chunk(ru, hi4, lo4);
+                  if (dbg_me && u == 0) { if (hi4.x == 0x12345678u) p.dbg[0] = 1; DBGI(9) }
+                  const size_t o = ((size_t)c * kChainRows + crow) * 8;
+                  *reinterpret_cast<uint4*>(h_hi + o) = hi4;
+                  *reinterpret_cast<uint4*>(h_lo + o) = lo4;
+                  if (dbg_me && u == 0) { DBGI(10) }
+                }
+              }
+            } else if (s.epi == EPI_FIRST) {
+              // work item = (pair of rows of this chain, chunk of 8 hidden units)
+              const int nchunks = s.e_ncols >> 3;
+              const int u0 = s.e_aux;
+              for (int it = ctid; it < nchunks * (kChainRows / 2); it += kChainThreads) {
+                const int c = it / (kChainRows / 2), r2 = (it % (kChainRows / 2)) * 2;
+                uint32_t ra[8], rb[8];
+                switch (p.kinp) {
+                  case 4: first_layer_item<4>(lc, p.lc_b0, xin, p.kin, u0 + c * 8, ch * kChainRows + r2, ra, rb); break;
+                  case 8: first_layer_item<8>(lc, p.lc_b0, xin, p.kin, u0 + c * 8, ch * kChainRows + r2, ra, rb); break;
+                  case 12: first_layer_item<12>(lc, p.lc_b0, xin, p.kin, u0 + c * 8, ch * kChainRows + r2, ra, rb); break;
+                  default: first_layer_item<16>(lc, p.lc_b0, xin, p.kin, u0 + c * 8, ch * kChainRows + r2, ra, rb); break;
+                }
+                uint4 hi4, lo4;
+                const size_t o = ((size_t)c * kChainRows + r2) * 8;
+                tanh_chunk(ra, hi4, lo4);
+                *reinterpret_cast<uint4*>(h_hi + o) = hi4;
+                *reinterpret_cast<uint4*>(h_lo + o) = lo4;
+                tanh_chunk(rb, hi4, lo4);
+                *reinterpret_cast<uint4*>(h_hi + o + 8) = hi4;
+                *reinterpret_cast<uint4*>(h_lo + o + 8) = lo4;
+              }
+            } else if (s.epi == EPI_XINV) {
+              if (part == 0) {   // warp-uniform; inside, lanes 0-15 own the 16 rows of this quadrant
+                const int r = s.stage, d = perm[r];
+                const float yv = ycur[d * kTileM + trow];
+                const float* bo = lc + s.e_aux;
+                const bool has_acc = !(s.flags & 1);
+                float xv = 0.f, ld = 0.f;
+                if (!spline) {
+                  uint32_t rr[2] = {0u, 0u};
+                  if (has_acc) { tcx::tmem_ld16x2_2<0>(lane_base + s.e_col, rr); tcx::tmem_ld_wait(); }
+                  float mu = __uint_as_float(rr[0]) + bo[0];
+                  float sc = fminf(fmaxf(__uint_as_float(rr[1]) + bo[1], p.clip_lo), p.clip_hi);
+                  xv = (yv - mu) * expf(-sc);
+                  ld = sc;
+                } else if (fast_rqs) {
+                  uint32_t rr[24];
+#pragma unroll
+                  for (int e = 0; e < 24; ++e) rr[e] = 0u;
+                  if (has_acc) {
+                    tcx::tmem_ld16x2_8<0>(lane_base + s.e_col, rr);
+                    tcx::tmem_ld16x2_8<0>(lane_base + s.e_col + 8, rr + 8);
+                    tcx::tmem_ld16x2_8<0>(lane_base + s.e_col + 16, rr + 16);
+                    tcx::tmem_ld_wait();
+                  }
+                  if (hw == 0) {
+                    float rf[24];
+#pragma unroll
+                    for (int e = 0; e < 24; ++e) rf[e] = __uint_as_float(rr[e]) + bo[e];
+                    nazb::rqs_fast<8>(yv, p.bound, true, rf, xv, ld);
+                  }
+                } else {
+                  for (int m0 = 0; m0 < p.Mp; m0 += 8) {
+                    uint32_t rr[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) rr[e] = 0u;
+                    if (has_acc) { tcx::tmem_ld16x2_8<0>(lane_base + s.e_col + m0, rr); tcx::tmem_ld_wait(); }
+                    if (hw == 0) {
+#pragma unroll
+                      for (int e = 0; e < 8; ++e)
+                        if (m0 + e < M) scr[(m0 + e) * kTileM] = __uint_as_float(rr[e]) + bo[m0 + e];
+                    }
+                  }
+                  if (hw == 0) {
+                    if (p.kind == NAZB_KIND_RQS) nazb::rational_spline<false>(yv, p.K, p.bound, true, raw, setw, xv, ld);
+                    else nazb::rational_spline<true>(yv, p.K, p.bound, true, raw, setw, xv, ld);
+                  }
+                }
+                if (hw == 0) {
+                  ld_acc += ld;
+                  xin[(C + d) * kTileM + trow] = xv;
+                  if (r == D - 1) {
+                    // end of this flow layer: x becomes the y of the next (earlier) layer, x restarts at 0
+                    for (int dd = 0; dd < D; ++dd) {
+                      ycur[dd * kTileM + trow] = xin[(C + dd) * kTileM + trow];
+                      xin[(C + dd) * kTileM + trow] = 0.f;
+                    }
+                  }
+                }
+              }
+            }
+            if (dbg_me) { DBGI(5) }
+            tcx::tc_fence_before();
+            tcx::fence_async_smem();
+            chain_sync(ch);
+            if (dbg_me) { DBGI(6) }
+            ++dbg_i;
+          }
+          // this layer's constants are no longer needed by this chain
+          if (ctid == 0) tcx::mbar_arrive(lc_empty + (lcnt & 1));
+          ++lcnt;
+        }
+
+        // ---- draw end ----
+        if (part == 0) {
+          float lp = 0.f;
+          const bool mine = row_owner && trow < npts;
+          if (row_owner) {
+            float qd = 0.f;
+            for (int d = 0; d < D; ++d) { float z = ycur[d * kTileM + trow]; qd += 0.5f * z * z; }
+            lp = -qd - 0.5f * D * NAZB_LOG_2PI - ld_acc + ljac[trow];
+          }
+          if (mine) {
+            if (io.out_l) io.out_l[(size_t)si * io.N + n0 + trow] = lp;
+            if (io.lse_max) {
+              float v = lp + (io.log_w ? io.log_w[si] : 0.f);
+              if (!(v <= run_m)) { run_s = run_s * expf(run_m - v) + 1.f; run_m = v; }
+              else if (v > -INFINITY) run_s += expf(v - run_m);
+            }
+            if (io.out_x) {
+              float* dst = io.out_x + ((size_t)si * io.N + n0 + trow) * D;
+              for (int d = 0; d < D; ++d) dst[d] = ycur[d * kTileM + trow];
+            }
+          }
+          if (io.sum_n) {
+            double v = mine ? (double)lp : 0.0;
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) atomicAdd(io.sum_n + si, v);
+          }
+        }
+      }
+      if (io.lse_max && row_owner && trow < npts) {
+        io.lse_max[(size_t)grp * io.N + n0 + trow] = run_m;
+        io.lse_sum[(size_t)grp * io.N + n0 + trow] = run_s;
+      }
+    }
+  }
+  tcx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tcx::tmem_dealloc(tmem, kTmemCols);
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -835,6 +1343,7 @@ void nazb_tc_destroy(nazb_handle* h) {
     if (t->steps_dev[d]) cudaFree(t->steps_dev[d]);
   }
   if (t->tab_dev) cudaFree(t->tab_dev);
+  if (t->lc_dev) cudaFree(t->lc_dev);
   delete t;
   h->tc = nullptr;
 }
@@ -842,7 +1351,7 @@ void nazb_tc_destroy(nazb_handle* h) {
 int64_t nazb_tc_packed_bytes(const nazb_handle* h) {
   const TcState* t = static_cast<const TcState*>(h->tc);
   if (!t) return 0;
-  return (int64_t)h->desc.S * (int64_t)(t->draw_bytes[0] + t->draw_bytes[1]);
+  return (int64_t)h->desc.S * (int64_t)(t->draw_bytes[0] + t->draw_bytes[1] + (t->lc_dev ? sizeof(float) * (size_t)h->geom.L * t->plan.lc_floats : 0));
 }
 
 bool nazb_tc_direction_ok(const nazb_handle* h, int dir) {
@@ -860,7 +1369,7 @@ cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* con
   TcPlan P;
   if (!base_dims(g, P) || !plan_smem(g, P)) return cudaErrorInvalidConfiguration;
   P.ok[1] = build_forward(g, P);
-  P.ok[0] = build_inverse(g, P);
+  P.ok[0] = build_inverse(g, P) && plan_smem_inv(g, P);
   if (!P.ok[0]) { P.steps[0].clear(); P.images[0].clear(); P.layer_bytes[0] = 0; }
   if (!P.ok[1]) return cudaErrorInvalidConfiguration;
   cudaError_t e;
@@ -905,6 +1414,18 @@ cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* con
       nazb_count_launch();
     }
   }
+  if (t->lc_dev) { cudaFree(t->lc_dev); t->lc_dev = nullptr; }
+  if (P.ok[0]) {
+    if ((e = cudaMalloc(&t->lc_dev, sizeof(float) * (size_t)S * L * P.lc_floats)) != cudaSuccess) return e;
+    LcGeom lg{};
+    for (int j = 0; j < g.n_hidden; ++j) { lg.lc_b[j] = P.lc_b[j]; lg.hdim[j] = g.hidden[j]; }
+    long long total = (long long)S * L * P.lc_floats;
+    int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
+    tc_pack_lc_kernel<<<blocks, 256, 0, st>>>(S, L, n_lin, g.D, g.M, P.mp, g.kin, P.kinp, ceil_to(g.hidden[0], 16), g.hidden[0],
+                                              P.lc_floats, lg, P.lc_bout, t->tab_dev, t->tab_dev + ntab, t->tab_dev + 2 * ntab,
+                                              strides_dev, strides_dev + ntab, h->perm_dev, t->lc_dev);
+    nazb_count_launch();
+  }
   t->plan = P;
   return cudaGetLastError();
 }
@@ -915,6 +1436,32 @@ cudaError_t nazb_tc_launch(const nazb_handle* h, const IoArgs& io, int n_groups,
   const TcPlan& P = t->plan;
   const int d = io.dir;
   if (!P.ok[d]) return cudaErrorNotSupported;
+  if (d == 0) {
+    KParamsInv kp{};
+    kp.dbg = g_tc_dbg;
+    kp.nsteps = (int)P.steps[0].size();
+    for (int i = 0; i < kp.nsteps; ++i) kp.steps[i] = P.steps[0][i];
+    kp.wimg = t->wimg[0];
+    kp.draw_bytes = t->draw_bytes[0];
+    kp.layer_bytes = P.layer_bytes[0];
+    kp.lc = t->lc_dev; kp.lc_floats = P.lc_floats; kp.lc_b0 = P.lc_b[0];
+    kp.phase_delay = 0;
+    if (const char* env = getenv("NAZB_PHASE_DELAY")) kp.phase_delay = atoi(env);
+    kp.perm = h->perm_dev;
+    kp.D = g.D; kp.C = g.C; kp.L = g.L; kp.M = g.M; kp.Mp = P.mp; kp.K = g.K; kp.kind = g.kind; kp.kin = g.kin;
+    kp.kinp = P.kinp; kp.hp_max = P.hp_max; kp.nslots = P.i_nslots;
+    kp.bound = g.bound; kp.clip_lo = g.clip_lo; kp.clip_hi = g.clip_hi;
+    kp.off_xin = P.i_xin; kp.off_lc = P.i_lc; kp.off_h = P.i_h; kp.off_y = P.i_y; kp.off_xo = P.i_xo;
+    kp.off_misc = P.i_misc; kp.off_scratch = P.i_scratch; kp.off_ring = P.i_ring;
+    cudaError_t e = cudaFuncSetAttribute(flow_tc_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.i_smem_bytes);
+    if (e != cudaSuccess) return e;
+    const int n_tiles = (io.N + kTileM - 1) / kTileM;
+    long long items = (long long)n_tiles * n_groups;
+    int grid = (int)std::min<long long>(items, h->sm_count);
+    flow_tc_inv_kernel<<<grid, kInvThreads, P.i_smem_bytes, st>>>(kp, io, n_groups);
+    nazb_count_launch();
+    return cudaGetLastError();
+  }
   KParams kp{};
   kp.dbg = g_tc_dbg;
   kp.nsteps = (int)P.steps[d].size();

@@ -135,6 +135,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
 }
 
+// 16 lanes x 8 columns, twice: threads 0-15 get lanes base..base+15 at columns [col, col+8), threads 16-31 the
+// same lanes at columns [col+IMM, col+IMM+8)  (probed on B200: tools/tc_probe_ld16.cu).
+template <int IMM>
+__device__ __forceinline__ void tmem_ld16x2_8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.16x32bx2.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr), "n"(IMM));
+}
+template <int IMM>
+__device__ __forceinline__ void tmem_ld16x2_2(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.16x32bx2.x2.b32 {%0,%1}, [%2], %3;\n" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr), "n"(IMM));
+}
+// Instruction descriptor for kind::f16, A = B = fp16, D = fp32, both K-major, M = 64.
+__device__ __forceinline__ uint32_t make_idesc_f16_m64(uint32_t n) {
+  return (1u << 4) | ((n >> 3) << 17) | ((64u >> 4) << 24);
+}
+
 // Arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");

@@ -20,11 +20,11 @@ MAX_VIOL = 0.01
 WORST = 20.0
 
 
-def check(got, ref, what, max_viol=MAX_VIOL, worst=WORST):
+def check(got, ref, what, max_viol=MAX_VIOL, worst=WORST, atol=1e-5):
     if isinstance(got, torch.Tensor):
         got = got.detach().cpu().numpy()
     assert np.isfinite(got).all(), f"{what}: non-finite output"
-    viol, w = tol_report(got, ref)
+    viol, w = tol_report(got, ref, atol=atol)
     assert viol <= max_viol and w <= worst, f"{what}: {viol:.4%} outside 1e-4/1e-5, worst {w:.1f}x tolerance"
 
 
@@ -65,7 +65,9 @@ def test_log_prob_and_sample_match_oracle(shape, engine):
     xs, ld = eng.forward(T(zin), T(ctx), want_logdet=True)
     xs_ref, ld_ref = fo.sample_draws(spec, to64(draws), zin.astype(np.float64), None if ctx is None else ctx.astype(np.float64))
     check(xs, xs_ref, "samples")
-    check(ld, ld_ref, "forward log-det", max_viol=0.03)
+    # auxiliary output (not part of the north-star tolerance): a sum of L*D signed O(1) terms that often cancels to
+    # ~0, where the relative part of the tolerance vanishes; checked at atol 1e-4 (the fp32 oracle itself needs that)
+    check(ld, ld_ref, "forward log-det", atol=1e-4)
 
 
 @pytest.mark.parametrize("name", GOLDEN)
@@ -80,7 +82,7 @@ def test_golden_fixtures(name, engine):
     check(out["z"], g["z"], "z")
     xs, ld = eng.forward(T(g["zin"].astype(np.float32)), ctx, bounds, want_logdet=True)
     check(xs, g["xs"], "samples")
-    check(ld, g["ld"], "ld")
+    check(ld, g["ld"], "ld", atol=1e-4)
 
 
 def test_incremental_equals_reference_d_pass_schedule():

@@ -14,7 +14,7 @@ L = _lib.lib()
 prog = (C.c_int * (8*64))()
 L.nazb_debug_program.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_int]
 nsteps = L.nazb_debug_program(eng._h, 0 if direction == "inverse" else 1, prog, 8*64)
-buf = torch.zeros(256*8, dtype=torch.int64, device="cuda")
+buf = torch.zeros(256*16, dtype=torch.int64, device="cuda")
 def run():
     if direction == "inverse": eng.inverse(x, ctx, want_lp=False, want_lse=True, n_groups=1)
     else: eng.forward(x, ctx)
@@ -23,9 +23,25 @@ L.nazb_debug_set_clock_buffer.argtypes = [C.c_void_p]
 L.nazb_debug_set_clock_buffer(buf.data_ptr())
 run(); torch.cuda.synchronize()
 L.nazb_debug_set_clock_buffer(None)
-t = buf.cpu().numpy().reshape(256, 8)
+t = buf.cpu().numpy().reshape(256, 8) if direction != "inverse" else buf.cpu().numpy().reshape(256, 16)
 t0 = t[0, 0]
 names = {0: "none", 1: "tanh", 2: "xinv", 3: "xfwd"}
+print("step  n ks sp epi ncols wKB | v2 inverse: wait_w issue acc_wait | epi_work sync | total")
+names = {0: "none", 1: "tanh", 2: "xinv", 3: "xfwd", 4: "first"}
+if direction == "inverse":
+    for i in range(min(2*nsteps, 127)):
+        s = i % nsteps
+        n, ks, sp, epi, ncols, wb, dcol, abuf = [prog[s*8+j] for j in range(8)]
+        m0, m1, m2, m3, e4, e5, e6, e7 = t[i][:8]
+        x8, x9, x10 = t[i][8:11]
+        prev_end = t[i-1, 6] if i > 0 else m0
+        if wb:
+            extra = f"  ld {e4-m3:5d} bias {x8-e4:4d} tanh {x9-x8:4d} st {x10-x9:4d} rest {e5-x10:5d}" if epi == 1 else ""
+            print(f"{i:3d} {n:4d} {ks:2d} {sp:1d} {names[epi]:5s} {ncols:3d} {wb/1024:5.1f} | {m1-m0:6d} {m2-m1:6d} {m3-m2:6d} | {e5-m3:6d} {e6-e5:5d} | {e6-prev_end:6d}" + extra)
+        else:
+            print(f"{i:3d} {n:4d} {ks:2d} {sp:1d} {names[epi]:5s} {ncols:3d} {wb/1024:5.1f} | {'':6s} {'':6s} {'':6s} | {e5-m3:6d} {e6-e5:5d} | {e6-prev_end:6d}")
+    print("two layers:", t[2*nsteps-1, 6] - t[0, 3], "cycles")
+    sys.exit(0)
 print("step  n ks sp epi ncols wKB | mma: wait_a  wait_w  issue | epi: wait_acc(after mma issue)  work  signal | step_total")
 for i in range(min(2*nsteps, 255)):
     s = i % nsteps
