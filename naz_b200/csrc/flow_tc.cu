@@ -1170,13 +1170,10 @@ __global__ void __launch_bounds__(kInvThreads, 1) flow_tc_inv_kernel(const __gri
                   ru[4] = __float_as_uint(__uint_as_float(ru[4]) + b1.x); ru[5] = __float_as_uint(__uint_as_float(ru[5]) + b1.y);
                   ru[6] = __float_as_uint(__uint_as_float(ru[6]) + b1.z); ru[7] = __float_as_uint(__uint_as_float(ru[7]) + b1.w);
                   uint4 hi4, lo4;
-                  if (dbg_me && u == 0) { DBGI(8) }
                   tanh_chunk(ru, hi4, lo4);
-                  if (dbg_me && u == 0) { if (hi4.x == 0x12345678u) p.dbg[0] = 1; DBGI(9) }
                   const size_t o = ((size_t)c * kChainRows + crow) * 8;
                   *reinterpret_cast<uint4*>(h_hi + o) = hi4;
                   *reinterpret_cast<uint4*>(h_lo + o) = lo4;
-                  if (dbg_me && u == 0) { DBGI(10) }
                 }
               }
             } else if (s.epi == EPI_FIRST) {
