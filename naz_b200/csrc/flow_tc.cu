@@ -36,7 +36,7 @@ constexpr int kEpiWarps = 16;   // 4 per TMEM lane quadrant; the column range of
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kParts = kEpiWarps / 4;
 constexpr int kThreads = (kEpiWarps + 2) * 32;
-constexpr int kSlotBytes = 32768;
+constexpr int kSlotBytes = 40960;
 constexpr int kTmemCols = 512;
 
 enum : uint8_t { EPI_NONE = 0, EPI_TANH = 1, EPI_XINV = 2, EPI_XFWD = 3, EPI_FIRST = 4 };
