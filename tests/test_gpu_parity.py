@@ -290,3 +290,76 @@ def test_reference_python_api_drop_in():
     mref, _ = fo.sample_draws(mspec, mparams, zz.cpu().numpy().astype(np.float64), ctx[0].astype(np.float64),
                               keep=keep.numpy().astype(np.float64), p_drop=0.25)
     check(arr, mref, "sample_uncertain")
+
+
+def test_full_size_cfg4_importance_evidence():
+    """cfg 4 at BASELINE size (256 draws x 1M points, MAF 2|2): sum_n lp per draw, importance log-evidence and ESS.
+    Oracle check on a 2000-point slice; whole-set check through additivity of the per-draw sums over point shards."""
+    from naz_b200 import importance
+    S, N = 256, 1_000_000
+    spec, draws, _, rng = make_case("maf", 2, 2, [150] * 3, 16, S, seed=3, scale=0.02)
+    eng = engine_for(spec, draws)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn((N, 2), device="cuda", generator=g) * 1.5
+    grid = torch.rand((19, 2), device="cuda", generator=g)
+    ctx = grid[torch.randint(0, 19, (N,), device="cuda", generator=g)]
+    full = eng.inverse(x, ctx, want_lp=False, want_sum=True)["sum_n"]
+    a = eng.inverse(x[:400_000], ctx[:400_000], want_lp=False, want_sum=True)["sum_n"]
+    b = eng.inverse(x[400_000:], ctx[400_000:], want_lp=False, want_sum=True)["sum_n"]
+    assert torch.allclose(a + b, full, rtol=1e-9, atol=1e-3)
+    sl = slice(0, 2000)
+    lp = eng.inverse(x[sl], ctx[sl], want_lp=True, s_begin=0, s_count=4)["lp"]
+    lp_ref, _ = fo.log_prob_draws(spec, [[(W[:4].astype(np.float64), bb[:4].astype(np.float64)) for (W, bb) in layer] for layer in draws],
+                                  x[sl].cpu().numpy().astype(np.float64), ctx[sl].cpu().numpy().astype(np.float64))
+    check(lp, lp_ref, "cfg4 lp slice")
+    lw, logz, ess, mx = importance(full)
+    lw_ref, logz_ref, ess_ref = fo.importance(full.cpu().numpy(), np.zeros(S), np.zeros(S))
+    assert abs(float(logz) - logz_ref) <= 1e-9 * abs(logz_ref) and abs(float(ess) - ess_ref) <= 1e-6 * ess_ref
+    assert 1.0 <= float(ess) <= S
+
+
+def test_full_size_cfg5_sampling_sweep():
+    """cfg 5: 1000 draws x 10k samples, conditional 8|4 MAF on tcgen05 and 16|4 (inverse served by SIMT): sampling,
+    then log_prob of the samples recovers the base noise (encode -> decode round trip) on a subset of draws."""
+    for D in (8, 16):
+        S, N = 1000, 10_000
+        spec, draws, _, rng = make_case("maf", D, 4, [150] * 3, 16, S, seed=4, scale=0.1)
+        eng = engine_for(spec, draws)
+        assert eng.engine_for("forward") == "tcgen05"
+        g = torch.Generator(device="cuda").manual_seed(2)
+        z = torch.randn((S, N, D), device="cuda", generator=g)
+        ctx = torch.tensor([0.2, 0.4, 0.6, 0.8])
+        x = eng.forward(z, ctx)
+        assert x.shape == (S, N, D) and torch.isfinite(x).all()
+        for s in (0, 499, 999):
+            out = eng.inverse(x[s], ctx, want_z=True, want_lp=False, s_begin=s, s_count=1)
+            err = (out["z"][0] - z[s]).abs()
+            assert (err > 2e-3 * (1 + z[s].abs())).float().mean().item() < 2e-3
+        # oracle on one draw, 300 samples
+        s = 7
+        one = [[(W[s:s + 1].astype(np.float64), b[s:s + 1].astype(np.float64)) for (W, b) in layer] for layer in draws]
+        ref, _ = fo.sample_draws(spec, one, z[s:s + 1, :300].cpu().numpy().astype(np.float64), ctx.numpy().astype(np.float64))
+        check(x[s:s + 1, :300], ref, f"cfg5 D={D} samples")
+
+
+def test_full_size_cfg2_mc_dropout():
+    """cfg 2: one weight set, 100 dropout masks x 100k points, 6|4 MAF: posterior-predictive log-density over the masks;
+    oracle on a slice, draw-shard additivity on the whole set."""
+    S, N, p = 100, 100_000, 0.25
+    spec, draws, keep, rng = make_case("maf", 6, 4, [150] * 3, 16, S, seed=1, dropout_p=p)
+    from naz_b200 import FlowEngine, FlowShape
+    shared = [[(T(W[0]), T(b[0])) for (W, b) in layer] for layer in draws]
+    eng = FlowEngine(FlowShape("maf", 6, 4, [150] * 3, 16), S, device="cuda:0")
+    eng.pack(shared, [[T(m) for m in ml] for ml in spec.masks()], T(spec.perms), T(keep), p)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = (torch.randn((N, 6), device="cuda", generator=g) * 1.5).clamp(-5.9, 5.9)
+    ctx = torch.rand((N, 4), device="cuda", generator=g)
+    out = eng.inverse(x, ctx, want_lp=False, want_lse=True, n_groups=1)
+    ppd = eng.lse_finish(out["lse_max"], out["lse_sum"], -math.log(S))
+    parts = [eng.inverse(x, ctx, want_lp=False, want_lse=True, n_groups=1, s_begin=b, s_count=e - b) for b, e in ((0, 13), (13, 100))]
+    merged = eng.lse_finish(torch.cat([q["lse_max"] for q in parts]), torch.cat([q["lse_sum"] for q in parts]), -math.log(S))
+    assert torch.allclose(ppd, merged, rtol=1e-5, atol=1e-5)
+    sl = slice(0, 256)
+    lp_ref, _ = fo.log_prob_draws(spec, to64(draws), x[sl].cpu().numpy().astype(np.float64), ctx[sl].cpu().numpy().astype(np.float64),
+                                  keep=keep.astype(np.float64), p_drop=p)
+    check(ppd[sl], fo.posterior_predictive(lp_ref), "cfg2 posterior predictive over masks")
