@@ -130,7 +130,7 @@ struct Builder {
   uint32_t w_off = 0;
   void gemm(uint8_t a_buf, int a_chunk0, int k_ext, int n_ext, int d_col, int nsplit, int accumulate, Image im,
             Step epi) {
-    int k_sub_max = (kSlotBytes / (n_ext * 4)) / 16 * 16;
+    int k_sub_max = std::min(96, (kSlotBytes / (n_ext * 4)) / 16 * 16);
     for (int k_off = 0; k_off < k_ext; k_off += k_sub_max) {
       int ks = std::min(k_sub_max, k_ext - k_off);
       bool last = (k_off + ks >= k_ext);
@@ -1114,24 +1114,20 @@ __global__ void __launch_bounds__(kInvThreads, 1) flow_tc_inv_kernel(const __gri
                 tcx::mbar_wait(bar_full + slot, use & 1);
                 tcx::tc_fence_after();
                 if (dbg_me) { DBGI(1) }
-                uint32_t da = da_hi0, db = db_hi0;
-#pragma unroll 4
-                for (int k = 0; k < ksteps; ++k) {            // a_hi * w_hi
-                  tcx::mma_f16_ss_elect(d_addr, dhi | da, dhi | db, idesc, (k == 0) ? s_acc : 1u, elected);
-                  da += da_step; db += db_step;
-                }
-                da = da_hi0; db = db_lo0;
-#pragma unroll 4
-                for (int k = 0; k < ksteps; ++k) {            // a_hi * w_lo
-                  tcx::mma_f16_ss_elect(d_addr, dhi | da, dhi | db, idesc, 1u, elected);
-                  da += da_step; db += db_step;
-                }
-                da = da_lo0; db = db_hi0;
-#pragma unroll 4
-                for (int k = 0; k < ksteps; ++k) {            // a_lo * w_hi
-                  tcx::mma_f16_ss_elect(d_addr, dhi | da, dhi | db, idesc, 1u, elected);
-                  da += da_step; db += db_step;
-                }
+                // independent descriptor per MMA (no loop-carried uniform-register chain), fully unrolled
+#pragma unroll
+                for (int k = 0; k < 6; ++k)                   // a_hi * w_hi
+                  if (k < ksteps)
+                    tcx::mma_f16_ss_elect(d_addr, dhi | (da_hi0 + k * da_step), dhi | (db_hi0 + k * db_step), idesc,
+                                          (k == 0) ? s_acc : 1u, elected);
+#pragma unroll
+                for (int k = 0; k < 6; ++k)                   // a_hi * w_lo
+                  if (k < ksteps)
+                    tcx::mma_f16_ss_elect(d_addr, dhi | (da_hi0 + k * da_step), dhi | (db_lo0 + k * db_step), idesc, 1u, elected);
+#pragma unroll
+                for (int k = 0; k < 6; ++k)                   // a_lo * w_hi
+                  if (k < ksteps)
+                    tcx::mma_f16_ss_elect(d_addr, dhi | (da_lo0 + k * da_step), dhi | (db_hi0 + k * db_step), idesc, 1u, elected);
                 tcx::mma_commit_elect(bar_empty + slot, elected);
                 if (s.epi != EPI_NONE) tcx::mma_commit_elect(my_acc, elected);
                 if (dbg_me) { DBGI(2) }
