@@ -54,6 +54,7 @@ struct Step {
   uint16_t e_col, e_ncols, e_dst_chunk;
   uint16_t e_aux;   // v2 inverse: TANH / XINV -> float offset of the bias of column e_col inside the layer
                     // constants; FIRST -> first hidden unit of the block
+  uint16_t n_crit;  // inverse pushes: the first n_crit image rows (the columns of block r) are the critical part
 };
 
 struct Image {          // how the pack kernel fills one step's weight image
@@ -79,6 +80,12 @@ struct TcPlan {
   uint32_t i_xin = 0, i_lc = 0, i_h = 0, i_y = 0, i_xo = 0, i_misc = 0, i_scratch = 0, i_ring = 0;
   int i_nslots = 0;
   size_t i_smem_bytes = 0;
+  // v3 inverse kernel: double-buffered A blocks of kr_max columns per chain
+  int kr_max = 0;
+  bool v3_ok = false;
+  uint32_t j_xin = 0, j_lc = 0, j_a = 0, j_y = 0, j_xo = 0, j_misc = 0, j_scratch = 0, j_ring = 0;
+  int j_nslots = 0;
+  size_t j_smem_bytes = 0;
 };
 
 struct TcState {
@@ -115,6 +122,7 @@ struct KParamsInv {
   int phase_delay;
   const int* perm;
   int D, C, L, M, Mp, K, kind, kin, kinp, hp_max, nslots;
+  int kr_max;                      // v3: columns of one A block buffer
   float bound, clip_lo, clip_hi;
   uint32_t off_xin, off_lc, off_h, off_y, off_xo, off_misc, off_scratch, off_ring;
 };
@@ -129,7 +137,7 @@ struct Builder {
   std::vector<Image>& images;
   uint32_t w_off = 0;
   void gemm(uint8_t a_buf, int a_chunk0, int k_ext, int n_ext, int d_col, int nsplit, int accumulate, Image im,
-            Step epi) {
+            Step epi, int n_crit = 0) {
     int k_sub_max = std::min(96, (kSlotBytes / (n_ext * 4)) / 16 * 16);
     for (int k_off = 0; k_off < k_ext; k_off += k_sub_max) {
       int ks = std::min(k_sub_max, k_ext - k_off);
@@ -144,6 +152,7 @@ struct Builder {
       s.d_col = (uint16_t)d_col;
       s.nsplit = (uint8_t)nsplit;
       s.accumulate = (uint8_t)((k_off > 0) ? 1 : accumulate);
+      s.n_crit = (uint16_t)(n_crit > 0 ? n_crit : n_ext);
       if (last) {
         s.epi = epi.epi; s.stage = epi.stage; s.nranks = epi.nranks; s.flags = epi.flags; s.e_aux = epi.e_aux;
         s.e_col = epi.e_col; s.e_ncols = epi.e_ncols; s.e_dst_chunk = epi.e_dst_chunk;
@@ -271,22 +280,23 @@ bool build_inverse(const FlowGeom& g, TcPlan& P) {
       int sc0 = sb0 & ~7, sc1 = ceil_to(sb1, 8);
       int kr = ceil_to(sc1 - sc0, 16);
       if (kr > P.hp_max) return false;
+      P.kr_max = std::max(P.kr_max, kr);
       if (j + 1 < nh) {
-        int tn0 = g.blk[j + 1][r] & ~15;
-        int n = hp(j + 1) - tn0;
         int tb0 = g.blk[j + 1][r], tb1 = g.blk[j + 1][r + 1];
         int tc0 = tb0 & ~7, tc1 = ceil_to(tb1, 8);
+        int tn0 = tc0;                         // M = 64 MMAs take any N % 8 == 0
+        int n = hp(j + 1) - tn0;
         if (first_push[j + 1] && tn0 != 0) return false;
         Step e = mk_epi(EPI_TANH, T_PRE[j + 1] + tc0, tc1 - tc0, 0);
         e.e_aux = (uint16_t)(P.lc_b[j + 1] + tc0);
         b.gemm(A_H, 0, kr, n, T_PRE[j + 1] + tn0, 3, first_push[j + 1] ? 0 : 1,
-               mk_img(j + 1, n, kr, 0, tn0, 0, 0, sc0, sb0, sb1, -1, 0), e);
+               mk_img(j + 1, n, kr, 0, tn0, 0, 0, sc0, sb0, sb1, -1, 0), e, tc1 - tc0);
         first_push[j + 1] = false;
       } else {
         int n = (D - r) * Mp;
         Step e = mk_epi(EPI_XINV, T_OUT + r * Mp, 0, 0, r);
         e.e_aux = (uint16_t)(P.lc_bout + r * Mp);
-        b.gemm(A_H, 0, kr, n, T_OUT + r * Mp, 3, first_push[nh] ? 0 : 1, mk_img(nh, n, kr, 1, 0, r, D, sc0, sb0, sb1, -1, 0), e);
+        b.gemm(A_H, 0, kr, n, T_OUT + r * Mp, 3, first_push[nh] ? 0 : 1, mk_img(nh, n, kr, 1, 0, r, D, sc0, sb0, sb1, -1, 0), e, Mp);
         first_push[nh] = false;
       }
     }
@@ -330,6 +340,26 @@ bool plan_smem_inv(const FlowGeom& g, TcPlan& P) {
   if (off + 2 * kSlotBytes > cap) return false;
   P.i_nslots = std::min(6u, (cap - off) / kSlotBytes);
   P.i_smem_bytes = off + (size_t)P.i_nslots * kSlotBytes;
+  return true;
+}
+
+bool plan_smem_inv3(const FlowGeom& g, TcPlan& P) {
+  if (P.kr_max <= 0 || P.kr_max > 128) return false;      // <= kV3MaxSlices K slices per A block
+  uint32_t off = 1024;
+  P.j_xin = off;     off += (uint32_t)ceil_to(g.kin, 4) * kTileM * 4;
+  P.j_lc = off;      off += 2u * (uint32_t)P.lc_floats * 4;
+  off = (off + 127) & ~127u;
+  P.j_a = off;       off += 2u * 2u * (uint32_t)P.kr_max * (kTileM / 2) * 2 * 2;   // [chain][buffer][hi | lo]
+  P.j_y = off;       off += (uint32_t)g.D * kTileM * 4;
+  P.j_xo = off;      off += (uint32_t)g.D * kTileM * 4;
+  P.j_misc = off;    off += kTileM * 4;
+  P.j_scratch = off; off += (g.kind == NAZB_KIND_AFFINE || (g.kind == NAZB_KIND_RQS && g.K == 8)) ? 0 : 32u * kTileM * 4;
+  off = (off + 127) & ~127u;
+  P.j_ring = off;
+  const uint32_t cap = 227 * 1024;
+  if (off + 2 * kSlotBytes > cap) return false;
+  P.j_nslots = std::min(6u, (cap - off) / kSlotBytes);
+  P.j_smem_bytes = off + (size_t)P.j_nslots * kSlotBytes;
   return true;
 }
 
@@ -1305,6 +1335,8 @@ __global__ void __launch_bounds__(kInvThreads, 1) flow_tc_inv_kernel(const __gri
   if (warp == 0) tcx::tmem_dealloc(tmem, kTmemCols);
 }
 
+#include "flow_tc_inv3.cuh"
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -1363,6 +1395,7 @@ cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* con
   if (!base_dims(g, P) || !plan_smem(g, P)) return cudaErrorInvalidConfiguration;
   P.ok[1] = build_forward(g, P);
   P.ok[0] = build_inverse(g, P) && plan_smem_inv(g, P);
+  P.v3_ok = P.ok[0] && plan_smem_inv3(g, P);
   if (!P.ok[0]) { P.steps[0].clear(); P.images[0].clear(); P.layer_bytes[0] = 0; }
   if (!P.ok[1]) return cudaErrorInvalidConfiguration;
   cudaError_t e;
@@ -1446,6 +1479,19 @@ cudaError_t nazb_tc_launch(const nazb_handle* h, const IoArgs& io, int n_groups,
     kp.bound = g.bound; kp.clip_lo = g.clip_lo; kp.clip_hi = g.clip_hi;
     kp.off_xin = P.i_xin; kp.off_lc = P.i_lc; kp.off_h = P.i_h; kp.off_y = P.i_y; kp.off_xo = P.i_xo;
     kp.off_misc = P.i_misc; kp.off_scratch = P.i_scratch; kp.off_ring = P.i_ring;
+    const char* v2env = getenv("NAZB_INV_V2");
+    if (P.v3_ok && !(v2env && atoi(v2env))) {
+      kp.kr_max = P.kr_max; kp.nslots = P.j_nslots;
+      kp.off_xin = P.j_xin; kp.off_lc = P.j_lc; kp.off_h = P.j_a; kp.off_y = P.j_y; kp.off_xo = P.j_xo;
+      kp.off_misc = P.j_misc; kp.off_scratch = P.j_scratch; kp.off_ring = P.j_ring;
+      cudaError_t e3 = cudaFuncSetAttribute(flow_tc_inv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.j_smem_bytes);
+      if (e3 != cudaSuccess) return e3;
+      const int n_tiles3 = (io.N + kTileM - 1) / kTileM;
+      int grid3 = (int)std::min<long long>((long long)n_tiles3 * n_groups, h->sm_count);
+      flow_tc_inv3_kernel<<<grid3, kV3Threads, P.j_smem_bytes, st>>>(kp, io, n_groups);
+      nazb_count_launch();
+      return cudaGetLastError();
+    }
     cudaError_t e = cudaFuncSetAttribute(flow_tc_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.i_smem_bytes);
     if (e != cudaSuccess) return e;
     const int n_tiles = (io.N + kTileM - 1) / kTileM;

@@ -1,0 +1,448 @@
+// v3 inverse (`log_prob` direction) kernel of the tcgen05 engine.  Included by flow_tc.cu inside its
+// anonymous namespace (it shares Step / KParamsInv / IoArgs and the helpers defined there).
+//
+// Same mathematics and the same weight images as the v2 kernel (push-style incremental inverse, two 64-row
+// chains per 128-point tile, accumulators resident in TMEM for a whole flow layer); what changes is the
+// hand-off structure, which is what bounded v2 (16 bar.sync-separated phases per flow layer, each 2.5-3 k cycles):
+//
+//   * A chain is 4 epilogue warps (one per TMEM lane quadrant); a warp owns its 16 rows of the chain for
+//     EVERY phase, two threads per row (the two half-warps take alternate 8-column chunks via
+//     tcgen05.ld.16x32bx2).  Spline -> first conditioner layer of the next stage is therefore warp-local
+//     (__syncwarp), and no block-level barrier is left anywhere in the steady state.
+//   * Each chain has its own MMA-issuer warp.  The A operand (fp16 hi/lo of the activations of one MADE
+//     block) is produced in 16-column K slices; every slice has its own mbarrier, and the issuer fires the
+//     slice's MMAs as soon as the slice lands, so MMA issue + execution of all but the last slice hides
+//     under the tanh of the following slices.
+//   * A push h_j[block r] -> pre_{j+1}[columns >= block r] is split into the CRITICAL part (the columns of
+//     block r, which the next epilogue needs: committed to the accumulator barrier) and the DEFERRED part
+//     (all later columns), issued after the commit so it overlaps the next epilogue.
+//   * A operand blocks are double-buffered; the in-order tensor pipe makes two buffers sufficient
+//     (the writer of block p+2 starts after the commit of push p+1, which retires after every MMA of push p).
+#pragma once
+
+constexpr int kV3EpiWarps = 8;                       // 2 chains x 4 quadrants
+constexpr int kV3Issuer0 = kV3EpiWarps;              // warps 8, 9: MMA issuers of chain 0, 1
+constexpr int kV3Producer = kV3EpiWarps + kChains;   // warp 10: TMA producer
+constexpr int kV3Threads = (kV3EpiWarps + kChains + 1) * 32;
+constexpr int kV3MaxSlices = 8;                      // A block <= 128 columns
+
+#define DBG3(slot)                                                                       \
+  if (p.dbg && blockIdx.x == 0 && dbg_i < 128) p.dbg[dbg_i * 16 + (slot)] = clk();
+
+// First conditioner layer on CUDA cores: 8 hidden units (n0 .. n0+7) for ONE row whose inputs are in xv.
+template <int KINP>
+__device__ __forceinline__ void first_chunk(const float* __restrict__ lc, int lc_b0, const float* __restrict__ xin,
+                                            int kin, int trow, int n0, uint32_t* out) {
+  float xv[KINP];
+#pragma unroll
+  for (int k = 0; k < KINP; ++k) xv[k] = (k < kin) ? xin[k * kTileM + trow] : 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int n = n0 + e;
+    const float4* wr = reinterpret_cast<const float4*>(lc + (size_t)n * KINP);
+    float a = lc[lc_b0 + n];
+#pragma unroll
+    for (int k4 = 0; k4 < KINP / 4; ++k4) {
+      const float4 w = wr[k4];
+      a = fmaf(w.x, xv[k4 * 4 + 0], a);
+      a = fmaf(w.y, xv[k4 * 4 + 1], a);
+      a = fmaf(w.z, xv[k4 * 4 + 2], a);
+      a = fmaf(w.w, xv[k4 * 4 + 3], a);
+    }
+    out[e] = __float_as_uint(a);
+  }
+}
+
+__global__ void __launch_bounds__(kV3Threads, 1) flow_tc_inv3_kernel(const __grid_constant__ KParamsInv p,
+                                                                      const __grid_constant__ IoArgs io, int n_groups) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* w_full = reinterpret_cast<uint64_t*>(smem);            // [nslots] TMA -> issuers
+  uint64_t* w_empty = w_full + 8;                                   // [nslots] count = kChains (one commit per issuer)
+  uint64_t* bar_acc = w_empty + 8;                                  // [kChains] issuer -> epilogue warps
+  uint64_t* lc_full = bar_acc + kChains;                            // [2]
+  uint64_t* lc_empty = lc_full + 2;                                 // [2], count = kV3EpiWarps
+  uint64_t* a_ready = lc_empty + 2;                                 // [kChains][2 buffers][kV3MaxSlices], count = 4 warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + kChains * 2 * kV3MaxSlices);
+  float* xin = reinterpret_cast<float*>(smem + p.off_xin);          // [kin][128]: ctx rows, then x rows
+  float* lcs = reinterpret_cast<float*>(smem + p.off_lc);           // [2][lc_floats]
+  float* ycur = reinterpret_cast<float*>(smem + p.off_y);           // [D][128]
+  float* xorig = reinterpret_cast<float*>(smem + p.off_xo);         // [D][128]
+  float* ljac = reinterpret_cast<float*>(smem + p.off_misc);        // [128]
+  float* scratch = reinterpret_cast<float*>(smem + p.off_scratch);  // [32][128] (generic spline only)
+  uint8_t* ring = smem + p.off_ring;
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int D = p.D, C = p.C, M = p.M;
+  const uint32_t a_img_bytes = (uint32_t)p.kr_max * kChainRows * 2;   // one fp16 image (hi or lo) of an A block
+  const uint32_t a_buf_bytes = 2 * a_img_bytes;
+
+  if (tid == 0) {
+    for (int i = 0; i < p.nslots; ++i) { tcx::mbar_init(w_full + i, 1); tcx::mbar_init(w_empty + i, kChains); }
+    for (int i = 0; i < kChains; ++i) tcx::mbar_init(bar_acc + i, 1);
+    for (int i = 0; i < 2; ++i) { tcx::mbar_init(lc_full + i, 1); tcx::mbar_init(lc_empty + i, kV3EpiWarps); }
+    for (int i = 0; i < kChains * 2 * kV3MaxSlices; ++i) tcx::mbar_init(a_ready + i, 4);
+    tcx::mbar_fence_init();
+  }
+  if (warp == 0) tcx::tmem_alloc(tmem_slot, kTmemCols);
+  for (uint32_t i = tid; i < (kChains * 2 * a_buf_bytes) / 16; i += kV3Threads)
+    reinterpret_cast<uint4*>(smem + p.off_h)[i] = make_uint4(0, 0, 0, 0);
+  tcx::fence_async_smem();
+  tcx::tc_fence_before();
+  __syncthreads();
+  tcx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const int n_tiles = (io.N + kTileM - 1) / kTileM;
+  const long long n_items = (long long)n_tiles * n_groups;
+
+  if (warp == kV3Producer) {
+    // ===================== TMA producer: weight images + layer constants =====================
+    if (lane == 0) {
+      uint32_t cnt = 0, lcnt = 0;
+      for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int grp = (int)(item / n_tiles);
+        for (int si = grp; si < io.s_count; si += n_groups) {
+          const uint8_t* wdraw = p.wimg + (size_t)(io.s_begin + si) * p.draw_bytes;
+          const float* lcdraw = p.lc + (size_t)(io.s_begin + si) * p.L * p.lc_floats;
+          for (int li = 0; li < p.L; ++li) {
+            const int l = p.L - 1 - li;
+            {
+              const uint32_t b = lcnt & 1, use = lcnt >> 1;
+              tcx::mbar_wait(lc_empty + b, (use & 1) ^ 1);
+              tcx::mbar_expect_tx(lc_full + b, (uint32_t)p.lc_floats * 4);
+              tcx::bulk_g2s(lcs + (size_t)b * p.lc_floats, lcdraw + (size_t)l * p.lc_floats, (uint32_t)p.lc_floats * 4, lc_full + b);
+              ++lcnt;
+            }
+            const uint8_t* wl = wdraw + (size_t)l * p.layer_bytes;
+            for (int st = 0; st < p.nsteps; ++st) {
+              const uint32_t wb = p.steps[st].w_bytes;
+              if (wb == 0) continue;
+              const uint32_t slot = cnt % p.nslots, use = cnt / p.nslots;
+              tcx::mbar_wait(w_empty + slot, (use & 1) ^ 1);
+              tcx::mbar_expect_tx(w_full + slot, wb);
+              tcx::bulk_g2s(ring + (size_t)slot * kSlotBytes, wl + p.steps[st].w_off, wb, w_full + slot);
+              ++cnt;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp >= kV3Issuer0) {
+    // ===================== MMA issuer of chain `ch` =====================
+    // Whole warp convergent, tcgen05 instructions predicated on the elected lane (descriptors stay uniform).
+    const int ch = warp - kV3Issuer0;
+    const uint32_t elected = tcx::elect_one();
+    const uint32_t ring_a = tcx::smem_u32(ring);
+    const uint32_t a_base = tcx::smem_u32(smem + p.off_h) + (uint32_t)ch * 2 * a_buf_bytes;
+    constexpr uint32_t lbo_a = kChainRows * 16;
+    constexpr uint64_t dhi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;   // SBO = 128 B, descriptor version 1
+    const uint32_t d_lane = tmem + ((uint32_t)(ch * 16) << 16);
+    uint64_t* my_acc = bar_acc + ch;
+    uint64_t* my_ready = a_ready + ch * 2 * kV3MaxSlices;
+    uint32_t slot = 0, use = 0, buf = 0, apar = 0;   // apar: one parity bit per (buffer, slice) barrier
+    int dbg_i = 0;
+    const bool dbg_me = (ch == 0 && lane == 0);
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int grp = (int)(item / n_tiles);
+      for (int si = grp; si < io.s_count; si += n_groups) {
+        for (int li = 0; li < p.L; ++li) {
+          for (int st = 0; st < p.nsteps; ++st) {
+            const uint32_t s_wbytes = p.steps[st].w_bytes;
+            if (s_wbytes == 0) { ++dbg_i; continue; }
+            const uint32_t s_n = p.steps[st].n, s_ncrit = p.steps[st].n_crit, s_dcol = p.steps[st].d_col;
+            const int ksteps = p.steps[st].ksteps;
+            const uint32_t s_acc = p.steps[st].accumulate, s_last = (p.steps[st].epi != EPI_NONE);
+            const uint32_t slice0 = p.steps[st].a_chunk0 >> 1;
+            const uint32_t n_rest = s_n - s_ncrit;
+            const uint32_t idesc_c = tcx::make_idesc_f16_m64(s_ncrit);
+            const uint32_t idesc_r = tcx::make_idesc_f16_m64(n_rest);
+            const uint32_t lbo_b = s_n * 16;
+            const uint32_t b_hi = ring_a + slot * kSlotBytes, b_lo = b_hi + (s_wbytes >> 1);
+            const uint32_t lbo_b_hi16 = (lbo_b >> 4) << 16, lbo_a_hi16 = (lbo_a >> 4) << 16;
+            const uint32_t a_hi = a_base + buf * a_buf_bytes, a_lo = a_hi + a_img_bytes;
+            const uint32_t d_c = d_lane + s_dcol, d_r = d_c + s_ncrit;
+            const uint32_t rest_off = s_ncrit * 16;   // byte offset of image row n_crit
+            if (dbg_me) { DBG3(8) }
+            tcx::mbar_wait(w_full + slot, use & 1);
+            if (dbg_me) { DBG3(9) }
+            for (int k = 0; k < ksteps; ++k) {
+              const uint32_t sl = slice0 + k, bit = 1u << (buf * kV3MaxSlices + sl);
+              tcx::mbar_wait(my_ready + buf * kV3MaxSlices + sl, (apar & bit) ? 1u : 0u);
+              apar ^= bit;
+              tcx::tc_fence_after();
+              if (dbg_me && k == 0) { DBG3(10) }
+              const uint32_t ao = sl * 2 * lbo_a, bo = (uint32_t)k * 2 * lbo_b;
+              const uint64_t da_h = dhi | (((a_hi + ao) >> 4) | lbo_a_hi16), da_l = dhi | (((a_lo + ao) >> 4) | lbo_a_hi16);
+              const uint64_t db_h = dhi | (((b_hi + bo) >> 4) | lbo_b_hi16), db_l = dhi | (((b_lo + bo) >> 4) | lbo_b_hi16);
+              const uint32_t acc0 = (k == 0) ? s_acc : 1u;
+              // critical columns (block r): hi*hi + hi*lo + lo*hi
+              tcx::mma_f16_ss_elect(d_c, da_h, db_h, idesc_c, acc0, elected);
+              tcx::mma_f16_ss_elect(d_c, da_h, db_l, idesc_c, 1u, elected);
+              tcx::mma_f16_ss_elect(d_c, da_l, db_h, idesc_c, 1u, elected);
+              if (s_last && k == ksteps - 1) tcx::mma_commit_elect(my_acc, elected);
+              if (n_rest) {
+                const uint32_t ro = rest_off >> 4;
+                tcx::mma_f16_ss_elect(d_r, da_h, db_h + ro, idesc_r, acc0, elected);
+                tcx::mma_f16_ss_elect(d_r, da_h, db_l + ro, idesc_r, 1u, elected);
+                tcx::mma_f16_ss_elect(d_r, da_l, db_h + ro, idesc_r, 1u, elected);
+              }
+            }
+            tcx::mma_commit_elect(w_empty + slot, elected);   // the slot is free once these MMAs retire
+            if (dbg_me) { DBG3(11) }
+            if (++slot == (uint32_t)p.nslots) { slot = 0; ++use; }
+            if (s_last) buf ^= 1;
+            ++dbg_i;
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps: 4 per chain, one per TMEM lane quadrant =====================
+    const int ch = warp >> 2, q = warp & 3;
+    const int hw = lane >> 4, lr = lane & 15;
+    const int crow = q * 16 + lr;                  // row inside the chain's 64-row sub-tile
+    const int trow = ch * kChainRows + crow;       // row inside the 128-point tile
+    const int wrow0 = ch * kChainRows + q * 16;    // first tile row owned by this warp
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32 + ch * 16) << 16);
+    const bool spline = p.kind != NAZB_KIND_AFFINE;
+    const bool fast_rqs = (p.kind == NAZB_KIND_RQS && p.K == 8);
+    const bool owner = (hw == 0);
+    float* scr = scratch + trow;
+    auto raw = [&](int m) { return scr[m * kTileM]; };
+    auto setw = [&](int m, float v) { scr[m * kTileM] = v; };
+    uint8_t* a_chain = smem + p.off_h + (size_t)ch * 2 * a_buf_bytes;
+    uint64_t* my_acc = bar_acc + ch;
+    uint64_t* my_ready = a_ready + ch * 2 * kV3MaxSlices;
+    uint32_t par_acc = 0, lcnt = 0, buf = 0;
+    int dbg_i = 0;
+    const bool dbg_me = (tid == 0);
+
+    // publish one 16-column K slice of the A block under construction
+    auto publish = [&](int slice) {
+      tcx::fence_async_smem();
+      __syncwarp();
+      if (lane == 0) tcx::mbar_arrive(my_ready + buf * kV3MaxSlices + slice);
+    };
+    // write this thread's 8-column chunk `c` (hi / lo fp16) of the A block: layout [chunk][64 rows][8 halves]
+    auto store_chunk = [&](int c, const uint4& hi4, const uint4& lo4) {
+      uint8_t* dst = a_chain + (size_t)buf * a_buf_bytes + ((size_t)c * kChainRows + crow) * 16;
+      *reinterpret_cast<uint4*>(dst) = hi4;
+      *reinterpret_cast<uint4*>(dst + a_img_bytes) = lo4;
+    };
+
+    if (ch == 1 && p.phase_delay > 0) { const long long t0 = clk(); while (clk() - t0 < p.phase_delay) { } }
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int tile = (int)(item % n_tiles), grp = (int)(item / n_tiles);
+      const int n0 = tile * kTileM;
+      const int npts = min(kTileM, io.N - n0);
+      float run_m = -INFINITY, run_s = 0.f;
+      // ---- tile load: the 16 rows of this warp ----
+      __syncwarp();
+      for (int i = lane; i < 16 * C; i += 32) {
+        const int pt = wrow0 + i / C, c = i % C;
+        float v = 0.f;
+        if (pt < npts) v = io.ctx[((io.ctx_rows == 1) ? 0 : (size_t)(n0 + pt)) * C + c];
+        xin[c * kTileM + pt] = v;
+      }
+      for (int i = lane; i < 16 * D; i += 32) {
+        const int pt = wrow0 + i / D, d = i % D;
+        xorig[d * kTileM + pt] = (pt < npts) ? io.x[(size_t)(n0 + pt) * D + d] : 0.f;
+      }
+      __syncwarp();
+      if (owner) {
+        float lj = 0.f;
+        if (io.lo != nullptr && trow < npts)
+          for (int d = 0; d < D; ++d) xorig[d * kTileM + trow] = nazb::bound_fwd(xorig[d * kTileM + trow], io.lo[d], io.hi[d], lj);
+        ljac[trow] = lj;
+      }
+
+      for (int si = grp; si < io.s_count; si += n_groups) {
+        // ---- draw start ----
+        float ld_acc = 0.f;
+        if (owner)
+          for (int d = 0; d < D; ++d) {
+            ycur[d * kTileM + trow] = xorig[d * kTileM + trow];
+            xin[(C + d) * kTileM + trow] = 0.f;
+          }
+        __syncwarp();
+
+        for (int li = 0; li < p.L; ++li) {
+          const int l = p.L - 1 - li;
+          const int* perm = p.perm + l * D;
+          const float* lc = lcs + (size_t)(lcnt & 1) * p.lc_floats;
+          tcx::mbar_wait(lc_full + (lcnt & 1), (lcnt >> 1) & 1);
+          for (int st = 0; st < p.nsteps; ++st) {
+            const uint32_t s_epi = p.steps[st].epi;
+            if (s_epi == EPI_NONE) { ++dbg_i; continue; }   // K-split sub-step: nothing to do on this side
+            const uint32_t s_ecol = p.steps[st].e_col, s_encols = p.steps[st].e_ncols, s_eaux = p.steps[st].e_aux;
+            const uint32_t s_stage = p.steps[st].stage, s_flags = p.steps[st].flags;
+            if (dbg_me) { DBG3(0) }
+            if (p.steps[st].w_bytes) {
+              tcx::mbar_wait(my_acc, par_acc);
+              par_acc ^= 1;
+              tcx::tc_fence_after();
+            }
+            if (dbg_me) { DBG3(1) }
+            if (s_epi == EPI_TANH) {
+              const int nch = s_encols >> 3, nsl = (nch + 1) >> 1;
+              for (int sb = 0; sb < nsl; sb += 4) {
+                uint32_t r[32];
+                const int ns = min(4, nsl - sb);
+                const uint32_t ta = lane_base + s_ecol + sb * 16;
+                tcx::tmem_ld16x2_8<8>(ta, r);
+                if (ns > 1) tcx::tmem_ld16x2_8<8>(ta + 16, r + 8);
+                if (ns > 2) tcx::tmem_ld16x2_8<8>(ta + 32, r + 16);
+                if (ns > 3) tcx::tmem_ld16x2_8<8>(ta + 48, r + 24);
+                tcx::tmem_ld_wait();
+                tcx::tc_fence_before();
+                if (dbg_me && sb == 0) { DBG3(2) }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  if (u < ns) {
+                    const int c = (sb + u) * 2 + hw;
+                    uint4 hi4 = make_uint4(0, 0, 0, 0), lo4 = hi4;
+                    if (c < nch) {
+                      const float4* bv = reinterpret_cast<const float4*>(lc + s_eaux + c * 8);
+                      const float4 b0 = bv[0], b1 = bv[1];
+                      uint32_t* ru = r + 8 * u;
+                      ru[0] = __float_as_uint(__uint_as_float(ru[0]) + b0.x); ru[1] = __float_as_uint(__uint_as_float(ru[1]) + b0.y);
+                      ru[2] = __float_as_uint(__uint_as_float(ru[2]) + b0.z); ru[3] = __float_as_uint(__uint_as_float(ru[3]) + b0.w);
+                      ru[4] = __float_as_uint(__uint_as_float(ru[4]) + b1.x); ru[5] = __float_as_uint(__uint_as_float(ru[5]) + b1.y);
+                      ru[6] = __float_as_uint(__uint_as_float(ru[6]) + b1.z); ru[7] = __float_as_uint(__uint_as_float(ru[7]) + b1.w);
+                      tanh_chunk(ru, hi4, lo4);
+                    }
+                    store_chunk(c, hi4, lo4);
+                    publish(sb + u);
+                  }
+                }
+              }
+              buf ^= 1;
+            } else if (s_epi == EPI_FIRST) {
+              const int nch = s_encols >> 3, nsl = (nch + 1) >> 1;
+              const int u0 = s_eaux;
+              for (int sl = 0; sl < nsl; ++sl) {
+                const int c = sl * 2 + hw;
+                uint4 hi4 = make_uint4(0, 0, 0, 0), lo4 = hi4;
+                if (c < nch) {
+                  uint32_t ra[8];
+                  switch (p.kinp) {
+                    case 4: first_chunk<4>(lc, p.lc_b0, xin, p.kin, trow, u0 + c * 8, ra); break;
+                    case 8: first_chunk<8>(lc, p.lc_b0, xin, p.kin, trow, u0 + c * 8, ra); break;
+                    case 12: first_chunk<12>(lc, p.lc_b0, xin, p.kin, trow, u0 + c * 8, ra); break;
+                    default: first_chunk<16>(lc, p.lc_b0, xin, p.kin, trow, u0 + c * 8, ra); break;
+                  }
+                  tanh_chunk(ra, hi4, lo4);
+                }
+                store_chunk(c, hi4, lo4);
+                publish(sl);
+              }
+              buf ^= 1;
+            } else if (s_epi == EPI_XINV) {
+              const int r = s_stage, d = perm[r];
+              const float yv = ycur[d * kTileM + trow];
+              const float* bo = lc + s_eaux;
+              const bool has_acc = !(s_flags & 1);
+              float xv = 0.f, ld = 0.f;
+              if (!spline) {
+                uint32_t rr[2] = {0u, 0u};
+                if (has_acc) { tcx::tmem_ld16x2_2<0>(lane_base + s_ecol, rr); tcx::tmem_ld_wait(); }
+                float mu = __uint_as_float(rr[0]) + bo[0];
+                float sc = fminf(fmaxf(__uint_as_float(rr[1]) + bo[1], p.clip_lo), p.clip_hi);
+                xv = (yv - mu) * expf(-sc);
+                ld = sc;
+              } else if (fast_rqs) {
+                uint32_t rr[24];
+#pragma unroll
+                for (int e = 0; e < 24; ++e) rr[e] = 0u;
+                if (has_acc) {
+                  tcx::tmem_ld16x2_8<0>(lane_base + s_ecol, rr);
+                  tcx::tmem_ld16x2_8<0>(lane_base + s_ecol + 8, rr + 8);
+                  tcx::tmem_ld16x2_8<0>(lane_base + s_ecol + 16, rr + 16);
+                  tcx::tmem_ld_wait();
+                }
+                if (dbg_me) { DBG3(2) }
+                if (owner) {
+                  float rf[24];
+#pragma unroll
+                  for (int e = 0; e < 24; ++e) rf[e] = __uint_as_float(rr[e]) + bo[e];
+                  nazb::rqs_fast<8>(yv, p.bound, true, rf, xv, ld);
+                }
+              } else {
+                for (int m0 = 0; m0 < p.Mp; m0 += 8) {
+                  uint32_t rr[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) rr[e] = 0u;
+                  if (has_acc) { tcx::tmem_ld16x2_8<0>(lane_base + s_ecol + m0, rr); tcx::tmem_ld_wait(); }
+                  if (owner) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                      if (m0 + e < M) scr[(m0 + e) * kTileM] = __uint_as_float(rr[e]) + bo[m0 + e];
+                  }
+                }
+                if (owner) {
+                  if (p.kind == NAZB_KIND_RQS) nazb::rational_spline<false>(yv, p.K, p.bound, true, raw, setw, xv, ld);
+                  else nazb::rational_spline<true>(yv, p.K, p.bound, true, raw, setw, xv, ld);
+                }
+              }
+              tcx::tc_fence_before();
+              if (owner) {
+                ld_acc += ld;
+                xin[(C + d) * kTileM + trow] = xv;
+                if (r == D - 1) {
+                  // end of this flow layer: x becomes the y of the next (earlier) layer, x restarts at 0
+                  for (int dd = 0; dd < D; ++dd) {
+                    ycur[dd * kTileM + trow] = xin[(C + dd) * kTileM + trow];
+                    xin[(C + dd) * kTileM + trow] = 0.f;
+                  }
+                }
+              }
+              __syncwarp();   // the row's second thread reads xin in the next FIRST phase
+            }
+            if (dbg_me) { DBG3(3) }
+            ++dbg_i;
+          }
+          // this layer's constants are no longer needed by this warp
+          __syncwarp();
+          if (lane == 0) tcx::mbar_arrive(lc_empty + (lcnt & 1));
+          ++lcnt;
+        }
+
+        // ---- draw end ----
+        {
+          float lp = 0.f;
+          const bool mine = owner && trow < npts;
+          if (owner) {
+            float qd = 0.f;
+            for (int d = 0; d < D; ++d) { float z = ycur[d * kTileM + trow]; qd += 0.5f * z * z; }
+            lp = -qd - 0.5f * D * NAZB_LOG_2PI - ld_acc + ljac[trow];
+          }
+          if (mine) {
+            if (io.out_l) io.out_l[(size_t)si * io.N + n0 + trow] = lp;
+            if (io.lse_max) {
+              float v = lp + (io.log_w ? io.log_w[si] : 0.f);
+              if (!(v <= run_m)) { run_s = run_s * expf(run_m - v) + 1.f; run_m = v; }
+              else if (v > -INFINITY) run_s += expf(v - run_m);
+            }
+            if (io.out_x) {
+              float* dst = io.out_x + ((size_t)si * io.N + n0 + trow) * D;
+              for (int d = 0; d < D; ++d) dst[d] = ycur[d * kTileM + trow];
+            }
+          }
+          if (io.sum_n) {
+            double v = mine ? (double)lp : 0.0;
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) atomicAdd(io.sum_n + si, v);
+          }
+        }
+      }
+      if (io.lse_max && owner && trow < npts) {
+        io.lse_max[(size_t)grp * io.N + n0 + trow] = run_m;
+        io.lse_sum[(size_t)grp * io.N + n0 + trow] = run_s;
+      }
+    }
+  }
+  tcx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tcx::tmem_dealloc(tmem, kTmemCols);
+}

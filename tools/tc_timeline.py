@@ -23,24 +23,29 @@ L.nazb_debug_set_clock_buffer.argtypes = [C.c_void_p]
 L.nazb_debug_set_clock_buffer(buf.data_ptr())
 run(); torch.cuda.synchronize()
 L.nazb_debug_set_clock_buffer(None)
-t = buf.cpu().numpy().reshape(256, 8) if direction != "inverse" else buf.cpu().numpy().reshape(256, 16)
+t = buf.cpu().numpy()[:2048].reshape(256, 8) if direction != "inverse" else buf.cpu().numpy().reshape(256, 16)
 t0 = t[0, 0]
 names = {0: "none", 1: "tanh", 2: "xinv", 3: "xfwd"}
 print("step  n ks sp epi ncols wKB | v2 inverse: wait_w issue acc_wait | epi_work sync | total")
 names = {0: "none", 1: "tanh", 2: "xinv", 3: "xfwd", 4: "first"}
 if direction == "inverse":
+    # v3 stamps: epilogue warp 0 [0] step start [1] acc barrier passed [2] TMEM loaded [3] step end;
+    #            issuer of chain 0 [8] step start [9] weights landed [10] first A slice landed [11] all MMAs issued
+    print("step  n ncrit ks epi ncols wKB | epi: acc_wait  ld   work  total | issuer: w_wait a_wait issue | issue_end - epi_end(prev)")
     for i in range(min(2*nsteps, 127)):
         s = i % nsteps
         n, ks, sp, epi, ncols, wb, dcol, abuf = [prog[s*8+j] for j in range(8)]
-        m0, m1, m2, m3, e4, e5, e6, e7 = t[i][:8]
-        x8, x9, x10 = t[i][8:11]
-        prev_end = t[i-1, 6] if i > 0 else m0
-        if wb:
-            extra = f"  ld {e4-m3:5d} bias {x8-e4:4d} tanh {x9-x8:4d} st {x10-x9:4d} rest {e5-x10:5d}" if epi == 1 else ""
-            print(f"{i:3d} {n:4d} {ks:2d} {sp:1d} {names[epi]:5s} {ncols:3d} {wb/1024:5.1f} | {m1-m0:6d} {m2-m1:6d} {m3-m2:6d} | {e5-m3:6d} {e6-e5:5d} | {e6-prev_end:6d}" + extra)
+        e0, e1, e2, e3 = t[i][:4]
+        m8, m9, m10, m11 = t[i][8:12]
+        line = f"{i:3d} {n:4d} {ks:2d} {names[epi]:5s} {ncols:3d} {wb/1024:5.1f} |"
+        if epi:
+            line += f" {e1-e0:6d} {max(e2-e1,0):5d} {e3-max(e2,e1):6d} {e3-e0:6d} |"
         else:
-            print(f"{i:3d} {n:4d} {ks:2d} {sp:1d} {names[epi]:5s} {ncols:3d} {wb/1024:5.1f} | {'':6s} {'':6s} {'':6s} | {e5-m3:6d} {e6-e5:5d} | {e6-prev_end:6d}")
-    print("two layers:", t[2*nsteps-1, 6] - t[0, 3], "cycles")
+            line += " " * 29 + "|"
+        if wb:
+            line += f" {m9-m8:6d} {m10-m9:6d} {m11-m10:6d}"
+        print(line)
+    print("two layers:", t[2*nsteps-1, 3] - t[0, 0], "cycles")
     sys.exit(0)
 print("step  n ks sp epi ncols wKB | mma: wait_a  wait_w  issue | epi: wait_acc(after mma issue)  work  signal | step_total")
 for i in range(min(2*nsteps, 255)):
