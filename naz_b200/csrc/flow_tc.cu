@@ -40,7 +40,7 @@ constexpr int kSlotBytes = 40960;
 constexpr int kTmemCols = 512;
 
 enum : uint8_t { EPI_NONE = 0, EPI_TANH = 1, EPI_XINV = 2, EPI_XFWD = 3, EPI_FIRST = 4 };
-enum : uint8_t { A_IN = 0, A_H = 1 };
+enum : uint8_t { A_IN = 0, A_H = 1, A_X = 2 };   // A_X: v3 inverse first-layer operand [ctx | x | 1]
 
 struct Step {
   uint32_t w_off;      // byte offset of the weight image inside a flow layer's block
@@ -50,7 +50,8 @@ struct Step {
   uint16_t n;          // N extent (multiple of 16)
   uint16_t d_col;      // TMEM column of D
   uint8_t a_buf, nsplit, accumulate, epi;
-  uint8_t stage, nranks, flags, pad1;   // flags bit 0: the accumulator holds nothing yet (bias-only output)
+  uint8_t stage, nranks, flags, pad1;   // flags bit 0: the accumulator holds nothing yet (bias-only output);
+                                        // bit 2: TANH block whose accumulator already holds scaled pre-activation + bias
   uint16_t e_col, e_ncols, e_dst_chunk;
   uint16_t e_aux;   // v2 inverse: TANH / XINV -> float offset of the bias of column e_col inside the layer
                     // constants; FIRST -> first hidden unit of the block
@@ -64,6 +65,7 @@ struct Image {          // how the pack kernel fills one step's weight image
   int n0, r0, r1;
   int k0, kv0, kv1;     // image column c <-> source column k0 + c, used iff kv0 <= k0 + c < kv1
   int bias_col, bias_only;
+  float scale;          // multiplies every packed value (1, or 2 log2 e for tensor-core first-layer blocks)
 };
 
 struct TcPlan {
@@ -76,13 +78,10 @@ struct TcPlan {
   uint32_t off_in, off_h, off_x, off_y, off_xo, off_ctx, off_misc, off_scratch, off_ring;
   // v2 inverse: per-(draw, layer) fp32 constants [W0 (Hp0 x kinp) | b_0 .. b_{nh-1} | b_out (D x Mp, rank-major)]
   int kinp = 0, lc_floats = 0, lc_b[NAZB_MAX_HIDDEN_LAYERS] = {0}, lc_bout = 0;
-  // v2 inverse kernel shared-memory plan
-  uint32_t i_xin = 0, i_lc = 0, i_h = 0, i_y = 0, i_xo = 0, i_misc = 0, i_scratch = 0, i_ring = 0;
-  int i_nslots = 0;
-  size_t i_smem_bytes = 0;
   // v3 inverse kernel: double-buffered A blocks of kr_max columns per chain
   int kr_max = 0;
-  bool v3_ok = false;
+  bool xf = false;      // first conditioner layer on tensor cores (K = 16 slice [ctx | x | 1])
+  uint32_t j_ax = 0, j_xring = 0;
   uint32_t j_xin = 0, j_lc = 0, j_a = 0, j_y = 0, j_xo = 0, j_misc = 0, j_scratch = 0, j_ring = 0;
   int j_nslots = 0;
   size_t j_smem_bytes = 0;
@@ -122,7 +121,9 @@ struct KParamsInv {
   int phase_delay;
   const int* perm;
   int D, C, L, M, Mp, K, kind, kin, kinp, hp_max, nslots;
-  int kr_max;                      // v3: columns of one A block buffer
+  int kr_max;                      // columns of one A block buffer
+  int xf;                          // first conditioner layer on tensor cores
+  uint32_t off_ax, off_xring;
   float bound, clip_lo, clip_hi;
   uint32_t off_xin, off_lc, off_h, off_y, off_xo, off_misc, off_scratch, off_ring;
 };
@@ -187,6 +188,7 @@ Image mk_img(int lin, int n_ext, int k_ext, int row_mode, int n0, int r0, int r1
   Image im{};
   im.lin = lin; im.n_ext = n_ext; im.k_ext = k_ext; im.row_mode = row_mode; im.n0 = n0; im.r0 = r0; im.r1 = r1;
   im.k0 = k0; im.kv0 = kv0; im.kv1 = kv1; im.bias_col = bias_col; im.bias_only = bias_only;
+  im.scale = 1.f;
   return im;
 }
 
@@ -247,9 +249,16 @@ bool build_inverse(const FlowGeom& g, TcPlan& P) {
   for (int j = 1; j < nh; ++j) { T_PRE[j] = col; col += hp(j); }
   const int T_OUT = col; col += D * Mp;
   if (col > kTmemCols) return false;
-  // layer constants
+  // first conditioner layer on tensor cores when TMEM has room for the transient block of pre-activations and
+  // [ctx | x | 1] fits one K = 16 slice; otherwise it runs on CUDA cores from the layer constants
+  int xw = 0;
+  for (int r = 0; r < D; ++r) xw = std::max(xw, ceil_to(g.blk[0][r + 1], 8) - (g.blk[0][r] & ~7));
+  const int T_PRE1 = col;
+  P.xf = (g.kin + 1 <= 16) && (xw <= 64) && (col + ceil_to(xw, 16) <= kTmemCols);
+  if (const char* env = getenv("NAZB_NO_XF")) if (atoi(env)) P.xf = false;
+  // layer constants: [W0 * c (Hp0 x kinp; CUDA-core first layer only) | b_0 * c .. b_{nh-1} * c | b_out], c = 2 log2 e
   P.kinp = ceil_to(g.kin, 4);
-  int off = hp(0) * P.kinp;
+  int off = P.xf ? 0 : hp(0) * P.kinp;
   for (int j = 0; j < nh; ++j) { P.lc_b[j] = off; off += hp(j); }
   P.lc_bout = off; off += D * Mp;
   P.lc_floats = ceil_to(off, 4);
@@ -274,6 +283,13 @@ bool build_inverse(const FlowGeom& g, TcPlan& P) {
       Step e = mk_epi(EPI_FIRST, 0, ec1 - ec0, 0, r);
       e.e_aux = (uint16_t)ec0;
       b.epi_only(e);
+      if (P.xf) {
+        Step t = mk_epi(EPI_TANH, T_PRE1, ec1 - ec0, 0);
+        t.flags = 4;
+        Image im = mk_img(0, ec1 - ec0, 16, 0, ec0, 0, 0, 0, 0, g.kin, g.kin, 0);
+        im.scale = 2.885390081777927f;
+        b.gemm(A_X, 0, 16, ec1 - ec0, T_PRE1, 3, 0, im, t, ec1 - ec0);
+      }
     }
     for (int j = 0; j < nh; ++j) {
       int sb0 = g.blk[j][r], sb1 = g.blk[j][r + 1];
@@ -324,25 +340,6 @@ bool plan_smem(const FlowGeom& g, TcPlan& P) {
   return true;
 }
 
-bool plan_smem_inv(const FlowGeom& g, TcPlan& P) {
-  uint32_t off = 1024;
-  P.i_xin = off;     off += (uint32_t)ceil_to(g.kin, 4) * kTileM * 4;      // [kin][128] fp32: ctx rows then x rows
-  P.i_lc = off;      off += 2u * (uint32_t)P.lc_floats * 4;
-  off = (off + 127) & ~127u;
-  P.i_h = off;       off += (uint32_t)P.hp_max * kTileM * 2 * 2;
-  P.i_y = off;       off += (uint32_t)g.D * kTileM * 4;
-  P.i_xo = off;      off += (uint32_t)g.D * kTileM * 4;
-  P.i_misc = off;    off += kTileM * 4;
-  P.i_scratch = off; off += (g.kind == NAZB_KIND_AFFINE || (g.kind == NAZB_KIND_RQS && g.K == 8)) ? 0 : 32u * kTileM * 4;
-  off = (off + 127) & ~127u;
-  P.i_ring = off;
-  const uint32_t cap = 227 * 1024;
-  if (off + 2 * kSlotBytes > cap) return false;
-  P.i_nslots = std::min(6u, (cap - off) / kSlotBytes);
-  P.i_smem_bytes = off + (size_t)P.i_nslots * kSlotBytes;
-  return true;
-}
-
 bool plan_smem_inv3(const FlowGeom& g, TcPlan& P) {
   if (P.kr_max <= 0 || P.kr_max > 128) return false;      // <= kV3MaxSlices K slices per A block
   uint32_t off = 1024;
@@ -350,6 +347,8 @@ bool plan_smem_inv3(const FlowGeom& g, TcPlan& P) {
   P.j_lc = off;      off += 2u * (uint32_t)P.lc_floats * 4;
   off = (off + 127) & ~127u;
   P.j_a = off;       off += 2u * 2u * (uint32_t)P.kr_max * (kTileM / 2) * 2 * 2;   // [chain][buffer][hi | lo]
+  P.j_ax = off;      off += 2u * 2u * 16u * (kTileM / 2) * 2;                      // [chain][hi | lo] one K = 16 slice
+  P.j_xring = off;   off += P.xf ? 4u * 4096u : 0u;                                // kXSlots x kXSlotBytes
   P.j_y = off;       off += (uint32_t)g.D * kTileM * 4;
   P.j_xo = off;      off += (uint32_t)g.D * kTileM * 4;
   P.j_misc = off;    off += kTileM * 4;
@@ -422,7 +421,7 @@ __global__ void tc_pack_kernel(Image im, int S, int L, int n_lin, int D, int M, 
           }
         }
       }
-      v = fminf(fmaxf(v, -65504.f), 65504.f);
+      v = fminf(fmaxf(v * im.scale, -65504.f), 65504.f);
       hi[e] = __float2half_rn(v);
       lo[e] = __float2half_rn(v - __half2float(hi[e]));
     }
@@ -889,11 +888,12 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const __grid_const
 
 
 // ------------------------------------------------------------------------------------------------
-// Layer-constants pack kernel (v2 inverse): fp32 [W0 masked (Hp0 x kinp) | hidden biases | output bias rank-major]
+// Layer-constants pack kernel (inverse): fp32 [W0 masked * c (Hp0 x kinp; absent when the first layer runs on tensor
+// cores) | hidden biases * c | output bias rank-major], c = 2 log2 e (the tanh epilogues take scaled pre-activations)
 // ------------------------------------------------------------------------------------------------
 struct LcGeom { int lc_b[NAZB_MAX_HIDDEN_LAYERS]; int hdim[NAZB_MAX_HIDDEN_LAYERS]; };
-__global__ void tc_pack_lc_kernel(int S, int L, int n_lin, int D, int M, int Mp, int kin, int kinp, int hp0, int h0,
-                                  int lc_floats, LcGeom lg, int lc_bout,
+__global__ void tc_pack_lc_kernel(int S, int L, int n_lin, int D, int M, int Mp, int kin, int kinp, int w0_floats, int h0,
+                                  float hscale, int lc_floats, LcGeom lg, int lc_bout,
                                   const float* const* __restrict__ Wtab, const float* const* __restrict__ btab,
                                   const float* const* __restrict__ mtab, const long long* __restrict__ wst,
                                   const long long* __restrict__ bst, const int* __restrict__ perm, float* __restrict__ dst) {
@@ -904,17 +904,17 @@ __global__ void tc_pack_lc_kernel(int S, int L, int n_lin, int D, int M, int Mp,
     int l = (int)((idx / lc_floats) % L);
     int s = (int)(idx / ((long long)lc_floats * L));
     float v = 0.f;
-    if (f < hp0 * kinp) {
+    if (f < w0_floats) {
       int n = f / kinp, k = f % kinp;
       if (n < h0 && k < kin) {
         int ti = l * n_lin;
-        v = Wtab[ti][(size_t)s * wst[ti] + (size_t)n * kin + k] * mtab[ti][(size_t)n * kin + k];
+        v = hscale * Wtab[ti][(size_t)s * wst[ti] + (size_t)n * kin + k] * mtab[ti][(size_t)n * kin + k];
       }
     } else if (f < lc_bout) {
       int j = 0;
       while (j + 1 < n_lin - 1 && f >= lg.lc_b[j + 1]) ++j;
       int n = f - lg.lc_b[j];
-      if (n < lg.hdim[j]) { int ti = l * n_lin + j; v = btab[ti][(size_t)s * bst[ti] + n]; }
+      if (n < lg.hdim[j]) { int ti = l * n_lin + j; v = hscale * btab[ti][(size_t)s * bst[ti] + n]; }
     } else if (f < lc_bout + D * Mp) {
       int n = f - lc_bout, rank = n / Mp, m = n % Mp;
       if (m < M) { int ti = l * n_lin + (n_lin - 1); v = btab[ti][(size_t)s * bst[ti] + m * D + perm[l * D + rank]]; }
@@ -924,7 +924,7 @@ __global__ void tc_pack_lc_kernel(int S, int L, int n_lin, int D, int M, int Mp,
 }
 
 // ------------------------------------------------------------------------------------------------
-// v2 inverse kernel: two self-issuing 64-row chains (8 warps each) + 1 TMA producer warp.
+// Inverse kernel (flow_tc_inv3.cuh): two independent 64-row chains per 128-point tile.
 //
 // An M = 64 tcgen05.mma writes its rows to lanes 0-15 of each 32-lane TMEM quadrant, and a lane offset of
 // 16 in the D address selects lanes 16-31 (probed: tools/tc_probe_m64.cu).  The 128-point tile is therefore
@@ -933,407 +933,7 @@ __global__ void tc_pack_lc_kernel(int S, int L, int n_lin, int D, int M, int Mp,
 // sits in its MMA / barrier latency the other one owns the MUFU and issue slots.
 // ------------------------------------------------------------------------------------------------
 constexpr int kChains = 2;
-constexpr int kChainWarps = kEpiWarps / kChains;      // 8
-constexpr int kChainThreads = kChainWarps * 32;       // 256
 constexpr int kChainRows = kTileM / kChains;          // 64
-constexpr int kInvThreads = kEpiThreads + 32;
-__device__ __forceinline__ void chain_sync(int c) { asm volatile("bar.sync %0, %1;\n" ::"r"(1 + c), "n"(kChainThreads) : "memory"); }
-
-#define DBGI(slot)                                                                       \
-  if (p.dbg && blockIdx.x == 0 && dbg_i < 128) p.dbg[dbg_i * 16 + (slot)] = clk();
-
-// per chunks of 8 columns: PER loads per thread, the two half-warps PER chunks apart
-template <int PER>
-__device__ __forceinline__ void ld_chunks(uint32_t taddr, uint32_t* r) {
-#pragma unroll
-  for (int j = 0; j < PER; ++j) tcx::tmem_ld16x2_8<PER * 8>(taddr + j * 8, r + 8 * j);
-}
-
-// First conditioner layer on CUDA cores for one work item = (pair of rows, chunk of 8 units).
-template <int KINP>
-__device__ __forceinline__ void first_layer_item(const float* __restrict__ lc, int lc_b0, const float* __restrict__ xin,
-                                                 int kin, int n0, int trow, uint32_t* ra, uint32_t* rb) {
-  float xa[KINP], xb[KINP];
-#pragma unroll
-  for (int k = 0; k < KINP; ++k) {
-    float2 v = (k < kin) ? *reinterpret_cast<const float2*>(xin + k * kTileM + trow) : make_float2(0.f, 0.f);
-    xa[k] = v.x; xb[k] = v.y;
-  }
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int n = n0 + e;
-    const float4* wr = reinterpret_cast<const float4*>(lc + (size_t)n * KINP);
-    float a0 = lc[lc_b0 + n], a1 = a0;
-#pragma unroll
-    for (int k4 = 0; k4 < KINP / 4; ++k4) {
-      float4 w = wr[k4];
-      a0 = fmaf(w.x, xa[k4 * 4 + 0], a0); a1 = fmaf(w.x, xb[k4 * 4 + 0], a1);
-      a0 = fmaf(w.y, xa[k4 * 4 + 1], a0); a1 = fmaf(w.y, xb[k4 * 4 + 1], a1);
-      a0 = fmaf(w.z, xa[k4 * 4 + 2], a0); a1 = fmaf(w.z, xb[k4 * 4 + 2], a1);
-      a0 = fmaf(w.w, xa[k4 * 4 + 3], a0); a1 = fmaf(w.w, xb[k4 * 4 + 3], a1);
-    }
-    ra[e] = __float_as_uint(a0); rb[e] = __float_as_uint(a1);
-  }
-}
-
-__global__ void __launch_bounds__(kInvThreads, 1) flow_tc_inv_kernel(const __grid_constant__ KParamsInv p,
-                                                                      const __grid_constant__ IoArgs io, int n_groups) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem);          // [nslots]
-  uint64_t* bar_empty = bar_full + 8;                               // [nslots], count = kChains
-  uint64_t* bar_acc = bar_empty + 8;                                // [kChains] MMA -> epilogue
-  uint64_t* lc_full = bar_acc + kChains;                            // [2]
-  uint64_t* lc_empty = lc_full + 2;                                 // [2], count = kChains
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lc_empty + 2);
-  float* xin = reinterpret_cast<float*>(smem + p.off_xin);          // [kin][128]: ctx rows, then x rows
-  float* lcs = reinterpret_cast<float*>(smem + p.off_lc);           // [2][lc_floats]
-  float* ycur = reinterpret_cast<float*>(smem + p.off_y);           // [D][128]
-  float* xorig = reinterpret_cast<float*>(smem + p.off_xo);         // [D][128]
-  float* ljac = reinterpret_cast<float*>(smem + p.off_misc);        // [128]
-  float* scratch = reinterpret_cast<float*>(smem + p.off_scratch);  // [32][128] (generic spline only)
-  uint8_t* ring = smem + p.off_ring;
-
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const int D = p.D, C = p.C, M = p.M;
-
-  if (tid == 0) {
-    for (int i = 0; i < p.nslots; ++i) { tcx::mbar_init(bar_full + i, 1); tcx::mbar_init(bar_empty + i, kChains); }
-    for (int i = 0; i < kChains; ++i) tcx::mbar_init(bar_acc + i, 1);
-    for (int i = 0; i < 2; ++i) { tcx::mbar_init(lc_full + i, 1); tcx::mbar_init(lc_empty + i, kChains); }
-    tcx::mbar_fence_init();
-  }
-  if (warp == 0) tcx::tmem_alloc(tmem_slot, kTmemCols);
-  for (uint32_t i = tid; i < ((uint32_t)p.hp_max * kTileM * 4) / 16; i += kInvThreads)
-    reinterpret_cast<uint4*>(smem + p.off_h)[i] = make_uint4(0, 0, 0, 0);
-  tcx::fence_async_smem();
-  tcx::tc_fence_before();
-  __syncthreads();
-  tcx::tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-
-  const int n_tiles = (io.N + kTileM - 1) / kTileM;
-  const long long n_items = (long long)n_tiles * n_groups;
-
-  if (warp == kEpiWarps) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      uint32_t cnt = 0, lcnt = 0;
-      for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int grp = (int)(item / n_tiles);
-        for (int si = grp; si < io.s_count; si += n_groups) {
-          const uint8_t* wdraw = p.wimg + (size_t)(io.s_begin + si) * p.draw_bytes;
-          const float* lcdraw = p.lc + (size_t)(io.s_begin + si) * p.L * p.lc_floats;
-          for (int li = 0; li < p.L; ++li) {
-            const int l = p.L - 1 - li;
-            {
-              const uint32_t b = lcnt & 1, use = lcnt >> 1;
-              tcx::mbar_wait(lc_empty + b, (use & 1) ^ 1);
-              tcx::mbar_expect_tx(lc_full + b, (uint32_t)p.lc_floats * 4);
-              tcx::bulk_g2s(lcs + (size_t)b * p.lc_floats, lcdraw + (size_t)l * p.lc_floats, (uint32_t)p.lc_floats * 4, lc_full + b);
-              ++lcnt;
-            }
-            const uint8_t* wl = wdraw + (size_t)l * p.layer_bytes;
-            for (int st = 0; st < p.nsteps; ++st) {
-              const uint32_t wb = p.steps[st].w_bytes;
-              if (wb == 0) continue;
-              const uint32_t slot = cnt % p.nslots, use = cnt / p.nslots;
-              tcx::mbar_wait(bar_empty + slot, (use & 1) ^ 1);
-              tcx::mbar_expect_tx(bar_full + slot, wb);
-              tcx::bulk_g2s(ring + (size_t)slot * kSlotBytes, wl + p.steps[st].w_off, wb, bar_full + slot);
-              ++cnt;
-            }
-          }
-        }
-      }
-    }
-  } else {
-    // ===================== chain warps: MMA issue (first warp of the chain) + epilogues (all) =====================
-    const int ch = warp / kChainWarps, wq = warp % kChainWarps;
-    const int q = wq & 3, part = wq >> 2;          // TMEM quadrant, column part (2 parts x 2 half-warps = 4 column groups)
-    const int hw = lane >> 4, lr = lane & 15;
-    const int grp4 = part * 2 + hw;                // column group 0..3
-    const int crow = q * 16 + lr;                  // row inside the chain's 64-row sub-tile
-    const int trow = ch * kChainRows + crow;       // row inside the 128-point tile
-    const int ctid = tid - ch * kChainThreads;     // thread index inside the chain
-    const uint32_t lane_base = tmem + ((uint32_t)(q * 32 + ch * 16) << 16);
-    const uint32_t elected = tcx::elect_one();
-    const bool spline = p.kind != NAZB_KIND_AFFINE;
-    const bool fast_rqs = (p.kind == NAZB_KIND_RQS && p.K == 8);
-    const bool row_owner = (grp4 == 0);
-    float* scr = scratch + trow;
-    auto raw = [&](int m) { return scr[m * kTileM]; };
-    auto setw = [&](int m, float v) { scr[m * kTileM] = v; };
-    // this chain's A operand: [hi | lo][K-chunk][64 rows][8 halves]
-    __half* h_hi = reinterpret_cast<__half*>(smem + p.off_h) + (size_t)ch * 2 * p.hp_max * kChainRows;
-    __half* h_lo = h_hi + (size_t)p.hp_max * kChainRows;
-    const uint32_t h_hi_a = tcx::smem_u32(h_hi), h_lo_a = tcx::smem_u32(h_lo), ring_a = tcx::smem_u32(ring);
-    constexpr uint32_t lbo_a = kChainRows * 16;
-    constexpr uint64_t dhi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;   // SBO = 128 B, descriptor version 1
-    uint64_t* my_acc = bar_acc + ch;
-    uint32_t slot = 0, use = 0, par_acc = 0, lcnt = 0;
-    int dbg_i = 0;
-    const bool dbg_me = (tid == 0);
-
-    // start the second chain half a step late so the two chains' MUFU bursts and MMA / barrier latencies interleave
-    if (ch == 1) { const long long t0 = clk(); while (clk() - t0 < p.phase_delay) { } }
-    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int tile = (int)(item % n_tiles), grp = (int)(item / n_tiles);
-      const int n0 = tile * kTileM;
-      const int npts = min(kTileM, io.N - n0);
-      float run_m = -INFINITY, run_s = 0.f;
-      // ---- tile load: this chain's 64 rows ----
-      chain_sync(ch);
-      for (int i = ctid; i < kChainRows * C; i += kChainThreads) {
-        int pt = ch * kChainRows + i / C, c = i % C;
-        float v = 0.f;
-        if (pt < npts) v = io.ctx[((io.ctx_rows == 1) ? 0 : (size_t)(n0 + pt)) * C + c];
-        xin[c * kTileM + pt] = v;
-      }
-      for (int i = ctid; i < kChainRows * D; i += kChainThreads) {
-        int pt = ch * kChainRows + i / D, d = i % D;
-        xorig[d * kTileM + pt] = (pt < npts) ? io.x[(size_t)(n0 + pt) * D + d] : 0.f;
-      }
-      chain_sync(ch);
-      if (row_owner) {
-        float lj = 0.f;
-        if (io.lo != nullptr && trow < npts)
-          for (int d = 0; d < D; ++d) xorig[d * kTileM + trow] = nazb::bound_fwd(xorig[d * kTileM + trow], io.lo[d], io.hi[d], lj);
-        ljac[trow] = lj;
-      }
-
-      for (int si = grp; si < io.s_count; si += n_groups) {
-        // ---- draw start ----
-        for (uint32_t i = ctid; i < ((uint32_t)p.hp_max * kChainRows * 4) / 16; i += kChainThreads)
-          reinterpret_cast<uint4*>(h_hi)[i] = make_uint4(0, 0, 0, 0);
-        float ld_acc = 0.f;
-        if (row_owner)
-          for (int d = 0; d < D; ++d) {
-            ycur[d * kTileM + trow] = xorig[d * kTileM + trow];
-            xin[(C + d) * kTileM + trow] = 0.f;
-          }
-        tcx::fence_async_smem();
-        chain_sync(ch);
-
-        for (int li = 0; li < p.L; ++li) {
-          const int l = p.L - 1 - li;
-          const int* perm = p.perm + l * D;
-          const float* lc = lcs + (size_t)(lcnt & 1) * p.lc_floats;
-          tcx::mbar_wait(lc_full + (lcnt & 1), (lcnt >> 1) & 1);
-          for (int st = 0; st < p.nsteps; ++st) {
-            struct { uint32_t epi, e_col, e_ncols, e_aux, stage, flags; } s;
-            s.epi = p.steps[st].epi; s.e_col = p.steps[st].e_col; s.e_ncols = p.steps[st].e_ncols;
-            s.e_aux = p.steps[st].e_aux; s.stage = p.steps[st].stage; s.flags = p.steps[st].flags;
-            const uint32_t s_wbytes = p.steps[st].w_bytes;
-            if (s_wbytes) {
-              if (wq == 0) {
-                // ---- MMA issue (chain leader warp, convergent; tcgen05 instructions predicated on the elected lane) ----
-                const uint32_t s_n = p.steps[st].n, s_dcol = p.steps[st].d_col;
-                const int ksteps = p.steps[st].ksteps;
-                const uint32_t s_acc = p.steps[st].accumulate;
-                const uint32_t idesc = tcx::make_idesc_f16_m64(s_n);
-                const uint32_t lbo_b = s_n * 16;
-                const uint32_t b_hi = ring_a + slot * kSlotBytes, b_lo = b_hi + (s_wbytes >> 1);
-                const uint32_t a_off = (uint32_t)p.steps[st].a_chunk0 * lbo_a;
-                const uint32_t da_hi0 = ((h_hi_a + a_off) >> 4) | ((lbo_a >> 4) << 16);
-                const uint32_t da_lo0 = ((h_lo_a + a_off) >> 4) | ((lbo_a >> 4) << 16);
-                const uint32_t db_hi0 = (b_hi >> 4) | ((lbo_b >> 4) << 16), db_lo0 = (b_lo >> 4) | ((lbo_b >> 4) << 16);
-                const uint32_t da_step = (2 * lbo_a) >> 4, db_step = (2 * lbo_b) >> 4;
-                const uint32_t d_addr = tmem + ((uint32_t)(ch * 16) << 16) + s_dcol;
-                if (dbg_me) { DBGI(0) }
-                tcx::mbar_wait(bar_full + slot, use & 1);
-                tcx::tc_fence_after();
-                if (dbg_me) { DBGI(1) }
-                // independent descriptor per MMA (no loop-carried uniform-register chain), fully unrolled
-#pragma unroll
-                for (int k = 0; k < 6; ++k)                   // a_hi * w_hi
-                  if (k < ksteps)
-                    tcx::mma_f16_ss_elect(d_addr, dhi | (da_hi0 + k * da_step), dhi | (db_hi0 + k * db_step), idesc,
-                                          (k == 0) ? s_acc : 1u, elected);
-#pragma unroll
-                for (int k = 0; k < 6; ++k)                   // a_hi * w_lo
-                  if (k < ksteps)
-                    tcx::mma_f16_ss_elect(d_addr, dhi | (da_hi0 + k * da_step), dhi | (db_lo0 + k * db_step), idesc, 1u, elected);
-#pragma unroll
-                for (int k = 0; k < 6; ++k)                   // a_lo * w_hi
-                  if (k < ksteps)
-                    tcx::mma_f16_ss_elect(d_addr, dhi | (da_lo0 + k * da_step), dhi | (db_hi0 + k * db_step), idesc, 1u, elected);
-                tcx::mma_commit_elect(bar_empty + slot, elected);
-                if (s.epi != EPI_NONE) tcx::mma_commit_elect(my_acc, elected);
-                if (dbg_me) { DBGI(2) }
-              }
-              if (++slot == (uint32_t)p.nslots) { slot = 0; ++use; }
-              if (s.epi == EPI_NONE) { ++dbg_i; continue; }   // K-split sub-step: the next sub-step's MMAs queue right behind
-              tcx::mbar_wait(my_acc, par_acc);
-              par_acc ^= 1;
-              tcx::tc_fence_after();
-            }
-            if (dbg_me) { DBGI(3) }
-            if (s.epi == EPI_TANH) {
-              const int nchunks = s.e_ncols >> 3;
-              const int per = (nchunks + 3) >> 2;            // chunks per column group
-              uint32_t r[40];
-              const uint32_t ta = lane_base + s.e_col + (uint32_t)(part * 2 * per) * 8;
-              switch (per) {
-                case 1: ld_chunks<1>(ta, r); break;
-                case 2: ld_chunks<2>(ta, r); break;
-                case 3: ld_chunks<3>(ta, r); break;
-                case 4: ld_chunks<4>(ta, r); break;
-                default: ld_chunks<5>(ta, r); break;
-              }
-              const int c0 = grp4 * per;
-              tcx::tmem_ld_wait();
-              if (dbg_me) { DBGI(4) }
-#pragma unroll
-              for (int u = 0; u < 5; ++u) {
-                const int c = c0 + u;
-                if (u < per && c < nchunks) {
-                  const float4* bv = reinterpret_cast<const float4*>(lc + s.e_aux + c * 8);
-                  float4 b0 = bv[0], b1 = bv[1];
-                  uint32_t* ru = r + 8 * u;
-                  ru[0] = __float_as_uint(__uint_as_float(ru[0]) + b0.x); ru[1] = __float_as_uint(__uint_as_float(ru[1]) + b0.y);
-                  ru[2] = __float_as_uint(__uint_as_float(ru[2]) + b0.z); ru[3] = __float_as_uint(__uint_as_float(ru[3]) + b0.w);
-                  ru[4] = __float_as_uint(__uint_as_float(ru[4]) + b1.x); ru[5] = __float_as_uint(__uint_as_float(ru[5]) + b1.y);
-                  ru[6] = __float_as_uint(__uint_as_float(ru[6]) + b1.z); ru[7] = __float_as_uint(__uint_as_float(ru[7]) + b1.w);
-                  uint4 hi4, lo4;
-                  tanh_chunk(ru, hi4, lo4);
-                  const size_t o = ((size_t)c * kChainRows + crow) * 8;
-                  *reinterpret_cast<uint4*>(h_hi + o) = hi4;
-                  *reinterpret_cast<uint4*>(h_lo + o) = lo4;
-                }
-              }
-            } else if (s.epi == EPI_FIRST) {
-              // work item = (pair of rows of this chain, chunk of 8 hidden units)
-              const int nchunks = s.e_ncols >> 3;
-              const int u0 = s.e_aux;
-              for (int it = ctid; it < nchunks * (kChainRows / 2); it += kChainThreads) {
-                const int c = it / (kChainRows / 2), r2 = (it % (kChainRows / 2)) * 2;
-                uint32_t ra[8], rb[8];
-                switch (p.kinp) {
-                  case 4: first_layer_item<4>(lc, p.lc_b0, xin, p.kin, u0 + c * 8, ch * kChainRows + r2, ra, rb); break;
-                  case 8: first_layer_item<8>(lc, p.lc_b0, xin, p.kin, u0 + c * 8, ch * kChainRows + r2, ra, rb); break;
-                  case 12: first_layer_item<12>(lc, p.lc_b0, xin, p.kin, u0 + c * 8, ch * kChainRows + r2, ra, rb); break;
-                  default: first_layer_item<16>(lc, p.lc_b0, xin, p.kin, u0 + c * 8, ch * kChainRows + r2, ra, rb); break;
-                }
-                uint4 hi4, lo4;
-                const size_t o = ((size_t)c * kChainRows + r2) * 8;
-                tanh_chunk(ra, hi4, lo4);
-                *reinterpret_cast<uint4*>(h_hi + o) = hi4;
-                *reinterpret_cast<uint4*>(h_lo + o) = lo4;
-                tanh_chunk(rb, hi4, lo4);
-                *reinterpret_cast<uint4*>(h_hi + o + 8) = hi4;
-                *reinterpret_cast<uint4*>(h_lo + o + 8) = lo4;
-              }
-            } else if (s.epi == EPI_XINV) {
-              if (part == 0) {   // warp-uniform; inside, lanes 0-15 own the 16 rows of this quadrant
-                const int r = s.stage, d = perm[r];
-                const float yv = ycur[d * kTileM + trow];
-                const float* bo = lc + s.e_aux;
-                const bool has_acc = !(s.flags & 1);
-                float xv = 0.f, ld = 0.f;
-                if (!spline) {
-                  uint32_t rr[2] = {0u, 0u};
-                  if (has_acc) { tcx::tmem_ld16x2_2<0>(lane_base + s.e_col, rr); tcx::tmem_ld_wait(); }
-                  float mu = __uint_as_float(rr[0]) + bo[0];
-                  float sc = fminf(fmaxf(__uint_as_float(rr[1]) + bo[1], p.clip_lo), p.clip_hi);
-                  xv = (yv - mu) * expf(-sc);
-                  ld = sc;
-                } else if (fast_rqs) {
-                  uint32_t rr[24];
-#pragma unroll
-                  for (int e = 0; e < 24; ++e) rr[e] = 0u;
-                  if (has_acc) {
-                    tcx::tmem_ld16x2_8<0>(lane_base + s.e_col, rr);
-                    tcx::tmem_ld16x2_8<0>(lane_base + s.e_col + 8, rr + 8);
-                    tcx::tmem_ld16x2_8<0>(lane_base + s.e_col + 16, rr + 16);
-                    tcx::tmem_ld_wait();
-                  }
-                  if (hw == 0) {
-                    float rf[24];
-#pragma unroll
-                    for (int e = 0; e < 24; ++e) rf[e] = __uint_as_float(rr[e]) + bo[e];
-                    nazb::rqs_fast<8>(yv, p.bound, true, rf, xv, ld);
-                  }
-                } else {
-                  for (int m0 = 0; m0 < p.Mp; m0 += 8) {
-                    uint32_t rr[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) rr[e] = 0u;
-                    if (has_acc) { tcx::tmem_ld16x2_8<0>(lane_base + s.e_col + m0, rr); tcx::tmem_ld_wait(); }
-                    if (hw == 0) {
-#pragma unroll
-                      for (int e = 0; e < 8; ++e)
-                        if (m0 + e < M) scr[(m0 + e) * kTileM] = __uint_as_float(rr[e]) + bo[m0 + e];
-                    }
-                  }
-                  if (hw == 0) {
-                    if (p.kind == NAZB_KIND_RQS) nazb::rational_spline<false>(yv, p.K, p.bound, true, raw, setw, xv, ld);
-                    else nazb::rational_spline<true>(yv, p.K, p.bound, true, raw, setw, xv, ld);
-                  }
-                }
-                if (hw == 0) {
-                  ld_acc += ld;
-                  xin[(C + d) * kTileM + trow] = xv;
-                  if (r == D - 1) {
-                    // end of this flow layer: x becomes the y of the next (earlier) layer, x restarts at 0
-                    for (int dd = 0; dd < D; ++dd) {
-                      ycur[dd * kTileM + trow] = xin[(C + dd) * kTileM + trow];
-                      xin[(C + dd) * kTileM + trow] = 0.f;
-                    }
-                  }
-                }
-              }
-            }
-            if (dbg_me) { DBGI(5) }
-            tcx::tc_fence_before();
-            tcx::fence_async_smem();
-            chain_sync(ch);
-            if (dbg_me) { DBGI(6) }
-            ++dbg_i;
-          }
-          // this layer's constants are no longer needed by this chain
-          if (ctid == 0) tcx::mbar_arrive(lc_empty + (lcnt & 1));
-          ++lcnt;
-        }
-
-        // ---- draw end ----
-        if (part == 0) {
-          float lp = 0.f;
-          const bool mine = row_owner && trow < npts;
-          if (row_owner) {
-            float qd = 0.f;
-            for (int d = 0; d < D; ++d) { float z = ycur[d * kTileM + trow]; qd += 0.5f * z * z; }
-            lp = -qd - 0.5f * D * NAZB_LOG_2PI - ld_acc + ljac[trow];
-          }
-          if (mine) {
-            if (io.out_l) io.out_l[(size_t)si * io.N + n0 + trow] = lp;
-            if (io.lse_max) {
-              float v = lp + (io.log_w ? io.log_w[si] : 0.f);
-              if (!(v <= run_m)) { run_s = run_s * expf(run_m - v) + 1.f; run_m = v; }
-              else if (v > -INFINITY) run_s += expf(v - run_m);
-            }
-            if (io.out_x) {
-              float* dst = io.out_x + ((size_t)si * io.N + n0 + trow) * D;
-              for (int d = 0; d < D; ++d) dst[d] = ycur[d * kTileM + trow];
-            }
-          }
-          if (io.sum_n) {
-            double v = mine ? (double)lp : 0.0;
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) atomicAdd(io.sum_n + si, v);
-          }
-        }
-      }
-      if (io.lse_max && row_owner && trow < npts) {
-        io.lse_max[(size_t)grp * io.N + n0 + trow] = run_m;
-        io.lse_sum[(size_t)grp * io.N + n0 + trow] = run_s;
-      }
-    }
-  }
-  tcx::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tcx::tmem_dealloc(tmem, kTmemCols);
-}
 
 #include "flow_tc_inv3.cuh"
 
@@ -1394,8 +994,7 @@ cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* con
   TcPlan P;
   if (!base_dims(g, P) || !plan_smem(g, P)) return cudaErrorInvalidConfiguration;
   P.ok[1] = build_forward(g, P);
-  P.ok[0] = build_inverse(g, P) && plan_smem_inv(g, P);
-  P.v3_ok = P.ok[0] && plan_smem_inv3(g, P);
+  P.ok[0] = build_inverse(g, P) && plan_smem_inv3(g, P);
   if (!P.ok[0]) { P.steps[0].clear(); P.images[0].clear(); P.layer_bytes[0] = 0; }
   if (!P.ok[1]) return cudaErrorInvalidConfiguration;
   cudaError_t e;
@@ -1447,8 +1046,8 @@ cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* con
     for (int j = 0; j < g.n_hidden; ++j) { lg.lc_b[j] = P.lc_b[j]; lg.hdim[j] = g.hidden[j]; }
     long long total = (long long)S * L * P.lc_floats;
     int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
-    tc_pack_lc_kernel<<<blocks, 256, 0, st>>>(S, L, n_lin, g.D, g.M, P.mp, g.kin, P.kinp, ceil_to(g.hidden[0], 16), g.hidden[0],
-                                              P.lc_floats, lg, P.lc_bout, t->tab_dev, t->tab_dev + ntab, t->tab_dev + 2 * ntab,
+    tc_pack_lc_kernel<<<blocks, 256, 0, st>>>(S, L, n_lin, g.D, g.M, P.mp, g.kin, P.kinp, P.lc_b[0], g.hidden[0],
+                                              2.885390081777927f, P.lc_floats, lg, P.lc_bout, t->tab_dev, t->tab_dev + ntab, t->tab_dev + 2 * ntab,
                                               strides_dev, strides_dev + ntab, h->perm_dev, t->lc_dev);
     nazb_count_launch();
   }
@@ -1475,29 +1074,18 @@ cudaError_t nazb_tc_launch(const nazb_handle* h, const IoArgs& io, int n_groups,
     if (const char* env = getenv("NAZB_PHASE_DELAY")) kp.phase_delay = atoi(env);
     kp.perm = h->perm_dev;
     kp.D = g.D; kp.C = g.C; kp.L = g.L; kp.M = g.M; kp.Mp = P.mp; kp.K = g.K; kp.kind = g.kind; kp.kin = g.kin;
-    kp.kinp = P.kinp; kp.hp_max = P.hp_max; kp.nslots = P.i_nslots;
+    kp.kinp = P.kinp; kp.hp_max = P.hp_max; kp.nslots = P.j_nslots;
+    kp.kr_max = P.kr_max; kp.xf = P.xf ? 1 : 0;
     kp.bound = g.bound; kp.clip_lo = g.clip_lo; kp.clip_hi = g.clip_hi;
-    kp.off_xin = P.i_xin; kp.off_lc = P.i_lc; kp.off_h = P.i_h; kp.off_y = P.i_y; kp.off_xo = P.i_xo;
-    kp.off_misc = P.i_misc; kp.off_scratch = P.i_scratch; kp.off_ring = P.i_ring;
-    const char* v2env = getenv("NAZB_INV_V2");
-    if (P.v3_ok && !(v2env && atoi(v2env))) {
-      kp.kr_max = P.kr_max; kp.nslots = P.j_nslots;
-      kp.off_xin = P.j_xin; kp.off_lc = P.j_lc; kp.off_h = P.j_a; kp.off_y = P.j_y; kp.off_xo = P.j_xo;
-      kp.off_misc = P.j_misc; kp.off_scratch = P.j_scratch; kp.off_ring = P.j_ring;
-      cudaError_t e3 = cudaFuncSetAttribute(flow_tc_inv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.j_smem_bytes);
-      if (e3 != cudaSuccess) return e3;
-      const int n_tiles3 = (io.N + kTileM - 1) / kTileM;
-      int grid3 = (int)std::min<long long>((long long)n_tiles3 * n_groups, h->sm_count);
-      flow_tc_inv3_kernel<<<grid3, kV3Threads, P.j_smem_bytes, st>>>(kp, io, n_groups);
-      nazb_count_launch();
-      return cudaGetLastError();
-    }
-    cudaError_t e = cudaFuncSetAttribute(flow_tc_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.i_smem_bytes);
-    if (e != cudaSuccess) return e;
+    kp.off_xin = P.j_xin; kp.off_lc = P.j_lc; kp.off_h = P.j_a; kp.off_y = P.j_y; kp.off_xo = P.j_xo;
+    kp.off_misc = P.j_misc; kp.off_scratch = P.j_scratch; kp.off_ring = P.j_ring;
+    kp.off_ax = P.j_ax; kp.off_xring = P.j_xring;
     const int n_tiles = (io.N + kTileM - 1) / kTileM;
-    long long items = (long long)n_tiles * n_groups;
-    int grid = (int)std::min<long long>(items, h->sm_count);
-    flow_tc_inv_kernel<<<grid, kInvThreads, P.i_smem_bytes, st>>>(kp, io, n_groups);
+    const int grid = (int)std::min<long long>((long long)n_tiles * n_groups, h->sm_count);
+    auto kern = g_tc_dbg ? flow_tc_inv3_kernel<true> : flow_tc_inv3_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.j_smem_bytes);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kV3Threads, P.j_smem_bytes, st>>>(kp, io, n_groups);
     nazb_count_launch();
     return cudaGetLastError();
   }

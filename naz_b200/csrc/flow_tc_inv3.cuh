@@ -25,14 +25,17 @@ constexpr int kV3Issuer0 = kV3EpiWarps;              // warps 8, 9: MMA issuers 
 constexpr int kV3Producer = kV3EpiWarps + kChains;   // warp 10: TMA producer
 constexpr int kV3Threads = (kV3EpiWarps + kChains + 1) * 32;
 constexpr int kV3MaxSlices = 8;                      // A block <= 128 columns
+constexpr int kXSlotBytes = 4096;                    // small ring: first-layer images (<= 64 units x K = 16, hi + lo)
+constexpr int kXSlots = 4;
+constexpr float kTanhScale = 2.885390081777927f;     // 2 log2(e): pre-activations are scaled so tanh needs no multiply
 
 #define DBG3(slot)                                                                       \
-  if (p.dbg && blockIdx.x == 0 && dbg_i < 128) p.dbg[dbg_i * 16 + (slot)] = clk();
+  if (kDbg && p.dbg && blockIdx.x == 0 && dbg_i < 128) p.dbg[dbg_i * 16 + (slot)] = clk();
 
 // First conditioner layer on CUDA cores: 8 hidden units (n0 .. n0+7) for ONE row whose inputs are in xv.
 template <int KINP>
 __device__ __forceinline__ void first_chunk(const float* __restrict__ lc, int lc_b0, const float* __restrict__ xin,
-                                            int kin, int trow, int n0, uint32_t* out) {
+                                            int kin, int trow, int n0, float* out) {
   float xv[KINP];
 #pragma unroll
   for (int k = 0; k < KINP; ++k) xv[k] = (k < kin) ? xin[k * kTileM + trow] : 0.f;
@@ -49,20 +52,23 @@ __device__ __forceinline__ void first_chunk(const float* __restrict__ lc, int lc
       a = fmaf(w.z, xv[k4 * 4 + 2], a);
       a = fmaf(w.w, xv[k4 * 4 + 3], a);
     }
-    out[e] = __float_as_uint(a);
+    out[e] = a;
   }
 }
 
+template <bool kDbg>
 __global__ void __launch_bounds__(kV3Threads, 1) flow_tc_inv3_kernel(const __grid_constant__ KParamsInv p,
                                                                       const __grid_constant__ IoArgs io, int n_groups) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* w_full = reinterpret_cast<uint64_t*>(smem);            // [nslots] TMA -> issuers
   uint64_t* w_empty = w_full + 8;                                   // [nslots] count = kChains (one commit per issuer)
-  uint64_t* bar_acc = w_empty + 8;                                  // [kChains] issuer -> epilogue warps
+  uint64_t* xw_full = w_empty + 8;                                  // [kXSlots] small ring (first-layer images)
+  uint64_t* xw_empty = xw_full + kXSlots;                           // [kXSlots] count = kChains
+  uint64_t* bar_acc = xw_empty + kXSlots;                           // [kChains] issuer -> epilogue warps
   uint64_t* lc_full = bar_acc + kChains;                            // [2]
   uint64_t* lc_empty = lc_full + 2;                                 // [2], count = kV3EpiWarps
-  uint64_t* a_ready = lc_empty + 2;                                 // [kChains][2 buffers][kV3MaxSlices], count = 4 warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + kChains * 2 * kV3MaxSlices);
+  uint64_t* a_ready = lc_empty + 2;                                 // [kChains][3: buffers 0, 1, A_X][kV3MaxSlices], count = 4 warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + kChains * 3 * kV3MaxSlices);
   float* xin = reinterpret_cast<float*>(smem + p.off_xin);          // [kin][128]: ctx rows, then x rows
   float* lcs = reinterpret_cast<float*>(smem + p.off_lc);           // [2][lc_floats]
   float* ycur = reinterpret_cast<float*>(smem + p.off_y);           // [D][128]
@@ -70,6 +76,8 @@ __global__ void __launch_bounds__(kV3Threads, 1) flow_tc_inv3_kernel(const __gri
   float* ljac = reinterpret_cast<float*>(smem + p.off_misc);        // [128]
   float* scratch = reinterpret_cast<float*>(smem + p.off_scratch);  // [32][128] (generic spline only)
   uint8_t* ring = smem + p.off_ring;
+  uint8_t* xring = smem + p.off_xring;
+  constexpr uint32_t ax_img_bytes = 16 * kChainRows * 2;            // A_X: one K = 16 slice [2 chunks][64 rows][8 halves]
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -81,12 +89,15 @@ __global__ void __launch_bounds__(kV3Threads, 1) flow_tc_inv3_kernel(const __gri
     for (int i = 0; i < p.nslots; ++i) { tcx::mbar_init(w_full + i, 1); tcx::mbar_init(w_empty + i, kChains); }
     for (int i = 0; i < kChains; ++i) tcx::mbar_init(bar_acc + i, 1);
     for (int i = 0; i < 2; ++i) { tcx::mbar_init(lc_full + i, 1); tcx::mbar_init(lc_empty + i, kV3EpiWarps); }
-    for (int i = 0; i < kChains * 2 * kV3MaxSlices; ++i) tcx::mbar_init(a_ready + i, 4);
+    for (int i = 0; i < kXSlots; ++i) { tcx::mbar_init(xw_full + i, 1); tcx::mbar_init(xw_empty + i, kChains); }
+    for (int i = 0; i < kChains * 3 * kV3MaxSlices; ++i) tcx::mbar_init(a_ready + i, 4);
     tcx::mbar_fence_init();
   }
   if (warp == 0) tcx::tmem_alloc(tmem_slot, kTmemCols);
   for (uint32_t i = tid; i < (kChains * 2 * a_buf_bytes) / 16; i += kV3Threads)
     reinterpret_cast<uint4*>(smem + p.off_h)[i] = make_uint4(0, 0, 0, 0);
+  for (uint32_t i = tid; i < (kChains * 2 * ax_img_bytes) / 16; i += kV3Threads)
+    reinterpret_cast<uint4*>(smem + p.off_ax)[i] = make_uint4(0, 0, 0, 0);
   tcx::fence_async_smem();
   tcx::tc_fence_before();
   __syncthreads();
@@ -99,7 +110,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) flow_tc_inv3_kernel(const __gri
   if (warp == kV3Producer) {
     // ===================== TMA producer: weight images + layer constants =====================
     if (lane == 0) {
-      uint32_t cnt = 0, lcnt = 0;
+      uint32_t cnt = 0, xcnt = 0, lcnt = 0;
       for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int grp = (int)(item / n_tiles);
         for (int si = grp; si < io.s_count; si += n_groups) {
@@ -118,6 +129,14 @@ __global__ void __launch_bounds__(kV3Threads, 1) flow_tc_inv3_kernel(const __gri
             for (int st = 0; st < p.nsteps; ++st) {
               const uint32_t wb = p.steps[st].w_bytes;
               if (wb == 0) continue;
+              if (p.steps[st].a_buf == A_X) {
+                const uint32_t slot = xcnt % kXSlots, use = xcnt / kXSlots;
+                tcx::mbar_wait(xw_empty + slot, (use & 1) ^ 1);
+                tcx::mbar_expect_tx(xw_full + slot, wb);
+                tcx::bulk_g2s(xring + (size_t)slot * kXSlotBytes, wl + p.steps[st].w_off, wb, xw_full + slot);
+                ++xcnt;
+                continue;
+              }
               const uint32_t slot = cnt % p.nslots, use = cnt / p.nslots;
               tcx::mbar_wait(w_empty + slot, (use & 1) ^ 1);
               tcx::mbar_expect_tx(w_full + slot, wb);
@@ -133,14 +152,15 @@ __global__ void __launch_bounds__(kV3Threads, 1) flow_tc_inv3_kernel(const __gri
     // Whole warp convergent, tcgen05 instructions predicated on the elected lane (descriptors stay uniform).
     const int ch = warp - kV3Issuer0;
     const uint32_t elected = tcx::elect_one();
-    const uint32_t ring_a = tcx::smem_u32(ring);
+    const uint32_t ring_a = tcx::smem_u32(ring), xring_a = tcx::smem_u32(xring);
     const uint32_t a_base = tcx::smem_u32(smem + p.off_h) + (uint32_t)ch * 2 * a_buf_bytes;
+    const uint32_t ax_base = tcx::smem_u32(smem + p.off_ax) + (uint32_t)ch * 2 * ax_img_bytes;
     constexpr uint32_t lbo_a = kChainRows * 16;
     constexpr uint64_t dhi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;   // SBO = 128 B, descriptor version 1
     const uint32_t d_lane = tmem + ((uint32_t)(ch * 16) << 16);
     uint64_t* my_acc = bar_acc + ch;
-    uint64_t* my_ready = a_ready + ch * 2 * kV3MaxSlices;
-    uint32_t slot = 0, use = 0, buf = 0, apar = 0;   // apar: one parity bit per (buffer, slice) barrier
+    uint64_t* my_ready = a_ready + ch * 3 * kV3MaxSlices;
+    uint32_t slot = 0, use = 0, xslot = 0, xuse = 0, buf = 0, apar = 0;   // apar: one parity bit per (buffer, slice) barrier
     int dbg_i = 0;
     const bool dbg_me = (ch == 0 && lane == 0);
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -154,21 +174,27 @@ __global__ void __launch_bounds__(kV3Threads, 1) flow_tc_inv3_kernel(const __gri
             const int ksteps = p.steps[st].ksteps;
             const uint32_t s_acc = p.steps[st].accumulate, s_last = (p.steps[st].epi != EPI_NONE);
             const uint32_t slice0 = p.steps[st].a_chunk0 >> 1;
+            const bool is_x = (p.steps[st].a_buf == A_X);
+            const uint32_t bsel = is_x ? 2u : buf;
             const uint32_t n_rest = s_n - s_ncrit;
             const uint32_t idesc_c = tcx::make_idesc_f16_m64(s_ncrit);
             const uint32_t idesc_r = tcx::make_idesc_f16_m64(n_rest);
             const uint32_t lbo_b = s_n * 16;
-            const uint32_t b_hi = ring_a + slot * kSlotBytes, b_lo = b_hi + (s_wbytes >> 1);
+            const uint32_t b_hi = is_x ? (xring_a + xslot * kXSlotBytes) : (ring_a + slot * kSlotBytes);
+            const uint32_t b_lo = b_hi + (s_wbytes >> 1);
             const uint32_t lbo_b_hi16 = (lbo_b >> 4) << 16, lbo_a_hi16 = (lbo_a >> 4) << 16;
-            const uint32_t a_hi = a_base + buf * a_buf_bytes, a_lo = a_hi + a_img_bytes;
+            const uint32_t a_hi = is_x ? ax_base : (a_base + buf * a_buf_bytes);
+            const uint32_t a_lo = a_hi + (is_x ? ax_img_bytes : a_img_bytes);
             const uint32_t d_c = d_lane + s_dcol, d_r = d_c + s_ncrit;
-            const uint32_t rest_off = s_ncrit * 16;   // byte offset of image row n_crit
+            const uint32_t ro = s_ncrit;              // image row n_crit = byte offset n_crit * 16, >> 4
+            uint64_t* wf = is_x ? (xw_full + xslot) : (w_full + slot);
+            uint64_t* we = is_x ? (xw_empty + xslot) : (w_empty + slot);
             if (dbg_me) { DBG3(8) }
-            tcx::mbar_wait(w_full + slot, use & 1);
+            tcx::mbar_wait(wf, (is_x ? xuse : use) & 1);
             if (dbg_me) { DBG3(9) }
             for (int k = 0; k < ksteps; ++k) {
-              const uint32_t sl = slice0 + k, bit = 1u << (buf * kV3MaxSlices + sl);
-              tcx::mbar_wait(my_ready + buf * kV3MaxSlices + sl, (apar & bit) ? 1u : 0u);
+              const uint32_t sl = slice0 + k, bit = 1u << (bsel * kV3MaxSlices + sl);
+              tcx::mbar_wait(my_ready + bsel * kV3MaxSlices + sl, (apar & bit) ? 1u : 0u);
               apar ^= bit;
               tcx::tc_fence_after();
               if (dbg_me && k == 0) { DBG3(10) }
@@ -182,16 +208,18 @@ __global__ void __launch_bounds__(kV3Threads, 1) flow_tc_inv3_kernel(const __gri
               tcx::mma_f16_ss_elect(d_c, da_l, db_h, idesc_c, 1u, elected);
               if (s_last && k == ksteps - 1) tcx::mma_commit_elect(my_acc, elected);
               if (n_rest) {
-                const uint32_t ro = rest_off >> 4;
                 tcx::mma_f16_ss_elect(d_r, da_h, db_h + ro, idesc_r, acc0, elected);
                 tcx::mma_f16_ss_elect(d_r, da_h, db_l + ro, idesc_r, 1u, elected);
                 tcx::mma_f16_ss_elect(d_r, da_l, db_h + ro, idesc_r, 1u, elected);
               }
             }
-            tcx::mma_commit_elect(w_empty + slot, elected);   // the slot is free once these MMAs retire
+            tcx::mma_commit_elect(we, elected);   // the slot is free once these MMAs retire
             if (dbg_me) { DBG3(11) }
-            if (++slot == (uint32_t)p.nslots) { slot = 0; ++use; }
-            if (s_last) buf ^= 1;
+            if (is_x) { if (++xslot == kXSlots) { xslot = 0; ++xuse; } }
+            else {
+              if (++slot == (uint32_t)p.nslots) { slot = 0; ++use; }
+              if (s_last) buf ^= 1;
+            }
             ++dbg_i;
           }
         }
@@ -208,27 +236,42 @@ __global__ void __launch_bounds__(kV3Threads, 1) flow_tc_inv3_kernel(const __gri
     const bool spline = p.kind != NAZB_KIND_AFFINE;
     const bool fast_rqs = (p.kind == NAZB_KIND_RQS && p.K == 8);
     const bool owner = (hw == 0);
+    const bool xf = p.xf != 0;
     float* scr = scratch + trow;
     auto raw = [&](int m) { return scr[m * kTileM]; };
     auto setw = [&](int m, float v) { scr[m * kTileM] = v; };
     uint8_t* a_chain = smem + p.off_h + (size_t)ch * 2 * a_buf_bytes;
+    uint8_t* ax_chain = smem + p.off_ax + (size_t)ch * 2 * ax_img_bytes;
     uint64_t* my_acc = bar_acc + ch;
-    uint64_t* my_ready = a_ready + ch * 2 * kV3MaxSlices;
+    uint64_t* my_ready = a_ready + ch * 3 * kV3MaxSlices;
     uint32_t par_acc = 0, lcnt = 0, buf = 0;
     int dbg_i = 0;
     const bool dbg_me = (tid == 0);
+    const uint64_t scale2 = tcx::pk2(kTanhScale, kTanhScale);
 
-    // publish one 16-column K slice of the A block under construction
-    auto publish = [&](int slice) {
-      tcx::fence_async_smem();
-      __syncwarp();
-      if (lane == 0) tcx::mbar_arrive(my_ready + buf * kV3MaxSlices + slice);
-    };
     // write this thread's 8-column chunk `c` (hi / lo fp16) of the A block: layout [chunk][64 rows][8 halves]
     auto store_chunk = [&](int c, const uint4& hi4, const uint4& lo4) {
       uint8_t* dst = a_chain + (size_t)buf * a_buf_bytes + ((size_t)c * kChainRows + crow) * 16;
       *reinterpret_cast<uint4*>(dst) = hi4;
       *reinterpret_cast<uint4*>(dst + a_img_bytes) = lo4;
+    };
+    // publish K slices [s0, s0 + n) of the A block under construction (n <= 2)
+    auto publish = [&](int s0, int n) {
+      tcx::fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tcx::mbar_arrive(my_ready + buf * kV3MaxSlices + s0);
+        if (n > 1) tcx::mbar_arrive(my_ready + buf * kV3MaxSlices + s0 + 1);
+      }
+    };
+    // one element (this row, input column col) of the first-layer A operand [ctx | x | 1]
+    auto ax_store = [&](int col, float v) {
+      const float c = fminf(fmaxf(v, -65504.f), 65504.f);
+      const __half h = __float2half_rn(c);
+      const __half l = __float2half_rn(c - __half2float(h));
+      uint8_t* dst = ax_chain + ((size_t)(col >> 3) * kChainRows + crow) * 16 + (col & 7) * 2;
+      *reinterpret_cast<__half*>(dst) = h;
+      *reinterpret_cast<__half*>(dst + ax_img_bytes) = l;
     };
 
     if (ch == 1 && p.phase_delay > 0) { const long long t0 = clk(); while (clk() - t0 < p.phase_delay) { } }
@@ -255,6 +298,10 @@ __global__ void __launch_bounds__(kV3Threads, 1) flow_tc_inv3_kernel(const __gri
         if (io.lo != nullptr && trow < npts)
           for (int d = 0; d < D; ++d) xorig[d * kTileM + trow] = nazb::bound_fwd(xorig[d * kTileM + trow], io.lo[d], io.hi[d], lj);
         ljac[trow] = lj;
+        if (xf) {   // constant part of the first-layer A operand: context and the bias column
+          for (int c = 0; c < C; ++c) ax_store(c, xin[c * kTileM + trow]);
+          ax_store(p.kin, 1.f);
+        }
       }
 
       for (int si = grp; si < io.s_count; si += n_groups) {
@@ -264,6 +311,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) flow_tc_inv3_kernel(const __gri
           for (int d = 0; d < D; ++d) {
             ycur[d * kTileM + trow] = xorig[d * kTileM + trow];
             xin[(C + d) * kTileM + trow] = 0.f;
+            if (xf) ax_store(C + d, 0.f);
           }
         __syncwarp();
 
@@ -285,7 +333,9 @@ __global__ void __launch_bounds__(kV3Threads, 1) flow_tc_inv3_kernel(const __gri
             }
             if (dbg_me) { DBG3(1) }
             if (s_epi == EPI_TANH) {
+              // block of nch 8-column chunks = nsl K slices; slice s = chunks {2s (half-warp 0), 2s+1 (half-warp 1)}
               const int nch = s_encols >> 3, nsl = (nch + 1) >> 1;
+              const bool prescaled = (s_flags & 4) != 0;   // first-layer block: bias and tanh scale folded into the image
               for (int sb = 0; sb < nsl; sb += 4) {
                 uint32_t r[32];
                 const int ns = min(4, nsl - sb);
@@ -298,46 +348,70 @@ __global__ void __launch_bounds__(kV3Threads, 1) flow_tc_inv3_kernel(const __gri
                 tcx::tc_fence_before();
                 if (dbg_me && sb == 0) { DBG3(2) }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  if (u < ns) {
-                    const int c = (sb + u) * 2 + hw;
-                    uint4 hi4 = make_uint4(0, 0, 0, 0), lo4 = hi4;
-                    if (c < nch) {
-                      const float4* bv = reinterpret_cast<const float4*>(lc + s_eaux + c * 8);
-                      const float4 b0 = bv[0], b1 = bv[1];
-                      uint32_t* ru = r + 8 * u;
-                      ru[0] = __float_as_uint(__uint_as_float(ru[0]) + b0.x); ru[1] = __float_as_uint(__uint_as_float(ru[1]) + b0.y);
-                      ru[2] = __float_as_uint(__uint_as_float(ru[2]) + b0.z); ru[3] = __float_as_uint(__uint_as_float(ru[3]) + b0.w);
-                      ru[4] = __float_as_uint(__uint_as_float(ru[4]) + b1.x); ru[5] = __float_as_uint(__uint_as_float(ru[5]) + b1.y);
-                      ru[6] = __float_as_uint(__uint_as_float(ru[6]) + b1.z); ru[7] = __float_as_uint(__uint_as_float(ru[7]) + b1.w);
-                      tanh_chunk(ru, hi4, lo4);
+                for (int hh = 0; hh < 2; ++hh) {
+                  if (2 * hh < ns) {
+                    const int npub = min(2, ns - 2 * hh);
+                    uint4 hi4[2], lo4[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                      const int c = (sb + 2 * hh + u) * 2 + hw;
+                      const int cl = min(c, nch - 1);
+                      const uint32_t* ru = r + 8 * (2 * hh + u);
+                      uint64_t s2[4];
+                      if (prescaled) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) s2[i] = tcx::pk2(__uint_as_float(ru[2 * i]), __uint_as_float(ru[2 * i + 1]));
+                      } else {
+                        const ulonglong2* bv = reinterpret_cast<const ulonglong2*>(lc + s_eaux + cl * 8);
+                        const ulonglong2 b0 = bv[0], b1 = bv[1];   // biases already multiplied by 2 log2 e
+                        s2[0] = tcx::fma2(tcx::pk2(__uint_as_float(ru[0]), __uint_as_float(ru[1])), scale2, b0.x);
+                        s2[1] = tcx::fma2(tcx::pk2(__uint_as_float(ru[2]), __uint_as_float(ru[3])), scale2, b0.y);
+                        s2[2] = tcx::fma2(tcx::pk2(__uint_as_float(ru[4]), __uint_as_float(ru[5])), scale2, b1.x);
+                        s2[3] = tcx::fma2(tcx::pk2(__uint_as_float(ru[6]), __uint_as_float(ru[7])), scale2, b1.y);
+                      }
+                      tcx::tanh8_scaled(s2, hi4[u], lo4[u]);
+                      if (c >= nch) { hi4[u] = make_uint4(0, 0, 0, 0); lo4[u] = hi4[u]; }   // K padding chunk
                     }
-                    store_chunk(c, hi4, lo4);
-                    publish(sb + u);
+                    if (dbg_me && sb == 0 && hh == 0) { DBG3(4) }
+                    store_chunk((sb + 2 * hh) * 2 + hw, hi4[0], lo4[0]);
+                    if (npub > 1) store_chunk((sb + 2 * hh + 1) * 2 + hw, hi4[1], lo4[1]);
+                    if (dbg_me && sb == 0 && hh == 0) { DBG3(5) }
+                    publish(sb + 2 * hh, npub);
+                    if (dbg_me && sb == 0 && hh == 0) { DBG3(6) }
                   }
                 }
               }
               buf ^= 1;
             } else if (s_epi == EPI_FIRST) {
-              const int nch = s_encols >> 3, nsl = (nch + 1) >> 1;
-              const int u0 = s_eaux;
-              for (int sl = 0; sl < nsl; ++sl) {
-                const int c = sl * 2 + hw;
-                uint4 hi4 = make_uint4(0, 0, 0, 0), lo4 = hi4;
-                if (c < nch) {
-                  uint32_t ra[8];
-                  switch (p.kinp) {
-                    case 4: first_chunk<4>(lc, p.lc_b0, xin, p.kin, trow, u0 + c * 8, ra); break;
-                    case 8: first_chunk<8>(lc, p.lc_b0, xin, p.kin, trow, u0 + c * 8, ra); break;
-                    case 12: first_chunk<12>(lc, p.lc_b0, xin, p.kin, trow, u0 + c * 8, ra); break;
-                    default: first_chunk<16>(lc, p.lc_b0, xin, p.kin, trow, u0 + c * 8, ra); break;
+              if (xf) {
+                // tensor-core first layer: the A operand [ctx | x | 1] was updated in place by the row owners
+                tcx::fence_async_smem();
+                __syncwarp();
+                if (lane == 0) tcx::mbar_arrive(my_ready + 2 * kV3MaxSlices);
+              } else {
+                const int nch = s_encols >> 3, nsl = (nch + 1) >> 1;
+                const int u0 = s_eaux;
+                for (int sl = 0; sl < nsl; ++sl) {
+                  const int c = sl * 2 + hw;
+                  uint4 hi4 = make_uint4(0, 0, 0, 0), lo4 = hi4;
+                  if (c < nch) {
+                    float ra[8];
+                    switch (p.kinp) {   // W0 and b0 are stored multiplied by 2 log2 e
+                      case 4: first_chunk<4>(lc, p.lc_b0, xin, p.kin, trow, u0 + c * 8, ra); break;
+                      case 8: first_chunk<8>(lc, p.lc_b0, xin, p.kin, trow, u0 + c * 8, ra); break;
+                      case 12: first_chunk<12>(lc, p.lc_b0, xin, p.kin, trow, u0 + c * 8, ra); break;
+                      default: first_chunk<16>(lc, p.lc_b0, xin, p.kin, trow, u0 + c * 8, ra); break;
+                    }
+                    uint64_t s2[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) s2[i] = tcx::pk2(ra[2 * i], ra[2 * i + 1]);
+                    tcx::tanh8_scaled(s2, hi4, lo4);
                   }
-                  tanh_chunk(ra, hi4, lo4);
+                  store_chunk(c, hi4, lo4);
+                  publish(sl, 1);
                 }
-                store_chunk(c, hi4, lo4);
-                publish(sl);
+                buf ^= 1;
               }
-              buf ^= 1;
             } else if (s_epi == EPI_XINV) {
               const int r = s_stage, d = perm[r];
               const float yv = ycur[d * kTileM + trow];
@@ -394,7 +468,10 @@ __global__ void __launch_bounds__(kV3Threads, 1) flow_tc_inv3_kernel(const __gri
                   for (int dd = 0; dd < D; ++dd) {
                     ycur[dd * kTileM + trow] = xin[(C + dd) * kTileM + trow];
                     xin[(C + dd) * kTileM + trow] = 0.f;
+                    if (xf) ax_store(C + dd, 0.f);
                   }
+                } else if (xf) {
+                  ax_store(C + d, xv);
                 }
               }
               __syncwarp();   // the row's second thread reads xin in the next FIRST phase

@@ -202,4 +202,49 @@ __device__ __forceinline__ void unpack2(uint32_t h2, float& a, float& b) {
       : "r"(h2));
 }
 
+// ---------------- packed fp32 pairs (Blackwell FFMA2 / FADD2) ----------------
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};\n" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;\n" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;\n" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;\n" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("sub.rn.f32x2 %0, %1, %2;\n" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// 8 pre-activations ALREADY scaled by 2 log2(e), as 4 packed pairs -> tanh -> fp16 hi / lo chunks (16 B each).
+// tanh(x) = 1 - 2 / (2^s + 1), s = 2 x log2 e.  6.5 issue slots per element (2 MUFU + FFMA2/FADD2 halves).
+__device__ __forceinline__ void tanh8_scaled(const uint64_t* s2, uint4& hi4, uint4& lo4) {
+  uint32_t h[4], l[4];
+  const uint64_t one2 = pk2(1.f, 1.f), m2 = pk2(-2.f, -2.f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float a, b;
+    upk2(s2[i], a, b);
+    const uint64_t e2 = add2(pk2(ex2_approx(a), ex2_approx(b)), one2);
+    upk2(e2, a, b);
+    const uint64_t t2 = fma2(pk2(rcp_approx(a), rcp_approx(b)), m2, one2);
+    upk2(t2, a, b);
+    h[i] = pack_hi2(a, b);
+    float fa, fb;
+    unpack2(h[i], fa, fb);
+    upk2(sub2(t2, pk2(fa, fb)), a, b);
+    l[i] = pack_hi2(a, b);
+  }
+  hi4 = make_uint4(h[0], h[1], h[2], h[3]);
+  lo4 = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 }  // namespace tcx

@@ -1,0 +1,60 @@
+// Dev probe: MUFU (ex2 / rcp) throughput per SM and the cost of the tanh -> fp16 hi/lo chunk routine,
+// as a function of resident warps per SM.   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o mufu_probe mufu_probe.cu
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include "../naz_b200/csrc/tc_ptx.cuh"
+
+__global__ void k_mufu(float* out, int iters, long long* cyc) {
+  float v[8];
+  for (int i = 0; i < 8; ++i) v[i] = 0.001f * (threadIdx.x + i);
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = tcx::ex2_approx(v[i]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = tcx::rcp_approx(v[i] + 1.f);
+  }
+  long long t1 = clock64();
+  float s = 0; for (int i = 0; i < 8; ++i) s += v[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+__global__ void k_tanh(float* out, int iters, long long* cyc) {
+  uint64_t s2[4];
+  for (int i = 0; i < 4; ++i) s2[i] = tcx::pk2(0.01f * threadIdx.x + i, 0.02f * threadIdx.x - i);
+  uint32_t acc = 0;
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    uint4 hi, lo;
+    tcx::tanh8_scaled(s2, hi, lo);
+    acc ^= hi.x ^ hi.y ^ hi.z ^ hi.w ^ lo.x ^ lo.y ^ lo.z ^ lo.w;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s2[i] = tcx::add2(s2[i], tcx::pk2(__uint_as_float((acc & 0xff) | 0x3c000000), 0.001f));
+  }
+  long long t1 = clock64();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = __uint_as_float(acc);
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+int main() {
+  float* out; long long* cyc;
+  cudaMalloc(&out, 148 * 1024 * 4); cudaMalloc(&cyc, 148 * 8);
+  const int iters = 2000;
+  for (int warps : {1, 2, 4, 8, 16, 32}) {
+    long long h[148];
+    k_mufu<<<148, warps * 32>>>(out, iters, cyc); cudaDeviceSynchronize();
+    k_mufu<<<148, warps * 32>>>(out, iters, cyc); cudaDeviceSynchronize();
+    cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    double c1 = (double)h[0] / iters;
+    k_tanh<<<148, warps * 32>>>(out, iters, cyc); cudaDeviceSynchronize();
+    cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    double c2 = (double)h[0] / iters;
+    printf("warps/SM %2d: 16 MUFU/thread-iter: %.1f cycles/iter -> %.2f MUFU lane-ops/clk/SM | tanh8 chunk: %.1f cycles/iter -> %.2f MUFU lane-ops/clk/SM\n",
+           warps, c1, 16.0 * warps * 32 / c1, c2, 16.0 * warps * 32 / c2);
+  }
+  printf("%s\n", cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}

@@ -40,6 +40,9 @@ if direction == "inverse":
         line = f"{i:3d} {n:4d} {ks:2d} {names[epi]:5s} {ncols:3d} {wb/1024:5.1f} |"
         if epi:
             line += f" {e1-e0:6d} {max(e2-e1,0):5d} {e3-max(e2,e1):6d} {e3-e0:6d} |"
+            if epi == 1:
+                e4, e5, e6 = t[i][4:7]
+                line += f" half0: tanh {e4-e2:5d} sts {e5-e4:4d} fence+arrive {e6-e5:4d} |"
         else:
             line += " " * 29 + "|"
         if wb:
