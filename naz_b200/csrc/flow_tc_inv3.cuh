@@ -20,9 +20,10 @@
 //     (the writer of block p+2 starts after the commit of push p+1, which retires after every MMA of push p).
 #pragma once
 
-constexpr int kV3EpiWarps = 8;                       // 2 chains x 4 quadrants
-constexpr int kV3Issuer0 = kV3EpiWarps;              // warps 8, 9: MMA issuers of chain 0, 1
-constexpr int kV3Producer = kV3EpiWarps + kChains;   // warp 10: TMA producer
+constexpr int kV3Parts = 2;                          // epilogue warps per (chain, quadrant): part p takes K slices p, p + kV3Parts, ...
+constexpr int kV3EpiWarps = kChains * 4 * kV3Parts;  // part 0 warps also own the rows (spline, first layer, outputs)
+constexpr int kV3Issuer0 = kV3EpiWarps;              // next kChains warps: MMA issuers of chain 0, 1
+constexpr int kV3Producer = kV3EpiWarps + kChains;   // last warp: TMA producer
 constexpr int kV3Threads = (kV3EpiWarps + kChains + 1) * 32;
 constexpr int kV3MaxSlices = 8;                      // A block <= 128 columns
 constexpr int kXSlotBytes = 4096;                    // small ring: first-layer images (<= 64 units x K = 16, hi + lo)
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) flow_tc_inv3_kernel(const __gri
     }
   } else {
     // ===================== epilogue warps: 4 per chain, one per TMEM lane quadrant =====================
-    const int ch = warp >> 2, q = warp & 3;
+    const int ch = warp / (4 * kV3Parts), part = (warp >> 2) % kV3Parts, q = warp & 3;
     const int hw = lane >> 4, lr = lane & 15;
     const int crow = q * 16 + lr;                  // row inside the chain's 64-row sub-tile
     const int trow = ch * kChainRows + crow;       // row inside the 128-point tile
@@ -235,7 +236,8 @@ __global__ void __launch_bounds__(kV3Threads, 1) flow_tc_inv3_kernel(const __gri
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32 + ch * 16) << 16);
     const bool spline = p.kind != NAZB_KIND_AFFINE;
     const bool fast_rqs = (p.kind == NAZB_KIND_RQS && p.K == 8);
-    const bool owner = (hw == 0);
+    const bool rows_mine = (part == 0);            // this warp owns the per-row state of its 16 rows
+    const bool owner = rows_mine && (hw == 0);
     const bool xf = p.xf != 0;
     float* scr = scratch + trow;
     auto raw = [&](int m) { return scr[m * kTileM]; };
@@ -255,14 +257,11 @@ __global__ void __launch_bounds__(kV3Threads, 1) flow_tc_inv3_kernel(const __gri
       *reinterpret_cast<uint4*>(dst) = hi4;
       *reinterpret_cast<uint4*>(dst + a_img_bytes) = lo4;
     };
-    // publish K slices [s0, s0 + n) of the A block under construction (n <= 2)
-    auto publish = [&](int s0, int n) {
+    // publish K slice `sl` of the A block under construction
+    auto publish = [&](int sl) {
       tcx::fence_async_smem();
       __syncwarp();
-      if (lane == 0) {
-        tcx::mbar_arrive(my_ready + buf * kV3MaxSlices + s0);
-        if (n > 1) tcx::mbar_arrive(my_ready + buf * kV3MaxSlices + s0 + 1);
-      }
+      if (lane == 0) tcx::mbar_arrive(my_ready + buf * kV3MaxSlices + sl);
     };
     // one element (this row, input column col) of the first-layer A operand [ctx | x | 1]
     auto ax_store = [&](int col, float v) {
@@ -282,13 +281,13 @@ __global__ void __launch_bounds__(kV3Threads, 1) flow_tc_inv3_kernel(const __gri
       float run_m = -INFINITY, run_s = 0.f;
       // ---- tile load: the 16 rows of this warp ----
       __syncwarp();
-      for (int i = lane; i < 16 * C; i += 32) {
+      for (int i = lane; i < 16 * C && rows_mine; i += 32) {
         const int pt = wrow0 + i / C, c = i % C;
         float v = 0.f;
         if (pt < npts) v = io.ctx[((io.ctx_rows == 1) ? 0 : (size_t)(n0 + pt)) * C + c];
         xin[c * kTileM + pt] = v;
       }
-      for (int i = lane; i < 16 * D; i += 32) {
+      for (int i = lane; i < 16 * D && rows_mine; i += 32) {
         const int pt = wrow0 + i / D, d = i % D;
         xorig[d * kTileM + pt] = (pt < npts) ? io.x[(size_t)(n0 + pt) * D + d] : 0.f;
       }
@@ -336,48 +335,44 @@ __global__ void __launch_bounds__(kV3Threads, 1) flow_tc_inv3_kernel(const __gri
               // block of nch 8-column chunks = nsl K slices; slice s = chunks {2s (half-warp 0), 2s+1 (half-warp 1)}
               const int nch = s_encols >> 3, nsl = (nch + 1) >> 1;
               const bool prescaled = (s_flags & 4) != 0;   // first-layer block: bias and tanh scale folded into the image
-              for (int sb = 0; sb < nsl; sb += 4) {
-                uint32_t r[32];
-                const int ns = min(4, nsl - sb);
-                const uint32_t ta = lane_base + s_ecol + sb * 16;
+              const int nmine = (nsl - part + kV3Parts - 1) / kV3Parts;   // slices part, part + kV3Parts, ...
+              for (int j0 = 0; j0 < nmine; j0 += 2) {
+                uint32_t r[16];
+                const int nj = min(2, nmine - j0);
+                const int sl0 = part + j0 * kV3Parts;
+                const uint32_t ta = lane_base + s_ecol + sl0 * 16;
                 tcx::tmem_ld16x2_8<8>(ta, r);
-                if (ns > 1) tcx::tmem_ld16x2_8<8>(ta + 16, r + 8);
-                if (ns > 2) tcx::tmem_ld16x2_8<8>(ta + 32, r + 16);
-                if (ns > 3) tcx::tmem_ld16x2_8<8>(ta + 48, r + 24);
+                if (nj > 1) tcx::tmem_ld16x2_8<8>(ta + 16 * kV3Parts, r + 8);
                 tcx::tmem_ld_wait();
                 tcx::tc_fence_before();
-                if (dbg_me && sb == 0) { DBG3(2) }
+                if (dbg_me && j0 == 0) { DBG3(2) }
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                  if (2 * hh < ns) {
-                    const int npub = min(2, ns - 2 * hh);
-                    uint4 hi4[2], lo4[2];
+                for (int u = 0; u < 2; ++u) {
+                  if (u < nj) {
+                    const int sl = sl0 + u * kV3Parts;
+                    const int c = sl * 2 + hw;
+                    const int cl = min(c, nch - 1);
+                    const uint32_t* ru = r + 8 * u;
+                    uint64_t s2[4];
+                    if (prescaled) {
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                      const int c = (sb + 2 * hh + u) * 2 + hw;
-                      const int cl = min(c, nch - 1);
-                      const uint32_t* ru = r + 8 * (2 * hh + u);
-                      uint64_t s2[4];
-                      if (prescaled) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) s2[i] = tcx::pk2(__uint_as_float(ru[2 * i]), __uint_as_float(ru[2 * i + 1]));
-                      } else {
-                        const ulonglong2* bv = reinterpret_cast<const ulonglong2*>(lc + s_eaux + cl * 8);
-                        const ulonglong2 b0 = bv[0], b1 = bv[1];   // biases already multiplied by 2 log2 e
-                        s2[0] = tcx::fma2(tcx::pk2(__uint_as_float(ru[0]), __uint_as_float(ru[1])), scale2, b0.x);
-                        s2[1] = tcx::fma2(tcx::pk2(__uint_as_float(ru[2]), __uint_as_float(ru[3])), scale2, b0.y);
-                        s2[2] = tcx::fma2(tcx::pk2(__uint_as_float(ru[4]), __uint_as_float(ru[5])), scale2, b1.x);
-                        s2[3] = tcx::fma2(tcx::pk2(__uint_as_float(ru[6]), __uint_as_float(ru[7])), scale2, b1.y);
-                      }
-                      tcx::tanh8_scaled(s2, hi4[u], lo4[u]);
-                      if (c >= nch) { hi4[u] = make_uint4(0, 0, 0, 0); lo4[u] = hi4[u]; }   // K padding chunk
+                      for (int i = 0; i < 4; ++i) s2[i] = tcx::pk2(__uint_as_float(ru[2 * i]), __uint_as_float(ru[2 * i + 1]));
+                    } else {
+                      const ulonglong2* bv = reinterpret_cast<const ulonglong2*>(lc + s_eaux + cl * 8);
+                      const ulonglong2 b0 = bv[0], b1 = bv[1];   // biases already multiplied by 2 log2 e
+                      s2[0] = tcx::fma2(tcx::pk2(__uint_as_float(ru[0]), __uint_as_float(ru[1])), scale2, b0.x);
+                      s2[1] = tcx::fma2(tcx::pk2(__uint_as_float(ru[2]), __uint_as_float(ru[3])), scale2, b0.y);
+                      s2[2] = tcx::fma2(tcx::pk2(__uint_as_float(ru[4]), __uint_as_float(ru[5])), scale2, b1.x);
+                      s2[3] = tcx::fma2(tcx::pk2(__uint_as_float(ru[6]), __uint_as_float(ru[7])), scale2, b1.y);
                     }
-                    if (dbg_me && sb == 0 && hh == 0) { DBG3(4) }
-                    store_chunk((sb + 2 * hh) * 2 + hw, hi4[0], lo4[0]);
-                    if (npub > 1) store_chunk((sb + 2 * hh + 1) * 2 + hw, hi4[1], lo4[1]);
-                    if (dbg_me && sb == 0 && hh == 0) { DBG3(5) }
-                    publish(sb + 2 * hh, npub);
-                    if (dbg_me && sb == 0 && hh == 0) { DBG3(6) }
+                    uint4 hi4, lo4;
+                    tcx::tanh8_scaled(s2, hi4, lo4);
+                    if (c >= nch) { hi4 = make_uint4(0, 0, 0, 0); lo4 = hi4; }   // K padding chunk
+                    if (dbg_me && j0 == 0 && u == 0) { DBG3(4) }
+                    store_chunk(c, hi4, lo4);
+                    if (dbg_me && j0 == 0 && u == 0) { DBG3(5) }
+                    publish(sl);
+                    if (dbg_me && j0 == 0 && u == 0) { DBG3(6) }
                   }
                 }
               }
@@ -385,13 +380,15 @@ __global__ void __launch_bounds__(kV3Threads, 1) flow_tc_inv3_kernel(const __gri
             } else if (s_epi == EPI_FIRST) {
               if (xf) {
                 // tensor-core first layer: the A operand [ctx | x | 1] was updated in place by the row owners
-                tcx::fence_async_smem();
-                __syncwarp();
-                if (lane == 0) tcx::mbar_arrive(my_ready + 2 * kV3MaxSlices);
+                if (rows_mine) {
+                  tcx::fence_async_smem();
+                  __syncwarp();
+                  if (lane == 0) tcx::mbar_arrive(my_ready + 2 * kV3MaxSlices);
+                }
               } else {
                 const int nch = s_encols >> 3, nsl = (nch + 1) >> 1;
                 const int u0 = s_eaux;
-                for (int sl = 0; sl < nsl; ++sl) {
+                for (int sl = 0; sl < nsl && rows_mine; ++sl) {   // (the row's inputs live with the part-0 warp)
                   const int c = sl * 2 + hw;
                   uint4 hi4 = make_uint4(0, 0, 0, 0), lo4 = hi4;
                   if (c < nch) {
@@ -408,11 +405,11 @@ __global__ void __launch_bounds__(kV3Threads, 1) flow_tc_inv3_kernel(const __gri
                     tcx::tanh8_scaled(s2, hi4, lo4);
                   }
                   store_chunk(c, hi4, lo4);
-                  publish(sl, 1);
+                  publish(sl);
                 }
                 buf ^= 1;
               }
-            } else if (s_epi == EPI_XINV) {
+            } else if (s_epi == EPI_XINV && rows_mine) {
               const int r = s_stage, d = perm[r];
               const float yv = ycur[d * kTileM + trow];
               const float* bo = lc + s_eaux;
@@ -486,7 +483,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) flow_tc_inv3_kernel(const __gri
         }
 
         // ---- draw end ----
-        {
+        if (rows_mine) {
           float lp = 0.f;
           const bool mine = owner && trow < npts;
           if (owner) {

@@ -19,15 +19,18 @@ ctx = torch.from_numpy(rng.uniform(size=(1, C)).astype(np.float32)).cuda() if C 
 z = torch.from_numpy(rng.normal(size=(N, D)).astype(np.float32)).cuda()
 for engname in os.environ.get("ENGS", "tcgen05,simt").split(","):
     eng = engine_for(spec, draws, engine=engname)
-    for direction in ("inverse", "forward"):
+    for direction in os.environ.get("DIRS", "inverse,forward").split(","):
         def run():
             if direction == "inverse":
                 return eng.inverse(x, ctx, want_lp=False, want_lse=True, n_groups=1)
             return eng.forward(z, ctx)
         run(); torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); run(); e1.record(); torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
+        times = []
+        for _ in range(int(os.environ.get("REPS", "3"))):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); run(); e1.record(); torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        ms = min(times)
         ev = S * N / (ms * 1e-3)
         fl = eng.shape.flops_per_eval() * ev
         print(f"{which} {engname:8s} {eng.engine_for(direction):8s} {direction:8s} S={S} N={N}: {ms:9.2f} ms  {ev/1e6:8.2f} Mevals/s  {fl/1e12:7.2f} TF/s algorithmic  -> 1e9 evals in {1e9/ev:6.1f} s")
