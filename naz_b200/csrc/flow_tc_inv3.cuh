@@ -423,22 +423,26 @@ __global__ void __launch_bounds__(kV3Threads, 1) flow_tc_inv3_kernel(const __gri
                 xv = (yv - mu) * expf(-sc);
                 ld = sc;
               } else if (fast_rqs) {
-                uint32_t rr[24];
+                // the two lanes of a row split the spline: half-warp 0 takes the widths, half-warp 1 the heights
+                uint32_t ro[8], rd[8];
 #pragma unroll
-                for (int e = 0; e < 24; ++e) rr[e] = 0u;
+                for (int e = 0; e < 8; ++e) { ro[e] = 0u; rd[e] = 0u; }
                 if (has_acc) {
-                  tcx::tmem_ld16x2_8<0>(lane_base + s_ecol, rr);
-                  tcx::tmem_ld16x2_8<0>(lane_base + s_ecol + 8, rr + 8);
-                  tcx::tmem_ld16x2_8<0>(lane_base + s_ecol + 16, rr + 16);
+                  tcx::tmem_ld16x2_8<8>(lane_base + s_ecol, ro);        // cols 0-7 (w) | 8-15 (h)
+                  tcx::tmem_ld16x2_8<0>(lane_base + s_ecol + 16, rd);   // cols 16-23 (derivatives) to both
                   tcx::tmem_ld_wait();
                 }
                 if (dbg_me) { DBG3(2) }
-                if (owner) {
-                  float rf[24];
-#pragma unroll
-                  for (int e = 0; e < 24; ++e) rf[e] = __uint_as_float(rr[e]) + bo[e];
-                  nazb::rqs_fast<8>(yv, p.bound, true, rf, xv, ld);
-                }
+                const float4* bw = reinterpret_cast<const float4*>(bo + hw * 8);
+                const float4* bd = reinterpret_cast<const float4*>(bo + 16);
+                const float4 w0 = bw[0], w1 = bw[1], e0 = bd[0], e1 = bd[1];
+                const float own[8] = {__uint_as_float(ro[0]) + w0.x, __uint_as_float(ro[1]) + w0.y, __uint_as_float(ro[2]) + w0.z,
+                                      __uint_as_float(ro[3]) + w0.w, __uint_as_float(ro[4]) + w1.x, __uint_as_float(ro[5]) + w1.y,
+                                      __uint_as_float(ro[6]) + w1.z, __uint_as_float(ro[7]) + w1.w};
+                const float dr[8] = {__uint_as_float(rd[0]) + e0.x, __uint_as_float(rd[1]) + e0.y, __uint_as_float(rd[2]) + e0.z,
+                                     __uint_as_float(rd[3]) + e0.w, __uint_as_float(rd[4]) + e1.x, __uint_as_float(rd[5]) + e1.y,
+                                     __uint_as_float(rd[6]) + e1.z, 0.f};
+                nazb::rqs8_inv_pair(yv, p.bound, own, dr, hw, xv, ld);
               } else {
                 for (int m0 = 0; m0 < p.Mp; m0 += 8) {
                   uint32_t rr[8];
