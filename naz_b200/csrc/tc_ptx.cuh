@@ -224,24 +224,43 @@ __device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
   asm("sub.rn.f32x2 %0, %1, %2;\n" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;\n" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 // 8 pre-activations ALREADY scaled by 2 log2(e), as 4 packed pairs -> tanh -> fp16 hi / lo chunks (16 B each).
-// tanh(x) = 1 - 2 / (2^s + 1), s = 2 x log2 e.  6.5 issue slots per element (2 MUFU + FFMA2/FADD2 halves).
+// tanh(x) = 1 - 2 / (2^s + 1), s = 2 x log2 e.  MUFU is the scarce pipe of this engine (16 lanes/clk/SM), so the
+// four reciprocals of a group share ONE rcp: with y = 2^s + 1, r = 1 / (y0 y1 y2 y3), 1/y0 = r (y1 y3) y2, ...
+// (three extra roundings, ~2 ulp on a value <= 1).  s is clamped to <= 30, where tanh already rounds to 1 in fp32,
+// so the product of four y stays below 2^121.  1.25 MUFU + ~7 other issue slots per element.
 __device__ __forceinline__ void tanh8_scaled(const uint64_t* s2, uint4& hi4, uint4& lo4) {
   uint32_t h[4], l[4];
   const uint64_t one2 = pk2(1.f, 1.f), m2 = pk2(-2.f, -2.f);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float a, b;
-    upk2(s2[i], a, b);
-    const uint64_t e2 = add2(pk2(ex2_approx(a), ex2_approx(b)), one2);
-    upk2(e2, a, b);
-    const uint64_t t2 = fma2(pk2(rcp_approx(a), rcp_approx(b)), m2, one2);
-    upk2(t2, a, b);
-    h[i] = pack_hi2(a, b);
+  for (int g = 0; g < 2; ++g) {
+    float a, b, c, d;
+    upk2(s2[2 * g], a, b);
+    upk2(s2[2 * g + 1], c, d);
+    const uint64_t y01 = add2(pk2(ex2_approx(fminf(a, 30.f)), ex2_approx(fminf(b, 30.f))), one2);
+    const uint64_t y23 = add2(pk2(ex2_approx(fminf(c, 30.f)), ex2_approx(fminf(d, 30.f))), one2);
+    float pac, pbd;
+    upk2(mul2(y01, y23), pac, pbd);                       // (y0 y2, y1 y3)
+    const float r = rcp_approx(pac * pbd);
+    const uint64_t R = mul2(pk2(r, r), pk2(pbd, pac));    // (r y1 y3, r y0 y2)
+    const uint64_t t01 = fma2(mul2(R, y23), m2, one2);    // 1 - 2 / y0, 1 - 2 / y1
+    const uint64_t t23 = fma2(mul2(R, y01), m2, one2);    // 1 - 2 / y2, 1 - 2 / y3
     float fa, fb;
-    unpack2(h[i], fa, fb);
-    upk2(sub2(t2, pk2(fa, fb)), a, b);
-    l[i] = pack_hi2(a, b);
+    upk2(t01, a, b);
+    h[2 * g] = pack_hi2(a, b);
+    unpack2(h[2 * g], fa, fb);
+    upk2(sub2(t01, pk2(fa, fb)), a, b);
+    l[2 * g] = pack_hi2(a, b);
+    upk2(t23, a, b);
+    h[2 * g + 1] = pack_hi2(a, b);
+    unpack2(h[2 * g + 1], fa, fb);
+    upk2(sub2(t23, pk2(fa, fb)), a, b);
+    l[2 * g + 1] = pack_hi2(a, b);
   }
   hi4 = make_uint4(h[0], h[1], h[2], h[3]);
   lo4 = make_uint4(l[0], l[1], l[2], l[3]);

@@ -43,6 +43,7 @@ SHAPES = [
     ("nsa", 16, 4, [150] * 3, 4, 2, 200, "quadratic"),       # cfg 5 spline, two output chunks
     ("nsa", 3, 2, [32, 40], 3, 2, 300, "linear"),            # linear-order spline
     ("maf", 5, 0, [37, 21], 3, 2, 257, "quadratic"),         # odd widths, unconditional, ragged tile
+    ("maf", 12, 4, [150] * 3, 4, 2, 200, "quadratic"),       # D + C = 16: first conditioner layer on CUDA cores (no K = 16 slice left for the bias column)
 ]
 
 
@@ -83,6 +84,22 @@ def test_golden_fixtures(name, engine):
     xs, ld = eng.forward(T(g["zin"].astype(np.float32)), ctx, bounds, want_logdet=True)
     check(xs, g["xs"], "samples")
     check(ld, g["ld"], "ld", atol=1e-4)
+
+
+def test_first_layer_cuda_core_fallback_matches_tensor_core_path(monkeypatch):
+    """The inverse kernel runs the first conditioner layer either as a K = 16 tcgen05 contraction or, when TMEM / the K slice
+    has no room, on CUDA cores from the layer constants; both must agree with the oracle on the headline shape."""
+    spec, draws, _, rng = make_case("nsa", 4, 2, [150] * 3, 16, 2, seed=21)
+    x = (rng.normal(size=(300, 4)) * 1.5).astype(np.float32)
+    ctx = rng.uniform(size=(300, 2)).astype(np.float32)
+    lp_ref, z_ref = fo.log_prob_draws(spec, to64(draws), x.astype(np.float64), ctx.astype(np.float64))
+    for no_xf in ("0", "1"):
+        monkeypatch.setenv("NAZB_NO_XF", no_xf)
+        eng = engine_for(spec, draws, engine="tcgen05")
+        assert eng.engine_for("inverse") == "tcgen05"
+        out = eng.inverse(T(x), T(ctx), want_z=True, want_lp=True)
+        check(out["lp"], lp_ref, f"lp (NAZB_NO_XF={no_xf})")
+        check(out["z"], z_ref, f"z (NAZB_NO_XF={no_xf})")
 
 
 def test_incremental_equals_reference_d_pass_schedule():
