@@ -82,6 +82,7 @@ struct TcPlan {
   int kr_max = 0;
   bool xf = false;      // first conditioner layer on tensor cores (K = 16 slice [ctx | x | 1])
   uint32_t j_ax = 0, j_xring = 0;
+  int xslot_bytes = 0;  // small-ring slot: the widest first-layer image (units x K = 16, hi + lo), rounded up to 1 KB
   uint32_t j_xin = 0, j_lc = 0, j_a = 0, j_y = 0, j_xo = 0, j_misc = 0, j_scratch = 0, j_ring = 0;
   int j_nslots = 0;
   size_t j_smem_bytes = 0;
@@ -124,6 +125,7 @@ struct KParamsInv {
   int kr_max;                      // columns of one A block buffer
   int xf;                          // first conditioner layer on tensor cores
   uint32_t off_ax, off_xring;
+  int xslot_bytes;
   float bound, clip_lo, clip_hi;
   uint32_t off_xin, off_lc, off_h, off_y, off_xo, off_misc, off_scratch, off_ring;
 };
@@ -254,8 +256,9 @@ bool build_inverse(const FlowGeom& g, TcPlan& P) {
   int xw = 0;
   for (int r = 0; r < D; ++r) xw = std::max(xw, ceil_to(g.blk[0][r + 1], 8) - (g.blk[0][r] & ~7));
   const int T_PRE1 = col;
-  P.xf = (g.kin + 1 <= 16) && (xw <= 64) && (col + ceil_to(xw, 16) <= kTmemCols);
+  P.xf = (g.kin + 1 <= 16) && (xw <= 128) && (col + ceil_to(xw, 16) <= kTmemCols);
   if (const char* env = getenv("NAZB_NO_XF")) if (atoi(env)) P.xf = false;
+  P.xslot_bytes = ceil_to(xw * 16 * 4, 1024);
   // layer constants: [W0 * c (Hp0 x kinp; CUDA-core first layer only) | b_0 * c .. b_{nh-1} * c | b_out], c = 2 log2 e
   P.kinp = ceil_to(g.kin, 4);
   int off = P.xf ? 0 : hp(0) * P.kinp;
@@ -348,7 +351,7 @@ bool plan_smem_inv3(const FlowGeom& g, TcPlan& P) {
   off = (off + 127) & ~127u;
   P.j_a = off;       off += 2u * 2u * (uint32_t)P.kr_max * (kTileM / 2) * 2 * 2;   // [chain][buffer][hi | lo]
   P.j_ax = off;      off += 2u * 2u * 16u * (kTileM / 2) * 2;                      // [chain][hi | lo] one K = 16 slice
-  P.j_xring = off;   off += P.xf ? 4u * 4096u : 0u;                                // kXSlots x kXSlotBytes
+  P.j_xring = off;   off += P.xf ? 4u * (uint32_t)P.xslot_bytes : 0u;                  // kXSlots small-ring slots
   P.j_y = off;       off += (uint32_t)g.D * kTileM * 4;
   P.j_xo = off;      off += (uint32_t)g.D * kTileM * 4;
   P.j_misc = off;    off += kTileM * 4;
@@ -1079,7 +1082,7 @@ cudaError_t nazb_tc_launch(const nazb_handle* h, const IoArgs& io, int n_groups,
     kp.bound = g.bound; kp.clip_lo = g.clip_lo; kp.clip_hi = g.clip_hi;
     kp.off_xin = P.j_xin; kp.off_lc = P.j_lc; kp.off_h = P.j_a; kp.off_y = P.j_y; kp.off_xo = P.j_xo;
     kp.off_misc = P.j_misc; kp.off_scratch = P.j_scratch; kp.off_ring = P.j_ring;
-    kp.off_ax = P.j_ax; kp.off_xring = P.j_xring;
+    kp.off_ax = P.j_ax; kp.off_xring = P.j_xring; kp.xslot_bytes = P.xslot_bytes;
     const int n_tiles = (io.N + kTileM - 1) / kTileM;
     const int grid = (int)std::min<long long>((long long)n_tiles * n_groups, h->sm_count);
     auto kern = g_tc_dbg ? flow_tc_inv3_kernel<true> : flow_tc_inv3_kernel<false>;

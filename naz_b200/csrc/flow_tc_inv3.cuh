@@ -26,7 +26,6 @@ constexpr int kV3Issuer0 = kV3EpiWarps;              // next kChains warps: MMA 
 constexpr int kV3Producer = kV3EpiWarps + kChains;   // last warp: TMA producer
 constexpr int kV3Threads = (kV3EpiWarps + kChains + 1) * 32;
 constexpr int kV3MaxSlices = 8;                      // A block <= 128 columns
-constexpr int kXSlotBytes = 4096;                    // small ring: first-layer images (<= 64 units x K = 16, hi + lo)
 constexpr int kXSlots = 4;
 constexpr float kTanhScale = 2.885390081777927f;     // 2 log2(e): pre-activations are scaled so tanh needs no multiply
 
@@ -134,7 +133,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) flow_tc_inv3_kernel(const __gri
                 const uint32_t slot = xcnt % kXSlots, use = xcnt / kXSlots;
                 tcx::mbar_wait(xw_empty + slot, (use & 1) ^ 1);
                 tcx::mbar_expect_tx(xw_full + slot, wb);
-                tcx::bulk_g2s(xring + (size_t)slot * kXSlotBytes, wl + p.steps[st].w_off, wb, xw_full + slot);
+                tcx::bulk_g2s(xring + (size_t)slot * p.xslot_bytes, wl + p.steps[st].w_off, wb, xw_full + slot);
                 ++xcnt;
                 continue;
               }
@@ -181,7 +180,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) flow_tc_inv3_kernel(const __gri
             const uint32_t idesc_c = tcx::make_idesc_f16_m64(s_ncrit);
             const uint32_t idesc_r = tcx::make_idesc_f16_m64(n_rest);
             const uint32_t lbo_b = s_n * 16;
-            const uint32_t b_hi = is_x ? (xring_a + xslot * kXSlotBytes) : (ring_a + slot * kSlotBytes);
+            const uint32_t b_hi = is_x ? (xring_a + xslot * (uint32_t)p.xslot_bytes) : (ring_a + slot * kSlotBytes);
             const uint32_t b_lo = b_hi + (s_wbytes >> 1);
             const uint32_t lbo_b_hi16 = (lbo_b >> 4) << 16, lbo_a_hi16 = (lbo_a >> 4) << 16;
             const uint32_t a_hi = is_x ? ax_base : (a_base + buf * a_buf_bytes);

@@ -33,6 +33,14 @@ def all_gather_lse(pmax: torch.Tensor, psum: torch.Tensor, S_total: int, log_w_g
     if pmax.dim() == 1:
         pmax, psum = pmax.unsqueeze(0), psum.unsqueeze(0)
     world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if pmax.shape[0] > 1 and world > 1:
+        # several draw groups per rank: fold them into ONE (max, sum) pair first so the collective stays [2,1,N]
+        if pmax.is_cuda:
+            from .engine import lse_finish
+            loc = lse_finish(pmax.contiguous(), psum.contiguous(), 0.0)
+        else:
+            loc = combine_lse_partials(pmax, psum, 0.0)
+        pmax, psum = loc.unsqueeze(0), torch.ones_like(loc).unsqueeze(0)
     local = torch.stack([pmax, psum])                      # [2, g, N]
     if world > 1:
         buf = [torch.empty_like(local) for _ in range(world)]
