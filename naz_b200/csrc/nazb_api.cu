@@ -226,6 +226,8 @@ static int pick_groups(const nazb_handle* h, int N, int s_count, int requested) 
   long long want = 4LL * h->sm_count * 2;
   long long gq = (want + tiles - 1) / tiles;
   if (gq < 1) gq = 1;
+  // large N: ~8 draws per group, so a group's weight images stay L2-resident while the CTAs sweep the point tiles
+  if (tiles >= 8LL * h->sm_count && gq < s_count / 8) gq = s_count / 8;
   if (gq > s_count) gq = s_count;
   if (gq > 65535) gq = 65535;
   return (int)gq;
