@@ -80,6 +80,11 @@ struct TcPlan {
   int kinp = 0, lc_floats = 0, lc_b[NAZB_MAX_HIDDEN_LAYERS] = {0}, lc_bout = 0;
   // v3 inverse kernel: double-buffered A blocks of kr_max columns per chain
   int kr_max = 0;
+  // slice-pipelined forward kernel (flow_tc_fwd3.cuh)
+  bool fwd3 = false;
+  int f_lc_floats = 0, f_lc_b[NAZB_MAX_HIDDEN_LAYERS] = {0}, f_lc_bout = 0, f_nslots = 0;
+  uint32_t f_ax = 0, f_a = 0, f_x = 0, f_ctx = 0, f_misc = 0, f_lc = 0, f_ring = 0;
+  size_t f_smem_bytes = 0;
   bool xf = false;      // first conditioner layer on tensor cores (K = 16 slice [ctx | x | 1])
   uint32_t j_ax = 0, j_xring = 0;
   int xslot_bytes = 0;  // small-ring slot: the widest first-layer image (units x K = 16, hi + lo), rounded up to 1 KB
@@ -95,6 +100,7 @@ struct TcState {
   const float** tab_dev = nullptr;   // [3][L * n_lin] W / b / mask pointer tables
   size_t draw_bytes[2] = {0, 0};
   float* lc_dev = nullptr;           // [S][L][lc_floats]
+  float* lcf_dev = nullptr;          // forward layer constants [S][L][f_lc_floats]
 };
 
 constexpr int kMaxSteps = 80;
@@ -233,6 +239,72 @@ bool build_forward(const FlowGeom& g, TcPlan& P) {
   }
   P.layer_bytes[1] = b.w_off;
   return (int)P.steps[1].size() <= kMaxSteps;
+}
+
+// Forward program for the slice-pipelined kernel (flow_tc_fwd3.cuh): per flow layer
+//   XF   [ctx | x | 1] (K = 16) -> pre, tanh;   L_j  h_{j-1} -> pre (other buffer), + bias, tanh;   OUT chunks -> transform.
+// Biases of L_j and OUT come from the layer constants; d_col = 0xFFFF means "the pre-activation buffer of this phase".
+bool build_forward3(const FlowGeom& g, TcPlan& P) {
+  const int nh = g.n_hidden, D = g.D, M = g.M;
+  if (g.kin + 1 > 16) return false;
+  if (!(g.kind == NAZB_KIND_AFFINE || (g.kind == NAZB_KIND_RQS && g.K == 8))) return false;
+  if (P.hp_max > 256) return false;
+  const int T_OUT = 2 * P.hp_max;
+  if (T_OUT + 16 > kTmemCols) return false;
+  int dims_per_chunk = std::min(D, std::min(256, kTmemCols - T_OUT) / M);
+  // single output chunk only: the output accumulator is not double-buffered, so a second chunk's MMAs would have to wait
+  // for the transform epilogue of the first (the old dense kernel handles those shapes)
+  if (dims_per_chunk < D) return false;
+  auto hp = [&](int j) { return ceil_to(g.hidden[j], 16); };
+  // layer constants: [b_1 * c | ... | b_{nh-1} * c | b_out (rank-major, stride M)]
+  int off = 0;
+  P.f_lc_b[0] = 0;
+  for (int j = 1; j < nh; ++j) { P.f_lc_b[j] = off; off += hp(j); }
+  P.f_lc_bout = off; off += ceil_to(D * M, 4);
+  P.f_lc_floats = ceil_to(off, 4);
+  P.steps[1].clear(); P.images[1].clear();
+  Builder b{P.steps[1], P.images[1]};
+  {
+    Step t = mk_epi(EPI_TANH, 0, hp(0), 0);
+    t.flags = 4;
+    Image im = mk_img(0, hp(0), 16, 0, 0, 0, 0, 0, 0, g.kin, g.kin, 0);
+    im.scale = 2.885390081777927f;
+    b.gemm(A_X, 0, 16, hp(0), 0xFFFF, 3, 0, im, t);
+  }
+  for (int j = 1; j < nh; ++j) {
+    Step t = mk_epi(EPI_TANH, 0, hp(j), 0);
+    t.e_aux = (uint16_t)P.f_lc_b[j];
+    b.gemm(A_H, 0, hp(j - 1), hp(j), 0xFFFF, 3, 0, mk_img(j, hp(j), hp(j - 1), 0, 0, 0, 0, 0, 0, g.hidden[j - 1], -1, 0), t);
+  }
+  bool first_chunk = true;
+  for (int r0 = 0; r0 < D; r0 += dims_per_chunk) {
+    int r1 = std::min(D, r0 + dims_per_chunk);
+    int n = ceil_to((r1 - r0) * M, 16);
+    Step t = mk_epi(EPI_XFWD, T_OUT, 0, 0, r0, r1 - r0);
+    t.e_aux = (uint16_t)(P.f_lc_bout + r0 * M);
+    size_t s0 = P.steps[1].size();
+    b.gemm(A_H, 0, hp(nh - 1), n, T_OUT, 3, 0, mk_img(nh, n, hp(nh - 1), 2, 0, r0, r1, 0, 0, g.hidden[nh - 1], -1, 0), t);
+    if (!first_chunk)
+      for (size_t i = s0; i < P.steps[1].size(); ++i) P.steps[1][i].flags |= 8;   // A slices already waited for
+    first_chunk = false;
+  }
+  P.layer_bytes[1] = b.w_off;
+  if ((int)P.steps[1].size() > kMaxSteps) return false;
+  // shared memory
+  uint32_t o = 1024;
+  P.f_ax = o;   o += 2u * 16u * kTileM * 2;
+  P.f_a = o;    o += 2u * (uint32_t)P.hp_max * kTileM * 2;
+  P.f_x = o;    o += (uint32_t)D * kTileM * 4;
+  P.f_ctx = o;  o += (uint32_t)std::max(1, g.C) * kTileM * 4;
+  P.f_misc = o; o += 4u * kTileM * 4;      // kF3Parts log-det partials
+  P.f_lc = o;   o += 2u * (uint32_t)P.f_lc_floats * 4;
+  o = (o + 127) & ~127u;
+  P.f_ring = o;
+  const uint32_t cap = 227 * 1024;
+  if (o + 2 * kSlotBytes > cap) return false;
+  P.f_nslots = std::min(6u, (cap - o) / kSlotBytes);
+  P.f_smem_bytes = o + (size_t)P.f_nslots * kSlotBytes;
+  return true;
 }
 
 // Inverse program, v2.  Per flow layer, stage r = 0..D-1 (finalises the dimension of rank r):
@@ -939,6 +1011,7 @@ constexpr int kChains = 2;
 constexpr int kChainRows = kTileM / kChains;          // 64
 
 #include "flow_tc_inv3.cuh"
+#include "flow_tc_fwd3.cuh"
 
 }  // namespace
 
@@ -972,6 +1045,7 @@ void nazb_tc_destroy(nazb_handle* h) {
   }
   if (t->tab_dev) cudaFree(t->tab_dev);
   if (t->lc_dev) cudaFree(t->lc_dev);
+  if (t->lcf_dev) cudaFree(t->lcf_dev);
   delete t;
   h->tc = nullptr;
 }
@@ -979,7 +1053,8 @@ void nazb_tc_destroy(nazb_handle* h) {
 int64_t nazb_tc_packed_bytes(const nazb_handle* h) {
   const TcState* t = static_cast<const TcState*>(h->tc);
   if (!t) return 0;
-  return (int64_t)h->desc.S * (int64_t)(t->draw_bytes[0] + t->draw_bytes[1] + (t->lc_dev ? sizeof(float) * (size_t)h->geom.L * t->plan.lc_floats : 0));
+  return (int64_t)h->desc.S * (int64_t)(t->draw_bytes[0] + t->draw_bytes[1] + (t->lc_dev ? sizeof(float) * (size_t)h->geom.L * t->plan.lc_floats : 0) +
+                                     (t->lcf_dev ? sizeof(float) * (size_t)h->geom.L * t->plan.f_lc_floats : 0));
 }
 
 bool nazb_tc_direction_ok(const nazb_handle* h, int dir) {
@@ -996,7 +1071,9 @@ cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* con
   // (re)build the programs now that the MADE block structure is known
   TcPlan P;
   if (!base_dims(g, P) || !plan_smem(g, P)) return cudaErrorInvalidConfiguration;
-  P.ok[1] = build_forward(g, P);
+  P.fwd3 = !(getenv("NAZB_FWD_OLD") && atoi(getenv("NAZB_FWD_OLD"))) && build_forward3(g, P);
+  if (!P.fwd3) { P.steps[1].clear(); P.images[1].clear(); }
+  P.ok[1] = P.fwd3 || build_forward(g, P);
   P.ok[0] = build_inverse(g, P) && plan_smem_inv3(g, P);
   if (!P.ok[0]) { P.steps[0].clear(); P.images[0].clear(); P.layer_bytes[0] = 0; }
   if (!P.ok[1]) return cudaErrorInvalidConfiguration;
@@ -1054,6 +1131,18 @@ cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* con
                                               strides_dev, strides_dev + ntab, h->perm_dev, t->lc_dev);
     nazb_count_launch();
   }
+  if (t->lcf_dev) { cudaFree(t->lcf_dev); t->lcf_dev = nullptr; }
+  if (P.fwd3) {
+    if ((e = cudaMalloc(&t->lcf_dev, sizeof(float) * (size_t)S * L * P.f_lc_floats)) != cudaSuccess) return e;
+    LcGeom lg{};
+    for (int j = 0; j < g.n_hidden; ++j) { lg.lc_b[j] = P.f_lc_b[j]; lg.hdim[j] = g.hidden[j]; }
+    long long total = (long long)S * L * P.f_lc_floats;
+    int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
+    tc_pack_lc_kernel<<<blocks, 256, 0, st>>>(S, L, n_lin, g.D, g.M, g.M, g.kin, P.kinp > 0 ? P.kinp : 4, 0, g.hidden[0],
+                                              2.885390081777927f, P.f_lc_floats, lg, P.f_lc_bout, t->tab_dev, t->tab_dev + ntab,
+                                              t->tab_dev + 2 * ntab, strides_dev, strides_dev + ntab, h->perm_dev, t->lcf_dev);
+    nazb_count_launch();
+  }
   t->plan = P;
   return cudaGetLastError();
 }
@@ -1089,6 +1178,28 @@ cudaError_t nazb_tc_launch(const nazb_handle* h, const IoArgs& io, int n_groups,
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.j_smem_bytes);
     if (e != cudaSuccess) return e;
     kern<<<grid, kV3Threads, P.j_smem_bytes, st>>>(kp, io, n_groups);
+    nazb_count_launch();
+    return cudaGetLastError();
+  }
+  if (P.fwd3) {
+    KParamsFwd3 kp{};
+    kp.nsteps = (int)P.steps[1].size();
+    for (int i = 0; i < kp.nsteps; ++i) kp.steps[i] = P.steps[1][i];
+    kp.wimg = t->wimg[1];
+    kp.draw_bytes = t->draw_bytes[1];
+    kp.layer_bytes = P.layer_bytes[1];
+    kp.lc = t->lcf_dev; kp.lc_floats = P.f_lc_floats;
+    kp.perm = h->perm_dev;
+    kp.D = g.D; kp.C = g.C; kp.L = g.L; kp.M = g.M; kp.K = g.K; kp.kind = g.kind; kp.kin = g.kin;
+    kp.hp_max = P.hp_max; kp.nslots = P.f_nslots; kp.t_pre1 = P.hp_max;
+    kp.bound = g.bound; kp.clip_lo = g.clip_lo; kp.clip_hi = g.clip_hi;
+    kp.off_ax = P.f_ax; kp.off_a = P.f_a; kp.off_x = P.f_x; kp.off_ctx = P.f_ctx; kp.off_misc = P.f_misc;
+    kp.off_lc = P.f_lc; kp.off_ring = P.f_ring;
+    cudaError_t e = cudaFuncSetAttribute(flow_tc_fwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.f_smem_bytes);
+    if (e != cudaSuccess) return e;
+    const int n_tiles = (io.N + kTileM - 1) / kTileM;
+    const int grid = (int)std::min<long long>((long long)n_tiles * n_groups, h->sm_count);
+    flow_tc_fwd3_kernel<<<grid, kF3Threads, P.f_smem_bytes, st>>>(kp, io, n_groups);
     nazb_count_launch();
     return cudaGetLastError();
   }

@@ -90,7 +90,12 @@ __global__ void __launch_bounds__(kV3Threads, 1) flow_tc_inv3_kernel(const __gri
     for (int i = 0; i < kChains; ++i) tcx::mbar_init(bar_acc + i, 1);
     for (int i = 0; i < 2; ++i) { tcx::mbar_init(lc_full + i, 1); tcx::mbar_init(lc_empty + i, kV3EpiWarps); }
     for (int i = 0; i < kXSlots; ++i) { tcx::mbar_init(xw_full + i, 1); tcx::mbar_init(xw_empty + i, kChains); }
-    for (int i = 0; i < kChains * 3 * kV3MaxSlices; ++i) tcx::mbar_init(a_ready + i, 4);
+    // slice 0 of every A block (and the A_X slice) also collects one arrival from each NON-producing warp of the chain:
+    // a warp that waits on the accumulator barrier must be needed for the next MMA, otherwise the issuer could complete
+    // two accumulator phases before a late warp (cold instruction / constant cache) has observed the first one, and the
+    // parity wait would never return
+    for (int i = 0; i < kChains * 3 * kV3MaxSlices; ++i)
+      tcx::mbar_init(a_ready + i, (i % kV3MaxSlices == 0) ? 4 * kV3Parts : 4);
     tcx::mbar_fence_init();
   }
   if (warp == 0) tcx::tmem_alloc(tmem_slot, kTmemCols);
@@ -335,6 +340,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) flow_tc_inv3_kernel(const __gri
               const int nch = s_encols >> 3, nsl = (nch + 1) >> 1;
               const bool prescaled = (s_flags & 4) != 0;   // first-layer block: bias and tanh scale folded into the image
               const int nmine = (nsl - part + kV3Parts - 1) / kV3Parts;   // slices part, part + kV3Parts, ...
+              if (part != 0 && lane == 0) tcx::mbar_arrive(my_ready + buf * kV3MaxSlices);   // observer arrival on slice 0
               for (int j0 = 0; j0 < nmine; j0 += 2) {
                 uint32_t r[16];
                 const int nj = min(2, nmine - j0);
@@ -382,11 +388,12 @@ __global__ void __launch_bounds__(kV3Threads, 1) flow_tc_inv3_kernel(const __gri
                 if (rows_mine) {
                   tcx::fence_async_smem();
                   __syncwarp();
-                  if (lane == 0) tcx::mbar_arrive(my_ready + 2 * kV3MaxSlices);
                 }
+                if (lane == 0) tcx::mbar_arrive(my_ready + 2 * kV3MaxSlices);   // other parts: observer arrival
               } else {
                 const int nch = s_encols >> 3, nsl = (nch + 1) >> 1;
                 const int u0 = s_eaux;
+                if (part != 0 && lane == 0) tcx::mbar_arrive(my_ready + buf * kV3MaxSlices);   // observer arrival on slice 0
                 for (int sl = 0; sl < nsl && rows_mine; ++sl) {   // (the row's inputs live with the part-0 warp)
                   const int c = sl * 2 + hw;
                   uint4 hi4 = make_uint4(0, 0, 0, 0), lo4 = hi4;
