@@ -37,6 +37,7 @@ constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kParts = kEpiWarps / 4;
 constexpr int kThreads = (kEpiWarps + 2) * 32;
 constexpr int kSlotBytes = 40960;
+constexpr int kFwdSlotBytes = 40960;   // pipelined forward kernels (20 KB slots measured 8-12 % slower: more sub-steps, waits and commits)
 constexpr int kTmemCols = 512;
 
 enum : uint8_t { EPI_NONE = 0, EPI_TANH = 1, EPI_XINV = 2, EPI_XFWD = 3, EPI_FIRST = 4 };
@@ -82,6 +83,10 @@ struct TcPlan {
   int kr_max = 0;
   // slice-pipelined forward kernel (flow_tc_fwd3.cuh)
   bool fwd3 = false;
+  bool fwd4 = false;    // two 128-point tiles per CTA sharing one A ring (flow_tc_fwd4.cuh); same program as fwd3
+  uint32_t g_ax = 0, g_a = 0, g_x = 0, g_ctx = 0, g_misc = 0, g_lc = 0, g_ring = 0;
+  int g_nslots = 0;
+  size_t g_smem_bytes = 0;
   int f_lc_floats = 0, f_lc_b[NAZB_MAX_HIDDEN_LAYERS] = {0}, f_lc_bout = 0, f_nslots = 0;
   uint32_t f_ax = 0, f_a = 0, f_x = 0, f_ctx = 0, f_misc = 0, f_lc = 0, f_ring = 0;
   size_t f_smem_bytes = 0;
@@ -145,9 +150,10 @@ struct Builder {
   std::vector<Step>& steps;
   std::vector<Image>& images;
   uint32_t w_off = 0;
+  int slot_bytes = kSlotBytes;
   void gemm(uint8_t a_buf, int a_chunk0, int k_ext, int n_ext, int d_col, int nsplit, int accumulate, Image im,
             Step epi, int n_crit = 0) {
-    int k_sub_max = std::min(96, (kSlotBytes / (n_ext * 4)) / 16 * 16);
+    int k_sub_max = std::min(96, (slot_bytes / (n_ext * 4)) / 16 * 16);
     for (int k_off = 0; k_off < k_ext; k_off += k_sub_max) {
       int ks = std::min(k_sub_max, k_ext - k_off);
       bool last = (k_off + ks >= k_ext);
@@ -264,6 +270,8 @@ bool build_forward3(const FlowGeom& g, TcPlan& P) {
   P.f_lc_floats = ceil_to(off, 4);
   P.steps[1].clear(); P.images[1].clear();
   Builder b{P.steps[1], P.images[1]};
+  b.slot_bytes = kFwdSlotBytes;
+  if (kFwdSlotBytes / (P.hp_max * 4) < 16) return false;
   {
     Step t = mk_epi(EPI_TANH, 0, hp(0), 0);
     t.flags = 4;
@@ -301,9 +309,27 @@ bool build_forward3(const FlowGeom& g, TcPlan& P) {
   o = (o + 127) & ~127u;
   P.f_ring = o;
   const uint32_t cap = 227 * 1024;
-  if (o + 2 * kSlotBytes > cap) return false;
-  P.f_nslots = std::min(6u, (cap - o) / kSlotBytes);
-  P.f_smem_bytes = o + (size_t)P.f_nslots * kSlotBytes;
+  if (o + 2 * kFwdSlotBytes > cap) return false;
+  P.f_nslots = std::min(8u, (cap - o) / kFwdSlotBytes);
+  P.f_smem_bytes = o + (size_t)P.f_nslots * kFwdSlotBytes;
+  // two-tile variant: each tile owns half of TMEM (pre + transform parameters <= 256 columns)
+  P.fwd4 = false;
+  if (P.hp_max + ceil_to(D * M, 16) <= kTmemCols / 2 && !(getenv("NAZB_FWD_ONE_TILE") && atoi(getenv("NAZB_FWD_ONE_TILE")))) {
+    uint32_t q = 1024;
+    P.g_ax = q;   q += 2u * 2u * 16u * kTileM * 2;
+    P.g_a = q;    q += 2u * (uint32_t)P.hp_max * kTileM * 2;
+    P.g_x = q;    q += 2u * (uint32_t)D * kTileM * 4;
+    P.g_ctx = q;  q += 2u * (uint32_t)std::max(1, g.C) * kTileM * 4;
+    P.g_misc = q; q += 2u * 4u * kTileM * 4;   // [tile][part <= 4] log-det partials
+    P.g_lc = q;   q += 2u * (uint32_t)P.f_lc_floats * 4;
+    q = (q + 127) & ~127u;
+    P.g_ring = q;
+    if (q + 2 * kFwdSlotBytes <= cap) {
+      P.g_nslots = std::min(8u, (cap - q) / kFwdSlotBytes);
+      P.g_smem_bytes = q + (size_t)P.g_nslots * kFwdSlotBytes;
+      P.fwd4 = true;
+    }
+  }
   return true;
 }
 
@@ -1012,6 +1038,7 @@ constexpr int kChainRows = kTileM / kChains;          // 64
 
 #include "flow_tc_inv3.cuh"
 #include "flow_tc_fwd3.cuh"
+#include "flow_tc_fwd4.cuh"
 
 }  // namespace
 
@@ -1195,6 +1222,18 @@ cudaError_t nazb_tc_launch(const nazb_handle* h, const IoArgs& io, int n_groups,
     kp.bound = g.bound; kp.clip_lo = g.clip_lo; kp.clip_hi = g.clip_hi;
     kp.off_ax = P.f_ax; kp.off_a = P.f_a; kp.off_x = P.f_x; kp.off_ctx = P.f_ctx; kp.off_misc = P.f_misc;
     kp.off_lc = P.f_lc; kp.off_ring = P.f_ring;
+    if (P.fwd4) {
+      kp.nslots = P.g_nslots;
+      kp.off_ax = P.g_ax; kp.off_a = P.g_a; kp.off_x = P.g_x; kp.off_ctx = P.g_ctx; kp.off_misc = P.g_misc;
+      kp.off_lc = P.g_lc; kp.off_ring = P.g_ring;
+      cudaError_t e4 = cudaFuncSetAttribute(flow_tc_fwd4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.g_smem_bytes);
+      if (e4 != cudaSuccess) return e4;
+      const int n_pairs = (io.N + 2 * kTileM - 1) / (2 * kTileM);
+      const int grid4 = (int)std::min<long long>((long long)n_pairs * n_groups, h->sm_count);
+      flow_tc_fwd4_kernel<<<grid4, kF4Threads, P.g_smem_bytes, st>>>(kp, io, n_groups);
+      nazb_count_launch();
+      return cudaGetLastError();
+    }
     cudaError_t e = cudaFuncSetAttribute(flow_tc_fwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.f_smem_bytes);
     if (e != cudaSuccess) return e;
     const int n_tiles = (io.N + kTileM - 1) / kTileM;

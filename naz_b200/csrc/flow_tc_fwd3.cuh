@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(kF3Threads, 1) flow_tc_fwd3_kernel(const __gri
               const uint32_t slot = cnt % p.nslots, use = cnt / p.nslots;
               tcx::mbar_wait(w_empty + slot, (use & 1) ^ 1);
               tcx::mbar_expect_tx(w_full + slot, wb);
-              tcx::bulk_g2s(ring + (size_t)slot * kSlotBytes, wl + p.steps[st].w_off, wb, w_full + slot);
+              tcx::bulk_g2s(ring + (size_t)slot * kFwdSlotBytes, wl + p.steps[st].w_off, wb, w_full + slot);
               ++cnt;
             }
           }
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kF3Threads, 1) flow_tc_fwd3_kernel(const __gri
             const bool to_pre = (p.steps[st].d_col == 0xFFFF);      // pre-activation buffer chosen by phase parity
             const uint32_t idesc = tcx::make_idesc_f16(s_n);
             const uint32_t lbo_b = s_n * 16;
-            const uint32_t b_hi = ring_a + slot * kSlotBytes, b_lo = b_hi + (s_wbytes >> 1);
+            const uint32_t b_hi = ring_a + slot * kFwdSlotBytes, b_lo = b_hi + (s_wbytes >> 1);
             const uint32_t lbo_b_hi16 = (lbo_b >> 4) << 16, lbo_a_hi16 = (lbo_a >> 4) << 16;
             const uint32_t a_hi = is_x ? ax_base : a_base;
             const uint32_t a_lo = a_hi + (is_x ? ax_img_bytes : a_img_bytes);
