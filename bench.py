@@ -292,10 +292,24 @@ def main_ours(args):
     barrier()
     e2e_s = time.perf_counter() - t0
 
-    tms = torch.tensor([total_ms, e2e_s * 1e3, k_ms], device=dev, dtype=torch.float64)
+    # auxiliary: the sampling direction (reference `sample`, one conditioner pass per flow layer) on the same draws,
+    # cfg-5-sized: every local draw x 10 000 base-noise points shared by the draws (kernel time, CUDA events)
+    n_s = 10_000
+    z_dev = torch.randn((n_s, D), device=dev, generator=gen)
+    eng.forward(z_dev, c_dev)
+    torch.cuda.synchronize()
+    f0, f1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    xs = eng.forward(z_dev, c_dev)
+    f1e.record()
+    torch.cuda.synchronize()
+    fwd_ms = f0.elapsed_time(f1e)
+    del xs
+
+    tms = torch.tensor([total_ms, e2e_s * 1e3, k_ms, fwd_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, k_ms = [float(v) for v in tms.tolist()]
+    total_ms, e2e_ms, k_ms, fwd_ms = [float(v) for v in tms.tolist()]
     finite = bool(torch.isfinite(res).all().item())
 
     if rank == 0:
@@ -336,6 +350,9 @@ def main_ours(args):
                     "d2h_bytes_per_step": int(N * 4)},
             "gpu_launches": int(launches),
             "clocks": clk,
+            "aux_sample_direction": {"value": float(S) * n_s / (fwd_ms * 1e-3), "unit": "samples/s", "draws": S, "points_per_draw": n_s,
+                                     "engine": eng.engine_for("forward"), "ms": fwd_ms,
+                                     "note": "reference `sample` direction on the same draws (not part of `value`)"},
         }
         if not args.no_cpu_baseline and world == 1:
             rate, cores, sample = cpu_reference_rate(CONFIGS[args.config], args.cpu_seconds)

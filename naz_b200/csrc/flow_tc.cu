@@ -1226,11 +1226,12 @@ cudaError_t nazb_tc_launch(const nazb_handle* h, const IoArgs& io, int n_groups,
       kp.nslots = P.g_nslots;
       kp.off_ax = P.g_ax; kp.off_a = P.g_a; kp.off_x = P.g_x; kp.off_ctx = P.g_ctx; kp.off_misc = P.g_misc;
       kp.off_lc = P.g_lc; kp.off_ring = P.g_ring;
-      cudaError_t e4 = cudaFuncSetAttribute(flow_tc_fwd4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.g_smem_bytes);
+      auto kern4 = g_tc_dbg ? flow_tc_fwd4_kernel<true> : flow_tc_fwd4_kernel<false>;
+      cudaError_t e4 = cudaFuncSetAttribute(kern4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.g_smem_bytes);
       if (e4 != cudaSuccess) return e4;
       const int n_pairs = (io.N + 2 * kTileM - 1) / (2 * kTileM);
       const int grid4 = (int)std::min<long long>((long long)n_pairs * n_groups, h->sm_count);
-      flow_tc_fwd4_kernel<<<grid4, kF4Threads, P.g_smem_bytes, st>>>(kp, io, n_groups);
+      kern4<<<grid4, kF4Threads, P.g_smem_bytes, st>>>(g_tc_dbg, kp, io, n_groups);
       nazb_count_launch();
       return cudaGetLastError();
     }

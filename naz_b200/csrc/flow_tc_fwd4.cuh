@@ -28,7 +28,10 @@ constexpr int kF4TileCols = kTmemCols / kF4Tiles;
 
 __device__ __forceinline__ void f4_tile_sync(int t) { asm volatile("bar.sync %0, %1;\n" ::"r"(1 + t), "n"(kF4TileWarps * 32) : "memory"); }
 
-__global__ void __launch_bounds__(kF4Threads, 1) flow_tc_fwd4_kernel(const __grid_constant__ KParamsFwd3 p,
+#define DBG4(slot) if (kDbg && dbg_buf && blockIdx.x == 0 && dbg_i < 128) dbg_buf[dbg_i * 16 + (slot)] = clk();
+
+template <bool kDbg>
+__global__ void __launch_bounds__(kF4Threads, 1) flow_tc_fwd4_kernel(long long* dbg_buf, const __grid_constant__ KParamsFwd3 p,
                                                                       const __grid_constant__ IoArgs io, int n_groups) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* w_full = reinterpret_cast<uint64_t*>(smem);            // [nslots]
@@ -117,6 +120,8 @@ __global__ void __launch_bounds__(kF4Threads, 1) flow_tc_fwd4_kernel(const __gri
     constexpr uint64_t dhi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;   // SBO = 128 B, descriptor version 1
     uint32_t slot = 0, use = 0, xpar = 0;
     uint32_t apar[kF4Tiles] = {0u, 0u};   // one parity bit per (tile, slice) a_ready barrier
+    int dbg_i = 0;
+    const bool dbg_me = (lane == 0);
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int grp = (int)(item / n_pairs);
       for (int si = grp; si < io.s_count; si += n_groups) {
@@ -132,6 +137,7 @@ __global__ void __launch_bounds__(kF4Threads, 1) flow_tc_fwd4_kernel(const __gri
 #pragma unroll 1
             for (int t = 0; t < kF4Tiles; ++t) {
               const uint32_t d_addr = tmem + (uint32_t)t * kF4TileCols + (to_pre ? 0u : (uint32_t)p.t_pre1);
+              if (dbg_me) { DBG4(8 + 3 * t) }
               if (is_x) {
                 tcx::mbar_wait(ax_ready + t, (xpar >> t) & 1);
                 xpar ^= 1u << t;
@@ -144,6 +150,7 @@ __global__ void __launch_bounds__(kF4Threads, 1) flow_tc_fwd4_kernel(const __gri
                 }
               }
               tcx::tc_fence_after();
+              if (dbg_me) { DBG4(9 + 3 * t) }
               for (int s2 = st; s2 <= st_end; ++s2) {
                 const uint32_t s_wbytes = p.steps[s2].w_bytes, s_n = p.steps[s2].n;
                 const int ksteps = p.steps[s2].ksteps;
@@ -170,7 +177,9 @@ __global__ void __launch_bounds__(kF4Threads, 1) flow_tc_fwd4_kernel(const __gri
                 tcx::mma_commit_elect(w_empty + slot, elected);
                 if (++slot == (uint32_t)p.nslots) { slot = 0; ++use; }
               }
+              if (dbg_me) { DBG4(10 + 3 * t) }
             }
+            ++dbg_i;
             st = st_end + 1;
           }
         }
@@ -190,6 +199,9 @@ __global__ void __launch_bounds__(kF4Threads, 1) flow_tc_fwd4_kernel(const __gri
     uint64_t* my_ready = a_ready + t * kF3MaxSlices;
     uint32_t par_acc = 0, lcnt = 0;
     uint32_t nwrites = 0;                       // A blocks produced so far by this tile (ring protocol parity)
+    int dbg_i = 0;
+    const bool dbg_me = (warp % kF4TileWarps == 0 && lane == 0);
+    const int dbg_o = t * 4;
     const uint64_t scale2 = tcx::pk2(kTanhScale, kTanhScale);
 
     auto ax_store = [&](int col, float v) {
@@ -239,9 +251,11 @@ __global__ void __launch_bounds__(kF4Threads, 1) flow_tc_fwd4_kernel(const __gri
             if (s_epi == EPI_NONE) continue;
             const uint32_t s_encols = p.steps[st].e_ncols, s_eaux = p.steps[st].e_aux;
             const uint32_t s_stage = p.steps[st].stage, s_nranks = p.steps[st].nranks, s_flags = p.steps[st].flags;
+            if (dbg_me) { DBG4(dbg_o + 0) }
             tcx::mbar_wait(bar_acc + t, par_acc);
             par_acc ^= 1;
             tcx::tc_fence_after();
+            if (dbg_me) { DBG4(dbg_o + 1) }
             if (s_epi == EPI_TANH) {
               const int nsl = (int)(s_encols + 15) >> 4;
               const bool prescaled = (s_flags & 4) != 0;
@@ -283,6 +297,7 @@ __global__ void __launch_bounds__(kF4Threads, 1) flow_tc_fwd4_kernel(const __gri
                 tcx::fence_async_smem();
                 __syncwarp();
                 if (lane == 0) tcx::mbar_arrive(my_ready + sl);
+                if (dbg_me && sl == part) { DBG4(dbg_o + 2) }
               }
               ++nwrites;
             } else {   // EPI_XFWD: transform the dims of ranks [stage, stage + nranks)
@@ -319,6 +334,8 @@ __global__ void __launch_bounds__(kF4Threads, 1) flow_tc_fwd4_kernel(const __gri
               }
               tcx::tc_fence_before();
             }
+            if (dbg_me) { DBG4(dbg_o + 3) }
+            ++dbg_i;
           }
           __syncwarp();
           if (lane == 0) tcx::mbar_arrive(lc_empty + (lcnt & 1));

@@ -44,6 +44,8 @@ SHAPES = [
     ("nsa", 3, 2, [32, 40], 3, 2, 300, "linear"),            # linear-order spline
     ("maf", 5, 0, [37, 21], 3, 2, 257, "quadratic"),         # odd widths, unconditional, ragged tile
     ("maf", 12, 4, [150] * 3, 4, 2, 200, "quadratic"),       # D + C = 16: first conditioner layer on CUDA cores (no K = 16 slice left for the bias column)
+    ("nsa", 3, 2, [32, 48], 3, 2, 300, "quadratic"),         # 2-3 K slices per layer: fewer slices than epilogue parts (idle parts must not be lapped)
+    ("maf", 3, 1, [16, 16], 4, 3, 600, "quadratic"),         # one K slice per layer, one 8-column block per stage
 ]
 
 
