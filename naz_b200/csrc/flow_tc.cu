@@ -1084,6 +1084,12 @@ int64_t nazb_tc_packed_bytes(const nazb_handle* h) {
                                      (t->lcf_dev ? sizeof(float) * (size_t)h->geom.L * t->plan.f_lc_floats : 0));
 }
 
+// points per kernel work item (the two-tile forward kernel takes 256-point pairs)
+int nazb_tc_rows_per_item(const nazb_handle* h, int dir) {
+  const TcState* t = static_cast<const TcState*>(h->tc);
+  return (t && dir == 1 && t->plan.fwd3 && t->plan.fwd4) ? 2 * kTileM : kTileM;
+}
+
 bool nazb_tc_direction_ok(const nazb_handle* h, int dir) {
   const TcState* t = static_cast<const TcState*>(h->tc);
   return t && t->plan.ok[dir];

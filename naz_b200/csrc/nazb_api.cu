@@ -1,9 +1,11 @@
 // C-ABI glue of libnazb.so (see include/nazb.h for the contract and the reference mapping).
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 #include "nazb_internal.h"
 
 static std::atomic<long long> g_launches{0};
@@ -129,6 +131,7 @@ extern "C" void nazb_destroy(nazb_handle* h) {
 extern "C" int nazb_engine_in_use(const nazb_handle* h) { return h ? h->engine : NAZB_ERR_BAD_ARG; }
 
 bool nazb_tc_direction_ok(const nazb_handle* h, int dir);
+int nazb_tc_rows_per_item(const nazb_handle* h, int dir);
 
 // Engine that serves one direction (0 = inverse / log_prob, 1 = forward / sample) after nazb_pack.
 extern "C" int nazb_engine_for_direction(const nazb_handle* h, int dir) {
@@ -218,18 +221,38 @@ static int check_io(const nazb_handle* h, int s_begin, int s_count, const void* 
   return NAZB_OK;
 }
 
-static int pick_groups(const nazb_handle* h, int N, int s_count, int requested) {
+// Work items are (point tile, draw group); CTA b takes items b, b + #SMs, ... (group-major order).  `rows` = points per
+// item of the kernel that will run (64 SIMT, 128 tcgen05 inverse / one-tile forward, 256 two-tile forward).
+static int pick_groups(const nazb_handle* h, int N, int s_count, int requested, int rows) {
   if (requested > 0) return requested < s_count ? requested : s_count;
-  // enough CTAs for >= 4 waves if the draw axis allows it
-  int P = 64;
-  long long tiles = (N + P - 1) / P;
-  long long want = 4LL * h->sm_count * 2;
-  long long gq = (want + tiles - 1) / tiles;
+  const long long sms = h->sm_count;
+  const long long tiles = (N + rows - 1) / rows;
+  long long gq = (4 * sms + tiles - 1) / tiles;          // >= 4 items per SM if the draw axis allows it
   if (gq < 1) gq = 1;
   // large N: ~8 draws per group, so a group's weight images stay L2-resident while the CTAs sweep the point tiles
-  if (tiles >= 8LL * h->sm_count && gq < s_count / 8) gq = s_count / 8;
+  if (tiles >= 8 * sms && gq < s_count / 8) gq = s_count / 8;
   if (gq > s_count) gq = s_count;
   if (gq > 65535) gq = 65535;
+  // few items per SM: the tail matters.  Pick the group count (up to 6x the minimum) whose busiest CTA is closest to
+  // the mean, counting draws per item exactly (group g holds ceil((s_count - g) / G) draws).
+  if (tiles * gq < 16 * sms) {
+    const long long g_hi = std::min<long long>(std::min<long long>(s_count, 65535), 6 * gq);
+    double best_eff = -1.0;
+    long long best_g = gq;
+    std::vector<long long> cost((size_t)sms);
+    for (long long G = gq; G <= g_hi; ++G) {
+      std::fill(cost.begin(), cost.end(), 0LL);
+      long long total = 0, item = 0;
+      for (long long g = 0; g < G; ++g) {
+        const long long nd = (s_count - g + G - 1) / G;
+        for (long long t = 0; t < tiles; ++t, ++item) { cost[(size_t)(item % sms)] += nd; total += nd; }
+      }
+      const long long mx = *std::max_element(cost.begin(), cost.end());
+      const double eff = (double)total / ((double)mx * (double)sms);
+      if (eff > best_eff + 1e-3) { best_eff = eff; best_g = G; }
+    }
+    gq = best_g;
+  }
   return (int)gq;
 }
 
@@ -248,7 +271,8 @@ extern "C" int nazb_inverse(nazb_handle* h, int32_t s_begin, int32_t s_count, co
   io.s_begin = s_begin; io.s_count = s_count; io.lo = lo; io.hi = hi;
   io.out_x = z; io.out_l = lp; io.log_w = log_w; io.lse_max = lse_max; io.lse_sum = lse_sum; io.sum_n = sum_n;
   io.dir = 0;
-  int G = pick_groups(h, N, s_count, lse_max ? n_groups : 0);
+  const int rows_inv = (nazb_engine_for_direction(h, 0) == NAZB_ENGINE_TCGEN05) ? 128 : 64;
+  int G = pick_groups(h, N, s_count, lse_max ? n_groups : 0, rows_inv);
   cudaError_t e = (nazb_engine_for_direction(h, 0) == NAZB_ENGINE_TCGEN05)
                       ? nazb_tc_launch(h, io, G, (cudaStream_t)stream)
                       : nazb_simt_launch(h, io, G, (cudaStream_t)stream);
@@ -267,7 +291,8 @@ extern "C" int nazb_forward(nazb_handle* h, int32_t s_begin, int32_t s_count, co
   io.x = z; io.x_draw_stride = z_shared ? 0 : (long long)N * h->geom.D; io.ctx = ctx; io.ctx_rows = ctx_rows; io.N = N;
   io.s_begin = s_begin; io.s_count = s_count; io.lo = lo; io.hi = hi;
   io.out_x = x; io.out_l = logdet; io.dir = 1;
-  int G = pick_groups(h, N, s_count, 0);
+  const int rows_fwd = (nazb_engine_for_direction(h, 1) == NAZB_ENGINE_TCGEN05) ? nazb_tc_rows_per_item(h, 1) : 64;
+  int G = pick_groups(h, N, s_count, 0, rows_fwd);
   cudaError_t e = (nazb_engine_for_direction(h, 1) == NAZB_ENGINE_TCGEN05)
                       ? nazb_tc_launch(h, io, G, (cudaStream_t)stream)
                       : nazb_simt_launch(h, io, G, (cudaStream_t)stream);
