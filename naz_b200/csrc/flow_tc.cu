@@ -85,6 +85,7 @@ struct TcPlan {
   bool fwd3 = false;
   bool fwd4 = false;    // two 128-point tiles per CTA sharing one A ring (flow_tc_fwd4.cuh); same program as fwd3
   uint32_t g_ax = 0, g_a = 0, g_x = 0, g_ctx = 0, g_misc = 0, g_lc = 0, g_ring = 0;
+  uint32_t g_slot_off[8] = {0};
   int g_nslots = 0;
   size_t g_smem_bytes = 0;
   int f_lc_floats = 0, f_lc_b[NAZB_MAX_HIDDEN_LAYERS] = {0}, f_lc_bout = 0, f_nslots = 0;
@@ -324,9 +325,19 @@ bool build_forward3(const FlowGeom& g, TcPlan& P) {
     P.g_lc = q;   q += 2u * (uint32_t)P.f_lc_floats * 4;
     q = (q + 127) & ~127u;
     P.g_ring = q;
-    if (q + 2 * kFwdSlotBytes <= cap) {
-      P.g_nslots = std::min(8u, (cap - q) / kFwdSlotBytes);
-      P.g_smem_bytes = q + (size_t)P.g_nslots * kFwdSlotBytes;
+    // weight slots: slot j holds sub-step j of the current gemm for BOTH tiles; its size is the largest j-th sub-step
+    uint32_t slot_sz[8] = {0};
+    int nsub_max = 0, j = 0;
+    for (const Step& stp : P.steps[1]) {
+      if (j < 8) slot_sz[j] = std::max(slot_sz[j], (stp.w_bytes + 127u) & ~127u);
+      nsub_max = std::max(nsub_max, j + 1);
+      j = (stp.epi == EPI_NONE) ? j + 1 : 0;
+    }
+    uint32_t ring_bytes = 0;
+    for (int i = 0; i < std::min(nsub_max, 8); ++i) { P.g_slot_off[i] = ring_bytes; ring_bytes += slot_sz[i]; }
+    if (nsub_max <= 8 && q + ring_bytes <= cap) {
+      P.g_nslots = nsub_max;
+      P.g_smem_bytes = q + ring_bytes;
       P.fwd4 = true;
     }
   }
@@ -1232,6 +1243,7 @@ cudaError_t nazb_tc_launch(const nazb_handle* h, const IoArgs& io, int n_groups,
       kp.nslots = P.g_nslots;
       kp.off_ax = P.g_ax; kp.off_a = P.g_a; kp.off_x = P.g_x; kp.off_ctx = P.g_ctx; kp.off_misc = P.g_misc;
       kp.off_lc = P.g_lc; kp.off_ring = P.g_ring;
+      for (int i = 0; i < 8; ++i) kp.slot_off[i] = P.g_slot_off[i];
       auto kern4 = g_tc_dbg ? flow_tc_fwd4_kernel<true> : flow_tc_fwd4_kernel<false>;
       cudaError_t e4 = cudaFuncSetAttribute(kern4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.g_smem_bytes);
       if (e4 != cudaSuccess) return e4;

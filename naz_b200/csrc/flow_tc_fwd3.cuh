@@ -35,6 +35,7 @@ struct KParamsFwd3 {
   int D, C, L, M, K, kind, kin, hp_max, nslots, t_pre1;
   float bound, clip_lo, clip_hi;
   uint32_t off_ax, off_a, off_x, off_ctx, off_misc, off_lc, off_ring;
+  uint32_t slot_off[8];            // two-tile kernel: byte offset of the weight slot of sub-step j of a gemm (shared by both tiles)
 };
 
 __device__ __forceinline__ void f3_epi_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(kF3EpiWarps * 32) : "memory"); }

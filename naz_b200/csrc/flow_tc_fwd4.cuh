@@ -14,7 +14,8 @@
 // pre-activation accumulator (160 columns) + the transform parameters (<= 96 columns) = one half of TMEM, therefore a
 // layer's MMAs start only when ALL K slices of that tile have landed (its epilogue has then finished reading `pre`).
 //   * warps 0-11 / 12-23: epilogue of tile 0 / 1 (4 TMEM quadrants x 3 parts, thread = row, part p takes slices p, p+3, ...)
-//   * warp 24: MMA issuer, warp 25: TMA producer (each weight image is streamed once per tile).
+//   * warp 24: MMA issuer, warp 25: TMA producer.  A gemm's weight images (one slot per K sub-step) are loaded ONCE and
+//     used by tile 0 then tile 1; tile 1's tcgen05.commit frees the slot for the next gemm's sub-step.
 #pragma once
 
 constexpr int kF4Tiles = 2;
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(kF4Threads, 1) flow_tc_fwd4_kernel(long long* 
   if (warp == kF4Producer) {
     // ===================== TMA producer: every image once per tile, in issue order =====================
     if (lane == 0) {
-      uint32_t cnt = 0, lcnt = 0;
+      uint32_t wuse = 0, lcnt = 0;   // wuse: 4-bit use counter per weight slot
       for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int grp = (int)(item / n_pairs);
         for (int si = grp; si < io.s_count; si += n_groups) {
@@ -96,15 +97,14 @@ __global__ void __launch_bounds__(kF4Threads, 1) flow_tc_fwd4_kernel(long long* 
             while (st < p.nsteps) {
               int st_end = st;                                   // [st, st_end]: the sub-steps of one gemm
               while (p.steps[st_end].epi == EPI_NONE) ++st_end;
-              for (int t = 0; t < kF4Tiles; ++t)
-                for (int s2 = st; s2 <= st_end; ++s2) {
-                  const uint32_t wb = p.steps[s2].w_bytes;
-                  const uint32_t slot = cnt % p.nslots, use = cnt / p.nslots;
-                  tcx::mbar_wait(w_empty + slot, (use & 1) ^ 1);
-                  tcx::mbar_expect_tx(w_full + slot, wb);
-                  tcx::bulk_g2s(ring + (size_t)slot * kFwdSlotBytes, wl + p.steps[s2].w_off, wb, w_full + slot);
-                  ++cnt;
-                }
+              for (int s2 = st; s2 <= st_end; ++s2) {
+                const uint32_t wb = p.steps[s2].w_bytes;
+                const uint32_t slot = (uint32_t)(s2 - st), use = (wuse >> (4 * slot)) & 15u;   // per-slot use parity
+                tcx::mbar_wait(w_empty + slot, (use & 1) ^ 1);
+                tcx::mbar_expect_tx(w_full + slot, wb);
+                tcx::bulk_g2s(ring + p.slot_off[slot], wl + p.steps[s2].w_off, wb, w_full + slot);
+                wuse = (wuse & ~(15u << (4 * slot))) | (((use + 1) & 15u) << (4 * slot));
+              }
               st = st_end + 1;
             }
           }
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kF4Threads, 1) flow_tc_fwd4_kernel(long long* 
     const uint32_t a_base = tcx::smem_u32(smem + p.off_a), ax_base0 = tcx::smem_u32(smem + p.off_ax);
     constexpr uint32_t lbo_a = kTileM * 16;
     constexpr uint64_t dhi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;   // SBO = 128 B, descriptor version 1
-    uint32_t slot = 0, use = 0, xpar = 0;
+    uint32_t wuse = 0, xpar = 0;   // wuse: 4-bit use counter per weight slot
     uint32_t apar[kF4Tiles] = {0u, 0u};   // one parity bit per (tile, slice) a_ready barrier
     int dbg_i = 0;
     const bool dbg_me = (lane == 0);
@@ -158,7 +158,8 @@ __global__ void __launch_bounds__(kF4Threads, 1) flow_tc_fwd4_kernel(long long* 
                 const uint32_t slice0 = p.steps[s2].a_chunk0 >> 1;
                 const uint32_t idesc = tcx::make_idesc_f16(s_n);
                 const uint32_t lbo_b = s_n * 16;
-                const uint32_t b_hi = ring_a + slot * kFwdSlotBytes, b_lo = b_hi + (s_wbytes >> 1);
+                const uint32_t slot = (uint32_t)(s2 - st), use = (wuse >> (4 * slot)) & 15u;
+                const uint32_t b_hi = ring_a + p.slot_off[slot], b_lo = b_hi + (s_wbytes >> 1);
                 const uint32_t lbo_b_hi16 = (lbo_b >> 4) << 16, lbo_a_hi16 = (lbo_a >> 4) << 16;
                 const uint32_t a_hi = is_x ? (ax_base0 + (uint32_t)t * 2 * ax_img_bytes) : a_base;
                 const uint32_t a_lo = a_hi + (is_x ? ax_img_bytes : a_img_bytes);
@@ -174,8 +175,10 @@ __global__ void __launch_bounds__(kF4Threads, 1) flow_tc_fwd4_kernel(long long* 
                   if (!is_x) tcx::mma_commit_elect(a_free + sl, elected);   // the other tile may overwrite this slice
                 }
                 if (s2 == st_end) tcx::mma_commit_elect(bar_acc + t, elected);
-                tcx::mma_commit_elect(w_empty + slot, elected);
-                if (++slot == (uint32_t)p.nslots) { slot = 0; ++use; }
+                if (t == kF4Tiles - 1) {   // the last tile's MMAs on this slot retire -> the producer may refill it
+                  tcx::mma_commit_elect(w_empty + slot, elected);
+                  wuse = (wuse & ~(15u << (4 * slot))) | (((use + 1) & 15u) << (4 * slot));
+                }
               }
               if (dbg_me) { DBG4(10 + 3 * t) }
             }
