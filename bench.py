@@ -149,6 +149,7 @@ def cpu_reference_rate(cfg, seconds: float, threads=None):
     rate = n_draws * probe_n / t
     npts = int(max(probe_n, min(400_000, rate * seconds / n_draws)))
     t = run(npts)
+    cpu_reference_rate.last_seconds = t
     return n_draws * npts / t, cores, f"{n_draws} draws x {npts} points of the {L}-layer {kind} D={D}|C={C} flow, fp32 torch CPU, {t:.1f} s"
 
 
@@ -158,15 +159,16 @@ def main_reference(args):
         return 0
     cfg = CONFIGS[args.config]
     kind, D, C, hidden, L, K, S, N = cfg
-    vals = []
+    vals, secs = [], []
     for i in range(args.warmup + args.steps):
         rate, cores, sample = cpu_reference_rate(cfg, max(2.0, args.cpu_seconds / 2))
         if i >= args.warmup:
             vals.append(rate)
+            secs.append(cpu_reference_rate.last_seconds)
     v = sum(vals) / len(vals)
     out = {
         "impl": "reference", "metric": "log-prob evals/s (weight-draws x points)", "value": v, "unit": "evals/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.config, "flow": kind, "D": D, "C": C, "hidden": hidden, "layers": L, "draws": S,
                    "points": N, "note": "reference CPU path = oracle/pyro_style.py (pyro-ppl is not installable here), bounded sample per step"},
