@@ -4,16 +4,19 @@ This module is the checker, never the product: only ``tests/``, ``__graft_entry_
 ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import it.  Nothing under
 ``naz_b200/`` imports it; the product path fails loudly when the CUDA library is missing.
 
-PARITY UNPINNED.  The reference (AnaryaRay1/naz) ships no tests, golden vectors or fixtures for
-this path, and its arithmetic lives partly in ``pyro-ppl`` (un-vendored, unpinned, not installed
-here; neither is jax).  What pins this oracle instead:
-  * the MAF branch follows the reference's own in-tree JAX restatement line by line
-    (src/naz/flows/bflow_jax_maf.py:48-77 masks / masked linear, :135-165 conditioner,
-    :173-194 forward / inverse, :210-223 log-prob / sampler assembly, :95-105 bounding);
+PARITY: MAF BRANCH PINNED BY REFERENCE OUTPUTS, SPLINE BRANCH UNPINNED.  The reference (AnaryaRay1/naz) ships
+no tests, golden vectors or fixtures for this path, and its arithmetic lives partly in ``pyro-ppl`` (un-vendored,
+unpinned, not installed here; neither is jax).  What pins this oracle:
+  * MAF branch — outputs of the reference itself: ``tools/make_reference_goldens.py`` EXECUTES the reference's own
+    src/naz/flows/bflow_jax_maf.py (create_mask :52-72, masked_linear :74-77, nn_fn :135-165, forward_fn / inverse_fn
+    :173-194, make_normalizing_flow log_prob / sample :196-225) on CPU with numpy standing in for jax.numpy, and commits
+    masks, log_prob and sampler outputs as tests/golden/ref_twin_*.npz; tests/test_oracle_cpu.py requires this oracle to
+    reproduce them to 1e-10 (masks bit-identical) and tests/test_gpu_parity.py checks the CUDA path against them;
   * the spline / coupling / Permute / BatchNorm branches restate pyro-ppl 1.9's published
     algorithm (pyro/distributions/transforms/spline.py ``_monotonic_rational_spline``,
     ``SplineAutoregressive``; pyro/nn/auto_reg_nn.py ``create_mask``), anchored on the reference's
-    call sites src/naz/flows/transforms.py:142-159,180-197 and src/naz/flows/flow.py:37-79;
+    call sites src/naz/flows/transforms.py:142-159,180-197 and src/naz/flows/flow.py:37-79 — pyro is absent, so there
+    is nothing of the reference to execute for them: PARITY UNPINNED for splines;
   * an independent second restatement (oracle/pyro_style.py, torch modules on the real
     ``torch.distributions.TransformedDistribution``) must agree with this one to fp64 round-off;
   * mathematical identities checked in tests/: round trip, log-det == autograd slogdet,

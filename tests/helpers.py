@@ -59,3 +59,17 @@ def load_golden(name):
 
 
 GOLDEN = ["maf_uncond_2d", "maf_cond_3d", "nsa_cond_4d", "nsa_uncond_2d_k5", "nsa_linear_3d"]
+
+# REFERENCE outputs: produced by executing the reference's own bflow_jax_maf.py (tools/make_reference_goldens.py)
+REF_TWIN = ["ref_twin_maf_cond_3d", "ref_twin_maf_cond_6d", "ref_twin_maf_uncond_2d", "ref_twin_maf_bcast_ctx_2d"]
+
+
+def load_ref_twin(name):
+    """-> (spec, params [L][n_lin](W, b) fp32 single draw, arrays dict incl. the reference's masks / lp / samples)"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"), allow_pickle=False)
+    D, C, L = int(g["D"]), int(g["C"]), int(g["L"])
+    hidden = [int(h) for h in g["hidden"]]
+    spec = fo.FlowSpec("maf", D, C, hidden, L, g["perms"])
+    params = [[(g[f"W_{l}_{j}"], g[f"b_{l}_{j}"]) for j in range(len(hidden) + 1)] for l in range(L)]
+    return spec, params, g

@@ -13,7 +13,7 @@ import pytest
 import torch
 
 from oracle import flow_oracle as fo
-from helpers import GOLDEN, engine_for, load_golden, make_case, to64, tol_report
+from helpers import GOLDEN, REF_TWIN, engine_for, load_golden, load_ref_twin, make_case, to64, tol_report
 
 pytestmark = pytest.mark.gpu
 MAX_VIOL = 0.01
@@ -86,6 +86,24 @@ def test_golden_fixtures(name, engine):
     xs, ld = eng.forward(T(g["zin"].astype(np.float32)), ctx, bounds, want_logdet=True)
     check(xs, g["xs"], "samples")
     check(ld, g["ld"], "ld", atol=1e-4)
+
+
+@pytest.mark.parametrize("name", REF_TWIN)
+@pytest.mark.parametrize("engine", ["auto", "simt"])
+def test_cuda_matches_reference_outputs_maf(name, engine):
+    """CUDA path against outputs of the reference's own code (tools/make_reference_goldens.py), not of the oracle."""
+    spec, params, g = load_ref_twin(name)
+    draws = [[(W[None], b[None]) for (W, b) in layer] for layer in params]
+    eng = engine_for(spec, draws, engine=engine)
+    ctx = T(g["ctx"].astype(np.float32)) if spec.C else None
+    out = eng.inverse(T(g["x"].astype(np.float32)), ctx, want_lp=True)
+    check(out["lp"][0], g["lp"], "lp vs reference")
+    if "ys" in g.files:
+        xs, ld = eng.forward(T(g["zin"].astype(np.float32)), ctx, want_logdet=True)
+        check(xs[0], g["ys"], "samples vs reference")
+        z = g["zin"].astype(np.float64)
+        base = -0.5 * (z ** 2).sum(-1) - 0.5 * spec.D * math.log(2 * math.pi)
+        check(ld[0].cpu().numpy().astype(np.float64) + base, g["log_j"], "sampler log_j vs reference", atol=1e-4)
 
 
 def test_first_layer_cuda_core_fallback_matches_tensor_core_path(monkeypatch):

@@ -1,0 +1,184 @@
+"""Generate tests/golden/ref_twin_*.npz by EXECUTING the reference's own MAF code
+(/root/reference/src/naz/flows/bflow_jax_maf.py) on CPU.
+
+jax / numpyro / optax / h5py / physt are not installed here, so the reference module is loaded from its
+file with a minimal stand-in: `jax.numpy` -> numpy (float32 arrays that carry the `.at[idx].set()` idiom the
+reference uses), `jax.jit` -> identity, `jax.nn` -> the three elementwise functions, `random.normal(key, shape)`
+-> the array passed as `key`, everything else the module merely imports -> empty stubs.  No reference source
+is copied: the functions that run (`create_mask`, `masked_linear`, `make_conditional_autoregressive_nn.nn_fn`,
+`make_masked_affine_autoregressive_transform.{forward_fn,inverse_fn}`, `make_normalizing_flow.{log_prob,sample}`)
+are the reference's bytes, executed as they are.  The outputs are therefore REFERENCE outputs for the
+masked-affine (MAF) branch of the hot path; the spline branch lives in pyro-ppl and stays unpinned.
+
+Run in the build container only (needs /root/reference):   python tools/make_reference_goldens.py
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference/src/naz/flows/bflow_jax_maf.py"
+F64 = os.environ.get("REF_DTYPE", "float64") == "float64"   # jax would run fp32; fp64 gives the checker more digits
+
+
+class JArr(np.ndarray):
+    """ndarray with jax's functional-update idiom: a.at[idx].set(v) -> updated copy."""
+
+    class _At:
+        def __init__(self, a):
+            self.a = a
+
+        def __getitem__(self, idx):
+            a = self.a
+
+            class _Set:
+                def set(self_inner, v):
+                    out = np.array(a, copy=True).view(JArr)
+                    out[idx] = v
+                    return out
+
+            return _Set()
+
+    @property
+    def at(self):
+        return JArr._At(self)
+
+
+def _wrap(fn):
+    def inner(*a, **k):
+        out = fn(*a, **k)
+        if isinstance(out, np.ndarray):
+            return out.view(JArr)
+        if isinstance(out, (list, tuple)):
+            return type(out)(o.view(JArr) if isinstance(o, np.ndarray) else o for o in out)
+        return out
+
+    return inner
+
+
+def make_shim():
+    dt = np.float64 if F64 else np.float32
+    jnp = types.ModuleType("jax.numpy")
+    for name in dir(np):
+        obj = getattr(np, name)
+        if callable(obj) and not isinstance(obj, type):
+            setattr(jnp, name, _wrap(obj))
+        else:
+            setattr(jnp, name, obj)
+    jnp.array = lambda a, dtype=None: np.array(a, dtype=dtype if dtype is not None else (dt if np.asarray(a).dtype.kind == "f" else None)).view(JArr)
+    jnp.float32 = dt                       # the reference asks for float32 explicitly in create_mask
+    jnp.linspace = lambda a, b, n: np.linspace(a, b, n, dtype=np.float32).astype(dt).view(JArr)   # jax: fp32 linspace
+    jnp.ndarray = np.ndarray
+    jax = types.ModuleType("jax")
+    jax.numpy = jnp
+    jax.jit = lambda f=None, **kw: f if f is not None else (lambda g: g)
+    nn = types.ModuleType("jax.nn")
+    nn.sigmoid = _wrap(lambda x: 1.0 / (1.0 + np.exp(-x)))
+    nn.softplus = _wrap(lambda x: np.logaddexp(x, 0.0))
+    nn.tanh = _wrap(np.tanh)
+    jax.nn = nn
+    rnd = types.ModuleType("jax.random")
+    rnd.normal = lambda key, shape=None: np.asarray(key).reshape(shape).view(JArr)   # "key" IS the base noise
+    rnd.PRNGKey = lambda s: s
+    jax.random = rnd
+    jax.value_and_grad = lambda f, **k: f
+    jax.lax = types.ModuleType("jax.lax")
+    fu = types.ModuleType("jax.flatten_util")
+    fu.ravel_pytree = lambda t: (None, None)
+    jax.flatten_util = fu
+    mods = {"jax": jax, "jax.numpy": jnp, "jax.nn": nn, "jax.random": rnd, "jax.lax": jax.lax, "jax.flatten_util": fu}
+    for name in ("optax", "numpyro", "numpyro.distributions", "numpyro.infer", "h5py", "physt"):
+        mods[name] = types.ModuleType(name)
+    for a in ("MCMC", "NUTS", "Predictive", "SVI", "Trace_ELBO"):
+        setattr(mods["numpyro.infer"], a, object)
+    mods["physt"].h2 = mods["physt"].h = None
+    mods["numpyro"].distributions = mods["numpyro.distributions"]
+    mods["numpyro"].infer = mods["numpyro.infer"]
+    # package context for the relative import `from ..statutils import ...`
+    naz = types.ModuleType("naz"); naz.__path__ = []
+    flows = types.ModuleType("naz.flows"); flows.__path__ = []
+    st = types.ModuleType("naz.statutils"); st.hpd_vectorized = st.equal_quantile_binning_nd = None
+    mods.update({"naz": naz, "naz.flows": flows, "naz.statutils": st})
+    return mods
+
+
+def load_reference():
+    saved = {k: sys.modules.get(k) for k in make_shim()}
+    sys.modules.update(make_shim())
+    try:
+        spec = importlib.util.spec_from_file_location("naz.flows.bflow_jax_maf", REF)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod
+
+
+CASES = {
+    # name: D, C, hidden, L, N, context per point?
+    "ref_twin_maf_cond_3d": (3, 2, [16, 12], 3, 64, True),
+    "ref_twin_maf_cond_6d": (6, 4, [40, 40, 40], 4, 48, True),
+    "ref_twin_maf_uncond_2d": (2, 0, [16, 16], 3, 64, False),
+    "ref_twin_maf_bcast_ctx_2d": (2, 2, [24, 24, 24], 5, 40, False),   # one context vector for all points (calibrate.py:85,126)
+}
+
+
+def main():
+    ref = load_reference()
+    dt = np.float64 if F64 else np.float32
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    for name, (D, C, hidden, L, N, per_point) in CASES.items():
+        rng = np.random.default_rng(sum(map(ord, name)))
+        perms = np.stack([rng.permutation(D) for _ in range(L)])
+        # the reference's own conditioner / transform factories and masks
+        nn_fn, param_shapes, _gen = ref.make_conditional_autoregressive_nn(D, C, hidden)
+        transform = ref.make_masked_affine_autoregressive_transform(nn_fn, D)
+        masks, mask_skips = [], []
+        for l in range(L):
+            m, ms = ref.create_mask(D, C, hidden, np.asarray(perms[l]).view(JArr), 2)
+            masks.append([np.asarray(a, dtype=dt).view(JArr) for a in m])
+            mask_skips.append(np.asarray(ms, dtype=dt).view(JArr))
+        params = []
+        dims = [D + C] + list(hidden) + [2 * D]
+        for l in range(L):
+            lay = []
+            for j in range(len(dims) - 1):
+                W = (rng.normal(size=(dims[j + 1], dims[j])) / np.sqrt(dims[j])).astype(np.float32)
+                b = (rng.normal(size=(dims[j + 1],)) * 0.1).astype(np.float32)
+                lay.append((W.astype(dt).view(JArr), b.astype(dt).view(JArr)))
+            params.append(lay)
+        x = (rng.normal(size=(N, D)) * 1.5).astype(np.float32)
+        ctx = None
+        if C:
+            ctx = rng.uniform(size=(N, C) if per_point else (C,)).astype(np.float32)
+        flow = ref.make_normalizing_flow(transform, x.astype(dt).view(JArr), masks, mask_skips,
+                                         [np.asarray(p).view(JArr) for p in perms], bounds=None,
+                                         context=None if ctx is None else ctx.astype(dt).view(JArr))
+        lp = np.asarray(flow["lp"](params), dtype=np.float64)
+        arrs = dict(kind="maf", D=D, C=C, hidden=np.array(hidden), L=L, perms=perms, x=x, lp=lp, dtype=str(np.dtype(dt)))
+        if ctx is not None:
+            arrs["ctx"] = ctx
+        # sampler: only defined upstream for a 1-D context (bflow_jax_maf.py:216-218)
+        if ctx is not None and ctx.ndim == 1:
+            zin = rng.normal(size=(N, D)).astype(np.float32)
+            y, log_j = flow["sampler"](params, zin.astype(dt), N)
+            arrs.update(zin=zin, ys=np.asarray(y, np.float64), log_j=np.asarray(log_j, np.float64))
+        for l in range(L):
+            for j, m in enumerate(masks[l]):
+                arrs[f"mask_{l}_{j}"] = np.asarray(m, np.float32)
+            for j, (W, b) in enumerate(params[l]):
+                arrs[f"W_{l}_{j}"] = np.asarray(W, np.float32)
+                arrs[f"b_{l}_{j}"] = np.asarray(b, np.float32)
+        np.savez_compressed(os.path.join(out_dir, name + ".npz"), **arrs)
+        print(name, "lp", lp.min(), lp.max(), "sampler" if "ys" in arrs else "", os.path.getsize(os.path.join(out_dir, name + ".npz")))
+
+
+if __name__ == "__main__":
+    main()
