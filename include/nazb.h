@@ -25,6 +25,9 @@
  *   nazb_lse_reduce/_finish      mean_s exp(lp_s) posterior predictive         examples/papers/2506.05657/plot.py:272-275
  *   nazb_importance              Importance(...).run + posterior.ESS()         src/naz/trainers/train_flows.py:358-380
  *                                compute_bic (max_s sum_n lp)                  src/naz/flows/bflow_jax_maf.py:474-475
+ *   nazb_histogramdd             per-draw np.histogram2d / jnp.histogramdd     src/naz/flows/bflow_jax_maf.py:436-441
+ *                                of the [S][N][D] sample tensor (density=True)
+ *   nazb_hpd                     hpd_vectorized across draws                   src/naz/statutils.py:22-46
  *
  * Conventions
  *   - Every data pointer is a DEVICE pointer owned by the caller (e.g. torch.Tensor.data_ptr()),
@@ -166,6 +169,18 @@ int nazb_lse_finish(const float* lse_max, const float* lse_sum, int32_t G, int32
  * out3 is a device double[3] = {log_evidence, ess, max_sum}; log_w_out device double[S] or NULL. */
 int nazb_importance(const double* sum_n, const float* log_prior, const float* log_q, int32_t S,
                     double* log_w_out, double* out3, void* stream);
+
+/* Consumers of the sample tensor.
+ * nazb_histogramdd: numpy.histogramdd semantics per draw — bin = searchsorted(edges_d, v, "right") - 1, the right-most
+ * edge belongs to the last bin, samples outside any dim's edges (or NaN) are dropped; comparisons in double.
+ *   x        device fp32 [S][N][D];   edges  device double, the D edge arrays concatenated (nbins[d] + 1 each);
+ *   nbins    HOST int32[D];           counts device uint32 [S][prod nbins] (zeroed by the call, C order);
+ *   density  device fp32 [S][prod nbins] or NULL: counts / (sum of the draw's counts * bin volume)  (density=True).
+ * nazb_hpd: v device fp32 [S][M] (e.g. the densities above, M = prod nbins) -> per column the narrowest interval
+ * holding floor((1 - alpha) * S) + 1 order statistics: lo[M], hi[M]  (first minimum on ties, as numpy.argmin). */
+int nazb_histogramdd(const float* x, int32_t S, int64_t N, int32_t D, const double* edges, const int32_t* nbins,
+                     uint32_t* counts, float* density, void* stream);
+int nazb_hpd(const float* v, int32_t S, int64_t M, double alpha, float* lo, float* hi, void* stream);
 
 const char* nazb_strerror(int status);
 const char* nazb_last_cuda_error(const nazb_handle* h);

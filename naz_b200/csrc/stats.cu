@@ -1,0 +1,239 @@
+// Consumers of the [S][N][D] sample tensor: per-draw N-D histograms against fixed bin edges and
+// the highest-posterior-density interval across draws of every bin.  Reference:
+//   calibrate():      A = np.histogram2d / jnp.histogramdd(this_ppd, bins=eq_bins, density=True) per draw
+//                     src/naz/flows/bflow_jax_maf.py:436-441
+//   hpd_vectorized(): src/naz/statutils.py:22-46
+// Both kernels are HBM-bound index work: the histogram reads 4*S*N*D bytes once, the HPD reads 4*S*M bytes once.
+#include <algorithm>
+#include <cfloat>
+#include <cstdio>
+#include <vector>
+#include "nazb_internal.h"
+
+namespace {
+
+constexpr int kHistThreads = 256;
+constexpr int kMaxHistDim = 8;
+constexpr int kSmemBins = 8192;   // 32 KB of shared counters; larger histograms use global atomics directly
+
+struct HistGeom {
+  int D;
+  int nb[kMaxHistDim];        // bins per dim
+  int eoff[kMaxHistDim];      // offset of the dim's edges inside `edges`
+  long long total_bins;
+};
+
+// numpy.histogramdd binning of one coordinate: searchsorted(edges, v, side="right") - 1, the right-most edge belongs to
+// the last bin, anything outside (or NaN) is dropped.  numpy compares the fp32 samples with the fp64 edges in double;
+// for an fp32 v that is EXACTLY  v >= e  <=>  v >= round_up_to_float(e)  and  v <= e  <=>  v <= round_down_to_float(e),
+// so the kernel compares floats against pre-rounded edges: ce[j] = float_ru(e[j]) for j < nb, ce[nb] = float_rd(e[nb]).
+__device__ __forceinline__ int bin_of(float v, const float* ce, int nb) {
+  if (!(v >= ce[0]) || !(v <= ce[nb])) return -1;
+  int lo = 1, hi = nb;               // number of interior edges ce[1..nb-1] that are <= v
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (v >= ce[mid]) lo = mid + 1; else hi = mid;
+  }
+  return lo - 1;
+}
+
+template <int DV>   // DV = 4 / 2: vector loads of a whole point; 0: generic
+__global__ void histdd_kernel(const float* __restrict__ x, long long N, HistGeom g, const double* __restrict__ edges,
+                              int n_edges, unsigned int* __restrict__ counts, int chunks_per_draw, bool use_smem) {
+  extern __shared__ unsigned char hsm[];
+  float* se = reinterpret_cast<float*>(hsm);                                      // [n_edges] pre-rounded edges
+  unsigned int* sc = reinterpret_cast<unsigned int*>(hsm + (size_t)((n_edges * 4 + 15) & ~15));   // [total_bins] if use_smem
+  const int s = blockIdx.x / chunks_per_draw, chunk = blockIdx.x % chunks_per_draw;
+  for (int i = threadIdx.x; i < n_edges; i += blockDim.x) {
+    bool last = false;
+    for (int d = 0; d < g.D; ++d) last = last || (i == g.eoff[d] + g.nb[d]);
+    se[i] = last ? __double2float_rd(edges[i]) : __double2float_ru(edges[i]);
+  }
+  if (use_smem)
+    for (long long i = threadIdx.x; i < g.total_bins; i += blockDim.x) sc[i] = 0u;
+  __syncthreads();
+  const long long per = (N + chunks_per_draw - 1) / chunks_per_draw;
+  const long long n0 = (long long)chunk * per, n1 = min(N, n0 + per);
+  const float* xs = x + (size_t)s * N * g.D;
+  unsigned int* gc = counts + (size_t)s * g.total_bins;
+  for (long long n = n0 + threadIdx.x; n < n1; n += blockDim.x) {
+    float v[kMaxHistDim];
+    if (DV == 4) {
+      const float4 q = *reinterpret_cast<const float4*>(xs + n * 4);
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else if (DV == 2) {
+      const float2 q = *reinterpret_cast<const float2*>(xs + n * 2);
+      v[0] = q.x; v[1] = q.y;
+    } else {
+      for (int d = 0; d < g.D; ++d) v[d] = xs[n * g.D + d];
+    }
+    long long flat = 0;
+    bool ok = true;
+    const int Dn = DV ? DV : g.D;
+#pragma unroll
+    for (int d = 0; d < (DV ? DV : kMaxHistDim); ++d) {
+      if (d < Dn) {
+        const int b = bin_of(v[d], se + g.eoff[d], g.nb[d]);
+        ok = ok && (b >= 0);
+        flat = flat * g.nb[d] + (b >= 0 ? b : 0);      // C order, as numpy
+      }
+    }
+    if (ok) {
+      if (use_smem) atomicAdd(sc + flat, 1u);
+      else atomicAdd(gc + flat, 1u);
+    }
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (long long i = threadIdx.x; i < g.total_bins; i += blockDim.x) {
+      const unsigned int c = sc[i];
+      if (c) atomicAdd(gc + i, c);
+    }
+  }
+}
+
+// density[s][b] = counts[s][b] / (sum_b counts[s][b] * volume[b])   (numpy density=True)
+__global__ void hist_density_kernel(const unsigned int* __restrict__ counts, HistGeom g, const double* __restrict__ edges,
+                                    float* __restrict__ density) {
+  __shared__ unsigned long long tot_s;
+  const int s = blockIdx.x;
+  const unsigned int* c = counts + (size_t)s * g.total_bins;
+  unsigned long long t = 0;
+  for (long long i = threadIdx.x; i < g.total_bins; i += blockDim.x) t += c[i];
+  if (threadIdx.x == 0) tot_s = 0ull;
+  __syncthreads();
+  atomicAdd(&tot_s, t);
+  __syncthreads();
+  const double tot = (double)tot_s;
+  for (long long i = threadIdx.x; i < g.total_bins; i += blockDim.x) {
+    long long r = i;
+    double vol = 1.0;
+    for (int d = g.D - 1; d >= 0; --d) {
+      const int b = (int)(r % g.nb[d]);
+      r /= g.nb[d];
+      vol *= edges[g.eoff[d] + b + 1] - edges[g.eoff[d] + b];
+    }
+    density[(size_t)s * g.total_bins + i] = (float)((double)c[i] / tot / vol);
+  }
+}
+
+// HPD across draws: one CTA = kCols consecutive columns (bins) of v[S][M]; the S values of each column are sorted in
+// shared memory (bitonic, padded with +inf), then the narrowest window holding floor((1 - alpha) S) + 1 order statistics
+// is selected (first minimum, as numpy.argmin).
+constexpr int kHpdCols = 4;
+__global__ void hpd_kernel(const float* __restrict__ v, int S, long long M, int n_pad, int inc, float* __restrict__ lo,
+                           float* __restrict__ hi) {
+  extern __shared__ float hs[];   // [kHpdCols][n_pad]
+  __shared__ float best_w[kHpdCols][32];
+  __shared__ int best_i[kHpdCols][32];
+  const long long m0 = (long long)blockIdx.x * kHpdCols;
+  for (int i = threadIdx.x; i < n_pad * kHpdCols; i += blockDim.x) {
+    const int c = i % kHpdCols, s = i / kHpdCols;
+    float val = INFINITY;
+    if (s < S && m0 + c < M) val = v[(size_t)s * M + m0 + c];
+    hs[c * n_pad + s] = val;
+  }
+  __syncthreads();
+  for (int k = 2; k <= n_pad; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n_pad * kHpdCols; i += blockDim.x) {
+        const int c = i / n_pad, a = i % n_pad, b = a ^ j;
+        if (b > a) {
+          float* col = hs + c * n_pad;
+          const float xa = col[a], xb = col[b];
+          const bool up = ((a & k) == 0);
+          // NaNs sort to the end like numpy: treat NaN as larger than everything
+          const bool gt = (xa > xb) || (xa != xa && xb == xb);
+          if (gt == up) { col[a] = xb; col[b] = xa; }
+        }
+      }
+      __syncthreads();
+    }
+  const int n_int = S - inc;   // number of candidate windows (> 0, checked by the host)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int c = 0; c < kHpdCols; ++c) {
+    const float* col = hs + c * n_pad;
+    float bw = INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < n_int; i += blockDim.x) {
+      const float w = col[i + inc] - col[i];
+      if (w < bw || (w == bw && i < bi)) { bw = w; bi = i; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ow = __shfl_xor_sync(0xffffffffu, bw, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ow < bw || (ow == bw && oi < bi)) { bw = ow; bi = oi; }
+    }
+    if (lane == 0) { best_w[c][warp] = bw; best_i[c][warp] = bi; }
+  }
+  __syncthreads();
+  if (threadIdx.x < kHpdCols && m0 + threadIdx.x < M) {
+    const int c = threadIdx.x;
+    float bw = best_w[c][0];
+    int bi = best_i[c][0];
+    for (int w = 1; w < nwarps; ++w)
+      if (best_w[c][w] < bw || (best_w[c][w] == bw && best_i[c][w] < bi)) { bw = best_w[c][w]; bi = best_i[c][w]; }
+    if (bi == 0x7fffffff) bi = 0;
+    lo[m0 + c] = hs[c * n_pad + bi];
+    hi[m0 + c] = hs[c * n_pad + bi + inc];
+  }
+}
+
+}  // namespace
+
+extern "C" int nazb_histogramdd(const float* x, int32_t S, int64_t N, int32_t D, const double* edges, const int32_t* nbins,
+                                uint32_t* counts, float* density, void* stream) {
+  if (!x || !edges || !nbins || !counts || S < 1 || N < 1 || D < 1 || D > kMaxHistDim) return NAZB_ERR_BAD_ARG;
+  HistGeom g{};
+  g.D = D;
+  long long total = 1;
+  int n_edges = 0;
+  for (int d = 0; d < D; ++d) {
+    if (nbins[d] < 1 || nbins[d] > 4096) return NAZB_ERR_BAD_ARG;
+    g.nb[d] = nbins[d];
+    g.eoff[d] = n_edges;
+    n_edges += nbins[d] + 1;
+    total *= nbins[d];
+    if (total > (1LL << 26)) return NAZB_ERR_UNSUPPORTED;
+  }
+  g.total_bins = total;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (size_t)S * total, st) != cudaSuccess) return NAZB_ERR_CUDA;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const bool use_smem = total <= kSmemBins;
+  // ~8 CTAs per SM in total, at least one chunk per draw, chunks of >= 4096 points
+  long long chunks = std::max<long long>(1, std::min<long long>((16LL * sms + S - 1) / S, (N + 4095) / 4096));
+  const size_t smem = (size_t)((n_edges * 4 + 15) & ~15) + (use_smem ? (size_t)total * 4 : 0);
+  const unsigned grid = (unsigned)(S * chunks);
+  // vector loads need the per-draw base (s * N * D floats) aligned: always true for D = 4; for D = 2 when x is 8-byte aligned
+  if (D == 4 && (reinterpret_cast<uintptr_t>(x) & 15) == 0)
+    histdd_kernel<4><<<grid, kHistThreads, smem, st>>>(x, (long long)N, g, edges, n_edges, counts, (int)chunks, use_smem);
+  else if (D == 2 && (reinterpret_cast<uintptr_t>(x) & 7) == 0)
+    histdd_kernel<2><<<grid, kHistThreads, smem, st>>>(x, (long long)N, g, edges, n_edges, counts, (int)chunks, use_smem);
+  else
+    histdd_kernel<0><<<grid, kHistThreads, smem, st>>>(x, (long long)N, g, edges, n_edges, counts, (int)chunks, use_smem);
+  nazb_count_launch();
+  if (density) {
+    hist_density_kernel<<<S, 256, 0, st>>>(counts, g, edges, density);
+    nazb_count_launch();
+  }
+  return cudaGetLastError() == cudaSuccess ? NAZB_OK : NAZB_ERR_CUDA;
+}
+
+extern "C" int nazb_hpd(const float* v, int32_t S, int64_t M, double alpha, float* lo, float* hi, void* stream) {
+  if (!v || !lo || !hi || S < 1 || M < 1 || !(alpha >= 0.0 && alpha <= 1.0)) return NAZB_ERR_BAD_ARG;
+  const int inc = (int)floor((1.0 - alpha) * (double)S);   // statutils.py:29-30: int(np.floor((1.0 - alpha) * ns)) in double
+  if (S - inc <= 0) return NAZB_ERR_BAD_ARG;                        // "Too few elements for interval calculation"
+  int n_pad = 1;
+  while (n_pad < S) n_pad <<= 1;
+  const size_t smem = (size_t)kHpdCols * n_pad * sizeof(float);
+  if (smem > 200 * 1024) return NAZB_ERR_UNSUPPORTED;               // S <= 8192 draws
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaFuncSetAttribute(hpd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return NAZB_ERR_CUDA;
+  const long long blocks = (M + kHpdCols - 1) / kHpdCols;
+  hpd_kernel<<<(unsigned)blocks, 512, smem, st>>>(v, S, (long long)M, n_pad, inc, lo, hi);
+  nazb_count_launch();
+  return cudaGetLastError() == cudaSuccess ? NAZB_OK : NAZB_ERR_CUDA;
+}

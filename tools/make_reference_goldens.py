@@ -180,5 +180,22 @@ def main():
         print(name, "lp", lp.min(), lp.max(), "sampler" if "ys" in arrs else "", os.path.getsize(os.path.join(out_dir, name + ".npz")))
 
 
+def stats_fixture():
+    """hpd_vectorized of the REAL reference module (src/naz/statutils.py is plain numpy + pandas, importable as is)."""
+    spec = importlib.util.spec_from_file_location("ref_statutils", "/root/reference/src/naz/statutils.py")
+    st = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(st)
+    rng = np.random.default_rng(7)
+    arrs = {}
+    for i, (S, nx, ny, alpha) in enumerate([(200, 5, 7, 0.1), (37, 4, 4, 0.32), (1000, 3, 2, 0.05), (64, 6, 6, 0.5)]):
+        v = rng.gamma(2.0, 1.0, size=(S, nx, ny)).astype(np.float32)
+        v[:, 0, 0] = np.round(v[:, 0, 0])             # ties: argmin must take the first minimum
+        out = st.hpd_vectorized(v, alpha)
+        arrs[f"v_{i}"] = v; arrs[f"alpha_{i}"] = alpha; arrs[f"hpd_{i}"] = np.asarray(out)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_stats_hpd.npz"), n=4, **arrs)
+    print("ref_stats_hpd", os.path.getsize(os.path.join(ROOT, "tests", "golden", "ref_stats_hpd.npz")))
+
+
 if __name__ == "__main__":
     main()
+    stats_fixture()
