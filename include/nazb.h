@@ -25,6 +25,7 @@
  *   nazb_lse_reduce/_finish      mean_s exp(lp_s) posterior predictive         examples/papers/2506.05657/plot.py:272-275
  *   nazb_importance              Importance(...).run + posterior.ESS()         src/naz/trainers/train_flows.py:358-380
  *                                compute_bic (max_s sum_n lp)                  src/naz/flows/bflow_jax_maf.py:474-475
+ *   nazb_pack_draw_map           theta_0 * (1 + scale * standard_params)        src/naz/flows/bflow_jax_maf.py:239-240
  *   nazb_histogramdd             per-draw np.histogram2d / jnp.histogramdd     src/naz/flows/bflow_jax_maf.py:436-441
  *                                of the [S][N][D] sample tensor (density=True)
  *   nazb_hpd                     hpd_vectorized across draws                   src/naz/statutils.py:22-46
@@ -154,6 +155,16 @@ int nazb_forward(nazb_handle* h, int32_t s_begin, int32_t s_count,
                  const float* z, int32_t z_shared, const float* ctx, int32_t ctx_rows, int32_t N,
                  const float* lo, const float* hi,
                  float* x, float* logdet, void* stream);
+
+/* nazb_pack with the Bayesian-flow draw map applied while packing:
+ *   theta_s = theta_0 * (1 + scale * u_s)   src/naz/flows/bflow_jax_maf.py:239-240 (fp32, rounded after every operation)
+ * W0 / b0: HOST tables [L * (n_hidden + 1)] of device pointers to the MLE weights (no draw axis);
+ * uW / ub + uwst / ubst: the standard parameters u_s in [-1, 1] with the same table / stride convention as nazb_pack
+ * (e.g. views into the reference's flat `standard_params` [S, P] matrix: stride P). */
+int nazb_pack_draw_map(nazb_handle* h, const float* const* W0, const float* const* b0, const float* const* uW,
+                       const float* const* ub, const int64_t* uwst, const int64_t* ubst, float scale,
+                       const float* const* mask, const int64_t* perm, const int32_t* hid_deg,
+                       const float* keep, float p_drop, void* stream);
 
 /* Stand-alone cross-draw reduction over a materialised lp[S][N] (kernel group 4):
  * partial (max, sum exp) per point over this rank's draws.  HBM-bound: 4*S*N bytes read. */

@@ -20,7 +20,7 @@ ENGINE_NAMES = {ENGINE_AUTO: "auto", ENGINE_SIMT: "simt", ENGINE_TCGEN05: "tcgen
 SYMBOLS = [
     "nazb_create", "nazb_destroy", "nazb_engine_in_use", "nazb_engine_for_direction", "nazb_pack", "nazb_inverse", "nazb_forward",
     "nazb_lse_reduce", "nazb_lse_finish", "nazb_importance", "nazb_strerror", "nazb_last_cuda_error",
-    "nazb_packed_bytes", "nazb_launch_count", "nazb_histogramdd", "nazb_hpd",
+    "nazb_packed_bytes", "nazb_launch_count", "nazb_histogramdd", "nazb_hpd", "nazb_pack_draw_map",
 ]
 
 
@@ -74,6 +74,9 @@ def lib() -> C.CDLL:
     L.nazb_pack.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), C.POINTER(vp),
                             C.POINTER(i64), C.POINTER(i32), vp, f32, vp]
     L.nazb_pack.restype = C.c_int
+    L.nazb_pack_draw_map.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), f32,
+                                     C.POINTER(vp), C.POINTER(i64), C.POINTER(i32), vp, f32, vp]
+    L.nazb_pack_draw_map.restype = C.c_int
     L.nazb_inverse.argtypes = [vp, i32, i32, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp]
     L.nazb_inverse.restype = C.c_int
     L.nazb_forward.argtypes = [vp, i32, i32, vp, i32, vp, i32, i32, vp, vp, vp, vp, vp]

@@ -489,7 +489,8 @@ __global__ void tc_pack_kernel(Image im, int S, int L, int n_lin, int D, int M, 
                                const long long* __restrict__ bst, const int* __restrict__ perm,
                                const float* __restrict__ keep, long long keep_draw_stride, long long keep_layer_stride,
                                int keep_hk, float inv_keep, uint8_t* __restrict__ dst, unsigned long long draw_bytes,
-                               unsigned long long layer_bytes) {
+                               unsigned long long layer_bytes, const float* const* __restrict__ bWtab,
+                               const float* const* __restrict__ bbtab, float dm_scale) {
   const int KC = im.k_ext >> 3;
   const long long per_layer = (long long)KC * im.n_ext;
   const long long total = per_layer * L * S;
@@ -515,6 +516,8 @@ __global__ void tc_pack_kernel(Image im, int S, int L, int n_lin, int D, int M, 
     const float* W = Wtab[ti] + (size_t)s * wst[ti];
     const float* bb = btab[ti] + (size_t)s * bst[ti];
     const float* mk = mtab[ti];
+    const float* bW = bWtab ? bWtab[ti] : nullptr;     // draw map: W / bb hold the standard parameters u_s
+    const float* bB = bbtab ? bbtab[ti] : nullptr;
     const float* kp = (keep && im.lin > 0) ? keep + (size_t)s * keep_draw_stride + (size_t)l * keep_layer_stride +
                                                  (size_t)(im.lin - 1) * keep_hk
                                            : nullptr;
@@ -524,11 +527,13 @@ __global__ void tc_pack_kernel(Image im, int S, int L, int n_lin, int D, int M, 
       int c = kc * 8 + e;
       float v = 0.f;
       if (o >= 0) {
-        if (c == im.bias_col) v = bb[o];
+        if (c == im.bias_col) { v = bb[o]; if (bB) v = nazb_draw_map(bB[o], v, dm_scale); }
         else if (!im.bias_only) {
           int ks = im.k0 + c;
           if (ks >= im.kv0 && ks < im.kv1 && ks < kdim) {
-            v = W[(size_t)o * kdim + ks] * mk[(size_t)o * kdim + ks];
+            v = W[(size_t)o * kdim + ks];
+            if (bW) v = nazb_draw_map(bW[(size_t)o * kdim + ks], v, dm_scale);
+            v *= mk[(size_t)o * kdim + ks];
             if (kp) v *= kp[ks] * inv_keep;
           }
         }
@@ -1008,7 +1013,8 @@ __global__ void tc_pack_lc_kernel(int S, int L, int n_lin, int D, int M, int Mp,
                                   float hscale, int lc_floats, LcGeom lg, int lc_bout,
                                   const float* const* __restrict__ Wtab, const float* const* __restrict__ btab,
                                   const float* const* __restrict__ mtab, const long long* __restrict__ wst,
-                                  const long long* __restrict__ bst, const int* __restrict__ perm, float* __restrict__ dst) {
+                                  const long long* __restrict__ bst, const int* __restrict__ perm, float* __restrict__ dst,
+                                  const float* const* __restrict__ bWtab, const float* const* __restrict__ bbtab, float dm_scale) {
   const long long total = (long long)S * L * lc_floats;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -1020,16 +1026,28 @@ __global__ void tc_pack_lc_kernel(int S, int L, int n_lin, int D, int M, int Mp,
       int n = f / kinp, k = f % kinp;
       if (n < h0 && k < kin) {
         int ti = l * n_lin;
-        v = hscale * Wtab[ti][(size_t)s * wst[ti] + (size_t)n * kin + k] * mtab[ti][(size_t)n * kin + k];
+        float w = Wtab[ti][(size_t)s * wst[ti] + (size_t)n * kin + k];
+        if (bWtab) w = nazb_draw_map(bWtab[ti][(size_t)n * kin + k], w, dm_scale);
+        v = hscale * w * mtab[ti][(size_t)n * kin + k];
       }
     } else if (f < lc_bout) {
       int j = 0;
       while (j + 1 < n_lin - 1 && f >= lg.lc_b[j + 1]) ++j;
       int n = f - lg.lc_b[j];
-      if (n < lg.hdim[j]) { int ti = l * n_lin + j; v = hscale * btab[ti][(size_t)s * bst[ti] + n]; }
+      if (n < lg.hdim[j]) {
+        int ti = l * n_lin + j;
+        float bv = btab[ti][(size_t)s * bst[ti] + n];
+        if (bbtab) bv = nazb_draw_map(bbtab[ti][n], bv, dm_scale);
+        v = hscale * bv;
+      }
     } else if (f < lc_bout + D * Mp) {
       int n = f - lc_bout, rank = n / Mp, m = n % Mp;
-      if (m < M) { int ti = l * n_lin + (n_lin - 1); v = btab[ti][(size_t)s * bst[ti] + m * D + perm[l * D + rank]]; }
+      if (m < M) {
+        int ti = l * n_lin + (n_lin - 1);
+        const int o = m * D + perm[l * D + rank];
+        v = btab[ti][(size_t)s * bst[ti] + o];
+        if (bbtab) v = nazb_draw_map(bbtab[ti][o], v, dm_scale);
+      }
     }
     dst[idx] = v;
   }
@@ -1108,7 +1126,7 @@ bool nazb_tc_direction_ok(const nazb_handle* h, int dir) {
 
 cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* const* b, const int64_t* wst,
                          const int64_t* bst, const float* const* mask, const float* keep, float p_drop,
-                         cudaStream_t st) {
+                         cudaStream_t st, const DrawMap& dm) {
   TcState* t = static_cast<TcState*>(h->tc);
   const FlowGeom& g = h->geom;
   const int S = h->desc.S, L = g.L, n_lin = g.n_hidden + 1, ntab = L * n_lin;
@@ -1136,12 +1154,14 @@ cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* con
   }
   // pointer / stride tables on the device
   if (t->tab_dev) { cudaFree(t->tab_dev); t->tab_dev = nullptr; }
-  std::vector<const float*> tabs(3 * (size_t)ntab);
+  std::vector<const float*> tabs(5 * (size_t)ntab);
   std::vector<long long> strides(2 * (size_t)ntab);
   for (int i = 0; i < ntab; ++i) {
     tabs[i] = W[i]; tabs[ntab + i] = b[i]; tabs[2 * ntab + i] = mask[i];
+    tabs[3 * ntab + i] = dm.baseW ? dm.baseW[i] : nullptr; tabs[4 * ntab + i] = dm.baseB ? dm.baseB[i] : nullptr;
     strides[i] = wst[i]; strides[ntab + i] = bst[i];
   }
+  const bool has_dm = dm.baseW != nullptr && dm.baseB != nullptr;
   size_t tab_bytes = tabs.size() * sizeof(float*) + strides.size() * sizeof(long long);
   if ((e = cudaMalloc(&t->tab_dev, tab_bytes)) != cudaSuccess) return e;
   if ((e = cudaMemcpy(t->tab_dev, tabs.data(), tabs.size() * sizeof(float*), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
@@ -1159,7 +1179,8 @@ cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* con
                                              t->tab_dev + ntab, t->tab_dev + 2 * ntab, strides_dev, strides_dev + ntab,
                                              h->perm_dev, keep, (long long)L * g.n_hidden * hk, (long long)g.n_hidden * hk,
                                              hk, 1.f / (1.f - p_drop), t->wimg[d], (unsigned long long)t->draw_bytes[d],
-                                             (unsigned long long)P.layer_bytes[d]);
+                                             (unsigned long long)P.layer_bytes[d], has_dm ? t->tab_dev + 3 * ntab : nullptr,
+                                             has_dm ? t->tab_dev + 4 * ntab : nullptr, dm.scale);
       nazb_count_launch();
     }
   }
@@ -1172,7 +1193,8 @@ cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* con
     int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
     tc_pack_lc_kernel<<<blocks, 256, 0, st>>>(S, L, n_lin, g.D, g.M, P.mp, g.kin, P.kinp, P.lc_b[0], g.hidden[0],
                                               2.885390081777927f, P.lc_floats, lg, P.lc_bout, t->tab_dev, t->tab_dev + ntab, t->tab_dev + 2 * ntab,
-                                              strides_dev, strides_dev + ntab, h->perm_dev, t->lc_dev);
+                                              strides_dev, strides_dev + ntab, h->perm_dev, t->lc_dev,
+                                              has_dm ? t->tab_dev + 3 * ntab : nullptr, has_dm ? t->tab_dev + 4 * ntab : nullptr, dm.scale);
     nazb_count_launch();
   }
   if (t->lcf_dev) { cudaFree(t->lcf_dev); t->lcf_dev = nullptr; }
@@ -1184,7 +1206,8 @@ cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* con
     int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
     tc_pack_lc_kernel<<<blocks, 256, 0, st>>>(S, L, n_lin, g.D, g.M, g.M, g.kin, P.kinp > 0 ? P.kinp : 4, 0, g.hidden[0],
                                               2.885390081777927f, P.f_lc_floats, lg, P.f_lc_bout, t->tab_dev, t->tab_dev + ntab,
-                                              t->tab_dev + 2 * ntab, strides_dev, strides_dev + ntab, h->perm_dev, t->lcf_dev);
+                                              t->tab_dev + 2 * ntab, strides_dev, strides_dev + ntab, h->perm_dev, t->lcf_dev,
+                                              has_dm ? t->tab_dev + 3 * ntab : nullptr, has_dm ? t->tab_dev + 4 * ntab : nullptr, dm.scale);
     nazb_count_launch();
   }
   t->plan = P;

@@ -148,9 +148,9 @@ extern "C" int64_t nazb_packed_bytes(const nazb_handle* h) {
   return n;
 }
 
-extern "C" int nazb_pack(nazb_handle* h, const float* const* W, const float* const* b, const int64_t* wst,
-                         const int64_t* bst, const float* const* mask, const int64_t* perm, const int32_t* hid_deg,
-                         const float* keep, float p_drop, void* stream) {
+static int pack_impl(nazb_handle* h, const float* const* W, const float* const* b, const int64_t* wst,
+                     const int64_t* bst, const float* const* mask, const int64_t* perm, const int32_t* hid_deg,
+                     const float* keep, float p_drop, void* stream, const DrawMap& dm) {
   if (!h || !W || !b || !wst || !bst || !mask || !perm) return NAZB_ERR_BAD_ARG;
   if (keep && !(p_drop >= 0.f && p_drop < 1.f)) return NAZB_ERR_BAD_ARG;
   FlowGeom& g = h->geom;
@@ -194,7 +194,7 @@ extern "C" int nazb_pack(nazb_handle* h, const float* const* W, const float* con
   cudaError_t e = cudaSuccess;
   bool need_simt = (h->engine == NAZB_ENGINE_SIMT);
   if (h->engine == NAZB_ENGINE_TCGEN05) {
-    e = nazb_tc_pack(h, W, b, wst, bst, mask, keep, p_drop, st);
+    e = nazb_tc_pack(h, W, b, wst, bst, mask, keep, p_drop, st, dm);
     CK(h, e);
     // a direction the tensor-core programs cannot hold (TMEM budget) is served by the SIMT engine
     need_simt = !nazb_tc_direction_ok(h, 0) || !nazb_tc_direction_ok(h, 1);
@@ -203,11 +203,32 @@ extern "C" int nazb_pack(nazb_handle* h, const float* const* W, const float* con
   }
   if (need_simt) {
     if (!h->packed) CK(h, cudaMalloc(&h->packed, sizeof(float) * (size_t)h->desc.S * h->geom.draw_stride));
-    e = nazb_pack_simt(h, W, b, wst, bst, mask, keep, p_drop, st);
+    e = nazb_pack_simt(h, W, b, wst, bst, mask, keep, p_drop, st, dm);
     CK(h, e);
   }
   h->is_packed = true;
   return NAZB_OK;
+}
+
+extern "C" int nazb_pack(nazb_handle* h, const float* const* W, const float* const* b, const int64_t* wst,
+                         const int64_t* bst, const float* const* mask, const int64_t* perm, const int32_t* hid_deg,
+                         const float* keep, float p_drop, void* stream) {
+  return pack_impl(h, W, b, wst, bst, mask, perm, hid_deg, keep, p_drop, stream, DrawMap());
+}
+
+// Pack S draws given as STANDARD parameters: theta_s = theta_0 * (1 + scale * u_s)  (bflow_jax_maf.py:239-240), applied
+// on the fly while packing, so neither the reference's [S, P] `params` array nor a host loop over draws is materialised.
+extern "C" int nazb_pack_draw_map(nazb_handle* h, const float* const* W0, const float* const* b0, const float* const* uW,
+                                  const float* const* ub, const int64_t* uwst, const int64_t* ubst, float scale,
+                                  const float* const* mask, const int64_t* perm, const int32_t* hid_deg,
+                                  const float* keep, float p_drop, void* stream) {
+  if (!h || !W0 || !b0) return NAZB_ERR_BAD_ARG;
+  const int n = h->geom.L * (h->geom.n_hidden + 1);
+  for (int i = 0; i < n; ++i)
+    if (!W0[i] || !b0[i]) return NAZB_ERR_BAD_ARG;
+  DrawMap dm;
+  dm.baseW = W0; dm.baseB = b0; dm.scale = scale;
+  return pack_impl(h, uW, ub, uwst, ubst, mask, perm, hid_deg, keep, p_drop, stream, dm);
 }
 
 static int check_io(const nazb_handle* h, int s_begin, int s_count, const void* x, const float* ctx, int ctx_rows,

@@ -49,6 +49,18 @@ struct IoArgs {
   int dir;                 // 0 = inverse (log_prob direction), 1 = forward (sample direction)
 };
 
+// Draw map of the Bayesian flow (src/naz/flows/bflow_jax_maf.py:239-240):  theta_s = theta_0 * (1 + scale * u_s)  in fp32,
+// rounded after every operation exactly as the reference's un-fused jnp expression.  When `base*` tables are given to the
+// pack functions, the per-draw tables hold the standard parameters u_s and the map is applied while packing.
+struct DrawMap {
+  const float* const* baseW = nullptr;   // host table [L * n_lin] of device pointers to theta_0 weights [out][in]
+  const float* const* baseB = nullptr;   // ... biases [out]
+  float scale = 0.f;
+};
+__device__ __forceinline__ float nazb_draw_map(float base, float u, float scale) {
+  return __fmul_rn(base, __fadd_rn(1.0f, __fmul_rn(scale, u)));
+}
+
 struct nazb_handle {
   nazb_desc desc;
   FlowGeom geom;
@@ -70,7 +82,7 @@ int nazb_simt_pick_P(const FlowGeom& g);
 
 cudaError_t nazb_pack_simt(nazb_handle* h, const float* const* W, const float* const* b,
                            const int64_t* wst, const int64_t* bst, const float* const* mask,
-                           const float* keep, float p_drop, cudaStream_t st);
+                           const float* keep, float p_drop, cudaStream_t st, const DrawMap& dm = DrawMap());
 
 // tcgen05 engine
 bool nazb_tc_supported(const FlowGeom& g, std::string* why);
@@ -78,7 +90,7 @@ cudaError_t nazb_tc_create(nazb_handle* h);
 void nazb_tc_destroy(nazb_handle* h);
 cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* const* b,
                          const int64_t* wst, const int64_t* bst, const float* const* mask,
-                         const float* keep, float p_drop, cudaStream_t st);
+                         const float* keep, float p_drop, cudaStream_t st, const DrawMap& dm = DrawMap());
 cudaError_t nazb_tc_launch(const nazb_handle* h, const IoArgs& io, int n_groups, cudaStream_t st);
 int64_t nazb_tc_packed_bytes(const nazb_handle* h);
 

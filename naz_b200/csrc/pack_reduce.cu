@@ -16,20 +16,27 @@ __global__ void pack_simt_kernel(const float* __restrict__ W, long long wst, con
                                  long long bst, const float* __restrict__ mask, const float* __restrict__ keep,
                                  long long keep_draw_stride, float inv_keep, int S, int out, int in, int ldw,
                                  int M, int D, const int* __restrict__ rank, float* __restrict__ dst,
-                                 long long off_w, long long off_b, long long draw_stride) {
+                                 long long off_w, long long off_b, long long draw_stride,
+                                 const float* __restrict__ baseW, const float* __restrict__ baseB, float dm_scale) {
   long long total = (long long)S * out * in;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     int k = (int)(i % in);
     int n = (int)((i / in) % out);
     int s = (int)(i / ((long long)in * out));
-    float v = W[(size_t)s * wst + (size_t)n * in + k] * mask[(size_t)n * in + k];
+    float v = W[(size_t)s * wst + (size_t)n * in + k];
+    if (baseW) v = nazb_draw_map(baseW[(size_t)n * in + k], v, dm_scale);
+    v *= mask[(size_t)n * in + k];
     if (keep) v *= keep[(size_t)s * keep_draw_stride + k] * inv_keep;
     int col = n;
     if (rank) { int m = n / D, d = n % D; col = rank[d] * M + m; }
     float* base = dst + (size_t)s * draw_stride;
     base[off_w + (size_t)k * ldw + col] = v;
-    if (k == 0) base[off_b + col] = b[(size_t)s * bst + n];
+    if (k == 0) {
+      float bv = b[(size_t)s * bst + n];
+      if (baseB) bv = nazb_draw_map(baseB[n], bv, dm_scale);
+      base[off_b + col] = bv;
+    }
   }
 }
 
@@ -137,7 +144,7 @@ __global__ void importance_kernel(const double* __restrict__ sum_n, const float*
 
 cudaError_t nazb_pack_simt(nazb_handle* h, const float* const* W, const float* const* b, const int64_t* wst,
                            const int64_t* bst, const float* const* mask, const float* keep, float p_drop,
-                           cudaStream_t st) {
+                           cudaStream_t st, const DrawMap& dm) {
   const FlowGeom& g = h->geom;
   const int S = h->desc.S, n_lin = g.n_hidden + 1;
   cudaError_t e = cudaMemsetAsync(h->packed, 0, (size_t)S * g.draw_stride * sizeof(float), st);
@@ -159,7 +166,8 @@ cudaError_t nazb_pack_simt(nazb_handle* h, const float* const* W, const float* c
                                                1.f / (1.f - p_drop), S, out, in, g.ldw[j], g.M, g.D,
                                                (j == n_lin - 1) ? rank_dev + (size_t)l * g.D : nullptr,
                                                h->packed + (size_t)l * g.layer_stride, g.off_w[j], g.off_b[j],
-                                               g.draw_stride);
+                                               g.draw_stride, dm.baseW ? dm.baseW[i] : nullptr,
+                                               dm.baseB ? dm.baseB[i] : nullptr, dm.scale);
       nazb_count_launch();
     }
   }

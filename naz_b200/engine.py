@@ -143,7 +143,31 @@ class FlowEngine:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     # ------------------------------------------------------------------
-    def pack(self, draws, masks, perms, keep: Optional[torch.Tensor] = None, p_drop: float = 0.0):
+    def pack_draw_map(self, base, standard_params: torch.Tensor, scale: float, masks, perms,
+                      keep: Optional[torch.Tensor] = None, p_drop: float = 0.0):
+        """Pack S draws given as the reference's STANDARD parameters (bflow_jax_maf.py:239-240):
+        theta_s = theta_0 * (1 + scale * u_s), applied while packing (no [S, P] `params` array, no per-draw loop).
+        base: [L][n_lin] of (W0 [out,in], b0 [out]); standard_params: [S, P] with P in `ravel_pytree` order of the params
+        pytree (layer by layer, W then b of each linear, C order) — the layout of posterior["standard_params"]."""
+        sh = self.shape
+        dims = [sh.D + sh.C] + list(sh.hidden) + [sh.M * sh.D]
+        u = _f32c(torch.as_tensor(standard_params), self.device)
+        P = sum(dims[j + 1] * dims[j] + dims[j + 1] for j in range(len(dims) - 1)) * sh.L
+        if u.dim() != 2 or u.shape[0] != self.S or u.shape[1] != P:
+            raise ValueError(f"standard_params must be [S={self.S}, P={P}]")
+        views, off = [], 0
+        for l in range(sh.L):
+            lay = []
+            for j in range(len(dims) - 1):
+                out, inn = dims[j + 1], dims[j]
+                uw = u[:, off:off + out * inn]; off += out * inn       # strided views into the flat matrix (stride P)
+                ub = u[:, off:off + out]; off += out
+                lay.append((uw, ub))
+            views.append(lay)
+        return self.pack(views, masks, perms, keep, p_drop, _base=base, _scale=float(scale), _u_stride=P)
+
+    def pack(self, draws, masks, perms, keep: Optional[torch.Tensor] = None, p_drop: float = 0.0, *, _base=None,
+             _scale: float = 0.0, _u_stride: int = 0):
         """draws: [L][n_lin] of (W, b); W is [S,out,in] or [out,in] (shared by all draws), same for b.
         masks: [L][n_lin] of [out,in] 0/1; perms: [L][D] int; keep: [S,L,n_hidden,max(hidden)] 0/1."""
         sh = self.shape
@@ -156,10 +180,15 @@ class FlowEngine:
         for l in range(L):
             for j in range(n_lin):
                 W, b = draws[l][j]
-                W = _f32c(torch.as_tensor(W), dev)
-                b = _f32c(torch.as_tensor(b), dev)
                 m = _f32c(torch.as_tensor(masks[l][j]), dev)
                 out, inn = dims[j + 1], dims[j]
+                if _base is not None:
+                    # W / b are [S, out*in] / [S, out] views into the flat standard-parameter matrix (draw stride _u_stride)
+                    Wt.append(W); bt.append(b); mt.append(m)
+                    wst.append(_u_stride); bst.append(_u_stride)
+                    continue
+                W = _f32c(torch.as_tensor(W), dev)
+                b = _f32c(torch.as_tensor(b), dev)
                 if W.dim() == 2:
                     W = W.unsqueeze(0)
                 if b.dim() == 1:
@@ -200,11 +229,24 @@ class FlowEngine:
         bp = VP(*[t.data_ptr() for t in bt])
         mp = VP(*[t.data_ptr() for t in mt])
         perm_arr = (C.c_int64 * (L * sh.D))(*perms_t.flatten().tolist())
-        rc = self._lib.nazb_pack(self._h, Wp, bp, I64(*wst), I64(*bst), mp, perm_arr, hid_deg_arr,
-                                 _ptr(keep_t), float(p_drop), self._stream())
-        self._check(rc, "nazb_pack")
+        base_t = None
+        if _base is not None:
+            base_t = [(_f32c(torch.as_tensor(W0), dev), _f32c(torch.as_tensor(b0), dev)) for layer in _base for (W0, b0) in layer]
+            for i, (W0, b0) in enumerate(base_t):
+                out, inn = dims[i % n_lin + 1], dims[i % n_lin]
+                if tuple(W0.shape) != (out, inn) or tuple(b0.shape) != (out,):
+                    raise ValueError("base weights must be [out, in] / [out] per linear")
+            W0p = VP(*[w.data_ptr() for (w, _) in base_t])
+            b0p = VP(*[b_.data_ptr() for (_, b_) in base_t])
+            rc = self._lib.nazb_pack_draw_map(self._h, W0p, b0p, Wp, bp, I64(*wst), I64(*bst), float(_scale), mp, perm_arr,
+                                              hid_deg_arr, _ptr(keep_t), float(p_drop), self._stream())
+            self._check(rc, "nazb_pack_draw_map")
+        else:
+            rc = self._lib.nazb_pack(self._h, Wp, bp, I64(*wst), I64(*bst), mp, perm_arr, hid_deg_arr,
+                                     _ptr(keep_t), float(p_drop), self._stream())
+            self._check(rc, "nazb_pack")
         # the pack kernels read the source tensors asynchronously on the current stream
-        self._keepalive = (Wt, bt, mt, keep_t)
+        self._keepalive = (Wt, bt, mt, keep_t, base_t)
         return self
 
     # ------------------------------------------------------------------

@@ -106,6 +106,46 @@ def test_cuda_matches_reference_outputs_maf(name, engine):
         check(ld[0].cpu().numpy().astype(np.float64) + base, g["log_j"], "sampler log_j vs reference", atol=1e-4)
 
 
+@pytest.mark.parametrize("engine", ["auto", "simt"])
+def test_draw_map_pack_equals_materialised_draws(engine):
+    """f3: theta_s = theta_0 (1 + scale u_s) applied while packing (nazb_pack_draw_map, bflow_jax_maf.py:239-240) gives
+    bit-identical results to packing the materialised fp32 draws, for both directions."""
+    from naz_b200 import FlowEngine, FlowShape
+    S, scale = 5, 0.25
+    spec, _, _, rng = make_case("nsa", 4, 2, [150] * 3, 4, 1, seed=31)
+    p0 = fo.init_weights(spec, rng, np.float32)
+    dims = [6, 150, 150, 150, 23 * 4]
+    P = sum(dims[j + 1] * dims[j] + dims[j + 1] for j in range(4)) * spec.L
+    u = rng.uniform(-1, 1, size=(S, P)).astype(np.float32)
+    # materialise exactly as the reference does: flat_params * (1.0 + scale * standard_params), fp32, ravel_pytree order
+    flat0 = np.concatenate([np.concatenate([W.ravel(), b.ravel()]) for layer in p0 for (W, b) in layer]).astype(np.float32)
+    theta = flat0[None, :] * (np.float32(1.0) + np.float32(scale) * u)
+    draws, off = [], 0
+    for l in range(spec.L):
+        lay = []
+        for j in range(4):
+            out, inn = dims[j + 1], dims[j]
+            W = theta[:, off:off + out * inn].reshape(S, out, inn); off += out * inn
+            b = theta[:, off:off + out]; off += out
+            lay.append((np.ascontiguousarray(W), np.ascontiguousarray(b)))
+        draws.append(lay)
+    x = (rng.normal(size=(300, 4)) * 1.5).astype(np.float32)
+    ctx = rng.uniform(size=(2,)).astype(np.float32)
+    z = rng.normal(size=(300, 4)).astype(np.float32)
+    ref_eng = engine_for(spec, draws, engine=engine)
+    a = ref_eng.inverse(T(x), T(ctx), want_lp=True)["lp"]
+    xa = ref_eng.forward(T(z), T(ctx))
+    shape = FlowShape("nsa", 4, 2, [150] * 3, spec.L, 8, spec.bound, spec.clip)
+    e2 = FlowEngine(shape, S, device="cuda:0", engine=engine)
+    e2.pack_draw_map([[(T(W), T(b)) for (W, b) in layer] for layer in p0], T(u), scale,
+                     [[T(m) for m in ml] for ml in spec.masks()], T(spec.perms))
+    b_ = e2.inverse(T(x), T(ctx), want_lp=True)["lp"]
+    xb = e2.forward(T(z), T(ctx))
+    assert torch.equal(a, b_) and torch.equal(xa, xb)
+    lp_ref, _ = fo.log_prob_draws(spec, to64(draws), x.astype(np.float64), ctx.astype(np.float64))
+    check(b_, lp_ref, "lp through the draw map")
+
+
 def test_first_layer_cuda_core_fallback_matches_tensor_core_path(monkeypatch):
     """The inverse kernel runs the first conditioner layer either as a K = 16 tcgen05 contraction or, when TMEM / the K slice
     has no room, on CUDA cores from the layer constants; both must agree with the oracle on the headline shape."""
