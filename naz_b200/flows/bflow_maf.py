@@ -92,7 +92,36 @@ def make_normalizing_flow(transform, x, masks, mask_skips, perms, bounds=None, c
             return y[0], log_j[0]
         return y, log_j
 
-    return {"lp": log_prob, "sampler": sample}
+    def _engine_standard(best_params, standard_params, scale) -> FlowEngine:
+        """Engine packed straight from the reference's posterior format {"standard_params": [S, P], "scale"}:
+        the draw map of bflow_jax_maf.py:239-240 runs inside the pack kernels (nazb_pack_draw_map)."""
+        u = torch.as_tensor(standard_params, dtype=torch.float32)
+        S = u.shape[0]
+        key = ("std", S, u.data_ptr(), float(scale)) + tuple(t.data_ptr() for layer in best_params for pair in layer for t in pair)
+        if cache.get("key") != key:
+            if cache.get("eng") is None or cache["eng"].S != S:
+                cache["eng"] = FlowEngine(shape, S, device=dev, engine=engine)
+            cache["eng"].pack_draw_map(best_params, u, scale, masks, torch.stack([torch.as_tensor(p) for p in perms]))
+            cache["key"] = key
+        return cache["eng"]
+
+    def log_prob_standard(best_params, standard_params, scale):
+        """[S, N] log-densities of all posterior draws given as standard parameters (additive entry point: replaces the
+        `for i in range(S): lp(unravel(params[i]))` loops of calibrate.py:144-150 / compute_bic_simpler.py:116-120)."""
+        assert bnd is None, "bounded flows: use lp(draw_params(...))"
+        return _engine_standard(best_params, standard_params, scale).inverse(x_dev, ctx, None, want_lp=True)["lp"]
+
+    def sample_standard(best_params, standard_params, scale, rng_key, size):
+        eng = _engine_standard(best_params, standard_params, scale)
+        gen = rng_key if isinstance(rng_key, torch.Generator) else None
+        if gen is None and rng_key is not None:
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(int(rng_key))
+        z = torch.randn((eng.S, size, D), device=dev, generator=gen)
+        assert ctx is None or ctx.dim() == 1
+        return eng.forward(z, ctx)
+
+    return {"lp": log_prob, "sampler": sample, "lp_standard": log_prob_standard, "sampler_standard": sample_standard}
 
 
 def draw_params(best_params, standard_params: torch.Tensor, scale: float):

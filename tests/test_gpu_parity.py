@@ -352,6 +352,13 @@ def test_reference_python_api_drop_in():
     batched = [[(post[f"flow_{i}_nn.layers.{j}.weight"], post[f"flow_{i}_nn.layers.{j}.bias"]) for j in range(4)] for i in range(L)]
     lpb_ref, _ = fo.log_prob_draws(spec, draws64, x.astype(np.float64), ctx.astype(np.float64))
     check(twin["lp"](batched), lpb_ref, "twin lp, batched draws")
+    # posterior format {"standard_params": [S, P], "scale"}: the draw map runs inside the pack kernels
+    from naz_b200.flows.bflow_maf import draw_params
+    Pn = sum(W.numel() + b.numel() for layer in tp for (W, b) in layer)
+    ustd = torch.rand((S, Pn), device="cuda") * 2 - 1
+    lps = twin["lp_standard"](tp, ustd, 0.1)
+    lpm = twin["lp"](draw_params(tp, ustd, 0.1))
+    assert lps.shape == (S, N) and torch.allclose(lps, lpm, rtol=1e-5, atol=1e-5)
     twin1 = make_normalizing_flow(tr, T(x), masks, mask_skips, tperms, context=c1)
     y, logj = twin1["sampler"](tp, 0, 128)
     assert y.shape == (128, D) and logj.shape == (128,)
