@@ -208,6 +208,19 @@ def test_ragged_and_tiny_batches(N):
         check(out["lp"], lp_ref, f"lp N={N} {engine}")
 
 
+@pytest.mark.parametrize("N", [1, 255, 256, 257, 513])
+def test_ragged_and_tiny_batches_sampling(N):
+    """forward (sample) direction at tile-pair boundaries of the two-tile kernel (256 points per work item)."""
+    spec, draws, _, rng = make_case("nsa", 4, 2, [48, 48], 3, 3, seed=5)
+    z = rng.normal(size=(3, N, 4)).astype(np.float32)
+    ctx = rng.uniform(size=(2,)).astype(np.float32)
+    xs_ref, ld_ref = fo.sample_draws(spec, to64(draws), z.astype(np.float64), ctx.astype(np.float64))
+    for engine in ("auto", "simt"):
+        xs, ld = engine_for(spec, draws, engine=engine).forward(T(z), T(ctx), want_logdet=True)
+        check(xs, xs_ref, f"samples N={N} {engine}")
+        check(ld, ld_ref, f"log-det N={N} {engine}", atol=1e-4)
+
+
 def test_error_behaviour():
     from naz_b200 import FlowEngine, FlowShape, _lib
     spec, draws, _, rng = make_case("maf", 3, 2, [16, 16], 2, 2, seed=0)
