@@ -46,6 +46,7 @@ SHAPES = [
     ("maf", 12, 4, [150] * 3, 4, 2, 200, "quadratic"),       # D + C = 16: first conditioner layer on CUDA cores (no K = 16 slice left for the bias column)
     ("nsa", 3, 2, [32, 48], 3, 2, 300, "quadratic"),         # 2-3 K slices per layer: fewer slices than epilogue parts (idle parts must not be lapped)
     ("maf", 3, 1, [16, 16], 4, 3, 600, "quadratic"),         # one K slice per layer, one 8-column block per stage
+    ("nsa", 8, 4, [150] * 3, 4, 2, 300, "quadratic"),        # 184 spline columns: one-tile forward kernel (fwd3), inverse on SIMT
 ]
 
 
