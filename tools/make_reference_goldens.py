@@ -130,10 +130,10 @@ CASES = {
 }
 
 
-def main():
+def main(out_dir=None):
     ref = load_reference()
     dt = np.float64 if F64 else np.float32
-    out_dir = os.path.join(ROOT, "tests", "golden")
+    out_dir = out_dir or os.path.join(ROOT, "tests", "golden")
     for name, (D, C, hidden, L, N, per_point) in CASES.items():
         rng = np.random.default_rng(sum(map(ord, name)))
         perms = np.stack([rng.permutation(D) for _ in range(L)])
@@ -180,8 +180,9 @@ def main():
         print(name, "lp", lp.min(), lp.max(), "sampler" if "ys" in arrs else "", os.path.getsize(os.path.join(out_dir, name + ".npz")))
 
 
-def stats_fixture():
+def stats_fixture(out_dir=None):
     """hpd_vectorized of the REAL reference module (src/naz/statutils.py is plain numpy + pandas, importable as is)."""
+    out_dir = out_dir or os.path.join(ROOT, "tests", "golden")
     spec = importlib.util.spec_from_file_location("ref_statutils", "/root/reference/src/naz/statutils.py")
     st = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(st)
@@ -192,8 +193,8 @@ def stats_fixture():
         v[:, 0, 0] = np.round(v[:, 0, 0])             # ties: argmin must take the first minimum
         out = st.hpd_vectorized(v, alpha)
         arrs[f"v_{i}"] = v; arrs[f"alpha_{i}"] = alpha; arrs[f"hpd_{i}"] = np.asarray(out)
-    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_stats_hpd.npz"), n=4, **arrs)
-    print("ref_stats_hpd", os.path.getsize(os.path.join(ROOT, "tests", "golden", "ref_stats_hpd.npz")))
+    np.savez_compressed(os.path.join(out_dir, "ref_stats_hpd.npz"), n=4, **arrs)
+    print("ref_stats_hpd", os.path.getsize(os.path.join(out_dir, "ref_stats_hpd.npz")))
 
 
 if __name__ == "__main__":
