@@ -26,6 +26,7 @@
  *   nazb_importance              Importance(...).run + posterior.ESS()         src/naz/trainers/train_flows.py:358-380
  *                                compute_bic (max_s sum_n lp)                  src/naz/flows/bflow_jax_maf.py:474-475
  *   nazb_pack_draw_map           theta_0 * (1 + scale * standard_params)        src/naz/flows/bflow_jax_maf.py:239-240
+ *   nazb_truncnorm_sample        TruncatedNormalTransform.__call__ / log_prob   src/naz/priors/TruncatedNormal.py:14-60
  *   nazb_histogramdd             per-draw np.histogram2d / jnp.histogramdd     src/naz/flows/bflow_jax_maf.py:436-441
  *                                of the [S][N][D] sample tensor (density=True)
  *   nazb_hpd                     hpd_vectorized across draws                   src/naz/statutils.py:22-46
@@ -165,6 +166,15 @@ int nazb_pack_draw_map(nazb_handle* h, const float* const* W0, const float* cons
                        const float* const* ub, const int64_t* uwst, const int64_t* ubst, float scale,
                        const float* const* mask, const int64_t* perm, const int32_t* hid_deg,
                        const float* keep, float p_drop, void* stream);
+
+/* Truncated-normal guide of the SVI / importance path: src/naz/priors/TruncatedNormal.py:14-60, used by
+ * src/naz/flows/bflow.py:35,43 and (numpyro's twin) bflow_jax_maf.py:257.  x: device fp32 [S][P] uniforms in (0, 1)
+ * supplied by the caller (RNG stays with the caller); loc / scale / low / high: device fp32 with 1 or P elements each;
+ * y: [S][P] samples (feed them to nazb_pack_draw_map as standard parameters); log_q: device double [S] = sum over the P
+ * parameters of log pdf(y) - log(cdf(high) - cdf(low))  (the log q(theta_s) of nazb_importance). */
+int nazb_truncnorm_sample(const float* x, int32_t S, int64_t P, const float* loc, int32_t loc_n, const float* scale,
+                          int32_t scale_n, const float* low, int32_t low_n, const float* high, int32_t high_n,
+                          float* y, double* log_q, void* stream);
 
 /* Stand-alone cross-draw reduction over a materialised lp[S][N] (kernel group 4):
  * partial (max, sum exp) per point over this rank's draws.  HBM-bound: 4*S*N bytes read. */

@@ -66,3 +66,29 @@ def hpd_draws(values: torch.Tensor, alpha: float = 0.1) -> torch.Tensor:
             raise ValueError("Too few elements for interval calculation")   # statutils.py:33-34
         raise _lib.NazbError(rc, "nazb_hpd")
     return out.view((2,) + tuple(values.shape[1:]))
+
+
+def truncnorm_sample(uniform: torch.Tensor, loc, scale, low, high) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Truncated-normal guide (priors/TruncatedNormal.py:14-60).  uniform: CUDA fp32 [S, P] in (0, 1); loc / scale / low /
+    high: scalars or [P].  Returns (samples [S, P] fp32, log_q [S] float64 = sum_p log q(sample))."""
+    if not uniform.is_cuda:
+        raise RuntimeError("naz_b200.stats needs a CUDA tensor (no CPU fallback)")
+    x = uniform.contiguous().float()
+    S, P = x.shape
+    dev = x.device
+    ps = []
+    for v in (loc, scale, low, high):
+        t = torch.as_tensor(v, dtype=torch.float32).to(dev).reshape(-1).contiguous()
+        if t.numel() not in (1, P):
+            raise ValueError("loc / scale / low / high must be scalars or have P elements")
+        ps.append(t)
+    y = torch.empty_like(x)
+    log_q = torch.empty((S,), dtype=torch.float64, device=dev)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        rc = L.nazb_truncnorm_sample(x.data_ptr(), S, P, ps[0].data_ptr(), ps[0].numel(), ps[1].data_ptr(), ps[1].numel(),
+                                     ps[2].data_ptr(), ps[2].numel(), ps[3].data_ptr(), ps[3].numel(), y.data_ptr(),
+                                     log_q.data_ptr(), _stream(dev))
+    if rc != 0:
+        raise _lib.NazbError(rc, "nazb_truncnorm_sample")
+    return y, log_q

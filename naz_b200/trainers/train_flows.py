@@ -43,3 +43,21 @@ def importance_weights(flow, theta_train, condition_train, draws, log_prior=None
     sum_n = flow.log_prob_draws(theta_train, draws, condition=condition_train, reduce="sum")
     lw, log_z, ess, _ = importance(sum_n, log_prior, log_q)
     return lw, float(log_z), float(ess)
+
+
+def svi_importance(engine, base_params, masks, perms, x, condition, mu_q, sigma_q, scale, uniform, low=-1.0, high=1.0):
+    """Importance-weighted evidence from the variational guide, entirely on the device:
+      u_s   ~ TruncatedNormal(mu_q, sigma_q, low, high)          bflow_jax_maf.py:251-257 / priors/TruncatedNormal.py
+      theta = theta_0 * (1 + scale * u_s)                        bflow_jax_maf.py:239-240  (inside the pack kernels)
+      log w = log p(u_s) + sum_n log p(x_n | theta_s) - log q(u_s), p(u) = Uniform(-1, 1)^P   (train_flows.py:358-378)
+    `uniform` is the caller's [S, P] U(0,1) noise.  Returns (log_w [S] float64, log_evidence, ESS, u [S, P])."""
+    import math
+    from ..engine import importance
+    from ..stats import truncnorm_sample
+    u, log_q = truncnorm_sample(uniform, mu_q, sigma_q, low, high)
+    engine.pack_draw_map(base_params, u, scale, masks, perms)
+    sum_n = engine.inverse(x, condition, want_lp=False, want_sum=True)["sum_n"]
+    P = u.shape[1]
+    log_prior = torch.full((u.shape[0],), -P * math.log(2.0), dtype=torch.float32, device=u.device)
+    lw, log_z, ess, _ = importance(sum_n, log_prior, log_q.to(torch.float32))
+    return lw, float(log_z), float(ess), u

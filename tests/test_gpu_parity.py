@@ -147,6 +147,48 @@ def test_draw_map_pack_equals_materialised_draws(engine):
     check(b_, lp_ref, "lp through the draw map")
 
 
+def test_svi_importance_pipeline_on_device():
+    """cfg-4 data flow end to end on the device: truncated-normal guide draws -> draw map while packing -> sum_n log-prob
+    -> importance weights / evidence / ESS, against the fp64 oracle pipeline."""
+    from naz_b200 import FlowEngine, FlowShape
+    from naz_b200.trainers import svi_importance
+    from oracle import stats_oracle as so
+    S, N, scale = 12, 500, 0.2
+    spec, _, _, rng = make_case("maf", 2, 2, [48, 48, 48], 4, 1, seed=17)
+    p0 = fo.init_weights(spec, rng, np.float32)
+    dims = [4, 48, 48, 48, 4]
+    P = sum(dims[j + 1] * dims[j] + dims[j + 1] for j in range(4)) * spec.L
+    mu_q = rng.uniform(-0.1, 0.1, size=P).astype(np.float32)
+    sigma_q = np.full(P, 0.1, np.float32)
+    unif = rng.uniform(0.02, 0.98, size=(S, P)).astype(np.float32)
+    x = (rng.normal(size=(N, 2)) * 1.5).astype(np.float32)
+    ctx = rng.uniform(size=(N, 2)).astype(np.float32)
+    eng = FlowEngine(FlowShape("maf", 2, 2, [48, 48, 48], spec.L), S, device="cuda:0")
+    lw, log_z, ess, u = svi_importance(eng, [[(T(W), T(b)) for (W, b) in layer] for layer in p0],
+                                       [[T(m) for m in ml] for ml in spec.masks()], T(spec.perms), T(x), T(ctx),
+                                       T(mu_q), T(sigma_q), scale, T(unif).cuda())
+    # oracle pipeline in float64 (draw map from the device's fp32 u so both sides score the same draws)
+    u64, log_q = so.truncnorm_sample(unif, mu_q, sigma_q, -1.0, 1.0)
+    assert np.allclose(u.cpu().numpy(), u64, rtol=1e-4, atol=1e-5)
+    uf = u.cpu().numpy()
+    flat0 = np.concatenate([np.concatenate([W.ravel(), b.ravel()]) for layer in p0 for (W, b) in layer]).astype(np.float32)
+    theta = (flat0[None, :] * (np.float32(1.0) + np.float32(scale) * uf)).astype(np.float64)
+    draws, off = [], 0
+    for l in range(spec.L):
+        lay = []
+        for j in range(4):
+            out, inn = dims[j + 1], dims[j]
+            W = theta[:, off:off + out * inn].reshape(S, out, inn); off += out * inn
+            b = theta[:, off:off + out]; off += out
+            lay.append((W, b))
+        draws.append(lay)
+    lp_ref, _ = fo.log_prob_draws(spec, draws, x.astype(np.float64), ctx.astype(np.float64))
+    lw_ref, logz_ref, ess_ref = fo.importance(lp_ref.sum(1), np.full(S, -P * math.log(2.0)), log_q)
+    assert np.allclose(lw.cpu().numpy(), lw_ref, rtol=2e-5, atol=2e-2)      # sums of N fp32 log-probs + P fp32 log-densities
+    assert abs(log_z - logz_ref) <= 2e-5 * abs(logz_ref) + 2e-2
+    assert 1.0 <= ess <= S and abs(ess - ess_ref) <= 0.05 * ess_ref + 0.05
+
+
 def test_first_layer_cuda_core_fallback_matches_tensor_core_path(monkeypatch):
     """The inverse kernel runs the first conditioner layer either as a K = 16 tcgen05 contraction or, when TMEM / the K slice
     has no room, on CUDA cores from the layer constants; both must agree with the oracle on the headline shape."""

@@ -18,8 +18,9 @@ def test_committed_reference_fixtures_are_reproducible(tmp_path):
     spec.loader.exec_module(gen)
     gen.main(str(tmp_path))
     gen.stats_fixture(str(tmp_path))
+    gen.truncnorm_fixture(str(tmp_path))
     names = [f for f in os.listdir(tmp_path) if f.endswith(".npz")]
-    assert len(names) >= 5
+    assert len(names) >= 6
     for f in names:
         new = np.load(os.path.join(tmp_path, f))
         old = np.load(os.path.join(ROOT, "tests", "golden", f))

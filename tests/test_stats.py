@@ -22,6 +22,38 @@ def test_hpd_oracle_matches_reference_outputs():
         so.hpd_vectorized(np.zeros((3, 2, 2)), 0.0)          # statutils.py:33-34
 
 
+TN_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_truncnorm.npz")
+
+
+def test_truncnorm_oracle_matches_reference_outputs():
+    """oracle (fp64) vs the reference's own TruncatedNormalTransform executed in fp32 (tools/make_reference_goldens.py)."""
+    g = np.load(TN_GOLD)
+    for i in range(int(g["n"])):
+        y, log_q = so.truncnorm_sample(g[f"x_{i}"], g[f"loc_{i}"], g[f"scale_{i}"], g[f"low_{i}"], g[f"high_{i}"])
+        assert np.allclose(y, g[f"y_{i}"], rtol=2e-5, atol=2e-6)
+        assert np.allclose(log_q, g[f"log_q_{i}"], rtol=2e-5)
+        lo, hi = np.broadcast_to(g[f"low_{i}"], y.shape[1:]), np.broadcast_to(g[f"high_{i}"], y.shape[1:])
+        assert (y >= lo - 1e-6).all() and (y <= hi + 1e-6).all()
+
+
+@pytest.mark.gpu
+def test_truncnorm_matches_reference_outputs_and_feeds_importance():
+    from naz_b200.stats import truncnorm_sample
+    g = np.load(TN_GOLD)
+    for i in range(int(g["n"])):
+        y, log_q = truncnorm_sample(torch.from_numpy(g[f"x_{i}"]).cuda(), g[f"loc_{i}"], g[f"scale_{i}"], g[f"low_{i}"], g[f"high_{i}"])
+        assert np.allclose(y.cpu().numpy(), g[f"y_{i}"], rtol=2e-5, atol=2e-6)          # vs the reference's fp32 outputs
+        assert np.allclose(log_q.cpu().numpy(), g[f"log_q_{i}"], rtol=2e-5)
+        yo, lqo = so.truncnorm_sample(g[f"x_{i}"], g[f"loc_{i}"], g[f"scale_{i}"], g[f"low_{i}"], g[f"high_{i}"])
+        assert np.allclose(y.cpu().numpy(), yo, rtol=2e-5, atol=2e-6) and np.allclose(log_q.cpu().numpy(), lqo, rtol=2e-5)
+    # big shape: 256 draws x 51 k parameters (cfg 4's flow), log_q sums in double
+    S, P = 256, 51_000
+    x = torch.rand((S, P), device="cuda") * 0.96 + 0.02
+    y, log_q = truncnorm_sample(x, 0.1, 0.1, -1.0, 1.0)
+    yo, lqo = so.truncnorm_sample(x.cpu().numpy(), 0.1, 0.1, -1.0, 1.0)
+    assert np.allclose(y.cpu().numpy(), yo, rtol=1e-4, atol=1e-5) and np.allclose(log_q.cpu().numpy(), lqo, rtol=1e-5)
+
+
 def _edges(rng, D, nb):
     # quantile-like, unequal bin widths
     return [np.concatenate([[-3.0], np.sort(rng.uniform(-2.5, 2.5, size=nb[d] - 1)), [3.0]]) for d in range(D)]

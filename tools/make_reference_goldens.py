@@ -197,6 +197,50 @@ def stats_fixture(out_dir=None):
     print("ref_stats_hpd", os.path.getsize(os.path.join(out_dir, "ref_stats_hpd.npz")))
 
 
+def truncnorm_fixture(out_dir=None):
+    """TruncatedNormalTransform of the REAL reference module (src/naz/priors/TruncatedNormal.py: pure torch math; only its
+    `pyro.distributions` import and `utils.set_device` are stubbed), executed on CPU in fp32 as the reference would."""
+    import torch
+    out_dir = out_dir or os.path.join(ROOT, "tests", "golden")
+    stubs = {"pyro": types.ModuleType("pyro"), "pyro.distributions": types.ModuleType("pyro.distributions"),
+             "utils": types.ModuleType("utils")}
+    stubs["pyro"].distributions = stubs["pyro.distributions"]
+    stubs["utils"].set_device = lambda t, *a, **k: t
+    saved = {k: sys.modules.get(k) for k in stubs}
+    sys.modules.update(stubs)
+    try:
+        spec = importlib.util.spec_from_file_location("ref_truncnorm", "/root/reference/src/naz/priors/TruncatedNormal.py")
+        tn = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(tn)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    rng = np.random.default_rng(11)
+    S, P = 6, 500
+    arrs = {}
+    # (0) the torch-path guide: per-parameter bounds mean -/+ sigma (bflow.py:30-35); (1) the twin's guide: [-1, 1] (bflow_jax_maf.py:251-257)
+    mean = (rng.normal(size=P) * 0.5).astype(np.float32)
+    sigma = (np.abs(mean) * 0.25 + 0.05).astype(np.float32)
+    cases = [(mean, sigma, mean - sigma, mean + sigma),
+             (rng.uniform(-0.5, 0.5, size=P).astype(np.float32), rng.uniform(0.3, 1.0, size=P).astype(np.float32),
+              np.float32(-1.0), np.float32(1.0))]
+    for i, (loc, scale, low, high) in enumerate(cases):
+        x = rng.uniform(0.02, 0.98, size=(S, P)).astype(np.float32)
+        tr = tn.TruncatedNormalTransform(torch.from_numpy(np.asarray(loc)), torch.from_numpy(np.asarray(scale)),
+                                         torch.as_tensor(low), torch.as_tensor(high))
+        xt = torch.from_numpy(x)
+        y = tr(xt)
+        log_q = -(tr.log_abs_det_jacobian(xt, y)).sum(-1)          # Uniform(0,1) base: log q(y) = 0 - log|dy/dx|
+        arrs.update({f"x_{i}": x, f"loc_{i}": np.asarray(loc), f"scale_{i}": np.asarray(scale), f"low_{i}": np.asarray(low),
+                     f"high_{i}": np.asarray(high), f"y_{i}": y.numpy(), f"log_q_{i}": log_q.numpy()})
+    np.savez_compressed(os.path.join(out_dir, "ref_truncnorm.npz"), n=len(cases), **arrs)
+    print("ref_truncnorm", os.path.getsize(os.path.join(out_dir, "ref_truncnorm.npz")))
+
+
 if __name__ == "__main__":
     main()
     stats_fixture()
+    truncnorm_fixture()
