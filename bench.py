@@ -347,7 +347,7 @@ def main_ours(args):
                        "pack_seconds_excluded": pack_s, "result_finite": finite},
             "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
                          "traffic": traffic, "peak_source": f"{peak_kind} bf16 dense, sustained",
-                         "note": "achieved = algorithmic F1 (%d flop/eval, masks as dense zeros, never the D-pass count) x evals per launch / CUDA-event kernel time; the kernel issues 3 fp16 MMAs per algorithmic product" % f1},
+                         "note": "achieved = algorithmic F1 (%d flop/eval, masks as dense zeros, never the D-pass count) x evals per launch / CUDA-event kernel time; the kernel issues 3 fp16 MMAs per algorithmic product (M = 64 tiles); ncu: tensor pipe ~32 %% active, MUFU ~20 %%, the kernel is bound by the dependency chain of the autoregressive inverse (DESIGN.md 5.2)" % f1},
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(x_host.numel() * 4 + (C * 4 if C else 0)),
                     "d2h_bytes_per_step": int(N * 4)},
             "gpu_launches": int(launches),
