@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include "../naz_b200/csrc/tc_ptx.cuh"
+#include "../naz_b200/csrc/transforms.cuh"
 
 __global__ void k_mufu(float* out, int iters, long long* cyc) {
   float v[8];
@@ -39,6 +40,25 @@ __global__ void k_tanh(float* out, int iters, long long* cyc) {
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
+__global__ void k_spline(float* out, int iters, long long* cyc, int pair) {
+  float own[8], dr[8], rf[24];
+  for (int i = 0; i < 8; ++i) { own[i] = 0.1f * i + 0.01f * threadIdx.x; dr[i] = 0.3f - 0.05f * i; }
+  for (int i = 0; i < 24; ++i) rf[i] = 0.07f * i - 0.5f + 0.01f * threadIdx.x;
+  float y = 0.3f, acc = 0.f;
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    float xv, ld;
+    if (pair) nazb::rqs8_inv_pair(y, 3.f, own, dr, (threadIdx.x >> 4) & 1, xv, ld);
+    else nazb::rqs_fast<8>(y, 3.f, true, rf, xv, ld);
+    acc += ld;
+    y = 0.9f * xv;            // dependent chain across iterations, like consecutive stages
+    own[it & 7] += 1e-3f * xv; rf[it % 24] += 1e-3f * xv;
+  }
+  long long t1 = clock64();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc + y;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
 int main() {
   float* out; long long* cyc;
   cudaMalloc(&out, 148 * 1024 * 4); cudaMalloc(&cyc, 148 * 8);
@@ -54,6 +74,14 @@ int main() {
     double c2 = (double)h[0] / iters;
     printf("warps/SM %2d: 16 MUFU/thread-iter: %.1f cycles/iter -> %.2f MUFU lane-ops/clk/SM | tanh8 chunk: %.1f cycles/iter -> %.2f MUFU lane-ops/clk/SM\n",
            warps, c1, 16.0 * warps * 32 / c1, c2, 16.0 * warps * 32 / c2);
+  }
+  for (int warps : {1, 4, 8}) {
+    long long h[148];
+    for (int pair = 0; pair < 2; ++pair) {
+      k_spline<<<148, warps * 32>>>(out, 500, cyc, pair); cudaDeviceSynchronize();
+      cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+      printf("warps/SM %2d: %s inverse spline: %.0f cycles per call\n", warps, pair ? "rqs8_inv_pair (2 lanes per row)" : "rqs_fast<8> (1 lane per row)    ", (double)h[0] / 500);
+    }
   }
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
