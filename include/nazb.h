@@ -27,6 +27,8 @@
  *                                compute_bic (max_s sum_n lp)                  src/naz/flows/bflow_jax_maf.py:474-475
  *   nazb_pack_draw_map           theta_0 * (1 + scale * standard_params)        src/naz/flows/bflow_jax_maf.py:239-240
  *   nazb_truncnorm_sample        TruncatedNormalTransform.__call__ / log_prob   src/naz/priors/TruncatedNormal.py:14-60
+ *   nazb_inverse_grad            jax.value_and_grad(log_prob) / autograd of    src/naz/flows/bflow_jax_maf.py:233-246,277-287,
+ *                                the summed log-likelihood (NUTS, SVI, MLE)    :321-327,:344-348; trainers/train_flows.py:195-213
  *   nazb_histogramdd             per-draw np.histogram2d / jnp.histogramdd     src/naz/flows/bflow_jax_maf.py:436-441
  *                                of the [S][N][D] sample tensor (density=True)
  *   nazb_hpd                     hpd_vectorized across draws                   src/naz/statutils.py:22-46
@@ -175,6 +177,23 @@ int nazb_pack_draw_map(nazb_handle* h, const float* const* W0, const float* cons
 int nazb_truncnorm_sample(const float* x, int32_t S, int64_t P, const float* loc, int32_t loc_n, const float* scale,
                           int32_t scale_n, const float* low, int32_t low_n, const float* high, int32_t high_n,
                           float* y, double* log_q, void* stream);
+
+/* SURVEY §8(f) f1 — value and gradient of the summed log-likelihood of draws [s_begin, s_begin + s_count):
+ *   sum_n[s] += sum_n log p(x_n | ctx_n; theta_s)   (device double [s_count], like nazb_inverse; may be NULL)
+ *   gW[i][s] += d sum_n / d W_i  (reference layout [out][in]; entries where mask_i == 0 are not touched)
+ *   gb[i][s] += d sum_n / d b_i
+ *   dx[s][n][:] = d lp[s][n] / d x_n  (device fp32 [s_count][N][D], in data space when lo / hi are given) or NULL
+ *   lp           device fp32 [s_count][N] or NULL.
+ * i runs over [flow layer][linear] exactly as in nazb_pack; mask / gW / gb are HOST tables of DEVICE pointers, gwst / gbst
+ * HOST arrays with the number of floats between consecutive draws of gW[i] / gb[i] (indexed by the GLOBAL draw s).  The
+ * gradient arrays are accumulated into (zero them first).  With nazb_pack_draw_map the gradient with respect to the standard
+ * parameters is scale * theta_0 * gW (chain rule on bflow_jax_maf.py:239-240; done by the caller).
+ * First cut of the row: NAZB_KIND_AFFINE flows on a handle created with NAZB_ENGINE_SIMT, no dropout keep-masks;
+ * anything else returns NAZB_ERR_UNSUPPORTED.  fp32 atomics: the sum over points is not bit-reproducible run to run. */
+int nazb_inverse_grad(nazb_handle* h, int32_t s_begin, int32_t s_count, const float* x, const float* ctx,
+                      int32_t ctx_rows, int32_t N, const float* lo, const float* hi, const float* const* mask,
+                      float* const* gW, float* const* gb, const int64_t* gwst, const int64_t* gbst, float* dx, float* lp,
+                      double* sum_n, void* stream);
 
 /* Stand-alone cross-draw reduction over a materialised lp[S][N] (kernel group 4):
  * partial (max, sum exp) per point over this rank's draws.  HBM-bound: 4*S*N bytes read. */

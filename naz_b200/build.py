@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnazb.so")
-SOURCES = ["nazb_api.cu", "flow_simt.cu", "pack_reduce.cu", "flow_tc.cu", "stats.cu"]
+SOURCES = ["nazb_api.cu", "flow_simt.cu", "pack_reduce.cu", "flow_tc.cu", "stats.cu", "flow_grad.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--threads", "4",

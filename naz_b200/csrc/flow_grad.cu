@@ -1,0 +1,392 @@
+// Gradient of the draw-batched log-likelihood  sum_n log p(x_n | c_n; theta_s)  with respect to every weight and bias of
+// draw s (and, optionally, to the points) for masked-affine autoregressive flows — SURVEY §8 row f1: the inner loop of
+// the reference's NUTS / SVI / MLE drivers, which call jax.grad / torch autograd on exactly this scalar
+// (src/naz/flows/bflow_jax_maf.py:233-246 log_prob -> :321-327 NUTS, :344-348 SVI, :277-287 MLE;
+//  src/naz/trainers/train_flows.py:195-213).
+//
+// fp32 CUDA-core engine (first cut of the row; same tiling as flow_simt.cu).  One CTA = one tile of P points of one draw:
+//   phase A  the incremental inverse of flow_simt.cu, keeping x^(l) (the conditioner input of every flow layer) in
+//            shared memory: L * D * P floats;
+//   phase B  flow layers in reverse evaluation order.  With x = x^(l) known, one conditioner pass gives h_j, mu, s.
+//            The layer is the implicit relation  x = (y - mu(x)) exp(-s(x)),  lp = G(x) - sum_d s_d(x), so with
+//            g = dG/dx the adjoint lambda solves  lambda = g + J^T c(lambda),
+//                 c_mu = -exp(-s) * lambda,   c_s = -(1 + x * lambda) * [lo <= s_raw <= hi],
+//            where J is the conditioner's Jacobian, strictly triangular in permutation order: D-1 fixed-point sweeps
+//            (each one back-propagation to the input) make every rank exact.  A last back-propagation with the final
+//            c accumulates  dW_j += h_{j-1} (x) delta_j,  db_j += delta_j  over the tile and adds them to the caller's
+//            gradient arrays (reference layout [out][in], masked entries untouched) with fp32 atomics;
+//            g <- lambda * exp(-s) is handed to the next layer.
+// Back-propagation to the input needs the weights transposed: a second image (rows = output units) is produced from
+// the SIMT image once per pack.
+#include <algorithm>
+#include "nazb_internal.h"
+#include "transforms.cuh"
+#include "simt_gemm.cuh"
+
+namespace {
+
+struct GradGeom {
+  long long offT[NAZB_MAX_LIN];   // float offset of W_j^T ([ldw_j rows][ldk_j]) inside one (draw, layer) block
+  int ldk[NAZB_MAX_LIN];          // kdim_j rounded up to 4
+  long long layer_strideT, draw_strideT;
+};
+
+struct GradArgs {
+  const float* const* mask;   // device table [L * n_lin] of device pointers, [out][in] 0/1
+  float* const* gW;           // ... gradient arrays, [S][out][in] (+=)
+  float* const* gb;           // ... [S][out] (+=)
+  const long long* gwst;      // floats between draws of gW[i]
+  const long long* gbst;
+  float* dx;                  // [s_count][N][D] or null
+};
+
+// dst[(draw, layer)][n][k] = src[(draw, layer)][k][n]
+__global__ void transpose_image_kernel(const float* __restrict__ src, float* __restrict__ dst, FlowGeom g, GradGeom gg,
+                                       int n_lin, long long blocks_dl) {
+  const long long per = gg.layer_strideT;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < blocks_dl * per;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long dl = i / per;
+    const long long f = i % per;
+    int j = 0;
+    while (j + 1 < n_lin && f >= gg.offT[j + 1]) ++j;
+    const long long e = f - gg.offT[j];
+    const int n = (int)(e / gg.ldk[j]), k = (int)(e % gg.ldk[j]);
+    float v = 0.f;
+    if (k < g.kdim[j] && n < g.ldw[j]) v = src[dl * g.layer_stride + g.off_w[j] + (long long)k * g.ldw[j] + n];
+    dst[dl * per + f] = v;
+  }
+}
+
+// gW[row(n)][k] += sum_p aT[k][p] * bT[n][p]  for unmasked (n, k);  gb[row(n)] += sum_p bT[n][p].
+// row(n) = n for hidden layers; the output layer's columns are rank-major (n = rank * M + m) while the reference's rows
+// are slot-major (m * D + dim)  (bflow_jax_maf.py:161-163 reshape [.., M, D]).
+template <int P>
+__device__ __forceinline__ void outer_acc(const float* __restrict__ aT, int K, const float* __restrict__ bT, int Nn,
+                                          const float* __restrict__ mask, float* __restrict__ gW,
+                                          float* __restrict__ gb, const int* __restrict__ perm, int M, int D,
+                                          bool out_layer) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int kt = (K + 3) >> 2, nt = (Nn + 3) >> 2;
+  for (int t = tid; t < kt * nt; t += kThreads) {
+    const int k0 = (t % kt) * 4, n0 = (t / kt) * 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 2
+    for (int pp = 0; pp < P / 4; ++pp) {
+      const int p = ((pp + lane) & (P / 4 - 1)) * 4;   // rotated per lane: conflict-free float4 reads
+      float4 a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(aT + (size_t)(k0 + i) * P + p);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float4*>(bT + (size_t)(n0 + j) * P + p);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          acc[i][j] = fmaf(a[i].x, b[j].x, fmaf(a[i].y, b[j].y, fmaf(a[i].z, b[j].z, fmaf(a[i].w, b[j].w, acc[i][j]))));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + j;
+      if (n >= Nn) continue;
+      const int row = out_layer ? ((n % M) * D + perm[n / M]) : n;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int k = k0 + i;
+        if (k < K && mask[(size_t)row * K + k] != 0.f) atomicAdd(gW + (size_t)row * K + k, acc[i][j]);
+      }
+    }
+  }
+  for (int n = tid; n < Nn; n += kThreads) {
+    float s = 0.f;
+    for (int pp = 0; pp < P; ++pp) s += bT[(size_t)n * P + ((pp + lane) & (P - 1))];
+    const int row = out_layer ? ((n % M) * D + perm[n / M]) : n;
+    atomicAdd(gb + row, s);
+  }
+}
+
+template <int P>
+__global__ void __launch_bounds__(kThreads) flow_grad_affine_kernel(FlowGeom g, GradGeom gg,
+                                                                     const float* __restrict__ packed,
+                                                                     const float* __restrict__ packedT,
+                                                                     const int* __restrict__ perm_all, IoArgs io,
+                                                                     GradArgs ga) {
+  using T = Tile<P>;
+  extern __shared__ __align__(16) float smem[];
+  const int D = g.D, C = g.C, nh = g.n_hidden, n_lin = nh + 1;
+  const int kin_pad = (g.kin + 3) & ~3, md_pad = (g.md + 3) & ~3;
+  float* xin = smem;                                   // [kin_pad][P]  rows: ctx (C), x (D)
+  float* gcur = xin + kin_pad * P;                     // [D][P]        phase A: y;  phase B: g = d lp / d x
+  float* hbuf = gcur + D * P;                          // [nh][hmax][P]
+  float* obuf = hbuf + (size_t)nh * g.hmax * P;        // [md_pad][P]   (mu, s_raw), rank-major
+  float* cbuf = obuf + (size_t)md_pad * P;             // [md_pad][P]   cotangent of the conditioner output
+  float* dA = cbuf + (size_t)md_pad * P;               // [hmax][P]     hidden cotangents (ping-pong)
+  float* dB = dA + (size_t)g.hmax * P;
+  float* dxb = dB + (size_t)g.hmax * P;                // [kin_pad][P]  cotangent of the conditioner input
+  float* chain = dxb + kin_pad * P;                    // [L][D][P]     x^(l)
+  float* lam = chain + (size_t)g.L * D * P;            // [D][P]
+  float* es = lam + D * P;                             // [D][P]  exp(-s), by rank
+  float* msk = es + D * P;                             // [D][P]  clip indicator, by rank
+  float* ldacc = msk + D * P;                          // [P]
+  float* ljac = ldacc + P;                             // [P]
+  float* zb = ljac + P;                                // [hmax]  zero bias of the transposed products
+  float* wbuf = zb + g.hmax;                           // [2][WCHUNK]
+  float* red = wbuf + 2 * T::WCHUNK;
+
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.x * P;
+  const int npts = min(P, io.N - n0);
+
+  for (int si = blockIdx.y; si < io.s_count; si += gridDim.y) {
+    const int sg = io.s_begin + si;
+    const float* wdraw = packed + (size_t)sg * g.draw_stride;
+    const float* wdrawT = packedT + (size_t)sg * gg.draw_strideT;
+    // ---- load tile ----
+    for (int i = tid; i < kin_pad * P; i += kThreads) xin[i] = 0.f;
+    for (int i = tid; i < g.hmax; i += kThreads) zb[i] = 0.f;
+    if (tid < P) { ldacc[tid] = 0.f; ljac[tid] = 0.f; }
+    __syncthreads();
+    for (int i = tid; i < npts * C; i += kThreads) {
+      int p = i / C, c = i % C;
+      size_t row = (io.ctx_rows == 1) ? 0 : (size_t)(n0 + p);
+      xin[c * P + p] = io.ctx[row * C + c];
+    }
+    for (int i = tid; i < P * D; i += kThreads) {
+      int p = i / D, d = i % D;
+      gcur[d * P + p] = (p < npts) ? io.x[(size_t)(n0 + p) * D + d] : 0.f;
+    }
+    __syncthreads();
+    if (io.lo != nullptr && tid < npts) {
+      float lj = 0.f;
+      for (int d = 0; d < D; ++d) gcur[d * P + tid] = nazb::bound_fwd(gcur[d * P + tid], io.lo[d], io.hi[d], lj);
+      ljac[tid] = lj;
+    }
+    __syncthreads();
+
+    // ================= phase A: inverse (log_prob direction), keeping x^(l) =================
+    for (int li = 0; li < g.L; ++li) {
+      const int l = g.L - 1 - li;
+      const float* wl = wdraw + (size_t)l * g.layer_stride;
+      const int* perm = perm_all + l * D;
+      const bool full = g.inv_mode == NAZB_INV_JACOBI;
+      for (int r = 0; r < D; ++r) {
+        for (int j = 0; j < nh; ++j) {
+          int c0 = full ? 0 : g.blk[j][r], c1 = full ? g.hidden[j] : g.blk[j][r + 1];
+          int K = (j == 0) ? g.kin : (full ? g.hidden[j - 1] : g.blk[j - 1][r + 1]);
+          const float* act = (j == 0) ? xin : hbuf + (size_t)(j - 1) * g.hmax * P;
+          if (c1 > c0)
+            gemm_panel<P, true>(act, K, wl + g.off_w[j], g.ldw[j], wl + g.off_b[j], c0, c1, hbuf + (size_t)j * g.hmax * P, wbuf);
+        }
+        {
+          int K = full ? g.hidden[nh - 1] : g.blk[nh - 1][r + 1];
+          gemm_panel<P, false>(hbuf + (size_t)(nh - 1) * g.hmax * P, K, wl + g.off_w[nh], g.ldw[nh], wl + g.off_b[nh],
+                               r * 2, (r + 1) * 2, obuf, wbuf);
+        }
+        if (tid < P) {
+          const int p = tid, d = perm[r];
+          float mu = obuf[(r * 2 + 0) * P + p];
+          float s = fminf(fmaxf(obuf[(r * 2 + 1) * P + p], g.clip_lo), g.clip_hi);
+          xin[(C + d) * P + p] = (gcur[d * P + p] - mu) * expf(-s);
+          ldacc[p] += s;
+        }
+        __syncthreads();
+      }
+      for (int i = tid; i < P * D; i += kThreads) {
+        int p = i % P, d = i / P;
+        float xv = xin[(C + d) * P + p];
+        chain[((size_t)l * D + d) * P + p] = xv;
+        gcur[d * P + p] = xv;
+        xin[(C + d) * P + p] = 0.f;
+      }
+      __syncthreads();
+    }
+    // ---- value: sum_n lp;  g = d lp / d z = -z ----
+    {
+      float lp = 0.f;
+      if (tid < P) {
+        float q = 0.f;
+        for (int d = 0; d < D; ++d) { float z = gcur[d * P + tid]; q += 0.5f * z * z; }
+        lp = -q - 0.5f * D * NAZB_LOG_2PI - ldacc[tid] + ljac[tid];
+        if (tid < npts && io.out_l) io.out_l[(size_t)si * io.N + n0 + tid] = lp;
+      }
+      if (io.sum_n) {
+        double v = (tid < npts) ? (double)lp : 0.0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        double* redd = reinterpret_cast<double*>(red);
+        if ((tid & 31) == 0) redd[tid >> 5] = v;
+        __syncthreads();
+        if (tid == 0) {
+          double t = 0.0;
+          for (int w = 0; w < kThreads / 32; ++w) t += redd[w];
+          atomicAdd(io.sum_n + si, t);
+        }
+      }
+      __syncthreads();
+      for (int i = tid; i < P * D; i += kThreads) {
+        int p = i % P;
+        gcur[i] = (p < npts) ? -gcur[i] : 0.f;
+      }
+      __syncthreads();
+    }
+
+    // ================= phase B: adjoint, flow layers in reverse evaluation order =================
+    for (int l = 0; l < g.L; ++l) {
+      const float* wl = wdraw + (size_t)l * g.layer_stride;
+      const float* wlT = wdrawT + (size_t)l * gg.layer_strideT;
+      const int* perm = perm_all + l * D;
+      for (int i = tid; i < P * D; i += kThreads) {
+        int p = i % P, d = i / P;
+        xin[(C + d) * P + p] = chain[((size_t)l * D + d) * P + p];
+      }
+      __syncthreads();
+      // conditioner at the solved x
+      for (int j = 0; j < nh; ++j)
+        gemm_panel<P, true>((j == 0) ? xin : hbuf + (size_t)(j - 1) * g.hmax * P, g.kdim[j], wl + g.off_w[j], g.ldw[j],
+                            wl + g.off_b[j], 0, g.hidden[j], hbuf + (size_t)j * g.hmax * P, wbuf);
+      gemm_panel<P, false>(hbuf + (size_t)(nh - 1) * g.hmax * P, g.kdim[nh], wl + g.off_w[nh], g.ldw[nh],
+                           wl + g.off_b[nh], 0, g.md, obuf, wbuf);
+      for (int i = tid; i < P * D; i += kThreads) {
+        int p = i % P, r = i / P;
+        float sraw = obuf[(r * 2 + 1) * P + p];
+        float s = fminf(fmaxf(sraw, g.clip_lo), g.clip_hi);
+        es[r * P + p] = expf(-s);
+        msk[r * P + p] = (sraw >= g.clip_lo && sraw <= g.clip_hi) ? 1.f : 0.f;
+        lam[i] = gcur[i];
+      }
+      __syncthreads();
+      for (int it = 0; it < D; ++it) {
+        const bool last = (it == D - 1);
+        for (int i = tid; i < P * D; i += kThreads) {
+          int p = i % P, r = i / P;
+          int d = perm[r];
+          float lm = lam[d * P + p];
+          bool valid = p < npts;
+          cbuf[(r * 2 + 0) * P + p] = valid ? -es[r * P + p] * lm : 0.f;
+          cbuf[(r * 2 + 1) * P + p] = valid ? -(1.f + xin[(C + d) * P + p] * lm) * msk[r * P + p] : 0.f;
+        }
+        __syncthreads();
+        const int to = l * n_lin + nh;
+        if (last)
+          outer_acc<P>(hbuf + (size_t)(nh - 1) * g.hmax * P, g.kdim[nh], cbuf, g.md, ga.mask[to],
+                       ga.gW[to] + (size_t)sg * ga.gwst[to], ga.gb[to] + (size_t)sg * ga.gbst[to], perm, 2, D, true);
+        const float* src = cbuf;
+        for (int j = nh; j >= 1; --j) {
+          float* dst = ((nh - j) & 1) ? dB : dA;
+          // delta_{j-1}[k][p] = (sum_n W_j[n][k] delta_j[n][p]) * (1 - h_{j-1}[k][p]^2)
+          gemm_panel<P, false>(src, g.ndim[j], wlT + gg.offT[j], gg.ldk[j], zb, 0, g.kdim[j], dst, wbuf);
+          const float* hj = hbuf + (size_t)(j - 1) * g.hmax * P;
+          for (int i = tid; i < g.kdim[j] * P; i += kThreads) { float hv = hj[i]; dst[i] *= (1.f - hv * hv); }
+          __syncthreads();
+          if (last) {
+            const int ti = l * n_lin + (j - 1);
+            outer_acc<P>((j - 1 == 0) ? xin : hbuf + (size_t)(j - 2) * g.hmax * P, g.kdim[j - 1], dst, g.ndim[j - 1],
+                         ga.mask[ti], ga.gW[ti] + (size_t)sg * ga.gwst[ti], ga.gb[ti] + (size_t)sg * ga.gbst[ti], perm, 2, D,
+                         false);
+          }
+          src = dst;
+        }
+        if (!last) {
+          gemm_panel<P, false>(src, g.ndim[0], wlT + gg.offT[0], gg.ldk[0], zb, 0, g.kin, dxb, wbuf);
+          for (int i = tid; i < P * D; i += kThreads) {
+            int p = i % P, d = i / P;
+            lam[i] = gcur[i] + dxb[(C + d) * P + p];
+          }
+        }
+        __syncthreads();
+      }
+      // g of the next layer: d lp / d y = lambda * exp(-s)
+      for (int i = tid; i < P * D; i += kThreads) {
+        int p = i % P, r = i / P;
+        int d = perm[r];
+        gcur[d * P + p] = lam[d * P + p] * es[r * P + p];
+      }
+      __syncthreads();
+    }
+    if (ga.dx) {
+      float* dst = ga.dx + ((size_t)si * io.N + n0) * D;
+      for (int i = tid; i < npts * D; i += kThreads) {
+        int p = i / D, d = i % D;
+        float v = gcur[d * P + p];
+        if (io.lo != nullptr) {
+          // y = logit(u), u = (x - lo) / (hi - lo);  lp also carries -log u - log(1 - u) - log(hi - lo)
+          float w = io.hi[d] - io.lo[d];
+          float u = (io.x[(size_t)(n0 + p) * D + d] - io.lo[d]) / w;
+          v = v / (w * u * (1.f - u)) - (1.f / u - 1.f / (1.f - u)) / w;
+        }
+        dst[i] = v;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+size_t grad_smem_bytes(const FlowGeom& g, int P) {
+  const int kin_pad = (g.kin + 3) & ~3, md_pad = (g.md + 3) & ~3;
+  size_t f = (size_t)2 * kin_pad * P + (size_t)4 * g.D * P + (size_t)(g.n_hidden + 2) * g.hmax * P +
+             (size_t)2 * md_pad * P + (size_t)g.L * g.D * P + 2 * P + g.hmax;
+  int TR = P / 4, TC = kThreads / TR, NPASS = TC * 4;
+  f += 2 * (size_t)kKC * NPASS;
+  f += 2 * (kThreads / 32) + 4;
+  return f * sizeof(float) + 16;
+}
+
+GradGeom make_grad_geom(const FlowGeom& g) {
+  GradGeom gg{};
+  long long off = 0;
+  for (int j = 0; j <= g.n_hidden; ++j) {
+    gg.ldk[j] = (g.kdim[j] + 3) & ~3;
+    gg.offT[j] = off;
+    off += (long long)g.ldw[j] * gg.ldk[j];
+  }
+  gg.layer_strideT = off;
+  gg.draw_strideT = off * g.L;
+  return gg;
+}
+
+}  // namespace
+
+// Gradient launcher.  `tabs` = device memory holding the five tables (mask, gW, gb pointers; gW, gb draw strides).
+cudaError_t nazb_grad_launch(nazb_handle* h, const IoArgs& io, const void* tabs, float* dx, cudaStream_t st) {
+  const FlowGeom& g = h->geom;
+  const GradGeom gg = make_grad_geom(g);
+  const int n = g.L * (g.n_hidden + 1);
+  cudaError_t e;
+  if (!h->packed_T) {
+    e = cudaMalloc(&h->packed_T, sizeof(float) * (size_t)h->desc.S * gg.draw_strideT);
+    if (e != cudaSuccess) return e;
+    h->packed_T_valid = false;
+  }
+  if (!h->packed_T_valid) {
+    const long long blocks_dl = (long long)h->desc.S * g.L;
+    const long long total = blocks_dl * gg.layer_strideT;
+    int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
+    transpose_image_kernel<<<blocks, 256, 0, st>>>(h->packed, h->packed_T, g, gg, g.n_hidden + 1, blocks_dl);
+    nazb_count_launch();
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    h->packed_T_valid = true;
+  }
+  constexpr int P = 32;
+  const size_t smem = grad_smem_bytes(g, P);
+  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+  GradArgs ga{};
+  const char* t = static_cast<const char*>(tabs);
+  ga.mask = reinterpret_cast<const float* const*>(t);
+  ga.gW = reinterpret_cast<float* const*>(t + sizeof(void*) * n);
+  ga.gb = reinterpret_cast<float* const*>(t + sizeof(void*) * 2 * n);
+  ga.gwst = reinterpret_cast<const long long*>(t + sizeof(void*) * 3 * n);
+  ga.gbst = reinterpret_cast<const long long*>(t + sizeof(void*) * 4 * n);
+  ga.dx = dx;
+  e = cudaFuncSetAttribute(flow_grad_affine_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int tiles = (io.N + P - 1) / P;
+  dim3 grid(tiles, std::min(io.s_count, 65535));
+  flow_grad_affine_kernel<P><<<grid, kThreads, smem, st>>>(g, gg, h->packed, h->packed_T, h->perm_dev, io, ga);
+  nazb_count_launch();
+  return cudaGetLastError();
+}
+
+bool nazb_grad_fits(const FlowGeom& g) { return grad_smem_bytes(g, 32) <= 227 * 1024; }

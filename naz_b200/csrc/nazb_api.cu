@@ -124,6 +124,8 @@ extern "C" void nazb_destroy(nazb_handle* h) {
   cudaSetDevice(h->device);
   if (h->tc) nazb_tc_destroy(h);
   if (h->packed) cudaFree(h->packed);
+  if (h->packed_T) cudaFree(h->packed_T);
+  if (h->grad_tabs) cudaFree(h->grad_tabs);
   if (h->perm_dev) cudaFree(h->perm_dev);
   delete h;
 }
@@ -207,6 +209,8 @@ static int pack_impl(nazb_handle* h, const float* const* W, const float* const* 
     CK(h, e);
   }
   h->is_packed = true;
+  h->has_keep = (keep != nullptr);
+  h->packed_T_valid = false;
   return NAZB_OK;
 }
 
@@ -318,5 +322,42 @@ extern "C" int nazb_forward(nazb_handle* h, int32_t s_begin, int32_t s_count, co
                       ? nazb_tc_launch(h, io, G, (cudaStream_t)stream)
                       : nazb_simt_launch(h, io, G, (cudaStream_t)stream);
   CK(h, e);
+  return NAZB_OK;
+}
+
+// value and gradient of the draw-batched log-likelihood (what the reference obtains from jax.grad /
+// autograd of bflow_jax_maf.py:233-235 `log_prob`).  Gradients are ADDED to the caller's arrays.
+extern "C" int nazb_inverse_grad(nazb_handle* h, int32_t s_begin, int32_t s_count, const float* x, const float* ctx,
+                                 int32_t ctx_rows, int32_t N, const float* lo, const float* hi,
+                                 const float* const* mask, float* const* gW, float* const* gb, const int64_t* gwst,
+                                 const int64_t* gbst, float* dx, float* lp, double* sum_n, void* stream) {
+  int rc = check_io(h, s_begin, s_count, x, ctx, ctx_rows, N, lo, hi);
+  if (rc != NAZB_OK) return rc;
+  if (!mask || !gW || !gb || !gwst || !gbst) return NAZB_ERR_BAD_ARG;
+  const FlowGeom& g = h->geom;
+  // first cut of the row: masked-affine flows on the fp32 engine's image, no dropout
+  if (g.kind != NAZB_KIND_AFFINE || h->engine != NAZB_ENGINE_SIMT || !h->packed || h->has_keep || !nazb_grad_fits(g))
+    return NAZB_ERR_UNSUPPORTED;
+  const int n = g.L * (g.n_hidden + 1);
+  for (int i = 0; i < n; ++i)
+    if (!mask[i] || !gW[i] || !gb[i] || gwst[i] < 0 || gbst[i] < 0) return NAZB_ERR_BAD_ARG;
+  CK(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!h->grad_tabs) CK(h, cudaMalloc(&h->grad_tabs, sizeof(void*) * 5 * (size_t)n));
+  std::vector<unsigned long long> tabs(5 * (size_t)n);
+  for (int i = 0; i < n; ++i) {
+    tabs[i] = (unsigned long long)(uintptr_t)mask[i];
+    tabs[n + i] = (unsigned long long)(uintptr_t)gW[i];
+    tabs[2 * n + i] = (unsigned long long)(uintptr_t)gb[i];
+    tabs[3 * n + i] = (unsigned long long)gwst[i];
+    tabs[4 * n + i] = (unsigned long long)gbst[i];
+  }
+  // pageable source: the runtime stages the bytes before returning, so the vector may die with this frame
+  CK(h, cudaMemcpyAsync(h->grad_tabs, tabs.data(), tabs.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+  IoArgs io{};
+  io.x = x; io.x_draw_stride = 0; io.ctx = ctx; io.ctx_rows = ctx_rows; io.N = N;
+  io.s_begin = s_begin; io.s_count = s_count; io.lo = lo; io.hi = hi;
+  io.out_l = lp; io.sum_n = sum_n; io.dir = 0;
+  CK(h, nazb_grad_launch(h, io, h->grad_tabs, dx, st));
   return NAZB_OK;
 }

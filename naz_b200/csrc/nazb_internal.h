@@ -70,6 +70,11 @@ struct nazb_handle {
   float* packed = nullptr;  // SIMT image
   int* perm_dev = nullptr;  // [L][D] int32
   bool is_packed = false;
+  bool has_keep = false;    // dropout keep-masks were folded in at pack time
+  // gradient engine (flow_grad.cu): transposed copy of the SIMT image, device tables of the caller's gradient arrays
+  float* packed_T = nullptr;
+  bool packed_T_valid = false;
+  void* grad_tabs = nullptr;
   std::string cuda_err;
   // tcgen05 engine state (opaque here; defined in flow_tc.cu)
   void* tc = nullptr;
@@ -93,5 +98,9 @@ cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* con
                          const float* keep, float p_drop, cudaStream_t st, const DrawMap& dm = DrawMap());
 cudaError_t nazb_tc_launch(const nazb_handle* h, const IoArgs& io, int n_groups, cudaStream_t st);
 int64_t nazb_tc_packed_bytes(const nazb_handle* h);
+
+// gradient of sum_n lp (masked-affine flows, SIMT image)
+cudaError_t nazb_grad_launch(nazb_handle* h, const IoArgs& io, const void* tabs, float* dx, cudaStream_t st);
+bool nazb_grad_fits(const FlowGeom& g);
 
 void nazb_count_launch(int n = 1);

@@ -340,6 +340,53 @@ class FlowEngine:
         return (x, ld) if want_logdet else x
 
     # ------------------------------------------------------------------
+    def inverse_grad(self, x, ctx=None, bounds=None, *, want_dx: bool = False, want_lp: bool = False,
+                     s_begin: int = 0, s_count: Optional[int] = None):
+        """Value and gradient of sum_n log p(x_n | ctx_n; theta_s) per draw (what the reference gets from
+        jax.value_and_grad / autograd of bflow_jax_maf.py:233-235).  Returns {"sum_n": [s_count] float64,
+        "gW": [L][n_lin] of [S,out,in], "gb": [L][n_lin] of [S,out], "dx": [s_count,N,D], "lp": [s_count,N]};
+        rows of gW / gb outside [s_begin, s_begin+s_count) stay zero.  Needs a handle created with engine="simt"
+        holding a masked-affine flow (nazb_inverse_grad returns "unsupported" otherwise)."""
+        sh = self.shape
+        if self._keepalive is None:
+            raise RuntimeError("inverse_grad: pack() has not been called on this engine")
+        s_count = self.S - s_begin if s_count is None else s_count
+        x, c, rows, lo, hi = self._prep_points(x, ctx, bounds)
+        if x.dim() != 2 or x.shape[1] != sh.D:
+            raise ValueError(f"x must be [N,{sh.D}]")
+        N = x.shape[0]
+        if N == 0:
+            raise ValueError("empty batch")
+        L, n_lin = sh.L, len(sh.hidden) + 1
+        dims = [sh.D + sh.C] + list(sh.hidden) + [sh.M * sh.D]
+        masks = self._keepalive[2]
+        gW = [torch.zeros((self.S, dims[j + 1], dims[j]), device=self.device, dtype=torch.float32)
+              for _ in range(L) for j in range(n_lin)]
+        gb = [torch.zeros((self.S, dims[j + 1]), device=self.device, dtype=torch.float32)
+              for _ in range(L) for j in range(n_lin)]
+        n = L * n_lin
+        VP = C.c_void_p * n
+        I64 = C.c_int64 * n
+        sum_n = torch.zeros((s_count,), device=self.device, dtype=torch.float64)
+        dx = torch.empty((s_count, N, sh.D), device=self.device, dtype=torch.float32) if want_dx else None
+        lp = torch.empty((s_count, N), device=self.device, dtype=torch.float32) if want_lp else None
+        rc = self._lib.nazb_inverse_grad(self._h, s_begin, s_count, x.data_ptr(), _ptr(c), rows, N, _ptr(lo), _ptr(hi),
+                                         VP(*[m.data_ptr() for m in masks]), VP(*[t.data_ptr() for t in gW]),
+                                         VP(*[t.data_ptr() for t in gb]),
+                                         I64(*[dims[i % n_lin + 1] * dims[i % n_lin] for i in range(n)]),
+                                         I64(*[dims[i % n_lin + 1] for i in range(n)]), _ptr(dx), _ptr(lp),
+                                         sum_n.data_ptr(), self._stream())
+        self._check(rc, "nazb_inverse_grad")
+        out = {"sum_n": sum_n,
+               "gW": [[gW[l * n_lin + j] for j in range(n_lin)] for l in range(L)],
+               "gb": [[gb[l * n_lin + j] for j in range(n_lin)] for l in range(L)]}
+        if want_dx:
+            out["dx"] = dx
+        if want_lp:
+            out["lp"] = lp
+        return out
+
+    # ------------------------------------------------------------------
     def lse_finish(self, lse_max: torch.Tensor, lse_sum: torch.Tensor, log_norm: float) -> torch.Tensor:
         G, N = lse_max.shape
         out = torch.empty((N,), device=self.device, dtype=torch.float32)

@@ -121,7 +121,34 @@ def make_normalizing_flow(transform, x, masks, mask_skips, perms, bounds=None, c
         assert ctx is None or ctx.dim() == 1
         return eng.forward(z, ctx)
 
-    return {"lp": log_prob, "sampler": sample, "lp_standard": log_prob_standard, "sampler_standard": sample_standard}
+    gcache = {}
+
+    def value_and_grad(params, mean: bool = False):
+        """(sum_n lp(params), d/d params) — what the reference's drivers obtain from jax.value_and_grad of
+        `log_prob(theta) = jnp.sum(lp(unravel(theta)))` (or jnp.mean) (bflow_jax_maf.py:233-235; NUTS :321-327, SVI :344-348,
+        MLE :277-287).  params: one draw `[L][n_lin](W[out,in], b[out])` or a batch `W[S,out,in]` (one gradient per draw /
+        chain).  Returns (value [S] float64 or a 0-d tensor, grads with the structure and shapes of params)."""
+        W0 = params[0][0][0]
+        single = W0.dim() == 2
+        S = 1 if single else W0.shape[0]
+        if gcache.get("eng") is None or gcache["eng"].S != S:
+            gcache["eng"] = FlowEngine(shape, S, device=dev, engine="simt")
+        eng = gcache["eng"]
+        eng.pack(params, masks, torch.stack([torch.as_tensor(p) for p in perms]))
+        r = eng.inverse_grad(x_dev, ctx, None if bnd is None else {"low": bnd[0], "high": bnd[1]})
+        val = r["sum_n"]
+        if bnd is not None:   # the twin's sign convention for the bounding log-Jacobian (see log_prob); parameter-free
+            u = (x_dev - lo) / (hi - lo)
+            log_jac = -(torch.log(u) + torch.log1p(-u)).sum(-1) - torch.log(hi - lo).sum()
+            val = val - 2.0 * log_jac.double().sum()
+        sc = 1.0 / x_dev.shape[0] if mean else 1.0
+        grads = [[((gw[0] if single else gw) * sc, (gb[0] if single else gb) * sc) for gw, gb in zip(lw, lb)]
+                 for lw, lb in zip(r["gW"], r["gb"])]
+        val = val * sc
+        return (val[0] if single else val), grads
+
+    return {"lp": log_prob, "sampler": sample, "lp_standard": log_prob_standard, "sampler_standard": sample_standard,
+            "value_and_grad": value_and_grad}
 
 
 def draw_params(best_params, standard_params: torch.Tensor, scale: float):

@@ -1,0 +1,160 @@
+"""value and gradient of the summed log-likelihood (masked-affine flows).
+CPU: the gradient oracle (torch autograd of the restated twin) is pinned on the forward side by the reference-executed
+fixtures and checked against finite differences.  GPU: nazb_inverse_grad against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import flow_oracle as fo
+from oracle import grad_oracle as go
+from helpers import make_case, load_ref_twin, REF_TWIN, to64
+
+
+def _single(draws, s):
+    return [[(W[s], b[s]) for (W, b) in layer] for layer in draws]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", REF_TWIN)
+def test_grad_oracle_forward_matches_reference_outputs(name):
+    """the differentiated function IS the reference's log_prob: its values equal the reference-executed fixtures"""
+    spec, params, g = load_ref_twin(name)
+    masks = [[g[f"mask_{l}_{j}"] for j in range(len(spec.hidden) + 1)] for l in range(spec.L)]
+    ctx = g["ctx"] if spec.C else None
+    _, _, _, _, lp = go.value_and_grad(to64([[(W, b) for (W, b) in layer] for layer in params]), masks, spec.perms, g["x"], ctx)
+    np.testing.assert_allclose(lp, g["lp"], rtol=1e-9, atol=1e-9)
+
+
+def test_grad_oracle_matches_flow_oracle_and_finite_differences():
+    spec, draws, _, rng = make_case("maf", 3, 2, [12, 12], 2, 1, seed=5)
+    p = to64(_single(draws, 0))
+    masks = spec.masks()
+    x = rng.normal(size=(7, 3))
+    ctx = rng.uniform(size=(7, 2))
+    bounds = (np.full(3, -6.0), np.full(3, 6.0))
+    val, gW, gb, dx, lp = go.value_and_grad(p, masks, spec.perms, x, ctx, bounds, want_dx=True)
+    ref = fo.log_prob_draws(spec, [[(W[None], b[None]) for (W, b) in layer] for layer in p], x, ctx, bounds)[0][0]
+    np.testing.assert_allclose(lp, ref, rtol=1e-10, atol=1e-10)
+
+    def f(pp, xx=x):
+        return fo.log_prob_draws(spec, [[(W[None], b[None]) for (W, b) in layer] for layer in pp], xx, ctx, bounds)[0][0].sum()
+
+    eps = 1e-6
+    for (l, j, idx) in [(0, 0, (3, 2)), (1, 1, (5, 4)), (0, 2, (1, 7)), (1, 2, (4, 0))]:
+        if masks[l][j][idx] == 0:
+            assert gW[l][j][idx] == 0.0
+            continue
+        pp = [[(W.copy(), b.copy()) for (W, b) in layer] for layer in p]
+        pp[l][j][0][idx] += eps
+        up = f(pp)
+        pp[l][j][0][idx] -= 2 * eps
+        dn = f(pp)
+        assert abs((up - dn) / (2 * eps) - gW[l][j][idx]) < 1e-5 * max(1.0, abs(gW[l][j][idx]))
+    pp = [[(W.copy(), b.copy()) for (W, b) in layer] for layer in p]
+    pp[1][0][1][3] += eps
+    up = f(pp)
+    pp[1][0][1][3] -= 2 * eps
+    dn = f(pp)
+    assert abs((up - dn) / (2 * eps) - gb[1][0][3]) < 1e-5 * max(1.0, abs(gb[1][0][3]))
+    xp = x.copy(); xp[2, 1] += eps
+    xm = x.copy(); xm[2, 1] -= eps
+    assert abs((f(p, xp) - f(p, xm)) / (2 * eps) - dx[2, 1]) < 1e-5 * max(1.0, abs(dx[2, 1]))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GPU
+# ----------------------------------------------------------------------------------------------------------------
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(1e-12, np.abs(b).max()))
+
+
+GRAD_CASES = [
+    # kind D C hidden L S N bounds ctx_rows
+    (2, 0, [16, 16], 3, 2, 37, False, 0),
+    (3, 2, [24, 24], 4, 3, 100, True, "N"),
+    (6, 4, [150, 150, 150], 2, 2, 70, False, "N"),
+    (4, 2, [150, 150, 150], 3, 1, 33, False, 1),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", GRAD_CASES)
+def test_inverse_grad_matches_autograd_oracle(case):
+    from helpers import engine_for
+    D, C, hidden, L, S, N, bounded, crow = case
+    spec, draws, _, rng = make_case("maf", D, C, hidden, L, S, seed=11)
+    x = (rng.normal(size=(N, D)) * 1.2).astype(np.float32)
+    ctx = None
+    if C:
+        ctx = rng.uniform(size=(N if crow == "N" else 1, C)).astype(np.float32)
+    bounds = (np.full(D, -7.0, np.float32), np.full(D, 7.0, np.float32)) if bounded else None
+    eng = engine_for(spec, draws, engine="simt")
+    r = eng.inverse_grad(torch.from_numpy(x), None if ctx is None else torch.from_numpy(ctx),
+                         None if bounds is None else (torch.from_numpy(bounds[0]), torch.from_numpy(bounds[1])),
+                         want_dx=True, want_lp=True)
+    torch.cuda.synchronize()
+    masks = spec.masks()
+    for s in range(S):
+        p = to64(_single(draws, s))
+        c64 = None if ctx is None else (ctx[0] if ctx.shape[0] == 1 else ctx).astype(np.float64)
+        b64 = None if bounds is None else tuple(b.astype(np.float64) for b in bounds)
+        val, gW, gb, dx, lp = go.value_and_grad(p, masks, spec.perms, x.astype(np.float64), c64, b64, want_dx=True)
+        np.testing.assert_allclose(r["lp"][s].cpu().numpy(), lp, rtol=1e-4, atol=1e-4)
+        assert abs(float(r["sum_n"][s]) - val) <= 1e-4 * max(1.0, abs(val))
+        # tolerance: relative to the largest entry of each gradient array (fp32 products and fp32 atomic sums over N)
+        for l in range(L):
+            for j in range(len(hidden) + 1):
+                assert _rel(r["gW"][l][j][s].cpu().numpy(), gW[l][j]) < 2e-4, (s, l, j, "W")
+                assert _rel(r["gb"][l][j][s].cpu().numpy(), gb[l][j]) < 2e-4, (s, l, j, "b")
+                # masked entries are never touched
+                assert np.all(r["gW"][l][j][s].cpu().numpy()[masks[l][j] == 0] == 0.0)
+        assert _rel(r["dx"][s].cpu().numpy(), dx) < 2e-4
+
+
+@pytest.mark.gpu
+def test_inverse_grad_draw_range_and_unsupported():
+    from helpers import engine_for
+    from naz_b200 import _lib
+    spec, draws, _, rng = make_case("maf", 3, 1, [16, 16], 2, 4, seed=3)
+    x = torch.from_numpy(rng.normal(size=(50, 3)).astype(np.float32))
+    ctx = torch.from_numpy(rng.uniform(size=(1, 1)).astype(np.float32))
+    eng = engine_for(spec, draws, engine="simt")
+    full = eng.inverse_grad(x, ctx)
+    part = eng.inverse_grad(x, ctx, s_begin=1, s_count=2)
+    torch.cuda.synchronize()
+    assert torch.allclose(part["sum_n"], full["sum_n"][1:3], rtol=1e-6)
+    g_f, g_p = full["gW"][0][1], part["gW"][0][1]
+    assert torch.all(g_p[0] == 0) and torch.all(g_p[3] == 0)
+    assert _rel(g_p[1:3].cpu().numpy(), g_f[1:3].cpu().numpy()) < 1e-4
+    # the value agrees with the log_prob entry point
+    lp = eng.inverse(x, ctx, want_lp=True)["lp"].double().sum(-1)
+    assert torch.allclose(lp, full["sum_n"], rtol=1e-5)
+    # splines and tensor-core handles are not served by the first cut: loud error, no fallback
+    spec2, draws2, _, _ = make_case("nsa", 3, 1, [16, 16], 2, 2, seed=3)
+    eng2 = engine_for(spec2, draws2, engine="simt")
+    with pytest.raises(_lib.NazbError):
+        eng2.inverse_grad(x, ctx)
+
+
+@pytest.mark.gpu
+def test_twin_value_and_grad_single_draw_against_reference_fixture():
+    """make_normalizing_flow(...)["value_and_grad"] on a reference-executed fixture: value = sum of the reference's own lp"""
+    from naz_b200.flows import bflow_maf as bm
+    spec, params, g = load_ref_twin("ref_twin_maf_cond_3d")
+    masks = [[torch.from_numpy(g[f"mask_{l}_{j}"]) for j in range(len(spec.hidden) + 1)] for l in range(spec.L)]
+    tparams = [[(torch.from_numpy(W), torch.from_numpy(b)) for (W, b) in layer] for layer in params]
+    nn = bm.make_conditional_autoregressive_nn(spec.D, spec.C, spec.hidden)
+    flow = bm.make_normalizing_flow(nn, torch.from_numpy(g["x"]), masks, None, [torch.from_numpy(p) for p in spec.perms],
+                                    context=torch.from_numpy(g["ctx"]))
+    val, grads = flow["value_and_grad"](tparams)
+    torch.cuda.synchronize()
+    assert abs(float(val) - float(g["lp"].astype(np.float64).sum())) < 1e-4 * max(1.0, abs(float(g["lp"].sum())))
+    m64 = [[g[f"mask_{l}_{j}"] for j in range(len(spec.hidden) + 1)] for l in range(spec.L)]
+    _, gW, gb, _, _ = go.value_and_grad(to64(params), m64, spec.perms, g["x"], g["ctx"])
+    for l in range(spec.L):
+        for j in range(len(spec.hidden) + 1):
+            assert _rel(grads[l][j][0].cpu().numpy(), gW[l][j]) < 2e-4
+            assert _rel(grads[l][j][1].cpu().numpy(), gb[l][j]) < 2e-4
