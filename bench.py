@@ -308,6 +308,32 @@ def main_ours(args):
     fwd_ms = f0.elapsed_time(f1e)
     del xs
 
+    # auxiliary: SURVEY §8 f1 — value + gradient of sum_n lp (the NUTS / SVI inner loop), config-4 architecture (maf 2|2),
+    # 4 chains x 100 000 points; 1 grad-eval = one (chain, point) pair through the value and the full parameter gradient
+    aux_grad = None
+    if world == 1:
+        torch.manual_seed(3)
+        gflow = NormalizingFlow("maf", None, 2, 2, [150, 150, 150], 16, engine="simt").to(dev)
+        gdraws = [[(lin.weight.detach().unsqueeze(0) * (1 + 0.25 * (torch.rand((4,) + tuple(lin.weight.shape), device=dev, generator=gen) * 2 - 1)),
+                    lin.bias.detach().unsqueeze(0) * (1 + 0.25 * (torch.rand((4,) + tuple(lin.bias.shape), device=dev, generator=gen) * 2 - 1)))
+                   for lin in arn.layers] for arn in gflow.nets]
+        geng = gflow.make_engine(gdraws, device=dev)
+        gx = torch.randn((100_000, 2), device=dev, generator=gen) * 1.5
+        gc = torch.rand((100_000, 2), device=dev, generator=gen)
+        geng.inverse_grad(gx, gc)
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        gr = geng.inverse_grad(gx, gc)
+        g1.record()
+        torch.cuda.synchronize()
+        g_ms = g0.elapsed_time(g1)
+        aux_grad = {"value": 4 * 100_000 / (g_ms * 1e-3), "unit": "grad-evals/s", "chains": 4, "points": 100_000, "ms": g_ms,
+                    "flow": "maf 2|2 [150,150,150] x16", "engine": "simt (fp32 CUDA cores)",
+                    "finite": bool(torch.isfinite(gr["sum_n"]).all().item()),
+                    "note": "nazb_inverse_grad: value + d/d(all weights) of sum_n lp per chain (first cut of row f1; not part of `value`)"}
+        del geng, gr, gdraws
+
     tms = torch.tensor([total_ms, e2e_s * 1e3, k_ms, fwd_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -356,6 +382,8 @@ def main_ours(args):
                                      "engine": eng.engine_for("forward"), "ms": fwd_ms,
                                      "note": "reference `sample` direction on the same draws (not part of `value`)"},
         }
+        if aux_grad is not None:
+            out["aux_grad_direction"] = aux_grad
         if not args.no_cpu_baseline and world == 1:
             rate, cores, sample = cpu_reference_rate(CONFIGS[args.config], args.cpu_seconds)
             out["cpu_baseline"] = {"value": rate, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample}
