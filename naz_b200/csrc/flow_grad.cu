@@ -19,11 +19,14 @@
 // Back-propagation to the input needs the weights transposed: a second image (rows = output units) is produced from
 // the SIMT image once per pack.
 #include <algorithm>
+#include <cstdlib>
 #include "nazb_internal.h"
 #include "transforms.cuh"
 #include "simt_gemm.cuh"
 
 namespace {
+
+constexpr int kTN = 5;   // 160-column passes (Tile<32, 5>)
 
 struct GradGeom {
   long long offT[NAZB_MAX_LIN];   // float offset of W_j^T ([ldw_j rows][ldk_j]) inside one (draw, layer) block
@@ -38,6 +41,7 @@ struct GradArgs {
   const long long* gwst;      // floats between draws of gW[i]
   const long long* gbst;
   float* dx;                  // [s_count][N][D] or null
+  int diag;                   // dev: 1 = skip the atomics (timing diagnosis only)
 };
 
 // dst[(draw, layer)][n][k] = src[(draw, layer)][k][n]
@@ -65,7 +69,7 @@ template <int P>
 __device__ __forceinline__ void outer_acc(const float* __restrict__ aT, int K, const float* __restrict__ bT, int Nn,
                                           const float* __restrict__ mask, float* __restrict__ gW,
                                           float* __restrict__ gb, const int* __restrict__ perm, int M, int D,
-                                          bool out_layer) {
+                                          bool out_layer, int diag) {
   const int tid = threadIdx.x, lane = tid & 31;
   const int kt = (K + 3) >> 2, nt = (Nn + 3) >> 2;
   for (int t = tid; t < kt * nt; t += kThreads) {
@@ -97,7 +101,7 @@ __device__ __forceinline__ void outer_acc(const float* __restrict__ aT, int K, c
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int k = k0 + i;
-        if (k < K && mask[(size_t)row * K + k] != 0.f) atomicAdd(gW + (size_t)row * K + k, acc[i][j]);
+        if (k < K && mask[(size_t)row * K + k] != 0.f && (!diag || acc[i][j] == 12345.678f)) atomicAdd(gW + (size_t)row * K + k, acc[i][j]);
       }
     }
   }
@@ -109,13 +113,13 @@ __device__ __forceinline__ void outer_acc(const float* __restrict__ aT, int K, c
   }
 }
 
-template <int P>
-__global__ void __launch_bounds__(kThreads) flow_grad_affine_kernel(FlowGeom g, GradGeom gg,
+template <int P, int NST>
+__global__ void __launch_bounds__(kThreads, 1) flow_grad_affine_kernel(FlowGeom g, GradGeom gg,
                                                                      const float* __restrict__ packed,
                                                                      const float* __restrict__ packedT,
                                                                      const int* __restrict__ perm_all, IoArgs io,
                                                                      GradArgs ga) {
-  using T = Tile<P>;
+  using T = Tile<P, kTN>;
   extern __shared__ __align__(16) float smem[];
   const int D = g.D, C = g.C, nh = g.n_hidden, n_lin = nh + 1;
   const int kin_pad = (g.kin + 3) & ~3, md_pad = (g.md + 3) & ~3;
@@ -134,8 +138,8 @@ __global__ void __launch_bounds__(kThreads) flow_grad_affine_kernel(FlowGeom g, 
   float* ldacc = msk + D * P;                          // [P]
   float* ljac = ldacc + P;                             // [P]
   float* zb = ljac + P;                                // [hmax]  zero bias of the transposed products
-  float* wbuf = zb + g.hmax;                           // [2][WCHUNK]
-  float* red = wbuf + 2 * T::WCHUNK;
+  float* wbuf = zb + g.hmax;                           // [NST][WCHUNK]
+  float* red = wbuf + NST * T::WCHUNK;
 
   const int tid = threadIdx.x;
   const int n0 = blockIdx.x * P;
@@ -179,11 +183,11 @@ __global__ void __launch_bounds__(kThreads) flow_grad_affine_kernel(FlowGeom g, 
           int K = (j == 0) ? g.kin : (full ? g.hidden[j - 1] : g.blk[j - 1][r + 1]);
           const float* act = (j == 0) ? xin : hbuf + (size_t)(j - 1) * g.hmax * P;
           if (c1 > c0)
-            gemm_panel<P, true>(act, K, wl + g.off_w[j], g.ldw[j], wl + g.off_b[j], c0, c1, hbuf + (size_t)j * g.hmax * P, wbuf);
+            gemm_panel_ms<P, true, kTN, NST>(act, K, wl + g.off_w[j], g.ldw[j], wl + g.off_b[j], c0, c1, hbuf + (size_t)j * g.hmax * P, wbuf);
         }
         {
           int K = full ? g.hidden[nh - 1] : g.blk[nh - 1][r + 1];
-          gemm_panel<P, false>(hbuf + (size_t)(nh - 1) * g.hmax * P, K, wl + g.off_w[nh], g.ldw[nh], wl + g.off_b[nh],
+          gemm_panel_ms<P, false, kTN, NST>(hbuf + (size_t)(nh - 1) * g.hmax * P, K, wl + g.off_w[nh], g.ldw[nh], wl + g.off_b[nh],
                                r * 2, (r + 1) * 2, obuf, wbuf);
         }
         if (tid < P) {
@@ -245,9 +249,9 @@ __global__ void __launch_bounds__(kThreads) flow_grad_affine_kernel(FlowGeom g, 
       __syncthreads();
       // conditioner at the solved x
       for (int j = 0; j < nh; ++j)
-        gemm_panel<P, true>((j == 0) ? xin : hbuf + (size_t)(j - 1) * g.hmax * P, g.kdim[j], wl + g.off_w[j], g.ldw[j],
+        gemm_panel_ms<P, true, kTN, NST>((j == 0) ? xin : hbuf + (size_t)(j - 1) * g.hmax * P, g.kdim[j], wl + g.off_w[j], g.ldw[j],
                             wl + g.off_b[j], 0, g.hidden[j], hbuf + (size_t)j * g.hmax * P, wbuf);
-      gemm_panel<P, false>(hbuf + (size_t)(nh - 1) * g.hmax * P, g.kdim[nh], wl + g.off_w[nh], g.ldw[nh],
+      gemm_panel_ms<P, false, kTN, NST>(hbuf + (size_t)(nh - 1) * g.hmax * P, g.kdim[nh], wl + g.off_w[nh], g.ldw[nh],
                            wl + g.off_b[nh], 0, g.md, obuf, wbuf);
       for (int i = tid; i < P * D; i += kThreads) {
         int p = i % P, r = i / P;
@@ -272,12 +276,12 @@ __global__ void __launch_bounds__(kThreads) flow_grad_affine_kernel(FlowGeom g, 
         const int to = l * n_lin + nh;
         if (last)
           outer_acc<P>(hbuf + (size_t)(nh - 1) * g.hmax * P, g.kdim[nh], cbuf, g.md, ga.mask[to],
-                       ga.gW[to] + (size_t)sg * ga.gwst[to], ga.gb[to] + (size_t)sg * ga.gbst[to], perm, 2, D, true);
+                       ga.gW[to] + (size_t)sg * ga.gwst[to], ga.gb[to] + (size_t)sg * ga.gbst[to], perm, 2, D, true, ga.diag);
         const float* src = cbuf;
         for (int j = nh; j >= 1; --j) {
           float* dst = ((nh - j) & 1) ? dB : dA;
           // delta_{j-1}[k][p] = (sum_n W_j[n][k] delta_j[n][p]) * (1 - h_{j-1}[k][p]^2)
-          gemm_panel<P, false>(src, g.ndim[j], wlT + gg.offT[j], gg.ldk[j], zb, 0, g.kdim[j], dst, wbuf);
+          gemm_panel_ms<P, false, kTN, NST>(src, g.ndim[j], wlT + gg.offT[j], gg.ldk[j], zb, 0, g.kdim[j], dst, wbuf);
           const float* hj = hbuf + (size_t)(j - 1) * g.hmax * P;
           for (int i = tid; i < g.kdim[j] * P; i += kThreads) { float hv = hj[i]; dst[i] *= (1.f - hv * hv); }
           __syncthreads();
@@ -285,12 +289,12 @@ __global__ void __launch_bounds__(kThreads) flow_grad_affine_kernel(FlowGeom g, 
             const int ti = l * n_lin + (j - 1);
             outer_acc<P>((j - 1 == 0) ? xin : hbuf + (size_t)(j - 2) * g.hmax * P, g.kdim[j - 1], dst, g.ndim[j - 1],
                          ga.mask[ti], ga.gW[ti] + (size_t)sg * ga.gwst[ti], ga.gb[ti] + (size_t)sg * ga.gbst[ti], perm, 2, D,
-                         false);
+                         false, ga.diag);
           }
           src = dst;
         }
         if (!last) {
-          gemm_panel<P, false>(src, g.ndim[0], wlT + gg.offT[0], gg.ldk[0], zb, 0, g.kin, dxb, wbuf);
+          gemm_panel_ms<P, false, kTN, NST>(src, g.ndim[0], wlT + gg.offT[0], gg.ldk[0], zb, 0, g.kin, dxb, wbuf);
           for (int i = tid; i < P * D; i += kThreads) {
             int p = i % P, d = i / P;
             lam[i] = gcur[i] + dxb[(C + d) * P + p];
@@ -324,12 +328,12 @@ __global__ void __launch_bounds__(kThreads) flow_grad_affine_kernel(FlowGeom g, 
   }
 }
 
-size_t grad_smem_bytes(const FlowGeom& g, int P) {
+size_t grad_smem_bytes(const FlowGeom& g, int P, int nst) {
   const int kin_pad = (g.kin + 3) & ~3, md_pad = (g.md + 3) & ~3;
   size_t f = (size_t)2 * kin_pad * P + (size_t)4 * g.D * P + (size_t)(g.n_hidden + 2) * g.hmax * P +
              (size_t)2 * md_pad * P + (size_t)g.L * g.D * P + 2 * P + g.hmax;
-  int TR = P / 4, TC = kThreads / TR, NPASS = TC * 4;
-  f += 2 * (size_t)kKC * NPASS;
+  int TR = P / 4, TC = kThreads / TR, NPASS = TC * kTN;
+  f += (size_t)nst * kKC * NPASS;
   f += 2 * (kThreads / 32) + 4;
   return f * sizeof(float) + 16;
 }
@@ -370,7 +374,8 @@ cudaError_t nazb_grad_launch(nazb_handle* h, const IoArgs& io, const void* tabs,
     h->packed_T_valid = true;
   }
   constexpr int P = 32;
-  const size_t smem = grad_smem_bytes(g, P);
+  const int nst = grad_smem_bytes(g, P, 4) <= 227 * 1024 ? 4 : 2;   // depth of the weight-panel ring
+  const size_t smem = grad_smem_bytes(g, P, nst);
   if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
   GradArgs ga{};
   const char* t = static_cast<const char*>(tabs);
@@ -380,13 +385,20 @@ cudaError_t nazb_grad_launch(nazb_handle* h, const IoArgs& io, const void* tabs,
   ga.gwst = reinterpret_cast<const long long*>(t + sizeof(void*) * 3 * n);
   ga.gbst = reinterpret_cast<const long long*>(t + sizeof(void*) * 4 * n);
   ga.dx = dx;
-  e = cudaFuncSetAttribute(flow_grad_affine_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
+  ga.diag = (getenv("NAZB_GRAD_DIAG") && atoi(getenv("NAZB_GRAD_DIAG"))) ? 1 : 0;
   const int tiles = (io.N + P - 1) / P;
   dim3 grid(tiles, std::min(io.s_count, 65535));
-  flow_grad_affine_kernel<P><<<grid, kThreads, smem, st>>>(g, gg, h->packed, h->packed_T, h->perm_dev, io, ga);
+  if (nst == 4) {
+    e = cudaFuncSetAttribute(flow_grad_affine_kernel<P, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    flow_grad_affine_kernel<P, 4><<<grid, kThreads, smem, st>>>(g, gg, h->packed, h->packed_T, h->perm_dev, io, ga);
+  } else {
+    e = cudaFuncSetAttribute(flow_grad_affine_kernel<P, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    flow_grad_affine_kernel<P, 2><<<grid, kThreads, smem, st>>>(g, gg, h->packed, h->packed_T, h->perm_dev, io, ga);
+  }
   nazb_count_launch();
   return cudaGetLastError();
 }
 
-bool nazb_grad_fits(const FlowGeom& g) { return grad_smem_bytes(g, 32) <= 227 * 1024; }
+bool nazb_grad_fits(const FlowGeom& g) { return grad_smem_bytes(g, 32, 2) <= 227 * 1024; }
