@@ -26,8 +26,6 @@
 
 namespace {
 
-constexpr int kTN = 5;   // 160-column passes (Tile<32, 5>)
-
 struct GradGeom {
   long long offT[NAZB_MAX_LIN];   // float offset of W_j^T ([ldw_j rows][ldk_j]) inside one (draw, layer) block
   int ldk[NAZB_MAX_LIN];          // kdim_j rounded up to 4
@@ -113,13 +111,14 @@ __device__ __forceinline__ void outer_acc(const float* __restrict__ aT, int K, c
   }
 }
 
-template <int P, int NST>
-__global__ void __launch_bounds__(kThreads, 1) flow_grad_affine_kernel(FlowGeom g, GradGeom gg,
+// P = 16, TN = 3 (192-column passes): ~100 KB of shared memory, two CTAs per SM;  P = 32, TN = 5 (160-column passes): one
+template <int P, int NST, int TN>
+__global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_affine_kernel(FlowGeom g, GradGeom gg,
                                                                      const float* __restrict__ packed,
                                                                      const float* __restrict__ packedT,
                                                                      const int* __restrict__ perm_all, IoArgs io,
                                                                      GradArgs ga) {
-  using T = Tile<P, kTN>;
+  using T = Tile<P, TN>;
   extern __shared__ __align__(16) float smem[];
   const int D = g.D, C = g.C, nh = g.n_hidden, n_lin = nh + 1;
   const int kin_pad = (g.kin + 3) & ~3, md_pad = (g.md + 3) & ~3;
@@ -183,11 +182,11 @@ __global__ void __launch_bounds__(kThreads, 1) flow_grad_affine_kernel(FlowGeom 
           int K = (j == 0) ? g.kin : (full ? g.hidden[j - 1] : g.blk[j - 1][r + 1]);
           const float* act = (j == 0) ? xin : hbuf + (size_t)(j - 1) * g.hmax * P;
           if (c1 > c0)
-            gemm_panel_ms<P, true, kTN, NST>(act, K, wl + g.off_w[j], g.ldw[j], wl + g.off_b[j], c0, c1, hbuf + (size_t)j * g.hmax * P, wbuf);
+            gemm_panel_ms<P, true, TN, NST>(act, K, wl + g.off_w[j], g.ldw[j], wl + g.off_b[j], c0, c1, hbuf + (size_t)j * g.hmax * P, wbuf);
         }
         {
           int K = full ? g.hidden[nh - 1] : g.blk[nh - 1][r + 1];
-          gemm_panel_ms<P, false, kTN, NST>(hbuf + (size_t)(nh - 1) * g.hmax * P, K, wl + g.off_w[nh], g.ldw[nh], wl + g.off_b[nh],
+          gemm_panel_ms<P, false, TN, NST>(hbuf + (size_t)(nh - 1) * g.hmax * P, K, wl + g.off_w[nh], g.ldw[nh], wl + g.off_b[nh],
                                r * 2, (r + 1) * 2, obuf, wbuf);
         }
         if (tid < P) {
@@ -249,9 +248,9 @@ __global__ void __launch_bounds__(kThreads, 1) flow_grad_affine_kernel(FlowGeom 
       __syncthreads();
       // conditioner at the solved x
       for (int j = 0; j < nh; ++j)
-        gemm_panel_ms<P, true, kTN, NST>((j == 0) ? xin : hbuf + (size_t)(j - 1) * g.hmax * P, g.kdim[j], wl + g.off_w[j], g.ldw[j],
+        gemm_panel_ms<P, true, TN, NST>((j == 0) ? xin : hbuf + (size_t)(j - 1) * g.hmax * P, g.kdim[j], wl + g.off_w[j], g.ldw[j],
                             wl + g.off_b[j], 0, g.hidden[j], hbuf + (size_t)j * g.hmax * P, wbuf);
-      gemm_panel_ms<P, false, kTN, NST>(hbuf + (size_t)(nh - 1) * g.hmax * P, g.kdim[nh], wl + g.off_w[nh], g.ldw[nh],
+      gemm_panel_ms<P, false, TN, NST>(hbuf + (size_t)(nh - 1) * g.hmax * P, g.kdim[nh], wl + g.off_w[nh], g.ldw[nh],
                            wl + g.off_b[nh], 0, g.md, obuf, wbuf);
       for (int i = tid; i < P * D; i += kThreads) {
         int p = i % P, r = i / P;
@@ -281,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_grad_affine_kernel(FlowGeom 
         for (int j = nh; j >= 1; --j) {
           float* dst = ((nh - j) & 1) ? dB : dA;
           // delta_{j-1}[k][p] = (sum_n W_j[n][k] delta_j[n][p]) * (1 - h_{j-1}[k][p]^2)
-          gemm_panel_ms<P, false, kTN, NST>(src, g.ndim[j], wlT + gg.offT[j], gg.ldk[j], zb, 0, g.kdim[j], dst, wbuf);
+          gemm_panel_ms<P, false, TN, NST>(src, g.ndim[j], wlT + gg.offT[j], gg.ldk[j], zb, 0, g.kdim[j], dst, wbuf);
           const float* hj = hbuf + (size_t)(j - 1) * g.hmax * P;
           for (int i = tid; i < g.kdim[j] * P; i += kThreads) { float hv = hj[i]; dst[i] *= (1.f - hv * hv); }
           __syncthreads();
@@ -294,7 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_grad_affine_kernel(FlowGeom 
           src = dst;
         }
         if (!last) {
-          gemm_panel_ms<P, false, kTN, NST>(src, g.ndim[0], wlT + gg.offT[0], gg.ldk[0], zb, 0, g.kin, dxb, wbuf);
+          gemm_panel_ms<P, false, TN, NST>(src, g.ndim[0], wlT + gg.offT[0], gg.ldk[0], zb, 0, g.kin, dxb, wbuf);
           for (int i = tid; i < P * D; i += kThreads) {
             int p = i % P, d = i / P;
             lam[i] = gcur[i] + dxb[(C + d) * P + p];
@@ -328,11 +327,11 @@ __global__ void __launch_bounds__(kThreads, 1) flow_grad_affine_kernel(FlowGeom 
   }
 }
 
-size_t grad_smem_bytes(const FlowGeom& g, int P, int nst) {
+size_t grad_smem_bytes(const FlowGeom& g, int P, int nst, int tn) {
   const int kin_pad = (g.kin + 3) & ~3, md_pad = (g.md + 3) & ~3;
   size_t f = (size_t)2 * kin_pad * P + (size_t)4 * g.D * P + (size_t)(g.n_hidden + 2) * g.hmax * P +
              (size_t)2 * md_pad * P + (size_t)g.L * g.D * P + 2 * P + g.hmax;
-  int TR = P / 4, TC = kThreads / TR, NPASS = TC * kTN;
+  int TR = P / 4, TC = kThreads / TR, NPASS = TC * tn;
   f += (size_t)nst * kKC * NPASS;
   f += 2 * (kThreads / 32) + 4;
   return f * sizeof(float) + 16;
@@ -373,10 +372,6 @@ cudaError_t nazb_grad_launch(nazb_handle* h, const IoArgs& io, const void* tabs,
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     h->packed_T_valid = true;
   }
-  constexpr int P = 32;
-  const int nst = grad_smem_bytes(g, P, 4) <= 227 * 1024 ? 4 : 2;   // depth of the weight-panel ring
-  const size_t smem = grad_smem_bytes(g, P, nst);
-  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
   GradArgs ga{};
   const char* t = static_cast<const char*>(tabs);
   ga.mask = reinterpret_cast<const float* const*>(t);
@@ -386,19 +381,27 @@ cudaError_t nazb_grad_launch(nazb_handle* h, const IoArgs& io, const void* tabs,
   ga.gbst = reinterpret_cast<const long long*>(t + sizeof(void*) * 4 * n);
   ga.dx = dx;
   ga.diag = (getenv("NAZB_GRAD_DIAG") && atoi(getenv("NAZB_GRAD_DIAG"))) ? 1 : 0;
+  // two 16-point CTAs per SM when they fit (16 warps hide the FFMA / LDS latencies better than one 32-point CTA)
+  const size_t cap = 227 * 1024;
+  int P = (2 * (grad_smem_bytes(g, 16, 2, 3) + 1024) <= cap) ? 16 : 32;
+  if (const char* env = getenv("NAZB_GRAD_P")) { if (atoi(env) == 32) P = 32; }
+  const size_t smem = (P == 16) ? grad_smem_bytes(g, 16, 2, 3) : grad_smem_bytes(g, 32, 2, 5);
+  if (smem > cap) return cudaErrorInvalidConfiguration;
   const int tiles = (io.N + P - 1) / P;
   dim3 grid(tiles, std::min(io.s_count, 65535));
-  if (nst == 4) {
-    e = cudaFuncSetAttribute(flow_grad_affine_kernel<P, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (P == 16) {
+    e = cudaFuncSetAttribute(flow_grad_affine_kernel<16, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    flow_grad_affine_kernel<P, 4><<<grid, kThreads, smem, st>>>(g, gg, h->packed, h->packed_T, h->perm_dev, io, ga);
+    flow_grad_affine_kernel<16, 2, 3><<<grid, kThreads, smem, st>>>(g, gg, h->packed, h->packed_T, h->perm_dev, io, ga);
   } else {
-    e = cudaFuncSetAttribute(flow_grad_affine_kernel<P, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(flow_grad_affine_kernel<32, 2, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    flow_grad_affine_kernel<P, 2><<<grid, kThreads, smem, st>>>(g, gg, h->packed, h->packed_T, h->perm_dev, io, ga);
+    flow_grad_affine_kernel<32, 2, 5><<<grid, kThreads, smem, st>>>(g, gg, h->packed, h->packed_T, h->perm_dev, io, ga);
   }
   nazb_count_launch();
   return cudaGetLastError();
 }
 
-bool nazb_grad_fits(const FlowGeom& g) { return grad_smem_bytes(g, 32, 2) <= 227 * 1024; }
+bool nazb_grad_fits(const FlowGeom& g) {
+  return grad_smem_bytes(g, 16, 2, 3) <= 227 * 1024 || grad_smem_bytes(g, 32, 2, 5) <= 227 * 1024;
+}
