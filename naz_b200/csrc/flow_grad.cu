@@ -111,7 +111,7 @@ __device__ __forceinline__ void outer_acc(const float* __restrict__ aT, int K, c
   }
 }
 
-// P = 16, TN = 3 (192-column passes): ~100 KB of shared memory, two CTAs per SM;  P = 32, TN = 5 (160-column passes): one
+// P = 32, TN = 5 (160-column passes), one CTA per SM: the default;  P = 16, TN = 3 (192-column passes): half the state
 template <int P, int NST, int TN>
 __global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_affine_kernel(FlowGeom g, GradGeom gg,
                                                                      const float* __restrict__ packed,
@@ -381,23 +381,24 @@ cudaError_t nazb_grad_launch(nazb_handle* h, const IoArgs& io, const void* tabs,
   ga.gbst = reinterpret_cast<const long long*>(t + sizeof(void*) * 4 * n);
   ga.dx = dx;
   ga.diag = (getenv("NAZB_GRAD_DIAG") && atoi(getenv("NAZB_GRAD_DIAG"))) ? 1 : 0;
-  // two 16-point CTAs per SM when they fit (16 warps hide the FFMA / LDS latencies better than one 32-point CTA)
+  // Measured (maf 2|2, 4 chains x 100 k points): one 32-point CTA per SM 245 ms, two 16-point CTAs per SM 274 ms — the
+  // shared-memory wavefronts per point double with the smaller tile — so 16-point tiles only serve shapes whose 32-point
+  // state does not fit.  The 4-deep weight ring costs nothing at one CTA per SM and is dropped first.
   const size_t cap = 227 * 1024;
-  int P = (2 * (grad_smem_bytes(g, 16, 2, 3) + 1024) <= cap) ? 16 : 32;
-  if (const char* env = getenv("NAZB_GRAD_P")) { if (atoi(env) == 32) P = 32; }
-  const size_t smem = (P == 16) ? grad_smem_bytes(g, 16, 2, 3) : grad_smem_bytes(g, 32, 2, 5);
+  int P = 32, nst = 4;
+  if (grad_smem_bytes(g, 32, 4, 5) > cap) nst = 2;
+  if (grad_smem_bytes(g, 32, nst, 5) > cap) P = 16;
+  if (const char* env = getenv("NAZB_GRAD_P")) { if (atoi(env) == 16) P = 16; }
+  const size_t smem = (P == 16) ? grad_smem_bytes(g, 16, 2, 3) : grad_smem_bytes(g, 32, nst, 5);
   if (smem > cap) return cudaErrorInvalidConfiguration;
   const int tiles = (io.N + P - 1) / P;
   dim3 grid(tiles, std::min(io.s_count, 65535));
-  if (P == 16) {
-    e = cudaFuncSetAttribute(flow_grad_affine_kernel<16, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    flow_grad_affine_kernel<16, 2, 3><<<grid, kThreads, smem, st>>>(g, gg, h->packed, h->packed_T, h->perm_dev, io, ga);
-  } else {
-    e = cudaFuncSetAttribute(flow_grad_affine_kernel<32, 2, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    flow_grad_affine_kernel<32, 2, 5><<<grid, kThreads, smem, st>>>(g, gg, h->packed, h->packed_T, h->perm_dev, io, ga);
-  }
+#define NAZB_GRAD_LAUNCH(PP, NS, TT)                                                                                   \
+  e = cudaFuncSetAttribute(flow_grad_affine_kernel<PP, NS, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+  if (e != cudaSuccess) return e;                                                                                      \
+  flow_grad_affine_kernel<PP, NS, TT><<<grid, kThreads, smem, st>>>(g, gg, h->packed, h->packed_T, h->perm_dev, io, ga);
+  if (P == 16) { NAZB_GRAD_LAUNCH(16, 2, 3) } else if (nst == 4) { NAZB_GRAD_LAUNCH(32, 4, 5) } else { NAZB_GRAD_LAUNCH(32, 2, 5) }
+#undef NAZB_GRAD_LAUNCH
   nazb_count_launch();
   return cudaGetLastError();
 }
