@@ -1,7 +1,11 @@
 """Sharding by weight draw across the GPUs of one box: rank g owns a contiguous slice
 of the draws and its packed weights only; points are replicated.  Exactly one collective per call:
 an all-gather of the per-rank (max, sum-exp) partials for the per-point posterior predictive, or of the
-per-draw sums for importance weights.  Raw [S,N] / [S,N,D] outputs stay sharded."""
+per-draw sums for importance weights.  Raw [S,N] / [S,N,D] outputs stay sharded.
+
+The gradient path shards the other way: the chains are few and every chain sums over the whole data set,
+so rank g takes a contiguous slice of the POINTS, every rank holds all chains, and one all-reduce(SUM) of the flattened
+gradient + value buffer finishes the step (the reference's jax.grad over `jnp.sum(lp)`, bflow_jax_maf.py:233-235)."""
 from __future__ import annotations
 
 import math
@@ -70,3 +74,46 @@ def all_gather_draw_sums(sum_local: torch.Tensor, S_total: int, group=None) -> t
         b, e = shard_range(S_total, r, world)
         parts.append(buf[r][: e - b])
     return torch.cat(parts)
+
+
+def point_range(N: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced slice of the points for the gradient path."""
+    return shard_range(N, rank, world)
+
+
+def all_reduce_value_and_grads(sum_n: torch.Tensor, gW, gb, group=None):
+    """Sum the per-rank partial values [S] and gradients ([L][n_lin] of [S,out,in] / [S,out]) over the ranks with ONE
+    all-reduce of a flat buffer; returns (sum_n, gW, gb) holding the totals (views into the reduced buffer)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return sum_n, gW, gb
+    leaves = [sum_n] + [t for layer in gW for t in layer] + [t for layer in gb for t in layer]
+    flat = torch.cat([t.reshape(-1) for t in leaves[1:]])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    val = sum_n.clone()
+    dist.all_reduce(val, op=dist.ReduceOp.SUM, group=group)     # float64 [S]: kept apart from the fp32 gradient buffer
+    out, off = [], 0
+    for t in leaves[1:]:
+        n = t.numel()
+        out.append(flat[off:off + n].view_as(t))
+        off += n
+    nW = sum(len(layer) for layer in gW)
+    it = iter(out[:nW])
+    gW2 = [[next(it) for _ in layer] for layer in gW]
+    it = iter(out[nW:])
+    gb2 = [[next(it) for _ in layer] for layer in gb]
+    return val, gW2, gb2
+
+
+def inverse_grad_point_sharded(eng, x: torch.Tensor, ctx: Optional[torch.Tensor] = None, bounds=None, group=None):
+    """FlowEngine.inverse_grad over this rank's slice of the points, then the all-reduce.  x (and a per-point ctx) are the
+    FULL arrays, identical on every rank."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    b, e = point_range(x.shape[0], rank, world)
+    c = ctx
+    if ctx is not None and ctx.dim() == 2 and ctx.shape[0] == x.shape[0]:
+        c = ctx[b:e]
+    r = eng.inverse_grad(x[b:e], c, bounds)
+    val, gW, gb = all_reduce_value_and_grads(r["sum_n"], r["gW"], r["gb"], group)
+    return {"sum_n": val, "gW": gW, "gb": gb}

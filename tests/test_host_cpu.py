@@ -150,3 +150,47 @@ def test_draw_sharded_reduction_world2_gloo():
     ret = mgr.dict()
     mp.spawn(_gloo_worker, args=(world, _free_port(), 7, 33, ret), nprocs=world, join=True)
     assert all(ret[r] for r in range(world))
+
+
+class _FakeGradEngine:
+    """Stands in for FlowEngine.inverse_grad on CPU: value and 'gradients' that are sums over points of simple functions."""
+
+    def inverse_grad(self, x, ctx=None, bounds=None):
+        c = 0.0 if ctx is None else (ctx.sum(-1, keepdim=True) if ctx.dim() == 2 and ctx.shape[0] == x.shape[0] else ctx.sum())
+        f = (x + c)
+        S = 3
+        sc = torch.arange(1, S + 1, dtype=torch.float32)
+        gW = [[(sc[:, None, None] * (f.T @ f.pow(2))[None]).contiguous()], [(sc[:, None, None] * f.pow(3).sum().reshape(1, 1, 1)).contiguous()]]
+        gb = [[(sc[:, None] * f.sum(0)[None]).contiguous()], [(sc[:, None] * f.abs().sum().reshape(1, 1)).contiguous()]]
+        return {"sum_n": (sc.double() * f.double().sum()), "gW": gW, "gb": gb}
+
+
+def _gloo_grad_worker(rank, world, port, N, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from naz_b200.parallel import inverse_grad_point_sharded
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(N, 2, generator=g)
+    ctx = torch.rand(N, 3, generator=g)
+    eng = _FakeGradEngine()
+    got = inverse_grad_point_sharded(eng, x, ctx)
+    ref = eng.inverse_grad(x, ctx)
+    ok = torch.allclose(got["sum_n"], ref["sum_n"], rtol=1e-6)
+    for a, b in zip([t for l in got["gW"] + got["gb"] for t in l], [t for l in ref["gW"] + ref["gb"] for t in l]):
+        ok = ok and a.shape == b.shape and torch.allclose(a, b, rtol=1e-4, atol=1e-4)
+    # broadcast context is not sliced
+    got1 = inverse_grad_point_sharded(eng, x, ctx[0])
+    ok = ok and torch.allclose(got1["sum_n"], eng.inverse_grad(x, ctx[0])["sum_n"], rtol=1e-6)
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_point_sharded_gradient_allreduce_world2_gloo():
+    """f1 multi-GPU: points sharded, one all-reduce of the gradient buffer (ragged split: 37 points over 2 ranks)"""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_gloo_grad_worker, args=(world, _free_port(), 37, ret), nprocs=world, join=True)
+    assert all(ret[r] for r in range(world))
