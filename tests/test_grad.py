@@ -158,3 +158,37 @@ def test_twin_value_and_grad_single_draw_against_reference_fixture():
         for j in range(len(spec.hidden) + 1):
             assert _rel(grads[l][j][0].cpu().numpy(), gW[l][j]) < 2e-4
             assert _rel(grads[l][j][1].cpu().numpy(), gb[l][j]) < 2e-4
+
+
+@pytest.mark.gpu
+def test_inverse_grad_directional_derivative_at_bench_size():
+    """Size-independent property at the size bench.py times (config-4 architecture, 100 000 points): the central
+    difference of the VALUE — computed by the tensor-core log_prob engine, an independent code path — along the
+    normalised gradient equals the gradient's norm."""
+    from helpers import engine_for
+    S, N = 2, 100_000
+    spec, draws, _, rng = make_case("maf", 2, 2, [150] * 3, 16, S, seed=21)
+    x = torch.from_numpy((rng.normal(size=(N, 2)) * 1.5).astype(np.float32))
+    ctx = torch.from_numpy(rng.uniform(size=(N, 2)).astype(np.float32))
+    r = engine_for(spec, draws, engine="simt").inverse_grad(x, ctx)
+    torch.cuda.synchronize()
+    gW = [[t.cpu().numpy().astype(np.float64) for t in layer] for layer in r["gW"]]
+    gb = [[t.cpu().numpy().astype(np.float64) for t in layer] for layer in r["gb"]]
+    norm = np.sqrt(sum((g ** 2).reshape(S, -1).sum(1) for layer in gW for g in layer) +
+                   sum((g ** 2).reshape(S, -1).sum(1) for layer in gb for g in layer))          # [S]
+    assert np.all(np.isfinite(norm)) and np.all(norm > 0)
+    eps = np.clip(20.0 / norm, 1e-5, 1e-3)                                                      # value step ~ +-20
+
+    def value(sign):
+        pert = [[((W + sign * (eps / norm)[:, None, None] * gW[l][j]).astype(np.float32),
+                  (b + sign * (eps / norm)[:, None] * gb[l][j]).astype(np.float32))
+                 for j, (W, b) in enumerate(layer)] for l, layer in enumerate(draws)]
+        e = engine_for(spec, pert, engine="auto")
+        v = e.inverse(x, ctx, want_lp=False, want_sum=True)["sum_n"].cpu().numpy()
+        return v, e.engine_for("inverse")
+
+    vp, used = value(+1.0)
+    vm, _ = value(-1.0)
+    assert used == "tcgen05"
+    fd = (vp - vm) / (2 * eps)
+    assert np.all(np.abs(fd - norm) <= 3e-2 * norm), (fd, norm, eps)
