@@ -143,7 +143,7 @@ class FlowEngine:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     # ------------------------------------------------------------------
-    def pack_draw_map(self, base, standard_params: torch.Tensor, scale: float, masks, perms,
+    def pack_draw_map(self, base, standard_params: torch.Tensor, scale, masks, perms,
                       keep: Optional[torch.Tensor] = None, p_drop: float = 0.0):
         """Pack S draws given as the reference's STANDARD parameters (bflow_jax_maf.py:239-240):
         theta_s = theta_0 * (1 + scale * u_s), applied while packing (no [S, P] `params` array, no per-draw loop).
@@ -155,6 +155,28 @@ class FlowEngine:
         P = sum(dims[j + 1] * dims[j] + dims[j + 1] for j in range(len(dims) - 1)) * sh.L
         if u.dim() != 2 or u.shape[0] != self.S or u.shape[1] != P:
             raise ValueError(f"standard_params must be [S={self.S}, P={P}]")
+        if isinstance(scale, torch.Tensor) and scale.numel() > 1:
+            # fixed_scale=False of the reference's model (bflow_jax_maf.py:238): `scale` is itself sampled, one value per
+            # draw [S] or per draw and parameter [S, P] (multi_scale=True).  The fused pack kernels take one scalar, so this
+            # rarely used variant materialises theta = theta_0 * (1 + scale * u) on the device with the reference's
+            # un-fused fp32 rounding order (mul, add, mul) and packs the result.
+            sc = _f32c(scale, self.device)
+            if tuple(sc.shape) not in ((self.S,), (self.S, 1), (self.S, P)):
+                raise ValueError(f"scale must be a float, [S={self.S}] or [S={self.S}, P={P}]")
+            sc = sc.reshape(self.S, -1)
+            flat0 = torch.cat([torch.cat([_f32c(torch.as_tensor(W0), self.device).reshape(-1),
+                                          _f32c(torch.as_tensor(b0), self.device).reshape(-1)]) for layer in base for (W0, b0) in layer])
+            theta = flat0.unsqueeze(0) * (1.0 + sc * u)
+            draws, off = [], 0
+            for l in range(sh.L):
+                lay = []
+                for j in range(len(dims) - 1):
+                    out, inn = dims[j + 1], dims[j]
+                    W = theta[:, off:off + out * inn].reshape(self.S, out, inn); off += out * inn
+                    bb = theta[:, off:off + out]; off += out
+                    lay.append((W, bb))
+                draws.append(lay)
+            return self.pack(draws, masks, perms, keep, p_drop)
         views, off = [], 0
         for l in range(sh.L):
             lay = []

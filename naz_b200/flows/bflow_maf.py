@@ -97,7 +97,8 @@ def make_normalizing_flow(transform, x, masks, mask_skips, perms, bounds=None, c
         the draw map of bflow_jax_maf.py:239-240 runs inside the pack kernels (nazb_pack_draw_map)."""
         u = torch.as_tensor(standard_params, dtype=torch.float32)
         S = u.shape[0]
-        key = ("std", S, u.data_ptr(), float(scale)) + tuple(t.data_ptr() for layer in best_params for pair in layer for t in pair)
+        sc_key = ("t", scale.data_ptr()) if isinstance(scale, torch.Tensor) and scale.numel() > 1 else float(scale)   # posterior["scale"] is [S]
+        key = ("std", S, u.data_ptr(), sc_key) + tuple(t.data_ptr() for layer in best_params for pair in layer for t in pair)
         if cache.get("key") != key:
             if cache.get("eng") is None or cache["eng"].S != S:
                 cache["eng"] = FlowEngine(shape, S, device=dev, engine=engine)

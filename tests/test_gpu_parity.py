@@ -147,6 +147,38 @@ def test_draw_map_pack_equals_materialised_draws(engine):
     check(b_, lp_ref, "lp through the draw map")
 
 
+def test_draw_map_with_sampled_scale_per_draw_and_per_parameter():
+    """fixed_scale=False of the reference's model (bflow_jax_maf.py:238): scale is [S] or, with multi_scale, [S, P]"""
+    from naz_b200 import FlowEngine, FlowShape
+    S = 3
+    spec, _, _, rng = make_case("maf", 3, 1, [32, 32], 2, 1, seed=41)
+    p0 = fo.init_weights(spec, rng, np.float32)
+    dims = [4, 32, 32, 6]
+    P = sum(dims[j + 1] * dims[j] + dims[j + 1] for j in range(3)) * spec.L
+    u = rng.uniform(-1, 1, size=(S, P)).astype(np.float32)
+    flat0 = np.concatenate([np.concatenate([W.ravel(), b.ravel()]) for layer in p0 for (W, b) in layer]).astype(np.float32)
+    x = (rng.normal(size=(70, 3)) * 1.2).astype(np.float32)
+    ctx = rng.uniform(size=(1,)).astype(np.float32)
+    shape = FlowShape("maf", 3, 1, [32, 32], spec.L)
+    for sc in (rng.uniform(0.05, 0.25, size=(S,)).astype(np.float32), rng.uniform(0.05, 0.25, size=(S, P)).astype(np.float32)):
+        theta = flat0[None, :] * (np.float32(1.0) + sc.reshape(S, -1) * u)
+        draws, off = [], 0
+        for l in range(spec.L):
+            lay = []
+            for j in range(3):
+                out, inn = dims[j + 1], dims[j]
+                W = theta[:, off:off + out * inn].reshape(S, out, inn); off += out * inn
+                b = theta[:, off:off + out]; off += out
+                lay.append((np.ascontiguousarray(W), np.ascontiguousarray(b)))
+            draws.append(lay)
+        e = FlowEngine(shape, S, device="cuda:0")
+        e.pack_draw_map([[(T(W), T(b)) for (W, b) in layer] for layer in p0], T(u), T(sc),
+                        [[T(m) for m in ml] for ml in spec.masks()], T(spec.perms))
+        got = e.inverse(T(x), T(ctx), want_lp=True)["lp"]
+        lp_ref, _ = fo.log_prob_draws(spec, to64(draws), x.astype(np.float64), ctx.astype(np.float64))
+        check(got, lp_ref, "lp with a sampled scale")
+
+
 def test_svi_importance_pipeline_on_device():
     """cfg-4 data flow end to end on the device: truncated-normal guide draws -> draw map while packing -> sum_n log-prob
     -> importance weights / evidence / ESS, against the fp64 oracle pipeline."""
