@@ -29,6 +29,33 @@ def test_library_builds_and_exports_every_declared_symbol(built_lib):
     assert b"sm_100" in _lib.lib().nazb_strerror(-5)
 
 
+def test_header_is_plain_c_and_a_c_caller_links(built_lib, tmp_path):
+    """The drop-in boundary is a C ABI: include/nazb.h must compile as C99 (what cgo / JNI / ctypes-style bindings parse)
+    and a C program must link against libnazb.so and reach the error paths that need no GPU."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "c_caller.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <string.h>\n#include "nazb.h"\n'
+        "int main(void) {\n"
+        "  nazb_handle* h = (nazb_handle*)0;\n"
+        "  if (strcmp(nazb_strerror(NAZB_OK), \"ok\") != 0) return 1;\n"
+        "  if (nazb_create(&h, (const nazb_desc*)0) != NAZB_ERR_BAD_ARG) return 2;   /* null descriptor */\n"
+        "  if (nazb_inverse_grad(h, 0, 1, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0) != NAZB_ERR_BAD_ARG) return 3;\n"
+        "  if (nazb_launch_count() != 0) return 4;\n"
+        '  puts("c-abi ok");\n  return 0;\n}\n')
+    exe = tmp_path / "c_caller"
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.dirname(built_lib)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", f"-I{inc}", str(src)], check=True)
+    subprocess.run(["gcc", "-std=c99", f"-I{inc}", str(src), "-o", str(exe), f"-L{libdir}", "-lnazb", f"-Wl,-rpath,{libdir}"],
+                   check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and "c-abi ok" in out.stdout, (out.returncode, out.stdout, out.stderr)
+
+
 def test_sass_is_blackwell_native(built_lib):
     """The tensor-core engine must contain tcgen05 MMAs (UTCHMMA), TMEM loads (LDTM) and TMA bulk copies (UBLKCP)."""
     import subprocess
