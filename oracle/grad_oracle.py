@@ -7,9 +7,12 @@ The reference has no hand-written backward pass: its NUTS / SVI / MLE drivers di
 of the restated forward function*: the masked-affine twin below follows bflow_jax_maf.py line by line
 (masked_linear :74-77, nn_fn :135-165 with the context first and the [.., M, D] reshape, inverse_fn :181-194 with its D
 sequential passes and clip(-5, 3), log_prob assembly :210-212) in torch float64, and torch.autograd supplies the
-gradients.  PINNING: tests/test_grad.py requires the forward values of this function to equal oracle/flow_oracle.py
-(whose MAF branch is pinned by the reference-executed fixtures tests/golden/ref_twin_*.npz) and the committed reference
-outputs themselves; the gradients are additionally checked against central finite differences of that pinned forward.
+gradients.  PINNED BY DERIVATIVES OF THE REFERENCE'S OWN CODE: tools/make_reference_goldens.py::grad_fixture executes the
+reference's bflow_jax_maf.py (make_conditional_autoregressive_nn / inverse_fn / make_normalizing_flow log_prob, its bytes)
+with torch standing in for jax.numpy and lets torch.autograd play jax.grad; the resulting d(sum lp)/d(W, b) and d lp/dx are
+committed as tests/golden/ref_twin_grad_*.npz, and tests/test_grad.py requires this oracle to reproduce them to 1e-8 (and
+its forward values to equal the reference-executed ref_twin_*.npz and oracle/flow_oracle.py); central finite differences
+of the pinned forward are checked as well.
 """
 from __future__ import annotations
 

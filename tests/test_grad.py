@@ -27,6 +27,31 @@ def test_grad_oracle_forward_matches_reference_outputs(name):
     np.testing.assert_allclose(lp, g["lp"], rtol=1e-9, atol=1e-9)
 
 
+REF_GRAD = ["ref_twin_maf_cond_3d", "ref_twin_maf_cond_6d", "ref_twin_maf_bcast_ctx_2d"]
+
+
+def load_ref_grad(name):
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name.replace("ref_twin_", "ref_twin_grad_") + ".npz"))
+
+
+@pytest.mark.parametrize("name", REF_GRAD)
+def test_grad_oracle_matches_autodiff_of_the_reference_code(name):
+    """tests/golden/ref_twin_grad_*.npz = reverse-mode derivatives of the REFERENCE's own log_prob (its bytes executed with
+    torch standing in for jax.numpy, tools/make_reference_goldens.py::grad_fixture): the gradient oracle must reproduce them"""
+    spec, params, g = load_ref_twin(name)
+    gr = load_ref_grad(name)
+    masks = [[g[f"mask_{l}_{j}"] for j in range(len(spec.hidden) + 1)] for l in range(spec.L)]
+    ctx = g["ctx"] if spec.C else None
+    val, gW, gb, dx, _ = go.value_and_grad(to64(params), masks, spec.perms, g["x"], ctx, want_dx=True)
+    assert abs(val - float(gr["sum_lp"])) < 1e-9 * max(1.0, abs(val))
+    for l in range(spec.L):
+        for j in range(len(spec.hidden) + 1):
+            np.testing.assert_allclose(gW[l][j], gr[f"gW_{l}_{j}"], rtol=1e-8, atol=1e-9)
+            np.testing.assert_allclose(gb[l][j], gr[f"gb_{l}_{j}"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(dx, gr["dx"], rtol=1e-8, atol=1e-9)
+
+
 def test_grad_oracle_matches_flow_oracle_and_finite_differences():
     spec, draws, _, rng = make_case("maf", 3, 2, [12, 12], 2, 1, seed=5)
     p = to64(_single(draws, 0))
@@ -192,3 +217,23 @@ def test_inverse_grad_directional_derivative_at_bench_size():
     assert used == "tcgen05"
     fd = (vp - vm) / (2 * eps)
     assert np.all(np.abs(fd - norm) <= 3e-2 * norm), (fd, norm, eps)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", REF_GRAD)
+def test_cuda_gradient_matches_autodiff_of_the_reference_code(name):
+    """nazb_inverse_grad against the derivatives of the reference's own code (ref_twin_grad_*.npz)"""
+    from helpers import engine_for
+    spec, params, g = load_ref_twin(name)
+    gr = load_ref_grad(name)
+    draws = [[(W[None], b[None]) for (W, b) in layer] for layer in params]
+    eng = engine_for(spec, draws, engine="simt")
+    ctx = torch.from_numpy(g["ctx"]) if spec.C else None
+    r = eng.inverse_grad(torch.from_numpy(g["x"]), ctx, want_dx=True)
+    torch.cuda.synchronize()
+    assert abs(float(r["sum_n"][0]) - float(gr["sum_lp"])) < 1e-4 * max(1.0, abs(float(gr["sum_lp"])))
+    for l in range(spec.L):
+        for j in range(len(spec.hidden) + 1):
+            assert _rel(r["gW"][l][j][0].cpu().numpy(), gr[f"gW_{l}_{j}"]) < 2e-4, (l, j, "W")
+            assert _rel(r["gb"][l][j][0].cpu().numpy(), gr[f"gb_{l}_{j}"]) < 2e-4, (l, j, "b")
+    assert _rel(r["dx"][0].cpu().numpy(), gr["dx"]) < 2e-4

@@ -240,7 +240,124 @@ def truncnorm_fixture(out_dir=None):
     print("ref_truncnorm", os.path.getsize(os.path.join(out_dir, "ref_truncnorm.npz")))
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# Gradient fixtures: the reference differentiates its OWN log_prob with jax.grad / jax.value_and_grad
+# (bflow_jax_maf.py:233-246, :277-287).  Here the same bytes run with torch standing in for jax.numpy (float64), and
+# torch.autograd plays jax.grad: the gradients are reverse-mode derivatives of the reference's code, not of a restatement.
+# ----------------------------------------------------------------------------------------------------------------------
+def make_torch_shim():
+    import torch
+
+    class JT(torch.Tensor):
+        """torch tensor carrying jax's functional update  a.at[idx].set(v)  (out-of-place, differentiable)."""
+
+        class _At:
+            def __init__(self, a):
+                self.a = a
+
+            def __getitem__(self, idx):
+                a = self.a
+
+                class _Set:
+                    def set(self_inner, v):
+                        out = a.clone()
+                        out[idx] = v
+                        return out
+
+                return _Set()
+
+        @property
+        def at(self):
+            return JT._At(self)
+
+    def T(a):
+        if isinstance(a, torch.Tensor):
+            return a.as_subclass(JT)
+        return torch.as_tensor(np.asarray(a)).as_subclass(JT)
+
+    jnp = types.ModuleType("jax.numpy")
+    jnp.pi = np.pi
+    jnp.ndarray = torch.Tensor
+    jnp.array = lambda a, dtype=None: T(a)
+    jnp.broadcast_to = lambda a, shape: T(a).expand(*shape)
+    jnp.concatenate = lambda xs, axis=0: torch.cat([T(x) for x in xs], dim=axis)
+    jnp.dot = lambda a, b: T(a) @ T(b)
+    jnp.exp = lambda a: torch.exp(T(a))
+    jnp.log = lambda a: torch.log(torch.as_tensor(a, dtype=torch.float64))
+    jnp.clip = lambda a, lo, hi: torch.clamp(T(a), lo, hi)
+    jnp.squeeze = lambda a: torch.squeeze(T(a))
+    jnp.zeros_like = lambda a: torch.zeros_like(T(a)).as_subclass(JT)
+    jnp.sum = lambda a, axis=None: T(a).sum() if axis is None else T(a).sum(dim=axis)
+    jnp.split = lambda a, n, axis=0: torch.chunk(T(a), n, dim=axis)
+    jnp.cumsum = lambda a: np.cumsum(np.asarray(a))          # construction-time integer bookkeeping only
+    jnp.ones = lambda n: torch.ones(n, dtype=torch.float64).as_subclass(JT)
+    jax = types.ModuleType("jax")
+    jax.numpy = jnp
+    jax.jit = lambda f=None, **kw: f if f is not None else (lambda g: g)
+    nn = types.ModuleType("jax.nn")
+    nn.tanh = lambda a: torch.tanh(T(a))
+    nn.sigmoid = lambda a: torch.sigmoid(T(a))
+    nn.softplus = lambda a: torch.nn.functional.softplus(T(a))
+    jax.nn = nn
+    rnd = types.ModuleType("jax.random")
+    rnd.PRNGKey = lambda s: s
+    jax.random = rnd
+    jax.value_and_grad = lambda f, **k: f
+    jax.lax = types.ModuleType("jax.lax")
+    fu = types.ModuleType("jax.flatten_util")
+    fu.ravel_pytree = lambda t: (None, None)
+    jax.flatten_util = fu
+    mods = make_shim()                                        # the empty stubs of everything the module merely imports
+    mods.update({"jax": jax, "jax.numpy": jnp, "jax.nn": nn, "jax.random": rnd, "jax.lax": jax.lax, "jax.flatten_util": fu})
+    return mods, T
+
+
+def grad_fixture(out_dir=None):
+    """tests/golden/ref_twin_grad_*.npz: d(sum_n lp)/d(W, b) and d lp / d x of the reference's own make_normalizing_flow
+    log_prob, at the parameters / points of the committed ref_twin_* fixtures (which also pins the value: the lp this run
+    computes must equal the lp stored there by the numpy-backed run)."""
+    import torch
+    out_dir = out_dir or os.path.join(ROOT, "tests", "golden")
+    mods, T = make_torch_shim()
+    saved = {k: sys.modules.get(k) for k in mods}
+    sys.modules.update(mods)
+    try:
+        spec = importlib.util.spec_from_file_location("naz.flows.bflow_jax_maf", REF)
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    for name in ("ref_twin_maf_cond_3d", "ref_twin_maf_cond_6d", "ref_twin_maf_bcast_ctx_2d"):
+        g = np.load(os.path.join(out_dir, name + ".npz"))
+        D, C, L = int(g["D"]), int(g["C"]), int(g["L"])
+        hidden = [int(h) for h in g["hidden"]]
+        nn_fn, _, _ = ref.make_conditional_autoregressive_nn(D, C, hidden)
+        transform = ref.make_masked_affine_autoregressive_transform(nn_fn, D)
+        n_lin = len(hidden) + 1
+        masks = [[T(g[f"mask_{l}_{j}"].astype(np.float64)) for j in range(n_lin)] for l in range(L)]
+        params = [[(T(g[f"W_{l}_{j}"].astype(np.float64)).requires_grad_(True), T(g[f"b_{l}_{j}"].astype(np.float64)).requires_grad_(True))
+                   for j in range(n_lin)] for l in range(L)]
+        x = T(g["x"].astype(np.float64)).requires_grad_(True)
+        ctx = T(g["ctx"].astype(np.float64)) if C else None
+        flow = ref.make_normalizing_flow(transform, x, masks, [None] * L, [np.asarray(p) for p in g["perms"]], bounds=None, context=ctx)
+        lp = flow["lp"](params)
+        assert np.allclose(lp.detach().numpy(), g["lp"], rtol=1e-12, atol=1e-12), "torch-backed run must reproduce the stored lp"
+        lp.sum().backward()
+        arrs = {"sum_lp": float(lp.detach().sum()), "dx": x.grad.numpy()}
+        for l in range(L):
+            for j in range(n_lin):
+                arrs[f"gW_{l}_{j}"] = params[l][j][0].grad.numpy()
+                arrs[f"gb_{l}_{j}"] = params[l][j][1].grad.numpy()
+        np.savez_compressed(os.path.join(out_dir, name.replace("ref_twin_", "ref_twin_grad_") + ".npz"), **arrs)
+        print(name, "grad", arrs["sum_lp"], os.path.getsize(os.path.join(out_dir, name.replace("ref_twin_", "ref_twin_grad_") + ".npz")))
+
+
 if __name__ == "__main__":
     main()
     stats_fixture()
     truncnorm_fixture()
+    grad_fixture()
