@@ -11,8 +11,8 @@
 //            The layer is the implicit relation  x = (y - mu(x)) exp(-s(x)),  lp = G(x) - sum_d s_d(x), so with
 //            g = dG/dx the adjoint lambda solves  lambda = g + J^T c(lambda),
 //                 c_mu = -exp(-s) * lambda,   c_s = -(1 + x * lambda) * [lo <= s_raw <= hi],
-//            where J is the conditioner's Jacobian, strictly triangular in permutation order: D-1 fixed-point sweeps
-//            (each one back-propagation to the input) make every rank exact.  A last back-propagation with the final
+//            where J is the conditioner's Jacobian, strictly triangular in permutation order: D-1 sweeps (each one
+//            back-propagation to the input, restricted to the MADE blocks above the rank it finalises) make every rank exact.  A last back-propagation with the final
 //            c accumulates  dW_j += h_{j-1} (x) delta_j,  db_j += delta_j  over the tile and adds them to the caller's
 //            gradient arrays (reference layout [out][in], masked entries untouched) with fp32 atomics;
 //            g <- lambda * exp(-s) is handed to the next layer.
@@ -272,6 +272,34 @@ __global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_affine_
           cbuf[(r * 2 + 1) * P + p] = valid ? -(1.f + xin[(C + d) * P + p] * lm) * msk[r * P + p] : 0.f;
         }
         __syncthreads();
+        if (!last && g.inv_mode == NAZB_INV_INCREMENTAL) {
+          // Sweep `it` only has to make rank t = D-2-it exact, from the ranks above it: x of rank t reaches the outputs
+          // of ranks > t through the hidden units of blocks > t only (block b = units that depend on ranks < b), so the
+          // back-propagation is restricted to output columns >= 2 (t+1) and hidden units >= blk[.][t+1].
+          const int t = D - 2 - it, r1 = t + 1, dt = perm[t];
+          const float* src = cbuf + (size_t)(r1 * 2) * P;
+          int ksrc = g.md - r1 * 2, woff = r1 * 2;
+          for (int j = nh; j >= 1 && ksrc > 0; --j) {
+            float* dst = ((nh - j) & 1) ? dB : dA;
+            const int c0 = g.blk[j - 1][r1];
+            if (c0 < g.kdim[j]) {
+              gemm_panel_ms<P, false, TN, NST>(src, ksrc, wlT + gg.offT[j] + (size_t)woff * gg.ldk[j], gg.ldk[j], zb, c0, g.kdim[j],
+                                               dst, wbuf);
+              const float* hj = hbuf + (size_t)(j - 1) * g.hmax * P;
+              for (int i = tid + c0 * P; i < g.kdim[j] * P; i += kThreads) { float hv = hj[i]; dst[i] *= (1.f - hv * hv); }
+              __syncthreads();
+            }
+            src = dst + (size_t)c0 * P;
+            ksrc = g.kdim[j] - c0;
+            woff = c0;
+          }
+          if (ksrc > 0) {
+            gemm_panel_ms<P, false, TN, NST>(src, ksrc, wlT + gg.offT[0] + (size_t)woff * gg.ldk[0], gg.ldk[0], zb, 0, g.kin, dxb, wbuf);
+            if (tid < P) lam[dt * P + tid] = gcur[dt * P + tid] + dxb[(C + dt) * P + tid];
+          }
+          __syncthreads();
+          continue;
+        }
         const int to = l * n_lin + nh;
         if (last)
           outer_acc<P>(hbuf + (size_t)(nh - 1) * g.hmax * P, g.kdim[nh], cbuf, g.md, ga.mask[to],
