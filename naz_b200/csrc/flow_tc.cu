@@ -1241,7 +1241,10 @@ cudaError_t nazb_tc_launch(const nazb_handle* h, const IoArgs& io, int n_groups,
     kp.off_ax = P.j_ax; kp.off_xring = P.j_xring; kp.xslot_bytes = P.xslot_bytes;
     const int n_tiles = (io.N + kTileM - 1) / kTileM;
     const int grid = (int)std::min<long long>((long long)n_tiles * n_groups, h->sm_count);
-    auto kern = g_tc_dbg ? flow_tc_inv3_kernel<true> : flow_tc_inv3_kernel<false>;
+    const int mode = (g.kind == NAZB_KIND_AFFINE) ? 0 : (g.kind == NAZB_KIND_RQS && g.K == 8) ? 1 : 2;
+    auto kern = flow_tc_inv3_kernel<false, 2>;
+    if (mode == 0) kern = g_tc_dbg ? flow_tc_inv3_kernel<true, 0> : flow_tc_inv3_kernel<false, 0>;
+    else if (mode == 1) kern = g_tc_dbg ? flow_tc_inv3_kernel<true, 1> : flow_tc_inv3_kernel<false, 1>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.j_smem_bytes);
     if (e != cudaSuccess) return e;
     kern<<<grid, kV3Threads, P.j_smem_bytes, st>>>(kp, io, n_groups);
