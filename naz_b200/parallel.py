@@ -4,8 +4,8 @@ an all-gather of the per-rank (max, sum-exp) partials for the per-point posterio
 per-draw sums for importance weights.  Raw [S,N] / [S,N,D] outputs stay sharded.
 
 The gradient path shards the other way: the chains are few and every chain sums over the whole data set,
-so rank g takes a contiguous slice of the POINTS, every rank holds all chains, and one all-reduce(SUM) of the flattened
-gradient + value buffer finishes the step (the reference's jax.grad over `jnp.sum(lp)`, bflow_jax_maf.py:233-235)."""
+so rank g takes a contiguous slice of the POINTS, every rank holds all chains, and an all-reduce(SUM) of the flattened
+gradient buffer (plus the [S] values) finishes the step (the reference's jax.grad over `jnp.sum(lp)`, bflow_jax_maf.py:233-235)."""
 from __future__ import annotations
 
 import math
@@ -82,25 +82,23 @@ def point_range(N: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 def all_reduce_value_and_grads(sum_n: torch.Tensor, gW, gb, group=None):
-    """Sum the per-rank partial values [S] and gradients ([L][n_lin] of [S,out,in] / [S,out]) over the ranks with ONE
-    all-reduce of a flat buffer; returns (sum_n, gW, gb) holding the totals (views into the reduced buffer)."""
+    """Sum the per-rank partial values [S] (float64) and gradients ([L][n_lin] of [S,out,in] / [S,out], fp32) over the
+    ranks: one all-reduce of the flat fp32 gradient buffer plus one of the [S] values (kept in float64); returns
+    (sum_n, gW, gb) holding the totals, the gradients as views into the reduced buffer."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return sum_n, gW, gb
-    leaves = [sum_n] + [t for layer in gW for t in layer] + [t for layer in gb for t in layer]
-    flat = torch.cat([t.reshape(-1) for t in leaves[1:]])
+    leaves = [t for layer in gW for t in layer] + [t for layer in gb for t in layer]
+    flat = torch.cat([t.reshape(-1) for t in leaves])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     val = sum_n.clone()
-    dist.all_reduce(val, op=dist.ReduceOp.SUM, group=group)     # float64 [S]: kept apart from the fp32 gradient buffer
-    out, off = [], 0
-    for t in leaves[1:]:
-        n = t.numel()
-        out.append(flat[off:off + n].view_as(t))
-        off += n
-    nW = sum(len(layer) for layer in gW)
-    it = iter(out[:nW])
+    dist.all_reduce(val, op=dist.ReduceOp.SUM, group=group)
+    views, off = [], 0
+    for t in leaves:
+        views.append(flat[off:off + t.numel()].view_as(t))
+        off += t.numel()
+    it = iter(views)
     gW2 = [[next(it) for _ in layer] for layer in gW]
-    it = iter(out[nW:])
     gb2 = [[next(it) for _ in layer] for layer in gb]
     return val, gW2, gb2
 
