@@ -308,7 +308,18 @@ class FlowEngine:
         N = x.shape[0]
         out = {}
         if N == 0:
-            raise ValueError("empty batch")
+            # an empty batch is legal upstream (pyro / jnp return empty arrays); nothing to launch
+            if want_z:
+                out["z"] = torch.empty((s_count, 0, sh.D), device=self.device, dtype=torch.float32)
+            if want_lp:
+                out["lp"] = torch.empty((s_count, 0), device=self.device, dtype=torch.float32)
+            if want_lse:
+                G = n_groups if n_groups else 1
+                out["lse_max"] = torch.empty((G, 0), device=self.device, dtype=torch.float32)
+                out["lse_sum"] = torch.empty((G, 0), device=self.device, dtype=torch.float32)
+            if want_sum:
+                out["sum_n"] = torch.zeros((s_count,), device=self.device, dtype=torch.float64)
+            return out
         z = torch.empty((s_count, N, sh.D), device=self.device, dtype=torch.float32) if want_z else None
         lp = torch.empty((s_count, N), device=self.device, dtype=torch.float32) if want_lp else None
         lmax = lsum = None
@@ -352,10 +363,10 @@ class FlowEngine:
         if z.shape[-1] != sh.D or (not shared and (z.dim() != 3 or z.shape[0] != s_count)):
             raise ValueError(f"z must be [N,{sh.D}] or [{s_count},N,{sh.D}]")
         N = z.shape[-2]
-        if N == 0:
-            raise ValueError("empty batch")
         x = torch.empty((s_count, N, sh.D), device=self.device, dtype=torch.float32)
         ld = torch.empty((s_count, N), device=self.device, dtype=torch.float32) if want_logdet else None
+        if N == 0:   # `flow.sample([0])` is legal upstream: empty result, nothing to launch
+            return (x, ld) if want_logdet else x
         rc = self._lib.nazb_forward(self._h, s_begin, s_count, z.data_ptr(), 1 if shared else 0, _ptr(c), rows, N,
                                     _ptr(lo), _ptr(hi), x.data_ptr(), _ptr(ld), self._stream())
         self._check(rc, "nazb_forward")
@@ -377,8 +388,6 @@ class FlowEngine:
         if x.dim() != 2 or x.shape[1] != sh.D:
             raise ValueError(f"x must be [N,{sh.D}]")
         N = x.shape[0]
-        if N == 0:
-            raise ValueError("empty batch")
         L, n_lin = sh.L, len(sh.hidden) + 1
         dims = [sh.D + sh.C] + list(sh.hidden) + [sh.M * sh.D]
         masks = self._keepalive[2]
@@ -392,7 +401,7 @@ class FlowEngine:
         sum_n = torch.zeros((s_count,), device=self.device, dtype=torch.float64)
         dx = torch.empty((s_count, N, sh.D), device=self.device, dtype=torch.float32) if want_dx else None
         lp = torch.empty((s_count, N), device=self.device, dtype=torch.float32) if want_lp else None
-        rc = self._lib.nazb_inverse_grad(self._h, s_begin, s_count, x.data_ptr(), _ptr(c), rows, N, _ptr(lo), _ptr(hi),
+        rc = 0 if N == 0 else self._lib.nazb_inverse_grad(self._h, s_begin, s_count, x.data_ptr(), _ptr(c), rows, N, _ptr(lo), _ptr(hi),
                                          VP(*[m.data_ptr() for m in masks]), VP(*[t.data_ptr() for t in gW]),
                                          VP(*[t.data_ptr() for t in gb]),
                                          I64(*[dims[i % n_lin + 1] * dims[i % n_lin] for i in range(n)]),
@@ -412,6 +421,8 @@ class FlowEngine:
     def lse_finish(self, lse_max: torch.Tensor, lse_sum: torch.Tensor, log_norm: float) -> torch.Tensor:
         G, N = lse_max.shape
         out = torch.empty((N,), device=self.device, dtype=torch.float32)
+        if N == 0:
+            return out
         rc = self._lib.nazb_lse_finish(lse_max.data_ptr(), lse_sum.data_ptr(), G, N, float(log_norm), out.data_ptr(),
                                        self._stream())
         self._check(rc, "nazb_lse_finish")

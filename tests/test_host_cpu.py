@@ -221,3 +221,31 @@ def test_point_sharded_gradient_allreduce_world2_gloo():
     ret = mgr.dict()
     mp.spawn(_gloo_grad_worker, args=(world, _free_port(), 37, ret), nprocs=world, join=True)
     assert all(ret[r] for r in range(world))
+
+
+def test_empty_batch_returns_empty_results_without_touching_the_library():
+    """`flow.log_prob(x[0:0])` / `flow.sample([0])` are legal upstream (pyro / jnp return empty arrays).  The engine answers
+    them on the host: exercised here on a bare FlowEngine object (no handle, no CUDA) so any library call would fail."""
+    from naz_b200.engine import FlowEngine, FlowShape
+    eng = object.__new__(FlowEngine)
+    eng.shape = FlowShape("maf", 3, 2, [8, 8], 2)
+    eng.S = 4
+    eng.device = torch.device("cpu")
+    eng._h = None
+    eng._lib = None
+    eng._keepalive = ([], [], [torch.ones(8, 5), torch.ones(8, 8), torch.ones(6, 8)] * 2, None, None)
+    x = torch.zeros((0, 3))
+    ctx = torch.zeros((0, 2))
+    out = eng.inverse(x, ctx, want_z=True, want_lp=True, want_lse=True, want_sum=True, n_groups=2)
+    assert out["z"].shape == (4, 0, 3) and out["lp"].shape == (4, 0)
+    assert out["lse_max"].shape == (2, 0) and out["lse_sum"].shape == (2, 0)
+    assert out["sum_n"].shape == (4,) and out["sum_n"].dtype == torch.float64 and float(out["sum_n"].abs().sum()) == 0.0
+    assert eng.lse_finish(out["lse_max"], out["lse_sum"], 0.0).shape == (0,)
+    xs, ld = eng.forward(torch.zeros((0, 3)), torch.zeros((2,)), want_logdet=True)
+    assert xs.shape == (4, 0, 3) and ld.shape == (4, 0)
+    assert eng.forward(torch.zeros((4, 0, 3)), torch.zeros((2,))).shape == (4, 0, 3)
+    g = eng.inverse_grad(x, ctx, want_dx=True, want_lp=True)
+    assert g["dx"].shape == (4, 0, 3) and g["lp"].shape == (4, 0) and float(g["sum_n"].abs().sum()) == 0.0
+    assert all(float(t.abs().sum()) == 0.0 for layer in g["gW"] + g["gb"] for t in layer)
+    assert g["gW"][1][2].shape == (4, 6, 8)
+    eng._h = None   # nothing to destroy
