@@ -305,8 +305,9 @@ def test_error_behaviour():
         eng.inverse(x, None)                                          # flow.py:75: condition required
     with pytest.raises(ValueError):
         eng.inverse(torch.zeros(8, 4), torch.zeros(2))
-    with pytest.raises(ValueError):
-        eng.inverse(torch.zeros(0, 3), torch.zeros(2))
+    empty = eng.inverse(torch.zeros(0, 3), torch.zeros(2), want_lp=True, want_sum=True)   # legal upstream: empty result
+    assert empty["lp"].shape == (2, 0) and float(empty["sum_n"].abs().sum()) == 0.0
+    assert eng.forward(torch.zeros(0, 3), torch.zeros(2)).shape == (2, 0, 3)
     e2 = FlowEngine(FlowShape("maf", 3, 2, [16, 16], 2), 2, device="cuda:0")
     with pytest.raises(_lib.NazbError, match="nazb_pack has not been called"):
         e2.inverse(x, torch.zeros(2))
