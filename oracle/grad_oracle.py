@@ -79,3 +79,33 @@ def value_and_grad(params_np, masks_np, perms, x_np, ctx_np=None, bounds_np=None
     gW = [[W.grad.numpy() for (W, _) in layer] for layer in P]
     gb = [[b.grad.numpy() for (_, b) in layer] for layer in P]
     return float(tot.detach()), gW, gb, (x.grad.numpy() if want_dx else None), lp.detach().numpy()
+
+
+def value_and_grad_flow(spec, params_np, x_np, ctx_np=None, bounds_np=None):
+    """Gradient oracle for ANY flow kind the forward oracle covers (maf, nsa quadratic / linear): torch autograd (float64)
+    through the second restatement oracle/pyro_style.py (torch modules on torch.distributions.TransformedDistribution), i.e.
+    what the reference's torch path does in `train` (train_flows.py:195-213: loss = -flow.log_prob(...).mean(); backward()).
+    The spline branch of that restatement is UNPINNED (pyro-ppl is absent); this function is groundwork for the spline
+    backward kernel, checked in tests/ against finite differences and, for maf, against the pinned twin above.
+    -> (sum_n lp, gW [L][n_lin], gb [L][n_lin]) float64 numpy, ONE draw."""
+    from oracle import pyro_style as ps
+    torch.set_default_dtype(torch.float64)
+    try:
+        bounds = None if bounds_np is None else {"low": torch.tensor(np.asarray(bounds_np[0], np.float64)),
+                                                 "high": torch.tensor(np.asarray(bounds_np[1], np.float64))}
+        flow = ps.PyroStyleFlow(spec.kind, bounds, spec.D, spec.C, list(spec.hidden), spec.L, spec.count_bins, spec.order,
+                                permutations=spec.perms)
+        flow.set_from_pytree([[(np.asarray(W, np.float64), np.asarray(b, np.float64)) for (W, b) in layer] for layer in params_np])
+        x = torch.tensor(np.asarray(x_np, np.float64))
+        ctx = None
+        if ctx_np is not None:
+            ctx = torch.tensor(np.asarray(ctx_np, np.float64))
+            if ctx.dim() == 1:
+                ctx = ctx.unsqueeze(0).expand(x.shape[0], -1)
+        tot = flow.log_prob(x, ctx).sum()
+        tot.backward()
+        gW = [[lin.weight.grad.numpy().copy() for lin in arn.layers] for arn in flow.nets]
+        gb = [[lin.bias.grad.numpy().copy() for lin in arn.layers] for arn in flow.nets]
+        return float(tot.detach()), gW, gb
+    finally:
+        torch.set_default_dtype(torch.float32)

@@ -237,3 +237,43 @@ def test_cuda_gradient_matches_autodiff_of_the_reference_code(name):
             assert _rel(r["gW"][l][j][0].cpu().numpy(), gr[f"gW_{l}_{j}"]) < 2e-4, (l, j, "W")
             assert _rel(r["gb"][l][j][0].cpu().numpy(), gr[f"gb_{l}_{j}"]) < 2e-4, (l, j, "b")
     assert _rel(r["dx"][0].cpu().numpy(), gr["dx"]) < 2e-4
+
+
+def test_flow_level_grad_oracle_maf_equals_twin_and_spline_matches_finite_differences():
+    """value_and_grad_flow (autograd through the pyro-style restatement): equals the pinned twin oracle for maf; for the
+    spline flow (unpinned branch, groundwork for the spline backward kernel) it matches central finite differences of the
+    numpy forward oracle."""
+    spec, draws, _, rng = make_case("maf", 3, 2, [12, 12], 2, 1, seed=9)
+    p = to64(_single(draws, 0))
+    x = rng.normal(size=(9, 3))
+    ctx = rng.uniform(size=(9, 2))
+    v1, gW1, gb1, _, _ = go.value_and_grad(p, spec.masks(), spec.perms, x, ctx)
+    v2, gW2, gb2 = go.value_and_grad_flow(spec, p, x, ctx)
+    assert abs(v1 - v2) < 1e-9 * max(1.0, abs(v1))
+    for l in range(spec.L):
+        for j in range(3):
+            np.testing.assert_allclose(gW2[l][j], gW1[l][j], rtol=1e-8, atol=1e-10)
+            np.testing.assert_allclose(gb2[l][j], gb1[l][j], rtol=1e-8, atol=1e-10)
+    spec, draws, _, rng = make_case("nsa", 2, 1, [10, 10], 2, 1, seed=10)
+    p = to64(_single(draws, 0))
+    x = rng.normal(size=(6, 2)) * 1.2
+    ctx = rng.uniform(size=(6, 1))
+    v, gW, gb = go.value_and_grad_flow(spec, p, x, ctx)
+
+    def f(pp):
+        return fo.log_prob_draws(spec, [[(W[None], b[None]) for (W, b) in layer] for layer in pp], x, ctx)[0][0].sum()
+
+    assert abs(f(p) - v) < 1e-8 * max(1.0, abs(v))
+    masks = spec.masks()
+    eps, checked = 1e-6, 0
+    for (l, j) in [(0, 0), (1, 1), (0, 2), (1, 2)]:
+        idxs = np.argwhere(masks[l][j] != 0)
+        for idx in (tuple(idxs[0]), tuple(idxs[len(idxs) // 2]), tuple(idxs[-1])):
+            pp = [[(W.copy(), b.copy()) for (W, b) in layer] for layer in p]
+            pp[l][j][0][idx] += eps
+            up = f(pp)
+            pp[l][j][0][idx] -= 2 * eps
+            dn = f(pp)
+            assert abs((up - dn) / (2 * eps) - gW[l][j][idx]) < 2e-5 * max(1.0, abs(gW[l][j][idx])), (l, j, idx)
+            checked += 1
+    assert checked == 12
