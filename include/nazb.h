@@ -222,6 +222,16 @@ int nazb_histogramdd(const float* x, int32_t S, int64_t N, int32_t D, const doub
                      uint32_t* counts, float* density, void* stream);
 int nazb_hpd(const float* v, int32_t S, int64_t M, double alpha, float* lo, float* hi, void* stream);
 
+/* Engine options (tuning and A/B switches; this library never reads the environment).  Names, tcgen05 engine:
+ *   "inv_kernel"   4 (default) | 3 (round-1 kernel)          — needs a new nazb_pack
+ *   "inv_merge_n"  pushes with N <= value are issued unsplit  — needs a new nazb_pack
+ *   "inv_fold"     1 (default) fold a broadcast context (ctx_rows == 1) into per-draw constants inside nazb_inverse
+ *   "inv_gate"     1 (default) bound the drift of CTAs across draw groups (keeps the weight images L2-resident)
+ * nazb_get_option also answers "inv_fold_available" and "watchdog" (non-zero after a kernel aborted on a barrier time-out:
+ * site | warp << 8 | block << 16).  Unknown names return NAZB_ERR_BAD_ARG, the SIMT engine NAZB_ERR_UNSUPPORTED. */
+int nazb_set_option(nazb_handle* h, const char* name, int32_t value);
+int nazb_get_option(const nazb_handle* h, const char* name, int32_t* value);
+
 const char* nazb_strerror(int status);
 const char* nazb_last_cuda_error(const nazb_handle* h);
 

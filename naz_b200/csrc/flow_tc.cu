@@ -40,7 +40,8 @@ constexpr int kSlotBytes = 40960;
 constexpr int kFwdSlotBytes = 40960;   // pipelined forward kernels (20 KB slots measured 8-12 % slower: more sub-steps, waits and commits)
 constexpr int kTmemCols = 512;
 
-enum : uint8_t { EPI_NONE = 0, EPI_TANH = 1, EPI_XINV = 2, EPI_XFWD = 3, EPI_FIRST = 4 };
+enum : uint8_t { EPI_NONE = 0, EPI_TANH = 1, EPI_XINV = 2, EPI_XFWD = 3, EPI_FIRST = 4,
+                 EPI_XINV0C = 5 };   // v4 inverse: rank-0 inverse transform from context-folded (per-draw constant) parameters
 enum : uint8_t { A_IN = 0, A_H = 1, A_X = 2 };   // A_X: v3 inverse first-layer operand [ctx | x | 1]
 
 struct Step {
@@ -97,6 +98,14 @@ struct TcPlan {
   uint32_t j_xin = 0, j_lc = 0, j_a = 0, j_y = 0, j_xo = 0, j_misc = 0, j_scratch = 0, j_ring = 0;
   int j_nslots = 0;
   size_t j_smem_bytes = 0;
+  // v4 inverse kernel (flow_tc_inv4.cuh): steps[0] is its GENERAL program; steps_fold the context-folded one (same images)
+  int inv_ver = 4;
+  int mp_inv = 0;                 // output columns per rank in the inverse accumulators / images (v4: ceil8(M))
+  bool fold_ok = false;
+  std::vector<Step> steps_fold;
+  std::vector<Image> fold_images; // stage-0 push images (what inv4_fold_kernel contracts with the degree-0 activations)
+  int lc_w0x = 0, lc_w0c = 0, lc_r0c = 0, dp4 = 0, cp4 = 0;
+  uint32_t j_xr = 0;
 };
 
 struct TcState {
@@ -107,6 +116,16 @@ struct TcState {
   size_t draw_bytes[2] = {0, 0};
   float* lc_dev = nullptr;           // [S][L][lc_floats]
   float* lcf_dev = nullptr;          // forward layer constants [S][L][f_lc_floats]
+  float* lcfold_dev = nullptr;       // v4 inverse: context-folded layer constants [S][L][lc_floats] (rewritten per call)
+  int* grp_done = nullptr;           // v4 inverse: draw-group gate counters [65536]
+  unsigned int* wd_host = nullptr;   // watchdog word: mapped pinned host memory ...
+  unsigned int* wd_dev = nullptr;    // ... and its device alias
+  size_t cap_wimg[2] = {0, 0}, cap_lc = 0, cap_lcf = 0, cap_lcfold = 0, cap_tab = 0;
+  // options (nazb_set_option); recorded by bench.py
+  int opt_inv_kernel = 4;            // 3 = round-1 kernel, 4 = v4
+  int opt_fold = 1;                  // context fold when ctx_rows == 1
+  int opt_merge_n = 0;               // pushes with N <= merge_n are issued unsplit (critical + deferred columns in one MMA)
+  int opt_gate = 1;                  // draw-group gate for large N
 };
 
 constexpr int kMaxSteps = 80;
@@ -152,6 +171,7 @@ struct Builder {
   std::vector<Image>& images;
   uint32_t w_off = 0;
   int slot_bytes = kSlotBytes;
+  bool emit = true;   // false: only advance w_off / record the images (steps of a program variant that skips this gemm)
   void gemm(uint8_t a_buf, int a_chunk0, int k_ext, int n_ext, int d_col, int nsplit, int accumulate, Image im,
             Step epi, int n_crit = 0) {
     int k_sub_max = std::min(96, (slot_bytes / (n_ext * 4)) / 16 * 16);
@@ -177,7 +197,7 @@ struct Builder {
       sub.w_off = s.w_off; sub.w_bytes = s.w_bytes;
       sub.k_ext = ks; sub.k0 = im.k0 + k_off;
       sub.bias_col = (im.bias_col >= k_off && im.bias_col < k_off + ks) ? im.bias_col - k_off : -1;
-      steps.push_back(s);
+      if (emit) steps.push_back(s);
       images.push_back(sub);
       w_off += s.w_bytes;
     }
@@ -315,7 +335,7 @@ bool build_forward3(const FlowGeom& g, TcPlan& P) {
   P.f_smem_bytes = o + (size_t)P.f_nslots * kFwdSlotBytes;
   // two-tile variant: each tile owns half of TMEM (pre + transform parameters <= 256 columns)
   P.fwd4 = false;
-  if (P.hp_max + ceil_to(D * M, 16) <= kTmemCols / 2 && !(getenv("NAZB_FWD_ONE_TILE") && atoi(getenv("NAZB_FWD_ONE_TILE")))) {
+  if (P.hp_max + ceil_to(D * M, 16) <= kTmemCols / 2) {
     uint32_t q = 1024;
     P.g_ax = q;   q += 2u * 2u * 16u * kTileM * 2;
     P.g_a = q;    q += 2u * (uint32_t)P.hp_max * kTileM * 2;
@@ -344,46 +364,76 @@ bool build_forward3(const FlowGeom& g, TcPlan& P) {
   return true;
 }
 
-// Inverse program, v2.  Per flow layer, stage r = 0..D-1 (finalises the dimension of rank r):
-//   FIRST(r)   fp32 CUDA-core first layer for the hidden units of degree r (K = C + D is tiny), tanh, -> A operand
+// Inverse program.  Per flow layer, stage r = 0..D-1 (finalises the dimension of rank r):
+//   FIRST(r)   first conditioner layer for the hidden units of degree r -> A operand.  v3: K = 16 MMA over [ctx | x | 1]
+//              (or CUDA cores when that slice does not fit); v4: always CUDA cores, by every epilogue warp of the chain
 //   PUSH j->j+1 for j = 0..nh-2: pre_{j+1}[cols >= block r] += h_j[block r] . W^T  (tcgen05), epilogue tanh(block r of j+1)
 //   PUSH nh-1 -> out: out[ranks >= r] += h_last[block r] . Wout^T, epilogue = inverse transform of rank r
 // Biases are added in the epilogues from the layer-constants block, so accumulators need no init pass: the first
 // push into each accumulator (stage 0, or stage 1 for unconditional flows) covers its full width with accumulate = 0.
-bool build_inverse(const FlowGeom& g, TcPlan& P) {
+// variant 0: v3 program;  1: v4 general program;  2: v4 context-folded program (stage 0 is constant per draw: its steps
+// are replaced by one XINV0C epilogue, its images stay where they are and feed inv4_fold_kernel).
+bool build_inverse(const FlowGeom& g, TcPlan& P, int variant, int merge_n, std::vector<Step>& steps_out,
+                   std::vector<Image>& images_out, std::vector<Image>* fold_images) {
   if (g.inv_mode != NAZB_INV_INCREMENTAL) return false;
-  const int nh = g.n_hidden, D = g.D, Mp = P.mp;
-  if (D * Mp > 256 || g.kin > 16) return false;
+  const bool v4 = variant != 0, folded = variant == 2;
+  const int nh = g.n_hidden, D = g.D;
+  const int Mp = v4 ? ceil_to(g.M, 8) : P.mp;
+  P.mp_inv = Mp;
+  // v3 feeds [ctx | x | 1] to a K = 16 MMA slice; v4 computes the first layer on CUDA cores from rank-ordered columns
+  if (D * Mp > 256 || (!v4 && g.kin > 16) || D > 16) return false;
   auto hp = [&](int j) { return ceil_to(g.hidden[j], 16); };
+  auto hp8 = [&](int j) { return v4 ? ceil_to(g.hidden[j], 8) : hp(j); };   // last column a push has to reach
   int col = 0;
   int T_PRE[NAZB_MAX_HIDDEN_LAYERS] = {0};
   for (int j = 1; j < nh; ++j) { T_PRE[j] = col; col += hp(j); }
   const int T_OUT = col; col += D * Mp;
   if (col > kTmemCols) return false;
-  // first conditioner layer on tensor cores when TMEM has room for the transient block of pre-activations and
-  // [ctx | x | 1] fits one K = 16 slice; otherwise it runs on CUDA cores from the layer constants
   int xw = 0;
   for (int r = 0; r < D; ++r) xw = std::max(xw, ceil_to(g.blk[0][r + 1], 8) - (g.blk[0][r] & ~7));
   const int T_PRE1 = col;
-  P.xf = (g.kin + 1 <= 16) && (xw <= 128) && (col + ceil_to(xw, 16) <= kTmemCols);
-  if (const char* env = getenv("NAZB_NO_XF")) if (atoi(env)) P.xf = false;
-  P.xslot_bytes = ceil_to(xw * 16 * 4, 1024);
-  // layer constants: [W0 * c (Hp0 x kinp; CUDA-core first layer only) | b_0 * c .. b_{nh-1} * c | b_out], c = 2 log2 e
-  P.kinp = ceil_to(g.kin, 4);
-  int off = P.xf ? 0 : hp(0) * P.kinp;
-  for (int j = 0; j < nh; ++j) { P.lc_b[j] = off; off += hp(j); }
-  P.lc_bout = off; off += D * Mp;
-  P.lc_floats = ceil_to(off, 4);
+  if (!v4) {
+    // first conditioner layer on tensor cores when TMEM has room for the transient block of pre-activations and
+    // [ctx | x | 1] fits one K = 16 slice; otherwise it runs on CUDA cores from the layer constants
+    P.xf = (g.kin + 1 <= 16) && (xw <= 128) && (col + ceil_to(xw, 16) <= kTmemCols);
+    P.xslot_bytes = ceil_to(xw * 16 * 4, 1024);
+    // layer constants: [W0 * c (Hp0 x kinp; CUDA-core first layer only) | b_0 * c .. b_{nh-1} * c | b_out], c = 2 log2 e
+    P.kinp = ceil_to(g.kin, 4);
+    int off = P.xf ? 0 : hp(0) * P.kinp;
+    for (int j = 0; j < nh; ++j) { P.lc_b[j] = off; off += hp(j); }
+    P.lc_bout = off; off += D * Mp;
+    P.lc_floats = ceil_to(off, 4);
+  } else {
+    // v4 layer constants: [W0x * c (Hp0 x dp4, x columns BY RANK) | W0c * c (Hp0 x cp4, context columns) |
+    //                      b_0 * c .. b_{nh-1} * c | b_out (D x Mp rank-major) | rank-0 constants (32 floats; folded copy only)]
+    P.xf = false;
+    P.dp4 = ceil_to(D, 4);
+    P.cp4 = g.C > 0 ? ceil_to(g.C, 4) : 0;
+    int off = 0;
+    P.lc_w0x = off; off += hp(0) * P.dp4;
+    P.lc_w0c = off; off += hp(0) * P.cp4;
+    for (int j = 0; j < nh; ++j) { P.lc_b[j] = off; off += hp(j); }
+    P.lc_bout = off; off += ceil_to(D * Mp, 4);
+    P.lc_r0c = off; off += 32;
+    P.lc_floats = ceil_to(off, 4);
+  }
   for (int r = 0; r < D; ++r) {
     bool empty0 = (g.blk[0][r + 1] == g.blk[0][r]);
     for (int j = 1; j < nh; ++j)
       if ((g.blk[j][r + 1] == g.blk[j][r]) != empty0) return false;   // blocks must be (non)empty together
   }
-  Builder b{P.steps[0], P.images[0]};
+  if (folded) {
+    // needs a context, a non-empty degree-0 block and a transform whose rank-0 parameters fold into a small table
+    if (g.C == 0 || g.blk[0][1] == g.blk[0][0]) return false;
+    if (!(g.kind == NAZB_KIND_AFFINE || (g.kind == NAZB_KIND_RQS && g.K == 8))) return false;
+  }
+  Builder b{steps_out, images_out};
   bool first_push[NAZB_MAX_LIN];
   for (int j = 0; j <= nh; ++j) first_push[j] = true;
   for (int r = 0; r < D; ++r) {
     int b0 = g.blk[0][r], b1 = g.blk[0][r + 1];
+    const bool skip = folded && r == 0;   // stage 0 of the folded program: constant, evaluated by inv4_fold_kernel
+    b.emit = !skip;
     if (b1 == b0) {
       Step e = mk_epi(EPI_XINV, T_OUT + r * Mp, 0, 0, r);
       e.flags = 1; e.e_aux = (uint16_t)(P.lc_bout + r * Mp);
@@ -394,7 +444,7 @@ bool build_inverse(const FlowGeom& g, TcPlan& P) {
       int ec0 = b0 & ~7, ec1 = ceil_to(b1, 8);
       Step e = mk_epi(EPI_FIRST, 0, ec1 - ec0, 0, r);
       e.e_aux = (uint16_t)ec0;
-      b.epi_only(e);
+      if (!skip) b.epi_only(e);
       if (P.xf) {
         Step t = mk_epi(EPI_TANH, T_PRE1, ec1 - ec0, 0);
         t.flags = 4;
@@ -409,28 +459,39 @@ bool build_inverse(const FlowGeom& g, TcPlan& P) {
       int kr = ceil_to(sc1 - sc0, 16);
       if (kr > P.hp_max) return false;
       P.kr_max = std::max(P.kr_max, kr);
+      const size_t img0 = images_out.size();
       if (j + 1 < nh) {
         int tb0 = g.blk[j + 1][r], tb1 = g.blk[j + 1][r + 1];
         int tc0 = tb0 & ~7, tc1 = ceil_to(tb1, 8);
         int tn0 = tc0;                         // M = 64 MMAs take any N % 8 == 0
-        int n = hp(j + 1) - tn0;
-        if (first_push[j + 1] && tn0 != 0) return false;
+        int n = hp8(j + 1) - tn0;
+        if (first_push[j + 1] && tn0 != 0 && !(folded && r == 1)) return false;
         Step e = mk_epi(EPI_TANH, T_PRE[j + 1] + tc0, tc1 - tc0, 0);
         e.e_aux = (uint16_t)(P.lc_b[j + 1] + tc0);
+        int n_crit = tc1 - tc0;
+        if (v4 && n <= merge_n) n_crit = n;
         b.gemm(A_H, 0, kr, n, T_PRE[j + 1] + tn0, 3, first_push[j + 1] ? 0 : 1,
-               mk_img(j + 1, n, kr, 0, tn0, 0, 0, sc0, sb0, sb1, -1, 0), e, tc1 - tc0);
-        first_push[j + 1] = false;
+               mk_img(j + 1, n, kr, 0, tn0, 0, 0, sc0, sb0, sb1, -1, 0), e, n_crit);
+        if (!skip) first_push[j + 1] = false;
       } else {
         int n = (D - r) * Mp;
         Step e = mk_epi(EPI_XINV, T_OUT + r * Mp, 0, 0, r);
         e.e_aux = (uint16_t)(P.lc_bout + r * Mp);
-        b.gemm(A_H, 0, kr, n, T_OUT + r * Mp, 3, first_push[nh] ? 0 : 1, mk_img(nh, n, kr, 1, 0, r, D, sc0, sb0, sb1, -1, 0), e, Mp);
-        first_push[nh] = false;
+        int n_crit = Mp;
+        if (v4 && n <= merge_n) n_crit = n;
+        b.gemm(A_H, 0, kr, n, T_OUT + r * Mp, 3, first_push[nh] ? 0 : 1, mk_img(nh, n, kr, 1, 0, r, D, sc0, sb0, sb1, -1, 0), e, n_crit);
+        if (!skip) first_push[nh] = false;
       }
+      if (fold_images && r == 0)
+        for (size_t i = img0; i < images_out.size(); ++i) fold_images->push_back(images_out[i]);
+    }
+    if (skip) {
+      b.emit = true;
+      b.epi_only(mk_epi(EPI_XINV0C, 0, 0, 0, 0));
     }
   }
   P.layer_bytes[0] = b.w_off;
-  return (int)P.steps[0].size() <= kMaxSteps;
+  return (int)steps_out.size() <= kMaxSteps;
 }
 
 bool plan_smem(const FlowGeom& g, TcPlan& P) {
@@ -463,6 +524,27 @@ bool plan_smem_inv3(const FlowGeom& g, TcPlan& P) {
   P.j_xring = off;   off += P.xf ? 4u * (uint32_t)P.xslot_bytes : 0u;                  // kXSlots small-ring slots
   P.j_y = off;       off += (uint32_t)g.D * kTileM * 4;
   P.j_xo = off;      off += (uint32_t)g.D * kTileM * 4;
+  P.j_misc = off;    off += kTileM * 4;
+  P.j_scratch = off; off += (g.kind == NAZB_KIND_AFFINE || (g.kind == NAZB_KIND_RQS && g.K == 8)) ? 0 : 32u * kTileM * 4;
+  off = (off + 127) & ~127u;
+  P.j_ring = off;
+  const uint32_t cap = 227 * 1024;
+  if (off + 2 * kSlotBytes > cap) return false;
+  P.j_nslots = std::min(6u, (cap - off) / kSlotBytes);
+  P.j_smem_bytes = off + (size_t)P.j_nslots * kSlotBytes;
+  return true;
+}
+
+bool plan_smem_inv4(const FlowGeom& g, TcPlan& P) {
+  if (P.kr_max <= 0 || P.kr_max > 128) return false;      // <= kV4MaxSlices K slices per A block
+  uint32_t off = 1024;
+  P.j_xin = off;     off += (uint32_t)std::max(1, g.C) * kTileM * 4;
+  P.j_lc = off;      off += 2u * (uint32_t)P.lc_floats * 4;
+  off = (off + 127) & ~127u;
+  P.j_a = off;       off += 2u * 2u * (uint32_t)P.kr_max * (kTileM / 2) * 2 * 2;   // [chain][buffer][hi | lo]
+  P.j_y = off;       off += (uint32_t)g.D * kTileM * 4;
+  P.j_xo = off;      off += (uint32_t)g.D * kTileM * 4;
+  P.j_xr = off;      off += (uint32_t)g.D * kTileM * 4;
   P.j_misc = off;    off += kTileM * 4;
   P.j_scratch = off; off += (g.kind == NAZB_KIND_AFFINE || (g.kind == NAZB_KIND_RQS && g.K == 8)) ? 0 : 32u * kTileM * 4;
   off = (off + 127) & ~127u;
@@ -1053,6 +1135,60 @@ __global__ void tc_pack_lc_kernel(int S, int L, int n_lin, int D, int M, int Mp,
   }
 }
 
+// v4 inverse layer constants: [W0x * c (Hp0 x dp4, x columns by RANK) | W0c * c (Hp0 x cp4) | hidden biases * c |
+// output bias rank-major (stride Mp) | 32 spare floats (rank-0 constants, written by inv4_fold_kernel)]
+struct Lc4Geom {
+  int lc_w0x, lc_w0c, lc_b[NAZB_MAX_HIDDEN_LAYERS], lc_bout, lc_r0c, lc_floats;
+  int hdim[NAZB_MAX_HIDDEN_LAYERS], hp[NAZB_MAX_HIDDEN_LAYERS];
+  int dp4, cp4;
+};
+__global__ void tc_pack_lc4_kernel(int S, int L, int n_lin, int D, int C, int M, int Mp, float hscale, Lc4Geom lg,
+                                   const float* const* __restrict__ Wtab, const float* const* __restrict__ btab,
+                                   const float* const* __restrict__ mtab, const long long* __restrict__ wst,
+                                   const long long* __restrict__ bst, const int* __restrict__ perm, float* __restrict__ dst,
+                                   const float* const* __restrict__ bWtab, const float* const* __restrict__ bbtab, float dm_scale) {
+  const int kin = C + D, nh = n_lin - 1;
+  const long long total = (long long)S * L * lg.lc_floats;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int f = (int)(idx % lg.lc_floats);
+    int l = (int)((idx / lg.lc_floats) % L);
+    int s = (int)(idx / ((long long)lg.lc_floats * L));
+    float v = 0.f;
+    if (f < lg.lc_b[0]) {
+      // first-layer weights: x part (by rank) or context part
+      int n, k = -1;
+      if (f < lg.lc_w0c) { n = f / lg.dp4; int q = f % lg.dp4; if (q < D) k = C + perm[l * D + q]; }
+      else { int g2 = f - lg.lc_w0c; n = g2 / lg.cp4; int c = g2 % lg.cp4; if (c < C) k = c; }
+      if (n < lg.hdim[0] && k >= 0) {
+        int ti = l * n_lin;
+        float w = Wtab[ti][(size_t)s * wst[ti] + (size_t)n * kin + k];
+        if (bWtab) w = nazb_draw_map(bWtab[ti][(size_t)n * kin + k], w, dm_scale);
+        v = hscale * w * mtab[ti][(size_t)n * kin + k];
+      }
+    } else if (f < lg.lc_bout) {
+      int j = 0;
+      while (j + 1 < nh && f >= lg.lc_b[j + 1]) ++j;
+      int n = f - lg.lc_b[j];
+      if (n < lg.hdim[j]) {
+        int ti = l * n_lin + j;
+        float bv = btab[ti][(size_t)s * bst[ti] + n];
+        if (bbtab) bv = nazb_draw_map(bbtab[ti][n], bv, dm_scale);
+        v = hscale * bv;
+      }
+    } else if (f < lg.lc_bout + D * Mp) {
+      int n = f - lg.lc_bout, rank = n / Mp, m = n % Mp;
+      if (m < M) {
+        int ti = l * n_lin + (n_lin - 1);
+        const int o = m * D + perm[l * D + rank];
+        v = btab[ti][(size_t)s * bst[ti] + o];
+        if (bbtab) v = nazb_draw_map(bbtab[ti][o], v, dm_scale);
+      }
+    }
+    dst[idx] = v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Inverse kernel (flow_tc_inv3.cuh): two independent 64-row chains per 128-point tile.
 //
@@ -1066,6 +1202,7 @@ constexpr int kChains = 2;
 constexpr int kChainRows = kTileM / kChains;          // 64
 
 #include "flow_tc_inv3.cuh"
+#include "flow_tc_inv4.cuh"
 #include "flow_tc_fwd3.cuh"
 #include "flow_tc_fwd4.cuh"
 
@@ -1089,21 +1226,55 @@ bool nazb_tc_supported(const FlowGeom& g, std::string* why) {
 cudaError_t nazb_tc_create(nazb_handle* h) {
   TcState* t = new TcState();
   h->tc = t;
-  return cudaSuccess;
+  cudaError_t e = cudaMalloc(&t->grp_done, sizeof(int) * 65536);
+  if (e != cudaSuccess) return e;
+  // watchdog word in mapped pinned host memory: readable by the host even after a device-side trap
+  e = cudaHostAlloc(&t->wd_host, sizeof(unsigned int) * 4, cudaHostAllocMapped);
+  if (e != cudaSuccess) return e;
+  t->wd_host[0] = 0;
+  return cudaHostGetDevicePointer(&t->wd_dev, t->wd_host, 0);
 }
 
 void nazb_tc_destroy(nazb_handle* h) {
   TcState* t = static_cast<TcState*>(h->tc);
   if (!t) return;
-  for (int d = 0; d < 2; ++d) {
+  for (int d = 0; d < 2; ++d)
     if (t->wimg[d]) cudaFree(t->wimg[d]);
-    if (t->steps_dev[d]) cudaFree(t->steps_dev[d]);
-  }
   if (t->tab_dev) cudaFree(t->tab_dev);
   if (t->lc_dev) cudaFree(t->lc_dev);
   if (t->lcf_dev) cudaFree(t->lcf_dev);
+  if (t->lcfold_dev) cudaFree(t->lcfold_dev);
+  if (t->grp_done) cudaFree(t->grp_done);
+  if (t->wd_host) cudaFreeHost(t->wd_host);
   delete t;
   h->tc = nullptr;
+}
+
+// Options of the tcgen05 engine (nazb_set_option).  They replace the round-1 environment overrides: whatever is set is
+// visible through nazb_get_option and recorded by bench.py.
+int nazb_tc_set_option(nazb_handle* h, const char* name, int value) {
+  TcState* t = static_cast<TcState*>(h->tc);
+  if (!t) return NAZB_ERR_UNSUPPORTED;
+  if (!strcmp(name, "inv_kernel")) { if (value != 3 && value != 4) return NAZB_ERR_BAD_ARG; t->opt_inv_kernel = value; h->is_packed = false; return NAZB_OK; }
+  if (!strcmp(name, "inv_fold")) { t->opt_fold = value ? 1 : 0; return NAZB_OK; }
+  if (!strcmp(name, "inv_merge_n")) { if (value < 0 || value > 256) return NAZB_ERR_BAD_ARG; t->opt_merge_n = value; h->is_packed = false; return NAZB_OK; }
+  if (!strcmp(name, "inv_gate")) { t->opt_gate = value ? 1 : 0; return NAZB_OK; }
+  return NAZB_ERR_BAD_ARG;
+}
+int nazb_tc_get_option(const nazb_handle* h, const char* name, int* value) {
+  const TcState* t = static_cast<const TcState*>(h->tc);
+  if (!t) return NAZB_ERR_UNSUPPORTED;
+  if (!strcmp(name, "inv_kernel")) *value = t->opt_inv_kernel;
+  else if (!strcmp(name, "inv_fold")) *value = t->opt_fold;
+  else if (!strcmp(name, "inv_merge_n")) *value = t->opt_merge_n;
+  else if (!strcmp(name, "inv_gate")) *value = t->opt_gate;
+  else if (!strcmp(name, "inv_fold_available")) *value = (t->plan.ok[0] && t->plan.inv_ver == 4 && t->plan.fold_ok) ? 1 : 0;
+  else return NAZB_ERR_BAD_ARG;
+  return NAZB_OK;
+}
+unsigned int nazb_tc_watchdog(const nazb_handle* h) {
+  const TcState* t = static_cast<const TcState*>(h->tc);
+  return (t && t->wd_host) ? t->wd_host[0] : 0u;
 }
 
 int64_t nazb_tc_packed_bytes(const nazb_handle* h) {
@@ -1124,36 +1295,53 @@ bool nazb_tc_direction_ok(const nazb_handle* h, int dir) {
   return t && t->plan.ok[dir];
 }
 
+// grow-only device buffer: repacking with unchanged sizes (every MCMC / SVI step) allocates nothing, so it never
+// triggers the implicit device synchronisation of cudaFree / cudaMalloc
+template <class T>
+static cudaError_t ensure_cap(T** ptr, size_t* cap, size_t bytes) {
+  if (*ptr && *cap >= bytes) return cudaSuccess;
+  if (*ptr) { cudaFree(*ptr); *ptr = nullptr; *cap = 0; }
+  cudaError_t e = cudaMalloc(ptr, bytes);
+  if (e == cudaSuccess) *cap = bytes;
+  return e;
+}
+
 cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* const* b, const int64_t* wst,
                          const int64_t* bst, const float* const* mask, const float* keep, float p_drop,
                          cudaStream_t st, const DrawMap& dm) {
   TcState* t = static_cast<TcState*>(h->tc);
   const FlowGeom& g = h->geom;
   const int S = h->desc.S, L = g.L, n_lin = g.n_hidden + 1, ntab = L * n_lin;
+  t->plan.ok[0] = t->plan.ok[1] = false;   // stays false if anything below fails
   // (re)build the programs now that the MADE block structure is known
   TcPlan P;
   if (!base_dims(g, P) || !plan_smem(g, P)) return cudaErrorInvalidConfiguration;
-  P.fwd3 = !(getenv("NAZB_FWD_OLD") && atoi(getenv("NAZB_FWD_OLD"))) && build_forward3(g, P);
+  P.fwd3 = build_forward3(g, P);
   if (!P.fwd3) { P.steps[1].clear(); P.images[1].clear(); }
   P.ok[1] = P.fwd3 || build_forward(g, P);
-  P.ok[0] = build_inverse(g, P) && plan_smem_inv3(g, P);
-  if (!P.ok[0]) { P.steps[0].clear(); P.images[0].clear(); P.layer_bytes[0] = 0; }
+  P.inv_ver = t->opt_inv_kernel;
+  if (P.inv_ver == 4) {
+    P.ok[0] = build_inverse(g, P, 1, t->opt_merge_n, P.steps[0], P.images[0], &P.fold_images) && plan_smem_inv4(g, P);
+    if (P.ok[0]) {
+      std::vector<Image> scratch_images;
+      TcPlan Q = P;   // the folded variant must not disturb kr_max / layer_bytes of the general plan
+      P.fold_ok = build_inverse(g, Q, 2, t->opt_merge_n, P.steps_fold, scratch_images, nullptr) &&
+                  Q.layer_bytes[0] == P.layer_bytes[0] && (int)P.fold_images.size() <= kMaxFoldImgs;
+      if (!P.fold_ok) P.steps_fold.clear();
+    }
+  } else {
+    P.ok[0] = build_inverse(g, P, 0, 0, P.steps[0], P.images[0], nullptr) && plan_smem_inv3(g, P);
+  }
+  if (!P.ok[0]) { P.steps[0].clear(); P.images[0].clear(); P.layer_bytes[0] = 0; P.fold_ok = false; }
   if (!P.ok[1]) return cudaErrorInvalidConfiguration;
   cudaError_t e;
   for (int d = 0; d < 2; ++d) {
-    if (t->wimg[d]) { cudaFree(t->wimg[d]); t->wimg[d] = nullptr; }
-    if (t->steps_dev[d]) { cudaFree(t->steps_dev[d]); t->steps_dev[d] = nullptr; }
     t->draw_bytes[d] = 0;
     if (!P.ok[d]) continue;
     t->draw_bytes[d] = P.layer_bytes[d] * (size_t)L;
-    if ((e = cudaMalloc(&t->wimg[d], t->draw_bytes[d] * (size_t)S)) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&t->steps_dev[d], P.steps[d].size() * sizeof(Step))) != cudaSuccess) return e;
-    if ((e = cudaMemcpy(t->steps_dev[d], P.steps[d].data(), P.steps[d].size() * sizeof(Step), cudaMemcpyHostToDevice)) !=
-        cudaSuccess)
-      return e;
+    if ((e = ensure_cap(&t->wimg[d], &t->cap_wimg[d], t->draw_bytes[d] * (size_t)S)) != cudaSuccess) return e;
   }
-  // pointer / stride tables on the device
-  if (t->tab_dev) { cudaFree(t->tab_dev); t->tab_dev = nullptr; }
+  // pointer / stride tables on the device (pinned staging + async copy on the caller's stream: nazb_stage_upload)
   std::vector<const float*> tabs(5 * (size_t)ntab);
   std::vector<long long> strides(2 * (size_t)ntab);
   for (int i = 0; i < ntab; ++i) {
@@ -1163,19 +1351,19 @@ cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* con
   }
   const bool has_dm = dm.baseW != nullptr && dm.baseB != nullptr;
   size_t tab_bytes = tabs.size() * sizeof(float*) + strides.size() * sizeof(long long);
-  if ((e = cudaMalloc(&t->tab_dev, tab_bytes)) != cudaSuccess) return e;
-  if ((e = cudaMemcpy(t->tab_dev, tabs.data(), tabs.size() * sizeof(float*), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+  if ((e = ensure_cap(&t->tab_dev, &t->cap_tab, tab_bytes)) != cudaSuccess) return e;
+  if ((e = nazb_stage_upload(h, t->tab_dev, tabs.data(), tabs.size() * sizeof(float*), st)) != cudaSuccess) return e;
   long long* strides_dev = reinterpret_cast<long long*>(t->tab_dev + tabs.size());
-  if ((e = cudaMemcpy(strides_dev, strides.data(), strides.size() * sizeof(long long), cudaMemcpyHostToDevice)) != cudaSuccess)
-    return e;
+  if ((e = nazb_stage_upload(h, strides_dev, strides.data(), strides.size() * sizeof(long long), st)) != cudaSuccess) return e;
   int hk = 0;
   for (int j = 0; j < g.n_hidden; ++j) hk = std::max(hk, g.hidden[j]);
   for (int d = 0; d < 2; ++d) {
     if (!P.ok[d]) continue;
+    const int mp_d = (d == 0) ? P.mp_inv : P.mp;
     for (const Image& im : P.images[d]) {
       long long total = (long long)(im.k_ext / 8) * im.n_ext * L * S;
       int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
-      tc_pack_kernel<<<blocks, 256, 0, st>>>(im, S, L, n_lin, g.D, g.M, P.mp, g.kdim[im.lin], g.ndim[im.lin], t->tab_dev,
+      tc_pack_kernel<<<blocks, 256, 0, st>>>(im, S, L, n_lin, g.D, g.M, mp_d, g.kdim[im.lin], g.ndim[im.lin], t->tab_dev,
                                              t->tab_dev + ntab, t->tab_dev + 2 * ntab, strides_dev, strides_dev + ntab,
                                              h->perm_dev, keep, (long long)L * g.n_hidden * hk, (long long)g.n_hidden * hk,
                                              hk, 1.f / (1.f - p_drop), t->wimg[d], (unsigned long long)t->draw_bytes[d],
@@ -1184,22 +1372,34 @@ cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* con
       nazb_count_launch();
     }
   }
-  if (t->lc_dev) { cudaFree(t->lc_dev); t->lc_dev = nullptr; }
   if (P.ok[0]) {
-    if ((e = cudaMalloc(&t->lc_dev, sizeof(float) * (size_t)S * L * P.lc_floats)) != cudaSuccess) return e;
-    LcGeom lg{};
-    for (int j = 0; j < g.n_hidden; ++j) { lg.lc_b[j] = P.lc_b[j]; lg.hdim[j] = g.hidden[j]; }
+    const size_t lc_bytes = sizeof(float) * (size_t)S * L * P.lc_floats;
+    if ((e = ensure_cap(&t->lc_dev, &t->cap_lc, lc_bytes)) != cudaSuccess) return e;
     long long total = (long long)S * L * P.lc_floats;
     int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
-    tc_pack_lc_kernel<<<blocks, 256, 0, st>>>(S, L, n_lin, g.D, g.M, P.mp, g.kin, P.kinp, P.lc_b[0], g.hidden[0],
-                                              2.885390081777927f, P.lc_floats, lg, P.lc_bout, t->tab_dev, t->tab_dev + ntab, t->tab_dev + 2 * ntab,
-                                              strides_dev, strides_dev + ntab, h->perm_dev, t->lc_dev,
-                                              has_dm ? t->tab_dev + 3 * ntab : nullptr, has_dm ? t->tab_dev + 4 * ntab : nullptr, dm.scale);
-    nazb_count_launch();
+    if (P.inv_ver == 4) {
+      Lc4Geom lg{};
+      lg.lc_w0x = P.lc_w0x; lg.lc_w0c = P.lc_w0c; lg.lc_bout = P.lc_bout; lg.lc_r0c = P.lc_r0c; lg.lc_floats = P.lc_floats;
+      lg.dp4 = P.dp4; lg.cp4 = std::max(P.cp4, 1);
+      for (int j = 0; j < g.n_hidden; ++j) { lg.lc_b[j] = P.lc_b[j]; lg.hdim[j] = g.hidden[j]; lg.hp[j] = ceil_to(g.hidden[j], 16); }
+      tc_pack_lc4_kernel<<<blocks, 256, 0, st>>>(S, L, n_lin, g.D, g.C, g.M, P.mp_inv, 2.885390081777927f, lg, t->tab_dev,
+                                                 t->tab_dev + ntab, t->tab_dev + 2 * ntab, strides_dev, strides_dev + ntab,
+                                                 h->perm_dev, t->lc_dev, has_dm ? t->tab_dev + 3 * ntab : nullptr,
+                                                 has_dm ? t->tab_dev + 4 * ntab : nullptr, dm.scale);
+      nazb_count_launch();
+      if (P.fold_ok && (e = ensure_cap(&t->lcfold_dev, &t->cap_lcfold, lc_bytes)) != cudaSuccess) return e;
+    } else {
+      LcGeom lg{};
+      for (int j = 0; j < g.n_hidden; ++j) { lg.lc_b[j] = P.lc_b[j]; lg.hdim[j] = g.hidden[j]; }
+      tc_pack_lc_kernel<<<blocks, 256, 0, st>>>(S, L, n_lin, g.D, g.M, P.mp, g.kin, P.kinp, P.lc_b[0], g.hidden[0],
+                                                2.885390081777927f, P.lc_floats, lg, P.lc_bout, t->tab_dev, t->tab_dev + ntab, t->tab_dev + 2 * ntab,
+                                                strides_dev, strides_dev + ntab, h->perm_dev, t->lc_dev,
+                                                has_dm ? t->tab_dev + 3 * ntab : nullptr, has_dm ? t->tab_dev + 4 * ntab : nullptr, dm.scale);
+      nazb_count_launch();
+    }
   }
-  if (t->lcf_dev) { cudaFree(t->lcf_dev); t->lcf_dev = nullptr; }
   if (P.fwd3) {
-    if ((e = cudaMalloc(&t->lcf_dev, sizeof(float) * (size_t)S * L * P.f_lc_floats)) != cudaSuccess) return e;
+    if ((e = ensure_cap(&t->lcf_dev, &t->cap_lcf, sizeof(float) * (size_t)S * L * P.f_lc_floats)) != cudaSuccess) return e;
     LcGeom lg{};
     for (int j = 0; j < g.n_hidden; ++j) { lg.lc_b[j] = P.f_lc_b[j]; lg.hdim[j] = g.hidden[j]; }
     long long total = (long long)S * L * P.f_lc_floats;
@@ -1210,7 +1410,71 @@ cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* con
                                               has_dm ? t->tab_dev + 3 * ntab : nullptr, has_dm ? t->tab_dev + 4 * ntab : nullptr, dm.scale);
     nazb_count_launch();
   }
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
   t->plan = P;
+  return cudaSuccess;
+}
+
+static cudaError_t launch_inv4(const nazb_handle* h, const TcState* t, const IoArgs& io, int n_groups, cudaStream_t st) {
+  const FlowGeom& g = h->geom;
+  const TcPlan& P = t->plan;
+  const bool fold = P.fold_ok && t->opt_fold && g.C > 0 && io.ctx_rows == 1;
+  const std::vector<Step>& prog = fold ? P.steps_fold : P.steps[0];
+  KParamsInv4 kp{};
+  kp.dbg = g_tc_dbg;
+  kp.nsteps = (int)prog.size();
+  for (int i = 0; i < kp.nsteps; ++i) kp.steps[i] = prog[i];
+  kp.wimg = t->wimg[0];
+  kp.draw_bytes = t->draw_bytes[0];
+  kp.layer_bytes = P.layer_bytes[0];
+  kp.lc = fold ? t->lcfold_dev : t->lc_dev;
+  kp.lc_floats = P.lc_floats; kp.lc_s0 = fold ? 0 : io.s_begin;
+  kp.lc_w0x = P.lc_w0x; kp.lc_w0c = P.lc_w0c; kp.lc_b0 = P.lc_b[0]; kp.lc_r0c = P.lc_r0c; kp.dp4 = P.dp4; kp.cp4 = P.cp4;
+  kp.perm = h->perm_dev;
+  kp.D = g.D; kp.C = g.C; kp.L = g.L; kp.M = g.M; kp.Mp = P.mp_inv; kp.K = g.K; kp.kind = g.kind;
+  kp.nslots = P.j_nslots; kp.kr_max = P.kr_max;
+  kp.folded = fold ? 1 : 0;
+  kp.bound = g.bound; kp.clip_lo = g.clip_lo; kp.clip_hi = g.clip_hi;
+  kp.off_xin = P.j_xin; kp.off_lc = P.j_lc; kp.off_h = P.j_a; kp.off_y = P.j_y; kp.off_xo = P.j_xo; kp.off_xr = P.j_xr;
+  kp.off_misc = P.j_misc; kp.off_scratch = P.j_scratch; kp.off_ring = P.j_ring;
+  kp.wd = t->wd_dev;
+  const int n_tiles = (io.N + kTileM - 1) / kTileM;
+  const int grid = (int)std::min<long long>((long long)n_tiles * n_groups, h->sm_count);
+  // draw-group gate: only when every CTA works in every group (n_tiles >= 2 grid) and there are groups to drift across
+  kp.grp_done = nullptr;
+  cudaError_t e;
+  if (t->opt_gate && n_groups >= 3 && n_tiles >= 2 * grid && n_groups <= 65536) {
+    if ((e = cudaMemsetAsync(t->grp_done, 0, sizeof(int) * (size_t)n_groups, st)) != cudaSuccess) return e;
+    kp.grp_done = t->grp_done;
+  }
+  if (fold) {
+    FoldParams fp{};
+    fp.n_img = (int)P.fold_images.size();
+    for (int i = 0; i < fp.n_img; ++i) {
+      const Image& im = P.fold_images[i];
+      FoldImg& fi = fp.img[i];
+      fi.w_off = im.w_off; fi.w_bytes = im.w_bytes; fi.lin = im.lin; fi.n_ext = im.n_ext; fi.k_ext = im.k_ext;
+      fi.n0 = (im.row_mode == 0) ? im.n0 : im.r0 * P.mp_inv; fi.k0 = im.k0;
+    }
+    fp.wimg = t->wimg[0]; fp.draw_bytes = t->draw_bytes[0]; fp.layer_bytes = P.layer_bytes[0];
+    fp.lc = t->lc_dev; fp.lcf = t->lcfold_dev; fp.lc_floats = P.lc_floats; fp.lc_w0c = P.lc_w0c; fp.lc_r0c = P.lc_r0c;
+    fp.cp4 = std::max(P.cp4, 1); fp.lc_bout = P.lc_bout;
+    for (int j = 0; j < g.n_hidden; ++j) { fp.lc_b[j] = P.lc_b[j]; fp.hp[j] = ceil_to(g.hidden[j], 16); fp.blk1[j] = g.blk[j][1]; }
+    fp.n_hidden = g.n_hidden; fp.L = g.L; fp.C = g.C; fp.D = g.D; fp.Mp = P.mp_inv; fp.kind = g.kind;
+    fp.bound = g.bound; fp.clip_lo = g.clip_lo; fp.clip_hi = g.clip_hi;
+    fp.ctx = io.ctx; fp.s_begin = io.s_begin;
+    inv4_fold_kernel<<<io.s_count * g.L, 256, 0, st>>>(fp);
+    nazb_count_launch();
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  const int mode = (g.kind == NAZB_KIND_AFFINE) ? 0 : (g.kind == NAZB_KIND_RQS && g.K == 8) ? 1 : 2;
+  auto kern = flow_tc_inv4_kernel<false, 2>;
+  if (mode == 0) kern = flow_tc_inv4_kernel<false, 0>;
+  else if (mode == 1) kern = flow_tc_inv4_kernel<false, 1>;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.j_smem_bytes);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, kV4Threads, P.j_smem_bytes, st>>>(kp, io, n_groups);
+  nazb_count_launch();
   return cudaGetLastError();
 }
 
@@ -1220,6 +1484,7 @@ cudaError_t nazb_tc_launch(const nazb_handle* h, const IoArgs& io, int n_groups,
   const TcPlan& P = t->plan;
   const int d = io.dir;
   if (!P.ok[d]) return cudaErrorNotSupported;
+  if (d == 0 && P.inv_ver == 4) return launch_inv4(h, t, io, n_groups, st);
   if (d == 0) {
     KParamsInv kp{};
     kp.dbg = g_tc_dbg;
@@ -1230,7 +1495,6 @@ cudaError_t nazb_tc_launch(const nazb_handle* h, const IoArgs& io, int n_groups,
     kp.layer_bytes = P.layer_bytes[0];
     kp.lc = t->lc_dev; kp.lc_floats = P.lc_floats; kp.lc_b0 = P.lc_b[0];
     kp.phase_delay = 0;
-    if (const char* env = getenv("NAZB_PHASE_DELAY")) kp.phase_delay = atoi(env);
     kp.perm = h->perm_dev;
     kp.D = g.D; kp.C = g.C; kp.L = g.L; kp.M = g.M; kp.Mp = P.mp; kp.K = g.K; kp.kind = g.kind; kp.kin = g.kin;
     kp.kinp = P.kinp; kp.hp_max = P.hp_max; kp.nslots = P.j_nslots;

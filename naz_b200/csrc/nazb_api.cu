@@ -100,10 +100,6 @@ extern "C" int nazb_create(nazb_handle** out, const nazb_desc* desc) {
   if (desc->engine == NAZB_ENGINE_AUTO) h->engine = tc_ok ? NAZB_ENGINE_TCGEN05 : NAZB_ENGINE_SIMT;
   else if (desc->engine == NAZB_ENGINE_SIMT || desc->engine == NAZB_ENGINE_TCGEN05) h->engine = desc->engine;
   else { delete h; return NAZB_ERR_BAD_ARG; }
-  if (const char* env = getenv("NAZB_FORCE_ENGINE")) {
-    if (!strcmp(env, "simt")) h->engine = NAZB_ENGINE_SIMT;
-    if (!strcmp(env, "tcgen05") && tc_ok) h->engine = NAZB_ENGINE_TCGEN05;
-  }
   if (h->engine == NAZB_ENGINE_SIMT && nazb_simt_pick_P(h->geom) == 0) { delete h; return NAZB_ERR_UNSUPPORTED; }
   cudaError_t e = cudaSetDevice(h->device);
   if (e == cudaSuccess) e = cudaMalloc(&h->perm_dev, sizeof(int) * 2 * (size_t)desc->L * desc->D);
@@ -127,6 +123,8 @@ extern "C" void nazb_destroy(nazb_handle* h) {
   if (h->packed_T) cudaFree(h->packed_T);
   if (h->grad_tabs) cudaFree(h->grad_tabs);
   if (h->perm_dev) cudaFree(h->perm_dev);
+  if (h->stage_host) cudaFreeHost(h->stage_host);
+  if (h->stage_ev) cudaEventDestroy((cudaEvent_t)h->stage_ev);
   delete h;
 }
 
@@ -142,12 +140,64 @@ extern "C" int nazb_engine_for_direction(const nazb_handle* h, int dir) {
   return NAZB_ENGINE_SIMT;
 }
 
+int nazb_tc_set_option(nazb_handle* h, const char* name, int value);
+int nazb_tc_get_option(const nazb_handle* h, const char* name, int* value);
+unsigned int nazb_tc_watchdog(const nazb_handle* h);
+
+// Tuning / A-B switches of the engines (they replace the round-1 NAZB_* environment overrides: nothing in this library
+// reads the environment).  Options that change the packed program ("inv_kernel", "inv_merge_n") require a new nazb_pack.
+extern "C" int nazb_set_option(nazb_handle* h, const char* name, int32_t value) {
+  if (!h || !name) return NAZB_ERR_BAD_ARG;
+  if (h->engine != NAZB_ENGINE_TCGEN05) return NAZB_ERR_UNSUPPORTED;
+  return nazb_tc_set_option(h, name, value);
+}
+extern "C" int nazb_get_option(const nazb_handle* h, const char* name, int32_t* value) {
+  if (!h || !name || !value) return NAZB_ERR_BAD_ARG;
+  if (!strcmp(name, "watchdog")) { *value = (h->engine == NAZB_ENGINE_TCGEN05) ? (int32_t)nazb_tc_watchdog(h) : 0; return NAZB_OK; }
+  if (h->engine != NAZB_ENGINE_TCGEN05) return NAZB_ERR_UNSUPPORTED;
+  int v = 0;
+  int rc = nazb_tc_get_option(h, name, &v);
+  if (rc == NAZB_OK) *value = v;
+  return rc;
+}
+
 extern "C" int64_t nazb_packed_bytes(const nazb_handle* h) {
   if (!h) return 0;
   int64_t n = 0;
   if (h->engine == NAZB_ENGINE_TCGEN05) n += nazb_tc_packed_bytes(h);
   if (h->packed) n += (int64_t)h->desc.S * h->geom.draw_stride * (int64_t)sizeof(float);
   return n;
+}
+
+// Host -> device upload of a small table without hidden synchronisation: the bytes are copied into a pinned staging
+// buffer owned by the handle and sent with cudaMemcpyAsync on the caller's stream.  nazb_stage_begin waits (host side
+// only) for the previous pack's copies to have left the staging buffer before it is reused.
+static cudaError_t nazb_stage_begin(nazb_handle* h, size_t need) {
+  cudaError_t e;
+  if (!h->stage_ev) {
+    cudaEvent_t ev;
+    if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+    h->stage_ev = ev;
+  } else if ((e = cudaEventSynchronize((cudaEvent_t)h->stage_ev)) != cudaSuccess) {
+    return e;
+  }
+  if (h->stage_cap < need) {
+    if (h->stage_host) cudaFreeHost(h->stage_host);
+    h->stage_host = nullptr; h->stage_cap = 0;
+    if ((e = cudaHostAlloc(&h->stage_host, need, cudaHostAllocDefault)) != cudaSuccess) return e;
+    h->stage_cap = need;
+  }
+  h->stage_off = 0;
+  return cudaSuccess;
+}
+cudaError_t nazb_stage_upload(nazb_handle* h, void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  const size_t off = (h->stage_off + 15) & ~(size_t)15;
+  if (off + bytes > h->stage_cap) return cudaErrorMemoryAllocation;
+  memcpy(static_cast<char*>(h->stage_host) + off, src, bytes);
+  h->stage_off = off + bytes;
+  cudaError_t e = cudaMemcpyAsync(dst, static_cast<char*>(h->stage_host) + off, bytes, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaEventRecord((cudaEvent_t)h->stage_ev, st);
+  return e;
 }
 
 static int pack_impl(nazb_handle* h, const float* const* W, const float* const* b, const int64_t* wst,
@@ -161,6 +211,8 @@ static int pack_impl(nazb_handle* h, const float* const* W, const float* const* 
     if (!W[i] || !b[i] || !mask[i]) return NAZB_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   CK(h, cudaSetDevice(h->device));
+  h->is_packed = false;   // stays false when anything below fails (a half-packed handle must not be evaluated)
+  CK(h, nazb_stage_begin(h, 64 + sizeof(int) * 2 * (size_t)g.L * g.D + 8 * (size_t)7 * g.L * n_lin + 64));
   // perm + rank tables
   std::vector<int> pr(2 * (size_t)g.L * g.D);
   for (int l = 0; l < g.L; ++l) {
@@ -173,8 +225,7 @@ static int pack_impl(nazb_handle* h, const float* const* W, const float* const* 
       pr[(size_t)g.L * g.D + (size_t)l * g.D + d] = r;
     }
   }
-  // the tables are tiny; a synchronous copy keeps the host vector's lifetime trivial
-  CK(h, cudaMemcpy(h->perm_dev, pr.data(), pr.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CK(h, nazb_stage_upload(h, h->perm_dev, pr.data(), pr.size() * sizeof(int), st));
   // inverse schedule from the MADE degrees
   if (g.inv_mode == NAZB_INV_INCREMENTAL) {
     if (!hid_deg) return NAZB_ERR_BAD_ARG;

@@ -76,9 +76,15 @@ struct nazb_handle {
   bool packed_T_valid = false;
   void* grad_tabs = nullptr;
   std::string cuda_err;
+  // pinned staging buffer for the small host tables of nazb_pack (async upload on the caller's stream)
+  void* stage_host = nullptr;
+  size_t stage_cap = 0, stage_off = 0;
+  void* stage_ev = nullptr;   // cudaEvent_t recorded after the last staged copy
   // tcgen05 engine state (opaque here; defined in flow_tc.cu)
   void* tc = nullptr;
 };
+
+cudaError_t nazb_stage_upload(nazb_handle* h, void* dst, const void* src, size_t bytes, cudaStream_t st);
 
 // ---- launchers implemented in the .cu files ----
 cudaError_t nazb_simt_launch(const nazb_handle* h, const IoArgs& io, int n_groups, cudaStream_t st);

@@ -139,6 +139,26 @@ class FlowEngine:
             detail = self._lib.nazb_last_cuda_error(self._h).decode() if self._h else ""
             raise _lib.NazbError(rc, where, detail)
 
+    # engine options (include/nazb.h: nazb_set_option); nothing in the library reads the environment
+    OPTION_NAMES = ("inv_kernel", "inv_merge_n", "inv_fold", "inv_gate")
+
+    def set_option(self, name: str, value: int) -> None:
+        self._check(self._lib.nazb_set_option(self._h, name.encode(), int(value)), f"nazb_set_option({name})")
+
+    def get_option(self, name: str) -> Optional[int]:
+        v = C.c_int32(0)
+        rc = self._lib.nazb_get_option(self._h, name.encode(), C.byref(v))
+        return int(v.value) if rc == 0 else None
+
+    def options(self) -> dict:
+        """Current engine options (for bench / test records); {} on the SIMT engine."""
+        out = {}
+        for k in self.OPTION_NAMES + ("inv_fold_available",):
+            v = self.get_option(k)
+            if v is not None:
+                out[k] = v
+        return out
+
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 

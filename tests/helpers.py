@@ -21,12 +21,14 @@ def make_case(kind, D, C, hidden, L, S, seed, count_bins=8, order="quadratic", s
     return spec, draws, keep, rng
 
 
-def engine_for(spec, draws, keep=None, p_drop=0.0, engine="auto", inverse_mode="incremental", device="cuda:0"):
+def engine_for(spec, draws, keep=None, p_drop=0.0, engine="auto", inverse_mode="incremental", device="cuda:0", options=None):
     from naz_b200 import FlowEngine, FlowShape
     kind = spec.kind if spec.order == "quadratic" or spec.kind == "maf" else "nsa_linear"
     shape = FlowShape(kind, spec.D, spec.C, list(spec.hidden), spec.L, spec.count_bins, spec.bound, spec.clip)
     S = draws[0][0][0].shape[0]
     eng = FlowEngine(shape, S, device=device, engine=engine, inverse_mode=inverse_mode)
+    for k, v in (options or {}).items():
+        eng.set_option(k, v)
     masks = spec.masks()
     tdraws = [[(torch.from_numpy(W), torch.from_numpy(b)) for (W, b) in layer] for layer in draws]
     tmasks = [[torch.from_numpy(m) for m in ml] for ml in masks]

@@ -221,20 +221,83 @@ def test_svi_importance_pipeline_on_device():
     assert 1.0 <= ess <= S and abs(ess - ess_ref) <= 0.05 * ess_ref + 0.05
 
 
-def test_first_layer_cuda_core_fallback_matches_tensor_core_path(monkeypatch):
-    """The inverse kernel runs the first conditioner layer either as a K = 16 tcgen05 contraction or, when TMEM / the K slice
-    has no room, on CUDA cores from the layer constants; both must agree with the oracle on the headline shape."""
+INV_VARIANTS = [
+    {},                                       # v4 kernel, defaults
+    {"inv_kernel": 3},                        # round-1 kernel (kept as the A/B baseline)
+    {"inv_merge_n": 256},                     # every push issued unsplit
+    {"inv_fold": 0},                          # broadcast context evaluated per point (general program)
+    {"inv_gate": 0},
+]
+
+
+@pytest.mark.parametrize("options", INV_VARIANTS, ids=lambda o: "-".join(f"{k}{v}" for k, v in o.items()) or "default")
+@pytest.mark.parametrize("bcast", [False, True], ids=["ctx_per_point", "ctx_broadcast"])
+def test_inverse_kernel_variants_headline_shape(options, bcast):
+    """Every program / kernel variant of the tcgen05 inverse (engine options, include/nazb.h) agrees with the oracle on the
+    headline shape, with a per-point context (general program) and with a broadcast one (context-folded program)."""
     spec, draws, _, rng = make_case("nsa", 4, 2, [150] * 3, 16, 2, seed=21)
     x = (rng.normal(size=(300, 4)) * 1.5).astype(np.float32)
-    ctx = rng.uniform(size=(300, 2)).astype(np.float32)
+    ctx = rng.uniform(size=(2,) if bcast else (300, 2)).astype(np.float32)
     lp_ref, z_ref = fo.log_prob_draws(spec, to64(draws), x.astype(np.float64), ctx.astype(np.float64))
-    for no_xf in ("0", "1"):
-        monkeypatch.setenv("NAZB_NO_XF", no_xf)
-        eng = engine_for(spec, draws, engine="tcgen05")
-        assert eng.engine_for("inverse") == "tcgen05"
-        out = eng.inverse(T(x), T(ctx), want_z=True, want_lp=True)
-        check(out["lp"], lp_ref, f"lp (NAZB_NO_XF={no_xf})")
-        check(out["z"], z_ref, f"z (NAZB_NO_XF={no_xf})")
+    eng = engine_for(spec, draws, engine="tcgen05", options=options)
+    assert eng.engine_for("inverse") == "tcgen05"
+    out = eng.inverse(T(x), T(ctx), want_z=True, want_lp=True, want_lse=True, want_sum=True)
+    check(out["lp"], lp_ref, f"lp ({options})")
+    check(out["z"], z_ref, f"z ({options})")
+    assert np.allclose(out["sum_n"].cpu().numpy(), lp_ref.sum(1), rtol=2e-5)
+
+
+FOLD_SHAPES = [
+    # kind, D, C, hidden, L, S, N
+    ("nsa", 4, 2, [150] * 3, 16, 3, 500),      # cfg 3
+    ("maf", 2, 2, [150] * 3, 16, 3, 400),      # cfg 4 architecture with a broadcast context
+    ("maf", 8, 4, [150] * 3, 8, 2, 300),       # cfg 5: more ranks than x registers of the first-layer path (r > 4)
+    ("maf", 6, 4, [150] * 3, 8, 2, 300),       # cfg 2 architecture
+    ("nsa", 3, 2, [32, 48], 3, 2, 300),        # few K slices per block
+    ("maf", 3, 1, [16, 16], 4, 3, 600),        # one K slice per layer
+    ("maf", 1, 2, [16, 16], 3, 2, 200),        # D = 1: the whole flow layer folds into constants
+    ("nsa", 2, 5, [64, 64], 4, 2, 260),        # C > 4: context columns beyond the first float4
+]
+
+
+@pytest.mark.parametrize("shape", FOLD_SHAPES)
+def test_context_fold_matches_oracle_and_general_program(shape):
+    """ctx_rows == 1: the context-folded program (stage 0 evaluated once per draw and flow layer by inv4_fold_kernel)
+    against the fp64 oracle, against the general program on the same inputs, and with a draw sub-range."""
+    kind, D, C, hidden, L, S, N = shape
+    spec, draws, _, rng = make_case(kind, D, C, hidden, L, S, seed=13)
+    x = (rng.normal(size=(N, D)) * 1.5).astype(np.float32)
+    ctx = rng.uniform(size=(C,)).astype(np.float32)
+    lp_ref, z_ref = fo.log_prob_draws(spec, to64(draws), x.astype(np.float64), ctx.astype(np.float64))
+    eng = engine_for(spec, draws, engine="auto")
+    if eng.engine_for("inverse") != "tcgen05":
+        pytest.skip("inverse direction of this shape runs on the SIMT engine")
+    assert eng.get_option("inv_fold_available") == 1
+    out = eng.inverse(T(x), T(ctx), want_z=True, want_lp=True)
+    check(out["lp"], lp_ref, "lp (folded)")
+    check(out["z"], z_ref, "z (folded)")
+    eng.set_option("inv_fold", 0)
+    gen = eng.inverse(T(x), T(ctx), want_z=True, want_lp=True)
+    check(gen["lp"], lp_ref, "lp (general)")
+    d = (out["lp"] - gen["lp"]).abs().cpu().numpy()
+    tol = 1e-5 + 1e-4 * np.abs(lp_ref)
+    assert (d <= 2 * tol).mean() > 0.995, "folded and general programs disagree"
+    eng.set_option("inv_fold", 1)
+    if S > 1:
+        sub = eng.inverse(T(x), T(ctx), want_lp=True, s_begin=1, s_count=S - 1)
+        assert torch.equal(sub["lp"], out["lp"][1:]), "draw sub-range of the folded program"
+
+
+def test_bounded_broadcast_context_fold():
+    """bounding transform + folded context (flow.py:70-79 with one condition vector)."""
+    spec, draws, _, rng = make_case("nsa", 4, 2, [150] * 3, 4, 2, seed=29)
+    x = np.clip(rng.normal(size=(300, 4)) * 1.5, -5.9, 5.9).astype(np.float32)
+    ctx = rng.uniform(size=(2,)).astype(np.float32)
+    bounds = {"low": torch.full((4,), -6.0), "high": torch.full((4,), 6.0)}
+    eng = engine_for(spec, draws, engine="tcgen05")
+    out = eng.inverse(T(x), T(ctx), bounds, want_lp=True)
+    lp_ref, _ = fo.log_prob_draws(spec, to64(draws), x.astype(np.float64), ctx.astype(np.float64), bounds=(np.full(4, -6.0), np.full(4, 6.0)))
+    check(out["lp"], lp_ref, "bounded lp (folded)")
 
 
 def test_incremental_equals_reference_d_pass_schedule():
