@@ -25,6 +25,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cuda_fp16.h>
+#include <type_traits>
 #include "nazb_internal.h"
 #include "tc_ptx.cuh"
 #include "transforms.cuh"
@@ -106,6 +107,9 @@ struct TcPlan {
   std::vector<Image> fold_images; // stage-0 push images (what inv4_fold_kernel contracts with the degree-0 activations)
   int lc_w0x = 0, lc_w0c = 0, lc_r0c = 0, dp4 = 0, cp4 = 0;
   uint32_t j_xr = 0;
+  bool fold_a_tmem = false;       // ... same for the folded program
+  int t_a = 0;                    // v5: TMEM column of the A operand (hi image; lo at + kr_max / 2), valid when a_tmem
+  bool a_tmem = false;
 };
 
 struct TcState {
@@ -122,10 +126,12 @@ struct TcState {
   unsigned int* wd_dev = nullptr;    // ... and its device alias
   size_t cap_wimg[2] = {0, 0}, cap_lc = 0, cap_lcf = 0, cap_lcfold = 0, cap_tab = 0;
   // options (nazb_set_option); recorded by bench.py
-  int opt_inv_kernel = 4;            // 3 = round-1 kernel, 4 = v4
+  int opt_inv_kernel = 5;            // 3 = round-1 kernel, 4 = v4 (two 64-row chains), 5 = v5 (one 128-row chain)
   int opt_fold = 1;                  // context fold when ctx_rows == 1
-  int opt_merge_n = 0;               // pushes with N <= merge_n are issued unsplit (critical + deferred columns in one MMA)
+  int opt_merge_n = -1;              // pushes with N <= merge_n are issued unsplit (critical + deferred columns in one MMA);
+                                     // -1 = kernel default (v4: 0 = always split, v5: 256 = never split)
   int opt_gate = 1;                  // draw-group gate for large N
+  int opt_a_tmem = 1;                // v5: A operand in tensor memory when the plan allows it
 };
 
 constexpr int kMaxSteps = 80;
@@ -376,14 +382,16 @@ bool build_forward3(const FlowGeom& g, TcPlan& P) {
 bool build_inverse(const FlowGeom& g, TcPlan& P, int variant, int merge_n, std::vector<Step>& steps_out,
                    std::vector<Image>& images_out, std::vector<Image>* fold_images) {
   if (g.inv_mode != NAZB_INV_INCREMENTAL) return false;
-  const bool v4 = variant != 0, folded = variant == 2;
+  // variants 3 / 4: the v5 kernel (one 128-row chain, M = 128 MMAs: every N and every accumulator offset a multiple of 16)
+  const bool v5 = variant >= 3;
+  const bool v4 = variant != 0, folded = (variant == 2 || variant == 4);
   const int nh = g.n_hidden, D = g.D;
-  const int Mp = v4 ? ceil_to(g.M, 8) : P.mp;
+  const int Mp = v5 ? P.mp : (v4 ? ceil_to(g.M, 8) : P.mp);
   P.mp_inv = Mp;
-  // v3 feeds [ctx | x | 1] to a K = 16 MMA slice; v4 computes the first layer on CUDA cores from rank-ordered columns
+  // v3 feeds [ctx | x | 1] to a K = 16 MMA slice; v4 / v5 compute the first layer on CUDA cores from rank-ordered columns
   if (D * Mp > 256 || (!v4 && g.kin > 16) || D > 16) return false;
   auto hp = [&](int j) { return ceil_to(g.hidden[j], 16); };
-  auto hp8 = [&](int j) { return v4 ? ceil_to(g.hidden[j], 8) : hp(j); };   // last column a push has to reach
+  auto hp8 = [&](int j) { return (v4 && !v5) ? ceil_to(g.hidden[j], 8) : hp(j); };   // last column a push has to reach
   int col = 0;
   int T_PRE[NAZB_MAX_HIDDEN_LAYERS] = {0};
   for (int j = 1; j < nh; ++j) { T_PRE[j] = col; col += hp(j); }
@@ -463,12 +471,12 @@ bool build_inverse(const FlowGeom& g, TcPlan& P, int variant, int merge_n, std::
       if (j + 1 < nh) {
         int tb0 = g.blk[j + 1][r], tb1 = g.blk[j + 1][r + 1];
         int tc0 = tb0 & ~7, tc1 = ceil_to(tb1, 8);
-        int tn0 = tc0;                         // M = 64 MMAs take any N % 8 == 0
+        int tn0 = v5 ? (tc0 & ~15) : tc0;      // M = 64 MMAs take any N % 8 == 0, M = 128 ones N % 16 == 0
         int n = hp8(j + 1) - tn0;
         if (first_push[j + 1] && tn0 != 0 && !(folded && r == 1)) return false;
         Step e = mk_epi(EPI_TANH, T_PRE[j + 1] + tc0, tc1 - tc0, 0);
         e.e_aux = (uint16_t)(P.lc_b[j + 1] + tc0);
-        int n_crit = tc1 - tc0;
+        int n_crit = v5 ? ceil_to(tc1, 16) - tn0 : tc1 - tc0;
         if (v4 && n <= merge_n) n_crit = n;
         b.gemm(A_H, 0, kr, n, T_PRE[j + 1] + tn0, 3, first_push[j + 1] ? 0 : 1,
                mk_img(j + 1, n, kr, 0, tn0, 0, 0, sc0, sb0, sb1, -1, 0), e, n_crit);
@@ -491,6 +499,14 @@ bool build_inverse(const FlowGeom& g, TcPlan& P, int variant, int merge_n, std::
     }
   }
   P.layer_bytes[0] = b.w_off;
+  if (v5) {
+    // A operand in tensor memory: one buffer of kr_max / 2 columns each for the hi and lo images behind the accumulators;
+    // needs unsplit pushes (every MMA of a push retires before the accumulator barrier that releases the next writer)
+    P.t_a = ceil_to(T_OUT + D * Mp, 16);
+    bool unsplit = true;
+    for (const Step& st : steps_out) if (st.w_bytes && st.n_crit != st.n) unsplit = false;
+    P.a_tmem = unsplit && (P.t_a + P.kr_max <= kTmemCols);
+  }
   return (int)steps_out.size() <= kMaxSteps;
 }
 
@@ -1203,6 +1219,7 @@ constexpr int kChainRows = kTileM / kChains;          // 64
 
 #include "flow_tc_inv3.cuh"
 #include "flow_tc_inv4.cuh"
+#include "flow_tc_inv5.cuh"
 #include "flow_tc_fwd3.cuh"
 #include "flow_tc_fwd4.cuh"
 
@@ -1255,10 +1272,11 @@ void nazb_tc_destroy(nazb_handle* h) {
 int nazb_tc_set_option(nazb_handle* h, const char* name, int value) {
   TcState* t = static_cast<TcState*>(h->tc);
   if (!t) return NAZB_ERR_UNSUPPORTED;
-  if (!strcmp(name, "inv_kernel")) { if (value != 3 && value != 4) return NAZB_ERR_BAD_ARG; t->opt_inv_kernel = value; h->is_packed = false; return NAZB_OK; }
+  if (!strcmp(name, "inv_kernel")) { if (value < 3 || value > 5) return NAZB_ERR_BAD_ARG; t->opt_inv_kernel = value; h->is_packed = false; return NAZB_OK; }
   if (!strcmp(name, "inv_fold")) { t->opt_fold = value ? 1 : 0; return NAZB_OK; }
-  if (!strcmp(name, "inv_merge_n")) { if (value < 0 || value > 256) return NAZB_ERR_BAD_ARG; t->opt_merge_n = value; h->is_packed = false; return NAZB_OK; }
+  if (!strcmp(name, "inv_merge_n")) { if (value < -1 || value > 256) return NAZB_ERR_BAD_ARG; t->opt_merge_n = value; h->is_packed = false; return NAZB_OK; }
   if (!strcmp(name, "inv_gate")) { t->opt_gate = value ? 1 : 0; return NAZB_OK; }
+  if (!strcmp(name, "inv_a_tmem")) { t->opt_a_tmem = value ? 1 : 0; return NAZB_OK; }
   return NAZB_ERR_BAD_ARG;
 }
 int nazb_tc_get_option(const nazb_handle* h, const char* name, int* value) {
@@ -1268,7 +1286,10 @@ int nazb_tc_get_option(const nazb_handle* h, const char* name, int* value) {
   else if (!strcmp(name, "inv_fold")) *value = t->opt_fold;
   else if (!strcmp(name, "inv_merge_n")) *value = t->opt_merge_n;
   else if (!strcmp(name, "inv_gate")) *value = t->opt_gate;
-  else if (!strcmp(name, "inv_fold_available")) *value = (t->plan.ok[0] && t->plan.inv_ver == 4 && t->plan.fold_ok) ? 1 : 0;
+  else if (!strcmp(name, "inv_a_tmem")) *value = t->opt_a_tmem;
+  else if (!strcmp(name, "inv_kernel_in_use")) *value = t->plan.ok[0] ? t->plan.inv_ver : 0;
+  else if (!strcmp(name, "inv_a_tmem_in_use")) *value = (t->plan.ok[0] && t->plan.inv_ver == 5 && t->plan.a_tmem && t->plan.fold_a_tmem && t->opt_a_tmem) ? 1 : 0;
+  else if (!strcmp(name, "inv_fold_available")) *value = (t->plan.ok[0] && t->plan.inv_ver >= 4 && t->plan.fold_ok) ? 1 : 0;
   else return NAZB_ERR_BAD_ARG;
   return NAZB_OK;
 }
@@ -1320,14 +1341,25 @@ cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* con
   if (!P.fwd3) { P.steps[1].clear(); P.images[1].clear(); }
   P.ok[1] = P.fwd3 || build_forward(g, P);
   P.inv_ver = t->opt_inv_kernel;
-  if (P.inv_ver == 4) {
-    P.ok[0] = build_inverse(g, P, 1, t->opt_merge_n, P.steps[0], P.images[0], &P.fold_images) && plan_smem_inv4(g, P);
+  if (P.inv_ver >= 4) {
+    const int vgen = (P.inv_ver == 5) ? 3 : 1;
+    const int merge_n = t->opt_merge_n >= 0 ? t->opt_merge_n : (P.inv_ver == 5 ? 256 : 0);
+    P.ok[0] = build_inverse(g, P, vgen, merge_n, P.steps[0], P.images[0], &P.fold_images) && plan_smem_inv4(g, P);
+    if (!P.ok[0] && P.inv_ver == 5) {
+      // shapes the 128-row kernel cannot hold (output accumulators at stride ceil16(M)) fall back to the two-chain kernel
+      P.steps[0].clear(); P.images[0].clear(); P.fold_images.clear(); P.kr_max = 0;
+      P.inv_ver = 4;
+      P.ok[0] = build_inverse(g, P, 1, t->opt_merge_n >= 0 ? t->opt_merge_n : 0, P.steps[0], P.images[0], &P.fold_images) && plan_smem_inv4(g, P);
+    }
     if (P.ok[0]) {
+      const int vgen2 = (P.inv_ver == 5) ? 3 : 1;
+      const int merge2 = t->opt_merge_n >= 0 ? t->opt_merge_n : (P.inv_ver == 5 ? 256 : 0);
       std::vector<Image> scratch_images;
       TcPlan Q = P;   // the folded variant must not disturb kr_max / layer_bytes of the general plan
-      P.fold_ok = build_inverse(g, Q, 2, t->opt_merge_n, P.steps_fold, scratch_images, nullptr) &&
+      P.fold_ok = build_inverse(g, Q, vgen2 + 1, merge2, P.steps_fold, scratch_images, nullptr) &&
                   Q.layer_bytes[0] == P.layer_bytes[0] && (int)P.fold_images.size() <= kMaxFoldImgs;
       if (!P.fold_ok) P.steps_fold.clear();
+      P.fold_a_tmem = !P.fold_ok || Q.a_tmem;
     }
   } else {
     P.ok[0] = build_inverse(g, P, 0, 0, P.steps[0], P.images[0], nullptr) && plan_smem_inv3(g, P);
@@ -1377,7 +1409,7 @@ cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* con
     if ((e = ensure_cap(&t->lc_dev, &t->cap_lc, lc_bytes)) != cudaSuccess) return e;
     long long total = (long long)S * L * P.lc_floats;
     int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
-    if (P.inv_ver == 4) {
+    if (P.inv_ver >= 4) {
       Lc4Geom lg{};
       lg.lc_w0x = P.lc_w0x; lg.lc_w0c = P.lc_w0c; lg.lc_bout = P.lc_bout; lg.lc_r0c = P.lc_r0c; lg.lc_floats = P.lc_floats;
       lg.dp4 = P.dp4; lg.cp4 = std::max(P.cp4, 1);
@@ -1469,11 +1501,27 @@ static cudaError_t launch_inv4(const nazb_handle* h, const TcState* t, const IoA
   }
   const int mode = (g.kind == NAZB_KIND_AFFINE) ? 0 : (g.kind == NAZB_KIND_RQS && g.K == 8) ? 1 : 2;
   auto kern = flow_tc_inv4_kernel<false, 2>;
-  if (mode == 0) kern = flow_tc_inv4_kernel<false, 0>;
-  else if (mode == 1) kern = flow_tc_inv4_kernel<false, 1>;
+  int threads = kV4Threads;
+  if (P.inv_ver == 5) {
+    threads = kV5Threads;
+    const bool atm = t->opt_a_tmem && P.a_tmem && P.fold_a_tmem;
+    kp.t_a = (uint32_t)P.t_a;
+    if (atm) {
+      kern = flow_tc_inv5_kernel<false, 2, true>;
+      if (mode == 0) kern = flow_tc_inv5_kernel<false, 0, true>;
+      else if (mode == 1) kern = g_tc_dbg ? flow_tc_inv5_kernel<true, 1, true> : flow_tc_inv5_kernel<false, 1, true>;
+    } else {
+      kern = flow_tc_inv5_kernel<false, 2, false>;
+      if (mode == 0) kern = flow_tc_inv5_kernel<false, 0, false>;
+      else if (mode == 1) kern = g_tc_dbg ? flow_tc_inv5_kernel<true, 1, false> : flow_tc_inv5_kernel<false, 1, false>;
+    }
+  } else {
+    if (mode == 0) kern = flow_tc_inv4_kernel<false, 0>;
+    else if (mode == 1) kern = flow_tc_inv4_kernel<false, 1>;
+  }
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.j_smem_bytes);
   if (e != cudaSuccess) return e;
-  kern<<<grid, kV4Threads, P.j_smem_bytes, st>>>(kp, io, n_groups);
+  kern<<<grid, threads, P.j_smem_bytes, st>>>(kp, io, n_groups);
   nazb_count_launch();
   return cudaGetLastError();
 }
@@ -1484,7 +1532,7 @@ cudaError_t nazb_tc_launch(const nazb_handle* h, const IoArgs& io, int n_groups,
   const TcPlan& P = t->plan;
   const int d = io.dir;
   if (!P.ok[d]) return cudaErrorNotSupported;
-  if (d == 0 && P.inv_ver == 4) return launch_inv4(h, t, io, n_groups, st);
+  if (d == 0 && P.inv_ver >= 4) return launch_inv4(h, t, io, n_groups, st);
   if (d == 0) {
     KParamsInv kp{};
     kp.dbg = g_tc_dbg;

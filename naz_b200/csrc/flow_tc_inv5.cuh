@@ -1,121 +1,53 @@
-// v4 inverse (`log_prob` direction) kernel of the tcgen05 engine.  Included by flow_tc.cu inside its anonymous
-// namespace (shares Step / IoArgs and the helpers defined there).
+// v5 inverse (`log_prob` direction) kernel of the tcgen05 engine: ONE 128-row chain per CTA, M = 128 MMAs.
+// Included by flow_tc.cu after flow_tc_inv4.cuh (shares KParamsInv4, mbar_wait4, the fold kernel and the helpers).
 //
-// Same mathematics as v3 (push-style incremental inverse of the reference's D-pass autoregressive inverse,
-// bflow_jax_maf.py:181-194; two 64-row chains per 128-point tile; accumulators resident in TMEM for a whole flow
-// layer; fp16 hi/lo 3-MMA products).  What changed, and why (round-1 profile: one chain's 20-phase dependency chain
-// per flow layer bounds the kernel, a third of the issued instructions were mbarrier spins):
-//
-//   * CONTEXT FOLD.  Hidden units of MADE degree 0 see only the context.  With a broadcast context vector
-//     (ctx_rows == 1: calibrate.py:85,126 `test_lambda`) everything stage 0 of a flow layer computes — the degree-0
-//     blocks of all hidden layers, their pushes into later blocks, the rank-0 transform parameters — is the same for
-//     every point.  `inv4_fold_kernel` evaluates it once per (draw, flow layer) inside the same nazb_inverse call and
-//     writes it into the layer constants (effective biases + the rank-0 knot table); the main kernel then runs D-1
-//     stages instead of D: 5 of 20 phases and ~40 % of the MMAs disappear.  Per-point contexts run the general program.
-//   * FIRST CONDITIONER LAYER WITHOUT AN MMA ROUND TRIP.  pre_1[block r] = b' + W0[:, x_{<r}] x_{<r} needs r <= D-1
-//     multiply-adds per unit, so every epilogue warp of the chain computes its K slices of tanh(pre_1) straight from
-//     the layer constants as soon as x_{r-1} is known (64-thread named barrier between the two warps that share a
-//     TMEM quadrant); the K = 16 MMA + commit + tcgen05.ld hop of v3 is gone (one of four round trips per stage).
-//   * mbarrier waits carry a clock watchdog that writes a tag to mapped host memory and traps instead of hanging the GPU.
-//   * x_r is published before its log-det is computed; pushes are trimmed to the last real column.
-//   * Optional draw-group gate: a CTA's producer does not start draw group g before every CTA has finished issuing
-//     group g-2, so the weight images in flight stay L2-resident (DRAM traffic of round 1: 140x algorithmic).
+// Why (measured on B200 with the event log of this file, tools/inv5_timeline.py, on the v4 kernel): the two 64-row chains
+// of v3 / v4 run in lockstep, so they do not hide each other's latencies, while every M = 64 MMA occupies the tensor pipe
+// and the shared-memory operand path as long as an M = 128 one.  A push of 4 K slices took ~550-850 cycles per slice in
+// the issuer (6 small dependent MMAs per slice and chain, ~4 KB of operand reads each against 128 B/clk of shared-memory
+// bandwidth), and that backlog — not the tanh epilogue — was the longest segment of every phase.  Here:
+//   * one chain of 128 rows: half the MMAs and half the operand bytes per row; all 16 epilogue warps work on the same
+//     phase (4 TMEM lane quadrants x 2 row halves x 2 slice lanes);
+//   * pushes are issued unsplit (one accumulator region of N % 16 == 0 columns, N >= 112 for the wide ones, so consecutive
+//     accumulating MMAs pipeline instead of waiting on each other), guarded by a fresh elect.sync so that ptxas keeps the
+//     descriptors in uniform registers (UIADD3 + UTCHMMA back to back; the v3 / v4 form re-broadcast 7-8 operands per MMA);
+//   * everything else as v4: context fold, first conditioner layer on CUDA cores, watchdog'd waits, draw-group gate.
+// Row mapping: epilogue warp w: quadrant q = w & 3, part = w >> 2; rows 32 q + 16 (part & 1) + (lane & 15), two lanes per
+// row (tcgen05.ld.16x32bx2); slice lane = part >> 1 takes K slices (part >> 1), (part >> 1) + 2, ...; the warps with
+// part < 2 own the per-row state (spline, x, outputs).
 #pragma once
 
-constexpr int kV4Parts = 2;                          // epilogue warps per (chain, quadrant)
-constexpr int kV4EpiWarps = kChains * 4 * kV4Parts;
-constexpr int kV4Issuer0 = kV4EpiWarps;              // next kChains warps: MMA issuers
-constexpr int kV4Producer = kV4EpiWarps + kChains;   // last warp: TMA producer
-constexpr int kV4Threads = (kV4EpiWarps + kChains + 1) * 32;
-constexpr int kV4MaxSlices = 8;                      // A block <= 128 columns
-
-
-struct KParamsInv4 {
-  Step steps[kMaxSteps];
-  int nsteps;
-  const uint8_t* wimg;
-  unsigned long long draw_bytes, layer_bytes;
-  const float* lc;                 // [rows][L][lc_floats]; row of local draw si = lc_s0 + si
-  int lc_floats, lc_s0;
-  int lc_w0x, lc_w0c, lc_b0, lc_r0c, dp4, cp4;
-  const int* perm;
-  int D, C, L, M, Mp, K, kind, nslots, kr_max;
-  int folded;                      // context folded into the layer constants: stage 0 is constant, ctx adds nothing
-  uint32_t t_a;                    // v5, A operand in tensor memory: first TMEM column of the hi image (lo at + kr_max / 2)
-  float bound, clip_lo, clip_hi;
-  uint32_t off_xin, off_lc, off_h, off_y, off_xo, off_xr, off_misc, off_scratch, off_ring;
-  int* grp_done;                   // [n_groups] producers that finished issuing a draw group (gate), or null
-  unsigned int* wd;                // watchdog word (mapped host memory) or null
-  long long* dbg;
-};
-
-// mbarrier wait (a suspend-time hint was measured: 2 % slower) with a clock watchdog (~2^32 cycles): on timeout the tag goes to mapped host
-// memory and the kernel traps, so a protocol bug surfaces as a launch failure with a location instead of a hung GPU.
-__device__ __forceinline__ void mbar_wait4(uint64_t* bar, uint32_t parity, unsigned int* wd, uint32_t tag) {
-  asm volatile(
-      "{\n\t.reg .pred P1, P2;\n\t.reg .u64 t0, t1;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE4;\n\t"
-      "mov.u64 t0, %%clock64;\n\t"
-      "LAB_WAIT4:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE4;\n\t"
-      "mov.u64 t1, %%clock64;\n\t"
-      "sub.u64 t1, t1, t0;\n\t"
-      "setp.gt.u64 P2, t1, 0x100000000;\n\t"
-      "@!P2 bra LAB_WAIT4;\n\t"
-      "setp.ne.u64 P2, %2, 0;\n\t"
-      "@P2 st.volatile.global.u32 [%2], %3;\n\t"
-      "fence.acq_rel.sys;\n\t"
-      "trap;\n\t"
-      "DONE4:\n\t}\n" ::"r"(tcx::smem_u32(bar)),
-      "r"(parity), "l"(wd), "r"(tag)
-      : "memory");
-}
-#define WD_TAG(site) ((uint32_t)(site) | ((uint32_t)warp << 8) | ((uint32_t)blockIdx.x << 16))
-
-__device__ __forceinline__ void pair_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// Inverse rational-quadratic spline (K = 8) from a precomputed knot table t = [x knots 0..8 | y knots 0..8 | derivatives 0..8]
-// (shared memory, the same for every row: context-folded rank 0).  Formulas of rqs8_inv_pair / rqs_fast<8>.
-__device__ __forceinline__ void rqs8_inv_knots(float in, float B, const float* __restrict__ t, float& out, float& ld_fwd) {
-  const float eps = 1e-6f, LN2 = 0.6931471805599453f;
-  int k = 0;
-#pragma unroll
-  for (int j = 1; j < 8; ++j) k += (in >= t[9 + j] + eps) ? 1 : 0;
-  const float sel_x = t[k], sel_w = t[k + 1] - t[k];
-  const float sel_y = t[9 + k], sel_h = t[10 + k] - t[9 + k];
-  const float d0 = t[18 + k], d1 = t[19 + k];
-  const float delta = sel_h * tcx::rcp_approx(sel_w);
-  const float t2 = d0 + d1 - 2.f * delta;
-  const float dy = in - sel_y;
-  const float a = fmaf(dy, t2, sel_h * (delta - d0));
-  const float b = fmaf(-dy, t2, sel_h * d0);
-  const float c = -delta * dy;
-  const float disc = fmaf(b, b, -4.f * a * c);
-  const float th = (2.f * c) * tcx::rcp_approx(-b - tcx::sqrt_approx(fmaxf(disc, 0.f)));
-  const bool inside = (in >= -B && in <= B);
-  out = inside ? fmaf(th, sel_w, sel_x) : in;
-  const float tomt = th * (1.f - th), omt = 1.f - th;
-  const float den = fmaf(t2, tomt, delta);
-  const float dnum = delta * delta * fmaf(d1, th * th, fmaf(2.f * delta, tomt, d0 * omt * omt));
-  ld_fwd = inside ? (tcx::lg2_approx(dnum) - 2.f * tcx::lg2_approx(den)) * LN2 : 0.f;
-}
+constexpr int kV5EpiWarps = 16;
+constexpr int kV5Issuer = kV5EpiWarps;
+constexpr int kV5Producer = kV5EpiWarps + 1;
+constexpr int kV5Threads = (kV5EpiWarps + 2) * 32;
+constexpr int kV5MaxSlices = 8;
+constexpr int kDbgEvents = 4096;
+// Debug event log (kDbg instantiation only): CTA 0, three logger warps (slot 0 = epilogue warp 0 (q 0, rows 0-15, slice lane 0),
+// slot 1 = epilogue warp 8 (same rows, slice lane 1), slot 2 = the issuer), each writing (clock, step << 8 | event) pairs.
+#define LOG5(slot, ev)                                                                                    \
+  if (kDbg && dbg_on && lane == 0 && dbg_n < kDbgEvents) {                                                \
+    p.dbg[((size_t)(slot) * kDbgEvents + dbg_n) * 2] = clk();                                             \
+    p.dbg[((size_t)(slot) * kDbgEvents + dbg_n) * 2 + 1] = ((long long)st << 8) | (ev);                   \
+    ++dbg_n;                                                                                              \
+  }
 
 // kMode: 0 = affine, 1 = rational-quadratic spline with K = 8 (two lanes per row), 2 = any other spline.
-template <bool kDbg, int kMode>
-__global__ void __launch_bounds__(kV4Threads, 1) flow_tc_inv4_kernel(const __grid_constant__ KParamsInv4 p,
+// kATmem: the A operand (fp16 hi / lo of the activations) lives in tensor memory (written with tcgen05.st, read by the MMA)
+// instead of shared memory: measured (tools/tc_probe_rate3.cu) an M = 128 MMA costs max(N/2, 32 + N/4) cycles with A in shared
+// memory (operand fetch at 128 B/clk) and the N/2 pipe floor with A in TMEM; in the kernel the shared-memory A path ran at
+// ~130 cycles per MMA because the epilogue warps' own traffic shares that port.
+template <bool kDbg, int kMode, bool kATmem>
+__global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __grid_constant__ KParamsInv4 p,
                                                                       const __grid_constant__ IoArgs io, int n_groups) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* w_full = reinterpret_cast<uint64_t*>(smem);            // [nslots] TMA -> issuers
-  uint64_t* w_empty = w_full + 8;                                   // [nslots] count = kChains (one commit per issuer)
-  uint64_t* bar_acc = w_empty + 8;                                  // [kChains] issuer -> epilogue warps
-  uint64_t* lc_full = bar_acc + kChains;                            // [2]
-  uint64_t* lc_empty = lc_full + 2;                                 // [2], count = kV4EpiWarps
-  uint64_t* a_ready = lc_empty + 2;                                 // [kChains][2 buffers][kV4MaxSlices]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + kChains * 2 * kV4MaxSlices);
+  uint64_t* w_empty = w_full + 8;                                   // [nslots] count = 1 (the issuer's commit)
+  uint64_t* bar_acc = w_empty + 8;                                  // [1] issuer -> epilogue warps
+  uint64_t* lc_full = bar_acc + 2;                                  // [2]
+  uint64_t* lc_empty = lc_full + 2;                                 // [2], count = kV5EpiWarps
+  uint64_t* a_ready = lc_empty + 2;                                 // [2 buffers][kV5MaxSlices]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 2 * kV5MaxSlices);
   float* xin = reinterpret_cast<float*>(smem + p.off_xin);          // [C][128] context rows (per-point contexts)
   float* lcs = reinterpret_cast<float*>(smem + p.off_lc);           // [2][lc_floats]
   float* ycur = reinterpret_cast<float*>(smem + p.off_y);           // [D][128] by dimension
@@ -128,33 +60,34 @@ __global__ void __launch_bounds__(kV4Threads, 1) flow_tc_inv4_kernel(const __gri
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int D = p.D, C = p.C, M = p.M;
-  const uint32_t a_img_bytes = (uint32_t)p.kr_max * kChainRows * 2;   // one fp16 image (hi or lo) of an A block
+  const uint32_t a_img_bytes = (uint32_t)p.kr_max * kTileM * 2;   // one fp16 image (hi or lo) of an A block: [chunk][128 rows][8 halves]
   const uint32_t a_buf_bytes = 2 * a_img_bytes;
 
   if (tid == 0) {
-    for (int i = 0; i < p.nslots; ++i) { tcx::mbar_init(w_full + i, 1); tcx::mbar_init(w_empty + i, kChains); }
-    for (int i = 0; i < kChains; ++i) tcx::mbar_init(bar_acc + i, 1);
-    for (int i = 0; i < 2; ++i) { tcx::mbar_init(lc_full + i, 1); tcx::mbar_init(lc_empty + i, kV4EpiWarps); }
+    for (int i = 0; i < p.nslots; ++i) { tcx::mbar_init(w_full + i, 1); tcx::mbar_init(w_empty + i, 1); }
+    tcx::mbar_init(bar_acc, 1);
+    for (int i = 0; i < 2; ++i) { tcx::mbar_init(lc_full + i, 1); tcx::mbar_init(lc_empty + i, kV5EpiWarps); }
     // slice 0 of every A block also collects one arrival from each NON-producing warp of the chain: a warp that waits
     // on the accumulator barrier must be needed for the next MMA, otherwise the issuer could complete two accumulator
     // phases before a late warp has observed the first one and its parity wait would never return
-    for (int i = 0; i < kChains * 2 * kV4MaxSlices; ++i)
-      tcx::mbar_init(a_ready + i, (i % kV4MaxSlices == 0) ? 4 * kV4Parts : 4);
+    // a K slice is produced by the 8 warps (4 quadrants x 2 row halves) of its slice lane; slice 0 also collects the 8 observers
+    for (int i = 0; i < 2 * kV5MaxSlices; ++i) tcx::mbar_init(a_ready + i, (i % kV5MaxSlices == 0) ? 16 : 8);
     tcx::mbar_fence_init();
   }
   if (warp == 0) tcx::tmem_alloc(tmem_slot, kTmemCols);
-  for (uint32_t i = tid; i < (kChains * 2 * a_buf_bytes) / 16; i += kV4Threads)
+  for (uint32_t i = tid; i < (2 * a_buf_bytes) / 16; i += kV5Threads)
     reinterpret_cast<uint4*>(smem + p.off_h)[i] = make_uint4(0, 0, 0, 0);
   tcx::fence_async_smem();
   tcx::tc_fence_before();
   __syncthreads();
   tcx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (tmem != 0) __trap();   // 512 of 512 columns: the allocation is the whole tensor memory (the issuer assumes base 0)
 
   const int n_tiles = (io.N + kTileM - 1) / kTileM;
   const long long n_items = (long long)n_tiles * n_groups;
 
-  if (warp == kV4Producer) {
+  if (warp == kV5Producer) {
     // ===================== TMA producer: weight images + layer constants =====================
     if (lane == 0) {
       uint32_t cnt = 0, lcnt = 0;
@@ -207,23 +140,19 @@ __global__ void __launch_bounds__(kV4Threads, 1) flow_tc_inv4_kernel(const __gri
         atomicAdd(p.grp_done + prev_grp, 1);
       }
     }
-  } else if (warp >= kV4Issuer0) {
-    // ===================== MMA issuer of chain `ch` =====================
-    // Whole warp convergent, tcgen05 instructions predicated on the elected lane (descriptors stay uniform).
-    const int ch = warp - kV4Issuer0;
-    const uint32_t elected = tcx::elect_one();
+  } else if (warp == kV5Issuer) {
+    // ===================== MMA issuer =====================
+    // Whole warp convergent through the waits; each group of MMAs is guarded by a fresh elect.sync (CUTLASS idiom).
     const uint32_t ring_a = tcx::smem_u32(ring);
-    const uint32_t a_base = tcx::smem_u32(smem + p.off_h) + (uint32_t)ch * 2 * a_buf_bytes;
-    constexpr uint32_t lbo_a = kChainRows * 16;
-    constexpr uint64_t dhi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;   // SBO = 128 B, descriptor version 1
-    const uint32_t d_lane = tmem + ((uint32_t)(ch * 16) << 16);
-    uint64_t* my_acc = bar_acc + ch;
-    uint64_t* my_ready = a_ready + ch * 2 * kV4MaxSlices;
+    const uint32_t a_base = tcx::smem_u32(smem + p.off_h);
+    constexpr uint32_t lbo_a = kTileM * 16;
     uint32_t slot = 0, use = 0, buf = 0, apar = 0;   // apar: one parity bit per (buffer, slice) barrier
+    int dbg_n = 0;
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int grp = (int)(item / n_tiles);
       for (int si = grp; si < io.s_count; si += n_groups) {
         for (int li = 0; li < p.L; ++li) {
+          const bool dbg_on = kDbg && p.dbg != nullptr && blockIdx.x == 0 && item == blockIdx.x && si != grp && li >= 2;
           for (int st = 0; st < p.nsteps; ++st) {
             const uint32_t s_wbytes = p.steps[st].w_bytes;
             if (s_wbytes == 0) continue;
@@ -232,38 +161,68 @@ __global__ void __launch_bounds__(kV4Threads, 1) flow_tc_inv4_kernel(const __gri
             const uint32_t s_acc = p.steps[st].accumulate, s_last = (p.steps[st].epi != EPI_NONE);
             const uint32_t slice0 = p.steps[st].a_chunk0 >> 1;
             const uint32_t n_rest = s_n - s_ncrit;
-            const uint32_t idesc_c = tcx::make_idesc_f16_m64(s_ncrit);
-            const uint32_t idesc_r = tcx::make_idesc_f16_m64(n_rest);
-            const uint32_t lbo_b = s_n * 16;
-            const uint32_t b_hi = ring_a + slot * kSlotBytes;
-            const uint32_t b_lo = b_hi + (s_wbytes >> 1);
-            const uint32_t lbo_b_hi16 = (lbo_b >> 4) << 16, lbo_a_hi16 = (lbo_a >> 4) << 16;
-            const uint32_t a_hi = a_base + buf * a_buf_bytes;
-            const uint32_t a_lo = a_hi + a_img_bytes;
-            const uint32_t d_c = d_lane + s_dcol, d_r = d_c + s_ncrit;
-            const uint32_t ro = s_ncrit;              // image row n_crit = byte offset n_crit * 16, >> 4
+            const uint32_t idesc_c = tcx::make_idesc_f16(s_ncrit);
+            const uint32_t idesc_r = tcx::make_idesc_f16(n_rest);
+            // The issuer is ONE thread running a serial instruction stream (~5 cycles per dependent instruction): what it
+            // executes per K slice bounds the MMA rate long before the tensor pipe does (tools/tc_probe_rate2.cu: 123 cycles
+            // per MMA for a 25-instruction loop body whatever M, N or the operand source).  So the slice loop only waits,
+            // adds constants to the low words of four running descriptors and fires the MMAs.
+            constexpr uint32_t dhi32 = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1
+            const uint32_t a_step = (2u * lbo_a) >> 4, b_step = (2u * s_n * 16u) >> 4;
+            uint32_t da_h = (((a_base + buf * a_buf_bytes) + slice0 * 2u * lbo_a) >> 4) | ((lbo_a >> 4) << 16);
+            uint32_t da_l = da_h + (a_img_bytes >> 4);
+            uint32_t db_h = ((ring_a + slot * kSlotBytes) >> 4) | (((s_n * 16u) >> 4) << 16);
+            uint32_t db_l = db_h + (s_wbytes >> 5);
+            const uint32_t d_c = s_dcol, d_r = d_c + s_ncrit;   // TMEM base is 0 (checked above): lane 0, column d_col
+            const uint32_t ro = s_ncrit;                        // image row n_crit = byte offset n_crit * 16, >> 4
+            // A in TMEM: ONE buffer (every MMA of a push has retired before the epilogue that writes the next block passes
+            // the accumulator barrier: pushes are unsplit), K slice s at columns t_a + 8 s (hi) / t_a + kr_max / 2 + 8 s (lo)
+            uint32_t ta_h = p.t_a + slice0 * 8u, ta_l = ta_h + (uint32_t)p.kr_max / 2u;
+            uint64_t* rdy = a_ready + buf * kV5MaxSlices + slice0;
+            uint32_t bit = 1u << (buf * kV5MaxSlices + slice0);
+            auto desc = [](uint32_t lo) { return ((uint64_t)dhi32 << 32) | lo; };
+            LOG5(2, 20)
             mbar_wait4(w_full + slot, use & 1, p.wd, WD_TAG(3));
+            LOG5(2, 21)
             for (int k = 0; k < ksteps; ++k) {
-              const uint32_t sl = slice0 + k, bit = 1u << (buf * kV4MaxSlices + sl);
-              mbar_wait4(my_ready + buf * kV4MaxSlices + sl, (apar & bit) ? 1u : 0u, p.wd, WD_TAG(4));
+              mbar_wait4(rdy, (apar & bit) ? 1u : 0u, p.wd, WD_TAG(4));
               apar ^= bit;
               tcx::tc_fence_after();
-              const uint32_t ao = sl * 2 * lbo_a, bo = (uint32_t)k * 2 * lbo_b;
-              const uint64_t da_h = dhi | (((a_hi + ao) >> 4) | lbo_a_hi16), da_l = dhi | (((a_lo + ao) >> 4) | lbo_a_hi16);
-              const uint64_t db_h = dhi | (((b_hi + bo) >> 4) | lbo_b_hi16), db_l = dhi | (((b_lo + bo) >> 4) | lbo_b_hi16);
+              LOG5(2, 32 + k)
               const uint32_t acc0 = (k == 0) ? s_acc : 1u;
-              // critical columns (block r): hi*hi + hi*lo + lo*hi
-              tcx::mma_f16_ss_elect(d_c, da_h, db_h, idesc_c, acc0, elected);
-              tcx::mma_f16_ss_elect(d_c, da_h, db_l, idesc_c, 1u, elected);
-              tcx::mma_f16_ss_elect(d_c, da_l, db_h, idesc_c, 1u, elected);
-              if (s_last && k == ksteps - 1) tcx::mma_commit_elect(my_acc, elected);
-              if (n_rest) {
-                tcx::mma_f16_ss_elect(d_r, da_h, db_h + ro, idesc_r, acc0, elected);
-                tcx::mma_f16_ss_elect(d_r, da_h, db_l + ro, idesc_r, 1u, elected);
-                tcx::mma_f16_ss_elect(d_r, da_l, db_h + ro, idesc_r, 1u, elected);
+              const bool lastk = (k == ksteps - 1);
+              if (tcx::elect_one()) {
+                // hi*hi + hi*lo + lo*hi on the critical columns, then (split pushes only) on the remaining ones
+                if (kATmem) {
+                  tcx::mma_f16_ts(d_c, ta_h, desc(db_h), idesc_c, acc0);
+                  tcx::mma_f16_ts(d_c, ta_h, desc(db_l), idesc_c, 1u);
+                  tcx::mma_f16_ts(d_c, ta_l, desc(db_h), idesc_c, 1u);
+                } else {
+                  tcx::mma_f16_ss(d_c, desc(da_h), desc(db_h), idesc_c, acc0);
+                  tcx::mma_f16_ss(d_c, desc(da_h), desc(db_l), idesc_c, 1u);
+                  tcx::mma_f16_ss(d_c, desc(da_l), desc(db_h), idesc_c, 1u);
+                }
+                if (s_last && lastk) tcx::mma_commit(bar_acc);
+                if (n_rest) {
+                  if (kATmem) {
+                    tcx::mma_f16_ts(d_r, ta_h, desc(db_h + ro), idesc_r, acc0);
+                    tcx::mma_f16_ts(d_r, ta_h, desc(db_l + ro), idesc_r, 1u);
+                    tcx::mma_f16_ts(d_r, ta_l, desc(db_h + ro), idesc_r, 1u);
+                  } else {
+                    tcx::mma_f16_ss(d_r, desc(da_h), desc(db_h + ro), idesc_r, acc0);
+                    tcx::mma_f16_ss(d_r, desc(da_h), desc(db_l + ro), idesc_r, 1u);
+                    tcx::mma_f16_ss(d_r, desc(da_l), desc(db_h + ro), idesc_r, 1u);
+                  }
+                }
+                if (lastk) tcx::mma_commit(w_empty + slot);   // the slot is free once these MMAs retire
               }
+              __syncwarp();
+              LOG5(2, 48 + k)
+              da_h += a_step; da_l += a_step; db_h += b_step; db_l += b_step;
+              ta_h += 8; ta_l += 8;
+              ++rdy; bit <<= 1;
             }
-            tcx::mma_commit_elect(w_empty + slot, elected);   // the slot is free once these MMAs retire
+            LOG5(2, 23)
             if (++slot == (uint32_t)p.nslots) { slot = 0; ++use; }
             if (s_last) buf ^= 1;
           }
@@ -271,39 +230,50 @@ __global__ void __launch_bounds__(kV4Threads, 1) flow_tc_inv4_kernel(const __gri
       }
     }
   } else {
-    // ===================== epilogue warps: kV4Parts per (chain, TMEM lane quadrant) =====================
-    const int ch = warp / (4 * kV4Parts), part = (warp >> 2) % kV4Parts, q = warp & 3;
+    // ===================== epilogue warps: 4 TMEM lane quadrants x 2 row halves x 2 slice lanes =====================
+    const int q = warp & 3, part = warp >> 2, rh = part & 1, sll = part >> 1;
     const int hw = lane >> 4, lr = lane & 15;
-    const int crow = q * 16 + lr;                  // row inside the chain's 64-row sub-tile
-    const int trow = ch * kChainRows + crow;       // row inside the 128-point tile
-    const int wrow0 = ch * kChainRows + q * 16;    // first tile row owned by this quadrant
-    const uint32_t lane_base = tmem + ((uint32_t)(q * 32 + ch * 16) << 16);
+    const int trow = q * 32 + rh * 16 + lr;        // row inside the 128-point tile (= TMEM lane)
+    const int crow = trow;
+    const int wrow0 = q * 32 + rh * 16;            // first tile row of this warp
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32 + rh * 16) << 16);
     constexpr bool spline = kMode != 0;
     constexpr bool fast_rqs = kMode == 1;
-    const bool rows_mine = (part == 0);            // this warp owns the per-row state of its 16 rows
+    const bool rows_mine = (sll == 0);             // this warp owns the per-row state of its 16 rows
     const bool owner = rows_mine && (hw == 0);
     const bool add_ctx = (C > 0) && !p.folded;
-    const int pair_id = 1 + ch * 4 + q;            // named barrier of the kV4Parts warps sharing these 16 rows
+    const int pair_id = 1 + q * 2 + rh;            // named barrier of the two warps (slice lanes) sharing these 16 rows
     float* scr = scratch + trow;
     auto raw = [&](int m) { return scr[m * kTileM]; };
     auto setw = [&](int m, float v) { scr[m * kTileM] = v; };
-    uint8_t* a_chain = smem + p.off_h + (size_t)ch * 2 * a_buf_bytes;
-    uint64_t* my_acc = bar_acc + ch;
-    uint64_t* my_ready = a_ready + ch * 2 * kV4MaxSlices;
+    uint8_t* a_chain = smem + p.off_h;
+    uint64_t* my_acc = bar_acc;
+    uint64_t* my_ready = a_ready;
     uint32_t par_acc = 0, lcnt = 0, buf = 0;
+    int dbg_n = 0;
+    const int dbg_slot = sll;
     const uint64_t scale2 = tcx::pk2(kTanhScale, kTanhScale);
 
     // write this thread's 8-column chunk `c` (hi / lo fp16) of the A block: layout [chunk][64 rows][8 halves]
     auto store_chunk = [&](int c, const uint4& hi4, const uint4& lo4) {
-      uint8_t* dst = a_chain + (size_t)buf * a_buf_bytes + ((size_t)c * kChainRows + crow) * 16;
-      *reinterpret_cast<uint4*>(dst) = hi4;
-      *reinterpret_cast<uint4*>(dst + a_img_bytes) = lo4;
+      if (kATmem) {
+        // chunk c = K elements [8c, 8c + 8) = TMEM columns [4c, 4c + 4) of the hi / lo image; the two half-warps of a row hold
+        // chunks 2s and 2s + 1, i.e. the 8 columns of K slice s (the store is warp-collective: both halves always take part)
+        const uint32_t ta = lane_base + p.t_a + (uint32_t)(c >> 1) * 8u;
+        tcx::tmem_st16x2_4<4>(ta, hi4.x, hi4.y, hi4.z, hi4.w);
+        tcx::tmem_st16x2_4<4>(ta + (uint32_t)p.kr_max / 2u, lo4.x, lo4.y, lo4.z, lo4.w);
+      } else {
+        uint8_t* dst = a_chain + (size_t)buf * a_buf_bytes + ((size_t)c * kTileM + crow) * 16;
+        *reinterpret_cast<uint4*>(dst) = hi4;
+        *reinterpret_cast<uint4*>(dst + a_img_bytes) = lo4;
+      }
     };
     // publish K slice `sl` of the A block under construction
     auto publish = [&](int sl) {
-      tcx::fence_async_smem();
+      if (kATmem) { tcx::tmem_st_wait(); tcx::tc_fence_before(); }
+      else tcx::fence_async_smem();
       __syncwarp();
-      if (lane == 0) tcx::mbar_arrive(my_ready + buf * kV4MaxSlices + sl);
+      if (lane == 0) tcx::mbar_arrive(my_ready + buf * kV5MaxSlices + sl);
     };
 
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -312,7 +282,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) flow_tc_inv4_kernel(const __gri
       const int npts = min(kTileM, io.N - n0);
       float run_m = -INFINITY, run_s = 0.f;
       // ---- tile load: the 16 rows of this quadrant (part-0 warp), then visible to the other parts ----
-      pair_bar_sync(pair_id, 32 * kV4Parts);       // every part is done with the previous tile's rows
+      pair_bar_sync(pair_id, 64);       // every part is done with the previous tile's rows
       if (rows_mine) {
         if (add_ctx)
           for (int i = lane; i < 16 * C; i += 32) {
@@ -333,7 +303,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) flow_tc_inv4_kernel(const __gri
           ljac[trow] = lj;
         }
       }
-      pair_bar_sync(pair_id, 32 * kV4Parts);       // context rows are in shared memory
+      pair_bar_sync(pair_id, 64);       // context rows are in shared memory
 
       for (int si = grp; si < io.s_count; si += n_groups) {
         // ---- draw start ----
@@ -346,34 +316,38 @@ __global__ void __launch_bounds__(kV4Threads, 1) flow_tc_inv4_kernel(const __gri
           const int* perm = p.perm + l * D;
           const float* lc = lcs + (size_t)(lcnt & 1) * p.lc_floats;
           mbar_wait4(lc_full + (lcnt & 1), (lcnt >> 1) & 1, p.wd, WD_TAG(5));
+          const bool dbg_on = kDbg && p.dbg != nullptr && blockIdx.x == 0 && q == 0 && rh == 0 && item == blockIdx.x && si != grp && li >= 2;
           for (int st = 0; st < p.nsteps; ++st) {
             const uint32_t s_epi = p.steps[st].epi;
             if (s_epi == EPI_NONE) continue;   // K-split sub-step: nothing to do on this side
+            LOG5(dbg_slot, 1)
             const uint32_t s_ecol = p.steps[st].e_col, s_encols = p.steps[st].e_ncols, s_eaux = p.steps[st].e_aux;
             const uint32_t s_stage = p.steps[st].stage, s_flags = p.steps[st].flags;
             if (p.steps[st].w_bytes) {
               mbar_wait4(my_acc, par_acc, p.wd, WD_TAG(6));
               par_acc ^= 1;
               tcx::tc_fence_after();
+              LOG5(dbg_slot, 2)
             }
             if (s_epi == EPI_TANH) {
               // block of nch 8-column chunks = nsl K slices; slice s = chunks {2s (half-warp 0), 2s+1 (half-warp 1)}
               const int nch = s_encols >> 3, nsl = (nch + 1) >> 1;
-              const int nmine = (nsl - part + kV4Parts - 1) / kV4Parts;   // slices part, part + kV4Parts, ...
-              if (part != 0 && lane == 0) tcx::mbar_arrive(my_ready + buf * kV4MaxSlices);   // observer arrival on slice 0
+              const int nmine = (nsl - sll + 1) / 2;   // slices sll, sll + 2, ...
+              if (sll != 0 && lane == 0) tcx::mbar_arrive(my_ready + buf * kV5MaxSlices);   // observer arrival on slice 0
               for (int j0 = 0; j0 < nmine; j0 += 2) {
                 uint32_t r[16];
                 const int nj = min(2, nmine - j0);
-                const int sl0 = part + j0 * kV4Parts;
+                const int sl0 = sll + j0 * 2;
                 const uint32_t ta = lane_base + s_ecol + sl0 * 16;
                 tcx::tmem_ld16x2_8<8>(ta, r);
-                if (nj > 1) tcx::tmem_ld16x2_8<8>(ta + 16 * kV4Parts, r + 8);
+                if (nj > 1) tcx::tmem_ld16x2_8<8>(ta + 32, r + 8);
                 tcx::tmem_ld_wait();
                 tcx::tc_fence_before();
+                LOG5(dbg_slot, 3)
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                   if (u < nj) {
-                    const int sl = sl0 + u * kV4Parts;
+                    const int sl = sl0 + u * 2;
                     const int c = sl * 2 + hw;
                     const int cl = min(c, nch - 1);
                     const uint32_t* ru = r + 8 * u;
@@ -389,6 +363,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) flow_tc_inv4_kernel(const __gri
                     if (c >= nch) { hi4 = make_uint4(0, 0, 0, 0); lo4 = hi4; }   // K padding chunk
                     store_chunk(c, hi4, lo4);
                     publish(sl);
+                    LOG5(dbg_slot, 8 + sl)
                   }
                 }
               }
@@ -397,11 +372,12 @@ __global__ void __launch_bounds__(kV4Threads, 1) flow_tc_inv4_kernel(const __gri
               // first conditioner layer of block `stage` on CUDA cores: s = b'[n] + sum_c W0c[n][c] ctx_c + sum_{q < stage} W0x[n][q] x_q
               // (everything pre-multiplied by 2 log2 e), tanh, fp16 hi/lo A block.  x_q (by rank) were written by the row owners.
               const int r = (int)s_stage;
-              if (r > 0) pair_bar_sync(pair_id, 32 * kV4Parts);   // x_{r-1} of these rows is visible
+              if (r > 0) pair_bar_sync(pair_id, 64);   // x_{r-1} of these rows is visible
+              LOG5(dbg_slot, 4)
               const int nch = s_encols >> 3, nsl = (nch + 1) >> 1;
               const int u0 = s_eaux;
-              const int nmine = (nsl - part + kV4Parts - 1) / kV4Parts;
-              if (part != 0 && lane == 0) tcx::mbar_arrive(my_ready + buf * kV4MaxSlices);   // observer arrival on slice 0
+              const int nmine = (nsl - sll + 1) / 2;
+              if (sll != 0 && lane == 0) tcx::mbar_arrive(my_ready + buf * kV5MaxSlices);   // observer arrival on slice 0
               float xv[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
               for (int k = 0; k < 4; ++k)
@@ -413,7 +389,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) flow_tc_inv4_kernel(const __gri
                   if (k < C) cv[k] = xin[k * kTileM + trow];
               }
               for (int j = 0; j < nmine; ++j) {
-                const int sl = part + j * kV4Parts;
+                const int sl = sll + j * 2;
                 const int c = sl * 2 + hw;
                 uint4 hi4 = make_uint4(0, 0, 0, 0), lo4 = hi4;
                 if (c < nch) {
@@ -465,8 +441,10 @@ __global__ void __launch_bounds__(kV4Threads, 1) flow_tc_inv4_kernel(const __gri
                   for (int i = 0; i < 4; ++i) s2[i] = tcx::pk2(acc[2 * i], acc[2 * i + 1]);
                   tcx::tanh8_scaled(s2, hi4, lo4);
                 }
+                if (kATmem) __syncwarp();   // the TMEM store is warp-collective: reconverge after the per-chunk branch
                 store_chunk(c, hi4, lo4);
                 publish(sl);
+                LOG5(dbg_slot, 8 + sl)
               }
               buf ^= 1;
             } else if (s_epi == EPI_XINV0C) {
@@ -533,6 +511,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) flow_tc_inv4_kernel(const __gri
                 }
               }
               tcx::tc_fence_before();
+              LOG5(dbg_slot, 5)
               if (owner) {
                 xr[r * kTileM + trow] = xv;   // published first: the next stage's first layer waits for it
                 ld_acc += ld;
@@ -543,6 +522,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) flow_tc_inv4_kernel(const __gri
               }
             }
           }
+          { const int st = 255; LOG5(dbg_slot, 6) }
           // this layer's constants are no longer needed by this warp
           __syncwarp();
           if (lane == 0) tcx::mbar_arrive(lc_empty + (lcnt & 1));
@@ -588,124 +568,3 @@ __global__ void __launch_bounds__(kV4Threads, 1) flow_tc_inv4_kernel(const __gri
   if (warp == 0) tcx::tmem_dealloc(tmem, kTmemCols);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Context fold (see the header comment): one CTA per (draw, flow layer).
-// ------------------------------------------------------------------------------------------------
-struct FoldImg {
-  uint32_t w_off, w_bytes;
-  int lin;        // linear layer the image belongs to (1 .. n_hidden); its K axis indexes hidden layer lin - 1
-  int n_ext, k_ext, n0, k0;
-};
-constexpr int kMaxFoldImgs = 24;
-struct FoldParams {
-  FoldImg img[kMaxFoldImgs];
-  int n_img;
-  const uint8_t* wimg;
-  unsigned long long draw_bytes, layer_bytes;
-  const float* lc;       // general layer constants [S][L][lc_floats]
-  float* lcf;            // folded layer constants [s_count][L][lc_floats]
-  int lc_floats, lc_w0c, lc_r0c, cp4;
-  int lc_b[NAZB_MAX_HIDDEN_LAYERS], lc_bout;
-  int hp[NAZB_MAX_HIDDEN_LAYERS], blk1[NAZB_MAX_HIDDEN_LAYERS];   // padded widths; number of degree-0 units per hidden layer
-  int n_hidden, L, C, D, Mp, kind;
-  float bound, clip_lo, clip_hi;
-  const float* ctx;      // [C]
-  int s_begin;
-};
-
-__device__ __forceinline__ float tanh_from_scaled(float s) {   // s = 2 x log2 e
-  const float e = exp2f(fminf(s, 30.f));
-  return 1.f - 2.f / (e + 1.f);
-}
-
-__global__ void __launch_bounds__(256) inv4_fold_kernel(const __grid_constant__ FoldParams f) {
-  __shared__ float hvec[256];       // degree-0 activations of the current hidden layer (0 elsewhere)
-  __shared__ float accv[512];       // folded contribution to the next linear layer's pre-activations / outputs
-  const int s = blockIdx.x / f.L, l = blockIdx.x % f.L;
-  const int tid = threadIdx.x;
-  const float* lc = f.lc + ((size_t)(f.s_begin + s) * f.L + l) * f.lc_floats;
-  float* out = f.lcf + ((size_t)s * f.L + l) * f.lc_floats;
-  const uint8_t* wl = f.wimg + (size_t)(f.s_begin + s) * f.draw_bytes + (size_t)l * f.layer_bytes;
-  for (int i = tid; i < f.lc_floats; i += blockDim.x) out[i] = lc[i];
-  __syncthreads();
-  // first layer: b0' = b0 + W0[:, ctx] ctx (scaled domain) for every unit
-  for (int n = tid; n < f.hp[0]; n += blockDim.x) {
-    float a = lc[f.lc_b[0] + n];
-    for (int c = 0; c < f.C; ++c) a = fmaf(lc[f.lc_w0c + (size_t)n * f.cp4 + c], f.ctx[c], a);
-    out[f.lc_b[0] + n] = a;
-    hvec[n] = (n < f.blk1[0]) ? tanh_from_scaled(a) : 0.f;
-  }
-  for (int n = f.hp[0] + tid; n < 256; n += blockDim.x) hvec[n] = 0.f;
-  __syncthreads();
-  for (int lin = 1; lin <= f.n_hidden; ++lin) {
-    for (int i = tid; i < 512; i += blockDim.x) accv[i] = 0.f;
-    __syncthreads();
-    for (int im = 0; im < f.n_img; ++im) {
-      const FoldImg& g = f.img[im];
-      if (g.lin != lin) continue;
-      const uint8_t* hi = wl + g.w_off;
-      const uint8_t* lo = hi + (g.w_bytes >> 1);
-      for (int n = tid; n < g.n_ext; n += blockDim.x) {
-        float a = 0.f;
-        for (int kc = 0; kc < (g.k_ext >> 3); ++kc) {
-          const uint4 vh = *reinterpret_cast<const uint4*>(hi + ((size_t)kc * g.n_ext + n) * 16);
-          const uint4 vl = *reinterpret_cast<const uint4*>(lo + ((size_t)kc * g.n_ext + n) * 16);
-          const uint32_t hw[4] = {vh.x, vh.y, vh.z, vh.w}, lw[4] = {vl.x, vl.y, vl.z, vl.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float h0, h1, l0, l1;
-            tcx::unpack2(hw[e], h0, h1);
-            tcx::unpack2(lw[e], l0, l1);
-            const int k = g.k0 + kc * 8 + 2 * e;
-            a = fmaf(hvec[k], h0 + l0, a);
-            a = fmaf(hvec[k + 1], h1 + l1, a);
-          }
-        }
-        accv[g.n0 + n] += a;   // images of one linear layer cover disjoint (n, k) ranges per thread n: no race
-      }
-      __syncthreads();
-    }
-    if (lin < f.n_hidden) {
-      for (int n = tid; n < f.hp[lin]; n += blockDim.x) {
-        const float b = lc[f.lc_b[lin] + n] + kTanhScale * accv[n];
-        out[f.lc_b[lin] + n] = b;
-        hvec[n] = (n < f.blk1[lin]) ? tanh_from_scaled(b) : 0.f;
-      }
-      for (int n = f.hp[lin] + tid; n < 256; n += blockDim.x) hvec[n] = 0.f;
-    } else {
-      for (int n = tid; n < f.D * f.Mp; n += blockDim.x) out[f.lc_bout + n] = lc[f.lc_bout + n] + accv[n];
-    }
-    __syncthreads();
-  }
-  // rank-0 transform parameters -> constants
-  if (tid == 0) {
-    const float* ro = out + f.lc_bout;
-    float* t = out + f.lc_r0c;
-    if (f.kind == NAZB_KIND_AFFINE) {
-      const float sc = fminf(fmaxf(ro[1], f.clip_lo), f.clip_hi);
-      t[0] = ro[0]; t[1] = sc; t[2] = expf(-sc);
-    } else {
-      const int K = 8;
-      const float B = f.bound, min_bin = 1e-3f, min_d = 1e-3f;
-      for (int ax = 0; ax < 2; ++ax) {
-        const float* v = ro + ax * K;
-        float m = v[0];
-        for (int j = 1; j < K; ++j) m = fmaxf(m, v[j]);
-        float e[8], sum = 0.f;
-        for (int j = 0; j < K; ++j) { e[j] = expf(v[j] - m); sum += e[j]; }
-        const float inv = (1.f - min_bin * K) / sum;
-        float cum = 0.f;
-        t[ax * 9] = -B;
-        for (int j = 0; j < K; ++j) {
-          cum += fmaf(e[j], inv, min_bin);
-          t[ax * 9 + j + 1] = (j == K - 1) ? B : fmaf(2.f * B, cum, -B);
-        }
-      }
-      t[18] = 1.f - min_d; t[26] = 1.f - min_d;
-      for (int j = 0; j < K - 1; ++j) {
-        const float a = ro[2 * K + j];
-        t[19 + j] = min_d + (a > 20.f ? a : log1pf(expf(a)));
-      }
-    }
-  }
-}

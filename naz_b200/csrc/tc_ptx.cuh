@@ -107,6 +107,22 @@ __device__ __forceinline__ void mma_commit_elect(uint64_t* bar, uint32_t elected
       "r"(elected)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand read from tensor memory (lane = row, one 32-bit column = two consecutive-K fp16)
+__device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// registers -> TMEM, 16 lanes x 4 columns twice: threads 0-15 write lanes base..base+15 at columns [col, col+4), threads 16-31
+// the same lanes at columns [col+IMM, col+IMM+4)
+template <int IMM>
+__device__ __forceinline__ void tmem_st16x2_4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("tcgen05.st.sync.aligned.16x32bx2.x4.b32 [%0], %1, {%2,%3,%4,%5};\n" ::"r"(taddr), "n"(IMM), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ uint32_t elect_one() {
   uint32_t pred = 0;
   asm volatile(

@@ -222,9 +222,12 @@ def test_svi_importance_pipeline_on_device():
 
 
 INV_VARIANTS = [
-    {},                                       # v4 kernel, defaults
+    {},                                       # v5 kernel (one 128-row chain), defaults
     {"inv_kernel": 3},                        # round-1 kernel (kept as the A/B baseline)
-    {"inv_merge_n": 256},                     # every push issued unsplit
+    {"inv_kernel": 4},                        # two 64-row chains
+    {"inv_kernel": 4, "inv_merge_n": 256},    # ... every push issued unsplit
+    {"inv_merge_n": 0},                       # v5 with split pushes (critical columns first; forces the A operand to shared memory)
+    {"inv_a_tmem": 0},                        # v5 with the A operand in shared memory
     {"inv_fold": 0},                          # broadcast context evaluated per point (general program)
     {"inv_gate": 0},
 ]
