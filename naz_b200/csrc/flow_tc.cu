@@ -178,9 +178,10 @@ struct Builder {
   uint32_t w_off = 0;
   int slot_bytes = kSlotBytes;
   bool emit = true;   // false: only advance w_off / record the images (steps of a program variant that skips this gemm)
+  int k_align = 16;   // K-split sub-steps start at a multiple of this (v5 waits on PAIRS of K slices: 32)
   void gemm(uint8_t a_buf, int a_chunk0, int k_ext, int n_ext, int d_col, int nsplit, int accumulate, Image im,
             Step epi, int n_crit = 0) {
-    int k_sub_max = std::min(96, (slot_bytes / (n_ext * 4)) / 16 * 16);
+    int k_sub_max = std::min(96, (slot_bytes / (n_ext * 4)) / k_align * k_align);
     for (int k_off = 0; k_off < k_ext; k_off += k_sub_max) {
       int ks = std::min(k_sub_max, k_ext - k_off);
       bool last = (k_off + ks >= k_ext);
@@ -418,8 +419,10 @@ bool build_inverse(const FlowGeom& g, TcPlan& P, int variant, int merge_n, std::
     P.dp4 = ceil_to(D, 4);
     P.cp4 = g.C > 0 ? ceil_to(g.C, 4) : 0;
     int off = 0;
-    P.lc_w0x = off; off += hp(0) * P.dp4;
-    P.lc_w0c = off; off += hp(0) * P.cp4;
+    // v4: unit-major tables W0x[n][dp4], W0c[n][cp4];  v5: input-major tables W0x[q][hp0], W0c[c][hp0] (a thread's 8 units
+    // of one input are two 16-byte loads feeding packed FFMA2)
+    P.lc_w0x = off; off += v5 ? D * hp(0) : hp(0) * P.dp4;
+    P.lc_w0c = off; off += v5 ? g.C * hp(0) : hp(0) * P.cp4;
     for (int j = 0; j < nh; ++j) { P.lc_b[j] = off; off += hp(j); }
     P.lc_bout = off; off += ceil_to(D * Mp, 4);
     P.lc_r0c = off; off += 32;
@@ -436,6 +439,7 @@ bool build_inverse(const FlowGeom& g, TcPlan& P, int variant, int merge_n, std::
     if (!(g.kind == NAZB_KIND_AFFINE || (g.kind == NAZB_KIND_RQS && g.K == 8))) return false;
   }
   Builder b{steps_out, images_out};
+  if (v5) b.k_align = 32;
   bool first_push[NAZB_MAX_LIN];
   for (int j = 0; j <= nh; ++j) first_push[j] = true;
   for (int r = 0; r < D; ++r) {
@@ -1157,6 +1161,7 @@ struct Lc4Geom {
   int lc_w0x, lc_w0c, lc_b[NAZB_MAX_HIDDEN_LAYERS], lc_bout, lc_r0c, lc_floats;
   int hdim[NAZB_MAX_HIDDEN_LAYERS], hp[NAZB_MAX_HIDDEN_LAYERS];
   int dp4, cp4;
+  int qmajor;   // v5: first-layer tables stored input-major ([q][hp0], [c][hp0])
 };
 __global__ void tc_pack_lc4_kernel(int S, int L, int n_lin, int D, int C, int M, int Mp, float hscale, Lc4Geom lg,
                                    const float* const* __restrict__ Wtab, const float* const* __restrict__ btab,
@@ -1174,7 +1179,10 @@ __global__ void tc_pack_lc4_kernel(int S, int L, int n_lin, int D, int C, int M,
     if (f < lg.lc_b[0]) {
       // first-layer weights: x part (by rank) or context part
       int n, k = -1;
-      if (f < lg.lc_w0c) { n = f / lg.dp4; int q = f % lg.dp4; if (q < D) k = C + perm[l * D + q]; }
+      if (lg.qmajor) {
+        if (f < lg.lc_w0c) { int q = f / lg.hp[0]; n = f % lg.hp[0]; if (q < D) k = C + perm[l * D + q]; }
+        else { int g2 = f - lg.lc_w0c; int c = g2 / lg.hp[0]; n = g2 % lg.hp[0]; if (c < C) k = c; }
+      } else if (f < lg.lc_w0c) { n = f / lg.dp4; int q = f % lg.dp4; if (q < D) k = C + perm[l * D + q]; }
       else { int g2 = f - lg.lc_w0c; n = g2 / lg.cp4; int c = g2 % lg.cp4; if (c < C) k = c; }
       if (n < lg.hdim[0] && k >= 0) {
         int ti = l * n_lin;
@@ -1412,7 +1420,7 @@ cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* con
     if (P.inv_ver >= 4) {
       Lc4Geom lg{};
       lg.lc_w0x = P.lc_w0x; lg.lc_w0c = P.lc_w0c; lg.lc_bout = P.lc_bout; lg.lc_r0c = P.lc_r0c; lg.lc_floats = P.lc_floats;
-      lg.dp4 = P.dp4; lg.cp4 = std::max(P.cp4, 1);
+      lg.dp4 = P.dp4; lg.cp4 = std::max(P.cp4, 1); lg.qmajor = (P.inv_ver == 5) ? 1 : 0;
       for (int j = 0; j < g.n_hidden; ++j) { lg.lc_b[j] = P.lc_b[j]; lg.hdim[j] = g.hidden[j]; lg.hp[j] = ceil_to(g.hidden[j], 16); }
       tc_pack_lc4_kernel<<<blocks, 256, 0, st>>>(S, L, n_lin, g.D, g.C, g.M, P.mp_inv, 2.885390081777927f, lg, t->tab_dev,
                                                  t->tab_dev + ntab, t->tab_dev + 2 * ntab, strides_dev, strides_dev + ntab,
@@ -1461,7 +1469,9 @@ static cudaError_t launch_inv4(const nazb_handle* h, const TcState* t, const IoA
   kp.layer_bytes = P.layer_bytes[0];
   kp.lc = fold ? t->lcfold_dev : t->lc_dev;
   kp.lc_floats = P.lc_floats; kp.lc_s0 = fold ? 0 : io.s_begin;
-  kp.lc_w0x = P.lc_w0x; kp.lc_w0c = P.lc_w0c; kp.lc_b0 = P.lc_b[0]; kp.lc_r0c = P.lc_r0c; kp.dp4 = P.dp4; kp.cp4 = P.cp4;
+  kp.lc_w0x = P.lc_w0x; kp.lc_w0c = P.lc_w0c; kp.lc_b0 = P.lc_b[0]; kp.lc_r0c = P.lc_r0c;
+  kp.dp4 = (P.inv_ver == 5) ? ceil_to(g.hidden[0], 16) : P.dp4;   // v5: row stride of the input-major first-layer tables
+  kp.cp4 = P.cp4;
   kp.perm = h->perm_dev;
   kp.D = g.D; kp.C = g.C; kp.L = g.L; kp.M = g.M; kp.Mp = P.mp_inv; kp.K = g.K; kp.kind = g.kind;
   kp.nslots = P.j_nslots; kp.kr_max = P.kr_max;
@@ -1491,6 +1501,8 @@ static cudaError_t launch_inv4(const nazb_handle* h, const TcState* t, const IoA
     fp.wimg = t->wimg[0]; fp.draw_bytes = t->draw_bytes[0]; fp.layer_bytes = P.layer_bytes[0];
     fp.lc = t->lc_dev; fp.lcf = t->lcfold_dev; fp.lc_floats = P.lc_floats; fp.lc_w0c = P.lc_w0c; fp.lc_r0c = P.lc_r0c;
     fp.cp4 = std::max(P.cp4, 1); fp.lc_bout = P.lc_bout;
+    fp.w0c_sn = (P.inv_ver == 5) ? 1 : fp.cp4;                           // W0c[n][c] at n * w0c_sn + c * w0c_sc
+    fp.w0c_sc = (P.inv_ver == 5) ? ceil_to(g.hidden[0], 16) : 1;
     for (int j = 0; j < g.n_hidden; ++j) { fp.lc_b[j] = P.lc_b[j]; fp.hp[j] = ceil_to(g.hidden[j], 16); fp.blk1[j] = g.blk[j][1]; }
     fp.n_hidden = g.n_hidden; fp.L = g.L; fp.C = g.C; fp.D = g.D; fp.Mp = P.mp_inv; fp.kind = g.kind;
     fp.bound = g.bound; fp.clip_lo = g.clip_lo; fp.clip_hi = g.clip_hi;

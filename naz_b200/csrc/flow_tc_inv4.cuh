@@ -605,6 +605,7 @@ struct FoldParams {
   const float* lc;       // general layer constants [S][L][lc_floats]
   float* lcf;            // folded layer constants [s_count][L][lc_floats]
   int lc_floats, lc_w0c, lc_r0c, cp4;
+  int w0c_sn, w0c_sc;    // W0c[n][c] lives at lc_w0c + n * w0c_sn + c * w0c_sc (v4: unit-major, v5: input-major)
   int lc_b[NAZB_MAX_HIDDEN_LAYERS], lc_bout;
   int hp[NAZB_MAX_HIDDEN_LAYERS], blk1[NAZB_MAX_HIDDEN_LAYERS];   // padded widths; number of degree-0 units per hidden layer
   int n_hidden, L, C, D, Mp, kind;
@@ -631,7 +632,7 @@ __global__ void __launch_bounds__(256) inv4_fold_kernel(const __grid_constant__ 
   // first layer: b0' = b0 + W0[:, ctx] ctx (scaled domain) for every unit
   for (int n = tid; n < f.hp[0]; n += blockDim.x) {
     float a = lc[f.lc_b[0] + n];
-    for (int c = 0; c < f.C; ++c) a = fmaf(lc[f.lc_w0c + (size_t)n * f.cp4 + c], f.ctx[c], a);
+    for (int c = 0; c < f.C; ++c) a = fmaf(lc[f.lc_w0c + (size_t)n * f.w0c_sn + (size_t)c * f.w0c_sc], f.ctx[c], a);
     out[f.lc_b[0] + n] = a;
     hvec[n] = (n < f.blk1[0]) ? tanh_from_scaled(a) : 0.f;
   }

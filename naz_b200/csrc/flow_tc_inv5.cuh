@@ -22,6 +22,7 @@ constexpr int kV5Issuer = kV5EpiWarps;
 constexpr int kV5Producer = kV5EpiWarps + 1;
 constexpr int kV5Threads = (kV5EpiWarps + 2) * 32;
 constexpr int kV5MaxSlices = 8;
+constexpr int kV5MaxPairs = kV5MaxSlices / 2;   // a_ready barriers: one per PAIR of K slices (2 j, 2 j + 1), 16 arrivals each
 constexpr int kDbgEvents = 4096;
 // Debug event log (kDbg instantiation only): CTA 0, three logger warps (slot 0 = epilogue warp 0 (q 0, rows 0-15, slice lane 0),
 // slot 1 = epilogue warp 8 (same rows, slice lane 1), slot 2 = the issuer), each writing (clock, step << 8 | event) pairs.
@@ -46,8 +47,9 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
   uint64_t* bar_acc = w_empty + 8;                                  // [1] issuer -> epilogue warps
   uint64_t* lc_full = bar_acc + 2;                                  // [2]
   uint64_t* lc_empty = lc_full + 2;                                 // [2], count = kV5EpiWarps
-  uint64_t* a_ready = lc_empty + 2;                                 // [2 buffers][kV5MaxSlices]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 2 * kV5MaxSlices);
+  uint64_t* a_ready = lc_empty + 2;                                 // [2 barrier sets][kV5MaxPairs]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 2 * kV5MaxPairs);
+  volatile int* xflag = reinterpret_cast<volatile int*>(tmem_slot + 4);   // [8] x publications of each 16-row group (owner warp -> partner warp)
   float* xin = reinterpret_cast<float*>(smem + p.off_xin);          // [C][128] context rows (per-point contexts)
   float* lcs = reinterpret_cast<float*>(smem + p.off_lc);           // [2][lc_floats]
   float* ycur = reinterpret_cast<float*>(smem + p.off_y);           // [D][128] by dimension
@@ -70,8 +72,11 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
     // slice 0 of every A block also collects one arrival from each NON-producing warp of the chain: a warp that waits
     // on the accumulator barrier must be needed for the next MMA, otherwise the issuer could complete two accumulator
     // phases before a late warp has observed the first one and its parity wait would never return
-    // a K slice is produced by the 8 warps (4 quadrants x 2 row halves) of its slice lane; slice 0 also collects the 8 observers
-    for (int i = 0; i < 2 * kV5MaxSlices; ++i) tcx::mbar_init(a_ready + i, (i % kV5MaxSlices == 0) ? 16 : 8);
+    // pair j = K slices 2 j (slice lane 0) and 2 j + 1 (slice lane 1): EVERY epilogue warp arrives exactly once per pair and push
+    // (after publishing its slice, or as an observer when its lane has no slice in the pair).  A warp that waits on the
+    // accumulator barrier is therefore always needed for the next MMA group and can never be lapped by two accumulator phases.
+    for (int i = 0; i < 2 * kV5MaxPairs; ++i) tcx::mbar_init(a_ready + i, kV5EpiWarps);
+    for (int i = 0; i < 8; ++i) xflag[i] = 0;
     tcx::mbar_fence_init();
   }
   if (warp == 0) tcx::tmem_alloc(tmem_slot, kTmemCols);
@@ -178,48 +183,59 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
             // A in TMEM: ONE buffer (every MMA of a push has retired before the epilogue that writes the next block passes
             // the accumulator barrier: pushes are unsplit), K slice s at columns t_a + 8 s (hi) / t_a + kr_max / 2 + 8 s (lo)
             uint32_t ta_h = p.t_a + slice0 * 8u, ta_l = ta_h + (uint32_t)p.kr_max / 2u;
-            uint64_t* rdy = a_ready + buf * kV5MaxSlices + slice0;
-            uint32_t bit = 1u << (buf * kV5MaxSlices + slice0);
+            const uint32_t pair0 = slice0 >> 1;                 // sub-steps of a K-split push start at an even slice
+            uint64_t* rdy = a_ready + buf * kV5MaxPairs + pair0;
+            uint32_t bit = 1u << (buf * kV5MaxPairs + pair0);
             auto desc = [](uint32_t lo) { return ((uint64_t)dhi32 << 32) | lo; };
             LOG5(2, 20)
             mbar_wait4(w_full + slot, use & 1, p.wd, WD_TAG(3));
             LOG5(2, 21)
-            for (int k = 0; k < ksteps; ++k) {
+            for (int k = 0; k < ksteps; k += 2) {
               mbar_wait4(rdy, (apar & bit) ? 1u : 0u, p.wd, WD_TAG(4));
               apar ^= bit;
               tcx::tc_fence_after();
               LOG5(2, 32 + k)
-              const uint32_t acc0 = (k == 0) ? s_acc : 1u;
-              const bool lastk = (k == ksteps - 1);
+              const bool two = (k + 1 < ksteps);
+              const bool lastk = (k + 2 >= ksteps);
               if (tcx::elect_one()) {
-                // hi*hi + hi*lo + lo*hi on the critical columns, then (split pushes only) on the remaining ones
+                // hi*hi + hi*lo + lo*hi for each K slice of the pair
+                const uint32_t acc0 = (k == 0) ? s_acc : 1u;
                 if (kATmem) {
                   tcx::mma_f16_ts(d_c, ta_h, desc(db_h), idesc_c, acc0);
                   tcx::mma_f16_ts(d_c, ta_h, desc(db_l), idesc_c, 1u);
                   tcx::mma_f16_ts(d_c, ta_l, desc(db_h), idesc_c, 1u);
+                  if (two) {
+                    tcx::mma_f16_ts(d_c, ta_h + 8, desc(db_h + b_step), idesc_c, 1u);
+                    tcx::mma_f16_ts(d_c, ta_h + 8, desc(db_l + b_step), idesc_c, 1u);
+                    tcx::mma_f16_ts(d_c, ta_l + 8, desc(db_h + b_step), idesc_c, 1u);
+                  }
                 } else {
                   tcx::mma_f16_ss(d_c, desc(da_h), desc(db_h), idesc_c, acc0);
                   tcx::mma_f16_ss(d_c, desc(da_h), desc(db_l), idesc_c, 1u);
                   tcx::mma_f16_ss(d_c, desc(da_l), desc(db_h), idesc_c, 1u);
+                  if (two) {
+                    tcx::mma_f16_ss(d_c, desc(da_h + a_step), desc(db_h + b_step), idesc_c, 1u);
+                    tcx::mma_f16_ss(d_c, desc(da_h + a_step), desc(db_l + b_step), idesc_c, 1u);
+                    tcx::mma_f16_ss(d_c, desc(da_l + a_step), desc(db_h + b_step), idesc_c, 1u);
+                  }
                 }
                 if (s_last && lastk) tcx::mma_commit(bar_acc);
-                if (n_rest) {
-                  if (kATmem) {
-                    tcx::mma_f16_ts(d_r, ta_h, desc(db_h + ro), idesc_r, acc0);
-                    tcx::mma_f16_ts(d_r, ta_h, desc(db_l + ro), idesc_r, 1u);
-                    tcx::mma_f16_ts(d_r, ta_l, desc(db_h + ro), idesc_r, 1u);
-                  } else {
-                    tcx::mma_f16_ss(d_r, desc(da_h), desc(db_h + ro), idesc_r, acc0);
-                    tcx::mma_f16_ss(d_r, desc(da_h), desc(db_l + ro), idesc_r, 1u);
-                    tcx::mma_f16_ss(d_r, desc(da_l), desc(db_h + ro), idesc_r, 1u);
+                if (n_rest) {   // split pushes (A in shared memory only): the remaining columns
+                  tcx::mma_f16_ss(d_r, desc(da_h), desc(db_h + ro), idesc_r, acc0);
+                  tcx::mma_f16_ss(d_r, desc(da_h), desc(db_l + ro), idesc_r, 1u);
+                  tcx::mma_f16_ss(d_r, desc(da_l), desc(db_h + ro), idesc_r, 1u);
+                  if (two) {
+                    tcx::mma_f16_ss(d_r, desc(da_h + a_step), desc(db_h + b_step + ro), idesc_r, 1u);
+                    tcx::mma_f16_ss(d_r, desc(da_h + a_step), desc(db_l + b_step + ro), idesc_r, 1u);
+                    tcx::mma_f16_ss(d_r, desc(da_l + a_step), desc(db_h + b_step + ro), idesc_r, 1u);
                   }
                 }
                 if (lastk) tcx::mma_commit(w_empty + slot);   // the slot is free once these MMAs retire
               }
               __syncwarp();
               LOG5(2, 48 + k)
-              da_h += a_step; da_l += a_step; db_h += b_step; db_l += b_step;
-              ta_h += 8; ta_l += 8;
+              da_h += 2 * a_step; da_l += 2 * a_step; db_h += 2 * b_step; db_l += 2 * b_step;
+              ta_h += 16; ta_l += 16;
               ++rdy; bit <<= 1;
             }
             LOG5(2, 23)
@@ -252,6 +268,26 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
     uint32_t par_acc = 0, lcnt = 0, buf = 0;
     int dbg_n = 0;
     const int dbg_slot = sll;
+    // x_r hand-over inside a 16-row group: the owner warp (slice lane 0) publishes every x it finalises by bumping a
+    // shared-memory counter, its partner warp (slice lane 1) counts the same program steps and polls the counter before
+    // a first-layer phase that needs x (a 64-thread bar.sync cost ~300 cycles here, on the critical path of every stage)
+    volatile int* my_xflag = xflag + q * 2 + rh;
+    int xcount = 0;
+    float pend_n = 1.f, pend_d = 1.f;   // deferred log-dets: product of the pending spline derivative numerators / denominators
+    auto flush_ld = [&](float& ld_acc) {
+      // ld = log(num) - 2 log(den) of every pending inverse, taken off the critical path (after a publish)
+      ld_acc += (tcx::lg2_approx(pend_n) - 2.f * tcx::lg2_approx(pend_d)) * 0.6931471805599453f;
+      pend_n = 1.f; pend_d = 1.f;
+    };
+    auto publish_x = [&]() {   // owner warp, after the owner lanes stored x into xr
+      ++xcount;
+      __syncwarp();
+      if (lane == 0) { __threadfence_block(); *my_xflag = xcount; }
+    };
+    auto await_x = [&]() {     // partner warp: every x published so far is visible
+      if (lane == 0) { while ((int)(*my_xflag - xcount) < 0) { } __threadfence_block(); }
+      __syncwarp();
+    };
     const uint64_t scale2 = tcx::pk2(kTanhScale, kTanhScale);
 
     // write this thread's 8-column chunk `c` (hi / lo fp16) of the A block: layout [chunk][64 rows][8 halves]
@@ -273,7 +309,12 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
       if (kATmem) { tcx::tmem_st_wait(); tcx::tc_fence_before(); }
       else tcx::fence_async_smem();
       __syncwarp();
-      if (lane == 0) tcx::mbar_arrive(my_ready + buf * kV5MaxSlices + sl);
+      if (lane == 0) tcx::mbar_arrive(my_ready + buf * kV5MaxPairs + (sl >> 1));
+    };
+    // pairs in which this warp's slice lane has no slice (only the last pair of a block with an odd slice count)
+    auto observe = [&](int nsl) {
+      const int npairs = (nsl + 1) >> 1;
+      if (2 * (npairs - 1) + sll >= nsl && lane == 0) tcx::mbar_arrive(my_ready + buf * kV5MaxPairs + (npairs - 1));
     };
 
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -333,7 +374,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
               // block of nch 8-column chunks = nsl K slices; slice s = chunks {2s (half-warp 0), 2s+1 (half-warp 1)}
               const int nch = s_encols >> 3, nsl = (nch + 1) >> 1;
               const int nmine = (nsl - sll + 1) / 2;   // slices sll, sll + 2, ...
-              if (sll != 0 && lane == 0) tcx::mbar_arrive(my_ready + buf * kV5MaxSlices);   // observer arrival on slice 0
+              observe(nsl);
               for (int j0 = 0; j0 < nmine; j0 += 2) {
                 uint32_t r[16];
                 const int nj = min(2, nmine - j0);
@@ -372,73 +413,45 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
               // first conditioner layer of block `stage` on CUDA cores: s = b'[n] + sum_c W0c[n][c] ctx_c + sum_{q < stage} W0x[n][q] x_q
               // (everything pre-multiplied by 2 log2 e), tanh, fp16 hi/lo A block.  x_q (by rank) were written by the row owners.
               const int r = (int)s_stage;
-              if (r > 0) pair_bar_sync(pair_id, 64);   // x_{r-1} of these rows is visible
+              if (r > 0 && !rows_mine) await_x();   // x_{r-1} of these rows is visible (the owner warp wrote it itself)
               LOG5(dbg_slot, 4)
               const int nch = s_encols >> 3, nsl = (nch + 1) >> 1;
               const int u0 = s_eaux;
               const int nmine = (nsl - sll + 1) / 2;
-              if (sll != 0 && lane == 0) tcx::mbar_arrive(my_ready + buf * kV5MaxSlices);   // observer arrival on slice 0
-              float xv[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (k < r) xv[k] = xr[k * kTileM + trow];
-              float cv[4] = {0.f, 0.f, 0.f, 0.f};
-              if (add_ctx) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  if (k < C) cv[k] = xin[k * kTileM + trow];
-              }
+              observe(nsl);
+              // q-major weights: lc_w0x[q][n] (x of rank q -> unit n), lc_w0c[c][n] (context c -> unit n), everything scaled by
+              // 2 log2 e; a thread's 8 units are two 16-byte loads per input and the update is 4 packed FFMA2
+              const int hp0 = p.dp4;   // v5: KParamsInv4::dp4 carries the padded width of hidden layer 0 = row stride of both tables
               for (int j = 0; j < nmine; ++j) {
                 const int sl = sll + j * 2;
                 const int c = sl * 2 + hw;
                 uint4 hi4 = make_uint4(0, 0, 0, 0), lo4 = hi4;
                 if (c < nch) {
                   const int nb = u0 + c * 8;
-                  float acc[8];
-                  const float4* bb = reinterpret_cast<const float4*>(lc + p.lc_b0 + nb);
-                  const float4 ba = bb[0], bc = bb[1];
-                  acc[0] = ba.x; acc[1] = ba.y; acc[2] = ba.z; acc[3] = ba.w;
-                  acc[4] = bc.x; acc[5] = bc.y; acc[6] = bc.z; acc[7] = bc.w;
-                  if (add_ctx) {
-                    for (int k4 = 0; k4 < p.cp4; k4 += 4) {
-#pragma unroll
-                      for (int e = 0; e < 8; ++e) {
-                        const float4 w = *reinterpret_cast<const float4*>(lc + p.lc_w0c + (size_t)(nb + e) * p.cp4 + k4);
-                        if (k4 == 0) {
-                          acc[e] = fmaf(w.x, cv[0], acc[e]); acc[e] = fmaf(w.y, cv[1], acc[e]);
-                          acc[e] = fmaf(w.z, cv[2], acc[e]); acc[e] = fmaf(w.w, cv[3], acc[e]);
-                        } else {
-                          acc[e] = fmaf(w.x, xin[(k4 + 0) * kTileM + trow], acc[e]);
-                          acc[e] = fmaf(w.y, (k4 + 1 < C) ? xin[(k4 + 1) * kTileM + trow] : 0.f, acc[e]);
-                          acc[e] = fmaf(w.z, (k4 + 2 < C) ? xin[(k4 + 2) * kTileM + trow] : 0.f, acc[e]);
-                          acc[e] = fmaf(w.w, (k4 + 3 < C) ? xin[(k4 + 3) * kTileM + trow] : 0.f, acc[e]);
-                        }
-                      }
-                    }
-                  }
-                  if (r > 0) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                      const float4 w = *reinterpret_cast<const float4*>(lc + p.lc_w0x + (size_t)(nb + e) * p.dp4);
-                      acc[e] = fmaf(w.x, xv[0], acc[e]); acc[e] = fmaf(w.y, xv[1], acc[e]);
-                      acc[e] = fmaf(w.z, xv[2], acc[e]); acc[e] = fmaf(w.w, xv[3], acc[e]);
-                    }
-                  }
-                  for (int k4 = 4; k4 < r; k4 += 4) {   // D > 5 only
-                    const float x0 = xr[k4 * kTileM + trow];
-                    const float x1 = (k4 + 1 < r) ? xr[(k4 + 1) * kTileM + trow] : 0.f;
-                    const float x2 = (k4 + 2 < r) ? xr[(k4 + 2) * kTileM + trow] : 0.f;
-                    const float x3 = (k4 + 3 < r) ? xr[(k4 + 3) * kTileM + trow] : 0.f;
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                      const float4 w = *reinterpret_cast<const float4*>(lc + p.lc_w0x + (size_t)(nb + e) * p.dp4 + k4);
-                      acc[e] = fmaf(w.x, x0, acc[e]); acc[e] = fmaf(w.y, x1, acc[e]);
-                      acc[e] = fmaf(w.z, x2, acc[e]); acc[e] = fmaf(w.w, x3, acc[e]);
-                    }
-                  }
                   uint64_t s2[4];
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) s2[i] = tcx::pk2(acc[2 * i], acc[2 * i + 1]);
+                  {
+                    const ulonglong2* bb = reinterpret_cast<const ulonglong2*>(lc + p.lc_b0 + nb);
+                    const ulonglong2 b0 = bb[0], b1 = bb[1];
+                    s2[0] = b0.x; s2[1] = b0.y; s2[2] = b1.x; s2[3] = b1.y;
+                  }
+                  if (add_ctx) {
+                    for (int k = 0; k < C; ++k) {
+                      const float xc = xin[k * kTileM + trow];
+                      const uint64_t x2 = tcx::pk2(xc, xc);
+                      const ulonglong2* ww = reinterpret_cast<const ulonglong2*>(lc + p.lc_w0c + (size_t)k * hp0 + nb);
+                      const ulonglong2 w0 = ww[0], w1 = ww[1];
+                      s2[0] = tcx::fma2(w0.x, x2, s2[0]); s2[1] = tcx::fma2(w0.y, x2, s2[1]);
+                      s2[2] = tcx::fma2(w1.x, x2, s2[2]); s2[3] = tcx::fma2(w1.y, x2, s2[3]);
+                    }
+                  }
+                  for (int k = 0; k < r; ++k) {
+                    const float xq = xr[k * kTileM + trow];
+                    const uint64_t x2 = tcx::pk2(xq, xq);
+                    const ulonglong2* ww = reinterpret_cast<const ulonglong2*>(lc + p.lc_w0x + (size_t)k * hp0 + nb);
+                    const ulonglong2 w0 = ww[0], w1 = ww[1];
+                    s2[0] = tcx::fma2(w0.x, x2, s2[0]); s2[1] = tcx::fma2(w0.y, x2, s2[1]);
+                    s2[2] = tcx::fma2(w1.x, x2, s2[2]); s2[3] = tcx::fma2(w1.y, x2, s2[3]);
+                  }
                   tcx::tanh8_scaled(s2, hi4, lo4);
                 }
                 if (kATmem) __syncwarp();   // the TMEM store is warp-collective: reconverge after the per-chunk branch
@@ -446,6 +459,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
                 publish(sl);
                 LOG5(dbg_slot, 8 + sl)
               }
+              if (fast_rqs && owner) flush_ld(ld_acc);   // log-dets of the inverses since the last flush, off the critical path
               buf ^= 1;
             } else if (s_epi == EPI_XINV0C) {
               // context-folded rank 0: the transform parameters are per-draw constants (lc_r0c), no accumulator involved
@@ -460,7 +474,10 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
                 ld_acc += ld;
                 if (D == 1) ycur[d * kTileM + trow] = xv;
               }
-            } else if (s_epi == EPI_XINV && rows_mine) {
+              if (rows_mine) publish_x(); else ++xcount;
+            } else if (s_epi == EPI_XINV && !rows_mine) {
+              ++xcount;
+            } else if (s_epi == EPI_XINV) {
               const int r = s_stage, d = perm[r];
               const float yv = ycur[d * kTileM + trow];
               const float* bo = lc + s_eaux;
@@ -492,7 +509,9 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
                 const float dr[8] = {__uint_as_float(rd[0]) + e0.x, __uint_as_float(rd[1]) + e0.y, __uint_as_float(rd[2]) + e0.z,
                                      __uint_as_float(rd[3]) + e0.w, __uint_as_float(rd[4]) + e1.x, __uint_as_float(rd[5]) + e1.y,
                                      __uint_as_float(rd[6]) + e1.z, 0.f};
-                nazb::rqs8_inv_pair(yv, p.bound, own, dr, hw, xv, ld);
+                float dn, dd;
+                nazb::rqs8_inv_pair_nolog(yv, p.bound, own, dr, hw, xv, dn, dd);
+                pend_n *= dn; pend_d *= dd;
               } else {
                 for (int m0 = 0; m0 < p.Mp; m0 += 8) {
                   uint32_t rr[8];
@@ -512,8 +531,9 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
               }
               tcx::tc_fence_before();
               LOG5(dbg_slot, 5)
+              if (owner) xr[r * kTileM + trow] = xv;   // published first: the next stage's first layer waits for it
+              publish_x();
               if (owner) {
-                xr[r * kTileM + trow] = xv;   // published first: the next stage's first layer waits for it
                 ld_acc += ld;
                 if (r == D - 1) {
                   // end of this flow layer: x becomes the y of the next (earlier) layer
@@ -536,6 +556,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
           if (owner) {
             float qd = 0.f;
             for (int d = 0; d < D; ++d) { float z = ycur[d * kTileM + trow]; qd += 0.5f * z * z; }
+            if (fast_rqs) flush_ld(ld_acc);
             lp = -qd - 0.5f * D * NAZB_LOG_2PI - ld_acc + ljac[trow];
           }
           if (mine) {

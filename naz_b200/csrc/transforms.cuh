@@ -263,6 +263,72 @@ __device__ __forceinline__ void rqs8_inv_pair(float in, float B, const float* ow
   ld_fwd = inside ? (lg2(dnum) - 2.f * lg2(den)) * LN2 : 0.f;
 }
 
+// Same, but returns the two factors of the forward derivative instead of its logarithm: ld_fwd = log(dnum) - 2 log(den)
+// (dnum = den = 1 outside the box), so the caller can take the logarithms off the critical path.
+__device__ __forceinline__ void rqs8_inv_pair_nolog(float in, float B, const float* own, const float* dr, int hw, float& out,
+                                                    float& dnum_out, float& den_out) {
+  constexpr int K = 8;
+  const float min_bin = 1e-3f, min_d = 1e-3f, eps = 1e-6f;
+  const float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+  (void)LN2;
+  auto ex2 = [](float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; };
+  auto lg2 = [](float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; };
+  auto rcp = [](float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; };
+  auto sqr = [](float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; };
+  float m = own[0];
+#pragma unroll
+  for (int j = 1; j < K; ++j) m = fmaxf(m, own[j]);
+  float e[K], sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < K; ++j) { e[j] = ex2((own[j] - m) * LOG2E); sum += e[j]; }
+  const float inv = (1.f - min_bin * K) * rcp(sum);
+  float kn[K + 1], cum = 0.f;
+  kn[0] = -B;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    cum += fmaf(e[j], inv, min_bin);
+    kn[j + 1] = (j == K - 1) ? B : fmaf(2.f * B, cum, -B);
+  }
+  // bin = #{j in 1..K-1 : in >= knot_j + eps}, decided on the heights lane
+  int cnt = 0;
+#pragma unroll
+  for (int j = 1; j < K; ++j) cnt += (in >= kn[j] + eps) ? 1 : 0;
+  const int k = __shfl_sync(0xffffffffu, cnt, (threadIdx.x & 15) | 16);
+  float lo = kn[0], hi = kn[1];
+#pragma unroll
+  for (int j = 1; j < K; ++j)
+    if (k == j) { lo = kn[j]; hi = kn[j + 1]; }
+  // derivative at the left (lane half 0) / right (lane half 1) knot of the bin; the end knots are fixed
+  const int di = k - 1 + hw;
+  float draw = dr[0];
+#pragma unroll
+  for (int j = 1; j < K - 1; ++j)
+    if (di == j) draw = dr[j];
+  const float sp = draw > 20.f ? draw : lg2(1.f + ex2(draw * LOG2E)) * LN2;
+  const float dv = (di < 0 || di > K - 2) ? (1.f - min_d) : (min_d + sp);
+  const float width = hi - lo;
+  const float p_lo = __shfl_xor_sync(0xffffffffu, lo, 16), p_w = __shfl_xor_sync(0xffffffffu, width, 16);
+  const float p_d = __shfl_xor_sync(0xffffffffu, dv, 16);
+  const float sel_x = hw ? p_lo : lo, sel_w = hw ? p_w : width, d0 = hw ? p_d : dv;
+  const float sel_y = hw ? lo : p_lo, sel_h = hw ? width : p_w, d1 = hw ? dv : p_d;
+  const float delta = sel_h * rcp(sel_w);
+  const float t2 = d0 + d1 - 2.f * delta;
+  const float dy = in - sel_y;
+  const float a = fmaf(dy, t2, sel_h * (delta - d0));
+  const float b = fmaf(-dy, t2, sel_h * d0);
+  const float c = -delta * dy;
+  const float disc = fmaf(b, b, -4.f * a * c);
+  const float th = (2.f * c) * rcp(-b - sqr(fmaxf(disc, 0.f)));
+  const float tomt = th * (1.f - th), omt = 1.f - th;
+  const float den = fmaf(t2, tomt, delta);
+  const float dnum = delta * delta * fmaf(d1, th * th, fmaf(2.f * delta, tomt, d0 * omt * omt));
+  const bool inside = (in >= -B && in <= B);
+  out = inside ? fmaf(th, sel_w, sel_x) : in;
+  dnum_out = inside ? dnum : 1.f;
+  den_out = inside ? den : 1.f;
+}
+
+
 // Logit bounding transform of one coordinate (transforms.py:20-23): returns y, adds to log_jac.
 __device__ __forceinline__ float bound_fwd(float x, float lo, float hi, float& log_jac) {
   float u = (x - lo) / (hi - lo);
