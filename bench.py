@@ -49,8 +49,30 @@ def parse():
                     help="draw groups per rank (0 = auto: ~8 draws per group so a group's packed weights stay L2-resident "
                          "while the CTAs sweep their point tiles)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aux", action="store_true", help="skip the auxiliary workloads (configs 2, 4, 5)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the post-run parity probe against the fp64 oracle")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     return ap.parse_args()
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def workload_config(name, cfg, S, N):
+    """The workload definition: identical keys AND values in both arms (the driver compares the two `config` dicts);
+    everything specific to one arm lives under `detail`."""
+    kind, D, C, hidden, L, K, _, _ = cfg
+    return {"workload": name, "flow": kind, "D": D, "C": C, "hidden": list(hidden), "layers": L, "count_bins": K, "draws": S, "points": N,
+            "output": "logsumexp_s(lp) - log S  [N]", "context": "one [C] vector broadcast to all points (calibrate.py:85,126)",
+            "l2": "GPU arm: the packed weights of the draws (GBs) are streamed every step and exceed the 126 MB L2; CPU arm: not applicable"}
 
 
 def flops_per_eval(D, C, hidden, L, M):
@@ -117,9 +139,11 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------
 # reference CPU path (oracle port): torch fp32 on all host cores, the reference's own structure
 # --------------------------------------------------------------------------------------
-def cpu_reference_rate(cfg, seconds: float, threads=None):
+def cpu_reference_rate(cfg, seconds: float, threads=None, device=None):
     """Times oracle/pyro_style.py (the reference's torch path restated; pyro is not installable here) on a
-    bounded sample of the workload.  Returns (evals_per_s, cores, sample_description)."""
+    bounded sample of the workload: on the host cores (device=None: the CPU baseline / reference arm) or, with a CUDA
+    device, through stock eager PyTorch on the GPU (the "reference GPU path" of BASELINE.md §3).
+    Returns (evals_per_s, cores, sample_description)."""
     import numpy as np
     import torch
     from oracle import flow_oracle as fo
@@ -136,21 +160,41 @@ def cpu_reference_rate(cfg, seconds: float, threads=None):
     draws = fo.perturb_draws(p0, n_draws, 0.25, rng, np.float32)
     tdraws = [[(torch.from_numpy(W), torch.from_numpy(b)) for (W, b) in layer] for layer in draws]
     ctx = torch.from_numpy(rng.uniform(size=(C,)).astype(np.float32)) if C else None
+    on_gpu = device is not None
+    if on_gpu:
+        flow = flow.to(device)
+        flow.base_dist = torch.distributions.Normal(torch.zeros(D, device=device), torch.ones(D, device=device))
+        tdraws = [[(W.to(device), b.to(device)) for (W, b) in layer] for layer in tdraws]
+        ctx = None if ctx is None else ctx.to(device)
 
     def run(npts):
         x = torch.from_numpy((rng.normal(size=(npts, D)) * 1.5).astype(np.float32))
+        if on_gpu:
+            x = x.to(device)
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
         ps.log_prob_draws_reference_loop(flow, tdraws, x, ctx)
+        if on_gpu:
+            torch.cuda.synchronize()
         return time.perf_counter() - t0
 
     run(512)                                   # warm-up
     probe_n = 4096
     t = run(probe_n)
     rate = n_draws * probe_n / t
-    npts = int(max(probe_n, min(400_000, rate * seconds / n_draws)))
+    npts = int(max(probe_n, min(2_000_000 if on_gpu else 400_000, rate * seconds / n_draws)))
     t = run(npts)
     cpu_reference_rate.last_seconds = t
-    return n_draws * npts / t, cores, f"{n_draws} draws x {npts} points of the {L}-layer {kind} D={D}|C={C} flow, fp32 torch CPU, {t:.1f} s"
+    where = "eager PyTorch on the B200 (oracle port; upstream ships no Blackwell kernel)" if on_gpu else f"fp32 torch CPU ({cpu_model()})"
+    return n_draws * npts / t, cores, f"{n_draws} draws x {npts} points of the {L}-layer {kind} D={D}|C={C} flow, {where}, {t:.1f} s"
+
+
+def pyro_found():
+    try:
+        import pyro  # noqa: F401
+        return True
+    except Exception:
+        return False
 
 
 def main_reference(args):
@@ -159,6 +203,8 @@ def main_reference(args):
         return 0
     cfg = CONFIGS[args.config]
     kind, D, C, hidden, L, K, S, N = cfg
+    S = args.draws or S
+    N = args.points or N
     vals, secs = [], []
     for i in range(args.warmup + args.steps):
         rate, cores, sample = cpu_reference_rate(cfg, max(2.0, args.cpu_seconds / 2))
@@ -170,9 +216,10 @@ def main_reference(args):
         "impl": "reference", "metric": "log-prob evals/s (weight-draws x points)", "value": v, "unit": "evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.config, "flow": kind, "D": D, "C": C, "hidden": hidden, "layers": L, "draws": S,
-                   "points": N, "note": "reference CPU path = oracle/pyro_style.py (pyro-ppl is not installable here), bounded sample per step"},
-        "cpu_baseline": {"value": v, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args.config, cfg, S, N),
+        "detail": {"note": "reference CPU path = oracle/pyro_style.py (pyro-ppl is not installable here), bounded sample per step",
+                   "pyro_found": pyro_found()},
+        "cpu_baseline": {"value": v, "unit": "evals/s", "cores": cores, "cpu_model": cpu_model(), "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -183,6 +230,76 @@ def main_reference(args):
 # --------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------
+def parity_probe(flow, probe_draws, x, ctx, eng, kind, D, C, hidden, L, K):
+    """2 draws x 4096 points of the timed configuration (same weights, same inputs) against the fp64 oracle (checker only).
+    viol = fraction outside |cuda - ref| <= 1e-5 + 1e-4 |ref|; worst = largest error / tolerance."""
+    import numpy as np
+    from oracle import flow_oracle as fo
+    spec = fo.FlowSpec(kind, D, C, list(hidden), L, flow.perms().numpy(), count_bins=K)
+    out = eng.inverse(x, ctx, None, want_lp=True, s_begin=0, s_count=2)["lp"].cpu().numpy().astype(np.float64)
+    d64 = [[(W.astype(np.float64), b.astype(np.float64)) for (W, b) in lay] for lay in probe_draws]
+    ref, _ = fo.log_prob_draws(spec, d64, x.cpu().numpy().astype(np.float64), None if ctx is None else ctx.cpu().numpy().astype(np.float64))
+    err = np.abs(out - ref)
+    tol = 1e-5 + 1e-4 * np.abs(ref)
+    return {"viol": float((err > tol).mean()), "worst": float((err / tol).max()), "max_abs_err": float(err.max()),
+            "checked": "2 draws x %d points of the timed weights / inputs vs the fp64 oracle (oracle/flow_oracle.py)" % x.shape[0],
+            "tolerance": "1e-4 relative + 1e-5 absolute"}
+
+
+def aux_workloads(dev, gen, peak_tf, engine):
+    """SURVEY §8(d) configs 2, 4 and the log_prob leg of config 5 at full size (kernel time, CUDA events); every entry carries its
+    own algorithmic F1 and roofline fraction.  Not part of `value`."""
+    import torch
+    from naz_b200.flows.flow import NormalizingFlow
+    specs = {
+        # name: (kind, D, C, hidden, L, K, S, N, per-point context, dropout masks)
+        "aux_cfg2": ("maf", 6, 4, [150] * 3, 16, 8, 100, 100_000, True, True),
+        "aux_cfg4": ("maf", 2, 2, [150] * 3, 16, 8, 256, 1_000_000, True, False),
+        "aux_cfg5_logprob_maf_8d": ("maf", 8, 4, [150] * 3, 16, 8, 1000, 10_000, False, False),
+        "aux_cfg5_logprob_maf_16d": ("maf", 16, 4, [150] * 3, 16, 8, 1000, 10_000, False, False),
+        "aux_cfg5_logprob_nsa_8d": ("nsa", 8, 4, [150] * 3, 16, 8, 1000, 10_000, False, False),
+    }
+    res = {}
+    for name, (kind, D, C, hidden, L, K, S, N, per_point, dropout) in specs.items():
+        try:
+            torch.manual_seed(5)
+            if kind == "nsa":
+                fl = NormalizingFlow("nsa", None, D, C, hidden, L, K, engine=engine).to(dev)
+            else:
+                fl = NormalizingFlow("maf", None, D, C, hidden, L, engine=engine).to(dev)
+            x = torch.randn((N, D), device=dev, generator=gen) * 1.5
+            ctx = torch.rand((N, C) if per_point else (C,), device=dev, generator=gen)
+            if dropout:
+                keep = (torch.rand((S, L, len(hidden), max(hidden)), device=dev, generator=gen) > 0.25).float()
+                eng = fl.make_engine(fl.current_draw(), keep=keep, p_drop=0.25, device=dev)
+            else:
+                draws = [[(lin.weight.detach().unsqueeze(0) * (1 + 0.25 * (torch.rand((S,) + tuple(lin.weight.shape), device=dev, generator=gen) * 2 - 1)),
+                           lin.bias.detach().unsqueeze(0) * (1 + 0.25 * (torch.rand((S,) + tuple(lin.bias.shape), device=dev, generator=gen) * 2 - 1)))
+                          for lin in arn.layers] for arn in fl.nets]
+                eng = fl.make_engine(draws, device=dev)
+                del draws
+            run = lambda: eng.inverse(x, ctx, None, want_lp=False, want_lse=True, want_sum=True)
+            run()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            o = run()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            f1 = flops_per_eval(D, C, hidden, L, fl.shape.M)
+            ev = float(S) * N / (ms * 1e-3)
+            res[name] = {"value": ev, "unit": "evals/s", "ms": ms, "draws": S, "points": N, "flow": f"{kind} {D}|{C} {hidden} x{L}",
+                         "context": "per point" if per_point else "one vector", "engine": eng.engine_for("inverse"),
+                         "engine_options": eng.options(), "flops_per_eval": f1, "roofline_frac": f1 * ev / 1e12 / peak_tf,
+                         "finite": bool(torch.isfinite(o["sum_n"]).all().item())}
+            del eng, o, x, ctx, fl
+            torch.cuda.empty_cache()
+        except Exception as e:
+            res[name] = {"unavailable": repr(e)}
+    return res
+
+
 def main_ours(args):
     import numpy as np
     import torch
@@ -225,6 +342,8 @@ def main_ours(args):
             ub = torch.rand((S_loc,) + tuple(b.shape), device=dev, generator=gen) * 2 - 1
             lay.append((W.unsqueeze(0) * (1 + 0.25 * uW), b.unsqueeze(0) * (1 + 0.25 * ub)))
         draws.append(lay)
+    # the first two draws stay on the host for the post-run parity probe against the fp64 oracle
+    probe_draws = [[(W[:2].cpu().numpy().copy(), b[:2].cpu().numpy().copy()) for (W, b) in lay] for lay in draws] if rank == 0 else None
     t0 = time.perf_counter()
     eng = flow.make_engine(draws, device=dev)
     torch.cuda.synchronize()
@@ -334,6 +453,23 @@ def main_ours(args):
                     "note": "nazb_inverse_grad: value + d/d(all weights) of sum_n lp per chain (first cut of row f1; not part of `value`)"}
         del geng, gr, gdraws
 
+    # parity probe: the weights and inputs that were just timed, 2 draws x 4096 points, against the fp64 oracle
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = parity_probe(flow, probe_draws, x_dev[:4096], c_dev, eng, kind, D, C, hidden, L, K)
+    # auxiliary workloads: each with its own F1-based roofline fraction
+    aux = {}
+    if world == 1 and not args.no_aux:
+        peaks0, _ = load_peaks()
+        aux = aux_workloads(dev, gen, float(peaks0.get("bf16_tflops_sustained", peaks0.get("bf16_tflops"))), args.engine)
+    ref_gpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            rate_g, _, sample_g = cpu_reference_rate(CONFIGS[args.config], min(args.cpu_seconds, 6.0), device=dev)
+            ref_gpu = {"value": rate_g, "unit": "evals/s", "kind": "port", "sample": sample_g}
+        except Exception as e:   # the oracle port is test infrastructure: never let it take the bench line down
+            ref_gpu = {"unavailable": repr(e)}
+
     tms = torch.tensor([total_ms, e2e_s * 1e3, k_ms, fwd_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -364,16 +500,17 @@ def main_ours(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (fp16 hi/lo-split tcgen05 MMAs, fp32 TMEM accumulate)"
             if eng.engine_for("inverse") == "tcgen05" else "f32",
             "data": "synthetic",
-            "config": {"workload": args.config, "flow": kind, "D": D, "C": C, "hidden": hidden, "layers": L, "count_bins": K,
-                       "draws": S, "points": N, "draws_per_gpu": S_loc, "output": "logsumexp_s(lp) - log S  [N]",
+            "config": workload_config(args.config, CONFIGS[args.config], S, N),
+            "detail": {"draws_per_gpu": S_loc,
                        "parallelism": f"draw-sharded x{world}, one all-gather of the per-rank log-sum-exp partials [N]",
-                       "draw_groups_per_gpu": n_groups,
-                       "engine": eng.engine_for("inverse"), "l2": ("inputs larger than L2: %.1f GB of packed weights streamed per step" % (eng.packed_bytes / 1e9))
+                       "draw_groups_per_gpu": n_groups, "engine": eng.engine_for("inverse"), "engine_options": eng.options(),
+                       "packed_weights_gb": eng.packed_bytes / 1e9,
+                       "l2": ("inputs larger than L2: %.1f GB of packed weights streamed per step" % (eng.packed_bytes / 1e9))
                        if eng.packed_bytes > 126e6 else "dev-size run: packed weights fit L2 (not a judged configuration)",
-                       "pack_seconds_excluded": pack_s, "result_finite": finite},
+                       "pack_seconds_excluded": pack_s, "result_finite": finite, "pyro_found": pyro_found()},
             "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
                          "traffic": traffic, "peak_source": f"{peak_kind} bf16 dense, sustained",
-                         "note": "achieved = algorithmic F1 (%d flop/eval, masks as dense zeros, never the D-pass count) x evals per launch / CUDA-event kernel time; the kernel issues 3 fp16 MMAs per algorithmic product (M = 64 tiles); ncu: tensor pipe ~32 %% active, MUFU ~20 %%, the kernel is bound by the dependency chain of the autoregressive inverse (DESIGN.md 5.2)" % f1},
+                         "note": "achieved = algorithmic F1 (%d flop/eval, masks as dense zeros, never the D-pass count, never reduced by the context fold) x evals per launch / CUDA-event time of the launch (fold kernel + flow_tc_inv5_kernel); 3 fp16 MMAs per algorithmic product (M = 128, A operand in TMEM); bound by the dependency chain of the autoregressive inverse and the epilogue instruction issue (DESIGN.md 5.2)" % f1},
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(x_host.numel() * 4 + (C * 4 if C else 0)),
                     "d2h_bytes_per_step": int(N * 4)},
             "gpu_launches": int(launches),
@@ -384,9 +521,14 @@ def main_ours(args):
         }
         if aux_grad is not None:
             out["aux_grad_direction"] = aux_grad
+        out.update(aux)
+        if parity is not None:
+            out["parity"] = parity
+        if ref_gpu is not None:
+            out["reference_gpu"] = ref_gpu
         if not args.no_cpu_baseline and world == 1:
             rate, cores, sample = cpu_reference_rate(CONFIGS[args.config], args.cpu_seconds)
-            out["cpu_baseline"] = {"value": rate, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample}
+            out["cpu_baseline"] = {"value": rate, "unit": "evals/s", "cores": cores, "cpu_model": cpu_model(), "kind": "port", "sample": sample}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

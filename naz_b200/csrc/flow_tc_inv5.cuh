@@ -380,14 +380,17 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
                 const int nj = min(2, nmine - j0);
                 const int sl0 = sll + j0 * 2;
                 const uint32_t ta = lane_base + s_ecol + sl0 * 16;
+                // software-pipelined accumulator reads (TMEM -> registers runs at ~64 B/clk for the whole SM: 450 cycles for a
+                // 56-column block): the second slice of this warp is in flight while the first one goes through tanh
                 tcx::tmem_ld16x2_8<8>(ta, r);
-                if (nj > 1) tcx::tmem_ld16x2_8<8>(ta + 32, r + 8);
                 tcx::tmem_ld_wait();
+                if (nj > 1) tcx::tmem_ld16x2_8<8>(ta + 32, r + 8);
                 tcx::tc_fence_before();
                 LOG5(dbg_slot, 3)
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                   if (u < nj) {
+                    if (u == 1) { tcx::tmem_ld_wait(); tcx::tc_fence_before(); }
                     const int sl = sl0 + u * 2;
                     const int c = sl * 2 + hw;
                     const int cl = min(c, nch - 1);

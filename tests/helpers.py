@@ -63,7 +63,9 @@ def load_golden(name):
 GOLDEN = ["maf_uncond_2d", "maf_cond_3d", "nsa_cond_4d", "nsa_uncond_2d_k5", "nsa_linear_3d"]
 
 # REFERENCE outputs: produced by executing the reference's own bflow_jax_maf.py (tools/make_reference_goldens.py)
-REF_TWIN = ["ref_twin_maf_cond_3d", "ref_twin_maf_cond_6d", "ref_twin_maf_uncond_2d", "ref_twin_maf_bcast_ctx_2d"]
+REF_TWIN = ["ref_twin_maf_cond_3d", "ref_twin_maf_cond_6d", "ref_twin_maf_uncond_2d", "ref_twin_maf_bcast_ctx_2d",
+            # bench depth ([150] x 3 hidden, 16 flow layers); weights regenerated from the generator's seed (see load_ref_twin)
+            "ref_twin_deep_maf_2d", "ref_twin_deep_maf_6d", "ref_twin_deep_maf_8d_bcast"]
 
 
 def load_ref_twin(name):
@@ -73,5 +75,38 @@ def load_ref_twin(name):
     D, C, L = int(g["D"]), int(g["C"]), int(g["L"])
     hidden = [int(h) for h in g["hidden"]]
     spec = fo.FlowSpec("maf", D, C, hidden, L, g["perms"])
+    if "weights_regenerated" in g.files:
+        # replay tools/make_reference_goldens.py::main statement by statement (same Generator, same draw order)
+        rng = np.random.default_rng(sum(map(ord, name)))
+        perms = np.stack([rng.permutation(D) for _ in range(L)])
+        assert np.array_equal(perms, g["perms"])
+        dims = [D + C] + list(hidden) + [2 * D]
+        params = []
+        for l in range(L):
+            lay = []
+            for j in range(len(dims) - 1):
+                W = (rng.normal(size=(dims[j + 1], dims[j])) / np.sqrt(dims[j])).astype(np.float32)
+                b = (rng.normal(size=(dims[j + 1],)) * 0.1).astype(np.float32)
+                lay.append((W, b))
+            params.append(lay)
+        chk = float(sum(np.abs(W.astype(np.float64)).sum() + np.abs(b.astype(np.float64)).sum() for lay in params for (W, b) in lay))
+        assert abs(chk - float(g["weights_checksum"])) <= 1e-9 * chk, "regenerated weights differ from the generator's"
+        return spec, params, g
     params = [[(g[f"W_{l}_{j}"], g[f"b_{l}_{j}"]) for j in range(len(hidden) + 1)] for l in range(L)]
     return spec, params, g
+
+
+def pyro_case_to_spec(o):
+    """dict written by tools/dump_pyro_goldens.py (or loaded from its .npz) -> (spec, draws [L][n_lin](W[1,..], b[1,..]) fp32)"""
+    D, C, L, K = int(o["D"]), int(o["C"]), int(o["L"]), int(o["K"])
+    hidden = [int(h) for h in o["hidden"]]
+    spec = fo.FlowSpec("nsa", D, C, hidden, L, np.asarray(o["perms"]), count_bins=K, order=str(o["order"]))
+    draws = [[(np.asarray(o[f"W_{l}_{j}"], np.float32)[None], np.asarray(o[f"b_{l}_{j}"], np.float32)[None])
+              for j in range(len(hidden) + 1)] for l in range(L)]
+    return spec, draws
+
+
+def pyro_golden_files():
+    import glob
+    import os
+    return sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pyro_nsa_*.npz")))

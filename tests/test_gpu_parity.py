@@ -1,11 +1,17 @@
 """GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against the
 CPU oracle on identical seeded weights and inputs.
 
-Tolerance (BASELINE.json north_star): |cuda - ref| <= 1e-5 + 1e-4 |ref| on fp32 log_prob, same for samples.
-`ref` is the fp64 oracle.  The reference's OWN fp32 arithmetic misses that bar against fp64 truth on a small
-fraction of points of the deep synthetic spline flows (lp near 0, ill-conditioned draws: measured 0.05 % of
-points for the fp32 oracle), so tests assert (a) at most MAX_VIOL of entries outside the strict tolerance
-and (b) every entry within 20x the tolerance — the same envelope the fp32 oracle itself satisfies."""
+Tolerance (BASELINE.json north_star): |cuda - ref| <= 1e-5 + 1e-4 |ref| on fp32 log_prob, same for samples; `ref` is the
+fp64 oracle.  Deep spline flows have a few ill-conditioned points where ANY fp32 evaluation — the reference's own included
+(the oracle run in fp32 misses the bar on ~1e-4 of the points, worst ~2x) — cannot meet that bar: a one-ulp(fp32) change of
+the inputs already moves the fp64 answer by a sizeable fraction of the tolerance there.  The checks therefore are
+  (1) at most MAX_VIOL = 0.2 % of the entries outside the strict tolerance (measured: 0.01-0.04 %),
+  (2) EVERY entry within 2 tol + 20 sens, where sens = |ref(inputs (1 +- 2^-23)) - ref(inputs)| is the sensitivity of the fp64
+      answer to a one-ulp relative perturbation of the inputs (so only demonstrably ill-conditioned points may exceed twice
+      the tolerance; measured: violators sit in the top 1 % of sens, the worst entry 14.9 tol had sens = 1.13 tol),
+  (3) the same two bounds against the oracle evaluated in fp32 (the reference's dtype),
+and for fixtures without a sensitivity (reference-executed outputs, small goldens): (1) plus every entry within WORST = 6 tol."""
+import functools
 import math
 
 import numpy as np
@@ -16,16 +22,70 @@ from oracle import flow_oracle as fo
 from helpers import GOLDEN, REF_TWIN, engine_for, load_golden, load_ref_twin, make_case, to64, tol_report
 
 pytestmark = pytest.mark.gpu
-MAX_VIOL = 0.01
-WORST = 20.0
+MAX_VIOL = 0.002
+WORST = 6.0
+ULP32 = 2.0 ** -23
 
 
-def check(got, ref, what, max_viol=MAX_VIOL, worst=WORST, atol=1e-5):
+def check(got, ref, what, sens=None, ref32=None, max_viol=MAX_VIOL, worst=WORST, atol=1e-5):
     if isinstance(got, torch.Tensor):
         got = got.detach().cpu().numpy()
     assert np.isfinite(got).all(), f"{what}: non-finite output"
-    viol, w = tol_report(got, ref, atol=atol)
-    assert viol <= max_viol and w <= worst, f"{what}: {viol:.4%} outside 1e-4/1e-5, worst {w:.1f}x tolerance"
+    got = np.asarray(got, np.float64)
+    for name, r in (("fp64 oracle", ref), ("fp32 oracle", ref32)):
+        if r is None:
+            continue
+        r = np.asarray(r, np.float64)
+        err = np.abs(got - r)
+        tol = atol + 1e-4 * np.abs(r)
+        viol = float((err > tol).mean())
+        w = float(np.max(err / tol)) if err.size else 0.0
+        assert viol <= max_viol, f"{what} vs {name}: {viol:.4%} outside 1e-4/1e-5 (worst {w:.1f}x tolerance)"
+        if sens is None:
+            assert w <= worst, f"{what} vs {name}: worst entry {w:.1f}x tolerance"
+        else:
+            over = err - (2.0 * tol + 20.0 * sens)
+            i = np.unravel_index(np.argmax(over), over.shape) if over.size else None
+            assert not over.size or over[i] <= 0, (f"{what} vs {name}: entry {i} is {err[i] / tol[i]:.1f}x tolerance but the point is "
+                                                   f"well conditioned (sens = {sens[i] / tol[i]:.3f} tol)")
+
+
+def inverse_refs(spec, draws, x, ctx, bounds=None, keep=None, p_drop=0.0):
+    """fp64 oracle lp / z, their sensitivity to a one-ulp(fp32) relative perturbation of (x, ctx), and the fp32 oracle."""
+    d64 = to64(draws)
+    kw = {} if keep is None else {"keep": keep.astype(np.float64), "p_drop": p_drop}
+    c64 = None if ctx is None else ctx.astype(np.float64)
+    lp, z = fo.log_prob_draws(spec, d64, x.astype(np.float64), c64, bounds, **kw)
+    s_lp, s_z = np.zeros_like(lp), np.zeros_like(z)
+    for sg in (1.0, -1.0):
+        lp_p, z_p = fo.log_prob_draws(spec, d64, x.astype(np.float64) * (1 + sg * ULP32), None if c64 is None else c64 * (1 + sg * ULP32), bounds, **kw)
+        s_lp = np.maximum(s_lp, np.abs(lp_p - lp))
+        s_z = np.maximum(s_z, np.abs(z_p - z))
+    kw32 = {} if keep is None else {"keep": keep.astype(np.float32), "p_drop": p_drop}
+    lp32, z32 = fo.log_prob_draws(spec, draws, x.astype(np.float32), None if ctx is None else ctx.astype(np.float32), bounds, **kw32)
+    return {"lp": lp, "z": z, "s_lp": s_lp, "s_z": s_z, "lp32": lp32, "z32": z32}
+
+
+def forward_refs(spec, draws, zin, ctx):
+    d64 = to64(draws)
+    c64 = None if ctx is None else ctx.astype(np.float64)
+    xs, ld = fo.sample_draws(spec, d64, zin.astype(np.float64), c64)
+    s_x = np.zeros_like(xs)
+    for sg in (1.0, -1.0):
+        xs_p, _ = fo.sample_draws(spec, d64, zin.astype(np.float64) * (1 + sg * ULP32), None if c64 is None else c64 * (1 + sg * ULP32))
+        s_x = np.maximum(s_x, np.abs(xs_p - xs))
+    xs32, _ = fo.sample_draws(spec, draws, zin.astype(np.float32), None if ctx is None else ctx.astype(np.float32))
+    return {"xs": xs, "ld": ld, "s_x": s_x, "xs32": xs32}
+
+
+@functools.lru_cache(maxsize=None)
+def _main_case(shape):
+    kind, D, C, hidden, L, S, N, order = shape
+    spec, draws, _, rng = make_case(kind, D, C, list(hidden), L, S, seed=11, order=order)
+    x = (rng.normal(size=(N, D)) * 1.5).astype(np.float32)
+    ctx = rng.uniform(size=(N, C)).astype(np.float32) if C else None
+    zin = rng.normal(size=(S, N, D)).astype(np.float32)
+    return spec, draws, x, ctx, zin, inverse_refs(spec, draws, x, ctx), forward_refs(spec, draws, zin, ctx)
 
 
 def T(a):
@@ -54,24 +114,19 @@ SHAPES = [
 @pytest.mark.parametrize("shape", SHAPES)
 def test_log_prob_and_sample_match_oracle(shape, engine):
     kind, D, C, hidden, L, S, N, order = shape
-    spec, draws, _, rng = make_case(kind, D, C, hidden, L, S, seed=11, order=order)
-    x = (rng.normal(size=(N, D)) * 1.5).astype(np.float32)
-    ctx = rng.uniform(size=(N, C)).astype(np.float32) if C else None
+    spec, draws, x, ctx, zin, ri, rf = _main_case((kind, D, C, tuple(hidden), L, S, N, order))
     eng = engine_for(spec, draws, engine=engine)
     out = eng.inverse(T(x), T(ctx), want_z=True, want_lp=True, want_lse=True, want_sum=True)
-    lp_ref, z_ref = fo.log_prob_draws(spec, to64(draws), x.astype(np.float64), None if ctx is None else ctx.astype(np.float64))
-    check(out["lp"], lp_ref, "lp")
-    check(out["z"], z_ref, "z")
+    check(out["lp"], ri["lp"], "lp", sens=ri["s_lp"], ref32=ri["lp32"])
+    check(out["z"], ri["z"], "z", sens=ri["s_z"], ref32=ri["z32"])
     ppd = eng.lse_finish(out["lse_max"], out["lse_sum"], -math.log(S))
-    check(ppd, fo.posterior_predictive(lp_ref), "posterior predictive")
-    assert np.allclose(out["sum_n"].cpu().numpy(), lp_ref.sum(1), rtol=2e-5)
-    zin = rng.normal(size=(S, N, D)).astype(np.float32)
+    check(ppd, fo.posterior_predictive(ri["lp"]), "posterior predictive", sens=ri["s_lp"].max(0))
+    assert np.allclose(out["sum_n"].cpu().numpy(), ri["lp"].sum(1), rtol=2e-5)
     xs, ld = eng.forward(T(zin), T(ctx), want_logdet=True)
-    xs_ref, ld_ref = fo.sample_draws(spec, to64(draws), zin.astype(np.float64), None if ctx is None else ctx.astype(np.float64))
-    check(xs, xs_ref, "samples")
+    check(xs, rf["xs"], "samples", sens=rf["s_x"], ref32=rf["xs32"])
     # auxiliary output (not part of the north-star tolerance): a sum of L*D signed O(1) terms that often cancels to
     # ~0, where the relative part of the tolerance vanishes; checked at atol 1e-4 (the fp32 oracle itself needs that)
-    check(ld, ld_ref, "forward log-det", atol=1e-4)
+    check(ld, rf["ld"], "forward log-det", atol=1e-4)
 
 
 @pytest.mark.parametrize("name", GOLDEN)
@@ -233,6 +288,14 @@ INV_VARIANTS = [
 ]
 
 
+@functools.lru_cache(maxsize=None)
+def _variant_refs(bcast):
+    spec, draws, _, rng = make_case("nsa", 4, 2, [150] * 3, 16, 2, seed=21)
+    x = (rng.normal(size=(300, 4)) * 1.5).astype(np.float32)
+    ctx = rng.uniform(size=(2,) if bcast else (300, 2)).astype(np.float32)
+    return inverse_refs(spec, draws, x, ctx)
+
+
 @pytest.mark.parametrize("options", INV_VARIANTS, ids=lambda o: "-".join(f"{k}{v}" for k, v in o.items()) or "default")
 @pytest.mark.parametrize("bcast", [False, True], ids=["ctx_per_point", "ctx_broadcast"])
 def test_inverse_kernel_variants_headline_shape(options, bcast):
@@ -241,13 +304,13 @@ def test_inverse_kernel_variants_headline_shape(options, bcast):
     spec, draws, _, rng = make_case("nsa", 4, 2, [150] * 3, 16, 2, seed=21)
     x = (rng.normal(size=(300, 4)) * 1.5).astype(np.float32)
     ctx = rng.uniform(size=(2,) if bcast else (300, 2)).astype(np.float32)
-    lp_ref, z_ref = fo.log_prob_draws(spec, to64(draws), x.astype(np.float64), ctx.astype(np.float64))
+    ri = _variant_refs(bcast)
     eng = engine_for(spec, draws, engine="tcgen05", options=options)
     assert eng.engine_for("inverse") == "tcgen05"
     out = eng.inverse(T(x), T(ctx), want_z=True, want_lp=True, want_lse=True, want_sum=True)
-    check(out["lp"], lp_ref, f"lp ({options})")
-    check(out["z"], z_ref, f"z ({options})")
-    assert np.allclose(out["sum_n"].cpu().numpy(), lp_ref.sum(1), rtol=2e-5)
+    check(out["lp"], ri["lp"], f"lp ({options})", sens=ri["s_lp"], ref32=ri["lp32"])
+    check(out["z"], ri["z"], f"z ({options})", sens=ri["s_z"], ref32=ri["z32"])
+    assert np.allclose(out["sum_n"].cpu().numpy(), ri["lp"].sum(1), rtol=2e-5)
 
 
 FOLD_SHAPES = [
@@ -271,17 +334,18 @@ def test_context_fold_matches_oracle_and_general_program(shape):
     spec, draws, _, rng = make_case(kind, D, C, hidden, L, S, seed=13)
     x = (rng.normal(size=(N, D)) * 1.5).astype(np.float32)
     ctx = rng.uniform(size=(C,)).astype(np.float32)
-    lp_ref, z_ref = fo.log_prob_draws(spec, to64(draws), x.astype(np.float64), ctx.astype(np.float64))
+    ri = inverse_refs(spec, draws, x, ctx)
+    lp_ref = ri["lp"]
     eng = engine_for(spec, draws, engine="auto")
     if eng.engine_for("inverse") != "tcgen05":
         pytest.skip("inverse direction of this shape runs on the SIMT engine")
     assert eng.get_option("inv_fold_available") == 1
     out = eng.inverse(T(x), T(ctx), want_z=True, want_lp=True)
-    check(out["lp"], lp_ref, "lp (folded)")
-    check(out["z"], z_ref, "z (folded)")
+    check(out["lp"], ri["lp"], "lp (folded)", sens=ri["s_lp"], ref32=ri["lp32"])
+    check(out["z"], ri["z"], "z (folded)", sens=ri["s_z"], ref32=ri["z32"])
     eng.set_option("inv_fold", 0)
     gen = eng.inverse(T(x), T(ctx), want_z=True, want_lp=True)
-    check(gen["lp"], lp_ref, "lp (general)")
+    check(gen["lp"], ri["lp"], "lp (general)", sens=ri["s_lp"], ref32=ri["lp32"])
     d = (out["lp"] - gen["lp"]).abs().cpu().numpy()
     tol = 1e-5 + 1e-4 * np.abs(lp_ref)
     assert (d <= 2 * tol).mean() > 0.995, "folded and general programs disagree"
@@ -602,3 +666,27 @@ def test_full_size_cfg2_mc_dropout():
     lp_ref, _ = fo.log_prob_draws(spec, to64(draws), x[sl].cpu().numpy().astype(np.float64), ctx[sl].cpu().numpy().astype(np.float64),
                                   keep=keep.astype(np.float64), p_drop=p)
     check(ppd[sl], fo.posterior_predictive(lp_ref), "cfg2 posterior predictive over masks")
+
+
+def test_cuda_matches_real_pyro():
+    """When pyro-ppl is importable on the GPU box: build the reference's own transforms (transforms.py:165-198 via
+    tools/dump_pyro_goldens.py), and check BOTH the oracle and the CUDA path against real pyro outputs.  Skips otherwise
+    (pyro-ppl is not part of this image; bench.py reports `pyro_found`)."""
+    pytest.importorskip("pyro")
+    import sys
+    import os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import dump_pyro_goldens as dp
+    from helpers import pyro_case_to_spec
+    for c in dp.CASES:
+        o = dp.export_case(*c)
+        spec, draws = pyro_case_to_spec(o)
+        ctx = o["ctx"] if spec.C else None
+        lp64, _ = fo.log_prob_draws(spec, to64(draws), o["x"].astype(np.float64), None if ctx is None else ctx.astype(np.float64))
+        assert np.allclose(lp64[0], o["lp"], rtol=2e-4, atol=2e-4), f"{c[0]}: oracle differs from pyro"
+        for engine in ("auto", "simt"):
+            eng = engine_for(spec, draws, engine=engine)
+            out = eng.inverse(T(o["x"]), T(ctx), want_lp=True)
+            check(out["lp"][0], o["lp"], f"{c[0]} lp vs pyro ({engine})", atol=1e-4)
+            xs = eng.forward(T(o["zin"]), T(ctx))
+            check(xs[0], o["ys"], f"{c[0]} samples vs pyro ({engine})", atol=1e-4)

@@ -130,11 +130,22 @@ CASES = {
 }
 
 
+# Bench-depth cases ([150] x 3 hidden, 16 flow layers: where the fp16 hi/lo error of the tensor-core path accumulates).  The
+# weights (~3 MB per case) are NOT stored: they are regenerated from the seeded numpy Generator by the same statements below
+# (tests/helpers.py::load_ref_twin replays them and verifies a checksum); inputs, permutations and the REFERENCE outputs are.
+DEEP_CASES = {
+    "ref_twin_deep_maf_2d": (2, 2, [150, 150, 150], 16, 256, True),          # cfg 4 architecture
+    "ref_twin_deep_maf_6d": (6, 4, [150, 150, 150], 16, 256, True),          # cfg 2 architecture
+    "ref_twin_deep_maf_8d_bcast": (8, 4, [150, 150, 150], 16, 256, False),   # cfg 5 architecture, one context vector (+ sampler)
+}
+
+
 def main(out_dir=None):
     ref = load_reference()
     dt = np.float64 if F64 else np.float32
     out_dir = out_dir or os.path.join(ROOT, "tests", "golden")
-    for name, (D, C, hidden, L, N, per_point) in CASES.items():
+    for name, (D, C, hidden, L, N, per_point) in list(CASES.items()) + list(DEEP_CASES.items()):
+        deep = name in DEEP_CASES
         rng = np.random.default_rng(sum(map(ord, name)))
         perms = np.stack([rng.permutation(D) for _ in range(L)])
         # the reference's own conditioner / transform factories and masks
@@ -170,7 +181,13 @@ def main(out_dir=None):
             zin = rng.normal(size=(N, D)).astype(np.float32)
             y, log_j = flow["sampler"](params, zin.astype(dt), N)
             arrs.update(zin=zin, ys=np.asarray(y, np.float64), log_j=np.asarray(log_j, np.float64))
+        if deep:
+            arrs["weights_regenerated"] = True
+            arrs["weights_checksum"] = float(sum(np.abs(np.asarray(W, np.float64)).sum() + np.abs(np.asarray(b, np.float64)).sum()
+                                                 for lay in params for (W, b) in lay))
         for l in range(L):
+            if deep:
+                continue
             for j, m in enumerate(masks[l]):
                 arrs[f"mask_{l}_{j}"] = np.asarray(m, np.float32)
             for j, (W, b) in enumerate(params[l]):
