@@ -110,6 +110,13 @@ struct TcPlan {
   bool fold_a_tmem = false;       // ... same for the folded program
   int t_a = 0;                    // v5: TMEM column of the A operand (hi image; lo at + kr_max / 2), valid when a_tmem
   bool a_tmem = false;
+  int t_a_fold = 0;               // ... of the folded program (its accumulators drop the degree-0 columns)
+  // Block-aligned column layout of the inverse programs (v5 / v6; 0 = units packed contiguously in degree order): the hidden
+  // units of MADE degree r of every hidden layer occupy columns [r bw, r bw + n_r), the rest of the block is zero padding
+  // (zero image rows / columns, zero biases), so an A block is exactly bw / 16 K slices and the epilogue of a block touches
+  // aw = ceil8(max n_r) columns instead of the 8-aligned hull of an unaligned range (cfg3: 40 instead of 56-64).
+  int bw = 0, aw = 0;
+  int hpad[NAZB_MAX_HIDDEN_LAYERS] = {0};   // column count of each hidden layer in the inverse programs (ceil16(H) or D bw)
 };
 
 struct TcState {
@@ -122,16 +129,19 @@ struct TcState {
   float* lcf_dev = nullptr;          // forward layer constants [S][L][f_lc_floats]
   float* lcfold_dev = nullptr;       // v4 inverse: context-folded layer constants [S][L][lc_floats] (rewritten per call)
   int* grp_done = nullptr;           // v4 inverse: draw-group gate counters [65536]
+  short* pmap_dev = nullptr;         // block-aligned layout: [NAZB_MAX_HIDDEN_LAYERS][256] column -> hidden unit (-1 = padding)
   unsigned int* wd_host = nullptr;   // watchdog word: mapped pinned host memory ...
   unsigned int* wd_dev = nullptr;    // ... and its device alias
   size_t cap_wimg[2] = {0, 0}, cap_lc = 0, cap_lcf = 0, cap_lcfold = 0, cap_tab = 0;
   // options (nazb_set_option); recorded by bench.py
-  int opt_inv_kernel = 5;            // 3 = round-1 kernel, 4 = v4 (two 64-row chains), 5 = v5 (one 128-row chain)
+  int opt_inv_kernel = 5;            // 3 = round-1 kernel, 4 = v4 (two 64-row chains), 5 = v5 (one 128-row chain, 16 epilogue warps),
+                                     // 6 = v6 (one 128-row chain, 24 epilogue warps, split pushes)
   int opt_fold = 1;                  // context fold when ctx_rows == 1
   int opt_merge_n = -1;              // pushes with N <= merge_n are issued unsplit (critical + deferred columns in one MMA);
                                      // -1 = kernel default (v4: 0 = always split, v5: 256 = never split)
   int opt_gate = 1;                  // draw-group gate for large N
   int opt_a_tmem = 1;                // v5: A operand in tensor memory when the plan allows it
+  int opt_align = 0;                 // v5 / v6: block-aligned column layout when it fits tensor memory (measured: no gain)
 };
 
 constexpr int kMaxSteps = 80;
@@ -384,8 +394,9 @@ bool build_inverse(const FlowGeom& g, TcPlan& P, int variant, int merge_n, std::
                    std::vector<Image>& images_out, std::vector<Image>* fold_images) {
   if (g.inv_mode != NAZB_INV_INCREMENTAL) return false;
   // variants 3 / 4: the v5 kernel (one 128-row chain, M = 128 MMAs: every N and every accumulator offset a multiple of 16)
-  const bool v5 = variant >= 3;
-  const bool v4 = variant != 0, folded = (variant == 2 || variant == 4);
+  // variants 5 / 6: the v6 kernel (same program as v5; split pushes keep the A operand in tensor memory behind a_free)
+  const bool v5 = variant >= 3, v6 = variant >= 5;
+  const bool v4 = variant != 0, folded = (variant == 2 || variant == 4 || variant == 6);
   const int nh = g.n_hidden, D = g.D;
   const int Mp = v5 ? P.mp : (v4 ? ceil_to(g.M, 8) : P.mp);
   P.mp_inv = Mp;
@@ -393,11 +404,21 @@ bool build_inverse(const FlowGeom& g, TcPlan& P, int variant, int merge_n, std::
   if (D * Mp > 256 || (!v4 && g.kin > 16) || D > 16) return false;
   auto hp = [&](int j) { return ceil_to(g.hidden[j], 16); };
   auto hp8 = [&](int j) { return (v4 && !v5) ? ceil_to(g.hidden[j], 8) : hp(j); };   // last column a push has to reach
+  // Accumulator columns.  The folded program never touches the columns of degree 0 (constant per draw), so its
+  // accumulators start at the first live block (16-aligned) and rank 1: T_PRE / T_OUT are the (possibly negative) column
+  // of unit 0 / rank 0, only sums with live offsets are ever used.
   int col = 0;
   int T_PRE[NAZB_MAX_HIDDEN_LAYERS] = {0};
-  for (int j = 1; j < nh; ++j) { T_PRE[j] = col; col += hp(j); }
-  const int T_OUT = col; col += D * Mp;
+  const bool trim = folded && v5;
+  for (int j = 1; j < nh; ++j) {
+    const int dead = trim ? (g.blk[j][1] & ~15) : 0;
+    T_PRE[j] = col - dead; col += hp(j) - dead;
+  }
+  const int T_OUT = col - (trim ? Mp : 0); col += (trim ? D - 1 : D) * Mp;
   if (col > kTmemCols) return false;
+  const int t_end = col;
+  // width of a block as the epilogues see it: the aligned layout pads every block to bw columns of which only aw are live
+  auto ep_w = [&](int c0, int c1) { return (P.bw > 0) ? std::min(c1 - c0, P.aw) : (c1 - c0); };
   int xw = 0;
   for (int r = 0; r < D; ++r) xw = std::max(xw, ceil_to(g.blk[0][r + 1], 8) - (g.blk[0][r] & ~7));
   const int T_PRE1 = col;
@@ -453,7 +474,7 @@ bool build_inverse(const FlowGeom& g, TcPlan& P, int variant, int merge_n, std::
       continue;
     }
     {
-      int ec0 = b0 & ~7, ec1 = ceil_to(b1, 8);
+      int ec0 = b0 & ~7, ec1 = ec0 + ep_w(b0 & ~7, ceil_to(b1, 8));
       Step e = mk_epi(EPI_FIRST, 0, ec1 - ec0, 0, r);
       e.e_aux = (uint16_t)ec0;
       if (!skip) b.epi_only(e);
@@ -478,7 +499,7 @@ bool build_inverse(const FlowGeom& g, TcPlan& P, int variant, int merge_n, std::
         int tn0 = v5 ? (tc0 & ~15) : tc0;      // M = 64 MMAs take any N % 8 == 0, M = 128 ones N % 16 == 0
         int n = hp8(j + 1) - tn0;
         if (first_push[j + 1] && tn0 != 0 && !(folded && r == 1)) return false;
-        Step e = mk_epi(EPI_TANH, T_PRE[j + 1] + tc0, tc1 - tc0, 0);
+        Step e = mk_epi(EPI_TANH, T_PRE[j + 1] + tc0, ep_w(tc0, tc1), 0);
         e.e_aux = (uint16_t)(P.lc_b[j + 1] + tc0);
         int n_crit = v5 ? ceil_to(tc1, 16) - tn0 : tc1 - tc0;
         if (v4 && n <= merge_n) n_crit = n;
@@ -506,10 +527,11 @@ bool build_inverse(const FlowGeom& g, TcPlan& P, int variant, int merge_n, std::
   if (v5) {
     // A operand in tensor memory: one buffer of kr_max / 2 columns each for the hi and lo images behind the accumulators;
     // needs unsplit pushes (every MMA of a push retires before the accumulator barrier that releases the next writer)
-    P.t_a = ceil_to(T_OUT + D * Mp, 16);
+    P.t_a = ceil_to(t_end, 16);
     bool unsplit = true;
     for (const Step& st : steps_out) if (st.w_bytes && st.n_crit != st.n) unsplit = false;
-    P.a_tmem = unsplit && (P.t_a + P.kr_max <= kTmemCols);
+    (void)unsplit; (void)v6;   // split pushes keep the A operand in tensor memory too (a_free barrier in the kernels)
+    P.a_tmem = (P.t_a + P.kr_max <= kTmemCols);
   }
   return (int)steps_out.size() <= kMaxSteps;
 }
@@ -592,7 +614,10 @@ __global__ void tc_pack_kernel(Image im, int S, int L, int n_lin, int D, int M, 
                                const float* __restrict__ keep, long long keep_draw_stride, long long keep_layer_stride,
                                int keep_hk, float inv_keep, uint8_t* __restrict__ dst, unsigned long long draw_bytes,
                                unsigned long long layer_bytes, const float* const* __restrict__ bWtab,
-                               const float* const* __restrict__ bbtab, float dm_scale) {
+                               const float* const* __restrict__ bbtab, float dm_scale, const short* __restrict__ pmap) {
+  // pmap (block-aligned inverse layout): [hidden layer][256] column -> hidden unit, -1 = padding column; null = identity
+  const short* map_out = (pmap && im.row_mode == 0) ? pmap + (size_t)im.lin * 256 : nullptr;
+  const short* map_in = (pmap && im.lin > 0) ? pmap + (size_t)(im.lin - 1) * 256 : nullptr;
   const int KC = im.k_ext >> 3;
   const long long per_layer = (long long)KC * im.n_ext;
   const long long total = per_layer * L * S;
@@ -606,7 +631,8 @@ __global__ void tc_pack_kernel(Image im, int S, int L, int n_lin, int D, int M, 
     int o = -1;
     if (im.row_mode == 0) {
       int u = im.n0 + n;
-      if (u < ndim) o = u;
+      if (map_out) u = (u < 256) ? map_out[u] : -1;
+      if (u >= 0 && u < ndim) o = u;
     } else if (im.row_mode == 1) {
       int rank = im.r0 + n / Mp, m = n % Mp;
       if (rank < im.r1 && m < M) o = m * D + perm[l * D + rank];
@@ -632,7 +658,9 @@ __global__ void tc_pack_kernel(Image im, int S, int L, int n_lin, int D, int M, 
         if (c == im.bias_col) { v = bb[o]; if (bB) v = nazb_draw_map(bB[o], v, dm_scale); }
         else if (!im.bias_only) {
           int ks = im.k0 + c;
-          if (ks >= im.kv0 && ks < im.kv1 && ks < kdim) {
+          const bool in_range = (ks >= im.kv0 && ks < im.kv1);
+          if (map_in) ks = (ks >= 0 && ks < 256) ? map_in[ks] : -1;
+          if (in_range && ks >= 0 && ks < kdim) {
             v = W[(size_t)o * kdim + ks];
             if (bW) v = nazb_draw_map(bW[(size_t)o * kdim + ks], v, dm_scale);
             v *= mk[(size_t)o * kdim + ks];
@@ -1167,7 +1195,8 @@ __global__ void tc_pack_lc4_kernel(int S, int L, int n_lin, int D, int C, int M,
                                    const float* const* __restrict__ Wtab, const float* const* __restrict__ btab,
                                    const float* const* __restrict__ mtab, const long long* __restrict__ wst,
                                    const long long* __restrict__ bst, const int* __restrict__ perm, float* __restrict__ dst,
-                                   const float* const* __restrict__ bWtab, const float* const* __restrict__ bbtab, float dm_scale) {
+                                   const float* const* __restrict__ bWtab, const float* const* __restrict__ bbtab, float dm_scale,
+                                   const short* __restrict__ pmap) {
   const int kin = C + D, nh = n_lin - 1;
   const long long total = (long long)S * L * lg.lc_floats;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -1184,7 +1213,8 @@ __global__ void tc_pack_lc4_kernel(int S, int L, int n_lin, int D, int C, int M,
         else { int g2 = f - lg.lc_w0c; int c = g2 / lg.hp[0]; n = g2 % lg.hp[0]; if (c < C) k = c; }
       } else if (f < lg.lc_w0c) { n = f / lg.dp4; int q = f % lg.dp4; if (q < D) k = C + perm[l * D + q]; }
       else { int g2 = f - lg.lc_w0c; n = g2 / lg.cp4; int c = g2 % lg.cp4; if (c < C) k = c; }
-      if (n < lg.hdim[0] && k >= 0) {
+      if (pmap) n = (n < 256) ? pmap[n] : -1;
+      if (n >= 0 && n < lg.hdim[0] && k >= 0) {
         int ti = l * n_lin;
         float w = Wtab[ti][(size_t)s * wst[ti] + (size_t)n * kin + k];
         if (bWtab) w = nazb_draw_map(bWtab[ti][(size_t)n * kin + k], w, dm_scale);
@@ -1194,7 +1224,8 @@ __global__ void tc_pack_lc4_kernel(int S, int L, int n_lin, int D, int C, int M,
       int j = 0;
       while (j + 1 < nh && f >= lg.lc_b[j + 1]) ++j;
       int n = f - lg.lc_b[j];
-      if (n < lg.hdim[j]) {
+      if (pmap) n = (n < 256) ? pmap[(size_t)j * 256 + n] : -1;
+      if (n >= 0 && n < lg.hdim[j]) {
         int ti = l * n_lin + j;
         float bv = btab[ti][(size_t)s * bst[ti] + n];
         if (bbtab) bv = nazb_draw_map(bbtab[ti][n], bv, dm_scale);
@@ -1228,6 +1259,7 @@ constexpr int kChainRows = kTileM / kChains;          // 64
 #include "flow_tc_inv3.cuh"
 #include "flow_tc_inv4.cuh"
 #include "flow_tc_inv5.cuh"
+#include "flow_tc_inv6.cuh"
 #include "flow_tc_fwd3.cuh"
 #include "flow_tc_fwd4.cuh"
 
@@ -1270,6 +1302,7 @@ void nazb_tc_destroy(nazb_handle* h) {
   if (t->lcf_dev) cudaFree(t->lcf_dev);
   if (t->lcfold_dev) cudaFree(t->lcfold_dev);
   if (t->grp_done) cudaFree(t->grp_done);
+  if (t->pmap_dev) cudaFree(t->pmap_dev);
   if (t->wd_host) cudaFreeHost(t->wd_host);
   delete t;
   h->tc = nullptr;
@@ -1280,11 +1313,12 @@ void nazb_tc_destroy(nazb_handle* h) {
 int nazb_tc_set_option(nazb_handle* h, const char* name, int value) {
   TcState* t = static_cast<TcState*>(h->tc);
   if (!t) return NAZB_ERR_UNSUPPORTED;
-  if (!strcmp(name, "inv_kernel")) { if (value < 3 || value > 5) return NAZB_ERR_BAD_ARG; t->opt_inv_kernel = value; h->is_packed = false; return NAZB_OK; }
+  if (!strcmp(name, "inv_kernel")) { if (value < 3 || value > 6) return NAZB_ERR_BAD_ARG; t->opt_inv_kernel = value; h->is_packed = false; return NAZB_OK; }
   if (!strcmp(name, "inv_fold")) { t->opt_fold = value ? 1 : 0; return NAZB_OK; }
   if (!strcmp(name, "inv_merge_n")) { if (value < -1 || value > 256) return NAZB_ERR_BAD_ARG; t->opt_merge_n = value; h->is_packed = false; return NAZB_OK; }
   if (!strcmp(name, "inv_gate")) { t->opt_gate = value ? 1 : 0; return NAZB_OK; }
   if (!strcmp(name, "inv_a_tmem")) { t->opt_a_tmem = value ? 1 : 0; return NAZB_OK; }
+  if (!strcmp(name, "inv_align")) { t->opt_align = value ? 1 : 0; h->is_packed = false; return NAZB_OK; }
   return NAZB_ERR_BAD_ARG;
 }
 int nazb_tc_get_option(const nazb_handle* h, const char* name, int* value) {
@@ -1295,8 +1329,10 @@ int nazb_tc_get_option(const nazb_handle* h, const char* name, int* value) {
   else if (!strcmp(name, "inv_merge_n")) *value = t->opt_merge_n;
   else if (!strcmp(name, "inv_gate")) *value = t->opt_gate;
   else if (!strcmp(name, "inv_a_tmem")) *value = t->opt_a_tmem;
+  else if (!strcmp(name, "inv_align")) *value = t->opt_align;
+  else if (!strcmp(name, "inv_block_width")) *value = t->plan.ok[0] ? t->plan.bw : 0;
   else if (!strcmp(name, "inv_kernel_in_use")) *value = t->plan.ok[0] ? t->plan.inv_ver : 0;
-  else if (!strcmp(name, "inv_a_tmem_in_use")) *value = (t->plan.ok[0] && t->plan.inv_ver == 5 && t->plan.a_tmem && t->plan.fold_a_tmem && t->opt_a_tmem) ? 1 : 0;
+  else if (!strcmp(name, "inv_a_tmem_in_use")) *value = (t->plan.ok[0] && t->plan.inv_ver >= 5 && t->opt_a_tmem) ? (t->plan.a_tmem ? 1 : 0) + (t->plan.fold_a_tmem ? 2 : 0) : 0;   // bit 0: general program, bit 1: folded
   else if (!strcmp(name, "inv_fold_available")) *value = (t->plan.ok[0] && t->plan.inv_ver >= 4 && t->plan.fold_ok) ? 1 : 0;
   else return NAZB_ERR_BAD_ARG;
   return NAZB_OK;
@@ -1349,26 +1385,52 @@ cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* con
   if (!P.fwd3) { P.steps[1].clear(); P.images[1].clear(); }
   P.ok[1] = P.fwd3 || build_forward(g, P);
   P.inv_ver = t->opt_inv_kernel;
-  if (P.inv_ver >= 4) {
-    const int vgen = (P.inv_ver == 5) ? 3 : 1;
+  // geometry the inverse programs are built on: the real one (units contiguous in degree order) or the block-aligned one
+  FlowGeom gi = g;
+  std::vector<short> pmap;
+  auto plan_inverse = [&](const FlowGeom& gg) -> bool {
+    P.steps[0].clear(); P.images[0].clear(); P.fold_images.clear(); P.steps_fold.clear(); P.kr_max = 0; P.fold_ok = false;
+    const int vgen = (P.inv_ver == 6) ? 5 : (P.inv_ver == 5) ? 3 : 1;
     const int merge_n = t->opt_merge_n >= 0 ? t->opt_merge_n : (P.inv_ver == 5 ? 256 : 0);
-    P.ok[0] = build_inverse(g, P, vgen, merge_n, P.steps[0], P.images[0], &P.fold_images) && plan_smem_inv4(g, P);
-    if (!P.ok[0] && P.inv_ver == 5) {
-      // shapes the 128-row kernel cannot hold (output accumulators at stride ceil16(M)) fall back to the two-chain kernel
-      P.steps[0].clear(); P.images[0].clear(); P.fold_images.clear(); P.kr_max = 0;
+    if (!(build_inverse(gg, P, vgen, merge_n, P.steps[0], P.images[0], &P.fold_images) && plan_smem_inv4(gg, P))) return false;
+    std::vector<Image> scratch_images;
+    TcPlan Q = P;   // the folded variant must not disturb kr_max / layer_bytes of the general plan
+    P.fold_ok = build_inverse(gg, Q, vgen + 1, merge_n, P.steps_fold, scratch_images, nullptr) &&
+                Q.layer_bytes[0] == P.layer_bytes[0] && (int)P.fold_images.size() <= kMaxFoldImgs;
+    if (!P.fold_ok) P.steps_fold.clear();
+    P.fold_a_tmem = P.fold_ok && Q.a_tmem;
+    P.t_a_fold = Q.t_a;
+    return true;
+  };
+  if (P.inv_ver >= 4) {
+    if (P.inv_ver >= 5 && t->opt_align && g.inv_mode == NAZB_INV_INCREMENTAL) {
+      int maxblk = 0, minblk = 1 << 20;
+      for (int j = 0; j < g.n_hidden; ++j)
+        for (int r = 0; r < g.D; ++r) {
+          maxblk = std::max(maxblk, g.blk[j][r + 1] - g.blk[j][r]);
+          minblk = std::min(minblk, g.blk[j][r + 1] - g.blk[j][r]);
+        }
+      const int bw = ceil_to(std::max(maxblk, 1), 16);
+      if (minblk > 0 && g.D * bw <= 256) {   // (an empty degree block keeps the contiguous layout and its shortcuts)
+        P.bw = bw; P.aw = ceil_to(std::max(maxblk, 1), 8);
+        pmap.assign((size_t)NAZB_MAX_HIDDEN_LAYERS * 256, (short)-1);
+        for (int j = 0; j < g.n_hidden; ++j) {
+          gi.hidden[j] = g.D * bw;
+          for (int r = 0; r <= g.D; ++r) gi.blk[j][r] = (short)(r * bw);
+          for (int r = 0; r < g.D; ++r)
+            for (int u = g.blk[j][r]; u < g.blk[j][r + 1]; ++u) pmap[(size_t)j * 256 + r * bw + (u - g.blk[j][r])] = (short)u;
+        }
+        P.ok[0] = plan_inverse(gi);
+        if (!P.ok[0]) { P.bw = P.aw = 0; gi = g; pmap.clear(); }
+      }
+    }
+    if (!P.ok[0]) P.ok[0] = plan_inverse(g);
+    if (!P.ok[0] && P.inv_ver >= 5) {
+      // shapes the 128-row kernels cannot hold (output accumulators at stride ceil16(M)) fall back to the two-chain kernel
       P.inv_ver = 4;
-      P.ok[0] = build_inverse(g, P, 1, t->opt_merge_n >= 0 ? t->opt_merge_n : 0, P.steps[0], P.images[0], &P.fold_images) && plan_smem_inv4(g, P);
+      P.ok[0] = plan_inverse(g);
     }
-    if (P.ok[0]) {
-      const int vgen2 = (P.inv_ver == 5) ? 3 : 1;
-      const int merge2 = t->opt_merge_n >= 0 ? t->opt_merge_n : (P.inv_ver == 5 ? 256 : 0);
-      std::vector<Image> scratch_images;
-      TcPlan Q = P;   // the folded variant must not disturb kr_max / layer_bytes of the general plan
-      P.fold_ok = build_inverse(g, Q, vgen2 + 1, merge2, P.steps_fold, scratch_images, nullptr) &&
-                  Q.layer_bytes[0] == P.layer_bytes[0] && (int)P.fold_images.size() <= kMaxFoldImgs;
-      if (!P.fold_ok) P.steps_fold.clear();
-      P.fold_a_tmem = !P.fold_ok || Q.a_tmem;
-    }
+    for (int j = 0; j < g.n_hidden; ++j) P.hpad[j] = ceil_to(gi.hidden[j], 16);
   } else {
     P.ok[0] = build_inverse(g, P, 0, 0, P.steps[0], P.images[0], nullptr) && plan_smem_inv3(g, P);
   }
@@ -1395,6 +1457,10 @@ cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* con
   if ((e = nazb_stage_upload(h, t->tab_dev, tabs.data(), tabs.size() * sizeof(float*), st)) != cudaSuccess) return e;
   long long* strides_dev = reinterpret_cast<long long*>(t->tab_dev + tabs.size());
   if ((e = nazb_stage_upload(h, strides_dev, strides.data(), strides.size() * sizeof(long long), st)) != cudaSuccess) return e;
+  if (P.bw > 0) {
+    if (!t->pmap_dev && (e = cudaMalloc(&t->pmap_dev, sizeof(short) * NAZB_MAX_HIDDEN_LAYERS * 256)) != cudaSuccess) return e;
+    if ((e = nazb_stage_upload(h, t->pmap_dev, pmap.data(), sizeof(short) * pmap.size(), st)) != cudaSuccess) return e;
+  }
   int hk = 0;
   for (int j = 0; j < g.n_hidden; ++j) hk = std::max(hk, g.hidden[j]);
   for (int d = 0; d < 2; ++d) {
@@ -1408,7 +1474,8 @@ cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* con
                                              h->perm_dev, keep, (long long)L * g.n_hidden * hk, (long long)g.n_hidden * hk,
                                              hk, 1.f / (1.f - p_drop), t->wimg[d], (unsigned long long)t->draw_bytes[d],
                                              (unsigned long long)P.layer_bytes[d], has_dm ? t->tab_dev + 3 * ntab : nullptr,
-                                             has_dm ? t->tab_dev + 4 * ntab : nullptr, dm.scale);
+                                             has_dm ? t->tab_dev + 4 * ntab : nullptr, dm.scale,
+                                             (d == 0 && P.bw > 0) ? t->pmap_dev : nullptr);
       nazb_count_launch();
     }
   }
@@ -1420,12 +1487,12 @@ cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* con
     if (P.inv_ver >= 4) {
       Lc4Geom lg{};
       lg.lc_w0x = P.lc_w0x; lg.lc_w0c = P.lc_w0c; lg.lc_bout = P.lc_bout; lg.lc_r0c = P.lc_r0c; lg.lc_floats = P.lc_floats;
-      lg.dp4 = P.dp4; lg.cp4 = std::max(P.cp4, 1); lg.qmajor = (P.inv_ver == 5) ? 1 : 0;
-      for (int j = 0; j < g.n_hidden; ++j) { lg.lc_b[j] = P.lc_b[j]; lg.hdim[j] = g.hidden[j]; lg.hp[j] = ceil_to(g.hidden[j], 16); }
+      lg.dp4 = P.dp4; lg.cp4 = std::max(P.cp4, 1); lg.qmajor = (P.inv_ver >= 5) ? 1 : 0;
+      for (int j = 0; j < g.n_hidden; ++j) { lg.lc_b[j] = P.lc_b[j]; lg.hdim[j] = g.hidden[j]; lg.hp[j] = P.hpad[j]; }
       tc_pack_lc4_kernel<<<blocks, 256, 0, st>>>(S, L, n_lin, g.D, g.C, g.M, P.mp_inv, 2.885390081777927f, lg, t->tab_dev,
                                                  t->tab_dev + ntab, t->tab_dev + 2 * ntab, strides_dev, strides_dev + ntab,
                                                  h->perm_dev, t->lc_dev, has_dm ? t->tab_dev + 3 * ntab : nullptr,
-                                                 has_dm ? t->tab_dev + 4 * ntab : nullptr, dm.scale);
+                                                 has_dm ? t->tab_dev + 4 * ntab : nullptr, dm.scale, P.bw > 0 ? t->pmap_dev : nullptr);
       nazb_count_launch();
       if (P.fold_ok && (e = ensure_cap(&t->lcfold_dev, &t->cap_lcfold, lc_bytes)) != cudaSuccess) return e;
     } else {
@@ -1470,7 +1537,7 @@ static cudaError_t launch_inv4(const nazb_handle* h, const TcState* t, const IoA
   kp.lc = fold ? t->lcfold_dev : t->lc_dev;
   kp.lc_floats = P.lc_floats; kp.lc_s0 = fold ? 0 : io.s_begin;
   kp.lc_w0x = P.lc_w0x; kp.lc_w0c = P.lc_w0c; kp.lc_b0 = P.lc_b[0]; kp.lc_r0c = P.lc_r0c;
-  kp.dp4 = (P.inv_ver == 5) ? ceil_to(g.hidden[0], 16) : P.dp4;   // v5: row stride of the input-major first-layer tables
+  kp.dp4 = (P.inv_ver >= 5) ? P.hpad[0] : P.dp4;   // v5: row stride of the input-major first-layer tables
   kp.cp4 = P.cp4;
   kp.perm = h->perm_dev;
   kp.D = g.D; kp.C = g.C; kp.L = g.L; kp.M = g.M; kp.Mp = P.mp_inv; kp.K = g.K; kp.kind = g.kind;
@@ -1501,9 +1568,10 @@ static cudaError_t launch_inv4(const nazb_handle* h, const TcState* t, const IoA
     fp.wimg = t->wimg[0]; fp.draw_bytes = t->draw_bytes[0]; fp.layer_bytes = P.layer_bytes[0];
     fp.lc = t->lc_dev; fp.lcf = t->lcfold_dev; fp.lc_floats = P.lc_floats; fp.lc_w0c = P.lc_w0c; fp.lc_r0c = P.lc_r0c;
     fp.cp4 = std::max(P.cp4, 1); fp.lc_bout = P.lc_bout;
-    fp.w0c_sn = (P.inv_ver == 5) ? 1 : fp.cp4;                           // W0c[n][c] at n * w0c_sn + c * w0c_sc
-    fp.w0c_sc = (P.inv_ver == 5) ? ceil_to(g.hidden[0], 16) : 1;
-    for (int j = 0; j < g.n_hidden; ++j) { fp.lc_b[j] = P.lc_b[j]; fp.hp[j] = ceil_to(g.hidden[j], 16); fp.blk1[j] = g.blk[j][1]; }
+    fp.w0c_sn = (P.inv_ver >= 5) ? 1 : fp.cp4;                           // W0c[n][c] at n * w0c_sn + c * w0c_sc
+    fp.w0c_sc = (P.inv_ver >= 5) ? P.hpad[0] : 1;
+    // blk1 = number of degree-0 units: they occupy the first columns in both layouts
+    for (int j = 0; j < g.n_hidden; ++j) { fp.lc_b[j] = P.lc_b[j]; fp.hp[j] = P.hpad[j]; fp.blk1[j] = g.blk[j][1]; }
     fp.n_hidden = g.n_hidden; fp.L = g.L; fp.C = g.C; fp.D = g.D; fp.Mp = P.mp_inv; fp.kind = g.kind;
     fp.bound = g.bound; fp.clip_lo = g.clip_lo; fp.clip_hi = g.clip_hi;
     fp.ctx = io.ctx; fp.s_begin = io.s_begin;
@@ -1514,10 +1582,23 @@ static cudaError_t launch_inv4(const nazb_handle* h, const TcState* t, const IoA
   const int mode = (g.kind == NAZB_KIND_AFFINE) ? 0 : (g.kind == NAZB_KIND_RQS && g.K == 8) ? 1 : 2;
   auto kern = flow_tc_inv4_kernel<false, 2>;
   int threads = kV4Threads;
-  if (P.inv_ver == 5) {
+  if (P.inv_ver == 6) {
+    threads = kV6Threads;
+    const bool atm = t->opt_a_tmem && (fold ? P.fold_a_tmem : P.a_tmem);
+    kp.t_a = (uint32_t)(fold ? P.t_a_fold : P.t_a);
+    if (atm) {
+      kern = flow_tc_inv6_kernel<false, 2, true>;
+      if (mode == 0) kern = flow_tc_inv6_kernel<false, 0, true>;
+      else if (mode == 1) kern = g_tc_dbg ? flow_tc_inv6_kernel<true, 1, true> : flow_tc_inv6_kernel<false, 1, true>;
+    } else {
+      kern = flow_tc_inv6_kernel<false, 2, false>;
+      if (mode == 0) kern = flow_tc_inv6_kernel<false, 0, false>;
+      else if (mode == 1) kern = g_tc_dbg ? flow_tc_inv6_kernel<true, 1, false> : flow_tc_inv6_kernel<false, 1, false>;
+    }
+  } else if (P.inv_ver == 5) {
     threads = kV5Threads;
-    const bool atm = t->opt_a_tmem && P.a_tmem && P.fold_a_tmem;
-    kp.t_a = (uint32_t)P.t_a;
+    const bool atm = t->opt_a_tmem && (fold ? P.fold_a_tmem : P.a_tmem);
+    kp.t_a = (uint32_t)(fold ? P.t_a_fold : P.t_a);
     if (atm) {
       kern = flow_tc_inv5_kernel<false, 2, true>;
       if (mode == 0) kern = flow_tc_inv5_kernel<false, 0, true>;

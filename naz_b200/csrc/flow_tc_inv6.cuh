@@ -1,54 +1,46 @@
-// v5 inverse (`log_prob` direction) kernel of the tcgen05 engine: ONE 128-row chain per CTA, M = 128 MMAs.
-// Included by flow_tc.cu after flow_tc_inv4.cuh (shares KParamsInv4, mbar_wait4, the fold kernel and the helpers).
+// v6 inverse (`log_prob` direction) kernel of the tcgen05 engine: ONE 128-row chain per CTA (as v5), 24 epilogue warps.
+// Included by flow_tc.cu after flow_tc_inv5.cuh (shares KParamsInv4, mbar_wait4, the fold kernel, LOG5 and the helpers).
 //
-// Why (measured on B200 with the event log of this file, tools/inv5_timeline.py, on the v4 kernel): the two 64-row chains
-// of v3 / v4 run in lockstep, so they do not hide each other's latencies, while every M = 64 MMA occupies the tensor pipe
-// and the shared-memory operand path as long as an M = 128 one.  A push of 4 K slices took ~550-850 cycles per slice in
-// the issuer (6 small dependent MMAs per slice and chain, ~4 KB of operand reads each against 128 B/clk of shared-memory
-// bandwidth), and that backlog — not the tanh epilogue — was the longest segment of every phase.  Here:
-//   * one chain of 128 rows: half the MMAs and half the operand bytes per row; all 16 epilogue warps work on the same
-//     phase (4 TMEM lane quadrants x 2 row halves x 2 slice lanes);
-//   * pushes are issued unsplit (one accumulator region of N % 16 == 0 columns, N >= 112 for the wide ones, so consecutive
-//     accumulating MMAs pipeline instead of waiting on each other), guarded by a fresh elect.sync so that ptxas keeps the
-//     descriptors in uniform registers (UIADD3 + UTCHMMA back to back; the v3 / v4 form re-broadcast 7-8 operands per MMA);
-//   * everything else as v4: context fold, first conditioner layer on CUDA cores, watchdog'd waits, draw-group gate.
+// Why (measured with the v5 event log, tools/inv5_timeline.py, cfg3, broadcast context: 29 k cycles per flow layer and tile):
+// TMEM holds the push accumulators of exactly 128 rows, so one SM runs ONE dependency chain of 12 phases per flow layer and
+// the kernel is bound by the length of a phase, not by any pipe.  A v5 tanh phase was 2.7 k cycles: accumulator read 450,
+// TWO rounds of tanh (16 warps, a block of 56-64 columns = 4 K slices, each warp takes two) 1350, and a tail of 870 in which
+// the last six unsplit MMAs (N = 112-144, 60-70 cycles each) run after the last slice has landed.  Here:
+//   * 24 epilogue warps = 4 TMEM lane quadrants x 2 row halves x 3 slice lanes (72 registers per thread: no spills), so a
+//     block of up to 3 K slices is ONE round: every warp takes one 16-row x 16-column slice;
+//   * pushes are split again: the MMAs of the CRITICAL columns (the block the next epilogue reads, N = 48: 24 cycles each)
+//     are issued and committed first, the remaining columns follow behind them off the critical path.  The A operand
+//     stays single-buffered in tensor memory: a second barrier (a_free, committed after the trailing MMAs) is waited on
+//     by the next block's writers right before their first store — by then it has long completed;
+//   * one ready barrier per A block (24 arrivals) instead of one per pair of slices: all slices land together now;
+//   * with the block-aligned column layout (TcPlan::bw, flow_tc.cu) a block is exactly bw / 16 K slices and carries no
+//     columns of its neighbours (v5 tanh'd 56-64 columns for a 38-unit block).
 // Row mapping: epilogue warp w: quadrant q = w & 3, part = w >> 2; rows 32 q + 16 (part & 1) + (lane & 15), two lanes per
-// row (tcgen05.ld.16x32bx2); slice lane = part >> 1 takes K slices (part >> 1), (part >> 1) + 2, ...; the warps with
+// row (tcgen05.ld.16x32bx2); slice lane = part >> 1 takes K slices (part >> 1), (part >> 1) + 3, ...; the warps with
 // part < 2 own the per-row state (spline, x, outputs).
 #pragma once
 
-constexpr int kV5EpiWarps = 16;
-constexpr int kV5Issuer = kV5EpiWarps;
-constexpr int kV5Producer = kV5EpiWarps + 1;
-constexpr int kV5Threads = (kV5EpiWarps + 2) * 32;
-constexpr int kV5MaxSlices = 8;
-constexpr int kV5MaxPairs = kV5MaxSlices / 2;   // a_ready barriers: one per PAIR of K slices (2 j, 2 j + 1), 16 arrivals each
-constexpr int kDbgEvents = 4096;
-// Debug event log (kDbg instantiation only): CTA 0, three logger warps (slot 0 = epilogue warp 0 (q 0, rows 0-15, slice lane 0),
-// slot 1 = epilogue warp 8 (same rows, slice lane 1), slot 2 = the issuer), each writing (clock, step << 8 | event) pairs.
-#define LOG5(slot, ev)                                                                                    \
-  if (kDbg && dbg_on && lane == 0 && dbg_n < kDbgEvents) {                                                \
-    p.dbg[((size_t)(slot) * kDbgEvents + dbg_n) * 2] = clk();                                             \
-    p.dbg[((size_t)(slot) * kDbgEvents + dbg_n) * 2 + 1] = ((long long)st << 8) | (ev);                   \
-    ++dbg_n;                                                                                              \
-  }
-
+constexpr int kV6SliceLanes = 3;
+constexpr int kV6EpiWarps = 8 * kV6SliceLanes;
+constexpr int kV6Issuer = kV6EpiWarps;
+constexpr int kV6Producer = kV6EpiWarps + 1;
+constexpr int kV6Threads = (kV6EpiWarps + 2) * 32;
 // kMode: 0 = affine, 1 = rational-quadratic spline with K = 8 (two lanes per row), 2 = any other spline.
 // kATmem: the A operand (fp16 hi / lo of the activations) lives in tensor memory (written with tcgen05.st, read by the MMA)
 // instead of shared memory: measured (tools/tc_probe_rate3.cu) an M = 128 MMA costs max(N/2, 32 + N/4) cycles with A in shared
 // memory (operand fetch at 128 B/clk) and the N/2 pipe floor with A in TMEM; in the kernel the shared-memory A path ran at
 // ~130 cycles per MMA because the epilogue warps' own traffic shares that port.
 template <bool kDbg, int kMode, bool kATmem>
-__global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __grid_constant__ KParamsInv4 p,
+__global__ void __launch_bounds__(kV6Threads, 1) flow_tc_inv6_kernel(const __grid_constant__ KParamsInv4 p,
                                                                       const __grid_constant__ IoArgs io, int n_groups) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* w_full = reinterpret_cast<uint64_t*>(smem);            // [nslots] TMA -> issuers
   uint64_t* w_empty = w_full + 8;                                   // [nslots] count = 1 (the issuer's commit)
   uint64_t* bar_acc = w_empty + 8;                                  // [1] issuer -> epilogue warps
   uint64_t* lc_full = bar_acc + 2;                                  // [2]
-  uint64_t* lc_empty = lc_full + 2;                                 // [2], count = kV5EpiWarps
-  uint64_t* a_ready = lc_empty + 2;                                 // [2 barrier sets][kV5MaxPairs]
-  uint64_t* a_free = a_ready + 2 * kV5MaxPairs;                     // [1] A in TMEM: commit behind the last MMA that reads an A block
+  uint64_t* lc_empty = lc_full + 2;                                 // [2], count = kV6EpiWarps
+  uint64_t* a_ready = lc_empty + 2;                                 // [1] one arrival per epilogue warp and A block
+  uint64_t* a_free = a_ready + 1;                                   // [1] the issuer's commit behind the LAST MMA reading an A block
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_free + 1);
   volatile int* xflag = reinterpret_cast<volatile int*>(tmem_slot + 4);   // [8] x publications of each 16-row group (owner warp -> partner warp)
   float* xin = reinterpret_cast<float*>(smem + p.off_xin);          // [C][128] context rows (per-point contexts)
@@ -64,25 +56,22 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int D = p.D, C = p.C, M = p.M;
   const uint32_t a_img_bytes = (uint32_t)p.kr_max * kTileM * 2;   // one fp16 image (hi or lo) of an A block: [chunk][128 rows][8 halves]
-  const uint32_t a_buf_bytes = 2 * a_img_bytes;
+  const uint32_t a_buf_bytes = 2 * a_img_bytes;   // ONE A buffer (hi | lo), guarded by a_free
 
   if (tid == 0) {
     for (int i = 0; i < p.nslots; ++i) { tcx::mbar_init(w_full + i, 1); tcx::mbar_init(w_empty + i, 1); }
     tcx::mbar_init(bar_acc, 1);
-    for (int i = 0; i < 2; ++i) { tcx::mbar_init(lc_full + i, 1); tcx::mbar_init(lc_empty + i, kV5EpiWarps); }
-    // slice 0 of every A block also collects one arrival from each NON-producing warp of the chain: a warp that waits
-    // on the accumulator barrier must be needed for the next MMA, otherwise the issuer could complete two accumulator
-    // phases before a late warp has observed the first one and its parity wait would never return
-    // pair j = K slices 2 j (slice lane 0) and 2 j + 1 (slice lane 1): EVERY epilogue warp arrives exactly once per pair and push
-    // (after publishing its slice, or as an observer when its lane has no slice in the pair).  A warp that waits on the
-    // accumulator barrier is therefore always needed for the next MMA group and can never be lapped by two accumulator phases.
-    for (int i = 0; i < 2 * kV5MaxPairs; ++i) tcx::mbar_init(a_ready + i, kV5EpiWarps);
+    for (int i = 0; i < 2; ++i) { tcx::mbar_init(lc_full + i, 1); tcx::mbar_init(lc_empty + i, kV6EpiWarps); }
+    // EVERY epilogue warp arrives exactly once per A block (after publishing its slices, or as an observer when its slice
+    // lane has none).  A warp that waits on the accumulator barrier is therefore always needed for the next push and can
+    // never be lapped by two accumulator phases; the same argument covers a_free (protocol rule).
+    tcx::mbar_init(a_ready, kV6EpiWarps);
     tcx::mbar_init(a_free, 1);
     for (int i = 0; i < 8; ++i) xflag[i] = 0;
     tcx::mbar_fence_init();
   }
   if (warp == 0) tcx::tmem_alloc(tmem_slot, kTmemCols);
-  for (uint32_t i = tid; i < (2 * a_buf_bytes) / 16; i += kV5Threads)
+  for (uint32_t i = tid; i < a_buf_bytes / 16; i += kV6Threads)
     reinterpret_cast<uint4*>(smem + p.off_h)[i] = make_uint4(0, 0, 0, 0);
   tcx::fence_async_smem();
   tcx::tc_fence_before();
@@ -94,7 +83,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
   const int n_tiles = (io.N + kTileM - 1) / kTileM;
   const long long n_items = (long long)n_tiles * n_groups;
 
-  if (warp == kV5Producer) {
+  if (warp == kV6Producer) {
     // ===================== TMA producer: weight images + layer constants =====================
     if (lane == 0) {
       uint32_t cnt = 0, lcnt = 0;
@@ -147,13 +136,16 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
         atomicAdd(p.grp_done + prev_grp, 1);
       }
     }
-  } else if (warp == kV5Issuer) {
+  } else if (warp == kV6Issuer) {
     // ===================== MMA issuer =====================
-    // Whole warp convergent through the waits; each group of MMAs is guarded by a fresh elect.sync (CUTLASS idiom).
+    // Whole warp convergent through the waits; each push is issued under a fresh elect.sync (CUTLASS idiom) so that ptxas
+    // keeps the descriptors in uniform registers.  Per step (one weight image): wait for the image, at the first sub-step
+    // of a push wait for the A block, then  critical columns -> commit(accumulator barrier) -> remaining columns ->
+    // commit(weight slot) [-> commit(a_free)].
     const uint32_t ring_a = tcx::smem_u32(ring);
     const uint32_t a_base = tcx::smem_u32(smem + p.off_h);
     constexpr uint32_t lbo_a = kTileM * 16;
-    uint32_t slot = 0, use = 0, buf = 0, apar = 0;   // apar: one parity bit per (buffer, slice) barrier
+    uint32_t slot = 0, use = 0, rdy_par = 0;
     int dbg_n = 0;
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int grp = (int)(item / n_tiles);
@@ -166,104 +158,72 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
             const uint32_t s_n = p.steps[st].n, s_ncrit = p.steps[st].n_crit, s_dcol = p.steps[st].d_col;
             const int ksteps = p.steps[st].ksteps;
             const uint32_t s_acc = p.steps[st].accumulate, s_last = (p.steps[st].epi != EPI_NONE);
-            const uint32_t slice0 = p.steps[st].a_chunk0 >> 1;
+            const uint32_t chunk0 = p.steps[st].a_chunk0;
+            const uint32_t slice0 = chunk0 >> 1;
             const uint32_t n_rest = s_n - s_ncrit;
             const uint32_t idesc_c = tcx::make_idesc_f16(s_ncrit);
             const uint32_t idesc_r = tcx::make_idesc_f16(n_rest);
-            // The issuer is ONE thread running a serial instruction stream (~5 cycles per dependent instruction): what it
-            // executes per K slice bounds the MMA rate long before the tensor pipe does (tools/tc_probe_rate2.cu: 123 cycles
-            // per MMA for a 25-instruction loop body whatever M, N or the operand source).  So the slice loop only waits,
-            // adds constants to the low words of four running descriptors and fires the MMAs.
             constexpr uint32_t dhi32 = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1
             const uint32_t a_step = (2u * lbo_a) >> 4, b_step = (2u * s_n * 16u) >> 4;
-            uint32_t da_h = (((a_base + buf * a_buf_bytes) + slice0 * 2u * lbo_a) >> 4) | ((lbo_a >> 4) << 16);
-            uint32_t da_l = da_h + (a_img_bytes >> 4);
-            uint32_t db_h = ((ring_a + slot * kSlotBytes) >> 4) | (((s_n * 16u) >> 4) << 16);
-            uint32_t db_l = db_h + (s_wbytes >> 5);
+            const uint32_t da_h0 = ((a_base + slice0 * 2u * lbo_a) >> 4) | ((lbo_a >> 4) << 16);
+            const uint32_t da_l0 = da_h0 + (a_img_bytes >> 4);
+            const uint32_t db_h0 = ((ring_a + slot * kSlotBytes) >> 4) | (((s_n * 16u) >> 4) << 16);
+            const uint32_t db_l0 = db_h0 + (s_wbytes >> 5);
             const uint32_t d_c = s_dcol, d_r = d_c + s_ncrit;   // TMEM base is 0 (checked above): lane 0, column d_col
             const uint32_t ro = s_ncrit;                        // image row n_crit = byte offset n_crit * 16, >> 4
-            // A in TMEM: ONE buffer (every MMA of a push has retired before the epilogue that writes the next block passes
-            // the accumulator barrier: pushes are unsplit), K slice s at columns t_a + 8 s (hi) / t_a + kr_max / 2 + 8 s (lo)
-            uint32_t ta_h = p.t_a + slice0 * 8u, ta_l = ta_h + (uint32_t)p.kr_max / 2u;
-            const uint32_t pair0 = slice0 >> 1;                 // sub-steps of a K-split push start at an even slice
-            uint64_t* rdy = a_ready + buf * kV5MaxPairs + pair0;
-            uint32_t bit = 1u << (buf * kV5MaxPairs + pair0);
+            // A in TMEM: K slice s at columns t_a + 8 s (hi) / t_a + kr_max / 2 + 8 s (lo)
+            const uint32_t ta_h0 = p.t_a + slice0 * 8u, ta_l0 = ta_h0 + (uint32_t)p.kr_max / 2u;
             auto desc = [](uint32_t lo) { return ((uint64_t)dhi32 << 32) | lo; };
             LOG5(2, 20)
             mbar_wait4(w_full + slot, use & 1, p.wd, WD_TAG(3));
             LOG5(2, 21)
-            for (int k = 0; k < ksteps; k += 2) {
-              mbar_wait4(rdy, (apar & bit) ? 1u : 0u, p.wd, WD_TAG(4));
-              apar ^= bit;
-              tcx::tc_fence_after();
-              LOG5(2, 32 + k)
-              const bool two = (k + 1 < ksteps);
-              const bool lastk = (k + 2 >= ksteps);
-              if (tcx::elect_one()) {
-                // hi*hi + hi*lo + lo*hi for each K slice of the pair
+            if (chunk0 == 0) {
+              mbar_wait4(a_ready, rdy_par, p.wd, WD_TAG(4));
+              rdy_par ^= 1;
+            }
+            tcx::tc_fence_after();
+            LOG5(2, 32)
+            if (tcx::elect_one()) {
+              // hi*hi + hi*lo + lo*hi for each K slice: critical columns first
+              for (int k = 0; k < ksteps; ++k) {
                 const uint32_t acc0 = (k == 0) ? s_acc : 1u;
                 if (kATmem) {
-                  tcx::mma_f16_ts(d_c, ta_h, desc(db_h), idesc_c, acc0);
-                  tcx::mma_f16_ts(d_c, ta_h, desc(db_l), idesc_c, 1u);
-                  tcx::mma_f16_ts(d_c, ta_l, desc(db_h), idesc_c, 1u);
-                  if (two) {
-                    tcx::mma_f16_ts(d_c, ta_h + 8, desc(db_h + b_step), idesc_c, 1u);
-                    tcx::mma_f16_ts(d_c, ta_h + 8, desc(db_l + b_step), idesc_c, 1u);
-                    tcx::mma_f16_ts(d_c, ta_l + 8, desc(db_h + b_step), idesc_c, 1u);
-                  }
+                  tcx::mma_f16_ts(d_c, ta_h0 + 8u * k, desc(db_h0 + b_step * k), idesc_c, acc0);
+                  tcx::mma_f16_ts(d_c, ta_h0 + 8u * k, desc(db_l0 + b_step * k), idesc_c, 1u);
+                  tcx::mma_f16_ts(d_c, ta_l0 + 8u * k, desc(db_h0 + b_step * k), idesc_c, 1u);
                 } else {
-                  tcx::mma_f16_ss(d_c, desc(da_h), desc(db_h), idesc_c, acc0);
-                  tcx::mma_f16_ss(d_c, desc(da_h), desc(db_l), idesc_c, 1u);
-                  tcx::mma_f16_ss(d_c, desc(da_l), desc(db_h), idesc_c, 1u);
-                  if (two) {
-                    tcx::mma_f16_ss(d_c, desc(da_h + a_step), desc(db_h + b_step), idesc_c, 1u);
-                    tcx::mma_f16_ss(d_c, desc(da_h + a_step), desc(db_l + b_step), idesc_c, 1u);
-                    tcx::mma_f16_ss(d_c, desc(da_l + a_step), desc(db_h + b_step), idesc_c, 1u);
-                  }
+                  tcx::mma_f16_ss(d_c, desc(da_h0 + a_step * k), desc(db_h0 + b_step * k), idesc_c, acc0);
+                  tcx::mma_f16_ss(d_c, desc(da_h0 + a_step * k), desc(db_l0 + b_step * k), idesc_c, 1u);
+                  tcx::mma_f16_ss(d_c, desc(da_l0 + a_step * k), desc(db_h0 + b_step * k), idesc_c, 1u);
                 }
-                if (s_last && lastk) tcx::mma_commit(bar_acc);
-                if (n_rest) {   // split pushes: the remaining columns, behind the critical ones
-                  if (kATmem) {
-                    tcx::mma_f16_ts(d_r, ta_h, desc(db_h + ro), idesc_r, acc0);
-                    tcx::mma_f16_ts(d_r, ta_h, desc(db_l + ro), idesc_r, 1u);
-                    tcx::mma_f16_ts(d_r, ta_l, desc(db_h + ro), idesc_r, 1u);
-                    if (two) {
-                      tcx::mma_f16_ts(d_r, ta_h + 8, desc(db_h + b_step + ro), idesc_r, 1u);
-                      tcx::mma_f16_ts(d_r, ta_h + 8, desc(db_l + b_step + ro), idesc_r, 1u);
-                      tcx::mma_f16_ts(d_r, ta_l + 8, desc(db_h + b_step + ro), idesc_r, 1u);
-                    }
-                  } else {
-                    tcx::mma_f16_ss(d_r, desc(da_h), desc(db_h + ro), idesc_r, acc0);
-                    tcx::mma_f16_ss(d_r, desc(da_h), desc(db_l + ro), idesc_r, 1u);
-                    tcx::mma_f16_ss(d_r, desc(da_l), desc(db_h + ro), idesc_r, 1u);
-                    if (two) {
-                      tcx::mma_f16_ss(d_r, desc(da_h + a_step), desc(db_h + b_step + ro), idesc_r, 1u);
-                      tcx::mma_f16_ss(d_r, desc(da_h + a_step), desc(db_l + b_step + ro), idesc_r, 1u);
-                      tcx::mma_f16_ss(d_r, desc(da_l + a_step), desc(db_h + b_step + ro), idesc_r, 1u);
-                    }
-                  }
-                }
-                if (lastk) tcx::mma_commit(w_empty + slot);   // the slot is free once these MMAs retire
-                // A in TMEM is single-buffered: the writers of the next block wait for this before their first store
-                // (with unsplit pushes it has completed before they pass the accumulator barrier; with split ones the
-                // trailing MMAs are still reading the block at that point)
-                if (kATmem && s_last && lastk) tcx::mma_commit(a_free);
               }
-              __syncwarp();
-              LOG5(2, 48 + k)
-              da_h += 2 * a_step; da_l += 2 * a_step; db_h += 2 * b_step; db_l += 2 * b_step;
-              ta_h += 16; ta_l += 16;
-              ++rdy; bit <<= 1;
+              if (s_last) tcx::mma_commit(bar_acc);
+              if (n_rest) {
+                for (int k = 0; k < ksteps; ++k) {
+                  const uint32_t acc0 = (k == 0) ? s_acc : 1u;
+                  if (kATmem) {
+                    tcx::mma_f16_ts(d_r, ta_h0 + 8u * k, desc(db_h0 + b_step * k + ro), idesc_r, acc0);
+                    tcx::mma_f16_ts(d_r, ta_h0 + 8u * k, desc(db_l0 + b_step * k + ro), idesc_r, 1u);
+                    tcx::mma_f16_ts(d_r, ta_l0 + 8u * k, desc(db_h0 + b_step * k + ro), idesc_r, 1u);
+                  } else {
+                    tcx::mma_f16_ss(d_r, desc(da_h0 + a_step * k), desc(db_h0 + b_step * k + ro), idesc_r, acc0);
+                    tcx::mma_f16_ss(d_r, desc(da_h0 + a_step * k), desc(db_l0 + b_step * k + ro), idesc_r, 1u);
+                    tcx::mma_f16_ss(d_r, desc(da_l0 + a_step * k), desc(db_h0 + b_step * k + ro), idesc_r, 1u);
+                  }
+                }
+              }
+              tcx::mma_commit(w_empty + slot);       // the slot is free once these MMAs retire
+              if (s_last) tcx::mma_commit(a_free);   // ... and so is the A block: the next block's writers wait for this
             }
+            __syncwarp();
             LOG5(2, 23)
             if (++slot == (uint32_t)p.nslots) { slot = 0; ++use; }
-            if (s_last) buf ^= 1;
           }
         }
       }
     }
   } else {
-    // ===================== epilogue warps: 4 TMEM lane quadrants x 2 row halves x 2 slice lanes =====================
+    // ===================== epilogue warps: 4 TMEM lane quadrants x 2 row halves x 3 slice lanes =====================
     const int q = warp & 3, part = warp >> 2, rh = part & 1, sll = part >> 1;
     const int hw = lane >> 4, lr = lane & 15;
     const int trow = q * 32 + rh * 16 + lr;        // row inside the 128-point tile (= TMEM lane)
@@ -275,24 +235,17 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
     const bool rows_mine = (sll == 0);             // this warp owns the per-row state of its 16 rows
     const bool owner = rows_mine && (hw == 0);
     const bool add_ctx = (C > 0) && !p.folded;
-    const int pair_id = 1 + q * 2 + rh;            // named barrier of the two warps (slice lanes) sharing these 16 rows
+    const int pair_id = 1 + q * 2 + rh;            // named barrier of the three warps (slice lanes) sharing these 16 rows
     float* scr = scratch + trow;
     auto raw = [&](int m) { return scr[m * kTileM]; };
     auto setw = [&](int m, float v) { scr[m * kTileM] = v; };
     uint8_t* a_chain = smem + p.off_h;
     uint64_t* my_acc = bar_acc;
-    uint64_t* my_ready = a_ready;
-    uint32_t par_acc = 0, lcnt = 0, buf = 0, par_free = 1;   // first A block: wait(parity 1) on the fresh barrier returns at once
+    uint32_t par_acc = 0, lcnt = 0, par_free = 1;   // par_free: first A block -> wait(parity 1) on the fresh barrier returns at once
     int dbg_n = 0;
     const int dbg_slot = sll;
-    auto await_a_free = [&](bool has_slices) {   // once per A block and warp, right before the first store
-      if (kATmem) {
-        if (has_slices) { mbar_wait4(a_free, par_free, p.wd, WD_TAG(7)); tcx::tc_fence_after(); }
-        par_free ^= 1;
-      }
-    };
     // x_r hand-over inside a 16-row group: the owner warp (slice lane 0) publishes every x it finalises by bumping a
-    // shared-memory counter, its partner warp (slice lane 1) counts the same program steps and polls the counter before
+    // shared-memory counter, its partner warps (slice lanes 1, 2) count the same program steps and polls the counter before
     // a first-layer phase that needs x (a 64-thread bar.sync cost ~300 cycles here, on the critical path of every stage)
     volatile int* my_xflag = xflag + q * 2 + rh;
     int xcount = 0;
@@ -313,7 +266,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
     };
     const uint64_t scale2 = tcx::pk2(kTanhScale, kTanhScale);
 
-    // write this thread's 8-column chunk `c` (hi / lo fp16) of the A block: layout [chunk][64 rows][8 halves]
+    // write this thread's 8-column chunk `c` (hi / lo fp16) of the A block: layout [chunk][128 rows][8 halves]
     auto store_chunk = [&](int c, const uint4& hi4, const uint4& lo4) {
       if (kATmem) {
         // chunk c = K elements [8c, 8c + 8) = TMEM columns [4c, 4c + 4) of the hi / lo image; the two half-warps of a row hold
@@ -322,22 +275,25 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
         tcx::tmem_st16x2_4<4>(ta, hi4.x, hi4.y, hi4.z, hi4.w);
         tcx::tmem_st16x2_4<4>(ta + (uint32_t)p.kr_max / 2u, lo4.x, lo4.y, lo4.z, lo4.w);
       } else {
-        uint8_t* dst = a_chain + (size_t)buf * a_buf_bytes + ((size_t)c * kTileM + crow) * 16;
+        uint8_t* dst = a_chain + ((size_t)c * kTileM + crow) * 16;
         *reinterpret_cast<uint4*>(dst) = hi4;
         *reinterpret_cast<uint4*>(dst + a_img_bytes) = lo4;
       }
     };
-    // publish K slice `sl` of the A block under construction
-    auto publish = [&](int sl) {
-      if (kATmem) { tcx::tmem_st_wait(); tcx::tc_fence_before(); }
-      else tcx::fence_async_smem();
-      __syncwarp();
-      if (lane == 0) tcx::mbar_arrive(my_ready + buf * kV5MaxPairs + (sl >> 1));
+    // the A block of the previous push may be overwritten: every MMA that reads it has retired (one wait per block and warp,
+    // taken right before the first store; all warps keep the parity in step whether or not they have a slice)
+    auto await_a_free = [&](bool has_slices) {
+      if (has_slices) { mbar_wait4(a_free, par_free, p.wd, WD_TAG(7)); tcx::tc_fence_after(); }
+      par_free ^= 1;
     };
-    // pairs in which this warp's slice lane has no slice (only the last pair of a block with an odd slice count)
-    auto observe = [&](int nsl) {
-      const int npairs = (nsl + 1) >> 1;
-      if (2 * (npairs - 1) + sll >= nsl && lane == 0) tcx::mbar_arrive(my_ready + buf * kV5MaxPairs + (npairs - 1));
+    // this warp's slices of the A block are written (or it has none): one arrival per warp and block
+    auto publish_block = [&](bool has_slices) {
+      if (has_slices) {
+        if (kATmem) { tcx::tmem_st_wait(); tcx::tc_fence_before(); }
+        else tcx::fence_async_smem();
+      }
+      __syncwarp();
+      if (lane == 0) tcx::mbar_arrive(a_ready);
     };
 
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -346,7 +302,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
       const int npts = min(kTileM, io.N - n0);
       float run_m = -INFINITY, run_s = 0.f;
       // ---- tile load: the 16 rows of this quadrant (part-0 warp), then visible to the other parts ----
-      pair_bar_sync(pair_id, 64);       // every part is done with the previous tile's rows
+      pair_bar_sync(pair_id, 32 * kV6SliceLanes);       // every part is done with the previous tile's rows
       if (rows_mine) {
         if (add_ctx)
           for (int i = lane; i < 16 * C; i += 32) {
@@ -367,7 +323,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
           ljac[trow] = lj;
         }
       }
-      pair_bar_sync(pair_id, 64);       // context rows are in shared memory
+      pair_bar_sync(pair_id, 32 * kV6SliceLanes);       // context rows are in shared memory
 
       for (int si = grp; si < io.s_count; si += n_groups) {
         // ---- draw start ----
@@ -380,7 +336,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
           const int* perm = p.perm + l * D;
           const float* lc = lcs + (size_t)(lcnt & 1) * p.lc_floats;
           mbar_wait4(lc_full + (lcnt & 1), (lcnt >> 1) & 1, p.wd, WD_TAG(5));
-          const bool dbg_on = kDbg && p.dbg != nullptr && blockIdx.x == 0 && q == 0 && rh == 0 && item == blockIdx.x && si != grp && li >= 2;
+          const bool dbg_on = kDbg && p.dbg != nullptr && blockIdx.x == 0 && q == 0 && rh == 0 && sll < 2 && item == blockIdx.x && si != grp && li >= 2;
           for (int st = 0; st < p.nsteps; ++st) {
             const uint32_t s_epi = p.steps[st].epi;
             if (s_epi == EPI_NONE) continue;   // K-split sub-step: nothing to do on this side
@@ -396,26 +352,24 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
             if (s_epi == EPI_TANH) {
               // block of nch 8-column chunks = nsl K slices; slice s = chunks {2s (half-warp 0), 2s+1 (half-warp 1)}
               const int nch = s_encols >> 3, nsl = (nch + 1) >> 1;
-              const int nmine = (nsl - sll + 1) / 2;   // slices sll, sll + 2, ...
-              observe(nsl);
-              if (nmine == 0) await_a_free(false);
+              const int nmine = nsl > sll ? (nsl - sll + kV6SliceLanes - 1) / kV6SliceLanes : 0;   // slices sll, sll + 3, ...
+              bool first = true;
               for (int j0 = 0; j0 < nmine; j0 += 2) {
                 uint32_t r[16];
                 const int nj = min(2, nmine - j0);
-                const int sl0 = sll + j0 * 2;
+                const int sl0 = sll + j0 * kV6SliceLanes;
                 const uint32_t ta = lane_base + s_ecol + sl0 * 16;
-                // software-pipelined accumulator reads (TMEM -> registers runs at ~64 B/clk for the whole SM: 450 cycles for a
-                // 56-column block): the second slice of this warp is in flight while the first one goes through tanh
+                // a second slice of this warp (blocks wider than 3 slices) is in flight while the first one goes through tanh
                 tcx::tmem_ld16x2_8<8>(ta, r);
                 tcx::tmem_ld_wait();
-                if (nj > 1) tcx::tmem_ld16x2_8<8>(ta + 32, r + 8);
+                if (nj > 1) tcx::tmem_ld16x2_8<8>(ta + 16 * kV6SliceLanes, r + 8);
                 tcx::tc_fence_before();
                 LOG5(dbg_slot, 3)
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                   if (u < nj) {
                     if (u == 1) { tcx::tmem_ld_wait(); tcx::tc_fence_before(); }
-                    const int sl = sl0 + u * 2;
+                    const int sl = sl0 + u * kV6SliceLanes;
                     const int c = sl * 2 + hw;
                     const int cl = min(c, nch - 1);
                     const uint32_t* ru = r + 8 * u;
@@ -429,14 +383,14 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
                     uint4 hi4, lo4;
                     tcx::tanh8_scaled(s2, hi4, lo4);
                     if (c >= nch) { hi4 = make_uint4(0, 0, 0, 0); lo4 = hi4; }   // K padding chunk
-                    if (j0 == 0 && u == 0) await_a_free(true);
+                    if (first) { await_a_free(true); first = false; }
                     store_chunk(c, hi4, lo4);
-                    publish(sl);
                     LOG5(dbg_slot, 8 + sl)
                   }
                 }
               }
-              buf ^= 1;
+              if (nmine == 0) await_a_free(false);
+              publish_block(nmine > 0);
             } else if (s_epi == EPI_FIRST) {
               // first conditioner layer of block `stage` on CUDA cores: s = b'[n] + sum_c W0c[n][c] ctx_c + sum_{q < stage} W0x[n][q] x_q
               // (everything pre-multiplied by 2 log2 e), tanh, fp16 hi/lo A block.  x_q (by rank) were written by the row owners.
@@ -445,14 +399,13 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
               LOG5(dbg_slot, 4)
               const int nch = s_encols >> 3, nsl = (nch + 1) >> 1;
               const int u0 = s_eaux;
-              const int nmine = (nsl - sll + 1) / 2;
-              observe(nsl);
-              await_a_free(nmine > 0);
+              const int nmine = nsl > sll ? (nsl - sll + kV6SliceLanes - 1) / kV6SliceLanes : 0;
               // q-major weights: lc_w0x[q][n] (x of rank q -> unit n), lc_w0c[c][n] (context c -> unit n), everything scaled by
               // 2 log2 e; a thread's 8 units are two 16-byte loads per input and the update is 4 packed FFMA2
-              const int hp0 = p.dp4;   // v5: KParamsInv4::dp4 carries the padded width of hidden layer 0 = row stride of both tables
+              const int hp0 = p.dp4;   // KParamsInv4::dp4 carries the padded width of hidden layer 0 = row stride of both tables
+              await_a_free(nmine > 0);
               for (int j = 0; j < nmine; ++j) {
-                const int sl = sll + j * 2;
+                const int sl = sll + j * kV6SliceLanes;
                 const int c = sl * 2 + hw;
                 uint4 hi4 = make_uint4(0, 0, 0, 0), lo4 = hi4;
                 if (c < nch) {
@@ -485,11 +438,10 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
                 }
                 if (kATmem) __syncwarp();   // the TMEM store is warp-collective: reconverge after the per-chunk branch
                 store_chunk(c, hi4, lo4);
-                publish(sl);
                 LOG5(dbg_slot, 8 + sl)
               }
+              publish_block(nmine > 0);
               if (fast_rqs && owner) flush_ld(ld_acc);   // log-dets of the inverses since the last flush, off the critical path
-              buf ^= 1;
             } else if (s_epi == EPI_XINV0C) {
               // context-folded rank 0: the transform parameters are per-draw constants (lc_r0c), no accumulator involved
               if (owner) {

@@ -212,7 +212,8 @@ static int pack_impl(nazb_handle* h, const float* const* W, const float* const* 
   cudaStream_t st = (cudaStream_t)stream;
   CK(h, cudaSetDevice(h->device));
   h->is_packed = false;   // stays false when anything below fails (a half-packed handle must not be evaluated)
-  CK(h, nazb_stage_begin(h, 64 + sizeof(int) * 2 * (size_t)g.L * g.D + 8 * (size_t)7 * g.L * n_lin + 64));
+  CK(h, nazb_stage_begin(h, 64 + sizeof(int) * 2 * (size_t)g.L * g.D + 8 * (size_t)7 * g.L * n_lin + 64 +
+                               sizeof(short) * NAZB_MAX_HIDDEN_LAYERS * 256 + 64));   // + the column map of the block-aligned layout
   // perm + rank tables
   std::vector<int> pr(2 * (size_t)g.L * g.D);
   for (int l = 0; l < g.L; ++l) {

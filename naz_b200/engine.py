@@ -140,7 +140,7 @@ class FlowEngine:
             raise _lib.NazbError(rc, where, detail)
 
     # engine options (include/nazb.h: nazb_set_option); nothing in the library reads the environment
-    OPTION_NAMES = ("inv_kernel", "inv_merge_n", "inv_fold", "inv_gate", "inv_a_tmem")
+    OPTION_NAMES = ("inv_kernel", "inv_merge_n", "inv_fold", "inv_gate", "inv_a_tmem", "inv_align")
 
     def set_option(self, name: str, value: int) -> None:
         self._check(self._lib.nazb_set_option(self._h, name.encode(), int(value)), f"nazb_set_option({name})")
@@ -153,7 +153,7 @@ class FlowEngine:
     def options(self) -> dict:
         """Current engine options (for bench / test records); {} on the SIMT engine."""
         out = {}
-        for k in self.OPTION_NAMES + ("inv_fold_available", "inv_kernel_in_use", "inv_a_tmem_in_use"):
+        for k in self.OPTION_NAMES + ("inv_fold_available", "inv_kernel_in_use", "inv_a_tmem_in_use", "inv_block_width"):
             v = self.get_option(k)
             if v is not None:
                 out[k] = v

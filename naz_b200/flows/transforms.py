@@ -9,16 +9,17 @@ from .made import AutoRegressiveNN, ConditionalAutoRegressiveNN
 
 
 def bounding_transform(x, low, high):
-    """transforms.py:20-23 — provided for API compatibility; inside log_prob it is fused into the kernel."""
-    y = (x - low.expand(x.shape)) / ((high - low).expand(x.shape))
-    log_jac = -torch.sum(torch.log(y) + torch.log1p(-y), axis=-1) - torch.sum(torch.log(high - low))
-    return torch.logit(y), log_jac
+    """transforms.py:20-23: box -> unbounded by a logit of the box coordinate; returns (y, log|dy/dx| summed over dims).
+    Host-side helper for API compatibility; inside log_prob the same map is fused into the kernels (transforms.cuh)."""
+    width = high - low
+    u = (x - low) / width                               # box coordinate in (0, 1); low / high broadcast over the batch
+    log_jac = -(u.log() + torch.log1p(-u)).sum(-1) - width.log().sum()
+    return torch.logit(u), log_jac
 
 
 def inverse_bounding_transform(y, low, high):
-    """transforms.py:25-27."""
-    x = torch.sigmoid(y)
-    return x * ((high - low).expand(y.shape)) + low.expand(y.shape)
+    """transforms.py:25-27: unbounded -> box."""
+    return low + (high - low) * torch.sigmoid(y)
 
 
 class _ARTransform(nn.Module):

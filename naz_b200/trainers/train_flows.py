@@ -2,8 +2,6 @@
 `predict` (:384-422) and the importance-weight reduction behind `train_importance` (:358-380)."""
 from __future__ import annotations
 
-import copy
-
 import numpy as np
 import torch
 
@@ -11,23 +9,19 @@ from ..engine import importance
 
 
 def get_params(flow):
-    params = []
-    for t in flow.flow_dist.transforms:
-        this_params = {}
-        for name, param in t.named_parameters():
-            this_params[name] = copy.deepcopy(param)
-        params.append(this_params)
-    return params
+    """train_flows.py:20-45 -> one {parameter name: detached copy} dict per flow transform, in transform order."""
+    return [{name: param.detach().clone().requires_grad_(param.requires_grad) for name, param in t.named_parameters()}
+            for t in flow.flow_dist.transforms]
 
 
 def set_params(flow, params, sample_idx=None):
-    for i, t in enumerate(flow.flow_dist.transforms):
-        for name, param in t.named_parameters():
-            with torch.no_grad():
-                if sample_idx is None:
-                    param.copy_(params[i][name])
-                else:
-                    param.copy_(params[f"flow_{i}_{name}"][sample_idx])
+    """train_flows.py:47-71.  `params` is either the list `get_params` returns, or (with `sample_idx`) the posterior-sample
+    dict `"flow_{i}_{name}" -> tensor[S, ...]` from which draw `sample_idx` is copied in."""
+    with torch.no_grad():
+        for i, t in enumerate(flow.flow_dist.transforms):
+            for name, param in t.named_parameters():
+                src = params[i][name] if sample_idx is None else params[f"flow_{i}_{name}"][sample_idx]
+                param.copy_(src)
 
 
 def predict(flow, cond, posterior_samples, Nsamples, base_noise=None):

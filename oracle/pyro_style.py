@@ -22,25 +22,38 @@ import torch.nn.functional as F
 from torch.distributions import Normal, TransformedDistribution, Transform, constraints
 
 
-def sample_mask_indices(input_dim, hidden_dim):
-    return torch.round(torch.linspace(1, input_dim, steps=hidden_dim))
+def hidden_degrees(n_degrees, width):
+    """Degrees of `width` hidden units spread evenly over 1..n_degrees (pyro `sample_mask_indices`, simple=True): an fp32
+    linspace rounded half-to-even, as torch / jax round."""
+    return torch.round(torch.linspace(1.0, float(n_degrees), steps=width))
 
 
 def create_mask(input_dim, context_dim, hidden_dims, permutation, output_dim_multiplier):
-    var_index = torch.empty(permutation.shape, dtype=torch.float32)
-    var_index[permutation] = torch.arange(input_dim, dtype=torch.float32)
-    input_indices = torch.cat((torch.zeros(context_dim), 1 + var_index))
+    """MADE masks from the DEFINITION (Germain et al. 2015, as pyro arranges it), written independently of
+    naz_b200/flows/made.py: every unit carries a degree; a connection in -> out exists iff degree(out) >= degree(in) for
+    hidden targets and degree(out) > degree(in) for output targets.  Context inputs have degree 0, x_d has degree
+    1 + rank(d) under the layer's permutation, hidden units of a CONDITIONAL net take degrees 0 .. D-1 (so that degree-0
+    units see the context only), of an unconditional one 1 .. D-1."""
+    D = int(input_dim)
+    rank = torch.zeros(D)
+    for position, dim in enumerate(permutation.tolist()):
+        rank[dim] = position
+    deg_in = torch.cat([torch.zeros(int(context_dim)), rank + 1.0])
     if context_dim > 0:
-        hidden_indices = [sample_mask_indices(input_dim, h) - 1 for h in hidden_dims]
+        deg_hidden = [hidden_degrees(D, h) - 1.0 for h in hidden_dims]
     else:
-        hidden_indices = [sample_mask_indices(input_dim - 1, h) for h in hidden_dims]
-    output_indices = (var_index + 1).repeat(output_dim_multiplier)
-    mask_skip = (output_indices.unsqueeze(-1) > input_indices.unsqueeze(0)).float()
-    masks = [(hidden_indices[0].unsqueeze(-1) >= input_indices.unsqueeze(0)).float()]
-    for i in range(1, len(hidden_dims)):
-        masks.append((hidden_indices[i].unsqueeze(-1) >= hidden_indices[i - 1].unsqueeze(0)).float())
-    masks.append((output_indices.unsqueeze(-1) > hidden_indices[-1].unsqueeze(0)).float())
-    return masks, mask_skip
+        deg_hidden = [hidden_degrees(D - 1, h) for h in hidden_dims]
+    deg_out = (rank + 1.0).repeat(output_dim_multiplier)
+
+    def connect(deg_to, deg_from, strict):
+        to, frm = deg_to[:, None], deg_from[None, :]
+        return (to > frm).float() if strict else (to >= frm).float()
+
+    masks = [connect(deg_hidden[0], deg_in, strict=False)]
+    for prev, cur in zip(deg_hidden[:-1], deg_hidden[1:]):
+        masks.append(connect(cur, prev, strict=False))
+    masks.append(connect(deg_out, deg_hidden[-1], strict=True))
+    return masks, connect(deg_out, deg_in, strict=True)
 
 
 class MaskedLinear(nn.Linear):

@@ -6,13 +6,16 @@ fp64 oracle.  Deep spline flows have a few ill-conditioned points where ANY fp32
 (the oracle run in fp32 misses the bar on ~1e-4 of the points, worst ~2x) — cannot meet that bar: a one-ulp(fp32) change of
 the inputs already moves the fp64 answer by a sizeable fraction of the tolerance there.  The checks therefore are
   (1) at most MAX_VIOL = 0.2 % of the entries outside the strict tolerance (measured: 0.01-0.04 %),
-  (2) EVERY entry within 2 tol + 20 sens, where sens = |ref(inputs (1 +- 2^-23)) - ref(inputs)| is the sensitivity of the fp64
-      answer to a one-ulp relative perturbation of the inputs (so only demonstrably ill-conditioned points may exceed twice
-      the tolerance; measured: violators sit in the top 1 % of sens, the worst entry 14.9 tol had sens = 1.13 tol),
+  (2) EVERY entry within 3 tol + 20 sens, where sens = |ref(inputs (1 +- 2^-23)) - ref(inputs)| is the sensitivity of the fp64
+      answer to a one-ulp relative perturbation of the inputs (so only demonstrably ill-conditioned points may exceed three
+      times the tolerance; measured on B200, tools/parity_stats2.py: violators sit in the top 1 % of sens, the worst entry
+      14.9 tol had sens = 1.13 tol; among well-conditioned points the worst was 2.3 tol for the fp32 SIMT engine, 2.0 tol for
+      the tensor-core engine and 2.15 tol for the fp32 oracle itself, i.e. the reference's own dtype),
   (3) the same two bounds against the oracle evaluated in fp32 (the reference's dtype),
 and for fixtures without a sensitivity (reference-executed outputs, small goldens): (1) plus every entry within WORST = 6 tol."""
 import functools
 import math
+import os
 
 import numpy as np
 import pytest
@@ -44,7 +47,7 @@ def check(got, ref, what, sens=None, ref32=None, max_viol=MAX_VIOL, worst=WORST,
         if sens is None:
             assert w <= worst, f"{what} vs {name}: worst entry {w:.1f}x tolerance"
         else:
-            over = err - (2.0 * tol + 20.0 * sens)
+            over = err - (3.0 * tol + 20.0 * sens)
             i = np.unravel_index(np.argmax(over), over.shape) if over.size else None
             assert not over.size or over[i] <= 0, (f"{what} vs {name}: entry {i} is {err[i] / tol[i]:.1f}x tolerance but the point is "
                                                    f"well conditioned (sens = {sens[i] / tol[i]:.3f} tol)")
@@ -277,12 +280,18 @@ def test_svi_importance_pipeline_on_device():
 
 
 INV_VARIANTS = [
-    {},                                       # v5 kernel (one 128-row chain), defaults
+    {},                                       # v5 kernel (one 128-row chain, 16 epilogue warps, unsplit pushes), defaults
+    {"inv_kernel": 6},                        # v6 kernel (24 epilogue warps, split pushes behind an a_free barrier)
+    {"inv_kernel": 6, "inv_merge_n": 256},    # v6 with unsplit pushes
+    {"inv_kernel": 6, "inv_a_tmem": 0},       # v6 with the A operand in shared memory
+    {"inv_align": 1},                         # v5 on the block-aligned column layout
+    {"inv_kernel": 6, "inv_align": 1},        # v6 on the block-aligned column layout
     {"inv_kernel": 3},                        # round-1 kernel (kept as the A/B baseline)
     {"inv_kernel": 4},                        # two 64-row chains
     {"inv_kernel": 4, "inv_merge_n": 256},    # ... every push issued unsplit
-    {"inv_merge_n": 0},                       # v5 with split pushes (critical columns first; forces the A operand to shared memory)
+    {"inv_merge_n": 0},                       # v5 with split pushes (critical columns first; A stays in tensor memory behind a_free)
     {"inv_a_tmem": 0},                        # v5 with the A operand in shared memory
+    {"inv_a_tmem": 0, "inv_merge_n": 0},      # ... and split pushes
     {"inv_fold": 0},                          # broadcast context evaluated per point (general program)
     {"inv_gate": 0},
 ]
@@ -564,7 +573,7 @@ def test_reference_python_api_drop_in():
     check(pred, ref, "predict")
     # twin API: ["lp"] per draw and batched, ["sampler"]
     tp, _, masks, mask_skips, tperms = torch_to_jax(flow)
-    nn_fn = make_conditional_autoregressive_nn(D, C, hidden)
+    nn_fn, param_shape, mask_generator = make_conditional_autoregressive_nn(D, C, hidden)     # calibrate.py:91, verbatim unpacking
     tr = make_masked_affine_autoregressive_transform(nn_fn, D)
     twin = make_normalizing_flow(tr, T(x), masks, mask_skips, tperms, bounds=None, context=T(ctx))
     check(twin["lp"](tp), lp2_ref, "twin lp")
@@ -690,3 +699,131 @@ def test_cuda_matches_real_pyro():
             check(out["lp"][0], o["lp"], f"{c[0]} lp vs pyro ({engine})", atol=1e-4)
             xs = eng.forward(T(o["zin"]), T(ctx))
             check(xs[0], o["ys"], f"{c[0]} samples vs pyro ({engine})", atol=1e-4)
+
+
+def test_twin_layer_functions_and_in_place_updates():
+    """forward_fn / inverse_fn of ONE layer (bflow_jax_maf.py:173-193) reduced over the layers as upstream does (:207,:219)
+    equal the fused all-layer launch and the reference-executed fixture; in-place parameter updates are picked up by lp."""
+    from functools import reduce
+    from naz_b200.flows.bflow_maf import (make_conditional_autoregressive_nn, make_masked_affine_autoregressive_transform,
+                                          make_normalizing_flow)
+    spec, params, g = load_ref_twin("ref_twin_maf_bcast_ctx_2d")
+    D, C, L = spec.D, spec.C, spec.L
+    nn_fn, _, gen_mask = make_conditional_autoregressive_nn(D, C, spec.hidden)
+    fwd, inv = make_masked_affine_autoregressive_transform(nn_fn, D)
+    tp = [[(T(W).cuda(), T(b).cuda()) for (W, b) in layer] for layer in params]
+    masks, mask_skips, perms = [], [], []
+    for l in range(L):
+        m, ms, pm = gen_mask(torch.from_numpy(spec.perms[l]))
+        masks.append(m); mask_skips.append(ms); perms.append(pm)
+        for j in range(len(m)):
+            assert np.array_equal(m[j].numpy(), g[f"mask_{l}_{j}"])        # generate_mask == the reference's create_mask
+    x, ctx = T(g["x"].astype(np.float32)).cuda(), T(g["ctx"].astype(np.float32)).cuda()
+    # log_prob the upstream way: reduce(inverse_fn, reversed layers, (x, 0))
+    inv_c = lambda yj, args: inv(yj, args, context=ctx)
+    z, ldj = reduce(inv_c, zip(reversed(tp), reversed(masks), reversed(mask_skips), reversed(perms)), (x, torch.zeros(x.shape[0], device="cuda")))
+    lp_layers = -(0.5 * z * z).sum(-1) - 0.5 * D * math.log(2 * math.pi) - ldj
+    check(lp_layers, g["lp"], "reduce(inverse_fn) vs reference lp", atol=2e-5)
+    twin = make_normalizing_flow((fwd, inv), x, masks, mask_skips, perms, context=ctx)
+    check(twin["lp"](tp), g["lp"], "fused lp vs reference lp")
+    # sampler the upstream way: reduce(forward_fn, layers, (z, base log-prob))
+    zin = T(g["zin"].astype(np.float32)).cuda()
+    fwd_c = lambda xj, args: fwd(xj, args, context=ctx)
+    y, lj = reduce(fwd_c, zip(tp, masks, mask_skips), (zin, -(0.5 * zin * zin).sum(-1) - 0.5 * D * math.log(2 * math.pi)))
+    check(y, g["ys"], "reduce(forward_fn) vs reference samples")
+    check(lj, g["log_j"], "reduce(forward_fn) log_j vs reference", atol=1e-4)
+    # in-place update of a leaf must change lp (the engine cache is keyed on tensor versions)
+    lp0 = twin["lp"](tp).clone()
+    with torch.no_grad():
+        tp[0][0][0].mul_(1.05)
+    lp1 = twin["lp"](tp)
+    assert (lp1 - lp0).abs().max().item() > 1e-4, "stale packed weights after an in-place update"
+    p64 = [[(W.cpu().numpy().astype(np.float64), b.cpu().numpy().astype(np.float64)) for (W, b) in layer] for layer in tp]
+    _, lp1_ref = fo.flow_inverse(spec, p64, g["x"].astype(np.float64), g["ctx"].astype(np.float64))
+    check(lp1, lp1_ref, "lp after in-place update")
+
+
+def test_twin_bounded_sampler_matches_reference_outputs():
+    """Sampler WITH bounds against outputs of the reference's own code (tools/make_reference_goldens.py::bounded_sampler_fixture):
+    samples and the second output including the inverse-bounding log-Jacobian (bflow_jax_maf.py:220-222)."""
+    from naz_b200.flows.bflow_maf import (make_conditional_autoregressive_nn, make_masked_affine_autoregressive_transform,
+                                          make_normalizing_flow)
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_twin_maf_bounded_sampler_3d.npz"))
+    D, C, L = int(g["D"]), int(g["C"]), int(g["L"])
+    hidden = [int(h) for h in g["hidden"]]
+    nn_fn, _, gen_mask = make_conditional_autoregressive_nn(D, C, hidden)
+    tr = make_masked_affine_autoregressive_transform(nn_fn, D)
+    tp = [[(T(g[f"W_{l}_{j}"]).cuda(), T(g[f"b_{l}_{j}"]).cuda()) for j in range(len(hidden) + 1)] for l in range(L)]
+    masks, mask_skips, perms = zip(*[gen_mask(torch.from_numpy(g["perms"][l])) for l in range(L)])
+    bounds = {"low": T(g["low"]).cuda(), "high": T(g["high"]).cuda()}
+    twin = make_normalizing_flow(tr, T(g["x"]).cuda(), list(masks), list(mask_skips), list(perms), bounds=bounds, context=T(g["ctx"]).cuda())
+    # the public sampler draws its own base noise: feed the fixture's noise through an engine packed the same way
+    from naz_b200.engine import FlowEngine, FlowShape
+    e = FlowEngine(FlowShape("maf", D, C, hidden, L), 1, device="cuda")
+    e.pack(tp, list(masks), torch.stack(list(perms)))
+    zin = T(g["zin"]).cuda()
+    y, ld = e.forward(zin.unsqueeze(0), T(g["ctx"]).cuda(), bounds, want_logdet=True)
+    check(y[0], g["ys"], "bounded samples vs reference")
+    lo, hi = bounds["low"], bounds["high"]
+    u = (y[0] - lo) / (hi - lo)
+    log_j = -(0.5 * zin * zin).sum(-1) - 0.5 * D * math.log(2 * math.pi) + ld[0] + (torch.log(u) + torch.log1p(-u)).sum(-1) + torch.log(hi - lo).sum()
+    check(log_j, g["log_j"], "bounded log_j vs reference", atol=1e-4)
+    # and the public sampler: shapes, bounds, and the same log_j expression on its own noise
+    ys, lj = twin["sampler"](tp, 3, 256)
+    assert ys.shape == (256, D) and lj.shape == (256,) and bool(((ys > lo) & (ys < hi)).all()) and bool(torch.isfinite(lj).all())
+
+
+def test_bayesian_flow_entry_points_and_calibrate():
+    """bayesian_normalizing_flow (bflow_jax_maf.py:227-268), BayesianNormalizingFlow (bflow.py) and calibrate (:406-465)
+    under their reference names, on the libnazb path."""
+    from naz_b200.flows import BayesianNormalizingFlow, NormalizingFlow
+    from naz_b200.flows.bflow_maf import (bayesian_normalizing_flow, calibrate, make_conditional_autoregressive_nn,
+                                          make_masked_affine_autoregressive_transform, make_normalizing_flow, torch_to_jax)
+    torch.manual_seed(1)
+    rng = np.random.default_rng(1)
+    D, C, hidden, L = 2, 2, [32, 32], 3
+    mle = NormalizingFlow("maf", None, D, C, hidden, L).cuda()
+    best_params, _, masks, mask_skips, perms = torch_to_jax(mle)
+    nn_fn, _, _ = make_conditional_autoregressive_nn(D, C, hidden)
+    tr = make_masked_affine_autoregressive_transform(nn_fn, D)
+    x = T((rng.normal(size=(200, D))).astype(np.float32)).cuda()
+    ctx = T(rng.uniform(size=(C,)).astype(np.float32)).cuda()
+    flow = make_normalizing_flow(tr, x, masks, mask_skips, perms, context=ctx)
+    model, guide, guided_model, unravel_fn, log_prob = bayesian_normalizing_flow(flow["lp"], best_params, scale_max=0.25, return_log_l=True)
+    spec = fo.FlowSpec("maf", D, C, hidden, L, mle.perms().numpy())
+    sites = model()
+    p1 = unravel_fn(sites["params"])
+    p64 = [[(W.cpu().numpy().astype(np.float64), b.cpu().numpy().astype(np.float64)) for (W, b) in layer] for layer in p1]
+    _, lp_ref = fo.flow_inverse(spec, p64, x.cpu().numpy().astype(np.float64), ctx.cpu().numpy().astype(np.float64))
+    assert abs(float(sites["log_l"]) - lp_ref.sum()) <= 2e-4 * abs(lp_ref.sum()) + 1e-2
+    # S draws in the posterior-file format go straight into the pack kernels
+    post = model.draw(6)
+    lps = flow["lp_standard"](best_params, post["standard_params"], 0.25)
+    lpb = flow["lp"](unravel_fn(model.params_of(post)))
+    assert lps.shape == (6, 200) and torch.allclose(lps, lpb, rtol=1e-5, atol=1e-5)
+    gs = guide.draw(4)
+    assert gs["standard_params"].shape == post["standard_params"][:4].shape and gs["log_q"].shape == (4,)
+    assert float(gs["standard_params"].abs().max()) <= 1.0
+    # BayesianNormalizingFlow: the three bounded priors stay inside mean +- scale |mean|, all four score through libnazb
+    for kind in ("Uniform", "TruncNorm", "Normal", "StandardNormal"):
+        bf = BayesianNormalizingFlow(mle, "maf", None, D, C, hidden, L, prior_dist=kind, scale_max=0.1).cuda()
+        draws, logp = bf.prior_draws(5)
+        assert logp.shape == (5,) and bool(torch.isfinite(logp).all())
+        W0 = mle.nets[0].layers[0].weight.detach()
+        if kind in ("Uniform", "TruncNorm"):
+            dev_rel = ((draws["flow_0_nn.layers.0.weight"] - W0).abs() / W0.abs().clamp_min(1e-30)).amax(dim=(1, 2))
+            assert bool((dev_rel <= draws["scale"] * (1 + 1e-4)).all())
+        lj = bf.log_joint_draws(x, draws, logp, condition=ctx)
+        assert lj.shape == (5,) and bool(torch.isfinite(lj).all())
+        one = bf.model(x, condition=ctx)
+        assert one.dim() == 0 and bool(torch.isfinite(one))
+    # calibrate: coverage of the true density by the draws' credible intervals, against the same computation in numpy
+    S, N = 40, 4000
+    ppds = rng.normal(size=(S, N, 2)).astype(np.float32) * (1 + 0.05 * rng.normal(size=(S, 1, 1))).astype(np.float32)
+    theta_true = rng.normal(size=(3000, 2))
+    cs = np.array([0.5, 0.9])
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+    cov = calibrate(ppds, theta_true, 25, cs, fthin=1, itype="eqt", twod=True, generator=g)
+    assert cov.shape == (2,) and np.all((cov >= 0) & (cov <= 1)) and cov[1] >= cov[0]
+    cov_h = calibrate(ppds, theta_true, 25, cs, fthin=2, itype="hpd", twod=True, generator=g)
+    assert cov_h.shape == (2,) and np.all((cov_h >= 0) & (cov_h <= 1))

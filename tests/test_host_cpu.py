@@ -249,3 +249,89 @@ def test_empty_batch_returns_empty_results_without_touching_the_library():
     assert all(float(t.abs().sum()) == 0.0 for layer in g["gW"] + g["gb"] for t in layer)
     assert g["gW"][1][2].shape == (4, 6, 8)
     eng._h = None   # nothing to destroy
+
+
+def test_twin_factories_unpack_like_the_reference_call_sites():
+    """calibrate.py:91-92 / hmc_maf_exact.py:105 / plot_svi.py:83 replayed verbatim: a 3-tuple and a (forward, inverse) pair."""
+    import torch
+    from naz_b200.flows.bflow_maf import (create_mask, make_conditional_autoregressive_nn,
+                                          make_masked_affine_autoregressive_transform, _perm_from_mask_skip)
+    theta_dim, lambda_dim, hidden_dims = 2, 2, [150, 150, 150]
+    nn, param_shape, mask_generator = make_conditional_autoregressive_nn(theta_dim, lambda_dim, hidden_dims)
+    transform = make_masked_affine_autoregressive_transform(nn, theta_dim)
+    assert len(transform) == 2 and callable(transform[0]) and callable(transform[1])
+    # param_shapes exactly as upstream builds them (bflow_jax_maf.py:130-133; bias "shapes" are bare ints there)
+    assert param_shape == [((150, 4), 150), ((150, 150), 150), ((150, 150), 150), ((4, 150), 4)]
+    # train_maf (:271) initialises from them: np.random.normal(size=shape[0]) / size=shape[1] must both be valid sizes
+    for ws, bs in param_shape:
+        assert np.random.normal(size=ws).shape == tuple(ws) and np.random.normal(size=bs).shape == (bs,)
+    masks, mask_skip, perm = mask_generator(torch.tensor([1, 0]))
+    assert [tuple(m.shape) for m in masks] == [(150, 4), (150, 150), (150, 150), (4, 150)] and tuple(mask_skip.shape) == (4, 4)
+    m2, ms2 = create_mask(2, 2, hidden_dims, torch.tensor([1, 0]), 2)
+    assert all(torch.equal(a, b) for a, b in zip(masks, m2)) and torch.equal(mask_skip, ms2)
+    for D, C in ((2, 2), (6, 4), (5, 0)):
+        for _ in range(3):
+            pm = torch.randperm(D)
+            _, ms, _ = make_conditional_autoregressive_nn(D, C, [32, 32])[2](pm)
+            assert torch.equal(_perm_from_mask_skip(ms, C), pm)
+    # the conditioner is fused into the transform kernels: calling it alone, or a transform on host tensors, fails loudly
+    with pytest.raises(RuntimeError):
+        nn(torch.zeros(3, 2), None, masks, mask_skip)
+    with pytest.raises(RuntimeError):
+        transform[0]((torch.zeros(3, 2), torch.zeros(3)), (None, masks, mask_skip))
+    with pytest.raises(NotImplementedError):
+        make_conditional_autoregressive_nn(2, 2, [8], skip_connections=True)
+
+
+def test_ravel_pytree_and_bayesian_sites_host_side():
+    import torch
+    from naz_b200.flows.bflow_maf import bayesian_normalizing_flow, draw_params, ravel_pytree
+    torch.manual_seed(0)
+    best = [[(torch.randn(5, 3), torch.randn(5)), (torch.randn(4, 5), torch.randn(4))] for _ in range(2)]
+    flat, unravel = ravel_pytree(best)
+    assert flat.shape == (2 * (15 + 5 + 20 + 4),)
+    back = unravel(flat)
+    assert all(torch.equal(a, c) and torch.equal(b, d) for la, lb in zip(best, back) for (a, b), (c, d) in zip(la, lb))
+    calls = []
+    model, guide, guided_model, unravel_fn, log_prob = bayesian_normalizing_flow(
+        lambda p: (calls.append(p), torch.arange(7.0))[1], best, scale_max=0.25, return_log_l=True)
+    sites = model()
+    assert float(sites["log_l"]) == 21.0 and sites["params"].shape == flat.shape
+    assert float(sites["scale"][0]) == 0.25 and float(sites["standard_params"].abs().max()) <= 1.0
+    assert float(model(prior=True)["log_l"]) == 0.0
+    # params = theta_MLE (1 + scale u), un-ravelled in pytree order == draw_params on the batched standard parameters
+    post = model.draw(3)
+    a = unravel_fn(model.params_of(post))
+    b = draw_params(best, post["standard_params"], 0.25)
+    assert all(torch.allclose(x1, x2) and torch.allclose(y1, y2) for la, lb in zip(a, b) for (x1, y1), (x2, y2) in zip(la, lb))
+    m2, *_ = bayesian_normalizing_flow(lambda p: torch.zeros(1), best, scale_max=0.5, fixed_scale=False, multi_scale=True)
+    s2 = m2.draw(4)
+    assert s2["scale"].shape == (4, flat.numel()) and float(s2["scale"].max()) <= 0.5
+
+
+def test_bayesian_normalizing_flow_class_priors_host_side():
+    """bflow.py:30-47,57-94: sigma = scale |theta_MLE|, the bounded priors stay inside mean +- sigma, sites are named
+    flow_{i}_{name}, the sampled weights are copied into the module."""
+    import torch
+    from naz_b200.flows import BayesianNormalizingFlow, NormalizingFlow
+    torch.manual_seed(0)
+    mle = NormalizingFlow("maf", None, 2, 2, [16, 16], 2)
+    for kind in ("Uniform", "TruncNorm", "Normal", "StandardNormal"):
+        bf = BayesianNormalizingFlow(mle, "maf", None, 2, 2, [16, 16], 2, prior_dist=kind, scale_max=0.1)
+        sites = bf.prior_model()
+        assert bf.n_params == sum(p.numel() for p in mle.parameters())
+        assert set(sites) == {"scale"} | {f"flow_{i}_{n}" for i, t in enumerate(bf.flow_dist.transforms) for n, _ in t.named_parameters()}
+        W_mle, W_new = mle.nets[0].layers[0].weight.data, bf.nets[0].layers[0].weight.data
+        assert torch.equal(W_new, sites["flow_0_nn.layers.0.weight"])
+        if kind in ("Uniform", "TruncNorm"):
+            assert bool(((W_new - W_mle).abs() <= sites["scale"] * W_mle.abs() * (1 + 1e-5)).all())
+        draws, logp = bf.prior_draws(4)
+        assert draws["flow_1_nn.layers.2.bias"].shape == (4, 4) and logp.shape == (4,) and bool(torch.isfinite(logp).all())
+    tr = bf.param_transforms()
+    fwd, inv = tr["flow_0_nn.layers.0.weight"]
+    a, b = bf.param_bounds["flow_0_nn.layers.0.weight"]
+    u = torch.randn_like(a)
+    x = fwd(u)
+    assert bool(((x >= torch.minimum(a, b)) & (x <= torch.maximum(a, b))).all()) and torch.allclose(inv(x), u, atol=1e-3)
+    with pytest.raises(ValueError):
+        BayesianNormalizingFlow(mle, "maf", None, 2, 2, [16, 16], 2, prior_dist="Cauchy")

@@ -20,6 +20,7 @@ def test_committed_reference_fixtures_are_reproducible(tmp_path):
     gen.stats_fixture(str(tmp_path))
     gen.truncnorm_fixture(str(tmp_path))
     gen.grad_fixture(str(tmp_path))     # torch-backed run of the same reference code + autograd
+    gen.bounded_sampler_fixture(str(tmp_path))
     names = [f for f in os.listdir(tmp_path) if f.endswith(".npz")]
     assert len(names) >= 9
     for f in names:

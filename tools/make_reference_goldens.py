@@ -197,6 +197,45 @@ def main(out_dir=None):
         print(name, "lp", lp.min(), lp.max(), "sampler" if "ys" in arrs else "", os.path.getsize(os.path.join(out_dir, name + ".npz")))
 
 
+def bounded_sampler_fixture(out_dir=None):
+    """The reference sampler WITH bounds (bflow_jax_maf.py:213-223: inverse_bounding_transform after the flow, its
+    log-Jacobian added to the second output).  Only the sampler is stored: upstream's bounded `lp` filters the points with
+    an integer 0/1 index (:198, `x[jnp.prod(...)]`), which gathers rows 0 / 1 instead of masking — not a behaviour to pin."""
+    ref = load_reference()
+    dt = np.float64 if F64 else np.float32
+    out_dir = out_dir or os.path.join(ROOT, "tests", "golden")
+    name, D, C, hidden, L, N = "ref_twin_maf_bounded_sampler_3d", 3, 2, [24, 24], 4, 64
+    rng = np.random.default_rng(sum(map(ord, name)))
+    perms = np.stack([rng.permutation(D) for _ in range(L)])
+    nn_fn, _, _ = ref.make_conditional_autoregressive_nn(D, C, hidden)
+    transform = ref.make_masked_affine_autoregressive_transform(nn_fn, D)
+    masks, mask_skips = [], []
+    for l in range(L):
+        m, ms = ref.create_mask(D, C, hidden, np.asarray(perms[l]).view(JArr), 2)
+        masks.append([np.asarray(a, dtype=dt).view(JArr) for a in m])
+        mask_skips.append(np.asarray(ms, dtype=dt).view(JArr))
+    dims = [D + C] + list(hidden) + [2 * D]
+    params = [[((rng.normal(size=(dims[j + 1], dims[j])) / np.sqrt(dims[j])).astype(np.float32).astype(dt).view(JArr),
+                (rng.normal(size=(dims[j + 1],)) * 0.1).astype(np.float32).astype(dt).view(JArr)) for j in range(len(dims) - 1)] for _ in range(L)]
+    low, high = np.array([-1.0, 0.0, 2.0], dtype=np.float32), np.array([3.0, 1.0, 7.0], dtype=np.float32)
+    x = (low + (high - low) * rng.uniform(0.05, 0.95, size=(N, D))).astype(np.float32)
+    ctx = rng.uniform(size=(C,)).astype(np.float32)
+    flow = ref.make_normalizing_flow(transform, x.astype(dt).view(JArr), masks, mask_skips, [np.asarray(p).view(JArr) for p in perms],
+                                     bounds={"low": low.astype(dt).view(JArr), "high": high.astype(dt).view(JArr)}, context=ctx.astype(dt).view(JArr))
+    zin = rng.normal(size=(N, D)).astype(np.float32)
+    y, log_j = flow["sampler"](params, zin.astype(dt), N)
+    arrs = dict(kind="maf", D=D, C=C, hidden=np.array(hidden), L=L, perms=perms, x=x, ctx=ctx, low=low, high=high, zin=zin,
+                ys=np.asarray(y, np.float64), log_j=np.asarray(log_j, np.float64), dtype=str(np.dtype(dt)))
+    for l in range(L):
+        for j, m in enumerate(masks[l]):
+            arrs[f"mask_{l}_{j}"] = np.asarray(m, np.float32)
+        for j, (W, b) in enumerate(params[l]):
+            arrs[f"W_{l}_{j}"] = np.asarray(W, np.float32)
+            arrs[f"b_{l}_{j}"] = np.asarray(b, np.float32)
+    np.savez_compressed(os.path.join(out_dir, name + ".npz"), **arrs)
+    print(name, "ys in bounds:", bool(((np.asarray(y) > low) & (np.asarray(y) < high)).all()), os.path.getsize(os.path.join(out_dir, name + ".npz")))
+
+
 def stats_fixture(out_dir=None):
     """hpd_vectorized of the REAL reference module (src/naz/statutils.py is plain numpy + pandas, importable as is)."""
     out_dir = out_dir or os.path.join(ROOT, "tests", "golden")
@@ -378,3 +417,4 @@ if __name__ == "__main__":
     stats_fixture()
     truncnorm_fixture()
     grad_fixture()
+    bounded_sampler_fixture()
