@@ -136,8 +136,11 @@ __global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_affine_
   float* msk = es + D * P;                             // [D][P]  clip indicator, by rank
   float* ldacc = msk + D * P;                          // [P]
   float* ljac = ldacc + P;                             // [P]
-  float* zb = ljac + P;                                // [hmax]  zero bias of the transposed products
-  float* wbuf = zb + g.hmax;                           // [NST][WCHUNK]
+  // zero bias of the transposed products: they read bias[n] for n < max(hidden widths, kin) (the back-propagation to the
+  // conditioner input has kin = C + D output columns, which a wide context can make larger than every hidden layer)
+  const int zb_n = (g.hmax > kin_pad) ? g.hmax : kin_pad;
+  float* zb = ljac + P;                                // [zb_n]
+  float* wbuf = zb + zb_n;                             // [NST][WCHUNK]
   float* red = wbuf + NST * T::WCHUNK;
 
   const int tid = threadIdx.x;
@@ -150,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_affine_
     const float* wdrawT = packedT + (size_t)sg * gg.draw_strideT;
     // ---- load tile ----
     for (int i = tid; i < kin_pad * P; i += kThreads) xin[i] = 0.f;
-    for (int i = tid; i < g.hmax; i += kThreads) zb[i] = 0.f;
+    for (int i = tid; i < zb_n; i += kThreads) zb[i] = 0.f;
     if (tid < P) { ldacc[tid] = 0.f; ljac[tid] = 0.f; }
     __syncthreads();
     for (int i = tid; i < npts * C; i += kThreads) {
@@ -358,7 +361,7 @@ __global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_affine_
 size_t grad_smem_bytes(const FlowGeom& g, int P, int nst, int tn) {
   const int kin_pad = (g.kin + 3) & ~3, md_pad = (g.md + 3) & ~3;
   size_t f = (size_t)2 * kin_pad * P + (size_t)4 * g.D * P + (size_t)(g.n_hidden + 2) * g.hmax * P +
-             (size_t)2 * md_pad * P + (size_t)g.L * g.D * P + 2 * P + g.hmax;
+             (size_t)2 * md_pad * P + (size_t)g.L * g.D * P + 2 * P + (size_t)((g.hmax > kin_pad) ? g.hmax : kin_pad);
   int TR = P / 4, TC = kThreads / TR, NPASS = TC * tn;
   f += (size_t)nst * kKC * NPASS;
   f += 2 * (kThreads / 32) + 4;

@@ -313,6 +313,8 @@ class FlowEngine:
                 lo = lo.expand(sh.D).contiguous()
             if hi.numel() == 1:
                 hi = hi.expand(sh.D).contiguous()
+            if lo.numel() != sh.D or hi.numel() != sh.D:      # the kernels read lo[d], hi[d] for every d < D
+                raise ValueError(f"bounds must be scalars or have D = {sh.D} entries (got {lo.numel()} / {hi.numel()})")
         return x, c, rows, lo, hi
 
     def inverse(self, x, ctx=None, bounds=None, *, want_z=False, want_lp=True, want_lse=False, want_sum=False,
@@ -349,7 +351,9 @@ class FlowEngine:
             lmax = torch.empty((G, N), device=self.device, dtype=torch.float32)
             lsum = torch.empty((G, N), device=self.device, dtype=torch.float32)
         sum_n = torch.zeros((s_count,), device=self.device, dtype=torch.float64) if want_sum else None
-        lw = None if log_w is None else _f32c(torch.as_tensor(log_w), self.device)
+        lw = None if log_w is None else _f32c(torch.as_tensor(log_w), self.device).reshape(-1)
+        if lw is not None and lw.numel() != s_count:          # local to [s_begin, s_begin + s_count): the kernel reads log_w[si]
+            raise ValueError(f"log_w must have s_count = {s_count} entries (got {lw.numel()})")
         rc = self._lib.nazb_inverse(self._h, s_begin, s_count, x.data_ptr(), _ptr(c), rows, N, _ptr(lo), _ptr(hi),
                                     _ptr(z), _ptr(lp), _ptr(lw), _ptr(lmax), _ptr(lsum), G, _ptr(sum_n), self._stream())
         self._check(rc, "nazb_inverse")

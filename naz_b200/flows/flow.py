@@ -119,6 +119,13 @@ class NormalizingFlow(nn.Module):
 
     # ------------------------------------------------------------------ reference API (flow.py:45-129)
     def log_prob(self, x, *args, condition=None, **kwargs):
+        """flow.py:66-79.  Evaluated by libnazb on the module's CURRENT weights; the result is a plain tensor (no autograd
+        graph — gradients come from FlowEngine.inverse_grad / the twin's value_and_grad).  A dropout flow in train() mode
+        would apply a fresh nn.Dropout mask upstream: that stochastic path is `MCDPNormalizingFlow.sample_uncertain` /
+        `log_prob_draws(keep=...)` here, so calling log_prob in that state raises instead of silently ignoring dropout."""
+        if self.training and self.dropout_p not in (None, 0.0):
+            raise RuntimeError("log_prob on a dropout flow in train() mode: call flow.eval() for the deterministic density, or "
+                               "log_prob_draws(..., keep=masks, p_drop=p) for explicit MC-dropout masks")
         eng = self._single_engine()
         out = eng.inverse(x, self._cond(condition), self.bounds, want_lp=True)
         return out["lp"][0]

@@ -102,6 +102,7 @@ GRAD_CASES = [
     (3, 2, [24, 24], 4, 3, 100, True, "N"),
     (6, 4, [150, 150, 150], 2, 2, 70, False, "N"),
     (4, 2, [150, 150, 150], 3, 1, 33, False, 1),
+    (3, 14, [12, 12], 2, 2, 50, False, "N"),      # C + D = 17 > every hidden width: the zero-bias buffer of the transposed products
 ]
 
 
