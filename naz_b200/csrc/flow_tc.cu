@@ -111,11 +111,13 @@ struct TcPlan {
   int t_a = 0;                    // v5: TMEM column of the A operand (hi image; lo at + kr_max / 2), valid when a_tmem
   bool a_tmem = false;
   int t_a_fold = 0;               // ... of the folded program (its accumulators drop the degree-0 columns)
+  bool split = false, split_fold = false;   // the program has pushes whose critical columns are issued first
   // Block-aligned column layout of the inverse programs (v5 / v6; 0 = units packed contiguously in degree order): the hidden
   // units of MADE degree r of every hidden layer occupy columns [r bw, r bw + n_r), the rest of the block is zero padding
   // (zero image rows / columns, zero biases), so an A block is exactly bw / 16 K slices and the epilogue of a block touches
   // aw = ceil8(max n_r) columns instead of the 8-aligned hull of an unaligned range (cfg3: 40 instead of 56-64).
   int bw = 0, aw = 0;
+  bool trim = true;               // folded programs: accumulators start at the first live block (set from opt_trim before building)
   int hpad[NAZB_MAX_HIDDEN_LAYERS] = {0};   // column count of each hidden layer in the inverse programs (ceil16(H) or D bw)
 };
 
@@ -139,9 +141,12 @@ struct TcState {
   int opt_fold = 1;                  // context fold when ctx_rows == 1
   int opt_merge_n = -1;              // pushes with N <= merge_n are issued unsplit (critical + deferred columns in one MMA);
                                      // -1 = kernel default (v4: 0 = always split, v5: 256 = never split)
-  int opt_gate = 1;                  // draw-group gate for large N
+  int opt_gate = 1;                  // draw-group gate for large N: 0 = off, 1 = a CTA may run one group ahead of the slowest (distance 2),
+                                     // 2 = no CTA starts a group before all have finished issuing the previous one (distance 1)
   int opt_a_tmem = 1;                // v5: A operand in tensor memory when the plan allows it
-  int opt_align = 0;                 // v5 / v6: block-aligned column layout when it fits tensor memory (measured: no gain)
+  int opt_trim = 1;                  // folded v5 / v6 programs drop the dead degree-0 accumulator columns
+  int opt_align = -1;                // v5 / v6: block-aligned column layout when it fits tensor memory: 1 = on, 0 = off, -1 = auto (on for
+                                     // flow layers with >= 4 hidden blocks: cfg2 +13 %; no effect on cfg3 / cfg4 whose blocks are wide)
 };
 
 constexpr int kMaxSteps = 80;
@@ -409,7 +414,7 @@ bool build_inverse(const FlowGeom& g, TcPlan& P, int variant, int merge_n, std::
   // of unit 0 / rank 0, only sums with live offsets are ever used.
   int col = 0;
   int T_PRE[NAZB_MAX_HIDDEN_LAYERS] = {0};
-  const bool trim = folded && v5;
+  const bool trim = folded && v5 && P.trim;
   for (int j = 1; j < nh; ++j) {
     const int dead = trim ? (g.blk[j][1] & ~15) : 0;
     T_PRE[j] = col - dead; col += hp(j) - dead;
@@ -530,7 +535,8 @@ bool build_inverse(const FlowGeom& g, TcPlan& P, int variant, int merge_n, std::
     P.t_a = ceil_to(t_end, 16);
     bool unsplit = true;
     for (const Step& st : steps_out) if (st.w_bytes && st.n_crit != st.n) unsplit = false;
-    (void)unsplit; (void)v6;   // split pushes keep the A operand in tensor memory too (a_free barrier in the kernels)
+    (void)v6;   // split pushes keep the A operand in tensor memory too (a_free barrier in the kernels)
+    P.split = !unsplit;
     P.a_tmem = (P.t_a + P.kr_max <= kTmemCols);
   }
   return (int)steps_out.size() <= kMaxSteps;
@@ -1316,9 +1322,10 @@ int nazb_tc_set_option(nazb_handle* h, const char* name, int value) {
   if (!strcmp(name, "inv_kernel")) { if (value < 3 || value > 6) return NAZB_ERR_BAD_ARG; t->opt_inv_kernel = value; h->is_packed = false; return NAZB_OK; }
   if (!strcmp(name, "inv_fold")) { t->opt_fold = value ? 1 : 0; return NAZB_OK; }
   if (!strcmp(name, "inv_merge_n")) { if (value < -1 || value > 256) return NAZB_ERR_BAD_ARG; t->opt_merge_n = value; h->is_packed = false; return NAZB_OK; }
-  if (!strcmp(name, "inv_gate")) { t->opt_gate = value ? 1 : 0; return NAZB_OK; }
+  if (!strcmp(name, "inv_gate")) { if (value < 0 || value > 2) return NAZB_ERR_BAD_ARG; t->opt_gate = value; return NAZB_OK; }
   if (!strcmp(name, "inv_a_tmem")) { t->opt_a_tmem = value ? 1 : 0; return NAZB_OK; }
-  if (!strcmp(name, "inv_align")) { t->opt_align = value ? 1 : 0; h->is_packed = false; return NAZB_OK; }
+  if (!strcmp(name, "inv_trim")) { t->opt_trim = value ? 1 : 0; h->is_packed = false; return NAZB_OK; }
+  if (!strcmp(name, "inv_align")) { if (value < -1 || value > 1) return NAZB_ERR_BAD_ARG; t->opt_align = value; h->is_packed = false; return NAZB_OK; }
   return NAZB_ERR_BAD_ARG;
 }
 int nazb_tc_get_option(const nazb_handle* h, const char* name, int* value) {
@@ -1329,6 +1336,7 @@ int nazb_tc_get_option(const nazb_handle* h, const char* name, int* value) {
   else if (!strcmp(name, "inv_merge_n")) *value = t->opt_merge_n;
   else if (!strcmp(name, "inv_gate")) *value = t->opt_gate;
   else if (!strcmp(name, "inv_a_tmem")) *value = t->opt_a_tmem;
+  else if (!strcmp(name, "inv_trim")) *value = t->opt_trim;
   else if (!strcmp(name, "inv_align")) *value = t->opt_align;
   else if (!strcmp(name, "inv_block_width")) *value = t->plan.ok[0] ? t->plan.bw : 0;
   else if (!strcmp(name, "inv_kernel_in_use")) *value = t->plan.ok[0] ? t->plan.inv_ver : 0;
@@ -1385,13 +1393,20 @@ cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* con
   if (!P.fwd3) { P.steps[1].clear(); P.images[1].clear(); }
   P.ok[1] = P.fwd3 || build_forward(g, P);
   P.inv_ver = t->opt_inv_kernel;
+  P.trim = t->opt_trim != 0;
   // geometry the inverse programs are built on: the real one (units contiguous in degree order) or the block-aligned one
   FlowGeom gi = g;
   std::vector<short> pmap;
+  int n_live_blocks = 0;
+  for (int r = 0; r < g.D; ++r) n_live_blocks += (g.blk[0][r + 1] > g.blk[0][r]) ? 1 : 0;
+  if (g.C > 0 && n_live_blocks > 0) --n_live_blocks;   // the degree-0 block is folded away for a broadcast context
   auto plan_inverse = [&](const FlowGeom& gg) -> bool {
     P.steps[0].clear(); P.images[0].clear(); P.fold_images.clear(); P.steps_fold.clear(); P.kr_max = 0; P.fold_ok = false;
     const int vgen = (P.inv_ver == 6) ? 5 : (P.inv_ver == 5) ? 3 : 1;
-    const int merge_n = t->opt_merge_n >= 0 ? t->opt_merge_n : (P.inv_ver == 5 ? 256 : 0);
+    // v5 default: split pushes (critical columns first) when the flow layer has >= 4 stages with hidden blocks — there the
+    // trailing columns are most of a push (cfg2 6|4: +20 %, cfg5 8|4: +7 %); with 2-3 wide blocks (cfg3, cfg4) the a_free
+    // hand-shake costs more than the shorter critical MMAs save (81.4 -> 77.8 M evals/s on cfg3), so those stay unsplit
+    const int merge_n = t->opt_merge_n >= 0 ? t->opt_merge_n : (P.inv_ver == 5 ? (n_live_blocks >= 4 ? 0 : 256) : 0);
     if (!(build_inverse(gg, P, vgen, merge_n, P.steps[0], P.images[0], &P.fold_images) && plan_smem_inv4(gg, P))) return false;
     std::vector<Image> scratch_images;
     TcPlan Q = P;   // the folded variant must not disturb kr_max / layer_bytes of the general plan
@@ -1400,10 +1415,12 @@ cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* con
     if (!P.fold_ok) P.steps_fold.clear();
     P.fold_a_tmem = P.fold_ok && Q.a_tmem;
     P.t_a_fold = Q.t_a;
+    P.split_fold = Q.split;
     return true;
   };
   if (P.inv_ver >= 4) {
-    if (P.inv_ver >= 5 && t->opt_align && g.inv_mode == NAZB_INV_INCREMENTAL) {
+    const bool want_align = t->opt_align > 0 || (t->opt_align < 0 && n_live_blocks >= 4);   // auto: measured gain only for many narrow blocks
+    if (P.inv_ver >= 5 && want_align && g.inv_mode == NAZB_INV_INCREMENTAL) {
       int maxblk = 0, minblk = 1 << 20;
       for (int j = 0; j < g.n_hidden; ++j)
         for (int r = 0; r < g.D; ++r) {
@@ -1556,6 +1573,7 @@ static cudaError_t launch_inv4(const nazb_handle* h, const TcState* t, const IoA
     if ((e = cudaMemsetAsync(t->grp_done, 0, sizeof(int) * (size_t)n_groups, st)) != cudaSuccess) return e;
     kp.grp_done = t->grp_done;
   }
+  kp.gate_dist = (t->opt_gate == 2) ? 1 : 2;
   if (fold) {
     FoldParams fp{};
     fp.n_img = (int)P.fold_images.size();
@@ -1599,7 +1617,13 @@ static cudaError_t launch_inv4(const nazb_handle* h, const TcState* t, const IoA
     threads = kV5Threads;
     const bool atm = t->opt_a_tmem && (fold ? P.fold_a_tmem : P.a_tmem);
     kp.t_a = (uint32_t)(fold ? P.t_a_fold : P.t_a);
-    if (atm) {
+    const bool afree = atm && (fold ? P.split_fold : P.split);
+    kp.a_free = afree ? 1 : 0;
+    if (atm && afree) {
+      kern = flow_tc_inv5_kernel<false, 2, true, true>;
+      if (mode == 0) kern = flow_tc_inv5_kernel<false, 0, true, true>;
+      else if (mode == 1) kern = flow_tc_inv5_kernel<false, 1, true, true>;
+    } else if (atm) {
       kern = flow_tc_inv5_kernel<false, 2, true>;
       if (mode == 0) kern = flow_tc_inv5_kernel<false, 0, true>;
       else if (mode == 1) kern = g_tc_dbg ? flow_tc_inv5_kernel<true, 1, true> : flow_tc_inv5_kernel<false, 1, true>;

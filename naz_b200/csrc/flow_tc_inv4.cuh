@@ -42,9 +42,12 @@ struct KParamsInv4 {
   int D, C, L, M, Mp, K, kind, nslots, kr_max;
   int folded;                      // context folded into the layer constants: stage 0 is constant, ctx adds nothing
   uint32_t t_a;                    // v5, A operand in tensor memory: first TMEM column of the hi image (lo at + kr_max / 2)
+  int a_free;                      // v5: the program has split pushes and A lives in TMEM: writers of an A block wait for the
+                                   // a_free barrier (measured: the extra commit + wait cost 7 % when no push is split, so it is off then)
   float bound, clip_lo, clip_hi;
   uint32_t off_xin, off_lc, off_h, off_y, off_xo, off_xr, off_misc, off_scratch, off_ring;
   int* grp_done;                   // [n_groups] producers that finished issuing a draw group (gate), or null
+  int gate_dist;                   // a producer starts group g once every CTA has finished issuing group g - gate_dist (1 or 2)
   unsigned int* wd;                // watchdog word (mapped host memory) or null
   long long* dbg;
 };
@@ -162,14 +165,14 @@ __global__ void __launch_bounds__(kV4Threads, 1) flow_tc_inv4_kernel(const __gri
       for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int grp = (int)(item / n_tiles);
         if (p.grp_done != nullptr && grp != prev_grp) {
-          // draw-group gate: finish group prev_grp, start group grp only once every CTA is done issuing grp - 2
+          // draw-group gate: finish group prev_grp, start group grp only once every CTA is done issuing grp - gate_dist
           if (prev_grp >= 0) {
             __threadfence();
             atomicAdd(p.grp_done + prev_grp, 1);
           }
-          if (grp >= 2) {
+          if (grp >= p.gate_dist) {
             const long long t0 = clk();
-            const int* flag = p.grp_done + (grp - 2);
+            const int* flag = p.grp_done + (grp - p.gate_dist);
             while (*reinterpret_cast<const volatile int*>(flag) < (int)gridDim.x) {
               __nanosleep(200);
               if (clk() - t0 > (1ll << 26)) break;   // the gate is an optimisation only: never wait more than ~30 ms

@@ -38,7 +38,9 @@ constexpr int kDbgEvents = 4096;
 // instead of shared memory: measured (tools/tc_probe_rate3.cu) an M = 128 MMA costs max(N/2, 32 + N/4) cycles with A in shared
 // memory (operand fetch at 128 B/clk) and the N/2 pipe floor with A in TMEM; in the kernel the shared-memory A path ran at
 // ~130 cycles per MMA because the epilogue warps' own traffic shares that port.
-template <bool kDbg, int kMode, bool kATmem>
+// kAFree: the program has split pushes while A lives in TMEM: writers of an A block wait for the a_free barrier.  A template
+// parameter, not a runtime flag: the mere presence of the hand-shake code cost 4 % on programs that never use it (81.4 -> 77.8).
+template <bool kDbg, int kMode, bool kATmem, bool kAFree = false>
 __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __grid_constant__ KParamsInv4 p,
                                                                       const __grid_constant__ IoArgs io, int n_groups) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -102,14 +104,14 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
       for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int grp = (int)(item / n_tiles);
         if (p.grp_done != nullptr && grp != prev_grp) {
-          // draw-group gate: finish group prev_grp, start group grp only once every CTA is done issuing grp - 2
+          // draw-group gate: finish group prev_grp, start group grp only once every CTA is done issuing grp - gate_dist
           if (prev_grp >= 0) {
             __threadfence();
             atomicAdd(p.grp_done + prev_grp, 1);
           }
-          if (grp >= 2) {
+          if (grp >= p.gate_dist) {
             const long long t0 = clk();
-            const int* flag = p.grp_done + (grp - 2);
+            const int* flag = p.grp_done + (grp - p.gate_dist);
             while (*reinterpret_cast<const volatile int*>(flag) < (int)gridDim.x) {
               __nanosleep(200);
               if (clk() - t0 > (1ll << 26)) break;   // the gate is an optimisation only: never wait more than ~30 ms
@@ -247,7 +249,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
                 // A in TMEM is single-buffered: the writers of the next block wait for this before their first store
                 // (with unsplit pushes it has completed before they pass the accumulator barrier; with split ones the
                 // trailing MMAs are still reading the block at that point)
-                if (kATmem && s_last && lastk) tcx::mma_commit(a_free);
+                if (kATmem && kAFree && s_last && lastk) tcx::mma_commit(a_free);
               }
               __syncwarp();
               LOG5(2, 48 + k)
@@ -282,11 +284,12 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
     uint8_t* a_chain = smem + p.off_h;
     uint64_t* my_acc = bar_acc;
     uint64_t* my_ready = a_ready;
-    uint32_t par_acc = 0, lcnt = 0, buf = 0, par_free = 1;   // first A block: wait(parity 1) on the fresh barrier returns at once
+    uint32_t par_acc = 0, lcnt = 0, buf = 0;
+    [[maybe_unused]] uint32_t par_free = 1;   // first A block: wait(parity 1) on the fresh barrier returns at once
     int dbg_n = 0;
     const int dbg_slot = sll;
     auto await_a_free = [&](bool has_slices) {   // once per A block and warp, right before the first store
-      if (kATmem) {
+      if (kATmem && kAFree) {
         if (has_slices) { mbar_wait4(a_free, par_free, p.wd, WD_TAG(7)); tcx::tc_fence_after(); }
         par_free ^= 1;
       }
@@ -398,7 +401,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
               const int nch = s_encols >> 3, nsl = (nch + 1) >> 1;
               const int nmine = (nsl - sll + 1) / 2;   // slices sll, sll + 2, ...
               observe(nsl);
-              if (nmine == 0) await_a_free(false);
+              if (kAFree && nmine == 0) await_a_free(false);
               for (int j0 = 0; j0 < nmine; j0 += 2) {
                 uint32_t r[16];
                 const int nj = min(2, nmine - j0);
@@ -429,7 +432,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
                     uint4 hi4, lo4;
                     tcx::tanh8_scaled(s2, hi4, lo4);
                     if (c >= nch) { hi4 = make_uint4(0, 0, 0, 0); lo4 = hi4; }   // K padding chunk
-                    if (j0 == 0 && u == 0) await_a_free(true);
+                    if (kAFree && j0 == 0 && u == 0) await_a_free(true);
                     store_chunk(c, hi4, lo4);
                     publish(sl);
                     LOG5(dbg_slot, 8 + sl)
@@ -447,7 +450,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
               const int u0 = s_eaux;
               const int nmine = (nsl - sll + 1) / 2;
               observe(nsl);
-              await_a_free(nmine > 0);
+              if (kAFree) await_a_free(nmine > 0);
               // q-major weights: lc_w0x[q][n] (x of rank q -> unit n), lc_w0c[c][n] (context c -> unit n), everything scaled by
               // 2 log2 e; a thread's 8 units are two 16-byte loads per input and the update is 4 packed FFMA2
               const int hp0 = p.dp4;   // v5: KParamsInv4::dp4 carries the padded width of hidden layer 0 = row stride of both tables

@@ -91,14 +91,14 @@ __global__ void __launch_bounds__(kV6Threads, 1) flow_tc_inv6_kernel(const __gri
       for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int grp = (int)(item / n_tiles);
         if (p.grp_done != nullptr && grp != prev_grp) {
-          // draw-group gate: finish group prev_grp, start group grp only once every CTA is done issuing grp - 2
+          // draw-group gate: finish group prev_grp, start group grp only once every CTA is done issuing grp - gate_dist
           if (prev_grp >= 0) {
             __threadfence();
             atomicAdd(p.grp_done + prev_grp, 1);
           }
-          if (grp >= 2) {
+          if (grp >= p.gate_dist) {
             const long long t0 = clk();
-            const int* flag = p.grp_done + (grp - 2);
+            const int* flag = p.grp_done + (grp - p.gate_dist);
             while (*reinterpret_cast<const volatile int*>(flag) < (int)gridDim.x) {
               __nanosleep(200);
               if (clk() - t0 > (1ll << 26)) break;   // the gate is an optimisation only: never wait more than ~30 ms

@@ -139,8 +139,24 @@ class FlowEngine:
             detail = self._lib.nazb_last_cuda_error(self._h).decode() if self._h else ""
             raise _lib.NazbError(rc, where, detail)
 
+    _warned_shapes = set()
+
+    def _warn_simt_directions(self):
+        """`engine="auto"` serves a direction whose tensor-core program does not fit tensor memory with the fp32 CUDA-core
+        kernel (~10x slower on the bench shapes): say so once per shape instead of degrading silently."""
+        if self.engine_name != "tcgen05":
+            return
+        slow = [d for d in ("inverse", "forward") if self.engine_for(d) == "simt"]
+        key = (self.shape.kind, self.shape.D, self.shape.C, tuple(self.shape.hidden), self.shape.count_bins, tuple(slow))
+        if slow and key not in FlowEngine._warned_shapes:
+            FlowEngine._warned_shapes.add(key)
+            import warnings
+            warnings.warn(f"naz_b200: the {' and '.join(slow)} direction of this {self.shape.kind} flow (D={self.shape.D}, C={self.shape.C}, "
+                          f"hidden={list(self.shape.hidden)}) does not fit the tcgen05 programs (tensor-memory budget) and runs on the "
+                          "fp32 SIMT kernel; FlowEngine.engine_for(direction) reports the engine per direction", RuntimeWarning, stacklevel=3)
+
     # engine options (include/nazb.h: nazb_set_option); nothing in the library reads the environment
-    OPTION_NAMES = ("inv_kernel", "inv_merge_n", "inv_fold", "inv_gate", "inv_a_tmem", "inv_align")
+    OPTION_NAMES = ("inv_kernel", "inv_merge_n", "inv_fold", "inv_gate", "inv_a_tmem", "inv_align", "inv_trim")
 
     def set_option(self, name: str, value: int) -> None:
         self._check(self._lib.nazb_set_option(self._h, name.encode(), int(value)), f"nazb_set_option({name})")
@@ -289,6 +305,7 @@ class FlowEngine:
             self._check(rc, "nazb_pack")
         # the pack kernels read the source tensors asynchronously on the current stream
         self._keepalive = (Wt, bt, mt, keep_t, base_t)
+        self._warn_simt_directions()
         return self
 
     # ------------------------------------------------------------------

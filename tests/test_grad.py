@@ -172,8 +172,9 @@ def test_twin_value_and_grad_single_draw_against_reference_fixture():
     spec, params, g = load_ref_twin("ref_twin_maf_cond_3d")
     masks = [[torch.from_numpy(g[f"mask_{l}_{j}"]) for j in range(len(spec.hidden) + 1)] for l in range(spec.L)]
     tparams = [[(torch.from_numpy(W), torch.from_numpy(b)) for (W, b) in layer] for layer in params]
-    nn = bm.make_conditional_autoregressive_nn(spec.D, spec.C, spec.hidden)
-    flow = bm.make_normalizing_flow(nn, torch.from_numpy(g["x"]), masks, None, [torch.from_numpy(p) for p in spec.perms],
+    nn, _, _ = bm.make_conditional_autoregressive_nn(spec.D, spec.C, spec.hidden)
+    transform = bm.make_masked_affine_autoregressive_transform(nn, spec.D)
+    flow = bm.make_normalizing_flow(transform, torch.from_numpy(g["x"]), masks, None, [torch.from_numpy(p) for p in spec.perms],
                                     context=torch.from_numpy(g["ctx"]))
     val, grads = flow["value_and_grad"](tparams)
     torch.cuda.synchronize()
