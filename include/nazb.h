@@ -223,11 +223,17 @@ int nazb_histogramdd(const float* x, int32_t S, int64_t N, int32_t D, const doub
 int nazb_hpd(const float* v, int32_t S, int64_t M, double alpha, float* lo, float* hi, void* stream);
 
 /* Engine options (tuning and A/B switches; this library never reads the environment).  Names, tcgen05 engine:
- *   "inv_kernel"   4 (default) | 3 (round-1 kernel)          — needs a new nazb_pack
- *   "inv_merge_n"  pushes with N <= value are issued unsplit  — needs a new nazb_pack
+ *   "inv_kernel"   5 (default: one 128-row chain, 16 epilogue warps) | 6 (24 epilogue warps, split pushes) |
+ *                  4 (two 64-row chains) | 3 (round-1 kernel)                                   — needs a new nazb_pack
+ *   "inv_merge_n"  pushes with N <= value are issued unsplit; 0 = always critical columns first; -1 (default) = by shape
+ *                  (split for flow layers with >= 4 hidden blocks)                              — needs a new nazb_pack
+ *   "inv_align"    block-aligned accumulator / operand columns: 1 on, 0 off, -1 (default) by shape — needs a new nazb_pack
+ *   "inv_trim"     1 (default) context-folded programs drop the dead degree-0 accumulator columns — needs a new nazb_pack
+ *   "inv_a_tmem"   1 (default) A operand of the pushes in tensor memory when the plan has room for it
  *   "inv_fold"     1 (default) fold a broadcast context (ctx_rows == 1) into per-draw constants inside nazb_inverse
- *   "inv_gate"     1 (default) bound the drift of CTAs across draw groups (keeps the weight images L2-resident)
- * nazb_get_option also answers "inv_fold_available" and "watchdog" (non-zero after a kernel aborted on a barrier time-out:
+ *   "inv_gate"     bound the drift of CTAs across draw groups (keeps the weight images L2-resident): 0 off, 2 = no CTA starts
+ *                  a group before all finished issuing the previous one, 3 = one group of slack, 1 (default) = by tile count
+ * nazb_get_option also answers "inv_fold_available", "inv_kernel_in_use", "inv_a_tmem_in_use", "inv_block_width" and "watchdog" (non-zero after a kernel aborted on a barrier time-out:
  * site | warp << 8 | block << 16).  Unknown names return NAZB_ERR_BAD_ARG, the SIMT engine NAZB_ERR_UNSUPPORTED. */
 int nazb_set_option(nazb_handle* h, const char* name, int32_t value);
 int nazb_get_option(const nazb_handle* h, const char* name, int32_t* value);

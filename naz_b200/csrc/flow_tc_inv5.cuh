@@ -224,7 +224,19 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
                   }
                 }
                 if (s_last && lastk) tcx::mma_commit(bar_acc);
-                if (n_rest) {   // split pushes: the remaining columns, behind the critical ones
+                if (n_rest && kATmem && kAFree) {
+                  // split pushes, A in TMEM: the remaining columns of ALL K slices of this step go behind the critical MMAs of
+                  // its last pair (issued per pair they would sit in front of the next pair's critical MMAs in the in-order pipe)
+                  if (lastk) {
+                    for (int kk = 0; kk < ksteps; ++kk) {
+                      const uint32_t dk = (uint32_t)(kk - k);   // K slices relative to the running descriptors (modular arithmetic)
+                      const uint32_t a0 = (kk == 0) ? s_acc : 1u;
+                      tcx::mma_f16_ts(d_r, ta_h + 8u * dk, desc(db_h + b_step * dk + ro), idesc_r, a0);
+                      tcx::mma_f16_ts(d_r, ta_h + 8u * dk, desc(db_l + b_step * dk + ro), idesc_r, 1u);
+                      tcx::mma_f16_ts(d_r, ta_l + 8u * dk, desc(db_h + b_step * dk + ro), idesc_r, 1u);
+                    }
+                  }
+                } else if (n_rest) {   // split pushes: the remaining columns, behind the critical ones
                   if (kATmem) {
                     tcx::mma_f16_ts(d_r, ta_h, desc(db_h + ro), idesc_r, acc0);
                     tcx::mma_f16_ts(d_r, ta_h, desc(db_l + ro), idesc_r, 1u);

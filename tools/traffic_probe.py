@@ -1,5 +1,6 @@
 """Dev tool: one full-shape log_prob launch (cfg3 flow, broadcast context) for DRAM-traffic measurements under
-`ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`.  usage: traffic_probe.py S N draws_per_group gate"""
+`ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`.  usage: traffic_probe.py S N draws_per_group gate   (gate = the inv_gate option: 2 = distance 1, 3 = distance 2, 1 = auto;
+the r2 logs under gpurun_out/ were taken when 1 meant distance 2 and 2 meant distance 1)"""
 import sys
 sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
 import torch
