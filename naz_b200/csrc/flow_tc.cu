@@ -1406,8 +1406,8 @@ cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* con
     P.steps[0].clear(); P.images[0].clear(); P.fold_images.clear(); P.steps_fold.clear(); P.kr_max = 0; P.fold_ok = false;
     const int vgen = (P.inv_ver == 6) ? 5 : (P.inv_ver == 5) ? 3 : 1;
     // v5 default: split pushes (critical columns first) when the flow layer has >= 4 stages with hidden blocks — there the
-    // trailing columns are most of a push (cfg2 6|4: +20 %, cfg5 8|4: +7 %); with 2-3 wide blocks (cfg3, cfg4) the a_free
-    // hand-shake costs more than the shorter critical MMAs save (81.4 -> 77.8 M evals/s on cfg3), so those stay unsplit
+    // trailing columns are most of a push (cfg2 6|4, cfg5 8|4: +1-2 %); with 2-3 wide blocks (cfg3, cfg4) the a_free
+    // hand-shake costs more than the shorter critical MMAs save (81.4 -> 79.0 M evals/s on cfg3), so those stay unsplit
     const int merge_n = t->opt_merge_n >= 0 ? t->opt_merge_n : (P.inv_ver == 5 ? (n_live_blocks >= 4 ? 0 : 256) : 0);
     if (!(build_inverse(gg, P, vgen, merge_n, P.steps[0], P.images[0], &P.fold_images) && plan_smem_inv4(gg, P))) return false;
     std::vector<Image> scratch_images;
