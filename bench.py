@@ -430,25 +430,39 @@ def main_ours(args):
     # auxiliary: SURVEY §8 f1 — value + gradient of sum_n lp (the NUTS / SVI inner loop), config-4 architecture (maf 2|2),
     # 4 chains x 100 000 points; 1 grad-eval = one (chain, point) pair through the value and the full parameter gradient
     aux_grad = None
-    if world == 1:
+    if not args.no_aux:
+        # every rank holds the same 4 chains (same seeds) and the same 400 000 points; with N > 1 GPUs the POINTS are sharded
+        # (strong scaling of one gradient step) and one all-reduce of the flat gradient buffer + the values finishes the step
+        # (naz_b200.parallel.inverse_grad_point_sharded); the time is the max over ranks of the CUDA-event time of the whole
+        # step, all-reduce included
+        from naz_b200.parallel import inverse_grad_point_sharded
         torch.manual_seed(3)
+        ggen = torch.Generator(device=dev)
+        ggen.manual_seed(99)
         gflow = NormalizingFlow("maf", None, 2, 2, [150, 150, 150], 16, engine="simt").to(dev)
-        gdraws = [[(lin.weight.detach().unsqueeze(0) * (1 + 0.25 * (torch.rand((4,) + tuple(lin.weight.shape), device=dev, generator=gen) * 2 - 1)),
-                    lin.bias.detach().unsqueeze(0) * (1 + 0.25 * (torch.rand((4,) + tuple(lin.bias.shape), device=dev, generator=gen) * 2 - 1)))
+        gdraws = [[(lin.weight.detach().unsqueeze(0) * (1 + 0.25 * (torch.rand((4,) + tuple(lin.weight.shape), device=dev, generator=ggen) * 2 - 1)),
+                    lin.bias.detach().unsqueeze(0) * (1 + 0.25 * (torch.rand((4,) + tuple(lin.bias.shape), device=dev, generator=ggen) * 2 - 1)))
                    for lin in arn.layers] for arn in gflow.nets]
         geng = gflow.make_engine(gdraws, device=dev)
-        gx = torch.randn((100_000, 2), device=dev, generator=gen) * 1.5
-        gc = torch.rand((100_000, 2), device=dev, generator=gen)
-        geng.inverse_grad(gx, gc)
+        GN = 100_000 * world if world > 1 else 100_000      # per-GPU work fixed at 100 k points x 4 chains
+        gx = torch.randn((GN, 2), device=dev, generator=ggen) * 1.5
+        gc = torch.rand((GN, 2), device=dev, generator=ggen)
+        inverse_grad_point_sharded(geng, gx, gc)
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
-        gr = geng.inverse_grad(gx, gc)
+        gr = inverse_grad_point_sharded(geng, gx, gc)
         g1.record()
         torch.cuda.synchronize()
-        g_ms = g0.elapsed_time(g1)
-        aux_grad = {"value": 4 * 100_000 / (g_ms * 1e-3), "unit": "grad-evals/s", "chains": 4, "points": 100_000, "ms": g_ms,
+        g_t = torch.tensor([g0.elapsed_time(g1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(g_t, op=dist.ReduceOp.MAX)
+        g_ms = float(g_t.item())
+        aux_grad = {"value": 4 * GN / (g_ms * 1e-3), "unit": "grad-evals/s", "chains": 4, "points": GN, "ms": g_ms,
                     "flow": "maf 2|2 [150,150,150] x16", "engine": "simt (fp32 CUDA cores)",
+                    "parallelism": f"point-sharded x{world}, one all-reduce of the gradient buffer (weak scaling: 100 k points per GPU)",
                     "finite": bool(torch.isfinite(gr["sum_n"]).all().item()),
                     "note": "nazb_inverse_grad: value + d/d(all weights) of sum_n lp per chain (first cut of row f1; not part of `value`)"}
         del geng, gr, gdraws
