@@ -460,7 +460,16 @@ def main_ours(args):
         if world > 1:
             dist.all_reduce(g_t, op=dist.ReduceOp.MAX)
         g_ms = float(g_t.item())
+        # algorithmic work of one grad-eval: the value pass (F1, masks as dense zeros) + the two products of the backward pass
+        # per linear layer (cotangent . W and the outer product into dW) = 3 F1; roofline = fp32 FMA issue of the CUDA cores
+        # (nominal: SMs x 128 lanes x 2 flop x measured SM clock; MEASURED_PEAKS.json holds no fp32 figure)
+        g_f1 = 3 * flops_per_eval(2, 2, [150, 150, 150], 16, 2)
+        g_peak = world * torch.cuda.get_device_properties(dev).multi_processor_count * 128 * 2 * 1.965e9 / 1e12
+        g_ach = g_f1 * 4 * GN / (g_ms * 1e-3) / 1e12
         aux_grad = {"value": 4 * GN / (g_ms * 1e-3), "unit": "grad-evals/s", "chains": 4, "points": GN, "ms": g_ms,
+                    "flops_per_grad_eval": g_f1,
+                    "roofline": {"bound": "fp32 FMA (CUDA cores)", "achieved": g_ach, "peak": g_peak, "unit": "TFLOP/s", "frac": g_ach / g_peak,
+                                 "peak_source": "nominal: SMs x 128 FMA lanes x 2 x 1.965 GHz, all GPUs of the run"},
                     "flow": "maf 2|2 [150,150,150] x16", "engine": "simt (fp32 CUDA cores)",
                     "parallelism": f"point-sharded x{world}, one all-reduce of the gradient buffer (weak scaling: 100 k points per GPU)",
                     "finite": bool(torch.isfinite(gr["sum_n"]).all().item()),

@@ -112,6 +112,7 @@ struct TcPlan {
   bool a_tmem = false;
   int t_a_fold = 0;               // ... of the folded program (its accumulators drop the degree-0 columns)
   bool split = false, split_fold = false;   // the program has pushes whose critical columns are issued first
+  bool a_tmem2 = false, fold_a_tmem2 = false;   // room for a second A buffer in TMEM (deferred trailing MMAs, kSplit = 2)
   // Block-aligned column layout of the inverse programs (v5 / v6; 0 = units packed contiguously in degree order): the hidden
   // units of MADE degree r of every hidden layer occupy columns [r bw, r bw + n_r), the rest of the block is zero padding
   // (zero image rows / columns, zero biases), so an A block is exactly bw / 16 K slices and the epilogue of a block touches
@@ -146,6 +147,8 @@ struct TcState {
                                      // distance 1 when every CTA has >= 32 tiles per group (measured: free at 53 tiles, +2.3 % at 26; the wait at a group boundary is then < 3 % of the
                                      // group), else distance 2.  Full-size cfg3: 76 GB of DRAM reads per launch at distance 2, 5.4 GB at 1.
   int opt_a_tmem = 1;                // v5: A operand in tensor memory when the plan allows it
+  int opt_defer = 0;                 // v5 split pushes: hold the trailing MMAs back until the accumulator reads are done (needs room for a
+                                     // second A buffer in TMEM)
   int opt_trim = 1;                  // folded v5 / v6 programs drop the dead degree-0 accumulator columns
   int opt_align = -1;                // v5 / v6: block-aligned column layout when it fits tensor memory: 1 = on, 0 = off, -1 = auto (on for
                                      // flow layers with >= 4 hidden blocks: cfg2 +13 %; no effect on cfg3 / cfg4 whose blocks are wide)
@@ -539,6 +542,7 @@ bool build_inverse(const FlowGeom& g, TcPlan& P, int variant, int merge_n, std::
     for (const Step& st : steps_out) if (st.w_bytes && st.n_crit != st.n) unsplit = false;
     (void)v6;   // split pushes keep the A operand in tensor memory too (a_free barrier in the kernels)
     P.split = !unsplit;
+    P.a_tmem2 = (P.t_a + 2 * P.kr_max <= kTmemCols);
     P.a_tmem = (P.t_a + P.kr_max <= kTmemCols);
   }
   return (int)steps_out.size() <= kMaxSteps;
@@ -1327,6 +1331,7 @@ int nazb_tc_set_option(nazb_handle* h, const char* name, int value) {
   if (!strcmp(name, "inv_gate")) { if (value < 0 || value > 3) return NAZB_ERR_BAD_ARG; t->opt_gate = value; return NAZB_OK; }
   if (!strcmp(name, "inv_a_tmem")) { t->opt_a_tmem = value ? 1 : 0; return NAZB_OK; }
   if (!strcmp(name, "inv_trim")) { t->opt_trim = value ? 1 : 0; h->is_packed = false; return NAZB_OK; }
+  if (!strcmp(name, "inv_defer")) { t->opt_defer = value ? 1 : 0; return NAZB_OK; }
   if (!strcmp(name, "inv_align")) { if (value < -1 || value > 1) return NAZB_ERR_BAD_ARG; t->opt_align = value; h->is_packed = false; return NAZB_OK; }
   return NAZB_ERR_BAD_ARG;
 }
@@ -1339,6 +1344,7 @@ int nazb_tc_get_option(const nazb_handle* h, const char* name, int* value) {
   else if (!strcmp(name, "inv_gate")) *value = t->opt_gate;
   else if (!strcmp(name, "inv_a_tmem")) *value = t->opt_a_tmem;
   else if (!strcmp(name, "inv_trim")) *value = t->opt_trim;
+  else if (!strcmp(name, "inv_defer")) *value = t->opt_defer;
   else if (!strcmp(name, "inv_align")) *value = t->opt_align;
   else if (!strcmp(name, "inv_block_width")) *value = t->plan.ok[0] ? t->plan.bw : 0;
   else if (!strcmp(name, "inv_kernel_in_use")) *value = t->plan.ok[0] ? t->plan.inv_ver : 0;
@@ -1418,6 +1424,7 @@ cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* con
     P.fold_a_tmem = P.fold_ok && Q.a_tmem;
     P.t_a_fold = Q.t_a;
     P.split_fold = Q.split;
+    P.fold_a_tmem2 = P.fold_ok && Q.a_tmem2;
     return true;
   };
   if (P.inv_ver >= 4) {
@@ -1621,10 +1628,15 @@ static cudaError_t launch_inv4(const nazb_handle* h, const TcState* t, const IoA
     kp.t_a = (uint32_t)(fold ? P.t_a_fold : P.t_a);
     const bool afree = atm && (fold ? P.split_fold : P.split);
     kp.a_free = afree ? 1 : 0;
-    if (atm && afree) {
-      kern = flow_tc_inv5_kernel<false, 2, true, true>;
-      if (mode == 0) kern = flow_tc_inv5_kernel<false, 0, true, true>;
-      else if (mode == 1) kern = flow_tc_inv5_kernel<false, 1, true, true>;
+    const bool defer = afree && t->opt_defer && (fold ? P.fold_a_tmem2 : P.a_tmem2);
+    if (atm && defer) {
+      kern = flow_tc_inv5_kernel<false, 2, true, 2>;
+      if (mode == 0) kern = flow_tc_inv5_kernel<false, 0, true, 2>;
+      else if (mode == 1) kern = flow_tc_inv5_kernel<false, 1, true, 2>;
+    } else if (atm && afree) {
+      kern = flow_tc_inv5_kernel<false, 2, true, 1>;
+      if (mode == 0) kern = flow_tc_inv5_kernel<false, 0, true, 1>;
+      else if (mode == 1) kern = flow_tc_inv5_kernel<false, 1, true, 1>;
     } else if (atm) {
       kern = flow_tc_inv5_kernel<false, 2, true>;
       if (mode == 0) kern = flow_tc_inv5_kernel<false, 0, true>;

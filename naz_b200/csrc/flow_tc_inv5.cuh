@@ -38,11 +38,15 @@ constexpr int kDbgEvents = 4096;
 // instead of shared memory: measured (tools/tc_probe_rate3.cu) an M = 128 MMA costs max(N/2, 32 + N/4) cycles with A in shared
 // memory (operand fetch at 128 B/clk) and the N/2 pipe floor with A in TMEM; in the kernel the shared-memory A path ran at
 // ~130 cycles per MMA because the epilogue warps' own traffic shares that port.
-// kAFree: the program has split pushes while A lives in TMEM: writers of an A block wait for the a_free barrier.  A template
-// parameter, not a runtime flag: the mere presence of the hand-shake code cost 4 % on programs that never use it (81.4 -> 77.8).
-template <bool kDbg, int kMode, bool kATmem, bool kAFree = false>
+// kSplit (A in TMEM, programs with split pushes): 1 = single A buffer, writers of an A block wait for the a_free barrier that
+// the issuer commits behind the trailing MMAs; 2 = DOUBLE-buffered A (needs 2 kr_max free columns), the trailing MMAs are held
+// back until every epilogue warp has finished reading its accumulators (ld_done barrier in the a_free slot): the
+// accumulator reads of the critical path no longer share the TMEM ports with MMAs.  A template parameter, not a runtime
+// flag: the mere presence of the hand-shake code cost 4 % on programs that never use it (81.4 -> 77.8).
+template <bool kDbg, int kMode, bool kATmem, int kSplit = 0>
 __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __grid_constant__ KParamsInv4 p,
                                                                       const __grid_constant__ IoArgs io, int n_groups) {
+  constexpr bool kAFree = (kSplit == 1), kDefer = (kSplit == 2);
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* w_full = reinterpret_cast<uint64_t*>(smem);            // [nslots] TMA -> issuers
   uint64_t* w_empty = w_full + 8;                                   // [nslots] count = 1 (the issuer's commit)
@@ -79,7 +83,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
     // (after publishing its slice, or as an observer when its lane has no slice in the pair).  A warp that waits on the
     // accumulator barrier is therefore always needed for the next MMA group and can never be lapped by two accumulator phases.
     for (int i = 0; i < 2 * kV5MaxPairs; ++i) tcx::mbar_init(a_ready + i, kV5EpiWarps);
-    tcx::mbar_init(a_free, 1);
+    tcx::mbar_init(a_free, kDefer ? kV5EpiWarps : 1);   // kDefer: the same slot is the ld_done barrier (one arrival per epilogue warp)
     for (int i = 0; i < 8; ++i) xflag[i] = 0;
     tcx::mbar_fence_init();
   }
@@ -156,6 +160,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
     const uint32_t a_base = tcx::smem_u32(smem + p.off_h);
     constexpr uint32_t lbo_a = kTileM * 16;
     uint32_t slot = 0, use = 0, buf = 0, apar = 0;   // apar: one parity bit per (buffer, slice) barrier
+    [[maybe_unused]] uint32_t par_ld = 0;
     int dbg_n = 0;
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int grp = (int)(item / n_tiles);
@@ -186,7 +191,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
             const uint32_t ro = s_ncrit;                        // image row n_crit = byte offset n_crit * 16, >> 4
             // A in TMEM: ONE buffer (every MMA of a push has retired before the epilogue that writes the next block passes
             // the accumulator barrier: pushes are unsplit), K slice s at columns t_a + 8 s (hi) / t_a + kr_max / 2 + 8 s (lo)
-            uint32_t ta_h = p.t_a + slice0 * 8u, ta_l = ta_h + (uint32_t)p.kr_max / 2u;
+            uint32_t ta_h = p.t_a + (kDefer ? buf * (uint32_t)p.kr_max : 0u) + slice0 * 8u, ta_l = ta_h + (uint32_t)p.kr_max / 2u;
             const uint32_t pair0 = slice0 >> 1;                 // sub-steps of a K-split push start at an even slice
             uint64_t* rdy = a_ready + buf * kV5MaxPairs + pair0;
             uint32_t bit = 1u << (buf * kV5MaxPairs + pair0);
@@ -224,10 +229,11 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
                   }
                 }
                 if (s_last && lastk) tcx::mma_commit(bar_acc);
-                if (n_rest && kATmem && kAFree) {
+                if (n_rest && kATmem && (kAFree || kDefer)) {
                   // split pushes, A in TMEM: the remaining columns of ALL K slices of this step go behind the critical MMAs of
-                  // its last pair (issued per pair they would sit in front of the next pair's critical MMAs in the in-order pipe)
-                  if (lastk) {
+                  // its last pair (issued per pair they would sit in front of the next pair's critical MMAs in the in-order pipe);
+                  // kDefer holds those of a push's last sub-step back further (below, after the ld_done barrier)
+                  if (lastk && !(kDefer && s_last)) {
                     for (int kk = 0; kk < ksteps; ++kk) {
                       const uint32_t dk = (uint32_t)(kk - k);   // K slices relative to the running descriptors (modular arithmetic)
                       const uint32_t a0 = (kk == 0) ? s_acc : 1u;
@@ -257,13 +263,30 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
                     }
                   }
                 }
-                if (lastk) tcx::mma_commit(w_empty + slot);   // the slot is free once these MMAs retire
+                if (lastk && !(kDefer && s_last && n_rest)) tcx::mma_commit(w_empty + slot);   // the slot is free once these MMAs retire
                 // A in TMEM is single-buffered: the writers of the next block wait for this before their first store
                 // (with unsplit pushes it has completed before they pass the accumulator barrier; with split ones the
                 // trailing MMAs are still reading the block at that point)
                 if (kATmem && kAFree && s_last && lastk) tcx::mma_commit(a_free);
               }
               __syncwarp();
+              if (kDefer && kATmem && lastk && s_last && n_rest) {
+                // the epilogue warps have their accumulators in registers: now the trailing columns may use the TMEM ports
+                mbar_wait4(a_free, par_ld, p.wd, WD_TAG(8));
+                par_ld ^= 1;
+                tcx::tc_fence_after();
+                if (tcx::elect_one()) {
+                  for (int kk = 0; kk < ksteps; ++kk) {
+                    const uint32_t dk = (uint32_t)(kk - k);
+                    const uint32_t a0 = (kk == 0) ? s_acc : 1u;
+                    tcx::mma_f16_ts(d_r, ta_h + 8u * dk, desc(db_h + b_step * dk + ro), idesc_r, a0);
+                    tcx::mma_f16_ts(d_r, ta_h + 8u * dk, desc(db_l + b_step * dk + ro), idesc_r, 1u);
+                    tcx::mma_f16_ts(d_r, ta_l + 8u * dk, desc(db_h + b_step * dk + ro), idesc_r, 1u);
+                  }
+                  tcx::mma_commit(w_empty + slot);
+                }
+                __syncwarp();
+              }
               LOG5(2, 48 + k)
               da_h += 2 * a_step; da_l += 2 * a_step; db_h += 2 * b_step; db_l += 2 * b_step;
               ta_h += 16; ta_l += 16;
@@ -300,6 +323,10 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
     [[maybe_unused]] uint32_t par_free = 1;   // first A block: wait(parity 1) on the fresh barrier returns at once
     int dbg_n = 0;
     const int dbg_slot = sll;
+    auto ld_done_arrive = [&]() {   // kDefer: this warp holds every accumulator it needs of the current step in registers
+      __syncwarp();
+      if (lane == 0) tcx::mbar_arrive(a_free);
+    };
     auto await_a_free = [&](bool has_slices) {   // once per A block and warp, right before the first store
       if (kATmem && kAFree) {
         if (has_slices) { mbar_wait4(a_free, par_free, p.wd, WD_TAG(7)); tcx::tc_fence_after(); }
@@ -333,7 +360,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
       if (kATmem) {
         // chunk c = K elements [8c, 8c + 8) = TMEM columns [4c, 4c + 4) of the hi / lo image; the two half-warps of a row hold
         // chunks 2s and 2s + 1, i.e. the 8 columns of K slice s (the store is warp-collective: both halves always take part)
-        const uint32_t ta = lane_base + p.t_a + (uint32_t)(c >> 1) * 8u;
+        const uint32_t ta = lane_base + p.t_a + (kDefer ? buf * (uint32_t)p.kr_max : 0u) + (uint32_t)(c >> 1) * 8u;
         tcx::tmem_st16x2_4<4>(ta, hi4.x, hi4.y, hi4.z, hi4.w);
         tcx::tmem_st16x2_4<4>(ta + (uint32_t)p.kr_max / 2u, lo4.x, lo4.y, lo4.z, lo4.w);
       } else {
@@ -408,12 +435,15 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
               tcx::tc_fence_after();
               LOG5(dbg_slot, 2)
             }
+            // kDefer: the issuer holds the trailing MMAs of this (split) push back until all 16 warps have arrived here
+            const bool s_split = kDefer && kATmem && p.steps[st].w_bytes && (p.steps[st].n != p.steps[st].n_crit);
             if (s_epi == EPI_TANH) {
               // block of nch 8-column chunks = nsl K slices; slice s = chunks {2s (half-warp 0), 2s+1 (half-warp 1)}
               const int nch = s_encols >> 3, nsl = (nch + 1) >> 1;
               const int nmine = (nsl - sll + 1) / 2;   // slices sll, sll + 2, ...
               observe(nsl);
               if (kAFree && nmine == 0) await_a_free(false);
+              if (s_split && nmine == 0) ld_done_arrive();
               for (int j0 = 0; j0 < nmine; j0 += 2) {
                 uint32_t r[16];
                 const int nj = min(2, nmine - j0);
@@ -422,14 +452,16 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
                 // software-pipelined accumulator reads (TMEM -> registers runs at ~64 B/clk for the whole SM: 450 cycles for a
                 // 56-column block): the second slice of this warp is in flight while the first one goes through tanh
                 tcx::tmem_ld16x2_8<8>(ta, r);
+                if (kDefer && nj > 1) tcx::tmem_ld16x2_8<8>(ta + 32, r + 8);   // both slices at once: the ld_done arrival needs them
                 tcx::tmem_ld_wait();
-                if (nj > 1) tcx::tmem_ld16x2_8<8>(ta + 32, r + 8);
+                if (!kDefer && nj > 1) tcx::tmem_ld16x2_8<8>(ta + 32, r + 8);
                 tcx::tc_fence_before();
+                if (s_split && j0 + 2 >= nmine) ld_done_arrive();
                 LOG5(dbg_slot, 3)
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                   if (u < nj) {
-                    if (u == 1) { tcx::tmem_ld_wait(); tcx::tc_fence_before(); }
+                    if (!kDefer && u == 1) { tcx::tmem_ld_wait(); tcx::tc_fence_before(); }
                     const int sl = sl0 + u * 2;
                     const int c = sl * 2 + hw;
                     const int cl = min(c, nch - 1);
@@ -520,6 +552,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
               }
               if (rows_mine) publish_x(); else ++xcount;
             } else if (s_epi == EPI_XINV && !rows_mine) {
+              if (s_split) ld_done_arrive();
               ++xcount;
             } else if (s_epi == EPI_XINV) {
               const int r = s_stage, d = perm[r];
@@ -530,6 +563,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
               if (!spline) {
                 uint32_t rr[2] = {0u, 0u};
                 if (has_acc) { tcx::tmem_ld16x2_2<0>(lane_base + s_ecol, rr); tcx::tmem_ld_wait(); }
+                if (s_split) ld_done_arrive();
                 float mu = __uint_as_float(rr[0]) + bo[0];
                 float sc = fminf(fmaxf(__uint_as_float(rr[1]) + bo[1], p.clip_lo), p.clip_hi);
                 xv = (yv - mu) * expf(-sc);
@@ -544,6 +578,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
                   tcx::tmem_ld16x2_8<0>(lane_base + s_ecol + 16, rd);   // cols 16-23 (derivatives) to both
                   tcx::tmem_ld_wait();
                 }
+                if (s_split) ld_done_arrive();
                 const float4* bw = reinterpret_cast<const float4*>(bo + hw * 8);
                 const float4* bd = reinterpret_cast<const float4*>(bo + 16);
                 const float4 w0 = bw[0], w1 = bw[1], e0 = bd[0], e1 = bd[1];
@@ -568,6 +603,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
                       if (m0 + e < M) scr[(m0 + e) * kTileM] = __uint_as_float(rr[e]) + bo[m0 + e];
                   }
                 }
+                if (s_split) ld_done_arrive();
                 if (owner) {
                   if (p.kind == NAZB_KIND_RQS) nazb::rational_spline<false>(yv, p.K, p.bound, true, raw, setw, xv, ld);
                   else nazb::rational_spline<true>(yv, p.K, p.bound, true, raw, setw, xv, ld);

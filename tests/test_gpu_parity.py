@@ -290,6 +290,7 @@ INV_VARIANTS = [
     {"inv_kernel": 4},                        # two 64-row chains
     {"inv_kernel": 4, "inv_merge_n": 256},    # ... every push issued unsplit
     {"inv_merge_n": 0},                       # v5 with split pushes (critical columns first; A stays in tensor memory behind a_free)
+    {"inv_merge_n": 0, "inv_defer": 1},       # ... trailing MMAs held back until the accumulator reads are done, A double-buffered in TMEM
     {"inv_a_tmem": 0},                        # v5 with the A operand in shared memory
     {"inv_a_tmem": 0, "inv_merge_n": 0},      # ... and split pushes
     {"inv_fold": 0},                          # broadcast context evaluated per point (general program)
