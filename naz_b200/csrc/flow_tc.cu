@@ -147,8 +147,8 @@ struct TcState {
                                      // distance 1 when every CTA has >= 32 tiles per group (measured: free at 53 tiles, +2.3 % at 26; the wait at a group boundary is then < 3 % of the
                                      // group), else distance 2.  Full-size cfg3: 76 GB of DRAM reads per launch at distance 2, 5.4 GB at 1.
   int opt_a_tmem = 1;                // v5: A operand in tensor memory when the plan allows it
-  int opt_defer = 0;                 // v5 split pushes: hold the trailing MMAs back until the accumulator reads are done (needs room for a
-                                     // second A buffer in TMEM)
+  int opt_defer = 2;                 // v5 split pushes with room for a second A buffer in TMEM: 1 = hold the trailing MMAs back until the
+                                     // accumulator reads are done (ld_done barrier), 2 = double buffer only (no a_free hand-shake), 0 = a_free
   int opt_trim = 1;                  // folded v5 / v6 programs drop the dead degree-0 accumulator columns
   int opt_align = -1;                // v5 / v6: block-aligned column layout when it fits tensor memory: 1 = on, 0 = off, -1 = auto (on for
                                      // flow layers with >= 4 hidden blocks: cfg2 +13 %; no effect on cfg3 / cfg4 whose blocks are wide)
@@ -1331,7 +1331,7 @@ int nazb_tc_set_option(nazb_handle* h, const char* name, int value) {
   if (!strcmp(name, "inv_gate")) { if (value < 0 || value > 3) return NAZB_ERR_BAD_ARG; t->opt_gate = value; return NAZB_OK; }
   if (!strcmp(name, "inv_a_tmem")) { t->opt_a_tmem = value ? 1 : 0; return NAZB_OK; }
   if (!strcmp(name, "inv_trim")) { t->opt_trim = value ? 1 : 0; h->is_packed = false; return NAZB_OK; }
-  if (!strcmp(name, "inv_defer")) { t->opt_defer = value ? 1 : 0; return NAZB_OK; }
+  if (!strcmp(name, "inv_defer")) { if (value < 0 || value > 2) return NAZB_ERR_BAD_ARG; t->opt_defer = value; h->is_packed = false; return NAZB_OK; }
   if (!strcmp(name, "inv_align")) { if (value < -1 || value > 1) return NAZB_ERR_BAD_ARG; t->opt_align = value; h->is_packed = false; return NAZB_OK; }
   return NAZB_ERR_BAD_ARG;
 }
@@ -1411,14 +1411,35 @@ cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* con
   auto plan_inverse = [&](const FlowGeom& gg) -> bool {
     P.steps[0].clear(); P.images[0].clear(); P.fold_images.clear(); P.steps_fold.clear(); P.kr_max = 0; P.fold_ok = false;
     const int vgen = (P.inv_ver == 6) ? 5 : (P.inv_ver == 5) ? 3 : 1;
-    // v5 default: split pushes (critical columns first) when the flow layer has >= 4 stages with hidden blocks — there the
-    // trailing columns are most of a push (cfg2 6|4, cfg5 8|4: +1-2 %); with 2-3 wide blocks (cfg3, cfg4) the a_free
-    // hand-shake costs more than the shorter critical MMAs save (81.4 -> 79.0 M evals/s on cfg3), so those stay unsplit
-    const int merge_n = t->opt_merge_n >= 0 ? t->opt_merge_n : (P.inv_ver == 5 ? (n_live_blocks >= 4 ? 0 : 256) : 0);
-    if (!(build_inverse(gg, P, vgen, merge_n, P.steps[0], P.images[0], &P.fold_images) && plan_smem_inv4(gg, P))) return false;
+    // Split pushes (critical columns first), v5 defaults by shape, measured at the dev sizes:
+    //  * a program whose plan has room for a SECOND A buffer in tensor memory is split and needs no hand-shake at all
+    //    (kSplit = 3): cfg3 folded 81.2 -> 84.0 M evals/s, cfg2 +8 %, cfg5 8|4 +6.5 %, cfg4 +0 %;
+    //  * otherwise (single A buffer + a_free hand-shake) splitting pays only for flow layers with >= 4 hidden blocks, where the
+    //    trailing columns are most of a push (cfg2, cfg5 8|4: +1-2 %); with 2-3 wide blocks it costs 3 % (cfg3: 81.4 -> 79.0).
+    // The general and the folded program share the images but not the step lists, so each takes its own decision.
+    const int merge_fallback = (P.inv_ver == 5 ? (n_live_blocks >= 4 ? 0 : 256) : 0);
+    auto build_prog = [&](TcPlan& T, int variant, std::vector<Step>& steps, std::vector<Image>& imgs, std::vector<Image>* fold) -> bool {
+      // built into locals: `steps` / `imgs` / `fold` may be members of T itself, which the plan copy below would clobber
+      auto attempt = [&](int merge_n, bool need_room) -> bool {
+        TcPlan T2 = T;
+        std::vector<Step> st;
+        std::vector<Image> im, fo;
+        if (!build_inverse(gg, T2, variant, merge_n, st, im, fold ? &fo : nullptr)) return false;
+        if (need_room && !(T2.split && T2.a_tmem2)) return false;
+        T = T2;
+        steps = std::move(st); imgs = std::move(im);
+        if (fold) *fold = std::move(fo);
+        return true;
+      };
+      if (t->opt_merge_n >= 0) return attempt(t->opt_merge_n, false);
+      if (P.inv_ver == 5 && t->opt_defer == 2 && t->opt_a_tmem && attempt(0, true)) return true;
+      return attempt(merge_fallback, false);
+    };
+    if (!(build_prog(P, vgen, P.steps[0], P.images[0], &P.fold_images) && plan_smem_inv4(gg, P))) return false;
     std::vector<Image> scratch_images;
     TcPlan Q = P;   // the folded variant must not disturb kr_max / layer_bytes of the general plan
-    P.fold_ok = build_inverse(gg, Q, vgen + 1, merge_n, P.steps_fold, scratch_images, nullptr) &&
+    Q.split = false; Q.a_tmem2 = false;
+    P.fold_ok = build_prog(Q, vgen + 1, P.steps_fold, scratch_images, nullptr) &&
                 Q.layer_bytes[0] == P.layer_bytes[0] && (int)P.fold_images.size() <= kMaxFoldImgs;
     if (!P.fold_ok) P.steps_fold.clear();
     P.fold_a_tmem = P.fold_ok && Q.a_tmem;
@@ -1628,15 +1649,21 @@ static cudaError_t launch_inv4(const nazb_handle* h, const TcState* t, const IoA
     kp.t_a = (uint32_t)(fold ? P.t_a_fold : P.t_a);
     const bool afree = atm && (fold ? P.split_fold : P.split);
     kp.a_free = afree ? 1 : 0;
-    const bool defer = afree && t->opt_defer && (fold ? P.fold_a_tmem2 : P.a_tmem2);
-    if (atm && defer) {
+    const bool dbl = afree && (fold ? P.fold_a_tmem2 : P.a_tmem2);
+    const bool defer = dbl && t->opt_defer == 1;
+    kp.a_free = (afree && !(dbl && t->opt_defer >= 1)) ? 1 : 0;
+    if (atm && dbl && t->opt_defer == 2) {
+      kern = flow_tc_inv5_kernel<false, 2, true, 3>;
+      if (mode == 0) kern = flow_tc_inv5_kernel<false, 0, true, 3>;
+      else if (mode == 1) kern = g_tc_dbg ? flow_tc_inv5_kernel<true, 1, true, 3> : flow_tc_inv5_kernel<false, 1, true, 3>;
+    } else if (atm && defer) {
       kern = flow_tc_inv5_kernel<false, 2, true, 2>;
       if (mode == 0) kern = flow_tc_inv5_kernel<false, 0, true, 2>;
       else if (mode == 1) kern = flow_tc_inv5_kernel<false, 1, true, 2>;
     } else if (atm && afree) {
       kern = flow_tc_inv5_kernel<false, 2, true, 1>;
       if (mode == 0) kern = flow_tc_inv5_kernel<false, 0, true, 1>;
-      else if (mode == 1) kern = flow_tc_inv5_kernel<false, 1, true, 1>;
+      else if (mode == 1) kern = g_tc_dbg ? flow_tc_inv5_kernel<true, 1, true, 1> : flow_tc_inv5_kernel<false, 1, true, 1>;
     } else if (atm) {
       kern = flow_tc_inv5_kernel<false, 2, true>;
       if (mode == 0) kern = flow_tc_inv5_kernel<false, 0, true>;

@@ -46,7 +46,10 @@ constexpr int kDbgEvents = 4096;
 template <bool kDbg, int kMode, bool kATmem, int kSplit = 0>
 __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __grid_constant__ KParamsInv4 p,
                                                                       const __grid_constant__ IoArgs io, int n_groups) {
-  constexpr bool kAFree = (kSplit == 1), kDefer = (kSplit == 2);
+  // kSplit = 3: double-buffered A, trailing MMAs right behind the critical ones, NO hand-shake: the writers of block k + 2
+  // start after the accumulator barrier of push k + 1, whose critical MMAs sit behind the trailing ones of push k in the
+  // in-order tensor pipe, so the buffer they overwrite is no longer read
+  constexpr bool kAFree = (kSplit == 1), kDefer = (kSplit == 2), kDbl = (kSplit >= 2);
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* w_full = reinterpret_cast<uint64_t*>(smem);            // [nslots] TMA -> issuers
   uint64_t* w_empty = w_full + 8;                                   // [nslots] count = 1 (the issuer's commit)
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
             const uint32_t ro = s_ncrit;                        // image row n_crit = byte offset n_crit * 16, >> 4
             // A in TMEM: ONE buffer (every MMA of a push has retired before the epilogue that writes the next block passes
             // the accumulator barrier: pushes are unsplit), K slice s at columns t_a + 8 s (hi) / t_a + kr_max / 2 + 8 s (lo)
-            uint32_t ta_h = p.t_a + (kDefer ? buf * (uint32_t)p.kr_max : 0u) + slice0 * 8u, ta_l = ta_h + (uint32_t)p.kr_max / 2u;
+            uint32_t ta_h = p.t_a + (kDbl ? buf * (uint32_t)p.kr_max : 0u) + slice0 * 8u, ta_l = ta_h + (uint32_t)p.kr_max / 2u;
             const uint32_t pair0 = slice0 >> 1;                 // sub-steps of a K-split push start at an even slice
             uint64_t* rdy = a_ready + buf * kV5MaxPairs + pair0;
             uint32_t bit = 1u << (buf * kV5MaxPairs + pair0);
@@ -229,7 +232,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
                   }
                 }
                 if (s_last && lastk) tcx::mma_commit(bar_acc);
-                if (n_rest && kATmem && (kAFree || kDefer)) {
+                if (n_rest && kATmem && kSplit != 0) {
                   // split pushes, A in TMEM: the remaining columns of ALL K slices of this step go behind the critical MMAs of
                   // its last pair (issued per pair they would sit in front of the next pair's critical MMAs in the in-order pipe);
                   // kDefer holds those of a push's last sub-step back further (below, after the ld_done barrier)
@@ -360,7 +363,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
       if (kATmem) {
         // chunk c = K elements [8c, 8c + 8) = TMEM columns [4c, 4c + 4) of the hi / lo image; the two half-warps of a row hold
         // chunks 2s and 2s + 1, i.e. the 8 columns of K slice s (the store is warp-collective: both halves always take part)
-        const uint32_t ta = lane_base + p.t_a + (kDefer ? buf * (uint32_t)p.kr_max : 0u) + (uint32_t)(c >> 1) * 8u;
+        const uint32_t ta = lane_base + p.t_a + (kDbl ? buf * (uint32_t)p.kr_max : 0u) + (uint32_t)(c >> 1) * 8u;
         tcx::tmem_st16x2_4<4>(ta, hi4.x, hi4.y, hi4.z, hi4.w);
         tcx::tmem_st16x2_4<4>(ta + (uint32_t)p.kr_max / 2u, lo4.x, lo4.y, lo4.z, lo4.w);
       } else {

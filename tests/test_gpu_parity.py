@@ -280,7 +280,8 @@ def test_svi_importance_pipeline_on_device():
 
 
 INV_VARIANTS = [
-    {},                                       # v5 kernel (one 128-row chain, 16 epilogue warps, unsplit pushes), defaults
+    {},                                       # v5 kernel (one 128-row chain, 16 epilogue warps), defaults: split pushes + double-buffered A in TMEM where it fits
+    {"inv_defer": 0},                         # v5 with the round-2a defaults (unsplit pushes for this shape, single A buffer)
     {"inv_kernel": 6},                        # v6 kernel (24 epilogue warps, split pushes behind an a_free barrier)
     {"inv_kernel": 6, "inv_merge_n": 256},    # v6 with unsplit pushes
     {"inv_kernel": 6, "inv_a_tmem": 0},       # v6 with the A operand in shared memory
@@ -291,6 +292,7 @@ INV_VARIANTS = [
     {"inv_kernel": 4, "inv_merge_n": 256},    # ... every push issued unsplit
     {"inv_merge_n": 0},                       # v5 with split pushes (critical columns first; A stays in tensor memory behind a_free)
     {"inv_merge_n": 0, "inv_defer": 1},       # ... trailing MMAs held back until the accumulator reads are done, A double-buffered in TMEM
+    {"inv_merge_n": 0, "inv_defer": 2},       # ... A double-buffered in TMEM, no hand-shake at all
     {"inv_a_tmem": 0},                        # v5 with the A operand in shared memory
     {"inv_a_tmem": 0, "inv_merge_n": 0},      # ... and split pushes
     {"inv_fold": 0},                          # broadcast context evaluated per point (general program)

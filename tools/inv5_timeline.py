@@ -11,7 +11,8 @@ spec, draws, keep, rng = make_case("nsa", 4, 2, [150]*3, 16, 4, seed=1)
 N = 148 * 128
 x = torch.from_numpy((rng.normal(size=(N, 4)) * 1.5).astype(np.float32)).cuda()
 ctx = torch.from_numpy(rng.uniform(size=(1, 2) if mode == "bcast" else (N, 2)).astype(np.float32)).cuda()
-eng = engine_for(spec, draws, engine="tcgen05")
+import json, os
+eng = engine_for(spec, draws, engine="tcgen05", options=json.loads(os.environ.get("OPTS", "{}")))
 L = _lib.lib()
 NEV = 4096
 buf = torch.zeros(3 * NEV * 2, dtype=torch.int64, device="cuda")
