@@ -523,13 +523,30 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
                       s2[2] = tcx::fma2(w1.x, x2, s2[2]); s2[3] = tcx::fma2(w1.y, x2, s2[3]);
                     }
                   }
-                  for (int k = 0; k < r; ++k) {
-                    const float xq = xr[k * kTileM + trow];
-                    const uint64_t x2 = tcx::pk2(xq, xq);
-                    const ulonglong2* ww = reinterpret_cast<const ulonglong2*>(lc + p.lc_w0x + (size_t)k * hp0 + nb);
-                    const ulonglong2 w0 = ww[0], w1 = ww[1];
-                    s2[0] = tcx::fma2(w0.x, x2, s2[0]); s2[1] = tcx::fma2(w0.y, x2, s2[1]);
-                    s2[2] = tcx::fma2(w1.x, x2, s2[2]); s2[3] = tcx::fma2(w1.y, x2, s2[3]);
+                  // r <= 2 (every stage of the 2-D ... 4-D bench flows): a predicated, fully unrolled block, all loads in flight
+                  // together (with a run-time trip count every iteration waits for its own shared-memory loads: +1.6 % on cfg3,
+                  // +2.3 % on cfg4); deeper stages keep the loop (unrolling 4 cost 1-2 % on the 6-D / 8-D flows)
+                  if (r <= 2) {
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                      if (k < r) {
+                        const float xq = xr[k * kTileM + trow];
+                        const uint64_t x2 = tcx::pk2(xq, xq);
+                        const ulonglong2* ww = reinterpret_cast<const ulonglong2*>(lc + p.lc_w0x + (size_t)k * hp0 + nb);
+                        const ulonglong2 w0 = ww[0], w1 = ww[1];
+                        s2[0] = tcx::fma2(w0.x, x2, s2[0]); s2[1] = tcx::fma2(w0.y, x2, s2[1]);
+                        s2[2] = tcx::fma2(w1.x, x2, s2[2]); s2[3] = tcx::fma2(w1.y, x2, s2[3]);
+                      }
+                    }
+                  } else {
+                    for (int k = 0; k < r; ++k) {
+                      const float xq = xr[k * kTileM + trow];
+                      const uint64_t x2 = tcx::pk2(xq, xq);
+                      const ulonglong2* ww = reinterpret_cast<const ulonglong2*>(lc + p.lc_w0x + (size_t)k * hp0 + nb);
+                      const ulonglong2 w0 = ww[0], w1 = ww[1];
+                      s2[0] = tcx::fma2(w0.x, x2, s2[0]); s2[1] = tcx::fma2(w0.y, x2, s2[1]);
+                      s2[2] = tcx::fma2(w1.x, x2, s2[2]); s2[3] = tcx::fma2(w1.y, x2, s2[3]);
+                    }
                   }
                   tcx::tanh8_scaled(s2, hi4, lo4);
                 }
