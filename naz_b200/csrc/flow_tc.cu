@@ -149,6 +149,8 @@ struct TcState {
   int opt_a_tmem = 1;                // v5: A operand in tensor memory when the plan allows it
   int opt_defer = 2;                 // v5 split pushes with room for a second A buffer in TMEM: 1 = hold the trailing MMAs back until the
                                      // accumulator reads are done (ld_done barrier), 2 = double buffer only (no a_free hand-shake), 0 = a_free
+  int opt_park = 0;                  // v5: 1 = the issuer / producer warps wait with a suspend-time hint instead of polling (measured: the stragglers move
+                                     // to other sub-partitions, the phase spread stays 150-400 cycles, throughput -1 %: off)
   int opt_trim = 1;                  // folded v5 / v6 programs drop the dead degree-0 accumulator columns
   int opt_align = -1;                // v5 / v6: block-aligned column layout when it fits tensor memory: 1 = on, 0 = off, -1 = auto (on for
                                      // flow layers with >= 4 hidden blocks: cfg2 +13 %; no effect on cfg3 / cfg4 whose blocks are wide)
@@ -1283,6 +1285,8 @@ constexpr int kChainRows = kTileM / kChains;          // 64
 static long long* g_tc_dbg = nullptr;
 // dev tool (not part of include/nazb.h): device buffer [256][8] receiving CTA 0's per-step clock stamps
 extern "C" void nazb_debug_set_clock_buffer(long long* dev_buf) { g_tc_dbg = dev_buf; }
+static int g_tc_dbg_all = 0;
+extern "C" void nazb_debug_set_all_warps(int on) { g_tc_dbg_all = on; }
 extern "C" int nazb_debug_program(const nazb_handle* h, int dir, int* out, int cap);
 bool nazb_tc_supported(const FlowGeom& g, std::string* why) {
   TcPlan P;
@@ -1330,6 +1334,7 @@ int nazb_tc_set_option(nazb_handle* h, const char* name, int value) {
   if (!strcmp(name, "inv_merge_n")) { if (value < -1 || value > 256) return NAZB_ERR_BAD_ARG; t->opt_merge_n = value; h->is_packed = false; return NAZB_OK; }
   if (!strcmp(name, "inv_gate")) { if (value < 0 || value > 3) return NAZB_ERR_BAD_ARG; t->opt_gate = value; return NAZB_OK; }
   if (!strcmp(name, "inv_a_tmem")) { t->opt_a_tmem = value ? 1 : 0; return NAZB_OK; }
+  if (!strcmp(name, "inv_park")) { t->opt_park = value ? 1 : 0; return NAZB_OK; }
   if (!strcmp(name, "inv_trim")) { t->opt_trim = value ? 1 : 0; h->is_packed = false; return NAZB_OK; }
   if (!strcmp(name, "inv_defer")) { if (value < 0 || value > 2) return NAZB_ERR_BAD_ARG; t->opt_defer = value; h->is_packed = false; return NAZB_OK; }
   if (!strcmp(name, "inv_align")) { if (value < -1 || value > 1) return NAZB_ERR_BAD_ARG; t->opt_align = value; h->is_packed = false; return NAZB_OK; }
@@ -1344,6 +1349,7 @@ int nazb_tc_get_option(const nazb_handle* h, const char* name, int* value) {
   else if (!strcmp(name, "inv_gate")) *value = t->opt_gate;
   else if (!strcmp(name, "inv_a_tmem")) *value = t->opt_a_tmem;
   else if (!strcmp(name, "inv_trim")) *value = t->opt_trim;
+  else if (!strcmp(name, "inv_park")) *value = t->opt_park;
   else if (!strcmp(name, "inv_defer")) *value = t->opt_defer;
   else if (!strcmp(name, "inv_align")) *value = t->opt_align;
   else if (!strcmp(name, "inv_block_width")) *value = t->plan.ok[0] ? t->plan.bw : 0;
@@ -1576,6 +1582,8 @@ static cudaError_t launch_inv4(const nazb_handle* h, const TcState* t, const IoA
   const std::vector<Step>& prog = fold ? P.steps_fold : P.steps[0];
   KParamsInv4 kp{};
   kp.dbg = g_tc_dbg;
+  kp.dbg_all = g_tc_dbg_all;
+  kp.park = t->opt_park;
   kp.nsteps = (int)prog.size();
   for (int i = 0; i < kp.nsteps; ++i) kp.steps[i] = prog[i];
   kp.wimg = t->wimg[0];

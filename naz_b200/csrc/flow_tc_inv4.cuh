@@ -50,6 +50,8 @@ struct KParamsInv4 {
   int gate_dist;                   // a producer starts group g once every CTA has finished issuing group g - gate_dist (1 or 2)
   unsigned int* wd;                // watchdog word (mapped host memory) or null
   long long* dbg;
+  int park;                        // issuer / producer waits use the suspend-time hint (mbar_wait4_parked)
+  int dbg_all;                     // dev tool: log every epilogue warp (slot = warp id, issuer = slot 16) instead of warps 0 / 8 / issuer
 };
 
 // mbarrier wait (a suspend-time hint was measured: 2 % slower) with a clock watchdog (~2^32 cycles): on timeout the tag goes to mapped host
@@ -72,6 +74,31 @@ __device__ __forceinline__ void mbar_wait4(uint64_t* bar, uint32_t parity, unsig
       "fence.acq_rel.sys;\n\t"
       "trap;\n\t"
       "DONE4:\n\t}\n" ::"r"(tcx::smem_u32(bar)),
+      "r"(parity), "l"(wd), "r"(tag)
+      : "memory");
+}
+// Same wait for the single-purpose warps (MMA issuer, TMA producer): try_wait with a suspend-time hint, so that the warp is
+// parked by the hardware until the phase completes instead of polling.  Measured with the all-warp event log
+// (tools/inv5_spread.py): the polling issuer / producer took 15-25 % of the issue slots of the sub-partition they live on, and the four
+// epilogue warps of that sub-partition finished every phase 150-500 cycles after the others — the whole tile waits for them.
+__device__ __forceinline__ void mbar_wait4_parked(uint64_t* bar, uint32_t parity, unsigned int* wd, uint32_t tag) {
+  asm volatile(
+      "{\n\t.reg .pred P1, P2;\n\t.reg .u64 t0, t1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x10000;\n\t"
+      "@P1 bra DONE4P;\n\t"
+      "mov.u64 t0, %%clock64;\n\t"
+      "LAB_WAIT4P:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x10000;\n\t"
+      "@P1 bra DONE4P;\n\t"
+      "mov.u64 t1, %%clock64;\n\t"
+      "sub.u64 t1, t1, t0;\n\t"
+      "setp.gt.u64 P2, t1, 0x100000000;\n\t"
+      "@!P2 bra LAB_WAIT4P;\n\t"
+      "setp.ne.u64 P2, %2, 0;\n\t"
+      "@P2 st.volatile.global.u32 [%2], %3;\n\t"
+      "fence.acq_rel.sys;\n\t"
+      "trap;\n\t"
+      "DONE4P:\n\t}\n" ::"r"(tcx::smem_u32(bar)),
       "r"(parity), "l"(wd), "r"(tag)
       : "memory");
 }

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
             const int l = p.L - 1 - li;
             {
               const uint32_t b = lcnt & 1, use = lcnt >> 1;
-              mbar_wait4(lc_empty + b, (use & 1) ^ 1, p.wd, WD_TAG(1));
+              if (p.park) mbar_wait4_parked(lc_empty + b, (use & 1) ^ 1, p.wd, WD_TAG(1)); else mbar_wait4(lc_empty + b, (use & 1) ^ 1, p.wd, WD_TAG(1));
               tcx::mbar_expect_tx(lc_full + b, (uint32_t)p.lc_floats * 4);
               tcx::bulk_g2s(lcs + (size_t)b * p.lc_floats, lcdraw + (size_t)l * p.lc_floats, (uint32_t)p.lc_floats * 4, lc_full + b);
               ++lcnt;
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
               const uint32_t wb = p.steps[st].w_bytes;
               if (wb == 0) continue;
               const uint32_t slot = cnt % p.nslots, use = cnt / p.nslots;
-              mbar_wait4(w_empty + slot, (use & 1) ^ 1, p.wd, WD_TAG(2));
+              if (p.park) mbar_wait4_parked(w_empty + slot, (use & 1) ^ 1, p.wd, WD_TAG(2)); else mbar_wait4(w_empty + slot, (use & 1) ^ 1, p.wd, WD_TAG(2));
               tcx::mbar_expect_tx(w_full + slot, wb);
               tcx::bulk_g2s(ring + (size_t)slot * kSlotBytes, wl + p.steps[st].w_off, wb, w_full + slot);
               ++cnt;
@@ -165,6 +165,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
     uint32_t slot = 0, use = 0, buf = 0, apar = 0;   // apar: one parity bit per (buffer, slice) barrier
     [[maybe_unused]] uint32_t par_ld = 0;
     int dbg_n = 0;
+    const int iss_slot = p.dbg_all ? kV5EpiWarps : 2;
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int grp = (int)(item / n_tiles);
       for (int si = grp; si < io.s_count; si += n_groups) {
@@ -199,14 +200,14 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
             uint64_t* rdy = a_ready + buf * kV5MaxPairs + pair0;
             uint32_t bit = 1u << (buf * kV5MaxPairs + pair0);
             auto desc = [](uint32_t lo) { return ((uint64_t)dhi32 << 32) | lo; };
-            LOG5(2, 20)
-            mbar_wait4(w_full + slot, use & 1, p.wd, WD_TAG(3));
-            LOG5(2, 21)
+            LOG5(iss_slot, 20)
+            if (p.park) mbar_wait4_parked(w_full + slot, use & 1, p.wd, WD_TAG(3)); else mbar_wait4(w_full + slot, use & 1, p.wd, WD_TAG(3));
+            LOG5(iss_slot, 21)
             for (int k = 0; k < ksteps; k += 2) {
-              mbar_wait4(rdy, (apar & bit) ? 1u : 0u, p.wd, WD_TAG(4));
+              if (p.park) mbar_wait4_parked(rdy, (apar & bit) ? 1u : 0u, p.wd, WD_TAG(4)); else mbar_wait4(rdy, (apar & bit) ? 1u : 0u, p.wd, WD_TAG(4));
               apar ^= bit;
               tcx::tc_fence_after();
-              LOG5(2, 32 + k)
+              LOG5(iss_slot, 32 + k)
               const bool two = (k + 1 < ksteps);
               const bool lastk = (k + 2 >= ksteps);
               if (tcx::elect_one()) {
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
               __syncwarp();
               if (kDefer && kATmem && lastk && s_last && n_rest) {
                 // the epilogue warps have their accumulators in registers: now the trailing columns may use the TMEM ports
-                mbar_wait4(a_free, par_ld, p.wd, WD_TAG(8));
+                if (p.park) mbar_wait4_parked(a_free, par_ld, p.wd, WD_TAG(8)); else mbar_wait4(a_free, par_ld, p.wd, WD_TAG(8));
                 par_ld ^= 1;
                 tcx::tc_fence_after();
                 if (tcx::elect_one()) {
@@ -290,12 +291,12 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
                 }
                 __syncwarp();
               }
-              LOG5(2, 48 + k)
+              LOG5(iss_slot, 48 + k)
               da_h += 2 * a_step; da_l += 2 * a_step; db_h += 2 * b_step; db_l += 2 * b_step;
               ta_h += 16; ta_l += 16;
               ++rdy; bit <<= 1;
             }
-            LOG5(2, 23)
+            LOG5(iss_slot, 23)
             if (++slot == (uint32_t)p.nslots) { slot = 0; ++use; }
             if (s_last) buf ^= 1;
           }
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
     uint32_t par_acc = 0, lcnt = 0, buf = 0;
     [[maybe_unused]] uint32_t par_free = 1;   // first A block: wait(parity 1) on the fresh barrier returns at once
     int dbg_n = 0;
-    const int dbg_slot = sll;
+    const int dbg_slot = p.dbg_all ? warp : sll;
     auto ld_done_arrive = [&]() {   // kDefer: this warp holds every accumulator it needs of the current step in registers
       __syncwarp();
       if (lane == 0) tcx::mbar_arrive(a_free);
@@ -425,7 +426,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
           const int* perm = p.perm + l * D;
           const float* lc = lcs + (size_t)(lcnt & 1) * p.lc_floats;
           mbar_wait4(lc_full + (lcnt & 1), (lcnt >> 1) & 1, p.wd, WD_TAG(5));
-          const bool dbg_on = kDbg && p.dbg != nullptr && blockIdx.x == 0 && q == 0 && rh == 0 && item == blockIdx.x && si != grp && li >= 2;
+          const bool dbg_on = kDbg && p.dbg != nullptr && blockIdx.x == 0 && (p.dbg_all || (q == 0 && rh == 0)) && item == blockIdx.x && si != grp && li >= 2;
           for (int st = 0; st < p.nsteps; ++st) {
             const uint32_t s_epi = p.steps[st].epi;
             if (s_epi == EPI_NONE) continue;   // K-split sub-step: nothing to do on this side
