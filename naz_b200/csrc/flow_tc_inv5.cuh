@@ -351,10 +351,17 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
     auto publish_x = [&]() {   // owner warp, after the owner lanes stored x into xr
       ++xcount;
       __syncwarp();
-      if (lane == 0) { __threadfence_block(); *my_xflag = xcount; }
+      // release store / acquire load on the counter itself instead of two block fences (fences: -1.6 % on cfg3: MEMBAR.ALL.CTA
+      // also waits for the thread's outstanding global stores)
+      if (lane == 0) asm volatile("st.release.cta.shared::cta.u32 [%0], %1;\n" ::"r"(tcx::smem_u32((const void*)my_xflag)), "r"(xcount) : "memory");
     };
     auto await_x = [&]() {     // partner warp: every x published so far is visible
-      if (lane == 0) { while ((int)(*my_xflag - xcount) < 0) { } __threadfence_block(); }
+      if (lane == 0) {
+        int seen;
+        do {
+          asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];\n" : "=r"(seen) : "r"(tcx::smem_u32((const void*)my_xflag)) : "memory");
+        } while (seen - xcount < 0);
+      }
       __syncwarp();
     };
     const uint64_t scale2 = tcx::pk2(kTanhScale, kTanhScale);
