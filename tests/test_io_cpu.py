@@ -157,3 +157,21 @@ def test_ppd_writer_round_trip_and_h5_blocker(tmp_path):
             nio.save_ppds(tmp_path / "ppds.h5", ppds)
         with pytest.raises(RuntimeError, match="h5py"):
             nio.load_ppds(tmp_path / "ppds.h5")
+
+
+def test_flow_state_of_our_own_flow_equals_torch_to_jax(tmp_path):
+    """The same walker reads a pickled naz_b200 flow (classes importable): identical to torch_to_jax on the live object."""
+    from naz_b200.flows import NormalizingFlow
+    from naz_b200.flows.bflow_maf import torch_to_jax
+    torch.manual_seed(5)
+    flow = NormalizingFlow("maf", None, 3, 2, [16, 12], 3)
+    f = tmp_path / "flow.pkl"
+    with open(f, "wb") as pf:
+        pickle.dump(flow, pf)
+    params, shapes, masks, mask_skips, perms = nio.load_pickled_flow(f)
+    p2, s2, m2, ms2, pm2 = torch_to_jax(flow)
+    assert shapes == s2
+    for l in range(3):
+        assert torch.equal(perms[l], pm2[l]) and torch.equal(mask_skips[l], ms2[l])
+        for j in range(3):
+            assert torch.equal(params[l][j][0], p2[l][j][0]) and torch.equal(params[l][j][1], p2[l][j][1]) and torch.equal(masks[l][j], m2[l][j])
