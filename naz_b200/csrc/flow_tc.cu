@@ -410,7 +410,10 @@ bool build_inverse(const FlowGeom& g, TcPlan& P, int variant, int merge_n, std::
   const bool v5 = variant >= 3, v6 = variant >= 5;
   const bool v4 = variant != 0, folded = (variant == 2 || variant == 4 || variant == 6);
   const int nh = g.n_hidden, D = g.D;
-  const int Mp = v5 ? P.mp : (v4 ? ceil_to(g.M, 8) : P.mp);
+  // output columns per rank: v4 / v5 ceil8(M) (v5: a push that does not start at a multiple of 16 columns starts at the
+  // 16-aligned column below and carries zero rows for the columns of the already finished rank it overlaps), v3 ceil16(M)
+  const int Mp = v4 ? ceil_to(g.M, 8) : P.mp;
+  const int out_w = v5 ? ceil_to(D * Mp, 16) : D * Mp;
   P.mp_inv = Mp;
   // v3 feeds [ctx | x | 1] to a K = 16 MMA slice; v4 / v5 compute the first layer on CUDA cores from rank-ordered columns
   if (D * Mp > 256 || (!v4 && g.kin > 16) || D > 16) return false;
@@ -426,7 +429,8 @@ bool build_inverse(const FlowGeom& g, TcPlan& P, int variant, int merge_n, std::
     const int dead = trim ? (g.blk[j][1] & ~15) : 0;
     T_PRE[j] = col - dead; col += hp(j) - dead;
   }
-  const int T_OUT = col - (trim ? Mp : 0); col += (trim ? D - 1 : D) * Mp;
+  const int dead_out = trim ? (v5 ? (Mp & ~15) : Mp) : 0;   // rank 0 is never read by the folded program
+  const int T_OUT = col - dead_out; col += out_w - dead_out;
   if (col > kTmemCols) return false;
   const int t_end = col;
   // width of a block as the epilogues see it: the aligned layout pads every block to bw columns of which only aw are live
@@ -519,12 +523,14 @@ bool build_inverse(const FlowGeom& g, TcPlan& P, int variant, int merge_n, std::
                mk_img(j + 1, n, kr, 0, tn0, 0, 0, sc0, sb0, sb1, -1, 0), e, n_crit);
         if (!skip) first_push[j + 1] = false;
       } else {
-        int n = (D - r) * Mp;
+        const int s0 = v5 ? ((r * Mp) & ~15) : r * Mp;          // first accumulator column of this push (M = 128: multiple of 16)
+        int n = out_w - s0;
         Step e = mk_epi(EPI_XINV, T_OUT + r * Mp, 0, 0, r);
         e.e_aux = (uint16_t)(P.lc_bout + r * Mp);
-        int n_crit = Mp;
+        int n_crit = v5 ? ceil_to((r + 1) * Mp, 16) - s0 : Mp;
         if (v4 && n <= merge_n) n_crit = n;
-        b.gemm(A_H, 0, kr, n, T_OUT + r * Mp, 3, first_push[nh] ? 0 : 1, mk_img(nh, n, kr, 1, 0, r, D, sc0, sb0, sb1, -1, 0), e, n_crit);
+        // image row n <-> output column s0 + n (rank = column / Mp, slot = column % Mp); rows of ranks < r and of the padding are zero
+        b.gemm(A_H, 0, kr, n, T_OUT + s0, 3, first_push[nh] ? 0 : 1, mk_img(nh, n, kr, 1, s0, r, D, sc0, sb0, sb1, -1, 0), e, n_crit);
         if (!skip) first_push[nh] = false;
       }
       if (fold_images && r == 0)
@@ -648,8 +654,10 @@ __global__ void tc_pack_kernel(Image im, int S, int L, int n_lin, int D, int M, 
       if (map_out) u = (u < 256) ? map_out[u] : -1;
       if (u >= 0 && u < ndim) o = u;
     } else if (im.row_mode == 1) {
-      int rank = im.r0 + n / Mp, m = n % Mp;
-      if (rank < im.r1 && m < M) o = m * D + perm[l * D + rank];
+      // n0 = output column of image row 0; ranks below r0 (columns a 16-aligned start overlaps) and padding rows stay zero
+      const int colo = im.n0 + n;
+      int rank = colo / Mp, m = colo % Mp;
+      if (rank >= im.r0 && rank < im.r1 && m < M) o = m * D + perm[l * D + rank];
     } else {
       int rank = im.r0 + n / M, m = n % M;
       if (rank < im.r1) o = m * D + perm[l * D + rank];
@@ -1619,7 +1627,7 @@ static cudaError_t launch_inv4(const nazb_handle* h, const TcState* t, const IoA
       const Image& im = P.fold_images[i];
       FoldImg& fi = fp.img[i];
       fi.w_off = im.w_off; fi.w_bytes = im.w_bytes; fi.lin = im.lin; fi.n_ext = im.n_ext; fi.k_ext = im.k_ext;
-      fi.n0 = (im.row_mode == 0) ? im.n0 : im.r0 * P.mp_inv; fi.k0 = im.k0;
+      fi.n0 = im.n0; fi.k0 = im.k0;   // hidden unit / output column of image row 0
     }
     fp.wimg = t->wimg[0]; fp.draw_bytes = t->draw_bytes[0]; fp.layer_bytes = P.layer_bytes[0];
     fp.lc = t->lc_dev; fp.lcf = t->lcfold_dev; fp.lc_floats = P.lc_floats; fp.lc_w0c = P.lc_w0c; fp.lc_r0c = P.lc_r0c;
