@@ -54,20 +54,21 @@ struct KParamsInv4 {
   int dbg_all;                     // dev tool: log every epilogue warp (slot = warp id, issuer = slot 16) instead of warps 0 / 8 / issuer
 };
 
-// mbarrier wait (a suspend-time hint was measured: 2 % slower) with a clock watchdog (~2^32 cycles): on timeout the tag goes to mapped host
+// mbarrier wait (a suspend-time hint was measured: 2 % slower) with a poll-count watchdog: on timeout the tag goes to mapped host
 // memory and the kernel traps, so a protocol bug surfaces as a launch failure with a location instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait4(uint64_t* bar, uint32_t parity, unsigned int* wd, uint32_t tag) {
+  // the watchdog counts polls instead of reading the clock (5 instead of 8 instructions per poll: the pollers share their
+  // sub-partition's issue slots with working warps); 2^27 polls of >= 20 cycles each are seconds, far beyond any legal wait
   asm volatile(
-      "{\n\t.reg .pred P1, P2;\n\t.reg .u64 t0, t1;\n\t"
+      "{\n\t.reg .pred P1, P2;\n\t.reg .u32 n;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
       "@P1 bra DONE4;\n\t"
-      "mov.u64 t0, %%clock64;\n\t"
+      "mov.u32 n, 0;\n\t"
       "LAB_WAIT4:\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
       "@P1 bra DONE4;\n\t"
-      "mov.u64 t1, %%clock64;\n\t"
-      "sub.u64 t1, t1, t0;\n\t"
-      "setp.gt.u64 P2, t1, 0x100000000;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "setp.gt.u32 P2, n, 0x8000000;\n\t"
       "@!P2 bra LAB_WAIT4;\n\t"
       "setp.ne.u64 P2, %2, 0;\n\t"
       "@P2 st.volatile.global.u32 [%2], %3;\n\t"
