@@ -1342,7 +1342,7 @@ int nazb_tc_set_option(nazb_handle* h, const char* name, int value) {
   if (!strcmp(name, "inv_merge_n")) { if (value < -1 || value > 256) return NAZB_ERR_BAD_ARG; t->opt_merge_n = value; h->is_packed = false; return NAZB_OK; }
   if (!strcmp(name, "inv_gate")) { if (value < 0 || value > 3) return NAZB_ERR_BAD_ARG; t->opt_gate = value; return NAZB_OK; }
   if (!strcmp(name, "inv_a_tmem")) { t->opt_a_tmem = value ? 1 : 0; return NAZB_OK; }
-  if (!strcmp(name, "inv_park")) { t->opt_park = value ? 1 : 0; return NAZB_OK; }
+  if (!strcmp(name, "inv_park")) { if (value < 0 || value > 2) return NAZB_ERR_BAD_ARG; t->opt_park = value; return NAZB_OK; }
   if (!strcmp(name, "inv_trim")) { t->opt_trim = value ? 1 : 0; h->is_packed = false; return NAZB_OK; }
   if (!strcmp(name, "inv_defer")) { if (value < 0 || value > 2) return NAZB_ERR_BAD_ARG; t->opt_defer = value; h->is_packed = false; return NAZB_OK; }
   if (!strcmp(name, "inv_align")) { if (value < -1 || value > 1) return NAZB_ERR_BAD_ARG; t->opt_align = value; h->is_packed = false; return NAZB_OK; }

@@ -103,6 +103,27 @@ __device__ __forceinline__ void mbar_wait4_parked(uint64_t* bar, uint32_t parity
       "r"(parity), "l"(wd), "r"(tag)
       : "memory");
 }
+__device__ __forceinline__ void mbar_wait4_sleepy(uint64_t* bar, uint32_t parity, unsigned int* wd, uint32_t tag) {
+  asm volatile(
+      "{\n\t.reg .pred P1, P2;\n\t.reg .u32 n;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE4S;\n\t"
+      "mov.u32 n, 0;\n\t"
+      "LAB_WAIT4S:\n\t"
+      "nanosleep.u32 64;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE4S;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "setp.gt.u32 P2, n, 0x8000000;\n\t"
+      "@!P2 bra LAB_WAIT4S;\n\t"
+      "setp.ne.u64 P2, %2, 0;\n\t"
+      "@P2 st.volatile.global.u32 [%2], %3;\n\t"
+      "fence.acq_rel.sys;\n\t"
+      "trap;\n\t"
+      "DONE4S:\n\t}\n" ::"r"(tcx::smem_u32(bar)),
+      "r"(parity), "l"(wd), "r"(tag)
+      : "memory");
+}
 #define WD_TAG(site) ((uint32_t)(site) | ((uint32_t)warp << 8) | ((uint32_t)blockIdx.x << 16))
 
 __device__ __forceinline__ void pair_bar_sync(int id, int nthreads) {

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
             const int l = p.L - 1 - li;
             {
               const uint32_t b = lcnt & 1, use = lcnt >> 1;
-              if (p.park) mbar_wait4_parked(lc_empty + b, (use & 1) ^ 1, p.wd, WD_TAG(1)); else mbar_wait4(lc_empty + b, (use & 1) ^ 1, p.wd, WD_TAG(1));
+              if (p.park == 2) mbar_wait4_sleepy(lc_empty + b, (use & 1) ^ 1, p.wd, WD_TAG(1)); else if (p.park == 1) mbar_wait4_parked(lc_empty + b, (use & 1) ^ 1, p.wd, WD_TAG(1)); else mbar_wait4(lc_empty + b, (use & 1) ^ 1, p.wd, WD_TAG(1));
               tcx::mbar_expect_tx(lc_full + b, (uint32_t)p.lc_floats * 4);
               tcx::bulk_g2s(lcs + (size_t)b * p.lc_floats, lcdraw + (size_t)l * p.lc_floats, (uint32_t)p.lc_floats * 4, lc_full + b);
               ++lcnt;
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
               const uint32_t wb = p.steps[st].w_bytes;
               if (wb == 0) continue;
               const uint32_t slot = cnt % p.nslots, use = cnt / p.nslots;
-              if (p.park) mbar_wait4_parked(w_empty + slot, (use & 1) ^ 1, p.wd, WD_TAG(2)); else mbar_wait4(w_empty + slot, (use & 1) ^ 1, p.wd, WD_TAG(2));
+              if (p.park == 2) mbar_wait4_sleepy(w_empty + slot, (use & 1) ^ 1, p.wd, WD_TAG(2)); else if (p.park == 1) mbar_wait4_parked(w_empty + slot, (use & 1) ^ 1, p.wd, WD_TAG(2)); else mbar_wait4(w_empty + slot, (use & 1) ^ 1, p.wd, WD_TAG(2));
               tcx::mbar_expect_tx(w_full + slot, wb);
               tcx::bulk_g2s(ring + (size_t)slot * kSlotBytes, wl + p.steps[st].w_off, wb, w_full + slot);
               ++cnt;
@@ -201,10 +201,10 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
             uint32_t bit = 1u << (buf * kV5MaxPairs + pair0);
             auto desc = [](uint32_t lo) { return ((uint64_t)dhi32 << 32) | lo; };
             LOG5(iss_slot, 20)
-            if (p.park) mbar_wait4_parked(w_full + slot, use & 1, p.wd, WD_TAG(3)); else mbar_wait4(w_full + slot, use & 1, p.wd, WD_TAG(3));
+            if (p.park == 2) mbar_wait4_sleepy(w_full + slot, use & 1, p.wd, WD_TAG(3)); else if (p.park == 1) mbar_wait4_parked(w_full + slot, use & 1, p.wd, WD_TAG(3)); else mbar_wait4(w_full + slot, use & 1, p.wd, WD_TAG(3));
             LOG5(iss_slot, 21)
             for (int k = 0; k < ksteps; k += 2) {
-              if (p.park) mbar_wait4_parked(rdy, (apar & bit) ? 1u : 0u, p.wd, WD_TAG(4)); else mbar_wait4(rdy, (apar & bit) ? 1u : 0u, p.wd, WD_TAG(4));
+              if (p.park == 2) mbar_wait4_sleepy(rdy, (apar & bit) ? 1u : 0u, p.wd, WD_TAG(4)); else if (p.park == 1) mbar_wait4_parked(rdy, (apar & bit) ? 1u : 0u, p.wd, WD_TAG(4)); else mbar_wait4(rdy, (apar & bit) ? 1u : 0u, p.wd, WD_TAG(4));
               apar ^= bit;
               tcx::tc_fence_after();
               LOG5(iss_slot, 32 + k)
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
               __syncwarp();
               if (kDefer && kATmem && lastk && s_last && n_rest) {
                 // the epilogue warps have their accumulators in registers: now the trailing columns may use the TMEM ports
-                if (p.park) mbar_wait4_parked(a_free, par_ld, p.wd, WD_TAG(8)); else mbar_wait4(a_free, par_ld, p.wd, WD_TAG(8));
+                if (p.park == 2) mbar_wait4_sleepy(a_free, par_ld, p.wd, WD_TAG(8)); else if (p.park == 1) mbar_wait4_parked(a_free, par_ld, p.wd, WD_TAG(8)); else mbar_wait4(a_free, par_ld, p.wd, WD_TAG(8));
                 par_ld ^= 1;
                 tcx::tc_fence_after();
                 if (tcx::elect_one()) {
