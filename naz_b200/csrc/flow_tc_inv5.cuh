@@ -531,29 +531,41 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
                       s2[2] = tcx::fma2(w1.x, x2, s2[2]); s2[3] = tcx::fma2(w1.y, x2, s2[3]);
                     }
                   }
-                  // r <= 2 (every stage of the 2-D ... 4-D bench flows): a predicated, fully unrolled block, all loads in flight
-                  // together (with a run-time trip count every iteration waits for its own shared-memory loads: +1.6 % on cfg3,
-                  // +2.3 % on cfg4); deeper stages keep the loop (unrolling 4 cost 1-2 % on the 6-D / 8-D flows)
-                  if (r <= 2) {
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                      if (k < r) {
-                        const float xq = xr[k * kTileM + trow];
-                        const uint64_t x2 = tcx::pk2(xq, xq);
-                        const ulonglong2* ww = reinterpret_cast<const ulonglong2*>(lc + p.lc_w0x + (size_t)k * hp0 + nb);
-                        const ulonglong2 w0 = ww[0], w1 = ww[1];
-                        s2[0] = tcx::fma2(w0.x, x2, s2[0]); s2[1] = tcx::fma2(w0.y, x2, s2[1]);
-                        s2[2] = tcx::fma2(w1.x, x2, s2[2]); s2[3] = tcx::fma2(w1.y, x2, s2[3]);
-                      }
-                    }
+                  // r = 1, 2, 3 (every stage of the 2-D ... 4-D bench flows) as straight-line code: all loads in flight together, no
+                  // loop / reconvergence bookkeeping (event log: with the run-time loop ONE x term cost ~300 of a round's ~1050
+                  // cycles, mostly branch-resolving and dependent shared-memory latency); deeper stages keep the loop
+                  const float* wb = lc + p.lc_w0x + nb;
+                  auto xterm = [&](int k, const ulonglong2& w0, const ulonglong2& w1, float xq) {
+                    const uint64_t x2 = tcx::pk2(xq, xq);
+                    s2[0] = tcx::fma2(w0.x, x2, s2[0]); s2[1] = tcx::fma2(w0.y, x2, s2[1]);
+                    s2[2] = tcx::fma2(w1.x, x2, s2[2]); s2[3] = tcx::fma2(w1.y, x2, s2[3]);
+                  };
+                  if (r == 1) {
+                    const float x0 = xr[trow];
+                    const ulonglong2* a0 = reinterpret_cast<const ulonglong2*>(wb);
+                    const ulonglong2 w00 = a0[0], w01 = a0[1];
+                    xterm(0, w00, w01, x0);
+                  } else if (r == 2) {
+                    const float x0 = xr[trow], x1 = xr[kTileM + trow];
+                    const ulonglong2* a0 = reinterpret_cast<const ulonglong2*>(wb);
+                    const ulonglong2* a1 = reinterpret_cast<const ulonglong2*>(wb + hp0);
+                    const ulonglong2 w00 = a0[0], w01 = a0[1], w10 = a1[0], w11 = a1[1];
+                    xterm(0, w00, w01, x0);
+                    xterm(1, w10, w11, x1);
+                  } else if (r == 3) {
+                    const float x0 = xr[trow], x1 = xr[kTileM + trow], x2v = xr[2 * kTileM + trow];
+                    const ulonglong2* a0 = reinterpret_cast<const ulonglong2*>(wb);
+                    const ulonglong2* a1 = reinterpret_cast<const ulonglong2*>(wb + hp0);
+                    const ulonglong2* a2 = reinterpret_cast<const ulonglong2*>(wb + 2 * hp0);
+                    const ulonglong2 w00 = a0[0], w01 = a0[1], w10 = a1[0], w11 = a1[1], w20 = a2[0], w21 = a2[1];
+                    xterm(0, w00, w01, x0);
+                    xterm(1, w10, w11, x1);
+                    xterm(2, w20, w21, x2v);
                   } else {
                     for (int k = 0; k < r; ++k) {
-                      const float xq = xr[k * kTileM + trow];
-                      const uint64_t x2 = tcx::pk2(xq, xq);
-                      const ulonglong2* ww = reinterpret_cast<const ulonglong2*>(lc + p.lc_w0x + (size_t)k * hp0 + nb);
+                      const ulonglong2* ww = reinterpret_cast<const ulonglong2*>(wb + (size_t)k * hp0);
                       const ulonglong2 w0 = ww[0], w1 = ww[1];
-                      s2[0] = tcx::fma2(w0.x, x2, s2[0]); s2[1] = tcx::fma2(w0.y, x2, s2[1]);
-                      s2[2] = tcx::fma2(w1.x, x2, s2[2]); s2[3] = tcx::fma2(w1.y, x2, s2[3]);
+                      xterm(k, w0, w1, xr[k * kTileM + trow]);
                     }
                   }
                   tcx::tanh8_scaled(s2, hi4, lo4);
