@@ -1668,27 +1668,30 @@ static cudaError_t launch_inv4(const nazb_handle* h, const TcState* t, const IoA
     const bool dbl = afree && (fold ? P.fold_a_tmem2 : P.a_tmem2);
     const bool defer = dbl && t->opt_defer == 1;
     kp.a_free = (afree && !(dbl && t->opt_defer >= 1)) ? 1 : 0;
+    // <debug, transform kind, A in TMEM, kSplit, per-point context code>: context-folded programs get the instantiation without it
+#define NAZB_V5K(dbg, md, at, sp) (fold ? flow_tc_inv5_kernel<dbg, md, at, sp, false> : flow_tc_inv5_kernel<dbg, md, at, sp, true>)
     if (atm && dbl && t->opt_defer == 2) {
-      kern = flow_tc_inv5_kernel<false, 2, true, 3>;
-      if (mode == 0) kern = flow_tc_inv5_kernel<false, 0, true, 3>;
-      else if (mode == 1) kern = g_tc_dbg ? flow_tc_inv5_kernel<true, 1, true, 3> : flow_tc_inv5_kernel<false, 1, true, 3>;
+      kern = NAZB_V5K(false, 2, true, 3);
+      if (mode == 0) kern = NAZB_V5K(false, 0, true, 3);
+      else if (mode == 1) kern = g_tc_dbg ? NAZB_V5K(true, 1, true, 3) : NAZB_V5K(false, 1, true, 3);
     } else if (atm && defer) {
-      kern = flow_tc_inv5_kernel<false, 2, true, 2>;
-      if (mode == 0) kern = flow_tc_inv5_kernel<false, 0, true, 2>;
-      else if (mode == 1) kern = flow_tc_inv5_kernel<false, 1, true, 2>;
+      kern = NAZB_V5K(false, 2, true, 2);
+      if (mode == 0) kern = NAZB_V5K(false, 0, true, 2);
+      else if (mode == 1) kern = NAZB_V5K(false, 1, true, 2);
     } else if (atm && afree) {
-      kern = flow_tc_inv5_kernel<false, 2, true, 1>;
-      if (mode == 0) kern = flow_tc_inv5_kernel<false, 0, true, 1>;
-      else if (mode == 1) kern = g_tc_dbg ? flow_tc_inv5_kernel<true, 1, true, 1> : flow_tc_inv5_kernel<false, 1, true, 1>;
+      kern = NAZB_V5K(false, 2, true, 1);
+      if (mode == 0) kern = NAZB_V5K(false, 0, true, 1);
+      else if (mode == 1) kern = g_tc_dbg ? NAZB_V5K(true, 1, true, 1) : NAZB_V5K(false, 1, true, 1);
     } else if (atm) {
-      kern = flow_tc_inv5_kernel<false, 2, true>;
-      if (mode == 0) kern = flow_tc_inv5_kernel<false, 0, true>;
-      else if (mode == 1) kern = g_tc_dbg ? flow_tc_inv5_kernel<true, 1, true> : flow_tc_inv5_kernel<false, 1, true>;
+      kern = NAZB_V5K(false, 2, true, 0);
+      if (mode == 0) kern = NAZB_V5K(false, 0, true, 0);
+      else if (mode == 1) kern = g_tc_dbg ? NAZB_V5K(true, 1, true, 0) : NAZB_V5K(false, 1, true, 0);
     } else {
-      kern = flow_tc_inv5_kernel<false, 2, false>;
-      if (mode == 0) kern = flow_tc_inv5_kernel<false, 0, false>;
-      else if (mode == 1) kern = g_tc_dbg ? flow_tc_inv5_kernel<true, 1, false> : flow_tc_inv5_kernel<false, 1, false>;
+      kern = NAZB_V5K(false, 2, false, 0);
+      if (mode == 0) kern = NAZB_V5K(false, 0, false, 0);
+      else if (mode == 1) kern = g_tc_dbg ? NAZB_V5K(true, 1, false, 0) : NAZB_V5K(false, 1, false, 0);
     }
+#undef NAZB_V5K
   } else {
     if (mode == 0) kern = flow_tc_inv4_kernel<false, 0>;
     else if (mode == 1) kern = flow_tc_inv4_kernel<false, 1>;

@@ -43,7 +43,9 @@ constexpr int kDbgEvents = 4096;
 // back until every epilogue warp has finished reading its accumulators (ld_done barrier in the a_free slot): the
 // accumulator reads of the critical path no longer share the TMEM ports with MMAs.  A template parameter, not a runtime
 // flag: the mere presence of the hand-shake code cost 4 % on programs that never use it (81.4 -> 77.8).
-template <bool kDbg, int kMode, bool kATmem, int kSplit = 0>
+// kCtx: the program adds a per-point context in the first-layer phase (false for context-folded programs: their instantiation
+// carries no context code — its presence alone moved the folded cfg3 path by 1.6 %).
+template <bool kDbg, int kMode, bool kATmem, int kSplit = 0, bool kCtx = true>
 __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __grid_constant__ KParamsInv4 p,
                                                                       const __grid_constant__ IoArgs io, int n_groups) {
   // kSplit = 3: double-buffered A, trailing MMAs right behind the critical ones, NO hand-shake: the writers of block k + 2
@@ -315,7 +317,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
     constexpr bool fast_rqs = kMode == 1;
     const bool rows_mine = (sll == 0);             // this warp owns the per-row state of its 16 rows
     const bool owner = rows_mine && (hw == 0);
-    const bool add_ctx = (C > 0) && !p.folded;
+    const bool add_ctx = kCtx && (C > 0) && !p.folded;
     const int pair_id = 1 + q * 2 + rh;            // named barrier of the two warps (slice lanes) sharing these 16 rows
     float* scr = scratch + trow;
     auto raw = [&](int m) { return scr[m * kTileM]; };
@@ -522,14 +524,19 @@ __global__ void __launch_bounds__(kV5Threads, 1) flow_tc_inv5_kernel(const __gri
                     s2[0] = b0.x; s2[1] = b0.y; s2[2] = b1.x; s2[3] = b1.y;
                   }
                   if (add_ctx) {
-                    for (int k = 0; k < C; ++k) {
+                    // per-point context: same treatment as the x terms below (straight-line for C = 2 and C = 4, the bench shapes)
+                    const float* cb = lc + p.lc_w0c + nb;
+                    auto cterm = [&](int k) {
                       const float xc = xin[k * kTileM + trow];
                       const uint64_t x2 = tcx::pk2(xc, xc);
-                      const ulonglong2* ww = reinterpret_cast<const ulonglong2*>(lc + p.lc_w0c + (size_t)k * hp0 + nb);
+                      const ulonglong2* ww = reinterpret_cast<const ulonglong2*>(cb + (size_t)k * hp0);
                       const ulonglong2 w0 = ww[0], w1 = ww[1];
                       s2[0] = tcx::fma2(w0.x, x2, s2[0]); s2[1] = tcx::fma2(w0.y, x2, s2[1]);
                       s2[2] = tcx::fma2(w1.x, x2, s2[2]); s2[3] = tcx::fma2(w1.y, x2, s2[3]);
-                    }
+                    };
+                    if (C == 2) { cterm(0); cterm(1); }
+                    else if (C == 4) { cterm(0); cterm(1); cterm(2); cterm(3); }
+                    else for (int k = 0; k < C; ++k) cterm(k);
                   }
                   // r = 1, 2, 3 (every stage of the 2-D ... 4-D bench flows) as straight-line code: all loads in flight together, no
                   // loop / reconvergence bookkeeping (event log: with the run-time loop ONE x term cost ~300 of a round's ~1050
