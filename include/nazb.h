@@ -188,8 +188,8 @@ int nazb_truncnorm_sample(const float* x, int32_t S, int64_t P, const float* loc
  * HOST arrays with the number of floats between consecutive draws of gW[i] / gb[i] (indexed by the GLOBAL draw s).  The
  * gradient arrays are accumulated into (zero them first).  With nazb_pack_draw_map the gradient with respect to the standard
  * parameters is scale * theta_0 * gW (chain rule on bflow_jax_maf.py:239-240; done by the caller).
- * First cut of the row: NAZB_KIND_AFFINE flows on a handle created with NAZB_ENGINE_SIMT, no dropout keep-masks;
- * anything else returns NAZB_ERR_UNSUPPORTED.  fp32 atomics: the sum over points is not bit-reproducible run to run. */
+ * Covered: NAZB_KIND_AFFINE and NAZB_KIND_RQS (quadratic neural-spline) flows on a handle created with NAZB_ENGINE_SIMT,
+ * no dropout keep-masks, no layer affine; anything else (linear-order splines) returns NAZB_ERR_UNSUPPORTED.  fp32 atomics: the sum over points is not bit-reproducible run to run. */
 int nazb_inverse_grad(nazb_handle* h, int32_t s_begin, int32_t s_count, const float* x, const float* ctx,
                       int32_t ctx_rows, int32_t N, const float* lo, const float* hi, const float* const* mask,
                       float* const* gW, float* const* gb, const int64_t* gwst, const int64_t* gbst, float* dx, float* lp,
@@ -233,10 +233,25 @@ int nazb_hpd(const float* v, int32_t S, int64_t M, double alpha, float* lo, floa
  *   "inv_fold"     1 (default) fold a broadcast context (ctx_rows == 1) into per-draw constants inside nazb_inverse
  *   "inv_gate"     bound the drift of CTAs across draw groups (keeps the weight images L2-resident): 0 off, 2 = no CTA starts
  *                  a group before all finished issuing the previous one, 3 = one group of slack, 1 (default) = by tile count
+ *   "grad_diag" / "grad_tile"  nazb_inverse_grad (any engine): 1 = skip the gradient atomics (timing diagnosis) / 16 = force
+ *                  16-point tiles (default 0: by shared-memory fit)
  * nazb_get_option also answers "inv_fold_available", "inv_kernel_in_use", "inv_a_tmem_in_use", "inv_block_width" and "watchdog" (non-zero after a kernel aborted on a barrier time-out:
  * site | warp << 8 | block << 16).  Unknown names return NAZB_ERR_BAD_ARG, the SIMT engine NAZB_ERR_UNSUPPORTED. */
 int nazb_set_option(nazb_handle* h, const char* name, int32_t value);
+
+/* Element-wise affine after every flow layer, the eval()-mode form of pyro's T.BatchNorm that naz appends with
+ * use_batchnorm=True (src/naz/flows/transforms.py:157-158, :195-196):  sampling direction x <- a[l][d] * x + b[l][d] after
+ * flow layer l, log-det sum_d log a[l][d];  nazb_inverse applies (y - b) / a before inverting layer l.  a, b: HOST fp32
+ * [L][D] (a > 0), copied on `stream`; a == NULL removes the step.  Flows with the step are served by the fp32 SIMT engine in
+ * both directions (call this BEFORE nazb_pack; a handle created with NAZB_ENGINE_TCGEN05 returns NAZB_ERR_UNSUPPORTED) and
+ * have no nazb_inverse_grad. */
+int nazb_set_layer_affine(nazb_handle* h, const float* a, const float* b, void* stream);
 int nazb_get_option(const nazb_handle* h, const char* name, int32_t* value);
+
+/* Test hook, needs no GPU: the device routine behind the neural-spline gradient (naz_b200/csrc/spline_grad.cuh) compiled for
+ * the host.  For spline input x and the 3K-1 raw conditioner outputs of one (point, dimension):  inv_tx = 1 / (dT/dx),
+ * ldx = d log T'(x) / dx,  ca[m] = -(dT/draw_m) / (dT/dx),  cb[m] = -d log T'(x) / draw_m   (quadratic order, [-bound, bound]). */
+int nazb_host_spline_grad(float x, int32_t K, float bound, const float* raw, float* ca, float* cb, float* inv_tx, float* ldx);
 
 const char* nazb_strerror(int status);
 const char* nazb_last_cuda_error(const nazb_handle* h);

@@ -21,7 +21,7 @@ SYMBOLS = [
     "nazb_create", "nazb_destroy", "nazb_engine_in_use", "nazb_engine_for_direction", "nazb_pack", "nazb_inverse", "nazb_forward",
     "nazb_lse_reduce", "nazb_lse_finish", "nazb_importance", "nazb_strerror", "nazb_last_cuda_error",
     "nazb_packed_bytes", "nazb_launch_count", "nazb_histogramdd", "nazb_hpd", "nazb_pack_draw_map", "nazb_truncnorm_sample",
-    "nazb_inverse_grad", "nazb_set_option", "nazb_get_option",
+    "nazb_inverse_grad", "nazb_set_option", "nazb_get_option", "nazb_set_layer_affine", "nazb_host_spline_grad",
 ]
 
 
@@ -104,6 +104,10 @@ def lib() -> C.CDLL:
     L.nazb_inverse_grad.restype = C.c_int
     L.nazb_set_option.argtypes = [vp, C.c_char_p, i32]
     L.nazb_set_option.restype = C.c_int
+    L.nazb_host_spline_grad.argtypes = [f32, i32, f32, vp, vp, vp, vp, vp]
+    L.nazb_host_spline_grad.restype = C.c_int
+    L.nazb_set_layer_affine.argtypes = [vp, vp, vp, vp]
+    L.nazb_set_layer_affine.restype = C.c_int
     L.nazb_get_option.argtypes = [vp, C.c_char_p, C.POINTER(i32)]
     L.nazb_get_option.restype = C.c_int
     L.nazb_launch_count.argtypes = []

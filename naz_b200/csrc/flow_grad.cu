@@ -1,5 +1,5 @@
 // Gradient of the draw-batched log-likelihood  sum_n log p(x_n | c_n; theta_s)  with respect to every weight and bias of
-// draw s (and, optionally, to the points) for masked-affine autoregressive flows — SURVEY §8 row f1: the inner loop of
+// draw s (and, optionally, to the points) for masked-affine AND neural-spline (quadratic) autoregressive flows — SURVEY §8 row f1: the inner loop of
 // the reference's NUTS / SVI / MLE drivers, which call jax.grad / torch autograd on exactly this scalar
 // (src/naz/flows/bflow_jax_maf.py:233-246 log_prob -> :321-327 NUTS, :344-348 SVI, :277-287 MLE;
 //  src/naz/trainers/train_flows.py:195-213).
@@ -16,12 +16,20 @@
 //            c accumulates  dW_j += h_{j-1} (x) delta_j,  db_j += delta_j  over the tile and adds them to the caller's
 //            gradient arrays (reference layout [out][in], masked entries untouched) with fp32 atomics;
 //            g <- lambda * exp(-s) is handed to the next layer.
+// Neural-spline layers (train_flows.py:195-213 differentiates them through pyro's spline): the same recursion with the general
+// form of the cotangent.  A layer is  y_r = T(x_r; p_r(x_<r)),  lp = G(x) - sum_r ld(x_r; p_r),  ld = log dT/dx, hence
+//      lambda = g - d ld/d x + J^T c(lambda),    c_m = lambda_r * ca_m + cb_m,
+//      ca_m = -(dT/dp_m) / (dT/dx)   (= d x_r / d p_m at fixed y),   cb_m = -d ld / d p_m,
+// and  d lp / d y_r = lambda_r / (dT/dx).  ca, cb, 1/(dT/dx) and d ld/dx are evaluated once per layer at the solved x
+// (spline_grad.cuh: forward-mode duals over the six numbers of the selected bin, then the softmax / softplus reverse steps)
+// and kept in shared memory; the affine layer is the special case ca = (-e^-s, -x [clip]), cb = (0, -[clip]).
 // Back-propagation to the input needs the weights transposed: a second image (rows = output units) is produced from
 // the SIMT image once per pack.
 #include <algorithm>
 #include <cstdlib>
 #include "nazb_internal.h"
 #include "transforms.cuh"
+#include "spline_grad.cuh"
 #include "simt_gemm.cuh"
 
 namespace {
@@ -112,29 +120,30 @@ __device__ __forceinline__ void outer_acc(const float* __restrict__ aT, int K, c
 }
 
 // P = 32, TN = 5 (160-column passes), one CTA per SM: the default;  P = 16, TN = 3 (192-column passes): half the state
-template <int P, int NST, int TN>
-__global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_affine_kernel(FlowGeom g, GradGeom gg,
+template <int P, int NST, int TN, bool SPLINE>
+__global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_kernel(FlowGeom g, GradGeom gg,
                                                                      const float* __restrict__ packed,
                                                                      const float* __restrict__ packedT,
                                                                      const int* __restrict__ perm_all, IoArgs io,
                                                                      GradArgs ga) {
   using T = Tile<P, TN>;
   extern __shared__ __align__(16) float smem[];
-  const int D = g.D, C = g.C, nh = g.n_hidden, n_lin = nh + 1;
+  const int D = g.D, C = g.C, nh = g.n_hidden, n_lin = nh + 1, M = g.M;
   const int kin_pad = (g.kin + 3) & ~3, md_pad = (g.md + 3) & ~3;
   float* xin = smem;                                   // [kin_pad][P]  rows: ctx (C), x (D)
   float* gcur = xin + kin_pad * P;                     // [D][P]        phase A: y;  phase B: g = d lp / d x
   float* hbuf = gcur + D * P;                          // [nh][hmax][P]
-  float* obuf = hbuf + (size_t)nh * g.hmax * P;        // [md_pad][P]   (mu, s_raw), rank-major
+  float* obuf = hbuf + (size_t)nh * g.hmax * P;        // [md_pad][P]   conditioner output ((mu, s_raw) / 3K-1 spline slots), rank-major
   float* cbuf = obuf + (size_t)md_pad * P;             // [md_pad][P]   cotangent of the conditioner output
   float* dA = cbuf + (size_t)md_pad * P;               // [hmax][P]     hidden cotangents (ping-pong)
   float* dB = dA + (size_t)g.hmax * P;
   float* dxb = dB + (size_t)g.hmax * P;                // [kin_pad][P]  cotangent of the conditioner input
   float* chain = dxb + kin_pad * P;                    // [L][D][P]     x^(l)
   float* lam = chain + (size_t)g.L * D * P;            // [D][P]
-  float* es = lam + D * P;                             // [D][P]  exp(-s), by rank
-  float* msk = es + D * P;                             // [D][P]  clip indicator, by rank
-  float* ldacc = msk + D * P;                          // [P]
+  float* es = lam + D * P;                             // [D][P]  1 / (dT/dx) = exp(-ld), by rank
+  float* ca = es + D * P;                              // [md_pad][P]  c = lambda * ca + cb  (see the header)
+  float* cb = ca + (size_t)md_pad * P;                 // [md_pad][P]
+  float* ldacc = cb + (size_t)md_pad * P;              // [P]
   float* ljac = ldacc + P;                             // [P]
   // zero bias of the transposed products: they read bias[n] for n < max(hidden widths, kin) (the back-propagation to the
   // conditioner input has kin = C + D output columns, which a wide context can make larger than every hidden layer)
@@ -190,14 +199,24 @@ __global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_affine_
         {
           int K = full ? g.hidden[nh - 1] : g.blk[nh - 1][r + 1];
           gemm_panel_ms<P, false, TN, NST>(hbuf + (size_t)(nh - 1) * g.hmax * P, K, wl + g.off_w[nh], g.ldw[nh], wl + g.off_b[nh],
-                               r * 2, (r + 1) * 2, obuf, wbuf);
+                               r * M, (r + 1) * M, obuf, wbuf);
         }
         if (tid < P) {
           const int p = tid, d = perm[r];
-          float mu = obuf[(r * 2 + 0) * P + p];
-          float s = fminf(fmaxf(obuf[(r * 2 + 1) * P + p], g.clip_lo), g.clip_hi);
-          xin[(C + d) * P + p] = (gcur[d * P + p] - mu) * expf(-s);
-          ldacc[p] += s;
+          if (!SPLINE) {
+            float mu = obuf[(r * 2 + 0) * P + p];
+            float s = fminf(fmaxf(obuf[(r * 2 + 1) * P + p], g.clip_lo), g.clip_hi);
+            xin[(C + d) * P + p] = (gcur[d * P + p] - mu) * expf(-s);
+            ldacc[p] += s;
+          } else {
+            float* o = obuf + (size_t)(r * M) * P + p;
+            auto raw = [&](int m) { return o[m * P]; };
+            auto setw = [&](int m, float v) { o[m * P] = v; };
+            float xv, ld;
+            nazb::rational_spline<false>(gcur[d * P + p], g.K, g.bound, true, raw, setw, xv, ld);
+            xin[(C + d) * P + p] = xv;
+            ldacc[p] += ld;
+          }
         }
         __syncthreads();
       }
@@ -256,32 +275,45 @@ __global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_affine_
       gemm_panel_ms<P, false, TN, NST>(hbuf + (size_t)(nh - 1) * g.hmax * P, g.kdim[nh], wl + g.off_w[nh], g.ldw[nh],
                            wl + g.off_b[nh], 0, g.md, obuf, wbuf);
       for (int i = tid; i < P * D; i += kThreads) {
-        int p = i % P, r = i / P;
-        float sraw = obuf[(r * 2 + 1) * P + p];
-        float s = fminf(fmaxf(sraw, g.clip_lo), g.clip_hi);
-        es[r * P + p] = expf(-s);
-        msk[r * P + p] = (sraw >= g.clip_lo && sraw <= g.clip_hi) ? 1.f : 0.f;
-        lam[i] = gcur[i];
+        const int p = i % P, r = i / P, d = perm[r];
+        const float xv = xin[(C + d) * P + p];
+        float gv = gcur[d * P + p];
+        if (!SPLINE) {
+          const float sraw = obuf[(r * 2 + 1) * P + p];
+          const float s = fminf(fmaxf(sraw, g.clip_lo), g.clip_hi);
+          const float e = expf(-s), mk = (sraw >= g.clip_lo && sraw <= g.clip_hi) ? 1.f : 0.f;
+          es[r * P + p] = e;
+          ca[(r * 2 + 0) * P + p] = -e;      cb[(r * 2 + 0) * P + p] = 0.f;
+          ca[(r * 2 + 1) * P + p] = -xv * mk; cb[(r * 2 + 1) * P + p] = -mk;
+        } else {
+          const float* o = obuf + (size_t)(r * M) * P + p;
+          float* pa = ca + (size_t)(r * M) * P + p;
+          float* pb = cb + (size_t)(r * M) * P + p;
+          float itx, ldx;
+          nazb::rqs_grad(xv, g.K, g.bound, [&](int m) { return o[m * P]; },
+                         [&](int m, float a, float b) { pa[m * P] = a; pb[m * P] = b; }, itx, ldx);
+          es[r * P + p] = itx;
+          gv -= ldx;                         // the direct dependence of ld on x joins g for the rest of this layer
+          gcur[d * P + p] = gv;
+        }
+        lam[d * P + p] = gv;
       }
       __syncthreads();
       for (int it = 0; it < D; ++it) {
         const bool last = (it == D - 1);
-        for (int i = tid; i < P * D; i += kThreads) {
-          int p = i % P, r = i / P;
-          int d = perm[r];
-          float lm = lam[d * P + p];
-          bool valid = p < npts;
-          cbuf[(r * 2 + 0) * P + p] = valid ? -es[r * P + p] * lm : 0.f;
-          cbuf[(r * 2 + 1) * P + p] = valid ? -(1.f + xin[(C + d) * P + p] * lm) * msk[r * P + p] : 0.f;
+        for (int i = tid; i < P * g.md; i += kThreads) {
+          const int p = i % P, row = i / P;
+          const float lm = lam[perm[row / M] * P + p];
+          cbuf[i] = (p < npts) ? fmaf(lm, ca[i], cb[i]) : 0.f;
         }
         __syncthreads();
         if (!last && g.inv_mode == NAZB_INV_INCREMENTAL) {
           // Sweep `it` only has to make rank t = D-2-it exact, from the ranks above it: x of rank t reaches the outputs
           // of ranks > t through the hidden units of blocks > t only (block b = units that depend on ranks < b), so the
-          // back-propagation is restricted to output columns >= 2 (t+1) and hidden units >= blk[.][t+1].
+          // back-propagation is restricted to output columns >= M (t+1) and hidden units >= blk[.][t+1].
           const int t = D - 2 - it, r1 = t + 1, dt = perm[t];
-          const float* src = cbuf + (size_t)(r1 * 2) * P;
-          int ksrc = g.md - r1 * 2, woff = r1 * 2;
+          const float* src = cbuf + (size_t)(r1 * M) * P;
+          int ksrc = g.md - r1 * M, woff = r1 * M;
           for (int j = nh; j >= 1 && ksrc > 0; --j) {
             float* dst = ((nh - j) & 1) ? dB : dA;
             const int c0 = g.blk[j - 1][r1];
@@ -306,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_affine_
         const int to = l * n_lin + nh;
         if (last)
           outer_acc<P>(hbuf + (size_t)(nh - 1) * g.hmax * P, g.kdim[nh], cbuf, g.md, ga.mask[to],
-                       ga.gW[to] + (size_t)sg * ga.gwst[to], ga.gb[to] + (size_t)sg * ga.gbst[to], perm, 2, D, true, ga.diag);
+                       ga.gW[to] + (size_t)sg * ga.gwst[to], ga.gb[to] + (size_t)sg * ga.gbst[to], perm, M, D, true, ga.diag);
         const float* src = cbuf;
         for (int j = nh; j >= 1; --j) {
           float* dst = ((nh - j) & 1) ? dB : dA;
@@ -318,7 +350,7 @@ __global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_affine_
           if (last) {
             const int ti = l * n_lin + (j - 1);
             outer_acc<P>((j - 1 == 0) ? xin : hbuf + (size_t)(j - 2) * g.hmax * P, g.kdim[j - 1], dst, g.ndim[j - 1],
-                         ga.mask[ti], ga.gW[ti] + (size_t)sg * ga.gwst[ti], ga.gb[ti] + (size_t)sg * ga.gbst[ti], perm, 2, D,
+                         ga.mask[ti], ga.gW[ti] + (size_t)sg * ga.gwst[ti], ga.gb[ti] + (size_t)sg * ga.gbst[ti], perm, M, D,
                          false, ga.diag);
           }
           src = dst;
@@ -332,7 +364,7 @@ __global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_affine_
         }
         __syncthreads();
       }
-      // g of the next layer: d lp / d y = lambda * exp(-s)
+      // g of the next layer: d lp / d y = lambda / (dT/dx)
       for (int i = tid; i < P * D; i += kThreads) {
         int p = i % P, r = i / P;
         int d = perm[r];
@@ -360,8 +392,8 @@ __global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_affine_
 
 size_t grad_smem_bytes(const FlowGeom& g, int P, int nst, int tn) {
   const int kin_pad = (g.kin + 3) & ~3, md_pad = (g.md + 3) & ~3;
-  size_t f = (size_t)2 * kin_pad * P + (size_t)4 * g.D * P + (size_t)(g.n_hidden + 2) * g.hmax * P +
-             (size_t)2 * md_pad * P + (size_t)g.L * g.D * P + 2 * P + (size_t)((g.hmax > kin_pad) ? g.hmax : kin_pad);
+  size_t f = (size_t)2 * kin_pad * P + (size_t)3 * g.D * P + (size_t)(g.n_hidden + 2) * g.hmax * P +
+             (size_t)4 * md_pad * P + (size_t)g.L * g.D * P + 2 * P + (size_t)((g.hmax > kin_pad) ? g.hmax : kin_pad);
   int TR = P / 4, TC = kThreads / TR, NPASS = TC * tn;
   f += (size_t)nst * kKC * NPASS;
   f += 2 * (kThreads / 32) + 4;
@@ -411,7 +443,7 @@ cudaError_t nazb_grad_launch(nazb_handle* h, const IoArgs& io, const void* tabs,
   ga.gwst = reinterpret_cast<const long long*>(t + sizeof(void*) * 3 * n);
   ga.gbst = reinterpret_cast<const long long*>(t + sizeof(void*) * 4 * n);
   ga.dx = dx;
-  ga.diag = (getenv("NAZB_GRAD_DIAG") && atoi(getenv("NAZB_GRAD_DIAG"))) ? 1 : 0;
+  ga.diag = h->opt_grad_diag;
   // Measured (maf 2|2, 4 chains x 100 k points): one 32-point CTA per SM 245 ms, two 16-point CTAs per SM 274 ms — the
   // shared-memory wavefronts per point double with the smaller tile — so 16-point tiles only serve shapes whose 32-point
   // state does not fit.  The 4-deep weight ring costs nothing at one CTA per SM and is dropped first.
@@ -419,17 +451,20 @@ cudaError_t nazb_grad_launch(nazb_handle* h, const IoArgs& io, const void* tabs,
   int P = 32, nst = 4;
   if (grad_smem_bytes(g, 32, 4, 5) > cap) nst = 2;
   if (grad_smem_bytes(g, 32, nst, 5) > cap) P = 16;
-  if (const char* env = getenv("NAZB_GRAD_P")) { if (atoi(env) == 16) P = 16; }
+  if (h->opt_grad_tile == 16) P = 16;
   const size_t smem = (P == 16) ? grad_smem_bytes(g, 16, 2, 3) : grad_smem_bytes(g, 32, nst, 5);
   if (smem > cap) return cudaErrorInvalidConfiguration;
   const int tiles = (io.N + P - 1) / P;
   dim3 grid(tiles, std::min(io.s_count, 65535));
-#define NAZB_GRAD_LAUNCH(PP, NS, TT)                                                                                   \
-  e = cudaFuncSetAttribute(flow_grad_affine_kernel<PP, NS, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-  if (e != cudaSuccess) return e;                                                                                      \
-  flow_grad_affine_kernel<PP, NS, TT><<<grid, kThreads, smem, st>>>(g, gg, h->packed, h->packed_T, h->perm_dev, io, ga);
+#define NAZB_GRAD_LAUNCH_K(PP, NS, TT, SP)                                                                                 \
+  e = cudaFuncSetAttribute(flow_grad_kernel<PP, NS, TT, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+  if (e != cudaSuccess) return e;                                                                                          \
+  flow_grad_kernel<PP, NS, TT, SP><<<grid, kThreads, smem, st>>>(g, gg, h->packed, h->packed_T, h->perm_dev, io, ga);
+#define NAZB_GRAD_LAUNCH(PP, NS, TT)                                                                                       \
+  if (g.kind == NAZB_KIND_AFFINE) { NAZB_GRAD_LAUNCH_K(PP, NS, TT, false) } else { NAZB_GRAD_LAUNCH_K(PP, NS, TT, true) }
   if (P == 16) { NAZB_GRAD_LAUNCH(16, 2, 3) } else if (nst == 4) { NAZB_GRAD_LAUNCH(32, 4, 5) } else { NAZB_GRAD_LAUNCH(32, 2, 5) }
 #undef NAZB_GRAD_LAUNCH
+#undef NAZB_GRAD_LAUNCH_K
   nazb_count_launch();
   return cudaGetLastError();
 }

@@ -79,6 +79,16 @@ __global__ void __launch_bounds__(kThreads) flow_simt_kernel(FlowGeom g, const f
       const float* wl = wdraw + (size_t)l * g.layer_stride;
       const int* perm = perm_all + l * D;
       const int nstage = inverse ? D : 1;
+      const float* af = io.aff ? io.aff + (size_t)l * (2 * D + 1) : nullptr;
+      if (inverse && af) {
+        // eval-mode BatchNorm behind flow layer l (nazb_set_layer_affine): undo y = a x + b before inverting the layer
+        for (int i = tid; i < P * D; i += kThreads) {
+          int d = i / P;
+          ycur[i] = (ycur[i] - af[D + d]) / af[d];
+        }
+        if (tid < P) ldacc[tid] += af[2 * D];
+        __syncthreads();
+      }
       for (int r = 0; r < nstage; ++r) {
         const bool full = !inverse || g.inv_mode == NAZB_INV_JACOBI;
         // ---- conditioner ----
@@ -181,6 +191,14 @@ __global__ void __launch_bounds__(kThreads) flow_simt_kernel(FlowGeom g, const f
           }
           __syncthreads();
         }
+      }
+      if (!inverse && af) {
+        for (int i = tid; i < P * D; i += kThreads) {
+          int d = i / P;
+          xin[(size_t)C * P + i] = fmaf(af[d], xin[(size_t)C * P + i], af[D + d]);
+        }
+        if (tid < P) ldacc[tid] += af[2 * D];
+        __syncthreads();
       }
       if (inverse) {
         // x of this layer becomes y of the next (earlier) layer; x restarts from zero

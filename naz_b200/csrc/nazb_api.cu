@@ -1,12 +1,14 @@
 // C-ABI glue of libnazb.so (see include/nazb.h for the contract and the reference mapping).
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
 #include "nazb_internal.h"
+#include "spline_grad.cuh"
 
 static std::atomic<long long> g_launches{0};
 void nazb_count_launch(int n) { g_launches += n; }
@@ -123,6 +125,7 @@ extern "C" void nazb_destroy(nazb_handle* h) {
   if (h->packed_T) cudaFree(h->packed_T);
   if (h->grad_tabs) cudaFree(h->grad_tabs);
   if (h->perm_dev) cudaFree(h->perm_dev);
+  if (h->aff_dev) cudaFree(h->aff_dev);
   if (h->stage_host) cudaFreeHost(h->stage_host);
   if (h->stage_ev) cudaEventDestroy((cudaEvent_t)h->stage_ev);
   delete h;
@@ -136,7 +139,7 @@ int nazb_tc_rows_per_item(const nazb_handle* h, int dir);
 // Engine that serves one direction (0 = inverse / log_prob, 1 = forward / sample) after nazb_pack.
 extern "C" int nazb_engine_for_direction(const nazb_handle* h, int dir) {
   if (!h || dir < 0 || dir > 1) return NAZB_ERR_BAD_ARG;
-  if (h->engine == NAZB_ENGINE_TCGEN05 && nazb_tc_direction_ok(h, dir)) return NAZB_ENGINE_TCGEN05;
+  if (h->engine == NAZB_ENGINE_TCGEN05 && !h->aff_dev && nazb_tc_direction_ok(h, dir)) return NAZB_ENGINE_TCGEN05;
   return NAZB_ENGINE_SIMT;
 }
 
@@ -148,11 +151,15 @@ unsigned int nazb_tc_watchdog(const nazb_handle* h);
 // reads the environment).  Options that change the packed program ("inv_kernel", "inv_merge_n") require a new nazb_pack.
 extern "C" int nazb_set_option(nazb_handle* h, const char* name, int32_t value) {
   if (!h || !name) return NAZB_ERR_BAD_ARG;
+  if (!strcmp(name, "grad_diag")) { h->opt_grad_diag = value ? 1 : 0; return NAZB_OK; }
+  if (!strcmp(name, "grad_tile")) { if (value != 0 && value != 16 && value != 32) return NAZB_ERR_BAD_ARG; h->opt_grad_tile = value; return NAZB_OK; }
   if (h->engine != NAZB_ENGINE_TCGEN05) return NAZB_ERR_UNSUPPORTED;
   return nazb_tc_set_option(h, name, value);
 }
 extern "C" int nazb_get_option(const nazb_handle* h, const char* name, int32_t* value) {
   if (!h || !name || !value) return NAZB_ERR_BAD_ARG;
+  if (!strcmp(name, "grad_diag")) { *value = h->opt_grad_diag; return NAZB_OK; }
+  if (!strcmp(name, "grad_tile")) { *value = h->opt_grad_tile; return NAZB_OK; }
   if (!strcmp(name, "watchdog")) { *value = (h->engine == NAZB_ENGINE_TCGEN05) ? (int32_t)nazb_tc_watchdog(h) : 0; return NAZB_OK; }
   if (h->engine != NAZB_ENGINE_TCGEN05) return NAZB_ERR_UNSUPPORTED;
   int v = 0;
@@ -251,7 +258,7 @@ static int pack_impl(nazb_handle* h, const float* const* W, const float* const* 
     e = nazb_tc_pack(h, W, b, wst, bst, mask, keep, p_drop, st, dm);
     CK(h, e);
     // a direction the tensor-core programs cannot hold (TMEM budget) is served by the SIMT engine
-    need_simt = !nazb_tc_direction_ok(h, 0) || !nazb_tc_direction_ok(h, 1);
+    need_simt = h->aff_dev != nullptr || !nazb_tc_direction_ok(h, 0) || !nazb_tc_direction_ok(h, 1);
     if (need_simt && h->desc.engine == NAZB_ENGINE_TCGEN05) return NAZB_ERR_UNSUPPORTED;
     if (need_simt && nazb_simt_pick_P(h->geom) == 0) return NAZB_ERR_UNSUPPORTED;
   }
@@ -285,6 +292,49 @@ extern "C" int nazb_pack_draw_map(nazb_handle* h, const float* const* W0, const 
   DrawMap dm;
   dm.baseW = W0; dm.baseB = b0; dm.scale = scale;
   return pack_impl(h, uW, ub, uwst, ubst, mask, perm, hid_deg, keep, p_drop, stream, dm);
+}
+
+namespace {
+struct HostRaw { const float* r; __host__ __device__ float operator()(int m) const { return r[m]; } };
+struct HostPut { float* a; float* b; __host__ __device__ void operator()(int m, float x, float y) const { a[m] = x; b[m] = y; } };
+}  // namespace
+extern "C" int nazb_host_spline_grad(float x, int32_t K, float bound, const float* raw, float* ca, float* cb, float* inv_tx,
+                                     float* ldx) {
+  if (!raw || !ca || !cb || !inv_tx || !ldx || K < 2 || K > 64) return NAZB_ERR_BAD_ARG;
+  nazb::rqs_grad(x, K, bound, HostRaw{raw}, HostPut{ca, cb}, *inv_tx, *ldx);
+  return NAZB_OK;
+}
+
+// BatchNorm (eval mode) as a per-layer element-wise affine; see include/nazb.h.
+extern "C" int nazb_set_layer_affine(nazb_handle* h, const float* a, const float* b, void* stream) {
+  if (!h) return NAZB_ERR_BAD_ARG;
+  CK(h, cudaSetDevice(h->device));
+  if (!a) {
+    if (h->aff_dev) { CK(h, cudaStreamSynchronize((cudaStream_t)stream)); cudaFree(h->aff_dev); h->aff_dev = nullptr; }
+    return NAZB_OK;
+  }
+  if (!b) return NAZB_ERR_BAD_ARG;
+  if (h->desc.engine == NAZB_ENGINE_TCGEN05) return NAZB_ERR_UNSUPPORTED;
+  const int D = h->geom.D, L = h->geom.L, row = 2 * D + 1;
+  std::vector<float> tab((size_t)L * row);
+  for (int l = 0; l < L; ++l) {
+    double ls = 0.0;
+    for (int d = 0; d < D; ++d) {
+      const float av = a[(size_t)l * D + d];
+      if (!(av > 0.f) || !std::isfinite(av) || !std::isfinite(b[(size_t)l * D + d])) return NAZB_ERR_BAD_ARG;
+      tab[(size_t)l * row + d] = av;
+      tab[(size_t)l * row + D + d] = b[(size_t)l * D + d];
+      ls += std::log((double)av);
+    }
+    tab[(size_t)l * row + 2 * D] = (float)ls;
+  }
+  if (!h->aff_dev) {
+    CK(h, cudaMalloc(&h->aff_dev, sizeof(float) * tab.size()));
+    if (h->engine == NAZB_ENGINE_TCGEN05) h->is_packed = false;   // the SIMT image is built by the next nazb_pack
+  }
+  // pageable source: the runtime stages the bytes before returning
+  CK(h, cudaMemcpyAsync(h->aff_dev, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return NAZB_OK;
 }
 
 static int check_io(const nazb_handle* h, int s_begin, int s_count, const void* x, const float* ctx, int ctx_rows,
@@ -347,7 +397,7 @@ extern "C" int nazb_inverse(nazb_handle* h, int32_t s_begin, int32_t s_count, co
   io.x = x; io.x_draw_stride = 0; io.ctx = ctx; io.ctx_rows = ctx_rows; io.N = N;
   io.s_begin = s_begin; io.s_count = s_count; io.lo = lo; io.hi = hi;
   io.out_x = z; io.out_l = lp; io.log_w = log_w; io.lse_max = lse_max; io.lse_sum = lse_sum; io.sum_n = sum_n;
-  io.dir = 0;
+  io.dir = 0; io.aff = h->aff_dev;
   const int rows_inv = (nazb_engine_for_direction(h, 0) == NAZB_ENGINE_TCGEN05) ? 128 : 64;
   int G = pick_groups(h, N, s_count, lse_max ? n_groups : 0, rows_inv);
   cudaError_t e = (nazb_engine_for_direction(h, 0) == NAZB_ENGINE_TCGEN05)
@@ -367,7 +417,7 @@ extern "C" int nazb_forward(nazb_handle* h, int32_t s_begin, int32_t s_count, co
   IoArgs io{};
   io.x = z; io.x_draw_stride = z_shared ? 0 : (long long)N * h->geom.D; io.ctx = ctx; io.ctx_rows = ctx_rows; io.N = N;
   io.s_begin = s_begin; io.s_count = s_count; io.lo = lo; io.hi = hi;
-  io.out_x = x; io.out_l = logdet; io.dir = 1;
+  io.out_x = x; io.out_l = logdet; io.dir = 1; io.aff = h->aff_dev;
   const int rows_fwd = (nazb_engine_for_direction(h, 1) == NAZB_ENGINE_TCGEN05) ? nazb_tc_rows_per_item(h, 1) : 64;
   int G = pick_groups(h, N, s_count, 0, rows_fwd);
   cudaError_t e = (nazb_engine_for_direction(h, 1) == NAZB_ENGINE_TCGEN05)
@@ -387,8 +437,8 @@ extern "C" int nazb_inverse_grad(nazb_handle* h, int32_t s_begin, int32_t s_coun
   if (rc != NAZB_OK) return rc;
   if (!mask || !gW || !gb || !gwst || !gbst) return NAZB_ERR_BAD_ARG;
   const FlowGeom& g = h->geom;
-  // first cut of the row: masked-affine flows on the fp32 engine's image, no dropout
-  if (g.kind != NAZB_KIND_AFFINE || h->engine != NAZB_ENGINE_SIMT || !h->packed || h->has_keep || !nazb_grad_fits(g))
+  // masked-affine and quadratic neural-spline flows on the fp32 engine's image, no dropout
+  if ((g.kind != NAZB_KIND_AFFINE && g.kind != NAZB_KIND_RQS) || h->engine != NAZB_ENGINE_SIMT || !h->packed || h->has_keep || h->aff_dev || !nazb_grad_fits(g))
     return NAZB_ERR_UNSUPPORTED;
   const int n = g.L * (g.n_hidden + 1);
   for (int i = 0; i < n; ++i)

@@ -47,6 +47,7 @@ struct IoArgs {
   float* lse_sum;
   double* sum_n;           // [s_count] or null
   int dir;                 // 0 = inverse (log_prob direction), 1 = forward (sample direction)
+  const float* aff;        // per-layer affine table [L][2 D + 1] (a[D], b[D], sum log a) or null  (nazb_set_layer_affine)
 };
 
 // Draw map of the Bayesian flow (src/naz/flows/bflow_jax_maf.py:239-240):  theta_s = theta_0 * (1 + scale * u_s)  in fp32,
@@ -71,10 +72,13 @@ struct nazb_handle {
   int* perm_dev = nullptr;  // [L][D] int32
   bool is_packed = false;
   bool has_keep = false;    // dropout keep-masks were folded in at pack time
+  float* aff_dev = nullptr; // [L][2 D + 1] per-layer affine (BatchNorm in eval mode) or null; SIMT engine only
   // gradient engine (flow_grad.cu): transposed copy of the SIMT image, device tables of the caller's gradient arrays
   float* packed_T = nullptr;
   bool packed_T_valid = false;
   void* grad_tabs = nullptr;
+  int opt_grad_diag = 0;    // nazb_set_option "grad_diag": 1 = skip the gradient atomics (timing diagnosis only)
+  int opt_grad_tile = 0;    // nazb_set_option "grad_tile": 16 = force 16-point tiles (0 = by shared-memory fit)
   std::string cuda_err;
   // pinned staging buffer for the small host tables of nazb_pack (async upload on the caller's stream)
   void* stage_host = nullptr;

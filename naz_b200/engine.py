@@ -152,8 +152,8 @@ class FlowEngine:
             FlowEngine._warned_shapes.add(key)
             import warnings
             warnings.warn(f"naz_b200: the {' and '.join(slow)} direction of this {self.shape.kind} flow (D={self.shape.D}, C={self.shape.C}, "
-                          f"hidden={list(self.shape.hidden)}) does not fit the tcgen05 programs (tensor-memory budget) and runs on the "
-                          "fp32 SIMT kernel; FlowEngine.engine_for(direction) reports the engine per direction", RuntimeWarning, stacklevel=3)
+                          f"hidden={list(self.shape.hidden)}) does not fit the tcgen05 programs (tensor-memory budget) or carries a per-layer "
+                          "affine (BatchNorm), and runs on the fp32 SIMT kernel; FlowEngine.engine_for(direction) reports the engine per direction", RuntimeWarning, stacklevel=3)
 
     # engine options (include/nazb.h: nazb_set_option); nothing in the library reads the environment
     OPTION_NAMES = ("inv_kernel", "inv_merge_n", "inv_fold", "inv_gate", "inv_a_tmem", "inv_align", "inv_trim", "inv_defer", "inv_park")
@@ -177,6 +177,21 @@ class FlowEngine:
 
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
+
+    def set_layer_affine(self, a: Optional[torch.Tensor], b: Optional[torch.Tensor] = None) -> None:
+        """Element-wise affine behind every flow layer (eval-mode `T.BatchNorm`, transforms.py:157-158): sampling direction
+        x <- a[l] * x + b[l] after layer l.  a, b: [L, D], a > 0; None removes the step.  Call before pack(): such flows are
+        served by the SIMT kernel in both directions (include/nazb.h `nazb_set_layer_affine`)."""
+        if a is None:
+            self._check(self._lib.nazb_set_layer_affine(self._h, None, None, self._stream()), "nazb_set_layer_affine")
+            return
+        sh = self.shape
+        a_h = torch.as_tensor(a).detach().to("cpu", torch.float32).contiguous()
+        b_h = torch.as_tensor(b).detach().to("cpu", torch.float32).contiguous()
+        if tuple(a_h.shape) != (sh.L, sh.D) or tuple(b_h.shape) != (sh.L, sh.D):
+            raise ValueError(f"layer affine must be [L={sh.L}, D={sh.D}]")
+        self._check(self._lib.nazb_set_layer_affine(self._h, a_h.data_ptr(), b_h.data_ptr(), self._stream()),
+                    "nazb_set_layer_affine")
 
     # ------------------------------------------------------------------
     def pack_draw_map(self, base, standard_params: torch.Tensor, scale, masks, perms,
@@ -420,7 +435,7 @@ class FlowEngine:
         jax.value_and_grad / autograd of bflow_jax_maf.py:233-235).  Returns {"sum_n": [s_count] float64,
         "gW": [L][n_lin] of [S,out,in], "gb": [L][n_lin] of [S,out], "dx": [s_count,N,D], "lp": [s_count,N]};
         rows of gW / gb outside [s_begin, s_begin+s_count) stay zero.  Needs a handle created with engine="simt"
-        holding a masked-affine flow (nazb_inverse_grad returns "unsupported" otherwise)."""
+        holding a masked-affine or quadratic neural-spline flow (nazb_inverse_grad returns "unsupported" otherwise)."""
         sh = self.shape
         if self._keepalive is None:
             raise RuntimeError("inverse_grad: pack() has not been called on this engine")

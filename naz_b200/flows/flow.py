@@ -33,10 +33,97 @@ class _FlowDist:
         return self
 
 
-def draws_from_posterior_samples(posterior_samples: Dict[str, torch.Tensor], L: int, n_lin: int):
-    """Reference format `"flow_{i}_{name}" -> tensor[S, ...]` (train_flows.py:71, bflow.py:72) -> pytree."""
+def draws_from_posterior_samples(posterior_samples: Dict[str, torch.Tensor], L, n_lin: int):
+    """Reference format `"flow_{i}_{name}" -> tensor[S, ...]` (train_flows.py:71, bflow.py:72) -> pytree.  `L` is the number
+    of flow layers or, when Permute / BatchNorm transforms sit between them, the positions of the autoregressive
+    transforms in `flow_dist.transforms` (the reference's `i` enumerates every transform)."""
+    pos = range(L) if isinstance(L, int) else L
     return [[(posterior_samples[f"flow_{i}_nn.layers.{j}.weight"], posterior_samples[f"flow_{i}_nn.layers.{j}.bias"])
-             for j in range(n_lin)] for i in range(L)]
+             for j in range(n_lin)] for i in pos]
+
+
+class Relabelling:
+    """`T.Permute` layers (transforms.py:155-156) cost nothing at run time: a permutation between two autoregressive layers is
+    a re-labelling of the variables, so it is folded into the conditioner weights when they are packed.  With q the running
+    map "actual index k of the reference <-> engine index q[k]" (identity before the first layer), an autoregressive layer
+    becomes one on engine variables by moving its input columns (`W0'[:, C + q[k]] = W0[:, C + k]`), its output rows
+    (`Wout'[m D + q[k]] = Wout[m D + k]`) and its MADE order (`perm' = q[perm]`); a Permute p then maps q <- q[p].  The
+    eval-mode BatchNorm scale / shift behind layer l are re-labelled the same way.  At the ends: log_prob feeds
+    `x[..., argsort(q_final)]` (and bounds in that order), sample returns `e[..., q_final]`."""
+
+    def __init__(self, transforms, D: int):
+        q = torch.arange(D)
+        self.D = D
+        self.ar_pos, self.q, self.bn = [], [], []
+        for i, t in enumerate(transforms):
+            kind = getattr(t, "kind", None)
+            if kind in ("maf", "nsa"):
+                self.ar_pos.append(i); self.q.append(q.clone()); self.bn.append(None)
+            elif kind == "permute":
+                q = q[t.permutation.cpu()]
+            elif kind == "batchnorm":
+                if not self.ar_pos or self.bn[-1] is not None:
+                    raise NotImplementedError("BatchNorm is supported directly behind an autoregressive layer (transforms.py:157)")
+                self.bn[-1] = (t, q.clone())
+            else:
+                raise NotImplementedError(f"transform {type(t).__name__} is not part of naz's discrete flows")
+        self.q_final = q
+        self.inv_final = torch.argsort(q)
+        self.trivial = all(torch.equal(qi, torch.arange(D)) for qi in self.q + [q])
+        self.has_bn = any(b is not None for b in self.bn)
+
+    def fold_layer(self, l: int, lins, C: int):
+        """lins: [n_lin] of tensors or (W, b) pairs of flow layer l whose LAST two axes are [out, in] / last axis [out]
+        (weights, masks alike; leading draw axes pass through)."""
+        if self.trivial:
+            return lins
+        D, invq = self.D, torch.argsort(self.q[l])
+        out = list(lins)
+
+        def cols(W):
+            idx = torch.cat([torch.arange(C), C + invq]).to(W.device)
+            return W.index_select(-1, idx)
+
+        def rows(T, axis):
+            M = T.shape[axis] // D
+            idx = torch.cat([m * D + invq for m in range(M)]).to(T.device)
+            return T.index_select(axis, idx)
+
+        first, last = out[0], out[-1]
+        out[0] = (cols(first[0]), first[1]) if isinstance(first, tuple) else cols(first)
+        last = out[-1]
+        out[-1] = (rows(last[0], -2), rows(last[1], -1)) if isinstance(last, tuple) else rows(last, -2)
+        return out
+
+    def fold_perm(self, l: int, perm):
+        return self.q[l][perm.cpu().to(torch.int64)]
+
+    def layer_affine(self):
+        """(a, b) [L, D] in engine order, identity rows where a layer has no BatchNorm."""
+        L = len(self.ar_pos)
+        a, b = torch.ones(L, self.D), torch.zeros(L, self.D)
+        for l, ent in enumerate(self.bn):
+            if ent is not None:
+                bn, q = ent
+                al, bl = bn.affine()
+                inv = torch.argsort(q)
+                a[l], b[l] = al.cpu()[inv], bl.cpu()[inv]
+        return a, b
+
+    def to_engine(self, x):
+        return x if self.trivial else x.index_select(-1, self.inv_final.to(x.device))
+
+    def from_engine(self, e):
+        return e if self.trivial else e.index_select(-1, self.q_final.to(e.device))
+
+    def bounds_to_engine(self, bounds):
+        if bounds is None or self.trivial:
+            return bounds
+        lo = torch.as_tensor(bounds["low"] if isinstance(bounds, dict) else bounds[0]).reshape(-1)
+        hi = torch.as_tensor(bounds["high"] if isinstance(bounds, dict) else bounds[1]).reshape(-1)
+        if lo.numel() == 1:
+            return {"low": lo, "high": hi}
+        return {"low": lo[self.inv_final.to(lo.device)], "high": hi[self.inv_final.to(hi.device)]}
 
 
 class NormalizingFlow(nn.Module):
@@ -56,6 +143,7 @@ class NormalizingFlow(nn.Module):
         self.flow, self.transforms, self.nets = flow_maker(*flow_maker_args, **flow_maker_kwargs)
         self.base_dist = torch.distributions.Normal(torch.zeros(self.theta_dim), torch.ones(self.theta_dim))
         self.flow_dist = _FlowDist(self.base_dist, self.transforms)
+        self.relabel = Relabelling(self.transforms, self.theta_dim)
         hidden = self.nets[0].hidden_dims
         order = flow_maker_kwargs.get("order", "quadratic")
         count_bins = 8
@@ -78,6 +166,28 @@ class NormalizingFlow(nn.Module):
     def current_draw(self):
         return [[(lin.weight.detach(), lin.bias.detach()) for lin in arn.layers] for arn in self.nets]
 
+    def _packed_masks(self):
+        """Masks / MADE orders as the engine packs them, i.e. with the Permute layers folded in (`Relabelling`)."""
+        return [self.relabel.fold_layer(l, ml, self.condition_dim) for l, ml in enumerate(self.masks())]
+
+    def _packed_perms(self):
+        return torch.stack([self.relabel.fold_perm(l, arn.permutation) for l, arn in enumerate(self.nets)])
+
+    def _fold_draws(self, draws):
+        if self.relabel.trivial:
+            return draws
+        return [self.relabel.fold_layer(l, [(torch.as_tensor(W), torch.as_tensor(b)) for (W, b) in layer], self.condition_dim)
+                for l, layer in enumerate(draws)]
+
+    def _new_engine(self, S: int, dev) -> FlowEngine:
+        eng = FlowEngine(self.shape, S, device=dev, engine=self._engine_kind)
+        if self.relabel.has_bn:
+            if self.training:
+                raise RuntimeError("BatchNorm flows are evaluated with their moving statistics: call flow.eval() first (the "
+                                   "train()-mode batch statistics belong to the training loop, which is out of scope)")
+            eng.set_layer_affine(*self.relabel.layer_affine())
+        return eng
+
     def _device(self):
         p = next(self.parameters())
         if p.device.type != "cuda":
@@ -87,11 +197,11 @@ class NormalizingFlow(nn.Module):
     def _single_engine(self) -> FlowEngine:
         """Engine holding the module's current parameters (S = 1), re-packed when they change."""
         dev = self._device()
-        key = (dev,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+        key = (dev, self.training) + tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
         if self._eng1 is None or self._eng1_key != key:
-            if self._eng1 is None or self._eng1.device != dev:
-                self._eng1 = FlowEngine(self.shape, 1, device=dev, engine=self._engine_kind)
-            self._eng1.pack(self.current_draw(), self.masks(), self.perms())
+            if self._eng1 is None or self._eng1.device != dev or self.relabel.has_bn:
+                self._eng1 = self._new_engine(1, dev)
+            self._eng1.pack(self._fold_draws(self.current_draw()), self._packed_masks(), self._packed_perms())
             self._eng1_key = key
         return self._eng1
 
@@ -99,7 +209,8 @@ class NormalizingFlow(nn.Module):
         """Engine holding S draws given as the reference pytree `[L][n_lin](W[S,out,in], b[S,out])`
         or as the `"flow_{i}_{name}"` dict."""
         if isinstance(draws, dict):
-            draws = draws_from_posterior_samples(draws, len(self.nets), len(self.nets[0].layers))
+            draws = draws_from_posterior_samples(draws, self.relabel.ar_pos, len(self.nets[0].layers))
+        draws = self._fold_draws(draws)
         S = 1
         for layer in draws:
             for (W, b) in layer:
@@ -107,9 +218,12 @@ class NormalizingFlow(nn.Module):
                     S = W.shape[0]
         if keep is not None:
             S = keep.shape[0]
-        eng = FlowEngine(self.shape, S, device=device or self._device(), engine=self._engine_kind)
-        eng.pack(draws, self.masks(), self.perms(), keep, p_drop)
+        eng = self._new_engine(S, device or self._device())
+        eng.pack(draws, self._packed_masks(), self._packed_perms(), keep, p_drop)
         return eng
+
+    def _bounds_e(self):
+        return self.relabel.bounds_to_engine(self.bounds)
 
     def _cond(self, condition):
         if self.conditional:
@@ -127,7 +241,7 @@ class NormalizingFlow(nn.Module):
             raise RuntimeError("log_prob on a dropout flow in train() mode: call flow.eval() for the deterministic density, or "
                                "log_prob_draws(..., keep=masks, p_drop=p) for explicit MC-dropout masks")
         eng = self._single_engine()
-        out = eng.inverse(x, self._cond(condition), self.bounds, want_lp=True)
+        out = eng.inverse(self.relabel.to_engine(x), self._cond(condition), self._bounds_e(), want_lp=True)
         return out["lp"][0]
 
     def bounded_log_prob(self, x, *args, condition=None, **kwargs):
@@ -160,7 +274,7 @@ class NormalizingFlow(nn.Module):
             assert shape is not None, "sample shape required"
             n = int(torch.Size(shape).numel())
             base_noise = torch.randn((n, self.theta_dim), device=eng.device)
-        x = eng.forward(base_noise.reshape(-1, self.theta_dim), self._cond(condition), self.bounds)[0]
+        x = self.relabel.from_engine(eng.forward(base_noise.reshape(-1, self.theta_dim), self._cond(condition), self._bounds_e())[0])
         return x.reshape(*(shape if shape is not None else [x.shape[0]]), self.theta_dim)
 
     # ------------------------------------------------------------------ draw-batched entry points
@@ -170,13 +284,14 @@ class NormalizingFlow(nn.Module):
         log (1/S) sum_s p(x_n|theta_s) [N] (or weighted by log_w); "sum" -> sum_n lp[s,n] [S] (float64)."""
         eng = engine or self.make_engine(draws, keep, p_drop)
         cond = self._cond(condition)
+        x, bounds = self.relabel.to_engine(torch.as_tensor(x)), self._bounds_e()
         if reduce is None:
-            return eng.inverse(x, cond, self.bounds, want_lp=True)["lp"]
+            return eng.inverse(x, cond, bounds, want_lp=True)["lp"]
         if reduce == "lse":
-            out = eng.inverse(x, cond, self.bounds, want_lp=False, want_lse=True, log_w=log_w)
+            out = eng.inverse(x, cond, bounds, want_lp=False, want_lse=True, log_w=log_w)
             return eng.lse_finish(out["lse_max"], out["lse_sum"], 0.0 if log_w is not None else -math.log(eng.S))
         if reduce == "sum":
-            return eng.inverse(x, cond, self.bounds, want_lp=False, want_sum=True)["sum_n"]
+            return eng.inverse(x, cond, bounds, want_lp=False, want_sum=True)["sum_n"]
         raise ValueError(reduce)
 
     def sample_draws(self, draws, n_or_noise, condition=None, keep=None, p_drop: float = 0.0,
@@ -188,4 +303,4 @@ class NormalizingFlow(nn.Module):
             z = torch.randn((eng.S, n_or_noise, self.theta_dim), device=eng.device, generator=generator)
         else:
             z = n_or_noise
-        return eng.forward(z, self._cond(condition), self.bounds)
+        return self.relabel.from_engine(eng.forward(z, self._cond(condition), self._bounds_e()))

@@ -34,5 +34,5 @@ class MCDPNormalizingFlow(NormalizingFlow):
             keep = self.draw_keep_masks(niter, generator)
         eng = self.make_engine(self.current_draw(), keep=keep, p_drop=float(self.dropout_p))
         z = base_noise if base_noise is not None else torch.randn((niter, n, self.theta_dim), device=eng.device)
-        x = eng.forward(z, self._cond(condition), self.bounds)
+        x = self.relabel.from_engine(eng.forward(z, self._cond(condition), self._bounds_e()))
         return x.cpu().detach().numpy()

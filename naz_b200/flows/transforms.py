@@ -55,15 +55,54 @@ def _hidden_list(hidden_dim):
     return list(hidden_dim) if isinstance(hidden_dim, (list, tuple)) else [hidden_dim]
 
 
-def _check_opts(use_batchnorm, random_perm):
-    if use_batchnorm or random_perm:
-        raise NotImplementedError("Permute / BatchNorm layers are off in every naz example and not built (DESIGN.md scope)")
+class Permute(nn.Module):
+    """pyro's `T.Permute` as naz appends it after each flow layer when `random_perm=True` (transforms.py:155-156, :193-194):
+    `y[..., k] = x[..., permutation[k]]`, log-det 0.  No kernel runs for it: `NormalizingFlow` folds the re-labelling
+    into the neighbouring conditioners' weight columns / output rows / MADE order when it packs (flows/flow.py)."""
+    kind = "permute"
+
+    def __init__(self, permutation):
+        super().__init__()
+        self.register_buffer("permutation", torch.as_tensor(permutation).to(torch.int64).cpu())
+
+
+class BatchNorm(nn.Module):
+    """pyro's `T.BatchNorm` as naz appends it when `use_batchnorm=True` (transforms.py:157-158, :195-196), in its eval()
+    form: sampling direction `y = (x - beta) / gamma_c * sqrt(moving_variance + eps) + moving_mean`, gamma_c = relu(gamma) +
+    1e-6, log|dy/dx| = 0.5 log(moving_variance + eps) - log gamma_c per dimension.  Evaluated inside the SIMT flow kernel as a
+    per-layer element-wise affine (`nazb_set_layer_affine`).  The train()-mode batch statistics belong to the training
+    loop (out of scope): `log_prob` in train() mode raises."""
+    kind = "batchnorm"
+
+    def __init__(self, input_dim, momentum=0.1, epsilon=1e-5):
+        super().__init__()
+        self.input_dim, self.momentum, self.epsilon = input_dim, momentum, epsilon
+        self.gamma = nn.Parameter(torch.ones(input_dim))
+        self.beta = nn.Parameter(torch.zeros(input_dim))
+        self.register_buffer("moving_mean", torch.zeros(input_dim))
+        self.register_buffer("moving_variance", torch.ones(input_dim))
+
+    @property
+    def constrained_gamma(self):
+        return torch.relu(self.gamma) + 1e-6
+
+    def affine(self):
+        """(a, b) of the sampling direction y = a x + b, float32 [D] each."""
+        with torch.no_grad():
+            a = torch.sqrt(self.moving_variance + self.epsilon) / self.constrained_gamma
+            return a.float(), (self.moving_mean - self.beta * a).float()
+
+
+def _extras(transforms, theta_dim, use_batchnorm, random_perm):
+    if random_perm:
+        transforms.append(Permute(torch.randperm(theta_dim)))
+    if use_batchnorm:
+        transforms.append(BatchNorm(theta_dim))
 
 
 def masked_affine_autoregressive(theta_dim, condition_dim, hidden_dim, num_layers, activation=None, use_batchnorm=False,
                                  random_mask=True, random_perm=False, dropout_p=None):
     """transforms.py:133-160."""
-    _check_opts(use_batchnorm, random_perm)
     transforms, nets = [], []
     for _ in range(num_layers):
         perm = None if random_mask else torch.arange(theta_dim)
@@ -71,6 +110,7 @@ def masked_affine_autoregressive(theta_dim, condition_dim, hidden_dim, num_layer
                                           permutation=perm, dropout_p=dropout_p)
         nets.append(arn)
         transforms.append(AffineAutoregressive(arn))
+        _extras(transforms, theta_dim, use_batchnorm, random_perm)
     return ComposeTransformModule(transforms), transforms, nets
 
 
@@ -78,7 +118,6 @@ def neural_spline_autoregressive(theta_dim, condition_dim, hidden_dim, num_layer
                                  activation=None, use_batchnorm=False, random_mask=True, random_perm=False,
                                  dropout_p=None):
     """transforms.py:165-198."""
-    _check_opts(use_batchnorm, random_perm)
     if order == "linear":
         paramdim = [count_bins, count_bins, count_bins - 1, count_bins]
     elif order == "quadratic":
@@ -92,6 +131,7 @@ def neural_spline_autoregressive(theta_dim, condition_dim, hidden_dim, num_layer
                                           nonlinearity=activation, permutation=perm, dropout_p=dropout_p)
         nets.append(arn)
         transforms.append(SplineAutoregressive(arn, count_bins=count_bins, order=order, bound=3.0))
+        _extras(transforms, theta_dim, use_batchnorm, random_perm)
     return ComposeTransformModule(transforms), transforms, nets
 
 

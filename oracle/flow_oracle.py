@@ -374,9 +374,10 @@ def _layer_kw(spec: FlowSpec, keep, p_drop, l):
     return kw
 
 
-def flow_inverse(spec: FlowSpec, params, x, context=None, bounds=None, keep=None, p_drop=0.0):
+def flow_inverse(spec: FlowSpec, params, x, context=None, bounds=None, keep=None, p_drop=0.0, layer_affine=None):
     """Reference ``log_prob`` direction: returns (z, lp).  Layers inverted in reverse order
-    (torch TransformedDistribution.log_prob; bflow_jax_maf.py:211)."""
+    (torch TransformedDistribution.log_prob; bflow_jax_maf.py:211).  ``layer_affine`` = (a, b) [L, D]: the element-wise
+    step x <- a[l] x + b[l] behind flow layer l in the sampling direction (eval-mode T.BatchNorm, transforms.py:157-158)."""
     dt = x.dtype
     masks = spec.masks()
     if bounds is not None:
@@ -386,6 +387,10 @@ def flow_inverse(spec: FlowSpec, params, x, context=None, bounds=None, keep=None
     ld_total = np.zeros(x.shape[:-1], dtype=dt)
     for l in reversed(range(spec.L)):
         kw = _layer_kw(spec, keep, p_drop, l)
+        if layer_affine is not None:
+            a, b = np.asarray(layer_affine[0][l], dt), np.asarray(layer_affine[1][l], dt)
+            y = (y - b) / a
+            ld_total = ld_total + np.log(a).sum().astype(dt)
         if spec.kind == "maf":
             y, ld = affine_inverse(y, params[l], masks[l], spec.perms[l], context, clip=spec.clip, **kw)
         else:
@@ -397,7 +402,7 @@ def flow_inverse(spec: FlowSpec, params, x, context=None, bounds=None, keep=None
     return z, lp.astype(dt)
 
 
-def flow_forward(spec: FlowSpec, params, z, context=None, bounds=None, keep=None, p_drop=0.0):
+def flow_forward(spec: FlowSpec, params, z, context=None, bounds=None, keep=None, p_drop=0.0, layer_affine=None):
     """Reference ``sample`` direction (one conditioner pass per layer): returns (x, sum log-det)."""
     dt = z.dtype
     masks = spec.masks()
@@ -411,6 +416,10 @@ def flow_forward(spec: FlowSpec, params, z, context=None, bounds=None, keep=None
             x, ld = spline_forward(x, params[l], masks[l], context, K=spec.count_bins, order=spec.order,
                                    bound=spec.bound, **kw)
         ld_total = ld_total + ld
+        if layer_affine is not None:
+            a, b = np.asarray(layer_affine[0][l], dt), np.asarray(layer_affine[1][l], dt)
+            x = a * x + b
+            ld_total = ld_total + np.log(a).sum().astype(dt)
     if bounds is not None:
         x = inverse_bounding_transform(x, np.asarray(bounds[0], dt), np.asarray(bounds[1], dt))
     return x, ld_total

@@ -294,6 +294,71 @@ class SplineAutoregressive(_ARTransform):
         return self._cached_ld.sum(-1)
 
 
+class Permute(Transform):
+    """pyro `T.Permute` (pyro/distributions/transforms/permute.py, restated): y = x.index_select(-1, permutation), inverse
+    by the inverse permutation, log|det J| = 0.  naz appends one per flow layer with random_perm=True (transforms.py:155-156)."""
+    domain = constraints.real_vector
+    codomain = constraints.real_vector
+    bijective = True
+
+    def __init__(self, permutation):
+        super().__init__(cache_size=0)
+        self.permutation = torch.as_tensor(permutation, dtype=torch.int64)
+        self.inv_permutation = torch.argsort(self.permutation)
+
+    def __hash__(self):
+        return id(self)
+
+    def __eq__(self, other):
+        return self is other
+
+    def _call(self, x):
+        return x.index_select(-1, self.permutation)
+
+    def _inverse(self, y):
+        return y.index_select(-1, self.inv_permutation)
+
+    def log_abs_det_jacobian(self, x, y):
+        return torch.zeros(x.shape[:-1], dtype=x.dtype)
+
+
+class BatchNormEval(Transform):
+    """pyro `T.BatchNorm` (pyro/distributions/transforms/batchnorm.py, restated) in eval() mode — the training-mode batch
+    statistics are the training loop's business:  _call(x) = (x - beta) / gamma_c * sqrt(moving_variance + eps) + moving_mean,
+    _inverse(y) = (y - moving_mean) * gamma_c / sqrt(moving_variance + eps) + beta, gamma_c = relu(gamma) + 1e-6,
+    log|dy/dx| = -log gamma_c + 0.5 log(moving_variance + eps) per dimension (summed here over the event dimension, as the
+    TransformedDistribution does for pyro's element-wise version).  naz appends one per flow layer with use_batchnorm=True
+    (transforms.py:157-158)."""
+    domain = constraints.real_vector
+    codomain = constraints.real_vector
+    bijective = True
+
+    def __init__(self, gamma, beta, moving_mean, moving_variance, epsilon=1e-5):
+        super().__init__(cache_size=0)
+        self.gamma, self.beta = torch.as_tensor(gamma), torch.as_tensor(beta)
+        self.moving_mean, self.moving_variance, self.epsilon = torch.as_tensor(moving_mean), torch.as_tensor(moving_variance), epsilon
+
+    def __hash__(self):
+        return id(self)
+
+    def __eq__(self, other):
+        return self is other
+
+    @property
+    def constrained_gamma(self):
+        return F.relu(self.gamma) + 1e-6
+
+    def _call(self, x):
+        return (x - self.beta) / self.constrained_gamma * torch.sqrt(self.moving_variance + self.epsilon) + self.moving_mean
+
+    def _inverse(self, y):
+        return (y - self.moving_mean) * self.constrained_gamma / torch.sqrt(self.moving_variance + self.epsilon) + self.beta
+
+    def log_abs_det_jacobian(self, x, y):
+        ld = -self.constrained_gamma.log() + 0.5 * torch.log(self.moving_variance + self.epsilon)
+        return ld.expand(x.shape).sum(-1)
+
+
 def bounding_transform(x, low, high):
     """src/naz/flows/transforms.py:20-23."""
     y = (x - low.expand(x.shape)) / ((high - low).expand(x.shape))
@@ -310,8 +375,11 @@ class PyroStyleFlow(nn.Module):
     """naz ``NormalizingFlow`` (flow.py:24-129) for flow_type in {"maf", "nsa"} on the torch stack."""
 
     def __init__(self, flow_type, bounds, theta_dim, condition_dim, hidden_dim, num_layers, count_bins=8,
-                 order="quadratic", permutations=None, dropout_p=None):
+                 order="quadratic", permutations=None, dropout_p=None, extras=None):
+        """extras: optional [L] of lists of ready-made transforms (Permute / BatchNormEval) placed behind flow layer l, in the
+        order naz appends them (transforms.py:155-158: Permute, then BatchNorm)."""
         super().__init__()
+        self.extras = extras
         assert flow_type in ("maf", "nsa")
         self.flow_type, self.bounds = flow_type, bounds
         self.theta_dim, self.condition_dim = theta_dim, condition_dim
@@ -330,13 +398,16 @@ class PyroStyleFlow(nn.Module):
         self.base_dist = Normal(torch.zeros(theta_dim), torch.ones(theta_dim))
 
     def _transforms(self, condition):
-        ts = []
+        ts, ts_ar = [], []
         for arn in self.nets:
             fn = partial(arn, context=condition) if self.conditional else arn
             if self.flow_type == "maf":
                 ts.append(AffineAutoregressive(fn, arn))
             else:
                 ts.append(SplineAutoregressive(fn, arn, self.count_bins, 3.0, self.order))
+            if self.extras is not None:
+                ts.extend(self.extras[len(ts_ar)])
+            ts_ar.append(arn)
         return ts
 
     def _pdf(self, condition):

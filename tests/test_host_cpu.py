@@ -335,3 +335,66 @@ def test_bayesian_normalizing_flow_class_priors_host_side():
     assert bool(((x >= torch.minimum(a, b)) & (x <= torch.maximum(a, b))).all()) and torch.allclose(inv(x), u, atol=1e-3)
     with pytest.raises(ValueError):
         BayesianNormalizingFlow(mle, "maf", None, 2, 2, [16, 16], 2, prior_dist="Cauchy")
+
+
+@pytest.mark.parametrize("flow_type", ["maf", "nsa"])
+def test_permute_and_batchnorm_layers_fold_into_the_packed_flow(flow_type):
+    """random_perm / use_batchnorm of the reference's factories (transforms.py:155-158, :193-196).  Three independent
+    statements must agree: (1) the module-structured restatement with EXPLICIT Permute / BatchNorm transforms on torch's
+    TransformedDistribution; (2) the numpy oracle evaluated on what the product hands to libnazb — conditioner weights with
+    the permutations folded in (`Relabelling`), re-labelled inputs / bounds, a per-layer affine; (3) the folded MADE masks
+    are exactly the masks the folded MADE orders generate."""
+    from naz_b200.flows.flow import NormalizingFlow
+    from naz_b200.flows.transforms import BatchNorm, Permute
+    from oracle import flow_oracle as fo, pyro_style as ps
+    torch.manual_seed(3)
+    D, C, hidden, L, K = 4, 2, [24, 24], 3, 6
+    bounds = {"low": torch.tensor([-1.0, 0.0, -2.0, 0.5]), "high": torch.tensor([1.0, 3.0, 2.0, 4.5])}
+    args = (D, C, hidden, L) + ((K,) if flow_type == "nsa" else ())
+    flow = NormalizingFlow(flow_type, bounds, *args, random_perm=True, use_batchnorm=True)
+    assert [type(t).__name__ for t in flow.transforms][1:3] == ["Permute", "BatchNorm"] and len(flow.transforms) == 3 * L
+    assert not flow.relabel.trivial and flow.relabel.has_bn and flow.relabel.ar_pos == [0, 3, 6]
+    with torch.no_grad():
+        for t in flow.transforms:
+            if isinstance(t, BatchNorm):
+                t.gamma.copy_(0.5 + torch.rand(D)); t.beta.copy_(0.3 * torch.randn(D))
+                t.moving_mean.copy_(0.2 * torch.randn(D)); t.moving_variance.copy_(0.5 + torch.rand(D))
+    # (1) explicit layers
+    torch.set_default_dtype(torch.float64)
+    try:
+        extras = []
+        for l in range(L):
+            pm, bn = flow.transforms[3 * l + 1], flow.transforms[3 * l + 2]
+            extras.append([ps.Permute(pm.permutation), ps.BatchNormEval(bn.gamma.detach().double(), bn.beta.detach().double(),
+                                                                        bn.moving_mean.double(), bn.moving_variance.double(), bn.epsilon)])
+        b64 = {k: v.double() for k, v in bounds.items()}
+        ref = ps.PyroStyleFlow(flow_type, b64, D, C, hidden, L, K, "quadratic", permutations=flow.perms().numpy(), extras=extras)
+        ref.set_from_pytree([[(W.double().numpy(), b.double().numpy()) for (W, b) in layer] for layer in flow.current_draw()])
+        x = torch.rand(64, D, dtype=torch.float64) * (b64["high"] - b64["low"]) * 0.96 + b64["low"] + 0.02 * (b64["high"] - b64["low"])
+        ctx = torch.randn(64, C, dtype=torch.float64)
+        with torch.no_grad():
+            lp_ref = ref.log_prob(x, ctx).numpy()
+            z = torch.randn(64, D, dtype=torch.float64)
+            xs_ref = ref.sample(None, ctx, base_noise=z).numpy()
+    finally:
+        torch.set_default_dtype(torch.float32)
+    # (2) what the product packs
+    perms_e = flow._packed_perms().numpy()
+    spec = fo.FlowSpec(flow_type, D, C, hidden, L, perms_e, count_bins=K)
+    params_e = [[(W.double().numpy(), b.double().numpy()) for (W, b) in layer] for layer in flow._fold_draws(flow.current_draw())]
+    aff = tuple(t.double().numpy() for t in flow.relabel.layer_affine())
+    be = flow._bounds_e()
+    xe = flow.relabel.to_engine(x).numpy()
+    _, lp_e = fo.flow_inverse(spec, params_e, xe, ctx.numpy(), (be["low"].double().numpy(), be["high"].double().numpy()), layer_affine=aff)
+    # the product's affine table is fp32 (what libnazb takes): agreement to fp32 round-off of (a, b); a folding mistake is O(1)
+    np.testing.assert_allclose(lp_e, lp_ref, rtol=2e-6, atol=2e-5)
+    xs_e, _ = fo.flow_forward(spec, params_e, z.numpy(), ctx.numpy(), (be["low"].double().numpy(), be["high"].double().numpy()), layer_affine=aff)
+    np.testing.assert_allclose(flow.relabel.from_engine(torch.as_tensor(xs_e)).numpy(), xs_ref, rtol=2e-6, atol=2e-5)
+    # (3) folded masks == masks of the folded orders
+    for ml_e, ml in zip(flow._packed_masks(), spec.masks()):
+        for me, m in zip(ml_e, ml):
+            assert np.array_equal(me.numpy(), m)
+    # posterior-sample dicts index EVERY transform (train_flows.py:71): flow_0, flow_3, flow_6 are the conditioners
+    from naz_b200.trainers.train_flows import get_params
+    gp = get_params(flow)
+    assert len(gp) == 3 * L and set(gp[1]) == set() and set(gp[2]) == {"gamma", "beta"}
