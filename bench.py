@@ -429,52 +429,59 @@ def main_ours(args):
 
     # auxiliary: SURVEY §8 f1 — value + gradient of sum_n lp (the NUTS / SVI inner loop), config-4 architecture (maf 2|2),
     # 4 chains x 100 000 points; 1 grad-eval = one (chain, point) pair through the value and the full parameter gradient
-    aux_grad = None
+    aux_grad = aux_grad_spline = None
     if not args.no_aux:
-        # every rank holds the same 4 chains (same seeds) and the same 400 000 points; with N > 1 GPUs the POINTS are sharded
+        # every rank holds the same chains (same seeds) and the same points; with N > 1 GPUs the POINTS are sharded
         # (strong scaling of one gradient step) and one all-reduce of the flat gradient buffer + the values finishes the step
         # (naz_b200.parallel.inverse_grad_point_sharded); the time is the max over ranks of the CUDA-event time of the whole
         # step, all-reduce included
         from naz_b200.parallel import inverse_grad_point_sharded
-        torch.manual_seed(3)
-        ggen = torch.Generator(device=dev)
-        ggen.manual_seed(99)
-        gflow = NormalizingFlow("maf", None, 2, 2, [150, 150, 150], 16, engine="simt").to(dev)
-        gdraws = [[(lin.weight.detach().unsqueeze(0) * (1 + 0.25 * (torch.rand((4,) + tuple(lin.weight.shape), device=dev, generator=ggen) * 2 - 1)),
-                    lin.bias.detach().unsqueeze(0) * (1 + 0.25 * (torch.rand((4,) + tuple(lin.bias.shape), device=dev, generator=ggen) * 2 - 1)))
-                   for lin in arn.layers] for arn in gflow.nets]
-        geng = gflow.make_engine(gdraws, device=dev)
-        GN = 100_000 * world if world > 1 else 100_000      # per-GPU work fixed at 100 k points x 4 chains
-        gx = torch.randn((GN, 2), device=dev, generator=ggen) * 1.5
-        gc = torch.rand((GN, 2), device=dev, generator=ggen)
-        inverse_grad_point_sharded(geng, gx, gc)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        gr = inverse_grad_point_sharded(geng, gx, gc)
-        g1.record()
-        torch.cuda.synchronize()
-        g_t = torch.tensor([g0.elapsed_time(g1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(g_t, op=dist.ReduceOp.MAX)
-        g_ms = float(g_t.item())
-        # algorithmic work of one grad-eval: the value pass (F1, masks as dense zeros) + the two products of the backward pass
-        # per linear layer (cotangent . W and the outer product into dW) = 3 F1; roofline = fp32 FMA issue of the CUDA cores
-        # (nominal: SMs x 128 lanes x 2 flop x measured SM clock; MEASURED_PEAKS.json holds no fp32 figure)
-        g_f1 = 3 * flops_per_eval(2, 2, [150, 150, 150], 16, 2)
-        g_peak = world * torch.cuda.get_device_properties(dev).multi_processor_count * 128 * 2 * 1.965e9 / 1e12
-        g_ach = g_f1 * 4 * GN / (g_ms * 1e-3) / 1e12
-        aux_grad = {"value": 4 * GN / (g_ms * 1e-3), "unit": "grad-evals/s", "chains": 4, "points": GN, "ms": g_ms,
+
+        def grad_aux(gkind, gD, gC, gK, chains, pts_per_gpu, what):
+            torch.manual_seed(3)
+            ggen = torch.Generator(device=dev)
+            ggen.manual_seed(99)
+            gargs = (gD, gC, [150, 150, 150], 16) + ((gK,) if gkind == "nsa" else ())
+            gflow = NormalizingFlow(gkind, None, *gargs, engine="simt").to(dev)
+            gdraws = [[(lin.weight.detach().unsqueeze(0) * (1 + 0.25 * (torch.rand((chains,) + tuple(lin.weight.shape), device=dev, generator=ggen) * 2 - 1)),
+                        lin.bias.detach().unsqueeze(0) * (1 + 0.25 * (torch.rand((chains,) + tuple(lin.bias.shape), device=dev, generator=ggen) * 2 - 1)))
+                       for lin in arn.layers] for arn in gflow.nets]
+            geng = gflow.make_engine(gdraws, device=dev)
+            GN = pts_per_gpu * world                            # per-GPU work fixed
+            gx = torch.randn((GN, gD), device=dev, generator=ggen) * 1.5
+            gc = torch.rand((GN, gC), device=dev, generator=ggen)
+            inverse_grad_point_sharded(geng, gx, gc)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            gr = inverse_grad_point_sharded(geng, gx, gc)
+            g1.record()
+            torch.cuda.synchronize()
+            g_t = torch.tensor([g0.elapsed_time(g1)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(g_t, op=dist.ReduceOp.MAX)
+            g_ms = float(g_t.item())
+            # algorithmic work of one grad-eval: the value pass (F1, masks as dense zeros) + the two products of the backward pass
+            # per linear layer (cotangent . W and the outer product into dW) = 3 F1; roofline = fp32 FMA issue of the CUDA cores
+            # (nominal: SMs x 128 lanes x 2 flop x measured SM clock; MEASURED_PEAKS.json holds no fp32 figure)
+            g_f1 = 3 * flops_per_eval(gD, gC, [150, 150, 150], 16, 2 if gkind == "maf" else 3 * gK - 1)
+            g_peak = world * torch.cuda.get_device_properties(dev).multi_processor_count * 128 * 2 * 1.965e9 / 1e12
+            g_ach = g_f1 * chains * GN / (g_ms * 1e-3) / 1e12
+            return {"value": chains * GN / (g_ms * 1e-3), "unit": "grad-evals/s", "chains": chains, "points": GN, "ms": g_ms,
                     "flops_per_grad_eval": g_f1,
                     "roofline": {"bound": "fp32 FMA (CUDA cores)", "achieved": g_ach, "peak": g_peak, "unit": "TFLOP/s", "frac": g_ach / g_peak,
                                  "peak_source": "nominal: SMs x 128 FMA lanes x 2 x 1.965 GHz, all GPUs of the run"},
-                    "flow": "maf 2|2 [150,150,150] x16", "engine": "simt (fp32 CUDA cores)",
-                    "parallelism": f"point-sharded x{world}, one all-reduce of the gradient buffer (weak scaling: 100 k points per GPU)",
+                    "flow": what, "engine": "simt (fp32 CUDA cores)",
+                    "parallelism": f"point-sharded x{world}, one all-reduce of the gradient buffer (weak scaling: {pts_per_gpu} points per GPU)",
                     "finite": bool(torch.isfinite(gr["sum_n"]).all().item()),
-                    "note": "nazb_inverse_grad: value + d/d(all weights) of sum_n lp per chain (first cut of row f1; not part of `value`)"}
-        del geng, gr, gdraws
+                    "note": "nazb_inverse_grad: value + d/d(all weights) of sum_n lp per chain (row f1; not part of `value`)"}
+
+        # config-4 architecture (maf 2|2), 4 chains x 100 000 points; 1 grad-eval = one (chain, point) pair through the value and
+        # the full parameter gradient;  and the benchmarked spline architecture (config 3: nsa 4|2, K = 8), 2 chains x 50 000 points
+        aux_grad = grad_aux("maf", 2, 2, 8, 4, 100_000, "maf 2|2 [150,150,150] x16")
+        aux_grad_spline = grad_aux("nsa", 4, 2, 8, 2, 50_000, "nsa 4|2 [150,150,150] x16, K = 8 (quadratic)")
 
     # parity probe: the weights and inputs that were just timed, 2 draws x 4096 points, against the fp64 oracle
     parity = None
@@ -544,6 +551,8 @@ def main_ours(args):
         }
         if aux_grad is not None:
             out["aux_grad_direction"] = aux_grad
+        if aux_grad_spline is not None:
+            out["aux_grad_direction_spline"] = aux_grad_spline
         out.update(aux)
         if parity is not None:
             out["parity"] = parity

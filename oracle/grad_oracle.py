@@ -81,13 +81,13 @@ def value_and_grad(params_np, masks_np, perms, x_np, ctx_np=None, bounds_np=None
     return float(tot.detach()), gW, gb, (x.grad.numpy() if want_dx else None), lp.detach().numpy()
 
 
-def value_and_grad_flow(spec, params_np, x_np, ctx_np=None, bounds_np=None):
+def value_and_grad_flow(spec, params_np, x_np, ctx_np=None, bounds_np=None, want_dx=False):
     """Gradient oracle for ANY flow kind the forward oracle covers (maf, nsa quadratic / linear): torch autograd (float64)
     through the second restatement oracle/pyro_style.py (torch modules on torch.distributions.TransformedDistribution), i.e.
     what the reference's torch path does in `train` (train_flows.py:195-213: loss = -flow.log_prob(...).mean(); backward()).
     The spline branch of that restatement is UNPINNED (pyro-ppl is absent); this function is groundwork for the spline
     backward kernel, checked in tests/ against finite differences and, for maf, against the pinned twin above.
-    -> (sum_n lp, gW [L][n_lin], gb [L][n_lin]) float64 numpy, ONE draw."""
+    -> (sum_n lp, gW [L][n_lin], gb [L][n_lin]) float64 numpy, ONE draw; with want_dx also d lp_n / d x_n [N, D]."""
     from oracle import pyro_style as ps
     torch.set_default_dtype(torch.float64)
     try:
@@ -96,7 +96,7 @@ def value_and_grad_flow(spec, params_np, x_np, ctx_np=None, bounds_np=None):
         flow = ps.PyroStyleFlow(spec.kind, bounds, spec.D, spec.C, list(spec.hidden), spec.L, spec.count_bins, spec.order,
                                 permutations=spec.perms)
         flow.set_from_pytree([[(np.asarray(W, np.float64), np.asarray(b, np.float64)) for (W, b) in layer] for layer in params_np])
-        x = torch.tensor(np.asarray(x_np, np.float64))
+        x = torch.tensor(np.asarray(x_np, np.float64), requires_grad=bool(want_dx))
         ctx = None
         if ctx_np is not None:
             ctx = torch.tensor(np.asarray(ctx_np, np.float64))
@@ -106,6 +106,8 @@ def value_and_grad_flow(spec, params_np, x_np, ctx_np=None, bounds_np=None):
         tot.backward()
         gW = [[lin.weight.grad.numpy().copy() for lin in arn.layers] for arn in flow.nets]
         gb = [[lin.bias.grad.numpy().copy() for lin in arn.layers] for arn in flow.nets]
+        if want_dx:
+            return float(tot.detach()), gW, gb, x.grad.numpy().copy()
         return float(tot.detach()), gW, gb
     finally:
         torch.set_default_dtype(torch.float32)

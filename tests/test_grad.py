@@ -1,4 +1,4 @@
-"""value and gradient of the summed log-likelihood (masked-affine flows).
+"""value and gradient of the summed log-likelihood (masked-affine and quadratic neural-spline flows).
 CPU: the gradient oracle (torch autograd of the restated twin) is pinned on the forward side by the reference-executed
 fixtures and checked against finite differences.  GPU: nazb_inverse_grad against the oracle."""
 import numpy as np
@@ -158,8 +158,8 @@ def test_inverse_grad_draw_range_and_unsupported():
     # the value agrees with the log_prob entry point
     lp = eng.inverse(x, ctx, want_lp=True)["lp"].double().sum(-1)
     assert torch.allclose(lp, full["sum_n"], rtol=1e-5)
-    # splines and tensor-core handles are not served by the first cut: loud error, no fallback
-    spec2, draws2, _, _ = make_case("nsa", 3, 1, [16, 16], 2, 2, seed=3)
+    # linear-order splines and tensor-core handles are not served: loud error, no fallback
+    spec2, draws2, _, _ = make_case("nsa", 3, 1, [16, 16], 2, 2, seed=3, order="linear")
     eng2 = engine_for(spec2, draws2, engine="simt")
     with pytest.raises(_lib.NazbError):
         eng2.inverse_grad(x, ctx)
@@ -279,3 +279,121 @@ def test_flow_level_grad_oracle_maf_equals_twin_and_spline_matches_finite_differ
             assert abs((up - dn) / (2 * eps) - gW[l][j][idx]) < 2e-5 * max(1.0, abs(gW[l][j][idx])), (l, j, idx)
             checked += 1
     assert checked == 12
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# neural-spline flows
+# ----------------------------------------------------------------------------------------------------------------
+def test_device_spline_derivative_routine_on_the_host_matches_autograd(built_lib):
+    """naz_b200/csrc/spline_grad.cuh compiled for the CPU (nazb_host_spline_grad; no GPU needed): 1/T', d ld/dx and the raw-slot
+    coefficients ca = -(dT/draw)/T', cb = -d ld/draw against torch autograd (fp64) of the oracle's spline, incl. the
+    identity region outside [-B, B], the first / last bins (fixed end derivatives) and K != 8."""
+    import ctypes as C
+    import torch.nn.functional as F
+    from naz_b200 import _lib
+    from oracle import pyro_style as ps
+    L = _lib.lib()
+    rng = np.random.default_rng(1)
+    errs, bins = [], set()
+    for trial in range(600):
+        K = (8, 8, 5, 12)[trial % 4]
+        M, B = 3 * K - 1, 3.0
+        raw = (rng.normal(size=M) * (0.5 + 1.5 * rng.uniform())).astype(np.float32)
+        x = np.float32(rng.uniform(-3.4, 3.4) if trial % 7 else rng.choice([-2.999, 2.999, -3.2, 0.0]))
+        ca, cb = np.zeros(M, np.float32), np.zeros(M, np.float32)
+        itx, ldx = C.c_float(), C.c_float()
+        assert L.nazb_host_spline_grad(float(x), K, B, raw.ctypes.data, ca.ctypes.data, cb.ctypes.data, C.addressof(itx),
+                                       C.addressof(ldx)) == 0
+        r = torch.tensor(raw.astype(np.float64), requires_grad=True)
+        xt = torch.tensor(float(x), dtype=torch.float64, requires_grad=True)
+        y, ld = ps.monotonic_rational_spline(xt[None], F.softmax(r[:K], -1)[None], F.softmax(r[K:2 * K], -1)[None],
+                                             F.softplus(r[2 * K:])[None], bound=B)
+        gy = torch.autograd.grad(y.sum(), [r, xt], retain_graph=True, allow_unused=True)
+        gl = torch.autograd.grad(ld.sum(), [r, xt], allow_unused=True)
+        z = lambda t, n: np.zeros(n) if t is None else t.numpy()
+        tx = float(z(gy[1], ())) if abs(float(x)) <= B else 1.0
+        ca_ref, cb_ref = -z(gy[0], M) / tx, -z(gl[0], M)
+        if abs(float(x)) > B:
+            assert itx.value == 1.0 and ldx.value == 0.0 and not ca.any() and not cb.any()
+            continue
+        bins.add(int(np.argmax(np.abs(ca_ref[:K]) > 0)) if np.any(ca_ref[:K]) else -1)
+        errs.append([np.abs(ca - ca_ref).max() / max(1.0, np.abs(ca_ref).max()), np.abs(cb - cb_ref).max() / max(1.0, np.abs(cb_ref).max()),
+                     abs(itx.value - 1.0 / tx) * tx, abs(ldx.value - float(z(gl[1], ()))) / max(1.0, abs(float(z(gl[1], ()))))])
+    e = np.array(errs)
+    assert len(e) > 400 and np.median(e) < 5e-6 and e.max() < 5e-3, (np.median(e, 0), e.max(0))
+
+
+SPLINE_GRAD_CASES = [
+    # D C hidden L K S N bounds ctx_rows
+    (2, 0, [16, 16], 3, 8, 2, 37, False, 0),
+    (3, 2, [24, 24], 4, 8, 2, 100, True, "N"),
+    (4, 2, [150, 150, 150], 2, 8, 1, 70, False, 1),
+    (3, 1, [32, 32], 2, 5, 2, 45, False, "N"),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", SPLINE_GRAD_CASES)
+def test_inverse_grad_spline_matches_autograd_oracle(case):
+    """nazb_inverse_grad on quadratic neural-spline flows against torch autograd (fp64) through the module-structured
+    restatement — what the reference's torch path differentiates in `train` (train_flows.py:195-213)."""
+    from helpers import engine_for
+    D, C, hidden, L, K, S, N, bounded, crow = case
+    spec, draws, _, rng = make_case("nsa", D, C, hidden, L, S, seed=13, count_bins=K)
+    x = (rng.normal(size=(N, D)) * 1.3).astype(np.float32)
+    x[0, 0] = 3.5                                   # one coordinate in the identity region of the last layer's spline
+    ctx = None
+    if C:
+        ctx = rng.uniform(size=(N if crow == "N" else 1, C)).astype(np.float32)
+    bounds = (np.full(D, -7.0, np.float32), np.full(D, 7.0, np.float32)) if bounded else None
+    eng = engine_for(spec, draws, engine="simt")
+    r = eng.inverse_grad(torch.from_numpy(x), None if ctx is None else torch.from_numpy(ctx),
+                         None if bounds is None else (torch.from_numpy(bounds[0]), torch.from_numpy(bounds[1])),
+                         want_dx=True, want_lp=True)
+    torch.cuda.synchronize()
+    masks = spec.masks()
+    for s in range(S):
+        p = to64(_single(draws, s))
+        c64 = None if ctx is None else (ctx[0] if ctx.shape[0] == 1 else ctx).astype(np.float64)
+        b64 = None if bounds is None else tuple(b.astype(np.float64) for b in bounds)
+        val, gW, gb, dx = go.value_and_grad_flow(spec, p, x.astype(np.float64), c64, b64, want_dx=True)
+        assert abs(float(r["sum_n"][s]) - val) <= 2e-4 * max(1.0, abs(val))
+        for l in range(L):
+            for j in range(len(hidden) + 1):
+                assert _rel(r["gW"][l][j][s].cpu().numpy(), gW[l][j]) < 5e-4, (s, l, j, "W")
+                assert _rel(r["gb"][l][j][s].cpu().numpy(), gb[l][j]) < 5e-4, (s, l, j, "b")
+                assert np.all(r["gW"][l][j][s].cpu().numpy()[masks[l][j] == 0] == 0.0)
+        assert _rel(r["dx"][s].cpu().numpy(), dx) < 5e-4
+
+
+@pytest.mark.gpu
+def test_inverse_grad_spline_directional_derivative_at_bench_shape():
+    """Size-independent property on the benchmarked architecture (config 3: 4|2, [150] x 3, 16 layers, K = 8): the central
+    difference of the VALUE — computed by the tensor-core log_prob engine, an independent code path — along the normalised
+    gradient equals the gradient's norm."""
+    from helpers import engine_for
+    S, N = 1, 20_000
+    spec, draws, _, rng = make_case("nsa", 4, 2, [150] * 3, 16, S, seed=23)
+    x = torch.from_numpy((rng.normal(size=(N, 4)) * 1.2).astype(np.float32))
+    ctx = torch.from_numpy(rng.uniform(size=(N, 2)).astype(np.float32))
+    r = engine_for(spec, draws, engine="simt").inverse_grad(x, ctx)
+    torch.cuda.synchronize()
+    gW = [[t.cpu().numpy().astype(np.float64) for t in layer] for layer in r["gW"]]
+    gb = [[t.cpu().numpy().astype(np.float64) for t in layer] for layer in r["gb"]]
+    norm = np.sqrt(sum((g ** 2).reshape(S, -1).sum(1) for layer in gW for g in layer) +
+                   sum((g ** 2).reshape(S, -1).sum(1) for layer in gb for g in layer))
+    assert np.all(np.isfinite(norm)) and np.all(norm > 0)
+    eps = np.clip(20.0 / norm, 1e-5, 1e-3)
+
+    def value(sign):
+        pert = [[((W + sign * (eps / norm)[:, None, None] * gW[l][j]).astype(np.float32),
+                  (b + sign * (eps / norm)[:, None] * gb[l][j]).astype(np.float32))
+                 for j, (W, b) in enumerate(layer)] for l, layer in enumerate(draws)]
+        e = engine_for(spec, pert, engine="auto")
+        return e.inverse(x, ctx, want_lp=False, want_sum=True)["sum_n"].cpu().numpy(), e.engine_for("inverse")
+
+    vp, used = value(+1.0)
+    vm, _ = value(-1.0)
+    assert used == "tcgen05"
+    fd = (vp - vm) / (2 * eps)
+    assert np.all(np.abs(fd - norm) <= 3e-2 * norm), (fd, norm, eps)
