@@ -21,7 +21,7 @@ SYMBOLS = [
     "nazb_create", "nazb_destroy", "nazb_engine_in_use", "nazb_engine_for_direction", "nazb_pack", "nazb_inverse", "nazb_forward",
     "nazb_lse_reduce", "nazb_lse_finish", "nazb_importance", "nazb_strerror", "nazb_last_cuda_error",
     "nazb_packed_bytes", "nazb_launch_count", "nazb_histogramdd", "nazb_hpd", "nazb_pack_draw_map", "nazb_truncnorm_sample",
-    "nazb_inverse_grad", "nazb_set_option", "nazb_get_option", "nazb_set_layer_affine", "nazb_host_spline_grad",
+    "nazb_inverse_grad", "nazb_set_option", "nazb_get_option", "nazb_set_layer_affine", "nazb_host_spline_grad", "nazb_inverse_vjp",
 ]
 
 
@@ -102,6 +102,8 @@ def lib() -> C.CDLL:
     L.nazb_truncnorm_sample.restype = C.c_int
     L.nazb_inverse_grad.argtypes = [vp, i32, i32, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.nazb_inverse_grad.restype = C.c_int
+    L.nazb_inverse_vjp.argtypes = [vp, i32, i32, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
+    L.nazb_inverse_vjp.restype = C.c_int
     L.nazb_set_option.argtypes = [vp, C.c_char_p, i32]
     L.nazb_set_option.restype = C.c_int
     L.nazb_host_spline_grad.argtypes = [f32, i32, f32, vp, vp, vp, vp, vp]

@@ -47,6 +47,8 @@ struct GradArgs {
   const long long* gwst;      // floats between draws of gW[i]
   const long long* gbst;
   float* dx;                  // [s_count][N][D] or null
+  const float* wgt;           // per-point cotangents of lp, [s_count][N] (draw stride wgt_stride, 0 = shared) or null (= 1)
+  long long wgt_stride;
   int diag;                   // dev: 1 = skip the atomics (timing diagnosis only)
 };
 
@@ -145,10 +147,11 @@ __global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_kernel(
   float* cb = ca + (size_t)md_pad * P;                 // [md_pad][P]
   float* ldacc = cb + (size_t)md_pad * P;              // [P]
   float* ljac = ldacc + P;                             // [P]
+  float* pwv = ljac + P;                               // [P]  cotangent of lp per point (nazb_inverse_vjp; 1 for the plain gradient)
   // zero bias of the transposed products: they read bias[n] for n < max(hidden widths, kin) (the back-propagation to the
   // conditioner input has kin = C + D output columns, which a wide context can make larger than every hidden layer)
   const int zb_n = (g.hmax > kin_pad) ? g.hmax : kin_pad;
-  float* zb = ljac + P;                                // [zb_n]
+  float* zb = pwv + P;                                 // [zb_n]
   float* wbuf = zb + zb_n;                             // [NST][WCHUNK]
   float* red = wbuf + NST * T::WCHUNK;
 
@@ -163,7 +166,10 @@ __global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_kernel(
     // ---- load tile ----
     for (int i = tid; i < kin_pad * P; i += kThreads) xin[i] = 0.f;
     for (int i = tid; i < zb_n; i += kThreads) zb[i] = 0.f;
-    if (tid < P) { ldacc[tid] = 0.f; ljac[tid] = 0.f; }
+    if (tid < P) {
+      ldacc[tid] = 0.f; ljac[tid] = 0.f;
+      pwv[tid] = (tid < npts) ? (ga.wgt ? ga.wgt[(size_t)si * ga.wgt_stride + n0 + tid] : 1.f) : 0.f;
+    }
     __syncthreads();
     for (int i = tid; i < npts * C; i += kThreads) {
       int p = i / C, c = i % C;
@@ -253,7 +259,7 @@ __global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_kernel(
       __syncthreads();
       for (int i = tid; i < P * D; i += kThreads) {
         int p = i % P;
-        gcur[i] = (p < npts) ? -gcur[i] : 0.f;
+        gcur[i] = -gcur[i] * pwv[p];                   // d (w lp) / d z = -w z  (w = 0 on the padding points of a ragged tile)
       }
       __syncthreads();
     }
@@ -284,16 +290,17 @@ __global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_kernel(
           const float e = expf(-s), mk = (sraw >= g.clip_lo && sraw <= g.clip_hi) ? 1.f : 0.f;
           es[r * P + p] = e;
           ca[(r * 2 + 0) * P + p] = -e;      cb[(r * 2 + 0) * P + p] = 0.f;
-          ca[(r * 2 + 1) * P + p] = -xv * mk; cb[(r * 2 + 1) * P + p] = -mk;
+          ca[(r * 2 + 1) * P + p] = -xv * mk; cb[(r * 2 + 1) * P + p] = -mk * pwv[p];
         } else {
           const float* o = obuf + (size_t)(r * M) * P + p;
           float* pa = ca + (size_t)(r * M) * P + p;
           float* pb = cb + (size_t)(r * M) * P + p;
           float itx, ldx;
+          const float pw = pwv[p];
           nazb::rqs_grad(xv, g.K, g.bound, [&](int m) { return o[m * P]; },
-                         [&](int m, float a, float b) { pa[m * P] = a; pb[m * P] = b; }, itx, ldx);
+                         [&](int m, float a, float b) { pa[m * P] = a; pb[m * P] = b * pw; }, itx, ldx);
           es[r * P + p] = itx;
-          gv -= ldx;                         // the direct dependence of ld on x joins g for the rest of this layer
+          gv -= ldx * pw;                         // the direct dependence of ld on x joins g for the rest of this layer
           gcur[d * P + p] = gv;
         }
         lam[d * P + p] = gv;
@@ -381,7 +388,7 @@ __global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_kernel(
           // y = logit(u), u = (x - lo) / (hi - lo);  lp also carries -log u - log(1 - u) - log(hi - lo)
           float w = io.hi[d] - io.lo[d];
           float u = (io.x[(size_t)(n0 + p) * D + d] - io.lo[d]) / w;
-          v = v / (w * u * (1.f - u)) - (1.f / u - 1.f / (1.f - u)) / w;
+          v = v / (w * u * (1.f - u)) - pwv[p] * (1.f / u - 1.f / (1.f - u)) / w;
         }
         dst[i] = v;
       }
@@ -393,7 +400,7 @@ __global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_kernel(
 size_t grad_smem_bytes(const FlowGeom& g, int P, int nst, int tn) {
   const int kin_pad = (g.kin + 3) & ~3, md_pad = (g.md + 3) & ~3;
   size_t f = (size_t)2 * kin_pad * P + (size_t)3 * g.D * P + (size_t)(g.n_hidden + 2) * g.hmax * P +
-             (size_t)4 * md_pad * P + (size_t)g.L * g.D * P + 2 * P + (size_t)((g.hmax > kin_pad) ? g.hmax : kin_pad);
+             (size_t)4 * md_pad * P + (size_t)g.L * g.D * P + 3 * P + (size_t)((g.hmax > kin_pad) ? g.hmax : kin_pad);
   int TR = P / 4, TC = kThreads / TR, NPASS = TC * tn;
   f += (size_t)nst * kKC * NPASS;
   f += 2 * (kThreads / 32) + 4;
@@ -416,7 +423,8 @@ GradGeom make_grad_geom(const FlowGeom& g) {
 }  // namespace
 
 // Gradient launcher.  `tabs` = device memory holding the five tables (mask, gW, gb pointers; gW, gb draw strides).
-cudaError_t nazb_grad_launch(nazb_handle* h, const IoArgs& io, const void* tabs, float* dx, cudaStream_t st) {
+cudaError_t nazb_grad_launch(nazb_handle* h, const IoArgs& io, const void* tabs, float* dx, const float* wgt,
+                             long long wgt_stride, cudaStream_t st) {
   const FlowGeom& g = h->geom;
   const GradGeom gg = make_grad_geom(g);
   const int n = g.L * (g.n_hidden + 1);
@@ -443,6 +451,7 @@ cudaError_t nazb_grad_launch(nazb_handle* h, const IoArgs& io, const void* tabs,
   ga.gwst = reinterpret_cast<const long long*>(t + sizeof(void*) * 3 * n);
   ga.gbst = reinterpret_cast<const long long*>(t + sizeof(void*) * 4 * n);
   ga.dx = dx;
+  ga.wgt = wgt; ga.wgt_stride = wgt_stride;
   ga.diag = h->opt_grad_diag;
   // Measured (maf 2|2, 4 chains x 100 k points): one 32-point CTA per SM 245 ms, two 16-point CTAs per SM 274 ms — the
   // shared-memory wavefronts per point double with the smaller tile — so 16-point tiles only serve shapes whose 32-point

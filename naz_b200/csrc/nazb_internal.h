@@ -110,7 +110,8 @@ cudaError_t nazb_tc_launch(const nazb_handle* h, const IoArgs& io, int n_groups,
 int64_t nazb_tc_packed_bytes(const nazb_handle* h);
 
 // gradient of sum_n lp (masked-affine flows, SIMT image)
-cudaError_t nazb_grad_launch(nazb_handle* h, const IoArgs& io, const void* tabs, float* dx, cudaStream_t st);
+cudaError_t nazb_grad_launch(nazb_handle* h, const IoArgs& io, const void* tabs, float* dx, const float* wgt,
+                             long long wgt_stride, cudaStream_t st);
 bool nazb_grad_fits(const FlowGeom& g);
 
 void nazb_count_launch(int n = 1);

@@ -32,6 +32,9 @@ class _FlowDist:
     def condition(self, context):
         return self
 
+    def clear_cache(self):
+        """train_flows.py:220 calls it after every epoch; nothing is cached between calls here."""
+
 
 def draws_from_posterior_samples(posterior_samples: Dict[str, torch.Tensor], L, n_lin: int):
     """Reference format `"flow_{i}_{name}" -> tensor[S, ...]` (train_flows.py:71, bflow.py:72) -> pytree.  `L` is the number
@@ -95,6 +98,16 @@ class Relabelling:
         out[-1] = (rows(last[0], -2), rows(last[1], -1)) if isinstance(last, tuple) else rows(last, -2)
         return out
 
+    def unfold_layer_grads(self, l: int, gW_first, gW_last, gb_last, C: int):
+        """Gradients with respect to the FOLDED first / last linear of flow layer l -> the reference's index order."""
+        if self.trivial:
+            return gW_first, gW_last, gb_last
+        D, q = self.D, self.q[l]
+        cols = torch.cat([torch.arange(C), C + q]).to(gW_first.device)          # folded column C + q[k] holds reference column C + k
+        M = gW_last.shape[-2] // D
+        rows = torch.cat([m * D + q for m in range(M)]).to(gW_last.device)
+        return gW_first.index_select(-1, cols), gW_last.index_select(-2, rows), gb_last.index_select(-1, rows)
+
     def fold_perm(self, l: int, perm):
         return self.q[l][perm.cpu().to(torch.int64)]
 
@@ -126,6 +139,40 @@ class Relabelling:
         return {"low": lo[self.inv_final.to(lo.device)], "high": hi[self.inv_final.to(hi.device)]}
 
 
+class _LogProbFn(torch.autograd.Function):
+    """Autograd node of `NormalizingFlow.log_prob`: the value comes from the forward engine, `backward` is ONE launch of
+    nazb_inverse_vjp (the incremental inverse recomputed, then the adjoint recursion; naz_b200/csrc/flow_grad.cu) — so the
+    reference's MLE loop `loss = -flow.log_prob(x, condition=y).mean(); loss.backward(); optimizer.step()`
+    (train_flows.py:195-213) runs on this path unchanged."""
+
+    @staticmethod
+    def forward(ctx, flow, x, cond, *params):
+        eng = flow._single_engine()
+        lp = eng.inverse(flow.relabel.to_engine(x), cond, flow._bounds_e(), want_lp=True)["lp"][0]
+        ctx.flow, ctx.cond = flow, cond
+        ctx.versions = tuple(p._version for p in params)
+        ctx.params = params
+        ctx.save_for_backward(x)
+        return lp
+
+    @staticmethod
+    def backward(ctx, g):
+        flow, (x,) = ctx.flow, ctx.saved_tensors
+        if tuple(p._version for p in ctx.params) != ctx.versions:
+            raise RuntimeError("NormalizingFlow parameters were modified in place between log_prob and backward")
+        eng = flow._grad_engine()
+        r = eng.inverse_grad(flow.relabel.to_engine(x), ctx.cond, flow._bounds_e(), want_dx=ctx.needs_input_grad[1],
+                             weights=g.detach().reshape(-1))
+        grads = []
+        for l in range(len(flow.nets)):
+            gW, gb = [t[0] for t in r["gW"][l]], [t[0] for t in r["gb"][l]]
+            gW[0], gW[-1], gb[-1] = flow.relabel.unfold_layer_grads(l, gW[0], gW[-1], gb[-1], flow.condition_dim)
+            for a, b in zip(gW, gb):
+                grads += [a, b]
+        dx = flow.relabel.from_engine(r["dx"][0]) if ctx.needs_input_grad[1] else None
+        return (None, dx, None) + tuple(grads)
+
+
 class NormalizingFlow(nn.Module):
     def __init__(self, flow_type, bounds, *flow_maker_args, embedding_net=None, engine: str = "auto", **flow_maker_kwargs):
         super().__init__()
@@ -155,6 +202,8 @@ class NormalizingFlow(nn.Module):
         self._engine_kind = engine
         self._eng1: Optional[FlowEngine] = None
         self._eng1_key = None
+        self._engg: Optional[FlowEngine] = None
+        self._engg_key = None
 
     # ------------------------------------------------------------------ packing helpers
     def masks(self):
@@ -205,6 +254,22 @@ class NormalizingFlow(nn.Module):
             self._eng1_key = key
         return self._eng1
 
+    def _grad_engine(self) -> FlowEngine:
+        """fp32-engine handle (S = 1) on the current parameters for nazb_inverse_grad / nazb_inverse_vjp."""
+        if self.relabel.has_bn:
+            raise NotImplementedError("gradients of BatchNorm flows are not built (nazb_inverse_grad has no layer affine)")
+        dev = self._device()
+        key = (dev,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._engg is None or self._engg_key != key:
+            if self._engg is None or self._engg.device != dev:
+                self._engg = FlowEngine(self.shape, 1, device=dev, engine="simt")
+            self._engg.pack(self._fold_draws(self.current_draw()), self._packed_masks(), self._packed_perms())
+            self._engg_key = key
+        return self._engg
+
+    def _flat_params(self):
+        return [t for arn in self.nets for lin in arn.layers for t in (lin.weight, lin.bias)]
+
     def make_engine(self, draws, keep=None, p_drop: float = 0.0, device=None) -> FlowEngine:
         """Engine holding S draws given as the reference pytree `[L][n_lin](W[S,out,in], b[S,out])`
         or as the `"flow_{i}_{name}"` dict."""
@@ -233,13 +298,19 @@ class NormalizingFlow(nn.Module):
 
     # ------------------------------------------------------------------ reference API (flow.py:45-129)
     def log_prob(self, x, *args, condition=None, **kwargs):
-        """flow.py:66-79.  Evaluated by libnazb on the module's CURRENT weights; the result is a plain tensor (no autograd
-        graph — gradients come from FlowEngine.inverse_grad / the twin's value_and_grad).  A dropout flow in train() mode
+        """flow.py:66-79.  Evaluated by libnazb on the module's CURRENT weights.  With autograd enabled and parameters (or x)
+        that require grad the result carries a grad_fn whose backward is one nazb_inverse_vjp launch (`_LogProbFn`: masked-affine
+        and quadratic-spline flows), so the reference's training loop (train_flows.py:195-213) works unchanged; under
+        torch.no_grad() it is a plain tensor.  A dropout flow in train() mode
         would apply a fresh nn.Dropout mask upstream: that stochastic path is `MCDPNormalizingFlow.sample_uncertain` /
         `log_prob_draws(keep=...)` here, so calling log_prob in that state raises instead of silently ignoring dropout."""
         if self.training and self.dropout_p not in (None, 0.0):
             raise RuntimeError("log_prob on a dropout flow in train() mode: call flow.eval() for the deterministic density, or "
                                "log_prob_draws(..., keep=masks, p_drop=p) for explicit MC-dropout masks")
+        params = self._flat_params()
+        if torch.is_grad_enabled() and (any(p.requires_grad for p in params) or (isinstance(x, torch.Tensor) and x.requires_grad)) \
+                and self.shape.kind in ("maf", "nsa") and not self.relabel.has_bn:
+            return _LogProbFn.apply(self, x, self._cond(condition), *params)
         eng = self._single_engine()
         out = eng.inverse(self.relabel.to_engine(x), self._cond(condition), self._bounds_e(), want_lp=True)
         return out["lp"][0]

@@ -397,3 +397,67 @@ def test_inverse_grad_spline_directional_derivative_at_bench_shape():
     assert used == "tcgen05"
     fd = (vp - vm) / (2 * eps)
     assert np.all(np.abs(fd - norm) <= 3e-2 * norm), (fd, norm, eps)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flow_type,random_perm", [("maf", False), ("nsa", False), ("nsa", True), ("maf", True)])
+def test_reference_training_step_runs_through_log_prob_backward(flow_type, random_perm):
+    """The reference's MLE loop body (train_flows.py:195-213): `loss = -flow.log_prob(x, condition=y).mean(); loss.backward();
+    optimizer.step()` on the product's NormalizingFlow.  The parameter gradients autograd receives from `_LogProbFn`
+    (one nazb_inverse_vjp launch) must equal fp64 autograd through the module-structured restatement — also with Permute
+    layers between the flow layers (their re-labelling is undone for the gradients) and with a bounded flow."""
+    from naz_b200.flows import NormalizingFlow
+    from oracle import pyro_style as ps
+    torch.manual_seed(5)
+    D, C, hidden, L, K = 3, 2, [32, 32], 3, 6
+    bounds = {"low": torch.tensor([-6.0, -5.0, -7.0]).cuda(), "high": torch.tensor([6.0, 7.0, 5.0]).cuda()}
+    args = (D, C, hidden, L) + ((K,) if flow_type == "nsa" else ())
+    flow = NormalizingFlow(flow_type, bounds, *args, random_perm=random_perm).cuda()
+    N = 257
+    x = (torch.randn(N, D) * 1.2).cuda()
+    y = torch.rand(N, C).cuda()
+    parameters = []
+    for t in flow.flow_dist.transforms:
+        parameters.extend(list(t.parameters()))
+    optimizer = torch.optim.Adam(parameters, lr=1e-3)
+    flow.train()
+    optimizer.zero_grad()
+    loss = -flow.log_prob(x, condition=y).mean()
+    loss.backward()
+    got = [[(lin.weight.grad.detach().cpu().numpy().astype(np.float64), lin.bias.grad.detach().cpu().numpy().astype(np.float64))
+            for lin in arn.layers] for arn in flow.nets]
+    # checker
+    torch.set_default_dtype(torch.float64)
+    try:
+        step = 2 if random_perm else 1
+        extras = [[ps.Permute(flow.transforms[step * l + 1].permutation.cpu())] for l in range(L)] if random_perm else None
+        b64 = {k: v.double().cpu() for k, v in bounds.items()}
+        ref = ps.PyroStyleFlow(flow_type, b64, D, C, hidden, L, K, "quadratic", permutations=flow.perms().numpy(), extras=extras)
+        ref.set_from_pytree([[(W.double().cpu().numpy(), b.double().cpu().numpy()) for (W, b) in layer] for layer in flow.current_draw()])
+        ref_loss = -ref.log_prob(x.double().cpu(), y.double().cpu()).mean()
+        ref_loss.backward()
+        want = [[(lin.weight.grad.numpy(), lin.bias.grad.numpy()) for lin in arn.layers] for arn in ref.nets]
+    finally:
+        torch.set_default_dtype(torch.float32)
+    assert abs(loss.item() - ref_loss.item()) < 1e-4 * max(1.0, abs(ref_loss.item()))
+    for l in range(L):
+        for j in range(len(hidden) + 1):
+            assert _rel(got[l][j][0], want[l][j][0]) < 5e-4, (l, j, "W")
+            assert _rel(got[l][j][1], want[l][j][1]) < 5e-4, (l, j, "b")
+    # a few optimizer steps of the reference loop lower the loss; the validation pass runs under no_grad (train_flows.py:222-223)
+    first = loss.item()
+    for _ in range(20):
+        optimizer.zero_grad()
+        loss = -flow.log_prob(x, condition=y).mean()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(flow.parameters(), 5.0)
+        optimizer.step()
+    flow.flow_dist.clear_cache()
+    flow.eval()
+    with torch.no_grad():
+        val = -flow.log_prob(x, condition=y).mean()
+    assert not val.requires_grad and float(val) < first
+    # d lp / d x through the same node
+    xg = x.clone().requires_grad_(True)
+    flow.log_prob(xg, condition=y).sum().backward()
+    assert xg.grad is not None and torch.isfinite(xg.grad).all() and xg.grad.abs().sum() > 0
