@@ -1,4 +1,4 @@
-"""Timing of the f1 row (nazb_inverse_grad): value + gradient of sum_n lp per draw, masked-affine flows.
+"""Timing of the f1 row (nazb_inverse_grad): value + gradient of sum_n lp per draw, masked-affine and quadratic-spline flows.
 1 grad-eval = one (draw, point) pair pushed through the value AND the full parameter gradient.
 CPU leg (CPU=1): torch autograd of the oracle's restated twin (oracle/grad_oracle.py) in fp32 with all host threads —
 the stand-in for the reference's jax.value_and_grad / autograd call (neither jax nor pyro exists here)."""
@@ -11,6 +11,8 @@ cases = {
     "cfg4": ("maf", 2, 2, [150] * 3, 16),
     "cfg2": ("maf", 6, 4, [150] * 3, 16),
     "cfg5a": ("maf", 8, 4, [150] * 3, 16),
+    "cfg3": ("nsa", 4, 2, [150] * 3, 16),        # the benchmarked spline architecture (K = 8, quadratic)
+    "cfg5b": ("nsa", 8, 4, [150] * 3, 16),
 }
 which = sys.argv[1] if len(sys.argv) > 1 else "cfg4"
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 4
