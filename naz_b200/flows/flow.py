@@ -140,14 +140,15 @@ class Relabelling:
 
 
 class _LogProbFn(torch.autograd.Function):
-    """Autograd node of `NormalizingFlow.log_prob`: the value comes from the forward engine, `backward` is ONE launch of
+    """Autograd node of `NormalizingFlow.log_prob`: value and gradient come from ONE fp32-engine handle (a single re-pack per
+    optimiser step; the backward pass, 6-7x the value pass, dominates a training step anyway); `backward` is ONE launch of
     nazb_inverse_vjp (the incremental inverse recomputed, then the adjoint recursion; naz_b200/csrc/flow_grad.cu) — so the
     reference's MLE loop `loss = -flow.log_prob(x, condition=y).mean(); loss.backward(); optimizer.step()`
     (train_flows.py:195-213) runs on this path unchanged."""
 
     @staticmethod
     def forward(ctx, flow, x, cond, *params):
-        eng = flow._single_engine()
+        eng = flow._grad_engine()
         lp = eng.inverse(flow.relabel.to_engine(x), cond, flow._bounds_e(), want_lp=True)["lp"][0]
         ctx.flow, ctx.cond = flow, cond
         ctx.versions = tuple(p._version for p in params)

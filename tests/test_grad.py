@@ -461,3 +461,29 @@ def test_reference_training_step_runs_through_log_prob_backward(flow_type, rando
     xg = x.clone().requires_grad_(True)
     flow.log_prob(xg, condition=y).sum().backward()
     assert xg.grad is not None and torch.isfinite(xg.grad).all() and xg.grad.abs().sum() > 0
+
+
+@pytest.mark.gpu
+def test_train_driver_fits_a_conditional_gaussian():
+    """naz_b200.trainers.train (signature and return tuple of train_flows.py:73-242) on x | y ~ N(A y + b, diag(s^2)): the
+    validation loss must approach the entropy of the conditional, -E log p = sum log s + D/2 log(2 pi e)."""
+    from naz_b200.flows import NormalizingFlow
+    from naz_b200.trainers import train
+    torch.manual_seed(2)
+    D, C, N = 2, 2, 6000
+    y = torch.rand(N, C).cuda()
+    A = torch.tensor([[1.0, -0.5], [0.3, 0.8]]).cuda()
+    s = torch.tensor([0.3, 0.6]).cuda()
+    x = y @ A.T + 0.2 + s * torch.randn(N, D).cuda()
+    flow = NormalizingFlow("maf", None, D, C, [32, 32], 3).cuda()
+    with torch.no_grad():
+        untrained = float(-flow.log_prob(x, condition=y).mean())
+    flow, history, history_val, best_mse, best_epoch = train(flow, x, y, lr=5e-3, num_epochs=25, batch_frac=0.1, min_epochs=5,
+                                                             patience=4, verbose=False)
+    entropy = float(s.log().sum()) + 0.5 * D * np.log(2 * np.pi * np.e)
+    assert len(history) == len(history_val) and 0 <= best_epoch < len(history_val)
+    assert untrained - best_mse > 0.3, (untrained, best_mse)
+    assert best_mse < entropy + 0.1, (best_mse, entropy)          # measured: entropy + 0.009
+    # the best-validation weights were restored
+    with torch.no_grad():
+        assert not flow.log_prob(x[:10], condition=y[:10]).requires_grad
