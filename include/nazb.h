@@ -188,8 +188,8 @@ int nazb_truncnorm_sample(const float* x, int32_t S, int64_t P, const float* loc
  * HOST arrays with the number of floats between consecutive draws of gW[i] / gb[i] (indexed by the GLOBAL draw s).  The
  * gradient arrays are accumulated into (zero them first).  With nazb_pack_draw_map the gradient with respect to the standard
  * parameters is scale * theta_0 * gW (chain rule on bflow_jax_maf.py:239-240; done by the caller).
- * Covered: NAZB_KIND_AFFINE and NAZB_KIND_RQS (quadratic neural-spline) flows on a handle created with NAZB_ENGINE_SIMT,
- * no dropout keep-masks, no layer affine; anything else (linear-order splines) returns NAZB_ERR_UNSUPPORTED.  fp32 atomics: the sum over points is not bit-reproducible run to run. */
+ * Covered: every flow kind (masked-affine, quadratic and linear-order neural-spline) on a handle created with
+ * NAZB_ENGINE_SIMT, no dropout keep-masks, no layer affine; anything else returns NAZB_ERR_UNSUPPORTED.  fp32 atomics: the sum over points is not bit-reproducible run to run. */
 int nazb_inverse_grad(nazb_handle* h, int32_t s_begin, int32_t s_count, const float* x, const float* ctx,
                       int32_t ctx_rows, int32_t N, const float* lo, const float* hi, const float* const* mask,
                       float* const* gW, float* const* gb, const int64_t* gwst, const int64_t* gbst, float* dx, float* lp,
@@ -259,9 +259,11 @@ int nazb_set_layer_affine(nazb_handle* h, const float* a, const float* b, void* 
 int nazb_get_option(const nazb_handle* h, const char* name, int32_t* value);
 
 /* Test hook, needs no GPU: the device routine behind the neural-spline gradient (naz_b200/csrc/spline_grad.cuh) compiled for
- * the host.  For spline input x and the 3K-1 raw conditioner outputs of one (point, dimension):  inv_tx = 1 / (dT/dx),
- * ldx = d log T'(x) / dx,  ca[m] = -(dT/draw_m) / (dT/dx),  cb[m] = -d log T'(x) / draw_m   (quadratic order, [-bound, bound]). */
-int nazb_host_spline_grad(float x, int32_t K, float bound, const float* raw, float* ca, float* cb, float* inv_tx, float* ldx);
+ * the host.  For spline input x and the 3K-1 (quadratic order) or 4K-1 (linear_order != 0) raw conditioner outputs of one
+ * (point, dimension):  inv_tx = 1 / (dT/dx),  ldx = d log T'(x) / dx,  ca[m] = -(dT/draw_m) / (dT/dx),
+ * cb[m] = -d log T'(x) / draw_m   (spline on [-bound, bound], identity outside). */
+int nazb_host_spline_grad(float x, int32_t K, float bound, int32_t linear_order, const float* raw, float* ca, float* cb,
+                          float* inv_tx, float* ldx);
 
 const char* nazb_strerror(int status);
 const char* nazb_last_cuda_error(const nazb_handle* h);

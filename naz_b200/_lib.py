@@ -106,7 +106,7 @@ def lib() -> C.CDLL:
     L.nazb_inverse_vjp.restype = C.c_int
     L.nazb_set_option.argtypes = [vp, C.c_char_p, i32]
     L.nazb_set_option.restype = C.c_int
-    L.nazb_host_spline_grad.argtypes = [f32, i32, f32, vp, vp, vp, vp, vp]
+    L.nazb_host_spline_grad.argtypes = [f32, i32, f32, i32, vp, vp, vp, vp, vp]
     L.nazb_host_spline_grad.restype = C.c_int
     L.nazb_set_layer_affine.argtypes = [vp, vp, vp, vp]
     L.nazb_set_layer_affine.restype = C.c_int

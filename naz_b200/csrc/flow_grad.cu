@@ -1,5 +1,5 @@
 // Gradient of the draw-batched log-likelihood  sum_n log p(x_n | c_n; theta_s)  with respect to every weight and bias of
-// draw s (and, optionally, to the points) for masked-affine AND neural-spline (quadratic) autoregressive flows — SURVEY §8 row f1: the inner loop of
+// draw s (and, optionally, to the points) for masked-affine AND neural-spline (quadratic and linear order) autoregressive flows — SURVEY §8 row f1: the inner loop of
 // the reference's NUTS / SVI / MLE drivers, which call jax.grad / torch autograd on exactly this scalar
 // (src/naz/flows/bflow_jax_maf.py:233-246 log_prob -> :321-327 NUTS, :344-348 SVI, :277-287 MLE;
 //  src/naz/trainers/train_flows.py:195-213).
@@ -219,7 +219,8 @@ __global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_kernel(
             auto raw = [&](int m) { return o[m * P]; };
             auto setw = [&](int m, float v) { o[m * P] = v; };
             float xv, ld;
-            nazb::rational_spline<false>(gcur[d * P + p], g.K, g.bound, true, raw, setw, xv, ld);
+            if (g.kind == NAZB_KIND_RQS) nazb::rational_spline<false>(gcur[d * P + p], g.K, g.bound, true, raw, setw, xv, ld);
+            else nazb::rational_spline<true>(gcur[d * P + p], g.K, g.bound, true, raw, setw, xv, ld);
             xin[(C + d) * P + p] = xv;
             ldacc[p] += ld;
           }
@@ -297,8 +298,10 @@ __global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_kernel(
           float* pb = cb + (size_t)(r * M) * P + p;
           float itx, ldx;
           const float pw = pwv[p];
-          nazb::rqs_grad(xv, g.K, g.bound, [&](int m) { return o[m * P]; },
-                         [&](int m, float a, float b) { pa[m * P] = a; pb[m * P] = b * pw; }, itx, ldx);
+          auto rawf = [&](int m) { return o[m * P]; };
+          auto putf = [&](int m, float a, float b) { pa[m * P] = a; pb[m * P] = b * pw; };
+          if (g.kind == NAZB_KIND_RQS) nazb::spline_grad<false>(xv, g.K, g.bound, rawf, putf, itx, ldx);
+          else nazb::spline_grad<true>(xv, g.K, g.bound, rawf, putf, itx, ldx);
           es[r * P + p] = itx;
           gv -= ldx * pw;                         // the direct dependence of ld on x joins g for the rest of this layer
           gcur[d * P + p] = gv;

@@ -298,10 +298,11 @@ namespace {
 struct HostRaw { const float* r; __host__ __device__ float operator()(int m) const { return r[m]; } };
 struct HostPut { float* a; float* b; __host__ __device__ void operator()(int m, float x, float y) const { a[m] = x; b[m] = y; } };
 }  // namespace
-extern "C" int nazb_host_spline_grad(float x, int32_t K, float bound, const float* raw, float* ca, float* cb, float* inv_tx,
-                                     float* ldx) {
+extern "C" int nazb_host_spline_grad(float x, int32_t K, float bound, int32_t linear_order, const float* raw, float* ca,
+                                     float* cb, float* inv_tx, float* ldx) {
   if (!raw || !ca || !cb || !inv_tx || !ldx || K < 2 || K > 64) return NAZB_ERR_BAD_ARG;
-  nazb::rqs_grad(x, K, bound, HostRaw{raw}, HostPut{ca, cb}, *inv_tx, *ldx);
+  if (linear_order) nazb::spline_grad<true>(x, K, bound, HostRaw{raw}, HostPut{ca, cb}, *inv_tx, *ldx);
+  else nazb::spline_grad<false>(x, K, bound, HostRaw{raw}, HostPut{ca, cb}, *inv_tx, *ldx);
   return NAZB_OK;
 }
 
@@ -438,8 +439,8 @@ static int grad_impl(nazb_handle* h, int32_t s_begin, int32_t s_count, const flo
   if (rc != NAZB_OK) return rc;
   if (!mask || !gW || !gb || !gwst || !gbst) return NAZB_ERR_BAD_ARG;
   const FlowGeom& g = h->geom;
-  // masked-affine and quadratic neural-spline flows on the fp32 engine's image, no dropout
-  if ((g.kind != NAZB_KIND_AFFINE && g.kind != NAZB_KIND_RQS) || h->engine != NAZB_ENGINE_SIMT || !h->packed || h->has_keep || h->aff_dev || !nazb_grad_fits(g))
+  // masked-affine and neural-spline flows (both orders) on the fp32 engine's image, no dropout
+  if (h->engine != NAZB_ENGINE_SIMT || !h->packed || h->has_keep || h->aff_dev || !nazb_grad_fits(g))
     return NAZB_ERR_UNSUPPORTED;
   const int n = g.L * (g.n_hidden + 1);
   for (int i = 0; i < n; ++i)

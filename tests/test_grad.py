@@ -158,9 +158,10 @@ def test_inverse_grad_draw_range_and_unsupported():
     # the value agrees with the log_prob entry point
     lp = eng.inverse(x, ctx, want_lp=True)["lp"].double().sum(-1)
     assert torch.allclose(lp, full["sum_n"], rtol=1e-5)
-    # linear-order splines and tensor-core handles are not served: loud error, no fallback
-    spec2, draws2, _, _ = make_case("nsa", 3, 1, [16, 16], 2, 2, seed=3, order="linear")
-    eng2 = engine_for(spec2, draws2, engine="simt")
+    # tensor-core handles are not served: loud error, no fallback
+    spec2, draws2, _, _ = make_case("maf", 2, 1, [32, 32], 2, 2, seed=3)
+    eng2 = engine_for(spec2, draws2, engine="tcgen05")
+    x = x[:, :2].contiguous()
     with pytest.raises(_lib.NazbError):
         eng2.inverse_grad(x, ctx)
 
@@ -286,8 +287,8 @@ def test_flow_level_grad_oracle_maf_equals_twin_and_spline_matches_finite_differ
 # ----------------------------------------------------------------------------------------------------------------
 def test_device_spline_derivative_routine_on_the_host_matches_autograd(built_lib):
     """naz_b200/csrc/spline_grad.cuh compiled for the CPU (nazb_host_spline_grad; no GPU needed): 1/T', d ld/dx and the raw-slot
-    coefficients ca = -(dT/draw)/T', cb = -d ld/draw against torch autograd (fp64) of the oracle's spline, incl. the
-    identity region outside [-B, B], the first / last bins (fixed end derivatives) and K != 8."""
+    coefficients ca = -(dT/draw)/T', cb = -d ld/draw against torch autograd (fp64) of the oracle's spline, both orders, incl.
+    the identity region outside [-B, B], the first / last bins (fixed end derivatives) and K != 8."""
     import ctypes as C
     import torch.nn.functional as F
     from naz_b200 import _lib
@@ -297,17 +298,19 @@ def test_device_spline_derivative_routine_on_the_host_matches_autograd(built_lib
     errs, bins = [], set()
     for trial in range(600):
         K = (8, 8, 5, 12)[trial % 4]
-        M, B = 3 * K - 1, 3.0
+        linear = (trial // 4) % 2
+        M, B = (4 if linear else 3) * K - 1, 3.0
         raw = (rng.normal(size=M) * (0.5 + 1.5 * rng.uniform())).astype(np.float32)
         x = np.float32(rng.uniform(-3.4, 3.4) if trial % 7 else rng.choice([-2.999, 2.999, -3.2, 0.0]))
         ca, cb = np.zeros(M, np.float32), np.zeros(M, np.float32)
         itx, ldx = C.c_float(), C.c_float()
-        assert L.nazb_host_spline_grad(float(x), K, B, raw.ctypes.data, ca.ctypes.data, cb.ctypes.data, C.addressof(itx),
+        assert L.nazb_host_spline_grad(float(x), K, B, linear, raw.ctypes.data, ca.ctypes.data, cb.ctypes.data, C.addressof(itx),
                                        C.addressof(ldx)) == 0
         r = torch.tensor(raw.astype(np.float64), requires_grad=True)
         xt = torch.tensor(float(x), dtype=torch.float64, requires_grad=True)
         y, ld = ps.monotonic_rational_spline(xt[None], F.softmax(r[:K], -1)[None], F.softmax(r[K:2 * K], -1)[None],
-                                             F.softplus(r[2 * K:])[None], bound=B)
+                                             F.softplus(r[2 * K:3 * K - 1])[None],
+                                             torch.sigmoid(r[3 * K - 1:])[None] if linear else None, bound=B)
         gy = torch.autograd.grad(y.sum(), [r, xt], retain_graph=True, allow_unused=True)
         gl = torch.autograd.grad(ld.sum(), [r, xt], allow_unused=True)
         z = lambda t, n: np.zeros(n) if t is None else t.numpy()
@@ -320,15 +323,18 @@ def test_device_spline_derivative_routine_on_the_host_matches_autograd(built_lib
         errs.append([np.abs(ca - ca_ref).max() / max(1.0, np.abs(ca_ref).max()), np.abs(cb - cb_ref).max() / max(1.0, np.abs(cb_ref).max()),
                      abs(itx.value - 1.0 / tx) * tx, abs(ldx.value - float(z(gl[1], ()))) / max(1.0, abs(float(z(gl[1], ()))))])
     e = np.array(errs)
-    assert len(e) > 400 and np.median(e) < 5e-6 and e.max() < 5e-3, (np.median(e, 0), e.max(0))
+    # fp32 against fp64: round-off in the median; the tail are narrow bins (width ~ 1e-3 of the box: (x - X0) / W cancels)
+    assert len(e) > 400 and np.median(e) < 5e-6 and np.percentile(e, 99) < 5e-4 and e.max() < 3e-2, (np.median(e, 0), np.percentile(e, 99, 0), e.max(0))
 
 
 SPLINE_GRAD_CASES = [
-    # D C hidden L K S N bounds ctx_rows
-    (2, 0, [16, 16], 3, 8, 2, 37, False, 0),
-    (3, 2, [24, 24], 4, 8, 2, 100, True, "N"),
-    (4, 2, [150, 150, 150], 2, 8, 1, 70, False, 1),
-    (3, 1, [32, 32], 2, 5, 2, 45, False, "N"),
+    # D C hidden L K S N bounds ctx_rows order
+    (2, 0, [16, 16], 3, 8, 2, 37, False, 0, "quadratic"),
+    (3, 2, [24, 24], 4, 8, 2, 100, True, "N", "quadratic"),
+    (4, 2, [150, 150, 150], 2, 8, 1, 70, False, 1, "quadratic"),
+    (3, 1, [32, 32], 2, 5, 2, 45, False, "N", "quadratic"),
+    (3, 2, [24, 24], 3, 8, 2, 90, True, "N", "linear"),
+    (2, 1, [32, 32], 2, 6, 1, 50, False, 1, "linear"),
 ]
 
 
@@ -338,8 +344,8 @@ def test_inverse_grad_spline_matches_autograd_oracle(case):
     """nazb_inverse_grad on quadratic neural-spline flows against torch autograd (fp64) through the module-structured
     restatement — what the reference's torch path differentiates in `train` (train_flows.py:195-213)."""
     from helpers import engine_for
-    D, C, hidden, L, K, S, N, bounded, crow = case
-    spec, draws, _, rng = make_case("nsa", D, C, hidden, L, S, seed=13, count_bins=K)
+    D, C, hidden, L, K, S, N, bounded, crow, order = case
+    spec, draws, _, rng = make_case("nsa", D, C, hidden, L, S, seed=13, count_bins=K, order=order)
     x = (rng.normal(size=(N, D)) * 1.3).astype(np.float32)
     x[0, 0] = 3.5                                   # one coordinate in the identity region of the last layer's spline
     ctx = None
