@@ -469,6 +469,10 @@ bool build_inverse(const FlowGeom& g, TcPlan& P, int variant, int merge_n, std::
     bool empty0 = (g.blk[0][r + 1] == g.blk[0][r]);
     for (int j = 1; j < nh; ++j)
       if ((g.blk[j][r + 1] == g.blk[j][r]) != empty0) return false;   // blocks must be (non)empty together
+    // The programs are built (and tested) for the MADE degree ladder: every degree populated, except degree 0 of a flow without
+    // context.  Other ladders — e.g. the single-degree form of a coupling layer (flows/transforms.py::SplineCoupling), which
+    // this builder used to accept and evaluate wrongly — are declined here and served by the fp32 engine.
+    if (empty0 && (r > 0 || g.C > 0)) return false;
   }
   if (folded) {
     // needs a context, a non-empty degree-0 block and a transform whose rank-0 parameters fold into a small table

@@ -60,7 +60,7 @@ class Relabelling:
         self.ar_pos, self.q, self.bn = [], [], []
         for i, t in enumerate(transforms):
             kind = getattr(t, "kind", None)
-            if kind in ("maf", "nsa"):
+            if kind in ("maf", "nsa", "nsc"):
                 self.ar_pos.append(i); self.q.append(q.clone()); self.bn.append(None)
             elif kind == "permute":
                 q = q[t.permutation.cpu()]
@@ -197,10 +197,16 @@ class NormalizingFlow(nn.Module):
         count_bins = 8
         if flow_type == "nsa":
             count_bins = flow_maker_kwargs.get("count_bins", flow_maker_args[4] if len(flow_maker_args) > 4 else 8)
+        if flow_type == "nsc":
+            count_bins = flow_maker_kwargs.get("count_bins", flow_maker_args[4] if len(flow_maker_args) > 4 else 8)
         kind = "maf" if flow_type == "maf" else ("nsa" if order == "quadratic" else "nsa_linear")
-        self.shape = FlowShape(kind, self.theta_dim, self.condition_dim, list(hidden), len(self.nets), count_bins)
+        self.shape = FlowShape(kind, self.theta_dim, max(self.condition_dim, 0), list(hidden), len(self.nets), count_bins)
         self.dropout_p = flow_maker_kwargs.get("dropout_p", None)
+        # coupling layers reach the engine as single-degree masked conditioners (transforms.py::SplineCoupling): the tensor-core
+        # forward (sample) programs take them as they are, the tensor-core inverse programs are built for the MADE degree ladder
+        # and decline, so `log_prob` of these flows is served by the fp32 kernel (one conditioner pass per layer there)
         self._engine_kind = engine
+        self._layers = [self.transforms[i] for i in self.relabel.ar_pos]
         self._eng1: Optional[FlowEngine] = None
         self._eng1_key = None
         self._engg: Optional[FlowEngine] = None
@@ -208,12 +214,21 @@ class NormalizingFlow(nn.Module):
 
     # ------------------------------------------------------------------ packing helpers
     def masks(self):
+        if self.flow_type == "nsc":
+            dev = next(self.parameters()).device
+            return [[m.to(dev) for m in t.made_masks(self.shape.C)] for t in self._layers]
         return [[lin.mask for lin in arn.layers] for arn in self.nets]
 
     def perms(self):
+        if self.flow_type == "nsc":
+            return torch.arange(self.theta_dim).repeat(len(self.nets), 1)
         return torch.stack([arn.permutation.cpu() for arn in self.nets])
 
     def current_draw(self):
+        """[L][n_lin](W, b) in the engine's conditioner format (for coupling flows: the single-degree masked form)."""
+        if self.flow_type == "nsc":
+            return [t.as_made([(lin.weight.detach(), lin.bias.detach()) for lin in t.nn.layers],
+                              [g.detach() for g in t.lower_spline.groups(t.order)], self.shape.C) for t in self._layers]
         return [[(lin.weight.detach(), lin.bias.detach()) for lin in arn.layers] for arn in self.nets]
 
     def _packed_masks(self):
@@ -221,7 +236,7 @@ class NormalizingFlow(nn.Module):
         return [self.relabel.fold_layer(l, ml, self.condition_dim) for l, ml in enumerate(self.masks())]
 
     def _packed_perms(self):
-        return torch.stack([self.relabel.fold_perm(l, arn.permutation) for l, arn in enumerate(self.nets)])
+        return torch.stack([self.relabel.fold_perm(l, perm) for l, perm in enumerate(self.perms())])
 
     def _fold_draws(self, draws):
         if self.relabel.trivial:
@@ -273,9 +288,14 @@ class NormalizingFlow(nn.Module):
 
     def make_engine(self, draws, keep=None, p_drop: float = 0.0, device=None) -> FlowEngine:
         """Engine holding S draws given as the reference pytree `[L][n_lin](W[S,out,in], b[S,out])`
-        or as the `"flow_{i}_{name}"` dict."""
+        or as the `"flow_{i}_{name}"` dict (coupling flows: the dict, or a pytree already in the engine's conditioner format)."""
         if isinstance(draws, dict):
-            draws = draws_from_posterior_samples(draws, self.relabel.ar_pos, len(self.nets[0].layers))
+            post = draws
+            draws = draws_from_posterior_samples(post, self.relabel.ar_pos, len(self.nets[0].layers))
+            if self.flow_type == "nsc":
+                names = ["unnormalized_widths", "unnormalized_heights", "unnormalized_derivatives", "unnormalized_lambdas"]
+                draws = [t.as_made(layer, [post[f"flow_{i}_lower_spline.{n}"] for n in names[:len(t.slot_groups())]], self.shape.C)
+                         for i, t, layer in zip(self.relabel.ar_pos, self._layers, draws)]
         draws = self._fold_draws(draws)
         S = 1
         for layer in draws:
@@ -310,7 +330,7 @@ class NormalizingFlow(nn.Module):
                                "log_prob_draws(..., keep=masks, p_drop=p) for explicit MC-dropout masks")
         params = self._flat_params()
         if torch.is_grad_enabled() and (any(p.requires_grad for p in params) or (isinstance(x, torch.Tensor) and x.requires_grad)) \
-                and self.shape.kind in ("maf", "nsa") and not self.relabel.has_bn:
+                and self.flow_type in ("maf", "nsa") and not self.relabel.has_bn:
             return _LogProbFn.apply(self, x, self._cond(condition), *params)
         eng = self._single_engine()
         out = eng.inverse(self.relabel.to_engine(x), self._cond(condition), self._bounds_e(), want_lp=True)

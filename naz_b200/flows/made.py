@@ -94,3 +94,29 @@ class ConditionalAutoRegressiveNN(nn.Module):
 class AutoRegressiveNN(ConditionalAutoRegressiveNN):
     def __init__(self, input_dim, hidden_dims, **kw):
         super().__init__(input_dim, 0, hidden_dims, **kw)
+
+
+class ConditionalDenseNN(nn.Module):
+    """Weight container of pyro's `(Conditional)DenseNN` — the hyper-network of the coupling flow (src/naz/flows/transforms.py:
+    219-224): plain `nn.Linear` layers `[context | x1] -> hidden... -> sum(param_dims)`, named `layers.{k}` as upstream.  No
+    forward(): `NormalizingFlow` maps the coupling layer onto the engine's masked-conditioner format when it packs
+    (`flows/transforms.py::SplineCoupling.as_made`)."""
+
+    def __init__(self, input_dim: int, context_dim: int, hidden_dims: List[int], param_dims: List[int] = [1, 1], nonlinearity=None,
+                 dropout_p: Optional[float] = None):
+        super().__init__()
+        if nonlinearity is not None and not isinstance(nonlinearity, nn.Tanh):
+            raise NotImplementedError("libnazb implements naz's default activation, nn.Tanh() (transforms.py:201)")
+        self.input_dim, self.context_dim = input_dim, context_dim
+        self.hidden_dims, self.param_dims = list(hidden_dims), list(param_dims)
+        self.dropout_p = dropout_p
+        dims = [input_dim + context_dim] + self.hidden_dims + [sum(self.param_dims)]
+        self.layers = nn.ModuleList([nn.Linear(dims[i], dims[i + 1]) for i in range(len(dims) - 1)])
+
+    def forward(self, *a, **k):  # pragma: no cover - deliberate
+        raise RuntimeError("naz_b200 conditioners are evaluated by libnazb (CUDA); there is no PyTorch forward path")
+
+
+class DenseNN(ConditionalDenseNN):
+    def __init__(self, input_dim, hidden_dims, **kw):
+        super().__init__(input_dim, 0, hidden_dims, **kw)

@@ -5,7 +5,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from .made import AutoRegressiveNN, ConditionalAutoRegressiveNN
+from .made import AutoRegressiveNN, ConditionalAutoRegressiveNN, ConditionalDenseNN
 
 
 def bounding_transform(x, low, high):
@@ -135,6 +135,104 @@ def neural_spline_autoregressive(theta_dim, condition_dim, hidden_dim, num_layer
     return ComposeTransformModule(transforms), transforms, nets
 
 
-def neural_spline_coupling(*args, **kwargs):
-    """transforms.py:201-236 cannot be constructed upstream (undefined names); out of scope."""
-    raise NotImplementedError("'nsc' is unconstructible in the reference (transforms.py:201-236) and is out of scope")
+class _LowerSpline(nn.Module):
+    """Free parameters of the element-wise spline on the first `split_dim` coordinates (pyro `T.Spline`, the `lower_spline`
+    of `T.SplineCoupling`): same parameter names and initialisers as upstream."""
+
+    def __init__(self, input_dim, count_bins, order):
+        super().__init__()
+        self.unnormalized_widths = nn.Parameter(torch.randn(input_dim, count_bins))
+        self.unnormalized_heights = nn.Parameter(torch.randn(input_dim, count_bins))
+        self.unnormalized_derivatives = nn.Parameter(torch.randn(input_dim, count_bins - 1))
+        if order == "linear":
+            self.unnormalized_lambdas = nn.Parameter(torch.rand(input_dim, count_bins))
+
+    def groups(self, order):
+        g = [self.unnormalized_widths, self.unnormalized_heights, self.unnormalized_derivatives]
+        return g + ([self.unnormalized_lambdas] if order == "linear" else [])
+
+
+class SplineCoupling(nn.Module):
+    """`ConditionalSplineCoupling(...).condition(context)` / `T.SplineCoupling` (transforms.py:113-129, :226): the first
+    `split_dim` coordinates pass through an element-wise spline with free parameters, the others through a spline whose
+    parameters a dense hyper-network computes from [context | first part].
+
+    No kernel of its own: a coupling layer IS a masked conditioner with a single hidden degree — every hidden unit sees the
+    context and the first `split_dim` inputs, the outputs of the remaining coordinates see every hidden unit, the outputs of the
+    first part see none (their biases are the free spline parameters).  `as_made` writes it in that form (identity MADE order,
+    hyper-network rows re-indexed from pyro's dimension-major `[.., D - split, K]` to the engine's slot-major `m D + d`), and
+    the incremental inverse then costs ONE conditioner pass per layer (all hidden units become final at stage `split_dim`)."""
+    kind = "nsc"
+
+    def __init__(self, input_dim, split_dim, dense_nn, count_bins=8, bound=3.0, order="quadratic"):
+        super().__init__()
+        if not 0 < split_dim < input_dim:
+            raise ValueError("split_dim must lie strictly between 0 and input_dim")
+        self.input_dim, self.split_dim, self.count_bins, self.bound, self.order = input_dim, split_dim, count_bins, bound, order
+        self.nn = dense_nn
+        self.lower_spline = _LowerSpline(split_dim, count_bins, order)
+
+    def slot_groups(self):
+        K = self.count_bins
+        return [K, K, K - 1] + ([K] if self.order == "linear" else [])
+
+    def made_masks(self, context_dim):
+        D, s, C, H = self.input_dim, self.split_dim, context_dim, self.nn.hidden_dims
+        M = sum(self.slot_groups())
+        m0 = torch.zeros(H[0], C + D)
+        m0[:, :C + s] = 1.0
+        masks = [m0] + [torch.ones(H[i], H[i - 1]) for i in range(1, len(H))]
+        mo = torch.zeros(M, D, H[-1])
+        mo[:, s:, :] = 1.0
+        return masks + [mo.reshape(M * D, H[-1])]
+
+    def as_made(self, lins, lower_groups, context_dim):
+        """lins: the hyper-network's [(W, b)] (optionally with leading draw axes), lower_groups: the free parameters
+        [widths, heights, derivatives(, lambdas)] each [.., split_dim, K_g]  ->  [(W, b)] in the engine's conditioner format."""
+        D, s, C = self.input_dim, self.split_dim, context_dim
+        out = [(W, b) for (W, b) in lins]
+        W0, b0 = lins[0]
+        W0e = W0.new_zeros(W0.shape[:-1] + (C + D,))
+        W0e[..., :C + s] = W0
+        out[0] = (W0e, b0)
+        Wl, bl = lins[-1]
+        H = Wl.shape[-1]
+        lead_w, lead_b = Wl.shape[:-2], bl.shape[:-1]
+        rows_W, rows_b, off = [], [], 0
+        for Kg, low in zip(self.slot_groups(), lower_groups):
+            n = (D - s) * Kg
+            up_W = Wl[..., off:off + n, :].reshape(lead_w + (D - s, Kg, H)).transpose(-3, -2)          # [.., Kg, D - s, H]
+            up_b = bl[..., off:off + n].reshape(lead_b + (D - s, Kg)).transpose(-2, -1)                  # [.., Kg, D - s]
+            lo_b = low.to(bl.dtype).transpose(-2, -1)                                                    # [.., Kg, s]
+            lo_b = lo_b.expand(lead_b + lo_b.shape[-2:]) if lo_b.dim() < up_b.dim() else lo_b
+            rows_W.append(torch.cat([up_W.new_zeros(lead_w + (Kg, s, H)), up_W], dim=-2))                # [.., Kg, D, H]
+            rows_b.append(torch.cat([lo_b, up_b], dim=-1))                                               # [.., Kg, D]
+            off += n
+        We = torch.cat(rows_W, dim=-3)
+        be = torch.cat(rows_b, dim=-2)
+        out[-1] = (We.reshape(lead_w + (We.shape[-3] * D, H)), be.reshape(lead_b + (be.shape[-2] * D,)))
+        return out
+
+
+def neural_spline_coupling(theta_dim, condition_dim, hidden_dim, num_layers, count_bins, split_dim, order="quadratic",
+                           activation=None, use_batchnorm=False, random_perm=False, dropout_p=None):
+    """transforms.py:201-236, built to its evident intent.  Upstream the function cannot run: it reads the undefined names
+    `input_dim`, `paramdim` and `condotion_dim`, and its unconditional branch constructs `T.SplineAutoregressive` with coupling
+    arguments.  With those read as `theta_dim`, `param_dims`, `condition_dim` and `T.SplineCoupling` it is:
+    `num_layers` coupling layers, hyper-network `(Conditional)DenseNN(split_dim[, condition_dim], hidden_dims, param_dims)`,
+    optional Permute / BatchNorm behind each layer.  Semantics restated from pyro (unpinned: pyro is absent and no upstream
+    output can exist)."""
+    n = theta_dim - split_dim
+    param_dims = [n * count_bins, n * count_bins, n * (count_bins - 1)]
+    if order == "linear":
+        param_dims.append(n * count_bins)
+    elif order != "quadratic":
+        raise ValueError(order)
+    transforms, nets = [], []
+    for _ in range(num_layers):
+        arn = ConditionalDenseNN(split_dim, max(condition_dim, 0), _hidden_list(hidden_dim), param_dims=param_dims,
+                                 nonlinearity=activation, dropout_p=dropout_p)
+        nets.append(arn)
+        transforms.append(SplineCoupling(theta_dim, split_dim, arn, count_bins=count_bins, order=order))
+        _extras(transforms, theta_dim, use_batchnorm, random_perm)
+    return ComposeTransformModule(transforms), transforms, nets

@@ -92,6 +92,7 @@ class FlowSpec:
     bound: float = 3.0
     clip: Tuple[float, float] = (-5.0, 3.0)
     activation: str = "tanh"       # naz default nn.Tanh() (transforms.py:133,165)
+    masks_override: Optional[list] = None   # [L][n_lin] masks that are not the canonical MADE masks of `perms` (coupling layers)
 
     @property
     def M(self) -> int:
@@ -101,6 +102,8 @@ class FlowSpec:
         return 3 * K - 1 if self.order == "quadratic" else 4 * K - 1
 
     def masks(self):
+        if self.masks_override is not None:
+            return self.masks_override
         return [create_masks(self.D, self.C, self.hidden, self.perms[l], self.M)[0] for l in range(self.L)]
 
     def n_params(self) -> int:

@@ -897,3 +897,54 @@ def test_permute_and_batchnorm_flows(flow_type, use_bn):
         flow.train()
         with pytest.raises(RuntimeError):
             flow.log_prob(x.float().cuda(), condition=ctx.float().cuda())
+
+
+@pytest.mark.parametrize("engine", ["simt", "auto"])
+@pytest.mark.parametrize("order,random_perm,C", [("quadratic", False, 2), ("quadratic", True, 2), ("linear", True, 0)])
+def test_coupling_flow_nsc(order, random_perm, C, engine):
+    """flow_type 'nsc' through the product API (coupling layers as single-degree masked conditioners: log_prob on the fp32
+    kernel — the incremental inverse needs ONE conditioner pass per layer —, sample on the tensor-core forward programs with
+    engine="auto") against the explicit-transform restatement in fp64: log_prob, sample, and the draw-batched entry point fed
+    with the reference's posterior-sample dict."""
+    from helpers import explicit_coupling_flow
+    from naz_b200.flows import NormalizingFlow
+    torch.manual_seed(17)
+    D, s, hidden, L, K = 5, 2, [48, 48], 4, 8
+    import warnings
+    flow = NormalizingFlow("nsc", None, D, C, hidden, L, K, s, order=order, random_perm=random_perm, engine=engine).cuda()
+    build = explicit_coupling_flow(flow, order)
+    N = 600
+    x = (torch.randn(N, D) * 1.4).double()
+    x[0, 0], x[1, 4] = 3.6, -3.3                          # identity region of both splines
+    ctx = torch.randn(N, C).double() if C else None
+    z = torch.randn(N, D).double()
+    with torch.no_grad():
+        pdf = build(ctx)
+        lp_ref = pdf.log_prob(x).numpy()
+        xs = z
+        for t in pdf.transforms:
+            xs = t(xs)
+        xs_ref = xs.numpy()
+    cg = None if ctx is None else ctx.float().cuda()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)       # "the inverse direction ... runs on the fp32 SIMT kernel"
+        lp = flow.log_prob(x.float().cuda(), condition=cg)
+    eng = flow._single_engine()
+    print(f"nsc {order} engine={engine}: inverse on {eng.engine_for('inverse')}, forward on {eng.engine_for('forward')}")
+    assert eng.engine_for("inverse") == "simt"              # the tensor-core inverse programs decline single-degree ladders
+    if engine == "simt":
+        assert eng.engine_for("forward") == "simt"
+    elif order == "quadratic":
+        assert eng.engine_for("forward") == "tcgen05"
+    check(lp, lp_ref, f"nsc {order} log_prob")
+    xs = flow.sample(condition=cg, base_noise=z.float().cuda())
+    check(xs, xs_ref, f"nsc {order} sample", atol=2e-5)
+    S = 3
+    post = {}
+    for i, t in enumerate(flow.transforms):
+        for name, p in t.named_parameters():
+            post[f"flow_{i}_{name}"] = torch.stack([p.detach() * (1.0 + 0.01 * k) for k in range(S)])
+    lps = flow.log_prob_draws(x.float().cuda(), post, condition=cg)
+    assert lps.shape == (S, N)
+    check(lps[0], lp_ref, "nsc log_prob_draws(dict)[0]")
+    assert float((lps[1] - lps[0]).abs().max()) > 1e-3

@@ -398,3 +398,44 @@ def test_permute_and_batchnorm_layers_fold_into_the_packed_flow(flow_type):
     from naz_b200.trainers.train_flows import get_params
     gp = get_params(flow)
     assert len(gp) == 3 * L and set(gp[1]) == set() and set(gp[2]) == {"gamma", "beta"}
+
+
+@pytest.mark.parametrize("order,random_perm,C", [("quadratic", False, 2), ("quadratic", True, 2), ("linear", True, 0)])
+def test_coupling_flow_is_a_single_degree_masked_conditioner(order, random_perm, C):
+    """'nsc' (transforms.py:201-236, built to its evident intent).  The product hands a coupling layer to libnazb as a masked
+    conditioner with one hidden degree (`SplineCoupling.as_made`).  Checked here without a GPU: the numpy oracle evaluated on
+    exactly those weights / masks / orders (+ the Permute re-labelling) equals the explicit-transform restatement, in both
+    directions; the masks are canonical MADE masks for the engine's incremental inverse with all hidden degrees = split_dim."""
+    from naz_b200.engine import hidden_degrees_from_masks
+    from naz_b200.flows.flow import NormalizingFlow
+    from oracle import flow_oracle as fo
+    torch.manual_seed(7)
+    D, s, hidden, L, K = 5, 2, [20, 20], 3, 6
+    flow = NormalizingFlow("nsc", None, D, C, hidden, L, K, s, order=order, random_perm=random_perm)
+    assert flow.shape.M == (4 * K - 1 if order == "linear" else 3 * K - 1)
+    from helpers import explicit_coupling_flow
+    build = explicit_coupling_flow(flow, order)
+    N = 50
+    x = torch.randn(N, D, dtype=torch.float64) * 1.5
+    ctx = torch.randn(N, C, dtype=torch.float64) if C else None
+    z = torch.randn(N, D, dtype=torch.float64)
+    with torch.no_grad():
+        pdf = build(ctx)
+        lp_ref = pdf.log_prob(x).numpy()
+        xs = z
+        for t in pdf.transforms:
+            xs = t(xs)
+        xs_ref = xs.numpy()
+    masks_e = [[m.numpy() for m in ml] for ml in flow._packed_masks()]
+    perms_e = flow._packed_perms().numpy()
+    kind = "nsa"
+    spec = fo.FlowSpec(kind, D, C, hidden, L, perms_e, count_bins=K, order=order, masks_override=masks_e)
+    params_e = [[(W.double().numpy(), b.double().numpy()) for (W, b) in layer] for layer in flow._fold_draws(flow.current_draw())]
+    cn = None if ctx is None else ctx.numpy()
+    _, lp_e = fo.flow_inverse(spec, params_e, flow.relabel.to_engine(x).numpy(), cn)
+    np.testing.assert_allclose(lp_e, lp_ref, rtol=1e-5, atol=1e-5)          # parameters are fp32 on both sides; fp64 arithmetic
+    xs_e, _ = fo.flow_forward(spec, params_e, z.numpy(), cn)
+    np.testing.assert_allclose(flow.relabel.from_engine(torch.as_tensor(xs_e)).numpy(), xs_ref, rtol=1e-5, atol=1e-5)
+    for l in range(L):
+        degs = hidden_degrees_from_masks([torch.as_tensor(m) for m in masks_e[l]], torch.as_tensor(perms_e[l]), D, C)
+        assert degs is not None and all(set(d) == {s if C else s} for d in degs), degs
