@@ -245,6 +245,8 @@ int nazb_hpd(const float* v, int32_t S, int64_t M, double alpha, float* lo, floa
  *                  a group before all finished issuing the previous one, 3 = one group of slack, 1 (default) = by tile count
  *   "grad_diag" / "grad_tile"  nazb_inverse_grad (any engine): 1 = skip the gradient atomics (timing diagnosis) / 16 = force
  *                  16-point tiles (default 0: by shared-memory fit)
+ *   "grad_stash"   1 (default) nazb_inverse_grad parks the conditioner activations of its value pass in a per-CTA scratch area
+ *                  (grow-only device allocation, ~1 MB per resident CTA) instead of recomputing them in the adjoint pass
  * nazb_get_option also answers "inv_fold_available", "inv_kernel_in_use", "inv_a_tmem_in_use", "inv_block_width" and "watchdog" (non-zero after a kernel aborted on a barrier time-out:
  * site | warp << 8 | block << 16).  Unknown names return NAZB_ERR_BAD_ARG, the SIMT engine NAZB_ERR_UNSUPPORTED. */
 int nazb_set_option(nazb_handle* h, const char* name, int32_t value);

@@ -47,6 +47,9 @@ struct GradArgs {
   const long long* gwst;      // floats between draws of gW[i]
   const long long* gbst;
   float* dx;                  // [s_count][N][D] or null
+  float* stash;               // per resident CTA: [L][n_hidden * hmax * P + md_pad * P] conditioner activations / raw outputs of phase A
+  long long stash_cta;        // floats per CTA (0 = no stash: phase B recomputes the conditioner)
+  int tiles;                  // point tiles per draw; work item w = draw * tiles + tile, CTA b takes w = b, b + gridDim.x, ...
   const float* wgt;           // per-point cotangents of lp, [s_count][N] (draw stride wgt_stride, 0 = shared) or null (= 1)
   long long wgt_stride;
   int diag;                   // dev: 1 = skip the atomics (timing diagnosis only)
@@ -156,10 +159,17 @@ __global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_kernel(
   float* red = wbuf + NST * T::WCHUNK;
 
   const int tid = threadIdx.x;
-  const int n0 = blockIdx.x * P;
-  const int npts = min(P, io.N - n0);
+  // Phase A leaves every hidden activation and raw conditioner output of a flow layer final (block r at stage r): instead of
+  // recomputing the conditioner at the solved x in phase B they are parked in a per-CTA scratch area in global memory
+  // (L2-resident: ~1 MB per CTA written and read once per work item) — one conditioner pass less per layer.
+  const bool use_stash = ga.stash_cta > 0 && g.inv_mode == NAZB_INV_INCREMENTAL;
+  float* stash = use_stash ? ga.stash + (size_t)blockIdx.x * ga.stash_cta : nullptr;
+  const size_t stash_h = (size_t)nh * g.hmax * P, stash_l = stash_h + (size_t)md_pad * P;
 
-  for (int si = blockIdx.y; si < io.s_count; si += gridDim.y) {
+  for (long long item = blockIdx.x; item < (long long)ga.tiles * io.s_count; item += gridDim.x) {
+    const int si = (int)(item / ga.tiles);
+    const int n0 = (int)(item % ga.tiles) * P;
+    const int npts = min(P, io.N - n0);
     const int sg = io.s_begin + si;
     const float* wdraw = packed + (size_t)sg * g.draw_stride;
     const float* wdrawT = packedT + (size_t)sg * gg.draw_strideT;
@@ -209,6 +219,10 @@ __global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_kernel(
         }
         if (tid < P) {
           const int p = tid, d = perm[r];
+          if (use_stash) {
+            float* so = stash + (size_t)l * stash_l + stash_h + (size_t)(r * M) * P + p;
+            for (int m = 0; m < M; ++m) so[m * P] = obuf[(size_t)(r * M + m) * P + p];   // raw outputs, before the spline's scratch writes
+          }
           if (!SPLINE) {
             float mu = obuf[(r * 2 + 0) * P + p];
             float s = fminf(fmaxf(obuf[(r * 2 + 1) * P + p], g.clip_lo), g.clip_hi);
@@ -233,6 +247,11 @@ __global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_kernel(
         chain[((size_t)l * D + d) * P + p] = xv;
         gcur[d * P + p] = xv;
         xin[(C + d) * P + p] = 0.f;
+      }
+      if (use_stash) {
+        float4* dst = reinterpret_cast<float4*>(stash + (size_t)l * stash_l);
+        const float4* src = reinterpret_cast<const float4*>(hbuf);
+        for (size_t i = tid; i < stash_h / 4; i += kThreads) dst[i] = src[i];
       }
       __syncthreads();
     }
@@ -275,12 +294,21 @@ __global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_kernel(
         xin[(C + d) * P + p] = chain[((size_t)l * D + d) * P + p];
       }
       __syncthreads();
-      // conditioner at the solved x
-      for (int j = 0; j < nh; ++j)
-        gemm_panel_ms<P, true, TN, NST>((j == 0) ? xin : hbuf + (size_t)(j - 1) * g.hmax * P, g.kdim[j], wl + g.off_w[j], g.ldw[j],
-                            wl + g.off_b[j], 0, g.hidden[j], hbuf + (size_t)j * g.hmax * P, wbuf);
-      gemm_panel_ms<P, false, TN, NST>(hbuf + (size_t)(nh - 1) * g.hmax * P, g.kdim[nh], wl + g.off_w[nh], g.ldw[nh],
-                           wl + g.off_b[nh], 0, g.md, obuf, wbuf);
+      // conditioner at the solved x: parked by phase A, or recomputed
+      if (use_stash) {
+        const float4* src = reinterpret_cast<const float4*>(stash + (size_t)l * stash_l);
+        float4* dh = reinterpret_cast<float4*>(hbuf);
+        float4* dobuf = reinterpret_cast<float4*>(obuf);
+        for (size_t i = tid; i < stash_h / 4; i += kThreads) dh[i] = src[i];
+        for (size_t i = tid; i < (size_t)md_pad * P / 4; i += kThreads) dobuf[i] = src[stash_h / 4 + i];
+        __syncthreads();
+      } else {
+        for (int j = 0; j < nh; ++j)
+          gemm_panel_ms<P, true, TN, NST>((j == 0) ? xin : hbuf + (size_t)(j - 1) * g.hmax * P, g.kdim[j], wl + g.off_w[j], g.ldw[j],
+                              wl + g.off_b[j], 0, g.hidden[j], hbuf + (size_t)j * g.hmax * P, wbuf);
+        gemm_panel_ms<P, false, TN, NST>(hbuf + (size_t)(nh - 1) * g.hmax * P, g.kdim[nh], wl + g.off_w[nh], g.ldw[nh],
+                             wl + g.off_b[nh], 0, g.md, obuf, wbuf);
+      }
       for (int i = tid; i < P * D; i += kThreads) {
         const int p = i % P, r = i / P, d = perm[r];
         const float xv = xin[(C + d) * P + p];
@@ -467,7 +495,25 @@ cudaError_t nazb_grad_launch(nazb_handle* h, const IoArgs& io, const void* tabs,
   const size_t smem = (P == 16) ? grad_smem_bytes(g, 16, 2, 3) : grad_smem_bytes(g, 32, nst, 5);
   if (smem > cap) return cudaErrorInvalidConfiguration;
   const int tiles = (io.N + P - 1) / P;
-  dim3 grid(tiles, std::min(io.s_count, 65535));
+  // persistent CTAs over (draw, tile) work items, draw-major (concurrent CTAs share a draw's weights in L2)
+  const long long items = (long long)tiles * io.s_count;
+  const int resident = h->sm_count * ((P == 16) ? 2 : 1);
+  dim3 grid((unsigned)std::min<long long>(items, resident));
+  ga.tiles = tiles;
+  {
+    const int md_pad = (g.md + 3) & ~3;
+    const long long per_cta = (long long)g.L * ((long long)g.n_hidden * g.hmax + md_pad) * P;
+    const size_t need = sizeof(float) * (size_t)per_cta * resident;
+    if (h->opt_grad_stash && g.inv_mode == NAZB_INV_INCREMENTAL) {
+      if (h->grad_stash_bytes < need) {
+        if (h->grad_stash) { if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e; cudaFree(h->grad_stash); h->grad_stash = nullptr; h->grad_stash_bytes = 0; }
+        if ((e = cudaMalloc(&h->grad_stash, need)) != cudaSuccess) return e;
+        h->grad_stash_bytes = need;
+      }
+      ga.stash = static_cast<float*>(h->grad_stash);
+      ga.stash_cta = per_cta;
+    }
+  }
 #define NAZB_GRAD_LAUNCH_K(PP, NS, TT, SP)                                                                                 \
   e = cudaFuncSetAttribute(flow_grad_kernel<PP, NS, TT, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
   if (e != cudaSuccess) return e;                                                                                          \

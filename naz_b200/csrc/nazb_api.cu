@@ -124,6 +124,7 @@ extern "C" void nazb_destroy(nazb_handle* h) {
   if (h->packed) cudaFree(h->packed);
   if (h->packed_T) cudaFree(h->packed_T);
   if (h->grad_tabs) cudaFree(h->grad_tabs);
+  if (h->grad_stash) cudaFree(h->grad_stash);
   if (h->perm_dev) cudaFree(h->perm_dev);
   if (h->aff_dev) cudaFree(h->aff_dev);
   if (h->stage_host) cudaFreeHost(h->stage_host);
@@ -152,6 +153,7 @@ unsigned int nazb_tc_watchdog(const nazb_handle* h);
 extern "C" int nazb_set_option(nazb_handle* h, const char* name, int32_t value) {
   if (!h || !name) return NAZB_ERR_BAD_ARG;
   if (!strcmp(name, "grad_diag")) { h->opt_grad_diag = value ? 1 : 0; return NAZB_OK; }
+  if (!strcmp(name, "grad_stash")) { h->opt_grad_stash = value ? 1 : 0; return NAZB_OK; }
   if (!strcmp(name, "grad_tile")) { if (value != 0 && value != 16 && value != 32) return NAZB_ERR_BAD_ARG; h->opt_grad_tile = value; return NAZB_OK; }
   if (h->engine != NAZB_ENGINE_TCGEN05) return NAZB_ERR_UNSUPPORTED;
   return nazb_tc_set_option(h, name, value);
@@ -159,6 +161,7 @@ extern "C" int nazb_set_option(nazb_handle* h, const char* name, int32_t value) 
 extern "C" int nazb_get_option(const nazb_handle* h, const char* name, int32_t* value) {
   if (!h || !name || !value) return NAZB_ERR_BAD_ARG;
   if (!strcmp(name, "grad_diag")) { *value = h->opt_grad_diag; return NAZB_OK; }
+  if (!strcmp(name, "grad_stash")) { *value = h->opt_grad_stash; return NAZB_OK; }
   if (!strcmp(name, "grad_tile")) { *value = h->opt_grad_tile; return NAZB_OK; }
   if (!strcmp(name, "watchdog")) { *value = (h->engine == NAZB_ENGINE_TCGEN05) ? (int32_t)nazb_tc_watchdog(h) : 0; return NAZB_OK; }
   if (h->engine != NAZB_ENGINE_TCGEN05) return NAZB_ERR_UNSUPPORTED;

@@ -77,6 +77,9 @@ struct nazb_handle {
   float* packed_T = nullptr;
   bool packed_T_valid = false;
   void* grad_tabs = nullptr;
+  void* grad_stash = nullptr;   // per-CTA scratch of nazb_inverse_grad (activations parked by phase A), grow-only
+  size_t grad_stash_bytes = 0;
+  int opt_grad_stash = 1;   // nazb_set_option "grad_stash": 0 = recompute the conditioner in the adjoint phase instead
   int opt_grad_diag = 0;    // nazb_set_option "grad_diag": 1 = skip the gradient atomics (timing diagnosis only)
   int opt_grad_tile = 0;    // nazb_set_option "grad_tile": 16 = force 16-point tiles (0 = by shared-memory fit)
   std::string cuda_err;
