@@ -27,6 +27,7 @@
 // the SIMT image once per pack.
 #include <algorithm>
 #include <cstdlib>
+#include <cstdint>
 #include "nazb_internal.h"
 #include "transforms.cuh"
 #include "spline_grad.cuh"
@@ -109,10 +110,26 @@ __device__ __forceinline__ void outer_acc(const float* __restrict__ aT, int K, c
       const int n = n0 + j;
       if (n >= Nn) continue;
       const int row = out_layer ? ((n % M) * D + perm[n / M]) : n;
+      const float* mrow = mask + (size_t)row * K + k0;
+      float* grow = gW + (size_t)row * K + k0;
+      // pairs of neighbouring entries go out as one 8-byte reduction when both are unmasked and the address allows it
+      // (MADE masks are block-structured, so pairs almost always share their mask bit): half the mask loads and atomics
+      const bool pairs = ((K & 1) == 0) && ((reinterpret_cast<uintptr_t>(grow) & 7) == 0) && ((reinterpret_cast<uintptr_t>(mrow) & 7) == 0);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 4; i += 2) {
         const int k = k0 + i;
-        if (k < K && mask[(size_t)row * K + k] != 0.f && (!diag || acc[i][j] == 12345.678f)) atomicAdd(gW + (size_t)row * K + k, acc[i][j]);
+        if (pairs && k + 1 < K) {
+          const float2 m = *reinterpret_cast<const float2*>(mrow + i);
+          const bool d0 = !diag || acc[i][j] == 12345.678f, d1 = !diag || acc[i + 1][j] == 12345.678f;
+          if (m.x != 0.f && m.y != 0.f && d0 && d1) atomicAdd(reinterpret_cast<float2*>(grow + i), make_float2(acc[i][j], acc[i + 1][j]));
+          else {
+            if (m.x != 0.f && d0) atomicAdd(grow + i, acc[i][j]);
+            if (m.y != 0.f && d1) atomicAdd(grow + i + 1, acc[i + 1][j]);
+          }
+        } else {
+          if (k < K && mrow[i] != 0.f && (!diag || acc[i][j] == 12345.678f)) atomicAdd(grow + i, acc[i][j]);
+          if (k + 1 < K && mrow[i + 1] != 0.f && (!diag || acc[i + 1][j] == 12345.678f)) atomicAdd(grow + i + 1, acc[i + 1][j]);
+        }
       }
     }
   }
