@@ -140,15 +140,19 @@ class Relabelling:
 
 
 class _LogProbFn(torch.autograd.Function):
-    """Autograd node of `NormalizingFlow.log_prob`: value and gradient come from ONE fp32-engine handle (a single re-pack per
-    optimiser step; the backward pass, 6-7x the value pass, dominates a training step anyway); `backward` is ONE launch of
+    """Autograd node of `NormalizingFlow.log_prob`.  Minibatches (< `BIG` points): value and gradient come from ONE fp32-engine
+    handle (a single re-pack per optimiser step; the backward pass, 6-7x the value pass, dominates a training step anyway).
+    Large batches: the value comes from the module's forward engine (tensor cores), so an evaluation that merely forgot
+    `torch.no_grad()` keeps its speed.  `backward` is ONE launch of
     nazb_inverse_vjp (the incremental inverse recomputed, then the adjoint recursion; naz_b200/csrc/flow_grad.cu) — so the
     reference's MLE loop `loss = -flow.log_prob(x, condition=y).mean(); loss.backward(); optimizer.step()`
     (train_flows.py:195-213) runs on this path unchanged."""
 
+    BIG = 16384
+
     @staticmethod
     def forward(ctx, flow, x, cond, *params):
-        eng = flow._grad_engine()
+        eng = flow._grad_engine() if x.shape[0] < _LogProbFn.BIG else flow._single_engine()
         lp = eng.inverse(flow.relabel.to_engine(x), cond, flow._bounds_e(), want_lp=True)["lp"][0]
         ctx.flow, ctx.cond = flow, cond
         ctx.versions = tuple(p._version for p in params)
@@ -329,9 +333,16 @@ class NormalizingFlow(nn.Module):
             raise RuntimeError("log_prob on a dropout flow in train() mode: call flow.eval() for the deterministic density, or "
                                "log_prob_draws(..., keep=masks, p_drop=p) for explicit MC-dropout masks")
         params = self._flat_params()
-        if torch.is_grad_enabled() and (any(p.requires_grad for p in params) or (isinstance(x, torch.Tensor) and x.requires_grad)) \
-                and self.flow_type in ("maf", "nsa") and not self.relabel.has_bn:
-            return _LogProbFn.apply(self, x, self._cond(condition), *params)
+        if torch.is_grad_enabled() and (any(p.requires_grad for p in params) or (isinstance(x, torch.Tensor) and x.requires_grad)):
+            cond = self._cond(condition)
+            if isinstance(cond, torch.Tensor) and cond.requires_grad:
+                raise NotImplementedError("the gradient with respect to the context (a trainable embedding_net) is not built; "
+                                          "detach the embedding or freeze it")
+            if self.flow_type in ("maf", "nsa") and not self.relabel.has_bn:
+                return _LogProbFn.apply(self, x, cond, *params)
+            if self.training:
+                raise NotImplementedError("gradients of coupling ('nsc') and BatchNorm flows are not built: log_prob in train() mode "
+                                          "with autograd enabled would silently return a constant — call flow.eval() / torch.no_grad()")
         eng = self._single_engine()
         out = eng.inverse(self.relabel.to_engine(x), self._cond(condition), self._bounds_e(), want_lp=True)
         return out["lp"][0]

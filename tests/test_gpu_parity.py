@@ -912,6 +912,9 @@ def test_coupling_flow_nsc(order, random_perm, C, engine):
     D, s, hidden, L, K = 5, 2, [48, 48], 4, 8
     import warnings
     flow = NormalizingFlow("nsc", None, D, C, hidden, L, K, s, order=order, random_perm=random_perm, engine=engine).cuda()
+    with pytest.raises(NotImplementedError):               # train() mode + autograd: no silent constant
+        flow.log_prob(torch.zeros(4, D).cuda(), condition=torch.zeros(4, C).cuda() if C else None)
+    flow.eval()
     build = explicit_coupling_flow(flow, order)
     N = 600
     x = (torch.randn(N, D) * 1.4).double()

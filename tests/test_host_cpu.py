@@ -118,7 +118,10 @@ def test_flow_api_mirrors_reference_formats():
     with pytest.raises(AssertionError):
         MCDPNormalizingFlow("maf", None, 2, 0, [16], 2, dropout_p=None)
     with pytest.raises(NotImplementedError):
-        NormalizingFlow("nsc", None, 4, 2, [32], 2, 8, 2)
+        NormalizingFlow("cnf", None, 4, 2, [32], 2)                  # continuous flows are outside the north star
+    nsc = NormalizingFlow("nsc", None, 4, 2, [32], 2, 8, 2)          # coupling flows: built
+    assert [n for n, _ in nsc.flow_dist.transforms[0].named_parameters()][:3] == [
+        "nn.layers.0.weight", "nn.layers.0.bias", "nn.layers.1.weight"]
 
 
 def test_hidden_degrees_recovered_from_masks():

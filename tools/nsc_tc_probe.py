@@ -5,7 +5,7 @@ import torch
 from naz_b200.flows import NormalizingFlow
 torch.manual_seed(1)
 D, C, s = 4, 2, 2
-flow = NormalizingFlow("nsc", None, D, C, [150, 150, 150], 16, 8, s).cuda()
+flow = NormalizingFlow("nsc", None, D, C, [150, 150, 150], 16, 8, s).cuda().eval()
 x = (torch.randn(20000, D) * 1.3).cuda(); c = torch.rand(20000, C).cuda(); z = torch.randn(20000, D).cuda()
 lp_s = flow.log_prob(x, condition=c); xs_s = flow.sample(condition=c, base_noise=z)
 flow._engine_kind = "auto"; flow._eng1 = None
