@@ -197,13 +197,16 @@ int nazb_inverse_grad(nazb_handle* h, int32_t s_begin, int32_t s_count, const fl
 
 /* The same pass with caller-given cotangents of lp — the vector-Jacobian product behind `loss.backward()` of the reference's
  * MLE loop (src/naz/trainers/train_flows.py:195-213: loss = -flow.log_prob(x_batch, condition=y_batch).mean(); loss.backward()):
- *   gW[i][s] += sum_n w[s][n] d lp[s][n] / d W_i,   gb likewise,   dx[s][n][:] = w[s][n] d lp[s][n] / d x_n.
+ *   gW[i][s] += sum_n w[s][n] d lp[s][n] / d W_i,   gb likewise,   dx[s][n][:] = w[s][n] d lp[s][n] / d x_n,
+ *   dctx[s][n][:] = w[s][n] d lp[s][n] / d ctx_n  (device fp32 [s_count][N][C] or NULL; for a broadcast context the caller sums
+ *   over n) — the cotangent a trainable embedding network in front of the flow needs (src/naz/flows/flow.py:30-36, :75).
  * w: device fp32, draw s at w + (s - s_begin) * w_draw_stride (0 = one [N] vector shared by the draws).  Same coverage as
  * nazb_inverse_grad, which is the case w == 1. */
 int nazb_inverse_vjp(nazb_handle* h, int32_t s_begin, int32_t s_count, const float* x, const float* ctx,
                      int32_t ctx_rows, int32_t N, const float* lo, const float* hi,
                      const float* const* mask, float* const* gW, float* const* gb, const int64_t* gwst,
-                     const int64_t* gbst, float* dx, float* lp, const float* w, int64_t w_draw_stride, void* stream);
+                     const int64_t* gbst, float* dx, float* dctx, float* lp, const float* w, int64_t w_draw_stride,
+                     void* stream);
 
 /* Stand-alone cross-draw reduction over a materialised lp[S][N] (kernel group 4):
  * partial (max, sum exp) per point over this rank's draws.  HBM-bound: 4*S*N bytes read. */

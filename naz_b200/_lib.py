@@ -102,7 +102,7 @@ def lib() -> C.CDLL:
     L.nazb_truncnorm_sample.restype = C.c_int
     L.nazb_inverse_grad.argtypes = [vp, i32, i32, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.nazb_inverse_grad.restype = C.c_int
-    L.nazb_inverse_vjp.argtypes = [vp, i32, i32, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
+    L.nazb_inverse_vjp.argtypes = [vp, i32, i32, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
     L.nazb_inverse_vjp.restype = C.c_int
     L.nazb_set_option.argtypes = [vp, C.c_char_p, i32]
     L.nazb_set_option.restype = C.c_int

@@ -48,6 +48,7 @@ struct GradArgs {
   const long long* gwst;      // floats between draws of gW[i]
   const long long* gbst;
   float* dx;                  // [s_count][N][D] or null
+  float* dctx;                // [s_count][N][C] or null: cotangent of the context rows (a trainable embedding net upstream)
   float* stash;               // per resident CTA: [L][n_hidden * hmax * P + md_pad * P] conditioner activations / raw outputs of phase A
   long long stash_cta;        // floats per CTA (0 = no stash: phase B recomputes the conditioner)
   int tiles;                  // point tiles per draw; work item w = draw * tiles + tile, CTA b takes w = b, b + gridDim.x, ...
@@ -168,10 +169,11 @@ __global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_kernel(
   float* ldacc = cb + (size_t)md_pad * P;              // [P]
   float* ljac = ldacc + P;                             // [P]
   float* pwv = ljac + P;                               // [P]  cotangent of lp per point (nazb_inverse_vjp; 1 for the plain gradient)
+  float* dcacc = pwv + P;                              // [C][P]  d (w lp) / d ctx, summed over the flow layers
   // zero bias of the transposed products: they read bias[n] for n < max(hidden widths, kin) (the back-propagation to the
   // conditioner input has kin = C + D output columns, which a wide context can make larger than every hidden layer)
   const int zb_n = (g.hmax > kin_pad) ? g.hmax : kin_pad;
-  float* zb = pwv + P;                                 // [zb_n]
+  float* zb = dcacc + (size_t)C * P;                   // [zb_n]
   float* wbuf = zb + zb_n;                             // [NST][WCHUNK]
   float* red = wbuf + NST * T::WCHUNK;
 
@@ -193,6 +195,7 @@ __global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_kernel(
     // ---- load tile ----
     for (int i = tid; i < kin_pad * P; i += kThreads) xin[i] = 0.f;
     for (int i = tid; i < zb_n; i += kThreads) zb[i] = 0.f;
+    for (int i = tid; i < C * P; i += kThreads) dcacc[i] = 0.f;
     if (tid < P) {
       ldacc[tid] = 0.f; ljac[tid] = 0.f;
       pwv[tid] = (tid < npts) ? (ga.wgt ? ga.wgt[(size_t)si * ga.wgt_stride + n0 + tid] : 1.f) : 0.f;
@@ -416,6 +419,10 @@ __global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_kernel(
             int p = i % P, d = i / P;
             lam[i] = gcur[i] + dxb[(C + d) * P + p];
           }
+        } else if (ga.dctx != nullptr && C > 0) {
+          // the context enters every layer's first linear: its cotangent is the first C columns of W_0^T delta_0, summed over layers
+          gemm_panel_ms<P, false, TN, NST>(src, g.ndim[0], wlT + gg.offT[0], gg.ldk[0], zb, 0, C, dxb, wbuf);
+          for (int i = tid; i < C * P; i += kThreads) dcacc[i] += dxb[i];
         }
         __syncthreads();
       }
@@ -426,6 +433,10 @@ __global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_kernel(
         gcur[d * P + p] = lam[d * P + p] * es[r * P + p];
       }
       __syncthreads();
+    }
+    if (ga.dctx != nullptr && C > 0) {
+      float* dst = ga.dctx + ((size_t)si * io.N + n0) * C;
+      for (int i = tid; i < npts * C; i += kThreads) dst[i] = dcacc[(i % C) * P + i / C];
     }
     if (ga.dx) {
       float* dst = ga.dx + ((size_t)si * io.N + n0) * D;
@@ -448,7 +459,7 @@ __global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_kernel(
 size_t grad_smem_bytes(const FlowGeom& g, int P, int nst, int tn) {
   const int kin_pad = (g.kin + 3) & ~3, md_pad = (g.md + 3) & ~3;
   size_t f = (size_t)2 * kin_pad * P + (size_t)3 * g.D * P + (size_t)(g.n_hidden + 2) * g.hmax * P +
-             (size_t)4 * md_pad * P + (size_t)g.L * g.D * P + 3 * P + (size_t)((g.hmax > kin_pad) ? g.hmax : kin_pad);
+             (size_t)4 * md_pad * P + (size_t)g.L * g.D * P + 3 * P + (size_t)g.C * P + (size_t)((g.hmax > kin_pad) ? g.hmax : kin_pad);
   int TR = P / 4, TC = kThreads / TR, NPASS = TC * tn;
   f += (size_t)nst * kKC * NPASS;
   f += 2 * (kThreads / 32) + 4;
@@ -471,7 +482,7 @@ GradGeom make_grad_geom(const FlowGeom& g) {
 }  // namespace
 
 // Gradient launcher.  `tabs` = device memory holding the five tables (mask, gW, gb pointers; gW, gb draw strides).
-cudaError_t nazb_grad_launch(nazb_handle* h, const IoArgs& io, const void* tabs, float* dx, const float* wgt,
+cudaError_t nazb_grad_launch(nazb_handle* h, const IoArgs& io, const void* tabs, float* dx, float* dctx, const float* wgt,
                              long long wgt_stride, cudaStream_t st) {
   const FlowGeom& g = h->geom;
   const GradGeom gg = make_grad_geom(g);
@@ -499,6 +510,7 @@ cudaError_t nazb_grad_launch(nazb_handle* h, const IoArgs& io, const void* tabs,
   ga.gwst = reinterpret_cast<const long long*>(t + sizeof(void*) * 3 * n);
   ga.gbst = reinterpret_cast<const long long*>(t + sizeof(void*) * 4 * n);
   ga.dx = dx;
+  ga.dctx = dctx;
   ga.wgt = wgt; ga.wgt_stride = wgt_stride;
   ga.diag = h->opt_grad_diag;
   // Measured (maf 2|2, 4 chains x 100 k points): one 32-point CTA per SM 245 ms, two 16-point CTAs per SM 274 ms — the

@@ -436,8 +436,8 @@ extern "C" int nazb_forward(nazb_handle* h, int32_t s_begin, int32_t s_count, co
 static int grad_impl(nazb_handle* h, int32_t s_begin, int32_t s_count, const float* x, const float* ctx,
                      int32_t ctx_rows, int32_t N, const float* lo, const float* hi,
                      const float* const* mask, float* const* gW, float* const* gb, const int64_t* gwst,
-                     const int64_t* gbst, float* dx, float* lp, double* sum_n, const float* w, int64_t w_draw_stride,
-                     void* stream) {
+                     const int64_t* gbst, float* dx, float* dctx, float* lp, double* sum_n, const float* w,
+                     int64_t w_draw_stride, void* stream) {
   int rc = check_io(h, s_begin, s_count, x, ctx, ctx_rows, N, lo, hi);
   if (rc != NAZB_OK) return rc;
   if (!mask || !gW || !gb || !gwst || !gbst) return NAZB_ERR_BAD_ARG;
@@ -465,7 +465,7 @@ static int grad_impl(nazb_handle* h, int32_t s_begin, int32_t s_count, const flo
   io.x = x; io.x_draw_stride = 0; io.ctx = ctx; io.ctx_rows = ctx_rows; io.N = N;
   io.s_begin = s_begin; io.s_count = s_count; io.lo = lo; io.hi = hi;
   io.out_l = lp; io.sum_n = sum_n; io.dir = 0;
-  CK(h, nazb_grad_launch(h, io, h->grad_tabs, dx, w, (long long)w_draw_stride, st));
+  CK(h, nazb_grad_launch(h, io, h->grad_tabs, dx, dctx, w, (long long)w_draw_stride, st));
   return NAZB_OK;
 }
 
@@ -473,7 +473,7 @@ extern "C" int nazb_inverse_grad(nazb_handle* h, int32_t s_begin, int32_t s_coun
                                  int32_t ctx_rows, int32_t N, const float* lo, const float* hi,
                                  const float* const* mask, float* const* gW, float* const* gb, const int64_t* gwst,
                                  const int64_t* gbst, float* dx, float* lp, double* sum_n, void* stream) {
-  return grad_impl(h, s_begin, s_count, x, ctx, ctx_rows, N, lo, hi, mask, gW, gb, gwst, gbst, dx, lp, sum_n, nullptr, 0, stream);
+  return grad_impl(h, s_begin, s_count, x, ctx, ctx_rows, N, lo, hi, mask, gW, gb, gwst, gbst, dx, nullptr, lp, sum_n, nullptr, 0, stream);
 }
 
 // Vector-Jacobian product of lp[s][n] with caller-given cotangents w: what `loss.backward()` of the reference's training loop
@@ -481,8 +481,8 @@ extern "C" int nazb_inverse_grad(nazb_handle* h, int32_t s_begin, int32_t s_coun
 extern "C" int nazb_inverse_vjp(nazb_handle* h, int32_t s_begin, int32_t s_count, const float* x, const float* ctx,
                                 int32_t ctx_rows, int32_t N, const float* lo, const float* hi,
                                 const float* const* mask, float* const* gW, float* const* gb, const int64_t* gwst,
-                                const int64_t* gbst, float* dx, float* lp, const float* w, int64_t w_draw_stride,
-                                void* stream) {
+                                const int64_t* gbst, float* dx, float* dctx, float* lp, const float* w,
+                                int64_t w_draw_stride, void* stream) {
   if (!w || w_draw_stride < 0) return NAZB_ERR_BAD_ARG;
-  return grad_impl(h, s_begin, s_count, x, ctx, ctx_rows, N, lo, hi, mask, gW, gb, gwst, gbst, dx, lp, nullptr, w, w_draw_stride, stream);
+  return grad_impl(h, s_begin, s_count, x, ctx, ctx_rows, N, lo, hi, mask, gW, gb, gwst, gbst, dx, dctx, lp, nullptr, w, w_draw_stride, stream);
 }

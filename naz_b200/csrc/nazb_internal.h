@@ -113,7 +113,7 @@ cudaError_t nazb_tc_launch(const nazb_handle* h, const IoArgs& io, int n_groups,
 int64_t nazb_tc_packed_bytes(const nazb_handle* h);
 
 // gradient of sum_n lp (masked-affine flows, SIMT image)
-cudaError_t nazb_grad_launch(nazb_handle* h, const IoArgs& io, const void* tabs, float* dx, const float* wgt,
+cudaError_t nazb_grad_launch(nazb_handle* h, const IoArgs& io, const void* tabs, float* dx, float* dctx, const float* wgt,
                              long long wgt_stride, cudaStream_t st);
 bool nazb_grad_fits(const FlowGeom& g);
 

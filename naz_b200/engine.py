@@ -430,14 +430,16 @@ class FlowEngine:
 
     # ------------------------------------------------------------------
     def inverse_grad(self, x, ctx=None, bounds=None, *, want_dx: bool = False, want_lp: bool = False,
-                     s_begin: int = 0, s_count: Optional[int] = None, weights: Optional[torch.Tensor] = None):
+                     s_begin: int = 0, s_count: Optional[int] = None, weights: Optional[torch.Tensor] = None,
+                     want_dctx: bool = False):
         """Value and gradient of sum_n log p(x_n | ctx_n; theta_s) per draw (what the reference gets from
         jax.value_and_grad / autograd of bflow_jax_maf.py:233-235).  Returns {"sum_n": [s_count] float64,
         "gW": [L][n_lin] of [S,out,in], "gb": [L][n_lin] of [S,out], "dx": [s_count,N,D], "lp": [s_count,N]};
         rows of gW / gb outside [s_begin, s_begin+s_count) stay zero.  Needs a handle created with engine="simt"
         holding a masked-affine or quadratic neural-spline flow (nazb_inverse_grad returns "unsupported" otherwise).
         `weights` ([N] shared or [s_count, N]): cotangents of lp — the result is then the vector-Jacobian product
-        sum_n w[s,n] d lp[s,n] / d theta (nazb_inverse_vjp; "dx" = w d lp / d x) and "sum_n" is not returned."""
+        sum_n w[s,n] d lp[s,n] / d theta (nazb_inverse_vjp; "dx" = w d lp / d x) and "sum_n" is not returned.  `want_dctx`:
+        also "dctx" [s_count, N, C] = w d lp / d ctx per point (weights default to 1; sum over N for a broadcast context)."""
         sh = self.shape
         if self._keepalive is None:
             raise RuntimeError("inverse_grad: pack() has not been called on this engine")
@@ -461,12 +463,20 @@ class FlowEngine:
         lp = torch.empty((s_count, N), device=self.device, dtype=torch.float32) if want_lp else None
         tabs = (VP(*[m.data_ptr() for m in masks]), VP(*[t.data_ptr() for t in gW]), VP(*[t.data_ptr() for t in gb]),
                 I64(*[dims[i % n_lin + 1] * dims[i % n_lin] for i in range(n)]), I64(*[dims[i % n_lin + 1] for i in range(n)]))
+        dctx = None
+        if want_dctx:
+            if sh.C == 0:
+                raise ValueError("want_dctx on a flow without context")
+            dctx = torch.empty((s_count, N, sh.C), device=self.device, dtype=torch.float32)
+            if weights is None:
+                weights = torch.ones((N,), device=self.device, dtype=torch.float32)
         if weights is not None:
             w = _f32c(torch.as_tensor(weights), self.device)
             if tuple(w.shape) not in ((N,), (s_count, N)):
                 raise ValueError(f"weights must be [N={N}] or [s_count={s_count}, N]")
             rc = 0 if N == 0 else self._lib.nazb_inverse_vjp(self._h, s_begin, s_count, x.data_ptr(), _ptr(c), rows, N, _ptr(lo), _ptr(hi),
-                                                             *tabs, _ptr(dx), _ptr(lp), w.data_ptr(), 0 if w.dim() == 1 else N, self._stream())
+                                                             *tabs, _ptr(dx), _ptr(dctx), _ptr(lp), w.data_ptr(), 0 if w.dim() == 1 else N,
+                                                             self._stream())
             self._check(rc, "nazb_inverse_vjp")
             sum_n = None
         else:
@@ -478,6 +488,8 @@ class FlowEngine:
                "gb": [[gb[l * n_lin + j] for j in range(n_lin)] for l in range(L)]}
         if want_dx:
             out["dx"] = dx
+        if want_dctx:
+            out["dctx"] = dctx
         if want_lp:
             out["lp"] = lp
         return out

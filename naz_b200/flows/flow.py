@@ -166,8 +166,9 @@ class _LogProbFn(torch.autograd.Function):
         if tuple(p._version for p in ctx.params) != ctx.versions:
             raise RuntimeError("NormalizingFlow parameters were modified in place between log_prob and backward")
         eng = flow._grad_engine()
+        want_dc = bool(ctx.needs_input_grad[2])
         r = eng.inverse_grad(flow.relabel.to_engine(x), ctx.cond, flow._bounds_e(), want_dx=ctx.needs_input_grad[1],
-                             weights=g.detach().reshape(-1))
+                             weights=g.detach().reshape(-1), want_dctx=want_dc)
         grads = []
         for l in range(len(flow.nets)):
             gW, gb = [t[0] for t in r["gW"][l]], [t[0] for t in r["gb"][l]]
@@ -175,7 +176,12 @@ class _LogProbFn(torch.autograd.Function):
             for a, b in zip(gW, gb):
                 grads += [a, b]
         dx = flow.relabel.from_engine(r["dx"][0]) if ctx.needs_input_grad[1] else None
-        return (None, dx, None) + tuple(grads)
+        dc = None
+        if want_dc:
+            dc = r["dctx"][0]                                   # [N, C]; a broadcast context ([C] or [1, C]) receives the sum over points
+            if ctx.cond.dim() == 1 or ctx.cond.shape[0] == 1:
+                dc = dc.sum(0).reshape(ctx.cond.shape)
+        return (None, dx, dc) + tuple(grads)
 
 
 class NormalizingFlow(nn.Module):
@@ -333,11 +339,9 @@ class NormalizingFlow(nn.Module):
             raise RuntimeError("log_prob on a dropout flow in train() mode: call flow.eval() for the deterministic density, or "
                                "log_prob_draws(..., keep=masks, p_drop=p) for explicit MC-dropout masks")
         params = self._flat_params()
-        if torch.is_grad_enabled() and (any(p.requires_grad for p in params) or (isinstance(x, torch.Tensor) and x.requires_grad)):
-            cond = self._cond(condition)
-            if isinstance(cond, torch.Tensor) and cond.requires_grad:
-                raise NotImplementedError("the gradient with respect to the context (a trainable embedding_net) is not built; "
-                                          "detach the embedding or freeze it")
+        if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or (isinstance(x, torch.Tensor) and x.requires_grad)
+                                        or (isinstance(condition, torch.Tensor) and condition.requires_grad)):
+            cond = self._cond(condition)          # may carry the graph of a trainable embedding_net (flow.py:30-36): d lp / d ctx flows back
             if self.flow_type in ("maf", "nsa") and not self.relabel.has_bn:
                 return _LogProbFn.apply(self, x, cond, *params)
             if self.training:

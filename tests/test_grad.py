@@ -493,3 +493,51 @@ def test_train_driver_fits_a_conditional_gaussian():
     # the best-validation weights were restored
     with torch.no_grad():
         assert not flow.log_prob(x[:10], condition=y[:10]).requires_grad
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flow_type,bcast", [("maf", False), ("nsa", False), ("nsa", True)])
+def test_log_prob_backward_reaches_a_trainable_embedding_net(flow_type, bcast):
+    """NormalizingFlow(embedding_net=...) (flow.py:30-36, :75): the context is the embedding of the raw condition, so training it
+    needs d lp / d ctx.  nazb_inverse_vjp returns it per point (`dctx`); here the gradients autograd delivers to the embedding
+    net's parameters, to the flow's own parameters and to x must equal fp64 autograd through the restatement — per-point
+    conditions and one broadcast condition vector (whose cotangent is the sum over the points)."""
+    from naz_b200.flows import NormalizingFlow
+    from oracle import pyro_style as ps
+    torch.manual_seed(9)
+    D, C, Craw, hidden, L, K = 3, 2, 5, [32, 32], 3, 6
+    emb = torch.nn.Sequential(torch.nn.Linear(Craw, 8), torch.nn.Tanh(), torch.nn.Linear(8, C))
+    args = (D, C, hidden, L) + ((K,) if flow_type == "nsa" else ())
+    flow = NormalizingFlow(flow_type, None, *args, embedding_net=emb).cuda()
+    N = 130
+    x = (torch.randn(N, D) * 1.2).cuda().requires_grad_(True)
+    y = torch.randn(1 if bcast else N, Craw).cuda()
+    wts = torch.rand(N).cuda() + 0.5                                   # non-uniform cotangents of lp
+    loss = -(flow.log_prob(x, condition=y) * wts).sum()
+    loss.backward()
+    got_emb = [p.grad.detach().cpu().double().numpy() for p in emb.parameters()]
+    got_w0 = flow.nets[0].layers[0].weight.grad.detach().cpu().double().numpy()
+    got_x = x.grad.detach().cpu().double().numpy()
+    torch.set_default_dtype(torch.float64)
+    try:
+        import copy
+        emb64 = copy.deepcopy(emb).cpu().double()
+        for p in emb64.parameters():
+            p.grad = None
+        ref = ps.PyroStyleFlow(flow_type, None, D, C, hidden, L, K, "quadratic", permutations=flow.perms().numpy())
+        ref.set_from_pytree([[(W.double().cpu().numpy(), b.double().cpu().numpy()) for (W, b) in layer] for layer in flow.current_draw()])
+        x64 = x.detach().cpu().double().requires_grad_(True)
+        c64 = emb64(y.cpu().double())
+        if bcast:
+            c64 = c64.expand(N, C)
+        ref_loss = -(ref.log_prob(x64, c64) * wts.cpu().double()).sum()
+        ref_loss.backward()
+        want_emb = [p.grad.numpy() for p in emb64.parameters()]
+        want_w0 = ref.nets[0].layers[0].weight.grad.numpy()
+        want_x = x64.grad.numpy()
+    finally:
+        torch.set_default_dtype(torch.float32)
+    assert abs(loss.item() - ref_loss.item()) < 2e-4 * max(1.0, abs(ref_loss.item()))
+    for g, w in zip(got_emb, want_emb):
+        assert _rel(g, w) < 1e-3, (g, w)
+    assert _rel(got_w0, want_w0) < 5e-4 and _rel(got_x, want_x) < 5e-4
