@@ -172,9 +172,12 @@ class _LogProbFn(torch.autograd.Function):
         grads = []
         for l in range(len(flow.nets)):
             gW, gb = [t[0] for t in r["gW"][l]], [t[0] for t in r["gb"][l]]
-            gW[0], gW[-1], gb[-1] = flow.relabel.unfold_layer_grads(l, gW[0], gW[-1], gb[-1], flow.condition_dim)
-            for a, b in zip(gW, gb):
-                grads += [a, b]
+            gW[0], gW[-1], gb[-1] = flow.relabel.unfold_layer_grads(l, gW[0], gW[-1], gb[-1], flow.shape.C)
+            if flow.flow_type == "nsc":
+                grads += flow._layers[l].grads_from_made(gW, gb, flow.shape.C)
+            else:
+                for a, b in zip(gW, gb):
+                    grads += [a, b]
         dx = flow.relabel.from_engine(r["dx"][0]) if ctx.needs_input_grad[1] else None
         dc = None
         if want_dc:
@@ -294,6 +297,10 @@ class NormalizingFlow(nn.Module):
         return self._engg
 
     def _flat_params(self):
+        """Parameters in the order `_LogProbFn.backward` returns their gradients."""
+        if self.flow_type == "nsc":
+            return [p for t in self._layers for p in ([q for lin in t.nn.layers for q in (lin.weight, lin.bias)]
+                                                      + t.lower_spline.groups(t.order))]
         return [t for arn in self.nets for lin in arn.layers for t in (lin.weight, lin.bias)]
 
     def make_engine(self, draws, keep=None, p_drop: float = 0.0, device=None) -> FlowEngine:
@@ -342,11 +349,11 @@ class NormalizingFlow(nn.Module):
         if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or (isinstance(x, torch.Tensor) and x.requires_grad)
                                         or (isinstance(condition, torch.Tensor) and condition.requires_grad)):
             cond = self._cond(condition)          # may carry the graph of a trainable embedding_net (flow.py:30-36): d lp / d ctx flows back
-            if self.flow_type in ("maf", "nsa") and not self.relabel.has_bn:
+            if not self.relabel.has_bn:
                 return _LogProbFn.apply(self, x, cond, *params)
             if self.training:
-                raise NotImplementedError("gradients of coupling ('nsc') and BatchNorm flows are not built: log_prob in train() mode "
-                                          "with autograd enabled would silently return a constant — call flow.eval() / torch.no_grad()")
+                raise NotImplementedError("gradients of BatchNorm flows are not built: log_prob in train() mode with autograd enabled "
+                                          "would silently return a constant — call flow.eval() / torch.no_grad()")
         eng = self._single_engine()
         out = eng.inverse(self.relabel.to_engine(x), self._cond(condition), self._bounds_e(), want_lp=True)
         return out["lp"][0]

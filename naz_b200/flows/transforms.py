@@ -213,6 +213,35 @@ class SplineCoupling(nn.Module):
         out[-1] = (We.reshape(lead_w + (We.shape[-3] * D, H)), be.reshape(lead_b + (be.shape[-2] * D,)))
         return out
 
+    def grads_from_made(self, gW, gb, context_dim):
+        return _coupling_grads(self, gW, gb, context_dim)
+
+
+def _coupling_grads(t, gW, gb, context_dim):
+    """Gradients in the engine's conditioner format (one draw: gW / gb [n_lin] of [out, in] / [out]) -> gradients of the
+    coupling layer's own parameters, in `t.parameters()` order: hyper-network (W, b) per linear, then the free spline
+    parameters.  The exact transpose of `SplineCoupling.as_made` (an index re-arrangement)."""
+    D, s, C = t.input_dim, t.split_dim, context_dim
+    out = []
+    n_lin = len(gW)
+    for j in range(n_lin - 1):
+        out += [gW[j][:, :C + s] if j == 0 else gW[j], gb[j]]
+    H = gW[-1].shape[-1]
+    M = sum(t.slot_groups())
+    gWl = gW[-1].reshape(M, D, H)
+    gbl = gb[-1].reshape(M, D)
+    up_W, up_b, low, m0 = [], [], [], 0
+    for Kg in t.slot_groups():
+        up_W.append(gWl[m0:m0 + Kg, s:, :].transpose(0, 1).reshape((D - s) * Kg, H))      # dimension-major rows, as pyro's reshape
+        up_b.append(gbl[m0:m0 + Kg, s:].transpose(0, 1).reshape((D - s) * Kg))
+        low.append(gbl[m0:m0 + Kg, :s].transpose(0, 1).contiguous())                      # [split_dim, K_g]
+        m0 += Kg
+    if n_lin == 1:
+        out += [torch.cat(up_W, 0)[:, :C + s], torch.cat(up_b, 0)]
+    else:
+        out += [torch.cat(up_W, 0), torch.cat(up_b, 0)]
+    return out + low
+
 
 def neural_spline_coupling(theta_dim, condition_dim, hidden_dim, num_layers, count_bins, split_dim, order="quadratic",
                            activation=None, use_batchnorm=False, random_perm=False, dropout_p=None):

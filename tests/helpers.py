@@ -114,30 +114,33 @@ def pyro_golden_files():
 
 def explicit_coupling_flow(flow, order, dtype=torch.float64):
     """Module-structured restatement of a product 'nsc' flow: explicit SplineCoupling (+ Permute) transforms on torch's
-    TransformedDistribution, sharing the product's parameter values."""
+    TransformedDistribution, sharing the product's parameter values.  `build.leaves` lists the restatement's parameters in
+    the order of `flow._flat_params()` (for gradient comparisons)."""
     from functools import partial
     from torch.distributions import Normal, TransformedDistribution
     from oracle import pyro_style as ps
     D, C = flow.theta_dim, flow.shape.C
-    ts, nets = [], []
+    nets, leaves = [], []
     for t in flow.transforms:
         if t.kind == "nsc":
             net = ps.ConditionalDenseNN(t.split_dim, C, t.nn.hidden_dims, t.nn.param_dims).to(dtype)
             with torch.no_grad():
                 for a, b in zip(net.layers, t.nn.layers):
                     a.weight.copy_(b.weight.detach().cpu()); a.bias.copy_(b.bias.detach().cpu())
-            nets.append((t, net))
+            lower = [g.detach().cpu().to(dtype).clone().requires_grad_(True) for g in t.lower_spline.groups(order)]
+            nets.append((t, net, lower))
+            leaves += [q for lin in net.layers for q in (lin.weight, lin.bias)] + lower
         elif t.kind == "permute":
-            nets.append((t, None))
+            nets.append((t, None, None))
 
     def build(ctx):
         out = []
-        for t, net in nets:
+        for t, net, lower in nets:
             if net is None:
                 out.append(ps.Permute(t.permutation.cpu()))
             else:
                 fn = partial(net, context=ctx) if C > 0 else net
-                lower = [g.detach().cpu().to(dtype) for g in t.lower_spline.groups(order)]
                 out.append(ps.SplineCoupling(D, t.split_dim, fn, lower, t.count_bins, t.bound, order))
         return TransformedDistribution(Normal(torch.zeros(D, dtype=dtype), torch.ones(D, dtype=dtype)), out)
+    build.leaves = leaves
     return build
