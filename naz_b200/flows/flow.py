@@ -178,12 +178,13 @@ class _LogProbFn(torch.autograd.Function):
             else:
                 for a, b in zip(gW, gb):
                     grads += [a, b]
-        dx = flow.relabel.from_engine(r["dx"][0]) if ctx.needs_input_grad[1] else None
+        dx = flow.relabel.from_engine(r["dx"][0]).to(x.device).reshape(x.shape) if ctx.needs_input_grad[1] else None
         dc = None
         if want_dc:
             dc = r["dctx"][0]                                   # [N, C]; a broadcast context ([C] or [1, C]) receives the sum over points
             if ctx.cond.dim() == 1 or ctx.cond.shape[0] == 1:
                 dc = dc.sum(0).reshape(ctx.cond.shape)
+            dc = dc.to(ctx.cond.device)
         return (None, dx, dc) + tuple(grads)
 
 
