@@ -3,7 +3,9 @@
 Where oracle/flow_oracle.py is functional numpy following the in-tree JAX twin, this file rebuilds
 the *module* structure the reference actually executes through pyro-ppl (absent here):
 ``MaskedLinear`` -> ``(Conditional)AutoRegressiveNN`` -> ``(Conditional)AffineAutoregressive`` /
-``(Conditional)SplineAutoregressive`` -> the real ``torch.distributions.TransformedDistribution``,
+``(Conditional)SplineAutoregressive`` (plus ``Permute``, eval-mode ``BatchNorm``, ``(Conditional)DenseNN`` and
+``SplineCoupling`` for the factories' optional layers and the coupling flow) -> the real
+``torch.distributions.TransformedDistribution``,
 assembled the way naz does it (src/naz/flows/transforms.py:133-198, src/naz/flows/flow.py:26-129).
 It keeps the reference's cost structure on purpose — ``W*mask`` re-multiplied on every call,
 D full conditioner passes per layer in ``_inverse``, a Python loop over draws with an in-place
