@@ -242,6 +242,8 @@ int nazb_hpd(const float* v, int32_t S, int64_t M, double alpha, float* lo, floa
  *                  (split for flow layers with >= 4 hidden blocks)                              — needs a new nazb_pack
  *   "inv_align"    block-aligned accumulator / operand columns: 1 on, 0 off, -1 (default) by shape — needs a new nazb_pack
  *   "inv_trim"     1 (default) context-folded programs drop the dead degree-0 accumulator columns — needs a new nazb_pack
+ *   "inv_gaps"     1: build inverse programs for MADE degree ladders with unpopulated degrees (the single-degree form of
+ *                  coupling layers); 0 (default): such ladders are served by the fp32 engine            — needs a new nazb_pack
  *   "inv_a_tmem"   1 (default) A operand of the pushes in tensor memory when the plan has room for it
  *   "inv_fold"     1 (default) fold a broadcast context (ctx_rows == 1) into per-draw constants inside nazb_inverse
  *   "inv_gate"     bound the drift of CTAs across draw groups (keeps the weight images L2-resident): 0 off, 2 = no CTA starts

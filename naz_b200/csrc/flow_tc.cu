@@ -118,6 +118,7 @@ struct TcPlan {
   // (zero image rows / columns, zero biases), so an A block is exactly bw / 16 K slices and the epilogue of a block touches
   // aw = ceil8(max n_r) columns instead of the 8-aligned hull of an unaligned range (cfg3: 40 instead of 56-64).
   int bw = 0, aw = 0;
+  bool allow_gaps = false;        // inverse programs for degree ladders with unpopulated degrees (set from opt_gaps)
   bool trim = true;               // folded programs: accumulators start at the first live block (set from opt_trim before building)
   int hpad[NAZB_MAX_HIDDEN_LAYERS] = {0};   // column count of each hidden layer in the inverse programs (ceil16(H) or D bw)
 };
@@ -152,6 +153,7 @@ struct TcState {
   int opt_park = 0;                  // v5: 1 = the issuer / producer warps wait with a suspend-time hint instead of polling (measured: the stragglers move
                                      // to other sub-partitions, the phase spread stays 150-400 cycles, throughput -1 %: off)
   int opt_trim = 1;                  // folded v5 / v6 programs drop the dead degree-0 accumulator columns
+  int opt_gaps = 0;                  // 1: build inverse programs for ladders with unpopulated degrees (coupling layers)
   int opt_align = -1;                // v5 / v6: block-aligned column layout when it fits tensor memory: 1 = on, 0 = off, -1 = auto (on for
                                      // flow layers with >= 4 hidden blocks: cfg2 +13 %; no effect on cfg3 / cfg4 whose blocks are wide)
 };
@@ -469,11 +471,15 @@ bool build_inverse(const FlowGeom& g, TcPlan& P, int variant, int merge_n, std::
     bool empty0 = (g.blk[0][r + 1] == g.blk[0][r]);
     for (int j = 1; j < nh; ++j)
       if ((g.blk[j][r + 1] == g.blk[j][r]) != empty0) return false;   // blocks must be (non)empty together
-    // The programs are built (and tested) for the MADE degree ladder: every degree populated, except degree 0 of a flow without
-    // context.  Other ladders — e.g. the single-degree form of a coupling layer (flows/transforms.py::SplineCoupling), which
-    // this builder used to accept and evaluate wrongly — are declined here and served by the fp32 engine.
-    if (empty0 && (r > 0 || g.C > 0)) return false;
   }
+  // Ladders with unpopulated degrees (beyond degree 0 of a context-free flow) — the single-degree form of a coupling layer,
+  // flows/transforms.py::SplineCoupling — need two things this builder used to get wrong: a stage without hidden units
+  // reads the output accumulators once ANY earlier stage has pushed into them (flags bit 0 only before the first push), and
+  // the last push before such a stage must retire completely before it (unsplit: no later accumulator barrier covers its
+  // trailing columns).  `allow_gaps` (engine option "inv_gaps", default off) enables them; off = declined, served by the fp32 engine.
+  bool gaps = false;
+  for (int r = 0; r < D; ++r) gaps = gaps || ((g.blk[0][r + 1] == g.blk[0][r]) && (r > 0 || g.C > 0));
+  if (gaps && !P.allow_gaps) return false;
   if (folded) {
     // needs a context, a non-empty degree-0 block and a transform whose rank-0 parameters fold into a small table
     if (g.C == 0 || g.blk[0][1] == g.blk[0][0]) return false;
@@ -489,7 +495,7 @@ bool build_inverse(const FlowGeom& g, TcPlan& P, int variant, int merge_n, std::
     b.emit = !skip;
     if (b1 == b0) {
       Step e = mk_epi(EPI_XINV, T_OUT + r * Mp, 0, 0, r);
-      e.flags = 1; e.e_aux = (uint16_t)(P.lc_bout + r * Mp);
+      e.flags = first_push[nh] ? 1 : 0; e.e_aux = (uint16_t)(P.lc_bout + r * Mp);
       b.epi_only(e);
       continue;
     }
@@ -533,6 +539,7 @@ bool build_inverse(const FlowGeom& g, TcPlan& P, int variant, int merge_n, std::
         e.e_aux = (uint16_t)(P.lc_bout + r * Mp);
         int n_crit = v5 ? ceil_to((r + 1) * Mp, 16) - s0 : Mp;
         if (v4 && n <= merge_n) n_crit = n;
+        if (gaps) n_crit = n;   // a stage without hidden units may follow: it reads columns no later barrier would cover
         // image row n <-> output column s0 + n (rank = column / Mp, slot = column % Mp); rows of ranks < r and of the padding are zero
         b.gemm(A_H, 0, kr, n, T_OUT + s0, 3, first_push[nh] ? 0 : 1, mk_img(nh, n, kr, 1, s0, r, D, sc0, sb0, sb1, -1, 0), e, n_crit);
         if (!skip) first_push[nh] = false;
@@ -1348,6 +1355,7 @@ int nazb_tc_set_option(nazb_handle* h, const char* name, int value) {
   if (!strcmp(name, "inv_a_tmem")) { t->opt_a_tmem = value ? 1 : 0; return NAZB_OK; }
   if (!strcmp(name, "inv_park")) { if (value < 0 || value > 2) return NAZB_ERR_BAD_ARG; t->opt_park = value; return NAZB_OK; }
   if (!strcmp(name, "inv_trim")) { t->opt_trim = value ? 1 : 0; h->is_packed = false; return NAZB_OK; }
+  if (!strcmp(name, "inv_gaps")) { t->opt_gaps = value ? 1 : 0; h->is_packed = false; return NAZB_OK; }
   if (!strcmp(name, "inv_defer")) { if (value < 0 || value > 2) return NAZB_ERR_BAD_ARG; t->opt_defer = value; h->is_packed = false; return NAZB_OK; }
   if (!strcmp(name, "inv_align")) { if (value < -1 || value > 1) return NAZB_ERR_BAD_ARG; t->opt_align = value; h->is_packed = false; return NAZB_OK; }
   return NAZB_ERR_BAD_ARG;
@@ -1361,6 +1369,7 @@ int nazb_tc_get_option(const nazb_handle* h, const char* name, int* value) {
   else if (!strcmp(name, "inv_gate")) *value = t->opt_gate;
   else if (!strcmp(name, "inv_a_tmem")) *value = t->opt_a_tmem;
   else if (!strcmp(name, "inv_trim")) *value = t->opt_trim;
+  else if (!strcmp(name, "inv_gaps")) *value = t->opt_gaps;
   else if (!strcmp(name, "inv_park")) *value = t->opt_park;
   else if (!strcmp(name, "inv_defer")) *value = t->opt_defer;
   else if (!strcmp(name, "inv_align")) *value = t->opt_align;
@@ -1420,6 +1429,7 @@ cudaError_t nazb_tc_pack(nazb_handle* h, const float* const* W, const float* con
   P.ok[1] = P.fwd3 || build_forward(g, P);
   P.inv_ver = t->opt_inv_kernel;
   P.trim = t->opt_trim != 0;
+  P.allow_gaps = t->opt_gaps != 0;
   // geometry the inverse programs are built on: the real one (units contiguous in degree order) or the block-aligned one
   FlowGeom gi = g;
   std::vector<short> pmap;

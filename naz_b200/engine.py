@@ -156,7 +156,8 @@ class FlowEngine:
                           "affine (BatchNorm), and runs on the fp32 SIMT kernel; FlowEngine.engine_for(direction) reports the engine per direction", RuntimeWarning, stacklevel=3)
 
     # engine options (include/nazb.h: nazb_set_option); nothing in the library reads the environment
-    OPTION_NAMES = ("inv_kernel", "inv_merge_n", "inv_fold", "inv_gate", "inv_a_tmem", "inv_align", "inv_trim", "inv_defer", "inv_park")
+    OPTION_NAMES = ("inv_kernel", "inv_merge_n", "inv_fold", "inv_gate", "inv_a_tmem", "inv_align", "inv_trim", "inv_defer", "inv_park",
+                    "inv_gaps")
 
     def set_option(self, name: str, value: int) -> None:
         self._check(self._lib.nazb_set_option(self._h, name.encode(), int(value)), f"nazb_set_option({name})")

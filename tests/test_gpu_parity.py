@@ -963,3 +963,25 @@ def test_coupling_flow_nsc(order, random_perm, C, engine):
             assert got.grad is not None and tuple(got.grad.shape) == tuple(want.grad.shape)
             err = float((got.grad.detach().cpu().double() - want.grad).abs().max() / max(1e-12, float(want.grad.abs().max())))
             assert err < 1e-3, (tuple(got.shape), err)
+
+
+@pytest.mark.parametrize("C", [2, 0])
+def test_coupling_flow_on_the_tensor_core_inverse_with_inv_gaps(C):
+    """Engine option inv_gaps = 1: the tensor-core inverse builder accepts degree ladders with unpopulated degrees (the
+    single-degree form of coupling layers; off by default).  Stages without hidden units read the output
+    accumulators after the first push, and that push is unsplit.  log_prob on tcgen05 against the fp64 restatement."""
+    from helpers import explicit_coupling_flow
+    from naz_b200.flows import NormalizingFlow
+    torch.manual_seed(21)
+    D, s, hidden, L, K, N = 5, 2, [64, 64], 3, 8, 2000
+    flow = NormalizingFlow("nsc", None, D, C, hidden, L, K, s).cuda().eval()
+    x = (torch.randn(N, D) * 0.8).double()
+    ctx = torch.randn(N, C).double() if C else None
+    with torch.no_grad():
+        lp_ref = explicit_coupling_flow(flow, "quadratic")(ctx).log_prob(x).numpy()
+        eng = flow._new_engine(1, flow._device())
+        eng.set_option("inv_gaps", 1)
+        eng.pack(flow._fold_draws(flow.current_draw()), flow._packed_masks(), flow._packed_perms())
+        assert eng.engine_for("inverse") == "tcgen05" and eng.get_option("watchdog") == 0
+        lp = eng.inverse(flow.relabel.to_engine(x.float().cuda()), None if ctx is None else ctx.float().cuda(), None, want_lp=True)["lp"][0]
+    check(lp, lp_ref, f"nsc C={C} log_prob on the tensor-core inverse (inv_gaps)")
