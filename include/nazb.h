@@ -230,7 +230,8 @@ int nazb_importance(const double* sum_n, const float* log_prior, const float* lo
  *   nbins    HOST int32[D];           counts device uint32 [S][prod nbins] (zeroed by the call, C order);
  *   density  device fp32 [S][prod nbins] or NULL: counts / (sum of the draw's counts * bin volume)  (density=True).
  * nazb_hpd: v device fp32 [S][M] (e.g. the densities above, M = prod nbins) -> per column the narrowest interval
- * holding floor((1 - alpha) * S) + 1 order statistics: lo[M], hi[M]  (first minimum on ties, as numpy.argmin). */
+ * holding floor((1 - alpha) * S) + 1 order statistics: lo[M], hi[M]  (first minimum on ties, as numpy.argmin);
+ * S <= 32768 draws (the per-column sort runs in shared memory), NAZB_ERR_UNSUPPORTED beyond. */
 int nazb_histogramdd(const float* x, int32_t S, int64_t N, int32_t D, const double* edges, const int32_t* nbins,
                      uint32_t* counts, float* density, void* stream);
 int nazb_hpd(const float* v, int32_t S, int64_t M, double alpha, float* lo, float* hi, void* stream);

@@ -121,14 +121,14 @@ __global__ void hist_density_kernel(const unsigned int* __restrict__ counts, His
 // shared memory (bitonic, padded with +inf), then the narrowest window holding floor((1 - alpha) S) + 1 order statistics
 // is selected (first minimum, as numpy.argmin).
 constexpr int kHpdCols = 4;
-__global__ void hpd_kernel(const float* __restrict__ v, int S, long long M, int n_pad, int inc, float* __restrict__ lo,
+__global__ void hpd_kernel(const float* __restrict__ v, int S, long long M, int n_pad, int inc, int cols, float* __restrict__ lo,
                            float* __restrict__ hi) {
-  extern __shared__ float hs[];   // [kHpdCols][n_pad]
+  extern __shared__ float hs[];   // [cols][n_pad], cols <= kHpdCols columns per CTA (fewer when S is large: shared-memory budget)
   __shared__ float best_w[kHpdCols][32];
   __shared__ int best_i[kHpdCols][32];
-  const long long m0 = (long long)blockIdx.x * kHpdCols;
-  for (int i = threadIdx.x; i < n_pad * kHpdCols; i += blockDim.x) {
-    const int c = i % kHpdCols, s = i / kHpdCols;
+  const long long m0 = (long long)blockIdx.x * cols;
+  for (int i = threadIdx.x; i < n_pad * cols; i += blockDim.x) {
+    const int c = i % cols, s = i / cols;
     float val = INFINITY;
     if (s < S && m0 + c < M) val = v[(size_t)s * M + m0 + c];
     hs[c * n_pad + s] = val;
@@ -136,7 +136,7 @@ __global__ void hpd_kernel(const float* __restrict__ v, int S, long long M, int 
   __syncthreads();
   for (int k = 2; k <= n_pad; k <<= 1)
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < n_pad * kHpdCols; i += blockDim.x) {
+      for (int i = threadIdx.x; i < n_pad * cols; i += blockDim.x) {
         const int c = i / n_pad, a = i % n_pad, b = a ^ j;
         if (b > a) {
           float* col = hs + c * n_pad;
@@ -151,7 +151,7 @@ __global__ void hpd_kernel(const float* __restrict__ v, int S, long long M, int 
     }
   const int n_int = S - inc;   // number of candidate windows (> 0, checked by the host)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int c = 0; c < kHpdCols; ++c) {
+  for (int c = 0; c < cols; ++c) {
     const float* col = hs + c * n_pad;
     float bw = INFINITY;
     int bi = 0x7fffffff;
@@ -167,7 +167,7 @@ __global__ void hpd_kernel(const float* __restrict__ v, int S, long long M, int 
     if (lane == 0) { best_w[c][warp] = bw; best_i[c][warp] = bi; }
   }
   __syncthreads();
-  if (threadIdx.x < kHpdCols && m0 + threadIdx.x < M) {
+  if (threadIdx.x < cols && m0 + threadIdx.x < M) {
     const int c = threadIdx.x;
     float bw = best_w[c][0];
     int bi = best_i[c][0];
@@ -281,12 +281,15 @@ extern "C" int nazb_hpd(const float* v, int32_t S, int64_t M, double alpha, floa
   if (S - inc <= 0) return NAZB_ERR_BAD_ARG;                        // "Too few elements for interval calculation"
   int n_pad = 1;
   while (n_pad < S) n_pad <<= 1;
-  const size_t smem = (size_t)kHpdCols * n_pad * sizeof(float);
-  if (smem > 200 * 1024) return NAZB_ERR_UNSUPPORTED;               // S <= 8192 draws
+  // columns per CTA: as many as the shared-memory budget allows (4 up to 8192 draws, 2 up to 16384, 1 up to 32768)
+  int cols = kHpdCols;
+  while (cols > 1 && (size_t)cols * n_pad * sizeof(float) > 200 * 1024) cols >>= 1;
+  const size_t smem = (size_t)cols * n_pad * sizeof(float);
+  if (smem > 200 * 1024) return NAZB_ERR_UNSUPPORTED;               // S <= 32768 draws
   cudaStream_t st = (cudaStream_t)stream;
   if (cudaFuncSetAttribute(hpd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return NAZB_ERR_CUDA;
-  const long long blocks = (M + kHpdCols - 1) / kHpdCols;
-  hpd_kernel<<<(unsigned)blocks, 512, smem, st>>>(v, S, (long long)M, n_pad, inc, lo, hi);
+  const long long blocks = (M + cols - 1) / cols;
+  hpd_kernel<<<(unsigned)blocks, 512, smem, st>>>(v, S, (long long)M, n_pad, inc, cols, lo, hi);
   nazb_count_launch();
   return cudaGetLastError() == cudaSuccess ? NAZB_OK : NAZB_ERR_CUDA;
 }

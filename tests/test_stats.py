@@ -118,3 +118,16 @@ def test_sample_then_histogram_then_hpd_pipeline():
     assert np.array_equal(counts.cpu().numpy(), c_ref)
     band = hpd_draws(dens, 0.32)
     assert np.array_equal(band.cpu().numpy(), so.hpd_vectorized(dens.cpu().numpy(), 0.32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("S", [9000, 20000, 32768])
+def test_hpd_many_draws(S):
+    """More than 8192 draws: fewer columns per CTA so the sort still fits shared memory (2 up to 16384 draws, 1 up to 32768),
+    exact against the restatement of statutils.hpd_vectorized."""
+    from naz_b200.stats import hpd_draws
+    rng = np.random.default_rng(S)
+    v = rng.gamma(2.0, 1.0, size=(S, 7)).astype(np.float32)
+    got = hpd_draws(torch.from_numpy(v).cuda(), 0.1).cpu().numpy()
+    want = so.hpd_vectorized(v, 0.1)
+    assert np.array_equal(got, want.astype(np.float32))
