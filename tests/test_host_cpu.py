@@ -442,3 +442,38 @@ def test_coupling_flow_is_a_single_degree_masked_conditioner(order, random_perm,
     for l in range(L):
         degs = hidden_degrees_from_masks([torch.as_tensor(m) for m in masks_e[l]], torch.as_tensor(perms_e[l]), D, C)
         assert degs is not None and all(set(d) == {s if C else s} for d in degs), degs
+
+
+def test_gradient_unmapping_is_the_exact_transpose_of_the_packing_maps():
+    """Gradients come back from libnazb in the engine's conditioner format.  Two host-side index maps take them to the
+    reference's parameters: `Relabelling.unfold_layer_grads` (Permute layers) and `SplineCoupling.grads_from_made` (coupling
+    layers).  Each must be the exact transpose of the map that packed the weights:  <pack(theta), G> == <theta, unpack(G)>."""
+    from naz_b200.flows.flow import NormalizingFlow
+    torch.manual_seed(5)
+    # Permute folding
+    D, C, hidden, L, K = 5, 3, [12, 12], 3, 4
+    flow = NormalizingFlow("nsa", None, D, C, hidden, L, K, random_perm=True)
+    M = flow.shape.M
+    for l in range(L):
+        W0, Wl, bl = torch.randn(hidden[0], C + D), torch.randn(M * D, hidden[-1]), torch.randn(M * D)
+        packed = flow.relabel.fold_layer(l, [(W0, torch.zeros(hidden[0])), (Wl, bl)], C)
+        G0, Gl, gl = torch.randn_like(W0), torch.randn_like(Wl), torch.randn_like(bl)
+        u0, ul, ub = flow.relabel.unfold_layer_grads(l, G0, Gl, gl, C)
+        lhs = (packed[0][0] * G0).sum() + (packed[1][0] * Gl).sum() + (packed[1][1] * gl).sum()
+        rhs = (W0 * u0).sum() + (Wl * ul).sum() + (bl * ub).sum()
+        assert abs(float(lhs - rhs)) < 1e-4 * max(1.0, abs(float(lhs)))
+    # coupling layers, both spline orders
+    for order in ("quadratic", "linear"):
+        flow = NormalizingFlow("nsc", None, D, C, hidden, 2, K, 2, order=order)
+        t = flow._layers[0]
+        lins = [(lin.weight.detach(), lin.bias.detach()) for lin in t.nn.layers]
+        lower = [g.detach() for g in t.lower_spline.groups(order)]
+        made = t.as_made(lins, lower, C)
+        gW = [torch.randn_like(W) * m for (W, _), m in zip(made, t.made_masks(C))]      # the kernel never touches masked entries
+        gb = [torch.randn_like(b) for (_, b) in made]
+        back = t.grads_from_made(gW, gb, C)
+        theta = [q for (W, b) in lins for q in (W, b)] + lower
+        assert len(back) == len(theta) and all(a.shape == b.shape for a, b in zip(back, theta))
+        lhs = sum(float((W * g).sum()) for (W, _), g in zip(made, gW)) + sum(float((b * g).sum()) for (_, b), g in zip(made, gb))
+        rhs = sum(float((a * b).sum()) for a, b in zip(theta, back))
+        assert abs(lhs - rhs) < 1e-4 * max(1.0, abs(lhs)), (order, lhs, rhs)
