@@ -189,7 +189,7 @@ int nazb_truncnorm_sample(const float* x, int32_t S, int64_t P, const float* loc
  * gradient arrays are accumulated into (zero them first).  With nazb_pack_draw_map the gradient with respect to the standard
  * parameters is scale * theta_0 * gW (chain rule on bflow_jax_maf.py:239-240; done by the caller).
  * Covered: every flow kind (masked-affine, quadratic and linear-order neural-spline) on a handle created with
- * NAZB_ENGINE_SIMT, no dropout keep-masks, no layer affine; anything else returns NAZB_ERR_UNSUPPORTED.  fp32 atomics: the sum over points is not bit-reproducible run to run. */
+ * NAZB_ENGINE_SIMT, no dropout keep-masks; anything else returns NAZB_ERR_UNSUPPORTED.  fp32 atomics: the sum over points is not bit-reproducible run to run. */
 int nazb_inverse_grad(nazb_handle* h, int32_t s_begin, int32_t s_count, const float* x, const float* ctx,
                       int32_t ctx_rows, int32_t N, const float* lo, const float* hi, const float* const* mask,
                       float* const* gW, float* const* gb, const int64_t* gwst, const int64_t* gbst, float* dx, float* lp,
@@ -261,8 +261,8 @@ int nazb_set_option(nazb_handle* h, const char* name, int32_t value);
  * use_batchnorm=True (src/naz/flows/transforms.py:157-158, :195-196):  sampling direction x <- a[l][d] * x + b[l][d] after
  * flow layer l, log-det sum_d log a[l][d];  nazb_inverse applies (y - b) / a before inverting layer l.  a, b: HOST fp32
  * [L][D] (a > 0), copied on `stream`; a == NULL removes the step.  Flows with the step are served by the fp32 SIMT engine in
- * both directions (call this BEFORE nazb_pack; a handle created with NAZB_ENGINE_TCGEN05 returns NAZB_ERR_UNSUPPORTED) and
- * have no nazb_inverse_grad. */
+ * both directions (call this BEFORE nazb_pack; a handle created with NAZB_ENGINE_TCGEN05 returns NAZB_ERR_UNSUPPORTED);
+ * nazb_inverse_grad / nazb_inverse_vjp treat a and b as constants (no gradient with respect to them). */
 int nazb_set_layer_affine(nazb_handle* h, const float* a, const float* b, void* stream);
 int nazb_get_option(const nazb_handle* h, const char* name, int32_t* value);
 

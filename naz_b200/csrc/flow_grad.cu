@@ -224,6 +224,13 @@ __global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_kernel(
       const float* wl = wdraw + (size_t)l * g.layer_stride;
       const int* perm = perm_all + l * D;
       const bool full = g.inv_mode == NAZB_INV_JACOBI;
+      if (io.aff != nullptr) {
+        // eval-mode BatchNorm behind flow layer l (nazb_set_layer_affine): undo y_hat = a y + b before inverting the layer
+        const float* af = io.aff + (size_t)l * (2 * D + 1);
+        for (int i = tid; i < P * D; i += kThreads) { const int d = i / P; gcur[i] = (gcur[i] - af[D + d]) / af[d]; }
+        if (tid < P) ldacc[tid] += af[2 * D];
+        __syncthreads();
+      }
       for (int r = 0; r < D; ++r) {
         for (int j = 0; j < nh; ++j) {
           int c0 = full ? 0 : g.blk[j][r], c1 = full ? g.hidden[j] : g.blk[j][r + 1];
@@ -430,7 +437,9 @@ __global__ void __launch_bounds__(kThreads, (P == 16) ? 2 : 1) flow_grad_kernel(
       for (int i = tid; i < P * D; i += kThreads) {
         int p = i % P, r = i / P;
         int d = perm[r];
-        gcur[d * P + p] = lam[d * P + p] * es[r * P + p];
+        float gy = lam[d * P + p] * es[r * P + p];
+        if (io.aff != nullptr) gy /= io.aff[(size_t)l * (2 * D + 1) + d];   // through y_hat = a y + b (constants) to the next layer
+        gcur[d * P + p] = gy;
       }
       __syncthreads();
     }

@@ -443,7 +443,7 @@ static int grad_impl(nazb_handle* h, int32_t s_begin, int32_t s_count, const flo
   if (!mask || !gW || !gb || !gwst || !gbst) return NAZB_ERR_BAD_ARG;
   const FlowGeom& g = h->geom;
   // masked-affine and neural-spline flows (both orders) on the fp32 engine's image, no dropout
-  if (h->engine != NAZB_ENGINE_SIMT || !h->packed || h->has_keep || h->aff_dev || !nazb_grad_fits(g))
+  if (h->engine != NAZB_ENGINE_SIMT || !h->packed || h->has_keep || !nazb_grad_fits(g))
     return NAZB_ERR_UNSUPPORTED;
   const int n = g.L * (g.n_hidden + 1);
   for (int i = 0; i < n; ++i)
@@ -464,7 +464,7 @@ static int grad_impl(nazb_handle* h, int32_t s_begin, int32_t s_count, const flo
   IoArgs io{};
   io.x = x; io.x_draw_stride = 0; io.ctx = ctx; io.ctx_rows = ctx_rows; io.N = N;
   io.s_begin = s_begin; io.s_count = s_count; io.lo = lo; io.hi = hi;
-  io.out_l = lp; io.sum_n = sum_n; io.dir = 0;
+  io.out_l = lp; io.sum_n = sum_n; io.dir = 0; io.aff = h->aff_dev;
   CK(h, nazb_grad_launch(h, io, h->grad_tabs, dx, dctx, w, (long long)w_draw_stride, st));
   return NAZB_OK;
 }

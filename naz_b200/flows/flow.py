@@ -286,13 +286,13 @@ class NormalizingFlow(nn.Module):
 
     def _grad_engine(self) -> FlowEngine:
         """fp32-engine handle (S = 1) on the current parameters for nazb_inverse_grad / nazb_inverse_vjp."""
-        if self.relabel.has_bn:
-            raise NotImplementedError("gradients of BatchNorm flows are not built (nazb_inverse_grad has no layer affine)")
         dev = self._device()
-        key = (dev,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+        key = (dev,) + tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
         if self._engg is None or self._engg_key != key:
-            if self._engg is None or self._engg.device != dev:
+            if self._engg is None or self._engg.device != dev or self.relabel.has_bn:
                 self._engg = FlowEngine(self.shape, 1, device=dev, engine="simt")
+                if self.relabel.has_bn:                     # eval-mode statistics and affine, constants of the gradient
+                    self._engg.set_layer_affine(*self.relabel.layer_affine())
             self._engg.pack(self._fold_draws(self.current_draw()), self._packed_masks(), self._packed_perms())
             self._engg_key = key
         return self._engg
@@ -350,11 +350,11 @@ class NormalizingFlow(nn.Module):
         if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or (isinstance(x, torch.Tensor) and x.requires_grad)
                                         or (isinstance(condition, torch.Tensor) and condition.requires_grad)):
             cond = self._cond(condition)          # may carry the graph of a trainable embedding_net (flow.py:30-36): d lp / d ctx flows back
-            if not self.relabel.has_bn:
-                return _LogProbFn.apply(self, x, cond, *params)
-            if self.training:
-                raise NotImplementedError("gradients of BatchNorm flows are not built: log_prob in train() mode with autograd enabled "
-                                          "would silently return a constant — call flow.eval() / torch.no_grad()")
+            if self.relabel.has_bn and self.training:
+                raise RuntimeError("BatchNorm flows are evaluated with their moving statistics: call flow.eval() first (the "
+                                   "train()-mode batch statistics belong to the training loop, which is out of scope)")
+            # BatchNorm (eval mode): its statistics, gamma and beta are constants of this node (they receive no gradient)
+            return _LogProbFn.apply(self, x, cond, *params)
         eng = self._single_engine()
         out = eng.inverse(self.relabel.to_engine(x), self._cond(condition), self._bounds_e(), want_lp=True)
         return out["lp"][0]

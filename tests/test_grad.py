@@ -541,3 +541,50 @@ def test_log_prob_backward_reaches_a_trainable_embedding_net(flow_type, bcast):
     for g, w in zip(got_emb, want_emb):
         assert _rel(g, w) < 1e-3, (g, w)
     assert _rel(got_w0, want_w0) < 5e-4 and _rel(got_x, want_x) < 5e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flow_type", ["maf", "nsa"])
+def test_log_prob_backward_through_eval_mode_batchnorm(flow_type):
+    """use_batchnorm=True flows in eval() mode: the per-layer affine is a constant of the adjoint recursion (cotangents pass
+    through y_hat = a y + b as 1/a).  Gradients of the conditioner parameters and of x against fp64 autograd of the restatement
+    with explicit BatchNorm (eval) and Permute transforms."""
+    from naz_b200.flows import NormalizingFlow
+    from naz_b200.flows.transforms import BatchNorm
+    from oracle import pyro_style as ps
+    torch.manual_seed(4)
+    D, C, hidden, L, K = 3, 2, [32, 32], 3, 6
+    args = (D, C, hidden, L) + ((K,) if flow_type == "nsa" else ())
+    flow = NormalizingFlow(flow_type, None, *args, random_perm=True, use_batchnorm=True)
+    with torch.no_grad():
+        for t in flow.transforms:
+            if isinstance(t, BatchNorm):
+                t.gamma.copy_(0.5 + torch.rand(D)); t.beta.copy_(0.3 * torch.randn(D))
+                t.moving_mean.copy_(0.2 * torch.randn(D)); t.moving_variance.copy_(0.5 + torch.rand(D))
+    flow = flow.cuda().eval()
+    N = 200
+    x = (torch.randn(N, D) * 1.1).cuda().requires_grad_(True)
+    y = torch.rand(N, C).cuda()
+    (-flow.log_prob(x, condition=y).mean()).backward()
+    torch.set_default_dtype(torch.float64)
+    try:
+        extras = []
+        for l in range(L):
+            pm, bn = flow.transforms[3 * l + 1], flow.transforms[3 * l + 2]
+            extras.append([ps.Permute(pm.permutation.cpu()),
+                           ps.BatchNormEval(bn.gamma.detach().double().cpu(), bn.beta.detach().double().cpu(),
+                                            bn.moving_mean.double().cpu(), bn.moving_variance.double().cpu(), bn.epsilon)])
+        ref = ps.PyroStyleFlow(flow_type, None, D, C, hidden, L, K, "quadratic", permutations=flow.perms().numpy(), extras=extras)
+        ref.set_from_pytree([[(W.double().cpu().numpy(), b.double().cpu().numpy()) for (W, b) in layer] for layer in flow.current_draw()])
+        x64 = x.detach().cpu().double().requires_grad_(True)
+        (-ref.log_prob(x64, y.cpu().double()).mean()).backward()
+    finally:
+        torch.set_default_dtype(torch.float32)
+    for arn, rarn in zip(flow.nets, ref.nets):
+        for lin, rlin in zip(arn.layers, rarn.layers):
+            assert _rel(lin.weight.grad.cpu().double().numpy(), rlin.weight.grad.numpy()) < 5e-4
+            assert _rel(lin.bias.grad.cpu().double().numpy(), rlin.bias.grad.numpy()) < 5e-4
+    assert _rel(x.grad.cpu().double().numpy(), x64.grad.numpy()) < 5e-4
+    flow.train()
+    with pytest.raises(RuntimeError):
+        flow.log_prob(x, condition=y)
