@@ -96,6 +96,93 @@ def export_case(name, D, C, hidden, L, K, order, N, seed=0):
     return out
 
 
+# ---- optional layers of the factories (Permute, BatchNorm in eval mode: transforms.py:155-158) and the coupling flow (:201-236) ----
+EXTRA_CASES = [
+    # name, kind, D, C, hidden, L, K, order, split_dim, N
+    ("pyro_extra_maf_perm_bn_3d", "maf", 3, 2, [32, 32], 3, 8, "quadratic", 0, 200),
+    ("pyro_extra_nsa_perm_bn_4d", "nsa", 4, 2, [48, 48], 3, 8, "quadratic", 0, 200),
+    ("pyro_extra_nsc_uncond_5d", "nsc", 5, 0, [48, 48], 3, 8, "quadratic", 2, 200),
+    ("pyro_extra_nsc_cond_5d_linear", "nsc", 5, 2, [48, 48], 3, 8, "linear", 2, 200),
+]
+
+
+def export_extra_case(name, kind, D, C, hidden, L, K, order, split, N, seed=0):
+    """Flows with T.Permute + T.BatchNorm (eval mode, perturbed statistics) behind every autoregressive layer, and coupling flows
+    (T.SplineCoupling over a (Conditional)DenseNN, the hyper-network conditioned the way transforms.py:113-129 does it), evaluated
+    by real pyro.  tests/test_oracle_cpu.py::test_restatement_matches_pyro_extras rebuilds them from oracle/pyro_style.py."""
+    from functools import partial
+    import torch
+    import torch.nn as nn
+    import pyro.distributions as dist
+    import pyro.distributions.transforms as T
+    from pyro.nn import AutoRegressiveNN, ConditionalAutoRegressiveNN, ConditionalDenseNN, DenseNN
+    torch.manual_seed(seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn((N, D), generator=g) * 1.2
+    ctx = torch.rand((N, C), generator=g) if C > 0 else None
+    zin = torch.randn((N, D), generator=g)
+    out = {"kind": kind, "D": D, "C": C, "L": L, "K": K, "hidden": np.asarray(hidden), "order": order, "split": split,
+           "x": x.numpy(), "zin": zin.numpy()}
+    if C > 0:
+        out["ctx"] = ctx.numpy()
+    transforms = []
+    for l in range(L):
+        if kind == "nsc":
+            n = D - split
+            pd = [n * K, n * K, n * (K - 1)] + ([n * K] if order == "linear" else [])
+            net = ConditionalDenseNN(split, C, hidden, param_dims=pd, nonlinearity=nn.Tanh()) if C > 0 else \
+                DenseNN(split, hidden, param_dims=pd, nonlinearity=nn.Tanh())
+            with torch.no_grad():
+                for lin in net.layers:
+                    lin.weight.mul_(2.0)
+            hyper = partial(net, context=ctx) if C > 0 else net
+            tr = T.SplineCoupling(D, split, hyper, count_bins=K, order=order)
+            for j, lin in enumerate(net.layers):
+                out[f"W_{l}_{j}"] = lin.weight.detach().numpy()
+                out[f"b_{l}_{j}"] = lin.bias.detach().numpy()
+            low = tr.lower_spline
+            names = ["unnormalized_widths", "unnormalized_heights", "unnormalized_derivatives"] + (["unnormalized_lambdas"] if order == "linear" else [])
+            for gi, nm in enumerate(names):
+                out[f"low_{l}_{gi}"] = getattr(low, nm).detach().numpy()
+            transforms.append(tr)
+        else:
+            pdm = [1, 1] if kind == "maf" else [K, K, K - 1]
+            arn = ConditionalAutoRegressiveNN(D, C, hidden, nonlinearity=nn.Tanh(), param_dims=pdm)
+            with torch.no_grad():
+                for lin in arn.layers:
+                    lin.weight.mul_(2.0)
+            tr = (T.ConditionalAffineAutoregressive(arn) if kind == "maf" else
+                  T.ConditionalSplineAutoregressive(D, arn, count_bins=K, order=order)).condition(ctx)
+            out[f"perm_arn_{l}"] = arn.permutation.numpy()
+            for j, lin in enumerate(arn.layers):
+                out[f"W_{l}_{j}"] = lin.weight.detach().numpy()
+                out[f"b_{l}_{j}"] = lin.bias.detach().numpy()
+            transforms.append(tr)
+        perm = torch.randperm(D, generator=g)
+        transforms.append(T.Permute(perm))
+        out[f"perm_{l}"] = perm.numpy()
+        if kind != "nsc":
+            bn = T.BatchNorm(D)
+            with torch.no_grad():
+                bn.gamma.copy_(0.5 + torch.rand(D, generator=g)); bn.beta.copy_(0.3 * torch.randn(D, generator=g))
+                bn.moving_mean.copy_(0.2 * torch.randn(D, generator=g)); bn.moving_variance.copy_(0.5 + torch.rand(D, generator=g))
+            bn.eval()
+            for nm in ("gamma", "beta", "moving_mean", "moving_variance"):
+                out[f"bn_{l}_{nm}"] = getattr(bn, nm).detach().numpy()
+            out[f"bn_{l}_eps"] = float(bn.epsilon)
+            transforms.append(bn)
+    with torch.no_grad():
+        fd = dist.TransformedDistribution(dist.Normal(torch.zeros(D), torch.ones(D)), transforms)
+        out["lp"] = fd.log_prob(x).numpy().astype(np.float64)
+        y = zin
+        for tr in transforms:
+            y = tr(y)
+        out["ys"] = y.numpy().astype(np.float64)
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    return out
+
+
 def main():
     try:
         import pyro  # noqa: F401
@@ -104,6 +191,9 @@ def main():
         return 2
     for c in CASES:
         o = export_case(*c)
+        print(f"wrote {c[0]}.npz  lp[:3] = {o['lp'][:3]}")
+    for c in EXTRA_CASES:
+        o = export_extra_case(*c)
         print(f"wrote {c[0]}.npz  lp[:3] = {o['lp'][:3]}")
     return 0
 
